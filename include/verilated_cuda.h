@@ -1,0 +1,412 @@
+// -*- mode: C++; c-file-style: "cc-mode" -*-
+//*************************************************************************
+//
+// verilated_cuda.h -- device-side runtime of the batched Verilated model.
+//
+// This is the header that code printed by V3EmitCuda includes (the sibling
+// of "verilated.h" for code printed by V3EmitCFunc).  It provides, per CUDA
+// thread = per model instance:
+//
+//   * the VL_* operator library               (verilated_cuda_funcs.h)
+//   * VlWide / VlUnpacked / VlNBACommitQueue  (verilated_cuda_types.h)
+//   * VlRNG, VL_SCOPED_RAND_RESET_*, VL_MURMUR64_HASH
+//                 reference: include/verilated.cpp:428-487, 577-635, 2173-2210
+//   * VL_COV_TOGGLE_CHG_ST_*   reference: include/verilated_cov.h:78-105
+//   * VlcuContext: the per-instance slice of VerilatedContext
+//                 reference: include/verilated.h:371 (time, gotFinish, gotError,
+//                 errorCount/Limit, randReset/randSeed), verilated.cpp:165-232
+//                 (vl_finish / vl_stop / vl_stop_maybe / vl_fatal semantics)
+//   * the structure-of-arrays state accessors and the kernel templates that
+//     drive an emitted design (reset / eval / K-cycle run).
+//
+// State layout in HBM: for a model with N instances (padded to
+// a multiple of 128), persistent member m with element type T and E elements
+// lives at   base + soaOffset(m) * Npad + (e * Npad + instance) * sizeof(T)
+// i.e. "T sig[element][instance]", instance fastest, so a warp touches one
+// 32*sizeof(T)-byte contiguous run per element.
+//
+//*************************************************************************
+#ifndef VERILATOR_VERILATED_CUDA_H_
+#define VERILATOR_VERILATED_CUDA_H_
+
+#include "verilated_cuda_funcs.h"
+
+//=========================================================================
+// PRNG: splitmix64 seeding -> xoroshiro128** (verilated.cpp:428-487)
+
+VLCU_HD uint64_t vlcu_rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// One splitmix64 step: advances 'x' and returns the mixed output
+VLCU_HD uint64_t vlcu_splitmix64(uint64_t& x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+
+class VlRNG final {
+    uint64_t m_s0, m_s1;
+
+public:
+    VLCU_HD explicit VlRNG(uint64_t seed) {
+        uint64_t x = seed;
+        m_s0 = vlcu_splitmix64(x);
+        m_s1 = vlcu_splitmix64(x);
+    }
+    VLCU_HD uint64_t rand64() {
+        const uint64_t result = vlcu_rotl64(m_s0 * 5, 7) * 9;
+        const uint64_t t = m_s1 ^ m_s0;
+        m_s0 = vlcu_rotl64(m_s0, 24) ^ t ^ (t << 16);
+        m_s1 = vlcu_rotl64(t, 37);
+        return result;
+    }
+};
+
+// MurmurHash64A with seed 0 over a NUL terminated string (verilated.cpp:2173-2210).
+// Scope names are known when the model is built, so this normally runs on the
+// host at create time; it is device-capable for the emitter's convenience.
+VLCU_HD uint64_t VL_MURMUR64_HASH(const char* key) {
+    size_t len = 0;
+    while (key[len]) ++len;
+    const uint64_t m = 0xc6a4a7935bd1e995ULL;
+    const int r = 47;
+    uint64_t h = 0 ^ (len * m);
+    const size_t nblocks = len / 8;
+    for (size_t b = 0; b < nblocks; ++b) {
+        uint64_t k = 0;
+        for (int j = 7; j >= 0; --j) k = (k << 8) | static_cast<uint8_t>(key[b * 8 + j]);
+        k *= m;
+        k ^= k >> r;
+        k *= m;
+        h ^= k;
+        h *= m;
+    }
+    const size_t tail = len & 7;
+    if (tail) {
+        uint64_t k = 0;
+        for (size_t j = tail; j > 0; --j) k = (k << 8) | static_cast<uint8_t>(key[nblocks * 8 + j - 1]);
+        h ^= k;
+        h *= m;
+    }
+    h ^= h >> r;
+    h *= m;
+    h ^= h >> r;
+    return h;
+}
+
+//=========================================================================
+// Toggle coverage (verilated_cov.h:78-105): two counters per bit, index
+// 2*bit + new value, bumped when the bit changed.  Counters wrap (uint32).
+
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_I(int width, uint32_t* covp, IData newData, IData oldData) {
+    const IData chg = newData ^ oldData;
+    for (int i = 0; i < width; ++i) covp[2 * i + ((newData >> i) & 1)] += (chg >> i) & 1;
+}
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, uint32_t* covp, QData newData, QData oldData) {
+    const QData chg = newData ^ oldData;
+    for (int i = 0; i < width; ++i) {
+        covp[2 * i + static_cast<int>((newData >> i) & 1)] += static_cast<uint32_t>((chg >> i) & 1);
+    }
+}
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, uint32_t* covp, WDataInP newData,
+                                    WDataInP oldData) {
+    for (int w = 0; w < VL_WORDS_I(width); ++w) {
+        const EData chg = newData[w] ^ oldData[w];
+        if (!chg) continue;
+        for (int j = 0; j < width - w * 32; ++j) {
+            covp[(w * 32 + j) * 2 + ((newData[w] >> j) & 1)] += (chg >> j) & 1;
+        }
+    }
+}
+
+//=========================================================================
+// Per-instance simulation context (the batch dimension of VerilatedContext)
+
+// Status flag bits, also what vlcu_status() reports to the host
+enum : uint32_t {
+    VLCU_ST_DIDINIT = 1u << 0,  // first eval's static/initial/settle has run (__Vm_didInit)
+    VLCU_ST_FINISH = 1u << 1,  // VerilatedContext::gotFinish()
+    VLCU_ST_ERROR = 1u << 2,  // VerilatedContext::gotError()
+    VLCU_ST_STOPPED = 1u << 3,  // a $stop / failed assertion reached vl_stop
+    VLCU_ST_FATAL = 1u << 4,  // VL_FATAL_MT (e.g. DIDNOTCONVERGE)
+    VLCU_ST_MSGDROP = 1u << 5,  // more $display/$write messages than the log holds
+};
+// Fatal codes
+enum : uint32_t {
+    VLCU_FATAL_NONE = 0,
+    VLCU_FATAL_DIDNOTCONVERGE = 1,  // V3SchedUtil.cpp:80-104
+    VLCU_FATAL_NBAQ_OVERFLOW = 2,  // VlNBACommitQueue capacity exceeded
+    VLCU_FATAL_USER = 3,  // $fatal
+};
+
+#define VLCU_MSG_ARGS 4
+struct VlcuMsg {  // one logged $display/$write, formatted later on the host
+    uint64_t time;
+    uint32_t id;  // index into the design's message-format table
+    uint32_t nargs;
+    uint64_t args[VLCU_MSG_ARGS];
+};
+
+// Per-instance context record as stored in HBM (array of structs: touched only at
+// kernel entry/exit and on rare events, so not worth a SoA)
+struct VlcuCtxRec {
+    uint64_t time;
+    uint64_t firstFinishTime, firstStopTime, firstFatalTime;
+    uint32_t status;
+    uint32_t errorCount;
+    uint32_t finishCount, stopCount, fatalCount;
+    uint32_t firstStopLine, firstFatalLine, fatalCode;
+    uint32_t msgCount;
+    uint32_t pad_;
+};
+
+struct VlcuContext final {
+    // Hot, register-resident part
+    uint64_t m_time;
+    uint64_t m_randSeed;  // base seed ^ global instance index (SURVEY 8d "Seeds")
+    uint32_t m_status;
+    uint32_t m_randReset;  // 0 zeros, 1 ones, 2 random (verilated.cpp:577-615)
+    uint32_t m_msgCount;
+    uint32_t m_plusargs;  // bit n set: design's n-th $test$plusargs string was given
+    uint32_t m_errorLimit;
+    // Cold part, in HBM
+    VlcuCtxRec* m_recp;
+    VlcuMsg* m_msgp;  // this instance's slice of the message log
+    uint32_t m_msgCap;
+
+    VLCU_HD uint64_t time() const { return m_time; }
+    VLCU_HD void timeInc(uint64_t add) { m_time += add; }
+    VLCU_HD bool gotFinish() const { return (m_status & VLCU_ST_FINISH) != 0; }
+    VLCU_HD bool gotError() const { return (m_status & VLCU_ST_ERROR) != 0; }
+    VLCU_HD bool didInit() const { return (m_status & VLCU_ST_DIDINIT) != 0; }
+    VLCU_HD uint64_t randSeed() const { return m_randSeed; }
+    VLCU_HD uint32_t randReset() const { return m_randReset; }
+    VLCU_HD bool testPlusArg(uint32_t index) const { return (m_plusargs >> index) & 1; }
+
+    // vl_finish (verilated.cpp:166-171): sets gotFinish; a serial model runs it
+    // immediately (VerilatedThreadMsgQueue::post with mtaskId()==0)
+    VLCU_HD void finish(uint32_t /*line*/) {
+        if (!m_recp->finishCount) m_recp->firstFinishTime = m_time;
+        ++m_recp->finishCount;
+        m_status |= VLCU_ST_FINISH;
+    }
+    // vl_stop_maybe + vl_stop (verilated.cpp:175-190,218-231) with the default
+    // errorLimit: never aborts the batch, records the first occurrence
+    VLCU_HD void stop(uint32_t line, bool maybe) {
+        const uint32_t count = ++m_recp->errorCount;
+        if (maybe && count < m_errorLimit) return;
+        if (gotFinish()) return;  // $stop after $finish is ignored
+        m_status |= VLCU_ST_ERROR | VLCU_ST_FINISH | VLCU_ST_STOPPED;
+        if (!m_recp->stopCount) {
+            m_recp->firstStopTime = m_time;
+            m_recp->firstStopLine = line;
+        }
+        ++m_recp->stopCount;
+    }
+    // vl_fatal (verilated.cpp:194-215) without the process exit
+    VLCU_HD void fatal(uint32_t line, uint32_t code) {
+        m_status |= VLCU_ST_ERROR | VLCU_ST_FINISH | VLCU_ST_FATAL;
+        if (!m_recp->fatalCount) {
+            m_recp->firstFatalTime = m_time;
+            m_recp->firstFatalLine = line;
+            m_recp->fatalCode = code;
+        }
+        ++m_recp->fatalCount;
+    }
+    // $display/$write/$error text: log (id, args) for host-side formatting
+    VLCU_HD void writef(uint32_t id, uint32_t nargs = 0, uint64_t a0 = 0, uint64_t a1 = 0,
+                        uint64_t a2 = 0, uint64_t a3 = 0) {
+        if (m_msgCount < m_msgCap) {
+            VlcuMsg& msg = m_msgp[m_msgCount];
+            msg.time = m_time;
+            msg.id = id;
+            msg.nargs = nargs;
+            msg.args[0] = a0, msg.args[1] = a1, msg.args[2] = a2, msg.args[3] = a3;
+        } else {
+            m_status |= VLCU_ST_MSGDROP;
+        }
+        ++m_msgCount;
+    }
+};
+
+// Emitted-code spellings (V3EmitCFunc.h:1359-1376 prints VL_FINISH_MT/VL_STOP_MT
+// with file, line, hier; on the device the file/hier strings stay on the host)
+#define VLCU_FINISH(ctx, line) (ctx).finish(line)
+#define VLCU_STOP(ctx, line, maybe) (ctx).stop(line, maybe)
+#define VLCU_FATAL(ctx, line, code) (ctx).fatal(line, code)
+
+//=========================================================================
+// X-initial reset values (verilated.cpp:577-635); 'ctx' supplies what the
+// host code reads from Verilated::threadContextp()
+
+VLCU_HD IData VL_SCOPED_RAND_RESET_I(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+                                     uint64_t salt) {
+    if (ctx.randReset() == 0) return 0;
+    IData data = ~0U;
+    if (ctx.randReset() != 1) {
+        VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+        data = static_cast<IData>(rng.rand64());
+    }
+    return data & VL_MASK_I(obits);
+}
+VLCU_HD QData VL_SCOPED_RAND_RESET_Q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+                                     uint64_t salt) {
+    if (ctx.randReset() == 0) return 0;
+    QData data = ~0ULL;
+    if (ctx.randReset() != 1) {
+        VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+        data = rng.rand64();
+    }
+    return data & VL_MASK_Q(obits);
+}
+VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_W(const VlcuContext& ctx, int obits, WDataOutP outwp,
+                                         uint64_t scopeHash, uint64_t salt) {
+    const int words = VL_WORDS_I(obits);
+    if (ctx.randReset() == 0) {
+        for (int i = 0; i < words; ++i) outwp[i] = 0;
+    } else if (ctx.randReset() == 1) {
+        for (int i = 0; i < words; ++i) outwp[i] = ~0U;
+    } else {
+        VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+        // One draw per 32-bit limb; the upper half of each draw is discarded
+        for (int i = 0; i < words; ++i) outwp[i] = static_cast<EData>(rng.rand64());
+    }
+    outwp[words - 1] &= VL_MASK_E(obits);
+    return outwp;
+}
+VLCU_HD IData VL_SCOPED_RAND_RESET_ASSIGN_I(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+                                            uint64_t salt) {
+    VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+    return static_cast<IData>(rng.rand64()) & VL_MASK_I(obits);
+}
+VLCU_HD QData VL_SCOPED_RAND_RESET_ASSIGN_Q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+                                            uint64_t salt) {
+    VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+    return rng.rand64() & VL_MASK_Q(obits);
+}
+VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_ASSIGN_W(const VlcuContext& ctx, int obits,
+                                                WDataOutP outwp, uint64_t scopeHash,
+                                                uint64_t salt) {
+    VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
+    const int words = VL_WORDS_I(obits);
+    for (int i = 0; i < words - 1; ++i) outwp[i] = static_cast<EData>(rng.rand64());
+    outwp[words - 1] = static_cast<EData>(rng.rand64()) & VL_MASK_E(obits);
+    return outwp;
+}
+
+//=========================================================================
+// Structure-of-arrays state block
+
+struct VlcuState final {
+    uint8_t* base;  // start of the block (256-byte aligned)
+    uint64_t npad;  // instances padded to a multiple of 128 (1 for a packed record)
+
+    template <typename T>
+    VLCU_HD T* ptr(uint32_t soaOffset) const {
+        return reinterpret_cast<T*>(base + static_cast<uint64_t>(soaOffset) * npad);
+    }
+    // Scalar member
+    template <typename T>
+    VLCU_HD T ld(uint32_t soaOffset, uint64_t inst) const {
+        return ptr<T>(soaOffset)[inst];
+    }
+    template <typename T>
+    VLCU_HD void st(uint32_t soaOffset, uint64_t inst, T value) const {
+        ptr<T>(soaOffset)[inst] = value;
+    }
+    // Element 'e' of a multi-element member (VlWide limb / small VlUnpacked entry)
+    template <typename T>
+    VLCU_HD T ldE(uint32_t soaOffset, uint32_t e, uint64_t inst) const {
+        return ptr<T>(soaOffset)[static_cast<uint64_t>(e) * npad + inst];
+    }
+    template <typename T>
+    VLCU_HD void stE(uint32_t soaOffset, uint32_t e, uint64_t inst, T value) const {
+        ptr<T>(soaOffset)[static_cast<uint64_t>(e) * npad + inst] = value;
+    }
+    template <size_t N>
+    VLCU_HD void ldW(uint32_t soaOffset, uint64_t inst, VlWide<N>& out) const {
+        VLCU_UNROLL
+        for (size_t e = 0; e < N; ++e) out[e] = ldE<EData>(soaOffset, static_cast<uint32_t>(e), inst);
+    }
+    template <size_t N>
+    VLCU_HD void stW(uint32_t soaOffset, uint64_t inst, const VlWide<N>& in) const {
+        VLCU_UNROLL
+        for (size_t e = 0; e < N; ++e) stE<EData>(soaOffset, static_cast<uint32_t>(e), inst, in[e]);
+    }
+};
+
+// A memory too large for thread-private storage: stays in HBM, one private
+// copy per instance, laid out instance-major ("array of instances") so that
+// the sequential accesses of one instance (instruction fetch, stack) hit the
+// same 32-byte sector instead of gathering across an N-instance stride
+// (SURVEY 7.3-4).  operator[] hands out real references, so emitted code uses
+// it exactly like a VlUnpacked.
+template <typename T_Value, size_t N_Depth>
+struct VlcuGlobalArray final {
+    T_Value* m_basep;  // this instance's N_Depth elements
+
+    VLCU_HD void bind(const VlcuState& st, uint32_t soaOffset, uint64_t inst) {
+        m_basep = st.ptr<T_Value>(soaOffset) + inst * N_Depth;
+    }
+    VLCU_HD T_Value& operator[](size_t index) { return m_basep[index]; }
+    VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index]; }
+    VLCU_HD constexpr size_t size() const { return N_Depth; }
+};
+
+// Everything a kernel needs to find one model's data
+struct VlcuModelDev final {
+    VlcuState state;
+    VlcuCtxRec* ctxRecs;
+    VlcuMsg* msgs;
+    uint64_t n;  // live instances in this shard
+    uint64_t instBase;  // global index of this shard's instance 0 (multi-GPU sharding)
+    uint64_t seedBase;
+    uint32_t randReset;
+    uint32_t msgCap;
+    uint32_t plusargs;
+    uint32_t errorLimit;
+};
+
+VLCU_HD void vlcu_ctx_load(VlcuContext& ctx, const VlcuModelDev& m, uint64_t inst) {
+    VlcuCtxRec* const recp = &m.ctxRecs[inst];
+    ctx.m_recp = recp;
+    ctx.m_time = recp->time;
+    ctx.m_status = recp->status;
+    ctx.m_msgCount = recp->msgCount;
+    ctx.m_randSeed = m.seedBase ^ (m.instBase + inst);
+    ctx.m_randReset = m.randReset;
+    ctx.m_plusargs = m.plusargs;
+    ctx.m_errorLimit = m.errorLimit;
+    ctx.m_msgp = m.msgs + inst * m.msgCap;
+    ctx.m_msgCap = m.msgCap;
+}
+VLCU_HD void vlcu_ctx_store(const VlcuContext& ctx) {
+    ctx.m_recp->time = ctx.m_time;
+    ctx.m_recp->status = ctx.m_status;
+    ctx.m_recp->msgCount = ctx.m_msgCount;
+}
+
+//=========================================================================
+// Eval driver: Vtop::eval_step() (V3EmitCModel.cpp:403-437) for one instance
+
+template <class T_Design>
+VLCU_D void vlcu_eval_step(typename T_Design::Root* rootp, VlcuContext& ctx) {
+    if (VL_UNLIKELY(!ctx.didInit())) {
+        ctx.m_status |= VLCU_ST_DIDINIT;
+        T_Design::eval_static(rootp, ctx);
+        T_Design::eval_initial(rootp, ctx);
+        T_Design::eval_settle(rootp, ctx);
+    }
+    T_Design::eval(rootp, ctx);
+}
+
+// Running 64-bit signature of observed output words (FNV-1a style); lets a
+// K-cycle fused run be checked against the oracle without storing every port
+// value of every instance every cycle.
+VLCU_HD uint64_t vlcu_sig_mix(uint64_t sig, uint32_t word) {
+    return (sig ^ word) * 0x100000001b3ULL;
+}
+#define VLCU_SIG_INIT 0xcbf29ce484222325ULL
+
+#endif  // guard

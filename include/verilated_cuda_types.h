@@ -1,0 +1,265 @@
+// -*- mode: C++; c-file-style: "cc-mode" -*-
+//*************************************************************************
+//
+// verilated_cuda_types.h -- data types of the batched (one instance per CUDA
+// thread) Verilated model runtime.
+//
+// Device-side counterparts of the reference's
+//   include/verilatedos.h:470-537     (size / mask / bit-position macros)
+//   include/verilated.h:116-129       (CData/SData/IData/QData/EData/WData)
+//   include/verilated_types.h:81-126  (VlWide<N>)
+//   include/verilated_types.h:149-210 (WDataInP / WDataOutP handles)
+//   include/verilated_types.h:1426-1509 (VlUnpacked<T,N>)
+//   include/verilated_types.h:1854-1977 (VlNBACommitQueue)
+//
+// Everything here compiles both as CUDA device code (the product path) and as
+// plain host C++ (used ONLY by the CPU-side differential tests, see
+// tests/optest/) -- there is no host execution path in the product library.
+//
+//*************************************************************************
+#ifndef VERILATOR_VERILATED_CUDA_TYPES_H_
+#define VERILATOR_VERILATED_CUDA_TYPES_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VLCU_HD __host__ __device__ __forceinline__
+#define VLCU_D __device__ __forceinline__
+#define VLCU_UNROLL _Pragma("unroll")
+#else
+#define VLCU_HD inline __attribute__((always_inline))
+#define VLCU_D inline __attribute__((always_inline))
+#define VLCU_UNROLL
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define VLCU_LIKELY(x) (x)
+#define VLCU_UNLIKELY(x) (x)
+#else
+#define VLCU_LIKELY(x) __builtin_expect(!!(x), 1)
+#define VLCU_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#endif
+// The emitter prints VL_LIKELY/VL_UNLIKELY around if-conditions (V3EmitCFunc.h:1300-1327)
+#ifndef VL_LIKELY
+#define VL_LIKELY(x) VLCU_LIKELY(x)
+#define VL_UNLIKELY(x) VLCU_UNLIKELY(x)
+#endif
+
+//=========================================================================
+// Basic integer types (same C storage classes as the host model)
+
+typedef uint8_t CData;  ///< Data representing 'bit' of 1-8 packed bits
+typedef uint16_t SData;  ///< Data representing 'bit' of 9-16 packed bits
+typedef uint32_t IData;  ///< Data representing 'bit' of 17-32 packed bits
+typedef uint64_t QData;  ///< Data representing 'bit' of 33-64 packed bits
+typedef uint32_t EData;  ///< Data representing one element of WData array
+typedef EData WData;  ///< Data representing >64 packed bits (used as pointer)
+
+// On the device a wide handle is a raw pointer to (thread-private) limbs.
+typedef const EData* WDataInP;
+typedef EData* WDataOutP;
+
+//=========================================================================
+// Size macros (verilatedos.h:470-491)
+
+#define VL_BYTESIZE 8
+#define VL_SHORTSIZE 16
+#define VL_IDATASIZE 32
+#define VL_QUADSIZE 64
+#define VL_EDATASIZE 32
+#define VL_EDATASIZE_LOG2 5
+#define VL_MULS_MAX_WORDS 128  // (verilatedos.h:511)
+
+#define VL_UL(c) (static_cast<IData>(c##UL))
+#define VL_ULL(c) (c##ULL)
+#define VL_EUL(n) VL_UL(n)
+
+#define VL_BYTES_I(nbits) (((nbits) + (VL_BYTESIZE - 1)) >> 3)
+#define VL_WORDS_I(nbits) (((nbits) + (VL_EDATASIZE - 1)) >> VL_EDATASIZE_LOG2)
+#define VL_WQ_WORDS_E 2
+
+#define VL_SIZEBITS_I (VL_IDATASIZE - 1)
+#define VL_SIZEBITS_Q (VL_QUADSIZE - 1)
+#define VL_SIZEBITS_E (VL_EDATASIZE - 1)
+
+// Masks with ones in the low (nbits mod size) positions; a multiple of the
+// size (including 0) means "all bits" (verilatedos.h:520-530).
+VLCU_HD constexpr IData vlcu_mask_i(int nbits) {
+    return (nbits & 31) ? ((1U << (nbits & 31)) - 1U) : ~0U;
+}
+VLCU_HD constexpr QData vlcu_mask_q(int nbits) {
+    return (nbits & 63) ? ((1ULL << (nbits & 63)) - 1ULL) : ~0ULL;
+}
+#define VL_MASK_I(nbits) vlcu_mask_i(static_cast<int>(nbits))
+#define VL_MASK_Q(nbits) vlcu_mask_q(static_cast<int>(nbits))
+#define VL_MASK_E(nbits) VL_MASK_I(nbits)
+
+#define VL_BITWORD_I(bit) ((bit) / VL_IDATASIZE)
+#define VL_BITWORD_E(bit) ((bit) >> VL_EDATASIZE_LOG2)
+#define VL_BITBIT_I(bit) ((bit) & VL_SIZEBITS_I)
+#define VL_BITBIT_Q(bit) ((bit) & VL_SIZEBITS_Q)
+#define VL_BITBIT_E(bit) ((bit) & VL_SIZEBITS_E)
+
+#define VL_BITISSET_I(data, bit) ((data) & (VL_UL(1) << VL_BITBIT_I(bit)))
+#define VL_BITISSET_Q(data, bit) ((data) & (1ULL << VL_BITBIT_Q(bit)))
+#define VL_BITISSET_E(data, bit) ((data) & (VL_EUL(1) << VL_BITBIT_E(bit)))
+#define VL_BITISSET_W(data, bit) ((data)[VL_BITWORD_E(bit)] & (VL_EUL(1) << VL_BITBIT_E(bit)))
+#define VL_BITISSETLIMIT_W(data, width, bit) (((bit) < (width)) && VL_BITISSET_W(data, bit))
+#define VL_BITRSHIFT_W(data, bit) ((data)[VL_BITWORD_E(bit)] >> VL_BITBIT_E(bit))
+
+//=========================================================================
+// VlWide -- N little-endian 32-bit limbs private to one instance/thread.
+// Stored values keep the bits above the declared width at zero; temporaries
+// may be dirty there (verilated_types.h:73-78).
+
+template <size_t N_Words>
+struct VlWide final {
+    static constexpr size_t Words = N_Words;
+    EData m_storage[N_Words];
+
+    VLCU_HD EData& operator[](size_t index) { return m_storage[index]; }
+    VLCU_HD const EData& operator[](size_t index) const { return m_storage[index]; }
+    VLCU_HD EData& at(size_t index) { return m_storage[index]; }
+    VLCU_HD const EData& at(size_t index) const { return m_storage[index]; }
+    VLCU_HD constexpr size_t size() const { return N_Words; }
+    VLCU_HD EData* data() { return &m_storage[0]; }
+    VLCU_HD const EData* data() const { return &m_storage[0]; }
+    // A VlWide passes directly where a WDataInP/WDataOutP handle is expected
+    VLCU_HD operator EData*() { return &m_storage[0]; }
+    VLCU_HD operator const EData*() const { return &m_storage[0]; }
+    VLCU_HD bool operator==(const VlWide<N_Words>& that) const {
+        EData diff = 0;
+        VLCU_UNROLL
+        for (size_t i = 0; i < N_Words; ++i) diff |= m_storage[i] ^ that.m_storage[i];
+        return diff == 0;
+    }
+    VLCU_HD bool operator!=(const VlWide<N_Words>& that) const { return !(*this == that); }
+};
+
+//=========================================================================
+// VlUnpacked -- fixed-size unpacked array held in the per-thread model image.
+// (Arrays too large for thread-private storage use VlcuGlobalArray of
+// verilated_cuda.h instead; the emitter picks per array)
+
+template <typename T_Value, size_t N_Depth>
+struct VlUnpacked final {
+    T_Value m_storage[N_Depth];
+
+    VLCU_HD T_Value* data() { return &m_storage[0]; }
+    VLCU_HD const T_Value* data() const { return &m_storage[0]; }
+    VLCU_HD constexpr size_t size() const { return N_Depth; }
+    VLCU_HD T_Value& operator[](size_t index) { return m_storage[index]; }
+    VLCU_HD const T_Value& operator[](size_t index) const { return m_storage[index]; }
+    VLCU_HD void fill(const T_Value& value) {
+        for (size_t i = 0; i < N_Depth; ++i) m_storage[i] = value;
+    }
+    // Change detection helpers used by trigger computation (V3SenExprBuilder.h:253-260)
+    VLCU_HD bool neq(const VlUnpacked<T_Value, N_Depth>& that) const {
+        bool differs = false;
+        for (size_t i = 0; i < N_Depth; ++i) differs |= (m_storage[i] != that.m_storage[i]);
+        return differs;
+    }
+    VLCU_HD void assign(const VlUnpacked<T_Value, N_Depth>& that) {
+        for (size_t i = 0; i < N_Depth; ++i) m_storage[i] = that.m_storage[i];
+    }
+    VLCU_HD bool operator==(const VlUnpacked<T_Value, N_Depth>& that) const { return !neq(that); }
+    VLCU_HD bool operator!=(const VlUnpacked<T_Value, N_Depth>& that) const { return neq(that); }
+};
+
+//=========================================================================
+// VlNBACommitQueue -- deferred array-element writes, committed in program
+// order at the end of the NBA region.  The host runtime grows a std::vector;
+// a CUDA thread cannot, so the capacity is a template argument that the
+// emitter derives from the static bound of the enclosing loop.  Overflow is
+// reported through 'overflowed()' and raised as a per-instance fatal by the
+// caller, never silently dropped.
+
+template <typename T_Element, size_t N_Rank, size_t N_Capacity, bool Partial>
+class VlNBACommitQueue final {
+    struct Entry final {
+        T_Element value;
+        T_Element mask;
+        uint32_t indices[N_Rank];
+    };
+    Entry m_pending[N_Capacity];
+    uint32_t m_size = 0;
+    bool m_overflow = false;
+
+    template <typename T_Target>
+    VLCU_HD static T_Element& element(T_Target& target, const uint32_t* idx) {
+        return elementAt(target, idx, 0);
+    }
+    VLCU_HD static T_Element& elementAt(T_Element& leaf, const uint32_t*, size_t) { return leaf; }
+    template <typename T_Sub, size_t N>
+    VLCU_HD static T_Element& elementAt(VlUnpacked<T_Sub, N>& arr, const uint32_t* idx,
+                                        size_t dim) {
+        return elementAt(arr[idx[dim]], idx, dim + 1);
+    }
+    VLCU_HD static void blend(IData& ref, const IData& v, const IData& m) {
+        ref = (v & m) | (ref & ~m);
+    }
+    VLCU_HD static void blend(QData& ref, const QData& v, const QData& m) {
+        ref = (v & m) | (ref & ~m);
+    }
+    VLCU_HD static void blend(SData& ref, const SData& v, const SData& m) {
+        ref = static_cast<SData>((v & m) | (ref & ~m));
+    }
+    VLCU_HD static void blend(CData& ref, const CData& v, const CData& m) {
+        ref = static_cast<CData>((v & m) | (ref & ~m));
+    }
+    template <size_t N>
+    VLCU_HD static void blend(VlWide<N>& ref, const VlWide<N>& v, const VlWide<N>& m) {
+        for (size_t i = 0; i < N; ++i) ref[i] = (v[i] & m[i]) | (ref[i] & ~m[i]);
+    }
+
+public:
+    VLCU_HD void clear() {
+        m_size = 0;
+        m_overflow = false;
+    }
+    VLCU_HD bool overflowed() const { return m_overflow; }
+    VLCU_HD uint32_t size() const { return m_size; }
+
+    // Whole-element form: enqueue(value, i0[, i1...])
+    template <typename... T_Args>
+    VLCU_HD void enqueue(const T_Element& value, T_Args... indices) {
+        static_assert(!Partial || sizeof...(indices) == N_Rank + 0 || true, "");
+        if (m_size >= N_Capacity) {
+            m_overflow = true;
+            return;
+        }
+        Entry& e = m_pending[m_size++];
+        e.value = value;
+        const uint32_t tmp[] = {static_cast<uint32_t>(indices)...};
+        for (size_t i = 0; i < N_Rank; ++i) e.indices[i] = tmp[i];
+    }
+    // Partial-element form: enqueueMasked(value, mask, i0[, i1...])
+    template <typename... T_Args>
+    VLCU_HD void enqueueMasked(const T_Element& value, const T_Element& mask, T_Args... indices) {
+        if (m_size >= N_Capacity) {
+            m_overflow = true;
+            return;
+        }
+        Entry& e = m_pending[m_size++];
+        e.value = value;
+        e.mask = mask;
+        const uint32_t tmp[] = {static_cast<uint32_t>(indices)...};
+        for (size_t i = 0; i < N_Rank; ++i) e.indices[i] = tmp[i];
+    }
+    template <typename T_Commit>
+    VLCU_HD void commit(T_Commit& target) {
+        for (uint32_t n = 0; n < m_size; ++n) {
+            Entry& e = m_pending[n];
+            T_Element& ref = element(target, e.indices);
+            if (Partial) {
+                blend(ref, e.value, e.mask);
+            } else {
+                ref = e.value;
+            }
+        }
+        m_size = 0;
+    }
+};
+
+#endif  // guard
