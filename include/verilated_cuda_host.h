@@ -1,0 +1,114 @@
+// -*- mode: C++; c-file-style: "cc-mode" -*-
+//*************************************************************************
+//
+// verilated_cuda_host.h -- host-side description of an emitted design and
+// the interface between emitted design code and the batch runtime
+// (verilated_cuda.cu).  This is the batched counterpart of what the
+// generated Vtop__Syms / Vtop.h give the host runtime: the list of ports
+// (V3EmitCModel.cpp:108-117), the member layout (V3EmitCHeaders.cpp:73-143),
+// the coverage-point registrations (V3EmitCImp.cpp:179-262) and the
+// $display format strings.
+//
+//*************************************************************************
+#ifndef VERILATOR_VERILATED_CUDA_HOST_H_
+#define VERILATOR_VERILATED_CUDA_HOST_H_
+
+#include "verilated_cuda.h"
+
+// Run flags (also used from the C ABI, include/verilated_cuda_abi.h)
+enum : uint32_t {
+    VLCU_RUN_TB_BEGIN = 1u << 0,  // call the testbench's begin() first (initial port values)
+    VLCU_RUN_STOP_ON_FINISH = 1u << 1,  // an instance stops evaluating once gotFinish() is set
+};
+#define VLCU_TRACE_HDR 16  // bytes before the state record in a trace sample: u64 time, u32 status, u32 valid
+
+// Per-launch parameters of the cycle-loop kernel
+struct VlcuRunDev final {
+    uint64_t nEvals;  // eval() calls to make (two per clock period)
+    uint64_t evalBase;  // index of the first eval (for resumed runs)
+    uint64_t npad;  // padded instance count (row stride of stim/obs)
+    uint32_t flags;
+    uint32_t stimBroadcast;  // stimulus rows hold one value for all instances
+    const uint32_t* stim;  // [eval][input word][instance] (VlcuTbTrace)
+    uint32_t* obs;  // [eval][output word][instance] or null
+    uint64_t obsEvals;
+    uint64_t* sigs;  // [instance] running output signature
+    uint64_t* evalsDone;  // [instance] evals executed (stop-on-finish accounting) or null
+    // Waveform sampling of a few instances
+    const uint64_t* sampleIds;  // local instance numbers
+    uint32_t nSamples;
+    uint8_t* trace;  // [eval][sample][VLCU_TRACE_HDR + stateBytes]
+    uint64_t traceEvals;
+    // Testbench parameters
+    uint64_t tbSeed;
+    uint32_t tbFlags;
+    uint32_t tbArg[4];
+    void* tbPtr[2];
+};
+
+enum VlcuMemberKind : uint8_t {
+    VLCU_MEMBER_IN = 0,  // primary input port
+    VLCU_MEMBER_OUT = 1,  // primary output port
+    VLCU_MEMBER_INOUT = 2,
+    VLCU_MEMBER_STATE = 3,  // internal persistent signal / trigger prev / NBA shadow
+    VLCU_MEMBER_COVERAGE = 4,  // uint32_t __Vcoverage[nBins]
+    VLCU_MEMBER_MEMORY = 5,  // VlcuGlobalArray: instance-major, not interleaved
+};
+
+struct VlcuMemberDesc final {
+    const char* name;  // C++ member name in Vtop___024root
+    const char* hierName;  // Verilog hierarchical name (for tracing), or nullptr
+    uint8_t kind;
+    uint8_t elemBytes;  // 1 CData, 2 SData, 4 IData/EData, 8 QData
+    uint16_t traceCode;  // first VCD code (0 = not traced)
+    uint32_t elems;  // words of a VlWide, depth of an array, else 1
+    uint32_t width;  // bits (of one array element)
+    int32_t msb, lsb;  // declared range
+    uint32_t soaOffset;  // byte offset per instance in the SoA block
+};
+
+struct VlcuCoverPoint final {  // arguments of __vlCoverInsert / __vlCoverToggleInsert
+    const char* filename;
+    int lineno;
+    int column;
+    const char* hier;  // relative to the model's name, e.g. ".top.sub"
+    const char* page;  // "v_line/sub", "v_toggle/top", "v_user/sub"
+    const char* comment;  // "block", "if", "else", "count_c[3]:0->1" ...
+    const char* linescov;
+};
+
+struct VlcuDesignInfo final {
+    const char* name;  // design name used with vlcu_create()
+    const char* topName;  // Verilog top module
+    const VlcuMemberDesc* members;
+    uint32_t nMembers;
+    uint32_t stateBytes;  // S_persist: bytes per instance in the SoA block
+    uint32_t inWords, outWords;  // 32-bit words per stimulus / observation row
+    uint32_t inBytes, outBytes;  // S_in / S_out in C storage bytes (SURVEY 8d B_alg)
+    const VlcuCoverPoint* coverPoints;
+    uint32_t nCoverPoints;
+    uint32_t coverageSoaOffset;  // of __Vcoverage, if nCoverPoints
+    const char* const* messages;  // $display/$write format strings by id
+    uint32_t nMessages;
+    const char* const* plusargs;  // $test$plusargs strings by index
+    uint32_t nPlusargs;
+};
+
+#if defined(__CUDACC__) || defined(VLCU_HOST_RUNTIME)
+#include <cuda_runtime.h>
+class VlcuDesignOps {
+public:
+    virtual ~VlcuDesignOps() {}
+    virtual const VlcuDesignInfo& info() const = 0;
+    virtual cudaError_t launchReset(const VlcuModelDev& m, cudaStream_t stream) const = 0;
+    virtual cudaError_t launchFinal(const VlcuModelDev& m, cudaStream_t stream) const = 0;
+    virtual cudaError_t launchRun(const char* tb, const VlcuModelDev& m, const VlcuRunDev& r,
+                                  cudaStream_t stream) const = 0;
+    virtual int tbCount() const = 0;
+    virtual const char* tbName(int i) const = 0;
+};
+// Implemented by the runtime; called from each design's static initialiser
+int vlcu_register_design(VlcuDesignOps* opsp);
+#endif
+
+#endif  // guard

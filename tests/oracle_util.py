@@ -1,0 +1,92 @@
+"""Bindings to the ORACLE (oracle/_ref/libvlref.so) -- TEST INFRASTRUCTURE.
+
+libvlref.so = the reference's own runtime (include/verilated*.cpp compiled from
+/root/reference) + the restated reference models under oracle/models/.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_PATH = os.path.join(ROOT, "oracle", "_ref", "libvlref.so")
+
+u64, u32, i32, i64, vp, cp = (ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int64,
+                              ctypes.c_void_p, ctypes.c_char_p)
+
+STATUS_DTYPE = np.dtype([
+    ("time", "<u8"), ("first_finish_time", "<u8"), ("first_stop_time", "<u8"),
+    ("first_fatal_time", "<u8"), ("status", "<u4"), ("error_count", "<u4"),
+    ("finish_count", "<u4"), ("stop_count", "<u4"), ("fatal_count", "<u4"),
+    ("first_stop_line", "<u4"), ("first_fatal_line", "<u4"), ("fatal_code", "<u4"),
+    ("msg_count", "<u4"), ("pad_", "<u4")])
+
+_lib = None
+
+
+def ref():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(REF_PATH):
+            raise RuntimeError(f"{REF_PATH} missing: run `make -C oracle` where /root/reference exists")
+        _lib = ctypes.CDLL(REF_PATH)
+        _lib.vlref_murmur64.restype = u64
+        _lib.vlref_murmur64.argtypes = [cp]
+        _lib.vlref_rand_reset_i.restype = u32
+        _lib.vlref_rand_reset_i.argtypes = [i32, u64, u64, u64, i32]
+        _lib.vlref_rand_reset_q.restype = u64
+        _lib.vlref_rand_reset_q.argtypes = [i32, u64, u64, u64, i32]
+        _lib.vlref_rand_reset_w.restype = None
+        _lib.vlref_rand_reset_w.argtypes = [i32, vp, u64, u64, u64, i32]
+        _lib.vlref_rng_rand64.restype = None
+        _lib.vlref_rng_rand64.argtypes = [u64, vp, i32]
+        _lib.vlref_mtc_run.restype = i32
+        _lib.vlref_mtc_run.argtypes = [u64, u64, u64, i32, u64, u32, u64, u32, u32, i32, vp, u64, vp,
+                                       vp, vp, vp, cp, i64, cp, i64, vp, u64, i32]
+    return _lib
+
+
+def murmur64(s):
+    return ref().vlref_murmur64(s.encode())
+
+
+def rand_reset_w(obits, scope_hash, salt, seed, rand_reset=2):
+    words = (obits + 31) // 32
+    out = np.zeros(words, dtype=np.uint32)
+    ref().vlref_rand_reset_w(obits, out.ctypes.data, scope_hash, salt, seed, rand_reset)
+    return out
+
+
+def rng_rand64(seed, n):
+    out = np.zeros(n, dtype=np.uint64)
+    ref().vlref_rng_rand64(seed, out.ctypes.data, n)
+    return out
+
+
+class MtcResult:
+    pass
+
+
+def mtc_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, stop_on_finish=False, tb_seed=0,
+            per_instance=False, reset_period=0, trace_plusarg=False, obs_evals=0, vcd_path=None,
+            vcd_instance=-1, cov_path=None, cov_instance=-1, threads=1):
+    """Run the restated reference model of examples/make_tracing_c for n instances."""
+    r = MtcResult()
+    r.obs = np.zeros((max(obs_evals, 1), 6, n), dtype=np.uint32)
+    r.sigs = np.zeros(n, dtype=np.uint64)
+    r.status = np.zeros(n, dtype=STATUS_DTYPE)
+    r.final = np.zeros((n, 4), dtype=np.uint32)
+    r.cov = np.zeros(527, dtype=np.uint64)
+    con = ctypes.create_string_buffer(1 << 16)
+    rc = ref().vlref_mtc_run(
+        n, inst_base, seed, rand_reset, n_evals, 2 if stop_on_finish else 0, tb_seed,
+        1 if per_instance else 0, reset_period, 1 if trace_plusarg else 0,
+        r.obs.ctypes.data if obs_evals else None, obs_evals, r.sigs.ctypes.data,
+        r.status.ctypes.data, r.final.ctypes.data, r.cov.ctypes.data,
+        vcd_path.encode() if vcd_path else None, vcd_instance,
+        cov_path.encode() if cov_path else None, cov_instance, con, len(con), threads)
+    assert rc == 0
+    r.console = con.value.decode()
+    if not obs_evals:
+        r.obs = None
+    return r

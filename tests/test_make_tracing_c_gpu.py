@@ -1,0 +1,210 @@
+"""Parity of the batched CUDA evaluator with the oracle for examples/make_tracing_c
+(BASELINE.json config 1), through the C ABI (include/verilated_cuda_abi.h).
+
+Oracle = restated reference model against the genuine runtime (oracle/models/make_tracing_c,
+pinned by tests/test_oracle.py).  Bit-exact: every output port of every instance after every
+eval, context flags, $display records, coverage counters, coverage.dat text.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_util as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STATUS_FIELDS = ["time", "first_finish_time", "first_stop_time", "status", "error_count",
+                 "finish_count", "stop_count", "fatal_count", "first_stop_line", "msg_count"]
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from verilator_b200 import abi
+    assert abi.lib.vlcu_device_count() > 0, "no CUDA device: GPU tests need a B200"
+    return abi
+
+
+def check_status(got, want):
+    for f in STATUS_FIELDS:
+        assert (got[f] == want[f]).all(), (f, got[f][:8], want[f][:8])
+
+
+@pytest.mark.parametrize("design", ["make_tracing_c", "make_tracing_c_cov"])
+@pytest.mark.parametrize("per_instance,period,rand_reset", [(False, 0, 2), (True, 0, 2),
+                                                            (True, 128, 2), (True, 128, 0)])
+def test_ports_every_eval_match_oracle(abi, design, per_instance, period, rand_reset):
+    n, evals = 300, 700
+    want = O.mtc_run(n, evals, seed=7, rand_reset=rand_reset, tb_seed=99, per_instance=per_instance,
+                     reset_period=period, obs_evals=evals)
+    with abi.Model(design, n, seed=7, rand_reset=rand_reset, msg_cap=8) as m:
+        obs, _ = m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, obs_evals=evals, tb_seed=99,
+                       tb_flags=1 if per_instance else 0, tb_arg=(period, 0, 0, 0))
+        assert (obs == want.obs).all()
+        assert (m.signatures() == want.sigs).all()
+        check_status(m.status(), want.status)
+        assert (m.get_member("top__DOT__sub__DOT__count_c") == want.final[:, 0]).all()
+        assert (m.get_output("out_quad") == (want.obs[-1, 1].astype(np.uint64)
+                                             | (want.obs[-1, 2].astype(np.uint64) << 32))).all()
+
+
+def test_golden_behavioural_vectors(abi):
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "make_tracing_c_ports.json")))["default"]
+    with abi.Model("make_tracing_c", 1, rand_reset=2) as m:
+        obs, _ = m.run("sim_main", gold["n_evals"], flags=abi.RUNF_TB_BEGIN, obs_evals=gold["n_evals"])
+        rows = np.array(gold["rows"], dtype=np.uint64)
+        assert (obs[:, :, 0] == rows[:, :6]).all()
+        st = m.status()
+        assert int(st["first_finish_time"][0]) == 17
+
+
+def test_stop_on_finish_like_sim_main_and_console(abi):
+    want = O.mtc_run(64, 1000, rand_reset=2, stop_on_finish=True, trace_plusarg=True)
+    with abi.Model("make_tracing_c", 64, rand_reset=2, msg_cap=8, plusargs="+trace") as m:
+        m.run("sim_main", 1000, flags=abi.RUNF_TB_BEGIN | abi.RUNF_STOP_ON_FINISH)
+        st = m.status()
+        check_status(st, want.status)
+        assert (st["time"] == 17).all()
+        msgs, count = m.messages(0)
+        text = "".join(m.format_message(x) for x in msgs)
+        assert count == 3 and text == want.console
+        assert text.endswith("*-* All Finished *-*\n")
+
+
+def test_split_runs_equal_one_run(abi):
+    """State and context persist across vlcu_run calls (K-cycle fusion is transparent)."""
+    n = 257
+    with abi.Model("make_tracing_c", n, seed=3, rand_reset=2) as a, \
+            abi.Model("make_tracing_c", n, seed=3, rand_reset=2) as b:
+        a.run("sim_main", 1000, flags=abi.RUNF_TB_BEGIN, tb_seed=5, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        b.run("sim_main", 1, flags=abi.RUNF_TB_BEGIN, tb_seed=5, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        b.run("sim_main", 332, tb_seed=5, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        b.run("sim_main", 667, tb_seed=5, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        assert (a.signatures() == b.signatures()).all()
+        for f in STATUS_FIELDS:
+            assert (a.status()[f] == b.status()[f]).all()
+        assert (a.snapshot(100) == b.snapshot(100)).all()
+
+
+def test_host_driven_eval_like_a_cpp_testbench(abi):
+    """Drop-in use: poke ports from the host, vlcu_eval(), read ports -- one eval at a time,
+    exactly what sim_main.cpp does with Vtop, for all instances at once."""
+    n, evals = 33, 60
+    want = O.mtc_run(n, evals, rand_reset=2, tb_seed=11, per_instance=True, obs_evals=evals)
+    rng_in = O.mtc_run  # (stimulus is regenerated below the same way the testbench does)
+    with abi.Model("make_tracing_c", n, rand_reset=2) as m:
+        # initial values as the device testbench would set them: read them back after begin()
+        m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=11, tb_flags=1)
+        in_quad = m.get_member("in_quad").astype(np.uint64)
+        clk, t = 0, 0
+        for e in range(evals):
+            t += 1
+            clk ^= 1
+            m.time_inc(1)
+            m.set_input("clk", np.uint8(clk))
+            if not clk:
+                m.set_input("reset_l", np.uint8(0 if 1 < t < 10 else 1))
+                in_quad = (in_quad + np.uint64(0x12)) & np.uint64((1 << 40) - 1)
+                m.set_input("in_quad", in_quad)
+            m.eval()
+            assert (m.get_output("out_small") == want.obs[e, 0]).all()
+            oq = m.get_output("out_quad")
+            assert (oq == (want.obs[e, 1].astype(np.uint64) | (want.obs[e, 2].astype(np.uint64) << 32))).all()
+            assert (m.get_output("out_wide") == want.obs[e, 3:6].T).all()
+        check_status(m.status(), want.status)
+
+
+def test_trace_testbench_with_host_stimulus_rows(abi):
+    """Generic 'trace' testbench: stimulus rows [eval][in_word][instance] from the host."""
+    n, evals = 130, 80
+    want = O.mtc_run(n, evals, rand_reset=2, tb_seed=4, per_instance=True, obs_evals=evals)
+    with abi.Model("make_tracing_c", n, rand_reset=2) as m:
+        m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=4, tb_flags=1)
+        in_small = m.get_member("in_small").astype(np.uint32)
+        in_quad = m.get_member("in_quad").astype(np.uint64)
+        in_wide = m.get_member("in_wide").astype(np.uint32)
+        stim = np.zeros((evals, m.in_words, m.npad), dtype=np.uint32)
+        clk, t, reset_l = 0, 0, 1
+        for e in range(evals):
+            t += 1
+            clk ^= 1
+            if not clk:
+                reset_l = 0 if 1 < t < 10 else 1
+                in_quad = (in_quad + np.uint64(0x12)) & np.uint64((1 << 40) - 1)
+            stim[e, 0, :n] = clk
+            stim[e, 1, :n] = reset_l
+            stim[e, 2, :n] = in_small
+            stim[e, 3, :n] = (in_quad & np.uint64(0xffffffff)).astype(np.uint32)
+            stim[e, 4, :n] = (in_quad >> np.uint64(32)).astype(np.uint32)
+            stim[e, 5:8, :n] = in_wide.T
+        obs, _ = m.run("trace", evals, stim=stim, obs_evals=evals)
+        assert (obs == want.obs).all()
+        check_status(m.status(), want.status)
+
+
+def test_x_initial_unique_reset_values(abi):
+    """ctor_var_reset: per-instance seeds feed VL_SCOPED_RAND_RESET_* (config 3 mechanism)."""
+    n = 1000
+    want = O.mtc_run(n, 0, inst_base=5000, seed=0x1234, rand_reset=2)
+    with abi.Model("make_tracing_c", n, inst_base=5000, seed=0x1234, rand_reset=2) as m:
+        got = m.get_member("top__DOT__sub__DOT__count_c")
+        assert len(set(got.tolist())) > n * 0.99
+    # the oracle's final count_c after zero evals is its reset value; sim_main then overwrites
+    # the input ports, which the GPU model has not done yet: compare count_c only
+    assert (got == want.final[:, 0]).all()
+    want1 = O.mtc_run(8, 0, seed=1, rand_reset=1)
+    with abi.Model("make_tracing_c", 8, seed=1, rand_reset=1) as m:
+        assert (m.get_member("top__DOT__sub__DOT__count_c") == want1.final[:, 0]).all()
+        assert (m.get_member("top__DOT__sub__DOT__count_c") == 0xffffffff).all()
+
+
+def test_coverage_counters_and_file(abi, tmp_path):
+    n, evals = 200, 900
+    want = O.mtc_run(n, evals, seed=2, rand_reset=2, tb_seed=8, per_instance=True, reset_period=128)
+    with abi.Model("make_tracing_c_cov", n, seed=2, rand_reset=2) as m:
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=8, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        sums = m.coverage_reduce()
+        assert m.coverage_bins() == 527
+        assert (sums == want.cov).all()
+        per_inst = m.get_member("__Vcoverage")
+        assert (per_inst.astype(np.uint64).sum(axis=0) == want.cov).all()
+    # single instance: the file must be byte-identical to the reference writer's
+    ref_path, gpu_path = str(tmp_path / "ref.dat"), str(tmp_path / "gpu.dat")
+    O.mtc_run(1, evals, seed=2, rand_reset=2, reset_period=128, cov_path=ref_path, cov_instance=0)
+    with abi.Model("make_tracing_c_cov", 1, seed=2, rand_reset=2) as m:
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_arg=(128, 0, 0, 0))
+        m.coverage_write(m.coverage_reduce(), gpu_path)
+    assert open(gpu_path, "rb").read() == open(ref_path, "rb").read()
+
+
+def test_assertion_failure_is_recorded_not_fatal(abi):
+    """Original reset rule on a long run: count_c passes 100, the design's assertion fires.
+    $finish came first, so (as in the reference's vl_stop) the stop is ignored."""
+    n, evals = 16, 400
+    want = O.mtc_run(n, evals, rand_reset=2)
+    with abi.Model("make_tracing_c", n, rand_reset=2, msg_cap=4) as m:
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN)
+        check_status(m.status(), want.status)
+        assert (m.status()["status"] & abi.ST_MSGDROP).all()
+
+
+def test_large_batch_signature_properties(abi):
+    """BASELINE size (65,536 instances): instances with identical stimulus have identical
+    signatures, different stimulus gives different signatures, sample checked against oracle."""
+    n, evals = 65536, 256
+    with abi.Model("make_tracing_c", n, seed=1, rand_reset=2) as m:
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=3, tb_flags=1, tb_arg=(128, 0, 0, 0))
+        sig = m.signatures()
+        ms = m.last_kernel_ms()
+        assert ms > 0
+    assert len(np.unique(sig)) > n * 0.99
+    want = O.mtc_run(64, evals, inst_base=0, seed=1, rand_reset=2, tb_seed=3, per_instance=True,
+                     reset_period=128)
+    assert (sig[:64] == want.sigs).all()
+    want_hi = O.mtc_run(8, evals, inst_base=65000, seed=1, rand_reset=2, tb_seed=3,
+                        per_instance=True, reset_period=128)
+    assert (sig[65000:65008] == want_hi.sigs).all()
+    with abi.Model("make_tracing_c", 4096, seed=1, rand_reset=2) as m:
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_arg=(128, 0, 0, 0))
+        assert len(np.unique(m.signatures())) == 1

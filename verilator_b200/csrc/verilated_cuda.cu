@@ -1,0 +1,982 @@
+// -*- mode: C++; c-file-style: "cc-mode" -*-
+//*************************************************************************
+//
+// verilated_cuda.cu -- host runtime of the B200 batched evaluator and the
+// implementation of the C ABI in include/verilated_cuda_abi.h.
+//
+// Role in the reference's layering: this is the sibling of
+// include/verilated.cpp for models printed by V3EmitCuda -- it owns the
+// batched VerilatedContext (one VlcuCtxRec per instance), the structure-of-
+// arrays design state in HBM, the port ingest/egress transposes, the
+// device-side coverage reduction (+ NCCL sum across shards) and the
+// coverage.dat writer (restating include/verilated_cov.cpp:143-171,368-438).
+//
+// There is deliberately no CPU execution path: every entry point that
+// computes launches a kernel, and vlcu_create() fails without a device.
+//
+//*************************************************************************
+#define VLCU_HOST_RUNTIME 1
+#include "verilated_cuda_abi.h"
+#include "verilated_cuda_host.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is dlopen()ed on first use
+
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(VlcuCtxRec) == sizeof(vlcu_status_t), "status record layouts must agree");
+static_assert(sizeof(VlcuMsg) == sizeof(vlcu_msg_t), "message record layouts must agree");
+static_assert(VLCU_RUN_TB_BEGIN == VLCU_RUNF_TB_BEGIN, "flag values must agree");
+static_assert(VLCU_RUN_STOP_ON_FINISH == VLCU_RUNF_STOP_ON_FINISH, "flag values must agree");
+static_assert(sizeof(ncclUniqueId) == VLCU_NCCL_ID_BYTES, "NCCL unique id size");
+
+//=========================================================================
+// Errors
+
+static thread_local std::string t_lastError;
+
+static int fail(int code, const std::string& msg) {
+    t_lastError = msg;
+    return code;
+}
+static int failCuda(cudaError_t e, const char* what) {
+    return fail(VLCU_E_CUDA, std::string{what} + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr) \
+    do { \
+        const cudaError_t e_ = (expr); \
+        if (e_ != cudaSuccess) return failCuda(e_, #expr); \
+    } while (0)
+
+//=========================================================================
+// Design registry
+
+static std::vector<VlcuDesignOps*>& registry() {
+    static std::vector<VlcuDesignOps*> s;
+    return s;
+}
+int vlcu_register_design(VlcuDesignOps* opsp) {
+    registry().push_back(opsp);
+    return static_cast<int>(registry().size());
+}
+
+//=========================================================================
+// NCCL, bound lazily so single-GPU use needs no NCCL at all
+
+struct NcclApi final {
+    void* libp = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (libp) return true;
+        // RTLD_NOLOAD first: reuse a copy the process (e.g. torch) already mapped
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            libp = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
+            if (libp) break;
+        }
+        if (!libp) {
+            for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+                libp = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+                if (libp) break;
+            }
+        }
+        if (!libp) {
+            err = std::string{"cannot load libnccl: "} + dlerror();
+            return false;
+        }
+#define BIND(field, sym) \
+    field = reinterpret_cast<decltype(field)>(dlsym(libp, sym)); \
+    if (!field) { \
+        err = std::string{"libnccl lacks "} + sym; \
+        return false; \
+    }
+        BIND(GetUniqueId, "ncclGetUniqueId");
+        BIND(CommInitRank, "ncclCommInitRank");
+        BIND(CommDestroy, "ncclCommDestroy");
+        BIND(AllReduce, "ncclAllReduce");
+        BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+        return true;
+    }
+};
+static NcclApi& nccl() {
+    static NcclApi s;
+    return s;
+}
+
+//=========================================================================
+// The model handle
+
+struct vlcu_model final {
+    const VlcuDesignOps* opsp = nullptr;
+    const VlcuDesignInfo* infop = nullptr;
+    int device = 0;
+    uint64_t n = 0, npad = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    uint8_t* dState = nullptr;
+    VlcuCtxRec* dCtx = nullptr;
+    VlcuMsg* dMsgs = nullptr;
+    uint64_t* dSigs = nullptr;
+    uint64_t* dEvalsDone = nullptr;
+    uint64_t* dCovSums = nullptr;
+    VlcuModelDev dev{};
+    uint64_t launches = 0;
+    uint64_t evalIndex = 0;  // evals issued so far (VlcuRunDev::evalBase)
+    bool haveTiming = false;
+    ncclComm_t comm = nullptr;
+    int commRank = 0, commWorld = 1;
+    std::vector<int> ports;  // member indices of primary IO, in declaration order
+    // Reusable device staging
+    uint8_t* dStage = nullptr;
+    size_t stageBytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard final {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensureStage(vlcu_model* h, size_t bytes) {
+    if (bytes <= h->stageBytes) return VLCU_OK;
+    if (h->dStage) cudaFree(h->dStage);
+    h->dStage = nullptr;
+    h->stageBytes = 0;
+    CUDA_TRY(cudaMalloc(&h->dStage, bytes));
+    h->stageBytes = bytes;
+    return VLCU_OK;
+}
+
+//-------------------------------------------------------------------------
+// Port / member transposes between the host's per-instance layout and SoA
+
+// src: packed records [inst][elems * elemBytes]; dst: SoA rows [elem][inst]
+template <typename T>
+__global__ void k_scatter(T* __restrict__ dst, const T* __restrict__ src, uint64_t n, uint64_t npad,
+                          uint32_t elems, uint32_t broadcast, T topMask) {
+    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= n * elems) return;
+    const uint64_t inst = idx % n;  // instance fastest: coalesced writes
+    const uint32_t e = static_cast<uint32_t>(idx / n);
+    T v = src[(broadcast ? 0 : inst * elems) + e];
+    if (e == elems - 1) v &= topMask;  // inputs are masked to the declared width on ingest
+    dst[static_cast<uint64_t>(e) * npad + inst] = v;
+}
+template <typename T>
+__global__ void k_gather(T* __restrict__ dst, const T* __restrict__ src, uint64_t n, uint64_t npad,
+                         uint32_t elems) {
+    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= n * elems) return;
+    const uint64_t inst = idx % n;
+    const uint32_t e = static_cast<uint32_t>(idx / n);
+    dst[inst * elems + e] = src[static_cast<uint64_t>(e) * npad + inst];
+}
+
+// One instance's state, packed at the members' SoA offsets (npad == 1 layout)
+__global__ void k_snapshot(uint8_t* __restrict__ dst, const uint8_t* __restrict__ state,
+                           uint64_t npad, uint64_t inst, const uint32_t* __restrict__ table,
+                           uint32_t nMembers) {
+    // table: per member {soaOffset, elemBytes, elems, instanceMajor}
+    for (uint32_t m = blockIdx.x; m < nMembers; m += gridDim.x) {
+        const uint32_t off = table[m * 4 + 0], eb = table[m * 4 + 1], elems = table[m * 4 + 2];
+        const bool instMajor = table[m * 4 + 3] != 0;
+        const uint8_t* const basep = state + static_cast<uint64_t>(off) * npad;
+        for (uint64_t b = threadIdx.x; b < static_cast<uint64_t>(eb) * elems; b += blockDim.x) {
+            const uint64_t e = b / eb, byte = b % eb;
+            const uint64_t src = instMajor ? ((inst * elems + e) * eb + byte)
+                                           : ((e * npad + inst) * eb + byte);
+            dst[off + b] = basep[src];
+        }
+    }
+}
+
+__global__ void k_time_inc(VlcuCtxRec* ctx, uint64_t n, uint64_t add) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) ctx[i].time += add;
+}
+
+// Coverage: counters[bin][instance] (uint32, each wrapped like the host's ++) -> uint64 per
+// bin.  One CTA per bin streams the bin's row with coalesced 128-bit loads.
+__global__ void __launch_bounds__(256) k_cov_reduce(const uint32_t* __restrict__ cov, uint64_t n,
+                                                    uint64_t npad, uint32_t bins,
+                                                    uint64_t* __restrict__ out) {
+    __shared__ uint64_t s_part[8];
+    for (uint32_t bin = blockIdx.x; bin < bins; bin += gridDim.x) {
+        const uint32_t* const rowp = cov + static_cast<uint64_t>(bin) * npad;
+        uint64_t acc = 0;
+        const uint64_t nvec = n / 4;
+        const uint4* const row4p = reinterpret_cast<const uint4*>(rowp);  // npad % 128 == 0
+        for (uint64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+            const uint4 v = row4p[i];
+            acc += static_cast<uint64_t>(v.x) + v.y + v.z + v.w;
+        }
+        for (uint64_t i = nvec * 4 + threadIdx.x; i < n; i += blockDim.x) acc += rowp[i];
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t total = 0;
+            for (int w = 0; w < 8; ++w) total += s_part[w];
+            out[bin] = total;
+        }
+        __syncthreads();
+    }
+}
+
+unsigned blocksFor(uint64_t work, unsigned threads) {
+    return static_cast<unsigned>((work + threads - 1) / threads);
+}
+
+const VlcuMemberDesc* memberAt(const vlcu_model* h, int member) {
+    if (!h || member < 0 || static_cast<uint32_t>(member) >= h->infop->nMembers) return nullptr;
+    return &h->infop->members[member];
+}
+
+int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, void* dst,
+                   size_t stride, bool toDevice, bool maskWidth) {
+    const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
+    const bool broadcast = toDevice && stride == 0;
+    if (!broadcast && stride < recBytes) return fail(VLCU_E_ARG, "stride smaller than one element");
+    const uint64_t n = h->n;
+    DeviceGuard guard{h->device};
+    if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major in HBM: a strided copy is enough
+        uint8_t* const devp = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+        if (toDevice) {
+            if (broadcast) {
+                for (uint64_t i = 0; i < n; ++i) {
+                    CUDA_TRY(cudaMemcpyAsync(devp + i * recBytes, src, recBytes,
+                                             cudaMemcpyHostToDevice, h->stream));
+                }
+            } else {
+                CUDA_TRY(cudaMemcpy2DAsync(devp, recBytes, src, stride, recBytes, n,
+                                           cudaMemcpyHostToDevice, h->stream));
+            }
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(dst, stride, devp, recBytes, recBytes, n,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        return VLCU_OK;
+    }
+    const size_t stageBytes = recBytes * (broadcast ? 1 : n);
+    if (const int rc = ensureStage(h, stageBytes)) return rc;
+    const uint64_t work = n * md.elems;
+    const unsigned threads = 256, blocks = blocksFor(work, threads);
+    void* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+    const int topBits = md.width - static_cast<int>(md.elems - 1) * md.elemBytes * 8;
+    const bool isWide = md.elems > 1 && md.kind != VLCU_MEMBER_COVERAGE;
+    const uint64_t topMask
+        = !maskWidth ? ~0ULL
+                     : (isWide || md.elems == 1)
+                           ? ((topBits >= md.elemBytes * 8) ? ~0ULL : ((1ULL << topBits) - 1ULL))
+                           : ~0ULL;
+    if (toDevice) {
+        if (broadcast) {
+            CUDA_TRY(cudaMemcpyAsync(h->dStage, src, recBytes, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(h->dStage, recBytes, src, stride, recBytes, n,
+                                       cudaMemcpyHostToDevice, h->stream));
+        }
+        switch (md.elemBytes) {
+        case 1:
+            k_scatter<uint8_t><<<blocks, threads, 0, h->stream>>>(
+                static_cast<uint8_t*>(soap), h->dStage, n, h->npad, md.elems, broadcast,
+                static_cast<uint8_t>(topMask));
+            break;
+        case 2:
+            k_scatter<uint16_t><<<blocks, threads, 0, h->stream>>>(
+                static_cast<uint16_t*>(soap), reinterpret_cast<uint16_t*>(h->dStage), n, h->npad,
+                md.elems, broadcast, static_cast<uint16_t>(topMask));
+            break;
+        case 4:
+            k_scatter<uint32_t><<<blocks, threads, 0, h->stream>>>(
+                static_cast<uint32_t*>(soap), reinterpret_cast<uint32_t*>(h->dStage), n, h->npad,
+                md.elems, broadcast, static_cast<uint32_t>(topMask));
+            break;
+        default:
+            k_scatter<uint64_t><<<blocks, threads, 0, h->stream>>>(
+                static_cast<uint64_t*>(soap), reinterpret_cast<uint64_t*>(h->dStage), n, h->npad,
+                md.elems, broadcast, topMask);
+            break;
+        }
+        ++h->launches;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    } else {
+        switch (md.elemBytes) {
+        case 1:
+            k_gather<uint8_t><<<blocks, threads, 0, h->stream>>>(
+                h->dStage, static_cast<const uint8_t*>(soap), n, h->npad, md.elems);
+            break;
+        case 2:
+            k_gather<uint16_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint16_t*>(h->dStage), static_cast<const uint16_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        case 4:
+            k_gather<uint32_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint32_t*>(h->dStage), static_cast<const uint32_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        default:
+            k_gather<uint64_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint64_t*>(h->dStage), static_cast<const uint64_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        }
+        ++h->launches;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy2DAsync(dst, stride, h->dStage, recBytes, recBytes, n,
+                                   cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return VLCU_OK;
+}
+
+void fillPortInfo(const VlcuMemberDesc& md, vlcu_port_info_t* out) {
+    out->name = md.name;
+    out->dir = md.kind == VLCU_MEMBER_IN    ? VLCU_DIR_IN
+               : md.kind == VLCU_MEMBER_OUT ? VLCU_DIR_OUT
+                                            : VLCU_DIR_INOUT;
+    out->width = static_cast<int>(md.width);
+    out->elem_bytes = md.elemBytes;
+    out->elems = static_cast<int>(md.elems);
+}
+
+int launchRun(vlcu_model* h, const char* tb, VlcuRunDev& r) {
+    r.npad = h->npad;
+    r.sigs = h->dSigs;
+    r.evalsDone = h->dEvalsDone;
+    r.evalBase = h->evalIndex;
+    CUDA_TRY(cudaEventRecord(h->evStart, h->stream));
+    const cudaError_t e = h->opsp->launchRun(tb, h->dev, r, h->stream);
+    if (e == cudaErrorInvalidValue) {
+        return fail(VLCU_E_ARG, std::string{"unknown testbench '"} + tb + "' for design "
+                                    + h->infop->name);
+    }
+    if (e != cudaSuccess) return failCuda(e, "kernel launch");
+    CUDA_TRY(cudaEventRecord(h->evStop, h->stream));
+    ++h->launches;
+    h->haveTiming = true;
+    h->evalIndex += r.nEvals;
+    return VLCU_OK;
+}
+
+}  // namespace
+
+//=========================================================================
+// C ABI
+
+extern "C" {
+
+int vlcu_abi_version(void) { return VLCU_ABI_VERSION; }
+const char* vlcu_last_error(void) { return t_lastError.c_str(); }
+int vlcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+int vlcu_design_count(void) { return static_cast<int>(registry().size()); }
+const char* vlcu_design_name(int index) {
+    if (index < 0 || index >= vlcu_design_count()) return nullptr;
+    return registry()[index]->info().name;
+}
+
+vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, uint64_t inst_base,
+                          uint64_t seed_base, int rand_reset, uint32_t msg_cap,
+                          const char* plusargs) {
+    if (!design || !n_instances) {
+        fail(VLCU_E_ARG, "vlcu_create: design name and a non-zero instance count are required");
+        return nullptr;
+    }
+    const VlcuDesignOps* opsp = nullptr;
+    for (VlcuDesignOps* p : registry()) {
+        if (!strcmp(p->info().name, design)) opsp = p;
+    }
+    if (!opsp) {
+        fail(VLCU_E_ARG, std::string{"vlcu_create: unknown design '"} + design + "'");
+        return nullptr;
+    }
+    int ndev = 0;
+    const cudaError_t de = cudaGetDeviceCount(&ndev);
+    if (de != cudaSuccess || ndev == 0) {
+        fail(VLCU_E_NODEVICE,
+             std::string{"vlcu_create: no CUDA device ("}
+                 + (de != cudaSuccess ? cudaGetErrorString(de) : "device count is 0")
+                 + "); the batched evaluator has no CPU path");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail(VLCU_E_ARG, "vlcu_create: device index out of range");
+        return nullptr;
+    }
+    vlcu_model* const h = new vlcu_model;
+    h->opsp = opsp;
+    h->infop = &opsp->info();
+    h->device = device;
+    h->n = n_instances;
+    h->npad = (n_instances + 127) / 128 * 128;
+    for (uint32_t m = 0; m < h->infop->nMembers; ++m) {
+        if (h->infop->members[m].kind <= VLCU_MEMBER_INOUT) h->ports.push_back(static_cast<int>(m));
+    }
+    DeviceGuard guard{device};
+    const auto bail = [&](cudaError_t e, const char* what) -> vlcu_model_t* {
+        failCuda(e, what);
+        vlcu_destroy(h);
+        return nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&h->evStart)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&h->evStop)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    const size_t stateBytes = static_cast<size_t>(h->infop->stateBytes) * h->npad;
+    if ((e = cudaMalloc(&h->dState, stateBytes)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
+    if ((e = cudaMemsetAsync(h->dState, 0, stateBytes, h->stream)) != cudaSuccess)
+        return bail(e, "cudaMemset(state)");
+    if ((e = cudaMalloc(&h->dCtx, sizeof(VlcuCtxRec) * h->npad)) != cudaSuccess)
+        return bail(e, "cudaMalloc(ctx)");
+    if (msg_cap) {
+        if ((e = cudaMalloc(&h->dMsgs, sizeof(VlcuMsg) * msg_cap * h->n)) != cudaSuccess)
+            return bail(e, "cudaMalloc(msgs)");
+    }
+    if ((e = cudaMalloc(&h->dSigs, sizeof(uint64_t) * h->npad)) != cudaSuccess)
+        return bail(e, "cudaMalloc(sigs)");
+    if ((e = cudaMalloc(&h->dEvalsDone, sizeof(uint64_t) * h->npad)) != cudaSuccess)
+        return bail(e, "cudaMalloc(evalsDone)");
+    if (h->infop->nCoverPoints) {
+        if ((e = cudaMalloc(&h->dCovSums, sizeof(uint64_t) * h->infop->nCoverPoints))
+            != cudaSuccess)
+            return bail(e, "cudaMalloc(covSums)");
+    }
+    // $test$plusargs are resolved here, once, into a bit per string the design asks about
+    uint32_t plusBits = 0;
+    if (plusargs) {
+        std::istringstream is{plusargs};
+        std::string tok;
+        while (is >> tok) {
+            if (!tok.empty() && tok[0] == '+') tok = tok.substr(1);
+            for (uint32_t k = 0; k < h->infop->nPlusargs; ++k) {
+                // $test$plusargs matches a prefix of the provided argument
+                if (tok.compare(0, strlen(h->infop->plusargs[k]), h->infop->plusargs[k]) == 0) {
+                    plusBits |= 1u << k;
+                }
+            }
+        }
+    }
+    h->dev.state = VlcuState{h->dState, h->npad};
+    h->dev.ctxRecs = h->dCtx;
+    h->dev.msgs = h->dMsgs;
+    h->dev.n = h->n;
+    h->dev.instBase = inst_base;
+    h->dev.seedBase = seed_base;
+    h->dev.randReset = static_cast<uint32_t>(rand_reset);
+    h->dev.msgCap = msg_cap;
+    h->dev.plusargs = plusBits;
+    h->dev.errorLimit = 1;  // VerilatedContext default (include/verilated.h:431)
+    if (vlcu_reset(h) != VLCU_OK) {
+        vlcu_destroy(h);
+        return nullptr;
+    }
+    return h;
+}
+
+void vlcu_destroy(vlcu_model_t* h) {
+    if (!h) return;
+    DeviceGuard guard{h->device};
+    if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->dState);
+    cudaFree(h->dCtx);
+    cudaFree(h->dMsgs);
+    cudaFree(h->dSigs);
+    cudaFree(h->dEvalsDone);
+    cudaFree(h->dCovSums);
+    cudaFree(h->dStage);
+    if (h->evStart) cudaEventDestroy(h->evStart);
+    if (h->evStop) cudaEventDestroy(h->evStop);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int vlcu_reset(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaMemsetAsync(h->dSigs, 0, sizeof(uint64_t) * h->npad, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->dEvalsDone, 0, sizeof(uint64_t) * h->npad, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->dCtx, 0, sizeof(VlcuCtxRec) * h->npad, h->stream));
+    const cudaError_t e = h->opsp->launchReset(h->dev, h->stream);
+    if (e != cudaSuccess) return failCuda(e, "reset kernel");
+    ++h->launches;
+    h->evalIndex = 0;
+    if (const int rc = vlcu_reset_signatures(h)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+uint64_t vlcu_instances(const vlcu_model_t* h) { return h ? h->n : 0; }
+uint64_t vlcu_padded_instances(const vlcu_model_t* h) { return h ? h->npad : 0; }
+uint32_t vlcu_state_bytes(const vlcu_model_t* h) { return h ? h->infop->stateBytes : 0; }
+uint32_t vlcu_in_words(const vlcu_model_t* h) { return h ? h->infop->inWords : 0; }
+uint32_t vlcu_out_words(const vlcu_model_t* h) { return h ? h->infop->outWords : 0; }
+uint32_t vlcu_in_bytes(const vlcu_model_t* h) { return h ? h->infop->inBytes : 0; }
+uint32_t vlcu_out_bytes(const vlcu_model_t* h) { return h ? h->infop->outBytes : 0; }
+uint32_t vlcu_trace_record_bytes(const vlcu_model_t* h) {
+    return h ? h->infop->stateBytes + VLCU_TRACE_HDR : 0;
+}
+
+int vlcu_port_count(const vlcu_model_t* h) { return h ? static_cast<int>(h->ports.size()) : 0; }
+int vlcu_port_info(const vlcu_model_t* h, int port, vlcu_port_info_t* out) {
+    if (!h || !out || port < 0 || port >= vlcu_port_count(h)) return fail(VLCU_E_ARG, "bad port");
+    fillPortInfo(h->infop->members[h->ports[port]], out);
+    return VLCU_OK;
+}
+int vlcu_port_index(const vlcu_model_t* h, const char* name) {
+    if (!h || !name) return fail(VLCU_E_ARG, "bad argument");
+    for (int p = 0; p < vlcu_port_count(h); ++p) {
+        if (!strcmp(h->infop->members[h->ports[p]].name, name)) return p;
+    }
+    return fail(VLCU_E_ARG, std::string{"no port named '"} + name + "'");
+}
+int vlcu_set_input(vlcu_model_t* h, int port, const void* src, size_t stride_bytes) {
+    if (!h || !src || port < 0 || port >= vlcu_port_count(h)) return fail(VLCU_E_ARG, "bad port");
+    const VlcuMemberDesc& md = h->infop->members[h->ports[port]];
+    if (md.kind == VLCU_MEMBER_OUT) return fail(VLCU_E_ARG, "port is an output");
+    return transferMember(h, md, src, nullptr, stride_bytes, true, true);
+}
+int vlcu_get_output(vlcu_model_t* h, int port, void* dst, size_t stride_bytes) {
+    if (!h || !dst || port < 0 || port >= vlcu_port_count(h)) return fail(VLCU_E_ARG, "bad port");
+    return transferMember(h, h->infop->members[h->ports[port]], nullptr, dst, stride_bytes, false,
+                          false);
+}
+int vlcu_member_count(const vlcu_model_t* h) { return h ? static_cast<int>(h->infop->nMembers) : 0; }
+const char* vlcu_member_name(const vlcu_model_t* h, int member) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    return mdp ? mdp->name : nullptr;
+}
+int vlcu_member_index(const vlcu_model_t* h, const char* name) {
+    if (!h || !name) return fail(VLCU_E_ARG, "bad argument");
+    for (uint32_t m = 0; m < h->infop->nMembers; ++m) {
+        if (!strcmp(h->infop->members[m].name, name)) return static_cast<int>(m);
+    }
+    return fail(VLCU_E_ARG, std::string{"no member named '"} + name + "'");
+}
+int vlcu_member_info(const vlcu_model_t* h, int member, vlcu_port_info_t* out) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    if (!mdp || !out) return fail(VLCU_E_ARG, "bad member");
+    fillPortInfo(*mdp, out);
+    return VLCU_OK;
+}
+int vlcu_set_member(vlcu_model_t* h, int member, const void* src, size_t stride_bytes) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    if (!mdp || !src) return fail(VLCU_E_ARG, "bad member");
+    return transferMember(h, *mdp, src, nullptr, stride_bytes, true, false);
+}
+int vlcu_get_member(vlcu_model_t* h, int member, void* dst, size_t stride_bytes) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    if (!mdp || !dst) return fail(VLCU_E_ARG, "bad member");
+    return transferMember(h, *mdp, nullptr, dst, stride_bytes, false, false);
+}
+int vlcu_member_device_ptr(vlcu_model_t* h, int member, void** ptr, uint64_t* npad) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    if (!mdp || !ptr) return fail(VLCU_E_ARG, "bad member");
+    *ptr = h->dState + static_cast<uint64_t>(mdp->soaOffset) * h->npad;
+    if (npad) *npad = h->npad;
+    return VLCU_OK;
+}
+uint32_t vlcu_member_offset(const vlcu_model_t* h, int member) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    return mdp ? mdp->soaOffset : 0;
+}
+
+int vlcu_time_inc(vlcu_model_t* h, uint64_t add) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    k_time_inc<<<blocksFor(h->n, 256), 256, 0, h->stream>>>(h->dCtx, h->n, add);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return VLCU_OK;
+}
+
+int vlcu_eval(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    VlcuRunDev r{};
+    r.nEvals = 1;
+    return launchRun(h, "none", r);
+}
+
+int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
+    if (!h || !d || !d->tb) return fail(VLCU_E_ARG, "vlcu_run: null argument");
+    DeviceGuard guard{h->device};
+    const VlcuDesignInfo& info = *h->infop;
+    VlcuRunDev r{};
+    r.nEvals = d->n_evals;
+    r.flags = d->flags & (VLCU_RUNF_TB_BEGIN | VLCU_RUNF_STOP_ON_FINISH);
+    r.stimBroadcast = (d->flags & VLCU_RUNF_STIM_BROADCAST) ? 1 : 0;
+    r.tbSeed = d->tb_seed;
+    r.tbFlags = d->tb_flags;
+    for (int k = 0; k < 4; ++k) r.tbArg[k] = d->tb_arg[k];
+    // Scratch device buffers for host-side stimulus / observation / trace
+    uint32_t* dStim = nullptr;
+    uint32_t* dObs = nullptr;
+    uint8_t* dTrace = nullptr;
+    uint64_t* dSamples = nullptr;
+    const auto cleanup = [&]() {
+        cudaFree(dStim);
+        cudaFree(dObs);
+        cudaFree(dTrace);
+        cudaFree(dSamples);
+    };
+#define RUN_TRY(expr) \
+    do { \
+        const cudaError_t e_ = (expr); \
+        if (e_ != cudaSuccess) { \
+            cleanup(); \
+            return failCuda(e_, #expr); \
+        } \
+    } while (0)
+    if (!strcmp(d->tb, "trace")) {
+        if (!d->stim) return fail(VLCU_E_ARG, "vlcu_run: the trace testbench needs stim");
+        const size_t rowWords = static_cast<size_t>(info.inWords) * (r.stimBroadcast ? 1 : h->npad);
+        if (d->flags & VLCU_RUNF_STIM_DEVICE) {
+            r.stim = d->stim;
+        } else {
+            const size_t bytes = rowWords * d->n_evals * sizeof(uint32_t);
+            RUN_TRY(cudaMalloc(&dStim, bytes));
+            RUN_TRY(cudaMemcpyAsync(dStim, d->stim, bytes, cudaMemcpyHostToDevice, h->stream));
+            r.stim = dStim;
+        }
+    }
+    size_t obsBytes = 0;
+    if (d->obs && d->obs_evals) {
+        r.obsEvals = d->obs_evals < d->n_evals ? d->obs_evals : d->n_evals;
+        obsBytes = static_cast<size_t>(info.outWords) * h->npad * r.obsEvals * sizeof(uint32_t);
+        if (d->flags & VLCU_RUNF_OBS_DEVICE) {
+            r.obs = d->obs;
+        } else {
+            RUN_TRY(cudaMalloc(&dObs, obsBytes));
+            RUN_TRY(cudaMemsetAsync(dObs, 0, obsBytes, h->stream));
+            r.obs = dObs;
+        }
+    }
+    size_t traceBytes = 0;
+    if (d->n_samples && d->trace_out && d->trace_evals && d->sample_instances) {
+        for (uint32_t s = 0; s < d->n_samples; ++s) {
+            if (d->sample_instances[s] >= h->n) {
+                cleanup();
+                return fail(VLCU_E_ARG, "vlcu_run: sampled instance out of range");
+            }
+        }
+        r.nSamples = d->n_samples;
+        r.traceEvals = d->trace_evals < d->n_evals ? d->trace_evals : d->n_evals;
+        traceBytes = static_cast<size_t>(info.stateBytes + VLCU_TRACE_HDR) * r.nSamples
+                     * r.traceEvals;
+        RUN_TRY(cudaMalloc(&dTrace, traceBytes));
+        RUN_TRY(cudaMemsetAsync(dTrace, 0, traceBytes, h->stream));
+        RUN_TRY(cudaMalloc(&dSamples, sizeof(uint64_t) * r.nSamples));
+        RUN_TRY(cudaMemcpyAsync(dSamples, d->sample_instances, sizeof(uint64_t) * r.nSamples,
+                                cudaMemcpyHostToDevice, h->stream));
+        r.trace = dTrace;
+        r.sampleIds = dSamples;
+    }
+    const int rc = launchRun(h, d->tb, r);
+    if (rc != VLCU_OK) {
+        cleanup();
+        return rc;
+    }
+    if (dObs) {
+        RUN_TRY(cudaMemcpyAsync(d->obs, dObs, obsBytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (dTrace) {
+        RUN_TRY(cudaMemcpyAsync(d->trace_out, dTrace, traceBytes, cudaMemcpyDeviceToHost,
+                                h->stream));
+    }
+    if (dStim || dObs || dTrace) RUN_TRY(cudaStreamSynchronize(h->stream));
+    cleanup();
+#undef RUN_TRY
+    return VLCU_OK;
+}
+
+int vlcu_final(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    const cudaError_t e = h->opsp->launchFinal(h->dev, h->stream);
+    if (e != cudaSuccess) return failCuda(e, "final kernel");
+    ++h->launches;
+    return VLCU_OK;
+}
+
+int vlcu_sync(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+int vlcu_last_kernel_ms(vlcu_model_t* h, float* ms) {
+    if (!h || !ms) return fail(VLCU_E_ARG, "null argument");
+    if (!h->haveTiming) return fail(VLCU_E_STATE, "no eval/run kernel has been launched yet");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaEventSynchronize(h->evStop));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->evStart, h->evStop));
+    return VLCU_OK;
+}
+uint64_t vlcu_launch_count(const vlcu_model_t* h) { return h ? h->launches : 0; }
+
+int vlcu_status(vlcu_model_t* h, vlcu_status_t* out) {
+    if (!h || !out) return fail(VLCU_E_ARG, "null argument");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaMemcpyAsync(out, h->dCtx, sizeof(VlcuCtxRec) * h->n, cudaMemcpyDeviceToHost,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+int vlcu_signatures(vlcu_model_t* h, uint64_t* out) {
+    if (!h || !out) return fail(VLCU_E_ARG, "null argument");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaMemcpyAsync(out, h->dSigs, sizeof(uint64_t) * h->n, cudaMemcpyDeviceToHost,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+int vlcu_reset_signatures(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    std::vector<uint64_t> init(h->npad, VLCU_SIG_INIT);
+    CUDA_TRY(cudaMemcpyAsync(h->dSigs, init.data(), sizeof(uint64_t) * h->npad,
+                             cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+int vlcu_messages(vlcu_model_t* h, uint64_t instance, vlcu_msg_t* out, uint32_t cap,
+                  uint32_t* count) {
+    if (!h || instance >= h->n || !count) return fail(VLCU_E_ARG, "bad argument");
+    DeviceGuard guard{h->device};
+    VlcuCtxRec rec;
+    CUDA_TRY(cudaMemcpyAsync(&rec, h->dCtx + instance, sizeof(rec), cudaMemcpyDeviceToHost,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *count = rec.msgCount;
+    uint32_t ncopy = rec.msgCount < h->dev.msgCap ? rec.msgCount : h->dev.msgCap;
+    if (ncopy > cap) ncopy = cap;
+    if (ncopy && out) {
+        CUDA_TRY(cudaMemcpyAsync(out, h->dMsgs + instance * h->dev.msgCap, sizeof(VlcuMsg) * ncopy,
+                                 cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return VLCU_OK;
+}
+const char* vlcu_message_format(const vlcu_model_t* h, uint32_t id) {
+    if (!h || id >= h->infop->nMessages) return nullptr;
+    return h->infop->messages[id];
+}
+
+int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_bytes) {
+    if (!h || !out || instance >= h->n) return fail(VLCU_E_ARG, "bad argument");
+    const VlcuDesignInfo& info = *h->infop;
+    if (out_bytes < info.stateBytes) return fail(VLCU_E_ARG, "snapshot buffer too small");
+    DeviceGuard guard{h->device};
+    std::vector<uint32_t> table(info.nMembers * 4);
+    for (uint32_t m = 0; m < info.nMembers; ++m) {
+        table[m * 4 + 0] = info.members[m].soaOffset;
+        table[m * 4 + 1] = info.members[m].elemBytes;
+        table[m * 4 + 2] = info.members[m].elems;
+        table[m * 4 + 3] = info.members[m].kind == VLCU_MEMBER_MEMORY;
+    }
+    const size_t tableBytes = table.size() * sizeof(uint32_t);
+    const size_t tableOff = (static_cast<size_t>(info.stateBytes) + 15) & ~size_t{15};
+    if (const int rc = ensureStage(h, tableOff + tableBytes)) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->dStage, 0, info.stateBytes, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->dStage + tableOff, table.data(), tableBytes, cudaMemcpyHostToDevice,
+                             h->stream));
+    k_snapshot<<<info.nMembers < 64 ? info.nMembers : 64, 128, 0, h->stream>>>(
+        h->dStage, h->dState, h->npad, instance,
+        reinterpret_cast<const uint32_t*>(h->dStage + tableOff), info.nMembers);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, h->dStage, info.stateBytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+//-------------------------------------------------------------------------
+// Coverage
+
+uint32_t vlcu_coverage_bins(const vlcu_model_t* h) { return h ? h->infop->nCoverPoints : 0; }
+int vlcu_coverage_point(const vlcu_model_t* h, uint32_t bin, const char** filename, int* lineno,
+                        int* column, const char** hier, const char** page, const char** comment,
+                        const char** linescov) {
+    if (!h || bin >= h->infop->nCoverPoints) return fail(VLCU_E_ARG, "bad coverage bin");
+    const VlcuCoverPoint& p = h->infop->coverPoints[bin];
+    if (filename) *filename = p.filename;
+    if (lineno) *lineno = p.lineno;
+    if (column) *column = p.column;
+    if (hier) *hier = p.hier;
+    if (page) *page = p.page;
+    if (comment) *comment = p.comment;
+    if (linescov) *linescov = p.linescov;
+    return VLCU_OK;
+}
+int vlcu_coverage_reduce(vlcu_model_t* h, uint64_t* out) {
+    if (!h || !out) return fail(VLCU_E_ARG, "null argument");
+    const uint32_t bins = h->infop->nCoverPoints;
+    if (!bins) return fail(VLCU_E_STATE, "design was not built with coverage");
+    DeviceGuard guard{h->device};
+    const uint32_t* const covp = reinterpret_cast<const uint32_t*>(
+        h->dState + static_cast<uint64_t>(h->infop->coverageSoaOffset) * h->npad);
+    k_cov_reduce<<<bins < 148 * 8 ? bins : 148 * 8, 256, 0, h->stream>>>(covp, h->n, h->npad, bins,
+                                                                       h->dCovSums);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (h->comm) {  // sum the per-shard totals over NVLink
+        const ncclResult_t nr = nccl().AllReduce(h->dCovSums, h->dCovSums, bins, ncclUint64,
+                                                 ncclSum, h->comm, h->stream);
+        if (nr != ncclSuccess) {
+            return fail(VLCU_E_NCCL, std::string{"ncclAllReduce: "} + nccl().GetErrorString(nr));
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, h->dCovSums, sizeof(uint64_t) * bins, cudaMemcpyDeviceToHost,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+namespace {
+// Restatement of VerilatedCovImp::dequote / keyValueFormatter / combineHier
+// (include/verilated_cov.cpp:143-171,175-220)
+std::string covDequote(const std::string& text) {
+    std::string out;
+    for (const char c : text) {
+        if (!std::isprint(static_cast<unsigned char>(c)) || c == '%' || c == '"') {
+            char hex[8];
+            snprintf(hex, sizeof(hex), "%%%02X", static_cast<unsigned char>(c));
+            out += hex;
+        } else {
+            out += c;
+        }
+    }
+    return out;
+}
+std::string covKeyValue(const std::string& key, const std::string& value) {
+    std::string out = "\001";
+    out += (key.length() == 1 && std::isalpha(static_cast<unsigned char>(key[0])))
+               ? key
+               : covDequote(key);
+    out += "\002" + covDequote(value);
+    return out;
+}
+std::string covCombineHier(const std::string& old, const std::string& add) {
+    if (old == add) return add;
+    if (old.empty()) return add;
+    if (add.empty()) return old;
+    size_t pre = 0;
+    while (old[pre] == add[pre]) ++pre;  // strings differ, so this stops inside both
+    size_t apost = old.size() - 1, bpost = add.size() - 1;
+    while (old[apost] == add[bpost] && apost > pre && bpost > pre) {
+        --apost;
+        --bpost;
+    }
+    const std::string suffix = bpost < add.size() ? add.substr(bpost + 1) : std::string{};
+    return old.substr(0, pre) + "*" + suffix;
+}
+}  // namespace
+
+int vlcu_coverage_write(const vlcu_model_t* h, const uint64_t* counts, const char* filename) {
+    if (!h || !counts || !filename) return fail(VLCU_E_ARG, "null argument");
+    const VlcuDesignInfo& info = *h->infop;
+    std::ofstream os{filename};
+    if (os.fail()) return fail(VLCU_E_IO, std::string{"Can't write '"} + filename + "'");
+    os << "# SystemC::Coverage-3\n";
+    // name -> (hier, count), ordered by name like the host writer's std::map
+    std::map<std::string, std::pair<std::string, uint64_t>> events;
+    for (uint32_t b = 0; b < info.nCoverPoints; ++b) {
+        const VlcuCoverPoint& p = info.coverPoints[b];
+        // Key order after VL_COVER_INSERT's de-duplication: filename, lineno, column, hier,
+        // page (preceded by the derived type), comment, then linescov when present
+        std::string name = covKeyValue("f", p.filename);
+        name += covKeyValue("l", std::to_string(p.lineno));
+        name += covKeyValue("n", std::to_string(p.column));
+        const std::string page = p.page;
+        name += covKeyValue("t", page.substr(2, page.find('/') - 2));
+        name += covKeyValue("page", page);
+        name += covKeyValue("o", p.comment);
+        if (p.linescov && p.linescov[0]) name += covKeyValue("S", p.linescov);
+        std::string hier = std::string{"TOP"} + p.hier;  // vlNamep + hierp
+        if (!hier.empty() && hier[0] == '.') hier = hier.substr(1);
+        const auto it = events.find(name);
+        if (it != events.end()) {
+            it->second.second += counts[b];
+            it->second.first = covCombineHier(it->second.first, hier);
+        } else {
+            events.emplace(name, std::make_pair(hier, counts[b]));
+        }
+    }
+    for (const auto& ev : events) {
+        os << "C '" << ev.first;
+        if (!ev.second.first.empty()) os << covKeyValue("h", ev.second.first);
+        os << "' " << ev.second.second << '\n';
+    }
+    return os.good() ? VLCU_OK : fail(VLCU_E_IO, "write failed");
+}
+
+//-------------------------------------------------------------------------
+// Multi-GPU
+
+int vlcu_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(VLCU_E_ARG, "null argument");
+    std::string err;
+    if (!nccl().load(err)) return fail(VLCU_E_NCCL, err);
+    ncclUniqueId id;
+    const ncclResult_t nr = nccl().GetUniqueId(&id);
+    if (nr != ncclSuccess) return fail(VLCU_E_NCCL, nccl().GetErrorString(nr));
+    memcpy(id_out, &id, sizeof(id));
+    return VLCU_OK;
+}
+int vlcu_comm_init(vlcu_model_t* h, const void* id, int rank, int world) {
+    if (!h || !id || rank < 0 || rank >= world) return fail(VLCU_E_ARG, "bad argument");
+    std::string err;
+    if (!nccl().load(err)) return fail(VLCU_E_NCCL, err);
+    DeviceGuard guard{h->device};
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    const ncclResult_t nr = nccl().CommInitRank(&h->comm, world, uid, rank);
+    if (nr != ncclSuccess) {
+        h->comm = nullptr;
+        return fail(VLCU_E_NCCL, std::string{"ncclCommInitRank: "} + nccl().GetErrorString(nr));
+    }
+    h->commRank = rank;
+    h->commWorld = world;
+    return VLCU_OK;
+}
+int vlcu_comm_destroy(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    if (h->comm) {
+        DeviceGuard guard{h->device};
+        nccl().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    return VLCU_OK;
+}
+
+}  // extern "C"
