@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""Benchmark driver: instance-cycles/sec of batched RTL evaluation (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (this repo's CUDA evaluator)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference model on host cores)
+
+One "step" = `cycles` clock periods (2*cycles eval() calls) of every instance, fused in one
+kernel launch.  One cycle = one full period of the design clock = two evals
+(examples/make_tracing_c/sim_main.cpp:71-106).  Instances are sharded over GPUs with no
+data-path collective (weak scaling: instances per GPU fixed).
+
+Timing: W >= 3 untimed warm-up steps; K timed steps bracketed by barrier + device sync; every
+kernel is timed with CUDA events on the stream it is launched on (inside the library,
+vlcu_last_kernel_ms); L2 is flushed (256 MB memset on the same stream, outside the events)
+between timed steps; max over ranks.  `value` = whole-job instance-cycles / summed event time
+with state resident in HBM.  `e2e` = the same work through the C ABI with HOST buffers:
+per step the per-instance stimulus is copied host->device from pinned memory and signatures +
+status are copied back, all inside the timed region.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "instance-cycles/sec (batched RTL eval)"
+UNIT = "instance-cycles/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[0] scaled out: the only design whose source is in the reference tree
+    "make_tracing_c": dict(
+        design="make_tracing_c", tb="sim_main", instances=65536, cycles=8192, tb_flags=1,
+        tb_arg=(128, 0, 0, 0), rand_reset=2,
+        inputs=("in_small", "in_quad", "in_wide"),
+        note="examples/make_tracing_c top+sub, per-instance random stimulus offsets, "
+             "reset every 128 time units"),
+}
+DEFAULT_WORKLOAD = "make_tracing_c"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.samples)}
+        try:
+            sm = sorted(float(s[1]) for s in self.samples)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = max(float(s[2]) for s in self.samples)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if any(len(s) > 5 + k and s[5 + k].lower().startswith("active") for s in self.samples):
+                    out["reasons"].append(nm)
+        except Exception:
+            pass
+        return out
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def allmax(dist, x, local):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def pinned_array(abi, shape, dtype):
+    """numpy view of page-locked host memory (cudaHostAlloc through the C ABI)."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = abi.lib.vlcu_host_alloc(nbytes)
+    if not ptr:
+        raise RuntimeError("vlcu_host_alloc failed")
+    buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr, ptr
+
+
+def cpu_reference_run(wl, sample_instances, cycles, threads):
+    """Times the reference model (restated Vtop against the genuine runtime, oracle/_ref) on the
+    host cores: one instance per thread at a time, as docs/guide/verilating.rst:232-236."""
+    import oracle_util as O
+    t0 = time.perf_counter()
+    O.mtc_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+              per_instance=bool(wl["tb_flags"] & 1), reset_period=wl["tb_arg"][0], threads=threads)
+    dt = time.perf_counter() - t0
+    return sample_instances * cycles / dt, dt
+
+
+def run_reference(args, wl):
+    rank, world, local, dist = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: ~1-2 s of CPU work per step
+    cycles = min(wl["cycles"], 4096)
+    probe, _ = cpu_reference_run(wl, threads, 512, threads)
+    sample = max(threads, int(probe * 1.5 / cycles) // threads * threads)
+    for _ in range(args.warmup):
+        cpu_reference_run(wl, sample, cycles, threads)
+    t_total, units = 0.0, 0
+    for _ in range(args.steps):
+        _, dt = cpu_reference_run(wl, sample, cycles, threads)
+        t_total += dt
+        units += sample * cycles
+    value = units / t_total
+    sample_txt = f"{sample} instances x {cycles} cycles per step on {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "design": wl["design"], "note": wl["note"],
+                   "instances_per_step": sample, "cycles_per_step": cycles},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
+                         "kind": "port (restated Vtop for the design, genuine verilated runtime)",
+                         "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args, wl):
+    from verilator_b200 import abi
+    rank, world, local, dist = dist_setup(args.gpus)
+    if abi.lib.vlcu_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the evaluator has no CPU path")
+    n = args.instances or wl["instances"]
+    cycles = args.cycles or wl["cycles"]
+    evals = 2 * cycles
+    m = abi.Model(wl["design"], n, device=local, inst_base=rank * n, seed=1,
+                  rand_reset=wl["rand_reset"], msg_cap=2)
+    run_kw = dict(tb_seed=3, tb_flags=wl["tb_flags"], tb_arg=wl["tb_arg"])
+    m.run(wl["tb"], 0, flags=abi.RUNF_TB_BEGIN, **run_kw)  # initial port values
+
+    def step():
+        m.run(wl["tb"], evals, **run_kw)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    m.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier(dist)
+    m.sync()
+    launches0 = m.launch_count()
+    wall0 = time.perf_counter()
+    ev_ms = []
+    for _ in range(args.steps):
+        m.flush_l2()
+        step()
+        ev_ms.append(m.last_kernel_ms())  # synchronises on the step's stop event
+    m.sync()
+    barrier(dist)
+    wall = time.perf_counter() - wall0
+    launches = m.launch_count() - launches0
+    dev_s = allmax(dist, sum(ev_ms) / 1e3, local)
+    wall_s = allmax(dist, wall, local)
+    total_units = world * n * cycles * args.steps
+    value = total_units / dev_s
+
+    # ---- end to end through the C ABI with host buffers -------------------------------
+    ins = {}
+    for name in wl["inputs"]:
+        _, _, _, eb, elems = m.ports[name]
+        arr, _ptr = pinned_array(abi, (n, elems), {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[eb])
+        arr[:] = m.get_member(name).reshape(n, elems)
+        ins[name] = arr
+    sig_host, _ = pinned_array(abi, (n,), np.uint64)
+    st_host, _ = pinned_array(abi, (n,), abi.STATUS_DTYPE)
+    h2d = sum(a.nbytes for a in ins.values())
+    d2h = sig_host.nbytes + st_host.nbytes
+
+    def e2e_step():
+        for name, arr in ins.items():
+            p = m.ports[name][0]
+            abi._check(abi.lib.vlcu_set_input(m.h, p, arr.ctypes.data, arr.strides[0]))
+        m.run(wl["tb"], evals, **run_kw)
+        abi._check(abi.lib.vlcu_signatures(m.h, sig_host.ctypes.data))
+        abi._check(abi.lib.vlcu_status(m.h, st_host.ctypes.data))
+
+    e2e_step()
+    barrier(dist)
+    m.sync()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    m.sync()
+    barrier(dist)
+    e2e_s = allmax(dist, time.perf_counter() - t0, local)
+    e2e_value = world * n * cycles * e2e_steps / e2e_s
+
+    clocks = sampler.finish() if rank == 0 else None
+    if rank != 0:
+        m.close()
+        return
+
+    # ---- roofline of the dominant kernel (vlcu_k_run) ------------------------------------
+    peak, peak_src = peaks()
+    b_alg = 2 * (2 * m.state_bytes) + 2 * (m.in_bytes + m.out_bytes)  # SURVEY 8d, bytes/instance-cycle
+    mean_ms = sum(ev_ms) / len(ev_ms)
+    achieved = n * cycles * b_alg / (mean_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------
+    threads = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu_baseline:
+        probe, _ = cpu_reference_run(wl, threads, 512, threads)
+        c_cycles = min(cycles, 4096)
+        sample = max(threads, int(probe * 12 / c_cycles) // threads * threads)
+        cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": threads,
+               "kind": "port (restated Vtop for the design, genuine verilated runtime)",
+               "sample": f"{sample} instances x {c_cycles} cycles, {cpu_dt:.1f} s, "
+                         f"{threads} threads, one instance per thread at a time"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "design": wl["design"], "note": wl["note"],
+                   "instances_per_gpu": n, "cycles_per_step": cycles, "evals_per_step": evals,
+                   "l2": "flushed between timed steps (256 MB memset, outside the CUDA events)",
+                   "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
+                   "wall_ms_per_step_incl_flush": 1e3 * wall_s / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "vlcu_k_run", "algorithmic_bytes_per_instance_cycle": b_alg,
+                     "note": "B_alg = 2*(2*S_persist) + 2*(S_in+S_out); the K-cycle fused kernel keeps "
+                             "state on chip, so real DRAM traffic is far below B_alg (see DESIGN.md)"},
+        "cpu_baseline": cpu,
+    }))
+    m.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--instances", type=int, default=0, help="instances per GPU")
+    ap.add_argument("--cycles", type=int, default=0, help="clock cycles per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

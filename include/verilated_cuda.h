@@ -109,13 +109,18 @@ VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, uint32_t* covp, QData newData, QD
         covp[2 * i + static_cast<int>((newData >> i) & 1)] += static_cast<uint32_t>((chg >> i) & 1);
     }
 }
+// NOTE (bug-compatible): the host runtime's inner loop runs j up to width - 32*w, i.e. past
+// 31 for every word but the last, and shifts a 32-bit word by j.  That is undefined in C++;
+// as built by the reference's default flags (scalar x86 `shr`, count taken mod 32) the low
+// words are therefore counted again into the counters of higher bits.  Reproduced here with
+// an explicit (j & 31) so the device gives the same counts as the reference binary.
 VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, uint32_t* covp, WDataInP newData,
                                     WDataInP oldData) {
     for (int w = 0; w < VL_WORDS_I(width); ++w) {
         const EData chg = newData[w] ^ oldData[w];
         if (!chg) continue;
         for (int j = 0; j < width - w * 32; ++j) {
-            covp[(w * 32 + j) * 2 + ((newData[w] >> j) & 1)] += (chg >> j) & 1;
+            covp[(w * 32 + j) * 2 + ((newData[w] >> (j & 31)) & 1)] += (chg >> (j & 31)) & 1;
         }
     }
 }

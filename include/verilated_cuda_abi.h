@@ -133,6 +133,11 @@ int vlcu_device_count(void);
 int vlcu_design_count(void);
 const char* vlcu_design_name(int index);
 
+/* Page-locked host memory for the buffers handed to vlcu_set_input / vlcu_get_output / vlcu_run
+   (plain malloc'ed memory works too, pinned memory makes the copies asynchronous DMA) */
+void* vlcu_host_alloc(size_t bytes);
+void vlcu_host_free(void* ptr);
+
 /* ---- model life cycle -------------------------------------------------- */
 /* n_instances models of `design` on CUDA device `device`; instance i of this shard has global
    index inst_base+i and PRNG seed (seed_base ^ global index); rand_reset as randReset();
@@ -177,6 +182,8 @@ int vlcu_eval(vlcu_model_t* h); /* one eval() per instance */
 int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* desc); /* n_evals fused in one kernel */
 int vlcu_final(vlcu_model_t* h);
 int vlcu_sync(vlcu_model_t* h);
+/* Benchmark hygiene: overwrite a scratch buffer larger than the 126 MB L2 on the model's stream */
+int vlcu_flush_l2(vlcu_model_t* h);
 /* Device time of the last vlcu_eval/vlcu_run kernel (CUDA events on the model's stream) */
 int vlcu_last_kernel_ms(vlcu_model_t* h, float* ms);
 uint64_t vlcu_launch_count(const vlcu_model_t* h); /* kernels launched so far by this model */

@@ -71,9 +71,9 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
     contextp->randSeed(static_cast<int>(p.seedBase ^ (p.instBase + i)));
     contextp->traceEverOn(true);
     contextp->fatalOnError(false);
-    if (p.tracePlusarg) {
+    {  // sim_main.cpp:49  contextp->commandArgs(argc, argv)
         const char* argv[] = {"oracle", "+trace"};
-        contextp->commandArgs(2, argv);
+        contextp->commandArgs(p.tracePlusarg ? 2 : 1, argv);
     }
     const std::unique_ptr<Vtop> top{new Vtop{contextp.get(), "TOP"}};
     std::unique_ptr<VerilatedVcdC> tfp;

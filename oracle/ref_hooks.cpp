@@ -60,8 +60,11 @@ void vl_stop(const char* filename, int linenum, const char* hier) VL_MT_UNSAFE {
     }
 }
 void vl_fatal(const char* filename, int linenum, const char* hier, const char* msg) VL_MT_UNSAFE {
-    (void)filename, (void)hier, (void)msg;
+    (void)hier;
     VerilatedContext* const ctxp = Verilated::threadContextp();
+    if (t_capturep) {
+        t_capturep->append(std::string{"%Fatal: "} + filename + ":" + std::to_string(linenum) + ": " + msg + "\n");
+    }
     ctxp->gotError(true);
     ctxp->gotFinish(true);
     if (t_eventsp) {

@@ -28,7 +28,10 @@ def abi():
 
 def check_status(got, want):
     for f in STATUS_FIELDS:
-        assert (got[f] == want[f]).all(), (f, got[f][:8], want[f][:8])
+        g = got[f]
+        if f == "status":  # the oracle's console is unbounded: it has no "log overflowed" flag
+            g = g & ~np.uint32(32)
+        assert (g == want[f]).all(), (f, g[:8], want[f][:8])
 
 
 @pytest.mark.parametrize("design", ["make_tracing_c", "make_tracing_c_cov"])

@@ -61,6 +61,8 @@ SIGNATURES = {
     "vlcu_device_count": (c_i32, []),
     "vlcu_design_count": (c_i32, []),
     "vlcu_design_name": (c_cp, [c_i32]),
+    "vlcu_host_alloc": (c_vp, [ctypes.c_size_t]),
+    "vlcu_host_free": (None, [c_vp]),
     "vlcu_create": (_H, [c_cp, c_u64, c_i32, c_u64, c_u64, c_i32, c_u32, c_cp]),
     "vlcu_destroy": (None, [_H]),
     "vlcu_reset": (c_i32, [_H]),
@@ -90,6 +92,7 @@ SIGNATURES = {
     "vlcu_run": (c_i32, [_H, ctypes.POINTER(RunDesc)]),
     "vlcu_final": (c_i32, [_H]),
     "vlcu_sync": (c_i32, [_H]),
+    "vlcu_flush_l2": (c_i32, [_H]),
     "vlcu_last_kernel_ms": (c_i32, [_H, ctypes.POINTER(ctypes.c_float)]),
     "vlcu_launch_count": (c_u64, [_H]),
     "vlcu_status": (c_i32, [_H, c_vp]),
@@ -180,10 +183,10 @@ class Model:
     # -- ports ---------------------------------------------------------------
     def _as_port_array(self, info, values):
         _, _, _, eb, elems = info[:5]
-        arr = np.ascontiguousarray(values, dtype=_ELEM_DTYPE[eb])
-        if arr.ndim == 0 or (arr.ndim == 1 and elems > 1 and arr.shape[0] == elems):
-            return arr.reshape(1, elems), 0  # broadcast
-        arr = arr.reshape(self.n, elems)
+        arr = np.asarray(values, dtype=_ELEM_DTYPE[eb])
+        if arr.size == elems and self.n != 1:
+            return np.ascontiguousarray(arr.reshape(1, elems)), 0  # one value for all instances
+        arr = np.ascontiguousarray(arr.reshape(self.n, elems))
         return arr, eb * elems
 
     def set_input(self, name, values):
@@ -257,6 +260,9 @@ class Model:
 
     def sync(self):
         _check(lib.vlcu_sync(self.h))
+
+    def flush_l2(self):
+        _check(lib.vlcu_flush_l2(self.h))
 
     def last_kernel_ms(self):
         ms = ctypes.c_float()

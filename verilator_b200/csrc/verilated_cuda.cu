@@ -142,6 +142,7 @@ struct vlcu_model final {
     // Reusable device staging
     uint8_t* dStage = nullptr;
     size_t stageBytes = 0;
+    uint8_t* dFlush = nullptr;  // L2 flush scratch (vlcu_flush_l2)
 };
 
 namespace {
@@ -402,6 +403,19 @@ const char* vlcu_design_name(int index) {
     return registry()[index]->info().name;
 }
 
+void* vlcu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        failCuda(e, "cudaHostAlloc");
+        return nullptr;
+    }
+    return p;
+}
+void vlcu_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, uint64_t inst_base,
                           uint64_t seed_base, int rand_reset, uint32_t msg_cap,
                           const char* plusargs) {
@@ -513,6 +527,7 @@ void vlcu_destroy(vlcu_model_t* h) {
     cudaFree(h->dEvalsDone);
     cudaFree(h->dCovSums);
     cudaFree(h->dStage);
+    cudaFree(h->dFlush);
     if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->evStop) cudaEventDestroy(h->evStop);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -731,6 +746,15 @@ int vlcu_sync(vlcu_model_t* h) {
     if (!h) return fail(VLCU_E_ARG, "null model");
     DeviceGuard guard{h->device};
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+int vlcu_flush_l2(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    DeviceGuard guard{h->device};
+    const size_t bytes = size_t{256} << 20;  // > 126 MB L2
+    if (!h->dFlush) CUDA_TRY(cudaMalloc(&h->dFlush, bytes));
+    CUDA_TRY(cudaMemsetAsync(h->dFlush, static_cast<int>(h->launches & 0xff), bytes, h->stream));
     return VLCU_OK;
 }
 
