@@ -156,6 +156,10 @@ uint32_t vlcu_out_words(const vlcu_model_t* h);
 uint32_t vlcu_in_bytes(const vlcu_model_t* h); /* S_in  (C storage bytes of input ports) */
 uint32_t vlcu_out_bytes(const vlcu_model_t* h); /* S_out */
 uint32_t vlcu_trace_record_bytes(const vlcu_model_t* h);
+/* Persistent bytes one triggered eval reads / writes (S_state_rd, S_state_wr of the roofline
+   model in DESIGN.md); equal to vlcu_state_bytes() when the design does not say */
+uint32_t vlcu_touched_read_bytes(const vlcu_model_t* h);
+uint32_t vlcu_touched_write_bytes(const vlcu_model_t* h);
 
 /* ---- ports ---------------------------------------------------------------- */
 int vlcu_port_count(const vlcu_model_t* h);

@@ -85,6 +85,9 @@ struct VlcuDesignInfo final {
     uint32_t stateBytes;  // S_persist: bytes per instance in the SoA block
     uint32_t inWords, outWords;  // 32-bit words per stimulus / observation row
     uint32_t inBytes, outBytes;  // S_in / S_out in C storage bytes (SURVEY 8d B_alg)
+    // Persistent bytes one triggered eval reads / writes (SURVEY 8d S_state_rd / S_state_wr,
+    // "touched memory words only"); 0 = the whole state (stateBytes)
+    uint32_t touchedReadBytes, touchedWriteBytes;
     const VlcuCoverPoint* coverPoints;
     uint32_t nCoverPoints;
     uint32_t coverageSoaOffset;  // of __Vcoverage, if nCoverPoints

@@ -90,3 +90,47 @@ def mtc_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, stop_on_finish=False,
     if not obs_evals:
         r.obs = None
     return r
+
+
+# ---- rv32_soc (oracle/models/rv32i) ------------------------------------------------------
+def _rv32():
+    lib = ref()
+    if not getattr(lib, "_rv32_ready", False):
+        lib.vlref_rv32_run.restype = i32
+        lib.vlref_rv32_run.argtypes = [u64, u64, u64, i32, u64, u64, u32, vp, vp, u64, vp, vp, vp, vp, vp, i32]
+        lib.vlref_rv32_gen_program.restype = None
+        lib.vlref_rv32_gen_program.argtypes = [u64, vp]
+        lib._rv32_ready = True
+    return lib
+
+
+def rv32_gen_program(seed):
+    out = np.zeros(1024, dtype=np.uint32)
+    _rv32().vlref_rv32_gen_program(seed, out.ctypes.data)
+    return out
+
+
+class Rv32Result:
+    pass
+
+
+def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_time=0, mem_images=None,
+             obs_evals=0, want_mem=False, threads=1):
+    r = Rv32Result()
+    r.obs = np.zeros((max(obs_evals, 1), 8, n), dtype=np.uint32)
+    r.sigs = np.zeros(n, dtype=np.uint64)
+    r.times = np.zeros(n, dtype=np.uint64)
+    r.regs = np.zeros((n, 32), dtype=np.uint32)
+    r.mem = np.zeros((n, 1024), dtype=np.uint32) if want_mem else None
+    r.scalars = np.zeros((n, 8), dtype=np.uint32)  # pc insn ld_addr instret state trap retired clk
+    if mem_images is not None:
+        mem_images = np.ascontiguousarray(mem_images, dtype=np.uint32).reshape(n, 1024)
+    rc = _rv32().vlref_rv32_run(
+        n, inst_base, seed, rand_reset, n_evals, tb_seed, reset_time,
+        mem_images.ctypes.data if mem_images is not None else None,
+        r.obs.ctypes.data if obs_evals else None, obs_evals, r.sigs.ctypes.data, r.times.ctypes.data,
+        r.regs.ctypes.data, r.mem.ctypes.data if want_mem else None, r.scalars.ctypes.data, threads)
+    assert rc == 0
+    if not obs_evals:
+        r.obs = None
+    return r

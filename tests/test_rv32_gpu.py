@@ -1,0 +1,131 @@
+"""Parity of the batched CUDA evaluator with the oracle for the RV32I core (BASELINE.json
+config 2 workload: 65,536 instances each running a random-seeded synthetic program), through
+the C ABI.  Bit-exact: all top-level ports after every eval, register file, memory, context."""
+import numpy as np
+import pytest
+
+import oracle_util as O
+import rv32_iss as ISS
+
+pytestmark = pytest.mark.gpu
+SCALARS = ["rv32_soc__DOT__pc", "rv32_soc__DOT__insn", "rv32_soc__DOT__ld_addr",
+           "rv32_soc__DOT__instret", "rv32_soc__DOT__state", "trap", "retired", "clk"]
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from verilator_b200 import abi
+    assert abi.lib.vlcu_device_count() > 0, "no CUDA device: GPU tests need a B200"
+    assert "rv32i" in abi.designs()
+    return abi
+
+
+def check_final_state(m, want):
+    assert (m.get_member("rv32_soc__DOT__regs") == want.regs).all()
+    for k, name in enumerate(SCALARS):
+        assert (m.get_member(name).astype(np.uint32) == want.scalars[:, k]).all(), name
+    if want.mem is not None:
+        assert (m.get_member("rv32_soc__DOT__mem") == want.mem).all()
+
+
+@pytest.mark.parametrize("rand_reset,reset_time", [(2, 0), (0, 0), (2, 5)])
+def test_ports_every_eval_match_oracle(abi, rand_reset, reset_time):
+    n, evals = 200, 1200
+    want = O.rv32_run(n, evals, seed=11, rand_reset=rand_reset, tb_seed=2024, reset_time=reset_time,
+                      obs_evals=evals, want_mem=True)
+    with abi.Model("rv32i", n, seed=11, rand_reset=rand_reset) as m:
+        obs, _ = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, obs_evals=evals, tb_seed=2024,
+                       tb_arg=(reset_time, 0, 0, 0))
+        assert (obs == want.obs).all()
+        assert (m.signatures() == want.sigs).all()
+        assert (m.status()["time"] == want.times).all()
+        check_final_state(m, want)
+
+
+def test_x_initial_reset_of_arrays_and_scalars(abi):
+    want = O.rv32_run(300, 0, inst_base=77, seed=123, rand_reset=2, want_mem=True)
+    with abi.Model("rv32i", 300, inst_base=77, seed=123, rand_reset=2) as m:
+        assert (m.get_member("rv32_soc__DOT__regs") == want.regs).all()
+        assert (m.get_member("rv32_soc__DOT__pc") == want.scalars[:, 0]).all()
+        # before the testbench loads a program the memory holds its x-initial value
+        mem = m.get_member("rv32_soc__DOT__mem")
+        assert (mem == mem[:, :1]).all() and len(np.unique(mem[:, 0])) == 300
+
+
+def test_host_loaded_memory_images_and_iss(abi):
+    """Programs supplied by the host (vlcu_set_member on the instance-major memory), including
+    illegal instructions / misaligned / out-of-range accesses that must trap."""
+    rng = np.random.default_rng(8)
+    n, evals = 96, 500
+    images = rng.integers(0, 1 << 32, size=(n, 1024), dtype=np.uint64).astype(np.uint32)
+    for i in range(n):
+        good = O.rv32_gen_program(900 + i)
+        sel = rng.random(1024) < 0.85
+        images[i, sel] = good[sel]
+    want = O.rv32_run(n, evals, seed=4, rand_reset=2, mem_images=images, obs_evals=evals, want_mem=True)
+    with abi.Model("rv32i", n, seed=4, rand_reset=2) as m:
+        regs0 = m.get_member("rv32_soc__DOT__regs")
+        m.set_member("rv32_soc__DOT__mem", images)
+        assert (m.get_member("rv32_soc__DOT__mem") == images).all()
+        obs, _ = m.run("rv32_host", evals, flags=abi.RUNF_TB_BEGIN, obs_evals=evals)
+        assert (obs == want.obs).all()
+        check_final_state(m, want)
+        assert m.get_output("trap").sum() > 0
+        # and straight against the instruction-set simulator
+        regs, mem, pc = m.get_member("rv32_soc__DOT__regs"), m.get_member("rv32_soc__DOT__mem"), \
+            m.get_member("rv32_soc__DOT__pc")
+        for i in range(0, n, 7):
+            sim = ISS.Rv32(images[i], regs0[i])
+            sim.run(evals)
+            assert sim.regs[1:] == regs[i, 1:].tolist() and sim.mem == mem[i].tolist()
+            assert sim.pc == int(pc[i])
+
+
+def test_split_runs_and_snapshot(abi):
+    n = 130
+    with abi.Model("rv32i", n, seed=6, rand_reset=2) as a, abi.Model("rv32i", n, seed=6, rand_reset=2) as b:
+        a.run("rv32_rand", 900, flags=abi.RUNF_TB_BEGIN, tb_seed=31)
+        b.run("rv32_rand", 7, flags=abi.RUNF_TB_BEGIN, tb_seed=31)
+        b.run("rv32_rand", 500, tb_seed=31)
+        b.run("rv32_rand", 393, tb_seed=31)
+        assert (a.signatures() == b.signatures()).all()
+        assert (a.get_member("rv32_soc__DOT__mem") == b.get_member("rv32_soc__DOT__mem")).all()
+        snap = a.snapshot(77)
+        assert (snap == b.snapshot(77)).all()
+        assert (a.record_member(snap, "rv32_soc__DOT__mem") == a.get_member("rv32_soc__DOT__mem")[77]).all()
+        assert (a.record_member(snap, "rv32_soc__DOT__regs") == a.get_member("rv32_soc__DOT__regs")[77]).all()
+
+
+def test_trace_samples_of_selected_instances(abi):
+    """Waveform sampling: full-state records of a few instances after every eval."""
+    n, evals = 300, 64
+    samples = [3, 150, 299]
+    want = O.rv32_run(n, evals, seed=2, rand_reset=2, tb_seed=5, obs_evals=evals)
+    with abi.Model("rv32i", n, seed=2, rand_reset=2) as m:
+        _, trace = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=5, samples=samples,
+                         trace_evals=evals)
+        for e in range(evals):
+            for k, inst in enumerate(samples):
+                rec = trace[e, k]
+                t = int(np.frombuffer(rec[:8].tobytes(), dtype=np.uint64)[0])
+                assert t == e + 1
+                body = rec[abi.TRACE_HDR:]
+                assert int(m.record_member(body, "mem_addr")) == int(want.obs[e, 3, inst])
+                assert int(m.record_member(body, "retired")) == int(want.obs[e, 7, inst])
+
+
+def test_full_batch_signatures_sample_against_oracle(abi):
+    """BASELINE config-2 size.  Every instance runs a different program: signatures are all
+    distinct; contiguous samples from both ends of the batch are checked against the oracle."""
+    n, evals = 65536, 1024
+    with abi.Model("rv32i", n, seed=1, rand_reset=2) as m:
+        m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=9)
+        sig = m.signatures()
+        retired = m.get_output("retired")
+        assert m.get_output("trap").sum() == 0
+    assert len(np.unique(sig)) == n
+    assert retired.min() > 100
+    for base in (0, 32768, 65536 - 48):
+        want = O.rv32_run(48, evals, inst_base=base, seed=1, rand_reset=2, tb_seed=9, threads=4)
+        assert (sig[base:base + 48] == want.sigs).all()
+        assert (retired[base:base + 48] == want.scalars[:, 6]).all()

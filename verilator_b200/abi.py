@@ -74,6 +74,8 @@ SIGNATURES = {
     "vlcu_in_bytes": (c_u32, [_H]),
     "vlcu_out_bytes": (c_u32, [_H]),
     "vlcu_trace_record_bytes": (c_u32, [_H]),
+    "vlcu_touched_read_bytes": (c_u32, [_H]),
+    "vlcu_touched_write_bytes": (c_u32, [_H]),
     "vlcu_port_count": (c_i32, [_H]),
     "vlcu_port_info": (c_i32, [_H, c_i32, ctypes.POINTER(PortInfo)]),
     "vlcu_port_index": (c_i32, [_H, c_cp]),
@@ -151,6 +153,8 @@ class Model:
         self.out_words = lib.vlcu_out_words(self.h)
         self.in_bytes = lib.vlcu_in_bytes(self.h)
         self.out_bytes = lib.vlcu_out_bytes(self.h)
+        self.touched_read_bytes = lib.vlcu_touched_read_bytes(self.h)
+        self.touched_write_bytes = lib.vlcu_touched_write_bytes(self.h)
         self.ports = {}
         for p in range(lib.vlcu_port_count(self.h)):
             info = PortInfo()

@@ -165,7 +165,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
     static const std::vector<VlcuMemberDesc> members = makeMembers<Vtop__cuda>(false);
     static const VlcuDesignInfo s = {
         "make_tracing_c", "top", members.data(), static_cast<uint32_t>(members.size()),
-        kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes,
+        kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes, 0, 0,
         nullptr, 0, 0,
         kMessages, 4, kPlusargs, 1};
     return s;
@@ -174,7 +174,7 @@ const VlcuDesignInfo& Vtop_cov__cuda::info() {
     static const std::vector<VlcuMemberDesc> members = makeCovMembers();
     static const VlcuDesignInfo s = {
         "make_tracing_c_cov", "top", members.data(), static_cast<uint32_t>(members.size()),
-        kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes,
+        kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes, 0, 0,
         coverTables().points.data(), static_cast<uint32_t>(coverTables().points.size()),
         OFF___Vcoverage,
         kMessages, 4, kPlusargs, 1};

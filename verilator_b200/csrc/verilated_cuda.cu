@@ -556,6 +556,14 @@ uint32_t vlcu_in_words(const vlcu_model_t* h) { return h ? h->infop->inWords : 0
 uint32_t vlcu_out_words(const vlcu_model_t* h) { return h ? h->infop->outWords : 0; }
 uint32_t vlcu_in_bytes(const vlcu_model_t* h) { return h ? h->infop->inBytes : 0; }
 uint32_t vlcu_out_bytes(const vlcu_model_t* h) { return h ? h->infop->outBytes : 0; }
+uint32_t vlcu_touched_read_bytes(const vlcu_model_t* h) {
+    if (!h) return 0;
+    return h->infop->touchedReadBytes ? h->infop->touchedReadBytes : h->infop->stateBytes;
+}
+uint32_t vlcu_touched_write_bytes(const vlcu_model_t* h) {
+    if (!h) return 0;
+    return h->infop->touchedWriteBytes ? h->infop->touchedWriteBytes : h->infop->stateBytes;
+}
 uint32_t vlcu_trace_record_bytes(const vlcu_model_t* h) {
     return h ? h->infop->stateBytes + VLCU_TRACE_HDR : 0;
 }
