@@ -359,6 +359,22 @@ struct VlcuGlobalArray final {
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
+// A small array that is indexed with run-time values (a register file, coverage counters).
+// Such an array cannot live in registers; if it were a plain member of the per-thread model
+// struct, nvcc would keep the WHOLE struct in local memory with it.  The emitter therefore
+// declares the storage separately (T_Design::Locals, thread-private local memory, L1 resident)
+// and gives the model struct only this handle, so every other member is promoted to a register.
+template <typename T_Value, size_t N_Depth>
+struct VlcuLocalArray final {
+    T_Value* m_basep;
+    VLCU_HD void bind(T_Value* storagep) { m_basep = storagep; }
+    VLCU_HD T_Value& operator[](size_t index) { return m_basep[index]; }
+    VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index]; }
+    VLCU_HD constexpr size_t size() const { return N_Depth; }
+    VLCU_HD operator T_Value*() { return m_basep; }
+    VLCU_HD operator const T_Value*() const { return m_basep; }
+};
+
 // Everything a kernel needs to find one model's data
 struct VlcuModelDev final {
     VlcuState state;

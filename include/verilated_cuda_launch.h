@@ -8,6 +8,8 @@
 // A T_Design provides (all static, __device__):
 //     typedef ... Root;                      the per-instance model image
 //                                            (Vtop___024root, V3EmitCHeaders.cpp:73-143)
+//     typedef ... Locals;                    storage of run-time indexed small arrays
+//     bind(Root&, Locals&, VlcuState, inst)  attach array handles (local / HBM resident)
 //     load / store(Root&, VlcuState, inst)   SoA <-> Root for all persistent members
 //     load_inputs_row / store_outputs_row    packed 32-bit port rows (stimulus / observation)
 //     outputs_sig(Root, sig)                 fold the output ports into a signature
@@ -30,7 +32,7 @@
 #include <string.h>
 
 #ifndef VLCU_BLOCK
-#define VLCU_BLOCK 128  // threads (= instances) per CTA
+#define VLCU_BLOCK 64  // threads (= instances) per CTA: 65,536 instances = 1024 CTAs = 6.9 per SM
 #endif
 
 //=========================================================================
@@ -80,7 +82,8 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
     typename T_Design::Root root;
-    T_Design::bind(root, m.state, inst);
+    typename T_Design::Locals locals;
+    T_Design::bind(root, locals, m.state, inst);
     T_Design::ctor_var_reset(&root, ctx);
     T_Design::store(root, m.state, inst);
     vlcu_ctx_store(ctx);
@@ -92,9 +95,10 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_run(VlcuModelDev m, VlcuRun
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (inst >= m.n) return;
     typename T_Design::Root root;
+    typename T_Design::Locals locals;
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
-    T_Design::bind(root, m.state, inst);
+    T_Design::bind(root, locals, m.state, inst);
     T_Design::load(root, m.state, inst);
     uint64_t sig = r.sigs[inst];
     if (r.flags & VLCU_RUN_TB_BEGIN) {
@@ -138,9 +142,10 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_final(VlcuModelDev m) {
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (inst >= m.n) return;
     typename T_Design::Root root;
+    typename T_Design::Locals locals;
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
-    T_Design::bind(root, m.state, inst);
+    T_Design::bind(root, locals, m.state, inst);
     T_Design::load(root, m.state, inst);
     T_Design::eval_final(&root, ctx);
     T_Design::store(root, m.state, inst);

@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libverilated_cuda.so")
+# VLCU_LIB: experiments only (e.g. a build with another block size); default is the in-tree build
+LIB_PATH = os.environ.get("VLCU_LIB") or os.path.join(_HERE, "libverilated_cuda.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -47,7 +47,7 @@ struct VTOP_ROOT final {
     CData /*1:0*/ top__DOT____Vtogcov__in_small;
     CData /*0:0*/ top__DOT__sub__DOT____Vtogcov__clk;
     CData /*0:0*/ top__DOT__sub__DOT____Vtogcov__reset_l;
-    uint32_t __Vcoverage[527];
+    VlcuLocalArray<uint32_t, 527> __Vcoverage;  // run-time indexed: storage in Locals
 #endif
     // Scheduling temporaries (noReset; never stored to HBM)
     VlUnpacked<QData /*63:0*/, 1> __VstlTriggered;
@@ -123,7 +123,18 @@ struct VTOP final {
         kCoverBins = VTOP_COVERAGE ? 527 : 0,
     };
 
-    VLCU_D static void bind(Root&, const VlcuState&, uint64_t) {}  // no HBM-resident arrays
+    struct Locals final {
+#if VTOP_COVERAGE
+        uint32_t __Vcoverage[527];
+#endif
+    };
+    VLCU_D static void bind(Root& s, Locals& l, const VlcuState&, uint64_t) {
+#if VTOP_COVERAGE
+        s.__Vcoverage.bind(l.__Vcoverage);
+#else
+        (void)s, (void)l;
+#endif
+    }
 
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
         s.in_quad = st.ld<QData>(OFF_in_quad, i);
@@ -504,8 +515,8 @@ struct VTOP final {
         IData /*31:0*/ __Vdly__top__DOT__sub__DOT__count_c;
         __Vdly__top__DOT__sub__DOT__count_c = vlSelfRef.top__DOT__sub__DOT__count_c;
 #if VTOP_COVERAGE
-        if ((3U == vlSelfRef.top__DOT__sub__DOT__count_c)) ++(vlSelf->__Vcoverage[526]);  // cover property
-        ++(vlSelf->__Vcoverage[525]);  // sub.v:34 block
+        if ((3U == vlSelfRef.top__DOT__sub__DOT__count_c)) ++(vlSelfRef.__Vcoverage[526]);  // cover property
+        ++(vlSelfRef.__Vcoverage[525]);  // sub.v:34 block
 #endif
         if (VL_UNLIKELY(((1U & (~((~(IData)(vlSelfRef.reset_l))
                                   | (0x00000064U > vlSelfRef.top__DOT__sub__DOT__count_c))))))) {
@@ -514,29 +525,29 @@ struct VTOP final {
             VLCU_STOP(vlCtx, 35, false);
         }
 #if VTOP_COVERAGE
-        ++(vlSelf->__Vcoverage[520]);  // sub.v:15 block
+        ++(vlSelfRef.__Vcoverage[520]);  // sub.v:15 block
 #endif
         if (vlSelfRef.reset_l) {
 #if VTOP_COVERAGE
-            ++(vlSelf->__Vcoverage[522]);  // sub.v:22 else
+            ++(vlSelfRef.__Vcoverage[522]);  // sub.v:22 else
 #endif
             __Vdly__top__DOT__sub__DOT__count_c
                 = ((IData)(1U) + vlSelfRef.top__DOT__sub__DOT__count_c);
             if ((3U <= vlSelfRef.top__DOT__sub__DOT__count_c)) {
 #if VTOP_COVERAGE
-                ++(vlSelf->__Vcoverage[523]);  // sub.v:24 if
+                ++(vlSelfRef.__Vcoverage[523]);  // sub.v:24 if
 #endif
                 vlCtx.writef(2);  // "*-* All Finished *-*\n"
                 VLCU_FINISH(vlCtx, 28);
             }
 #if VTOP_COVERAGE
             else {
-                ++(vlSelf->__Vcoverage[524]);  // sub.v:24 else
+                ++(vlSelfRef.__Vcoverage[524]);  // sub.v:24 else
             }
 #endif
         } else {
 #if VTOP_COVERAGE
-            ++(vlSelf->__Vcoverage[521]);  // sub.v:16 if
+            ++(vlSelfRef.__Vcoverage[521]);  // sub.v:16 if
 #endif
             __Vdly__top__DOT__sub__DOT__count_c = 0U;
         }

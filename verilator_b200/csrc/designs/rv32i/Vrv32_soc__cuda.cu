@@ -19,7 +19,7 @@ struct Vrv32_soc___024root final {
     IData /*31:0*/ rv32_soc__DOT__insn;
     IData /*31:0*/ rv32_soc__DOT__ld_addr;
     IData /*31:0*/ rv32_soc__DOT__instret;
-    VlUnpacked<IData /*31:0*/, 32> rv32_soc__DOT__regs;
+    VlcuLocalArray<IData /*31:0*/, 32> rv32_soc__DOT__regs;  // run-time indexed: storage in Locals
     // 4 KB per instance: stays in HBM, instance-major
     VlcuGlobalArray<IData /*31:0*/, 1024> rv32_soc__DOT__mem;
     CData /*0:0*/ clk;
@@ -73,7 +73,11 @@ struct Vrv32_soc__cuda final {
         kTouchedWriteBytes = 3 * 4 + 2 + 4 + 20,
     };
 
-    VLCU_D static void bind(Root& s, const VlcuState& st, uint64_t i) {
+    struct Locals final {
+        IData rv32_soc__DOT__regs[32];
+    };
+    VLCU_D static void bind(Root& s, Locals& l, const VlcuState& st, uint64_t i) {
+        s.rv32_soc__DOT__regs.bind(l.rv32_soc__DOT__regs);
         s.rv32_soc__DOT__mem.bind(st, OFF_mem, i);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
