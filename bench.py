@@ -253,6 +253,9 @@ def run_ours(args, wl):
     h2d = sum(a.nbytes for a in ins.values()) + (images.nbytes if images is not None else 0)
     d2h = sig_host.nbytes + st_host.nbytes + (regs_host.nbytes if images is not None else 0)
     e2e_tb = "rv32_host" if images is not None else wl["tb"]
+    # rv32i: one e2e step = one fuzz round: new program images from the host, reset, run
+    e2e_flags = abi.RUNF_TB_BEGIN if images is not None else 0
+    e2e_kw = dict(run_kw, tb_flags=1) if images is not None else run_kw
 
     def e2e_step():
         for name, arr in ins.items():
@@ -261,7 +264,7 @@ def run_ours(args, wl):
         if images is not None:
             mi = m.members["rv32_soc__DOT__mem"][0]
             abi._check(abi.lib.vlcu_set_member(m.h, mi, images.ctypes.data, images.strides[0]))
-        m.run(e2e_tb, evals, **run_kw)
+        m.run(e2e_tb, evals, flags=e2e_flags, **e2e_kw)
         abi._check(abi.lib.vlcu_signatures(m.h, sig_host.ctypes.data))
         abi._check(abi.lib.vlcu_status(m.h, st_host.ctypes.data))
         if images is not None:

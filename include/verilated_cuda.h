@@ -375,6 +375,27 @@ struct VlcuLocalArray final {
     VLCU_HD operator const T_Value*() const { return m_basep; }
 };
 
+// Threads (= instances) per CTA of every design kernel.  65,536 instances = 1024 CTAs = 6.9 per
+// SM, all co-resident (one wave); small CTAs keep the tail short when instances stop early.
+#ifndef VLCU_BLOCK
+#define VLCU_BLOCK 64
+#endif
+
+// The same kind of array (small, run-time indexed, private to an instance) kept in SHARED
+// memory instead: the emitter declares `T_Value name[N_Depth][VLCU_BLOCK]` in T_Design::Shared
+// (one per CTA) and element i of this thread's instance lives at [i][threadIdx.x].  The bank is
+// threadIdx.x % 32 whatever the index, so a warp whose lanes index different elements (32
+// instances reading 32 different RISC-V registers) is served in ONE conflict-free pass, where the
+// local-memory form needs up to 32 L1 sectors.
+template <typename T_Value, size_t N_Depth>
+struct VlcuSharedArray final {
+    T_Value* m_basep;  // &storage[0][threadIdx.x]
+    VLCU_HD void bind(T_Value (*storagep)[VLCU_BLOCK], unsigned lane) { m_basep = &storagep[0][lane]; }
+    VLCU_HD T_Value& operator[](size_t index) { return m_basep[index * VLCU_BLOCK]; }
+    VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index * VLCU_BLOCK]; }
+    VLCU_HD constexpr size_t size() const { return N_Depth; }
+};
+
 // Everything a kernel needs to find one model's data
 struct VlcuModelDev final {
     VlcuState state;

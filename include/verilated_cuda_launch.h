@@ -8,8 +8,9 @@
 // A T_Design provides (all static, __device__):
 //     typedef ... Root;                      the per-instance model image
 //                                            (Vtop___024root, V3EmitCHeaders.cpp:73-143)
-//     typedef ... Locals;                    storage of run-time indexed small arrays
-//     bind(Root&, Locals&, VlcuState, inst)  attach array handles (local / HBM resident)
+//     typedef ... Locals;                    per-thread storage of run-time indexed small arrays
+//     typedef ... Shared;                    per-CTA (shared memory) storage of the same kind
+//     bind(Root&, Locals&, Shared&, VlcuState, inst)   attach array handles (local/shared/HBM)
 //     load / store(Root&, VlcuState, inst)   SoA <-> Root for all persistent members
 //     load_inputs_row / store_outputs_row    packed 32-bit port rows (stimulus / observation)
 //     outputs_sig(Root, sig)                 fold the output ports into a signature
@@ -30,10 +31,6 @@
 
 #include <cuda_runtime.h>
 #include <string.h>
-
-#ifndef VLCU_BLOCK
-#define VLCU_BLOCK 64  // threads (= instances) per CTA: 65,536 instances = 1024 CTAs = 6.9 per SM
-#endif
 
 //=========================================================================
 // Built-in testbenches usable with any design
@@ -72,9 +69,17 @@ struct VlcuTbTrace final {
 //=========================================================================
 // Kernels
 
+// Resident CTAs per SM the register allocation must allow: 7 x 64 threads x 148 SMs = 66,304
+// >= 65,536 instances (BASELINE.json config 2), i.e. the whole batch is one co-resident wave
+// (<= 146 registers per thread).
+#ifndef VLCU_MIN_BLOCKS
+#define VLCU_MIN_BLOCKS 7
+#endif
+
 // Construct every instance: Vtop___024root___ctor_var_reset + zeroed context
 template <class T_Design>
 __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
+    __shared__ typename T_Design::Shared shared;
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (inst >= m.n) return;
     VlcuCtxRec* const recp = &m.ctxRecs[inst];
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
     vlcu_ctx_load(ctx, m, inst);
     typename T_Design::Root root;
     typename T_Design::Locals locals;
-    T_Design::bind(root, locals, m.state, inst);
+    T_Design::bind(root, locals, shared, m.state, inst);
     T_Design::ctor_var_reset(&root, ctx);
     T_Design::store(root, m.state, inst);
     vlcu_ctx_store(ctx);
@@ -91,14 +96,15 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
 
 // The cycle loop: nEvals x { testbench drive; eval_step; observe }
 template <class T_Design, class T_Tb>
-__global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_run(VlcuModelDev m, VlcuRunDev r) {
+__global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuModelDev m, VlcuRunDev r) {
+    __shared__ typename T_Design::Shared shared;
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (inst >= m.n) return;
     typename T_Design::Root root;
     typename T_Design::Locals locals;
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
-    T_Design::bind(root, locals, m.state, inst);
+    T_Design::bind(root, locals, shared, m.state, inst);
     T_Design::load(root, m.state, inst);
     uint64_t sig = r.sigs[inst];
     if (r.flags & VLCU_RUN_TB_BEGIN) {
@@ -139,13 +145,14 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_run(VlcuModelDev m, VlcuRun
 // Vtop::final(): run the design's final blocks
 template <class T_Design>
 __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_final(VlcuModelDev m) {
+    __shared__ typename T_Design::Shared shared;
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (inst >= m.n) return;
     typename T_Design::Root root;
     typename T_Design::Locals locals;
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
-    T_Design::bind(root, locals, m.state, inst);
+    T_Design::bind(root, locals, shared, m.state, inst);
     T_Design::load(root, m.state, inst);
     T_Design::eval_final(&root, ctx);
     T_Design::store(root, m.state, inst);

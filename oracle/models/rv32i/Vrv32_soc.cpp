@@ -190,6 +190,10 @@ struct Rv32Params {
     uint32_t* finalRegs;  // [n][32]
     uint32_t* finalMem;  // [n][1024]
     uint32_t* finalScalars;  // [n][8]: pc, insn, ld_addr, instret, state, trap, retired, clk
+    // Campaign mode (tb flag RV32_TBF_RESET_PER_RUN of the device testbench): `rounds` runs of
+    // nEvals evals on the same model; each run begins with clk = resetn = 0, a fresh program
+    // from (tbSeed + round) ^ index, and resetn low for the first resetTime evals OF THAT RUN
+    uint32_t rounds;
 };
 
 void runOne(const Rv32Params& p, uint64_t i) {
@@ -200,36 +204,40 @@ void runOne(const Rv32Params& p, uint64_t i) {
     const char* argv[] = {"oracle"};
     contextp->commandArgs(1, argv);
     const std::unique_ptr<Vrv32_soc> top{new Vrv32_soc{contextp.get(), "TOP"}};
-    top->clk = 0;
-    top->resetn = 0;
-    if (p.memImages) {
-        for (int w = 0; w < 1024; ++w) top->rootp->rv32_soc__DOT__mem[w] = p.memImages[i * 1024 + w];
-    } else {
-        rv32_gen_program(top->rootp->rv32_soc__DOT__mem, p.tbSeed ^ (p.instBase + i));
-    }
     const uint64_t resetTime = p.resetTime ? p.resetTime : 16;
     uint64_t sig = 0xcbf29ce484222325ULL;
-    for (uint64_t e = 0; e < p.nEvals; ++e) {
-        contextp->timeInc(1);
-        top->clk = !top->clk;
-        top->resetn = contextp->time() > resetTime;
-        top->eval();
-        sig = sigMix(sig, (static_cast<uint32_t>(top->trap) << 6) | (static_cast<uint32_t>(top->mem_valid) << 5)
-                              | (static_cast<uint32_t>(top->mem_instr) << 4) | top->mem_wstrb);
-        sig = sigMix(sig, top->mem_addr);
-        sig = sigMix(sig, top->mem_wdata);
-        sig = sigMix(sig, top->mem_rdata);
-        sig = sigMix(sig, top->retired);
-        if (p.obs && e < p.obsEvals) {
-            uint32_t* const rowp = p.obs + e * 8 * p.n;
-            rowp[0 * p.n + i] = top->trap;
-            rowp[1 * p.n + i] = top->mem_valid;
-            rowp[2 * p.n + i] = top->mem_instr;
-            rowp[3 * p.n + i] = top->mem_addr;
-            rowp[4 * p.n + i] = top->mem_wdata;
-            rowp[5 * p.n + i] = top->mem_wstrb;
-            rowp[6 * p.n + i] = top->mem_rdata;
-            rowp[7 * p.n + i] = top->retired;
+    const uint32_t rounds = p.rounds ? p.rounds : 1;
+    for (uint32_t round = 0; round < rounds; ++round) {
+        top->clk = 0;
+        top->resetn = 0;
+        if (p.memImages) {
+            for (int w = 0; w < 1024; ++w) top->rootp->rv32_soc__DOT__mem[w] = p.memImages[i * 1024 + w];
+        } else {
+            rv32_gen_program(top->rootp->rv32_soc__DOT__mem, (p.tbSeed + round) ^ (p.instBase + i));
+        }
+        for (uint64_t e = 0; e < p.nEvals; ++e) {
+            contextp->timeInc(1);
+            top->clk = !top->clk;
+            top->resetn = p.rounds ? (e >= resetTime) : (contextp->time() > resetTime);
+            top->eval();
+            sig = sigMix(sig, (static_cast<uint32_t>(top->trap) << 6) | (static_cast<uint32_t>(top->mem_valid) << 5)
+                                  | (static_cast<uint32_t>(top->mem_instr) << 4) | top->mem_wstrb);
+            sig = sigMix(sig, top->mem_addr);
+            sig = sigMix(sig, top->mem_wdata);
+            sig = sigMix(sig, top->mem_rdata);
+            sig = sigMix(sig, top->retired);
+            const uint64_t ge = round * p.nEvals + e;
+            if (p.obs && ge < p.obsEvals) {
+                uint32_t* const rowp = p.obs + ge * 8 * p.n;
+                rowp[0 * p.n + i] = top->trap;
+                rowp[1 * p.n + i] = top->mem_valid;
+                rowp[2 * p.n + i] = top->mem_instr;
+                rowp[3 * p.n + i] = top->mem_addr;
+                rowp[4 * p.n + i] = top->mem_wdata;
+                rowp[5 * p.n + i] = top->mem_wstrb;
+                rowp[6 * p.n + i] = top->mem_rdata;
+                rowp[7 * p.n + i] = top->retired;
+            }
         }
     }
     top->final();
@@ -255,9 +263,10 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                               uint64_t nEvals, uint64_t tbSeed, uint32_t resetTime,
                               const uint32_t* memImages, uint32_t* obs, uint64_t obsEvals,
                               uint64_t* sigs, uint64_t* times, uint32_t* finalRegs,
-                              uint32_t* finalMem, uint32_t* finalScalars, int threads) {
+                              uint32_t* finalMem, uint32_t* finalScalars, int threads,
+                              uint32_t rounds) {
     const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
-                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars};
+                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds};
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);
     } else {

@@ -42,6 +42,21 @@ def test_ports_every_eval_match_oracle(abi, rand_reset, reset_time):
         check_final_state(m, want)
 
 
+def test_campaign_rounds_fresh_program_and_reset_per_run(abi):
+    """Fuzz-campaign form used by bench.py's e2e leg: every vlcu_run starts a fresh program and
+    holds reset for the run's first evals (tb_flags bit 0), state otherwise carried over."""
+    n, evals, rounds = 160, 700, 3
+    want = O.rv32_run(n, evals, seed=5, rand_reset=2, tb_seed=900, reset_time=6, rounds=rounds,
+                      obs_evals=evals * rounds, want_mem=True)
+    with abi.Model("rv32i", n, seed=5, rand_reset=2) as m:
+        for k in range(rounds):
+            obs, _ = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, obs_evals=evals,
+                           tb_seed=900 + k, tb_flags=1, tb_arg=(6, 0, 0, 0))
+            assert (obs == want.obs[k * evals:(k + 1) * evals]).all(), k
+        assert (m.signatures() == want.sigs).all()
+        check_final_state(m, want)
+
+
 def test_x_initial_reset_of_arrays_and_scalars(abi):
     want = O.rv32_run(300, 0, inst_base=77, seed=123, rand_reset=2, want_mem=True)
     with abi.Model("rv32i", 300, inst_base=77, seed=123, rand_reset=2) as m:

@@ -128,7 +128,8 @@ struct VTOP final {
         uint32_t __Vcoverage[527];
 #endif
     };
-    VLCU_D static void bind(Root& s, Locals& l, const VlcuState&, uint64_t) {
+    struct Shared final {};
+    VLCU_D static void bind(Root& s, Locals& l, Shared&, const VlcuState&, uint64_t) {
 #if VTOP_COVERAGE
         s.__Vcoverage.bind(l.__Vcoverage);
 #else

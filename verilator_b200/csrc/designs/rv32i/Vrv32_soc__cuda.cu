@@ -19,7 +19,7 @@ struct Vrv32_soc___024root final {
     IData /*31:0*/ rv32_soc__DOT__insn;
     IData /*31:0*/ rv32_soc__DOT__ld_addr;
     IData /*31:0*/ rv32_soc__DOT__instret;
-    VlcuLocalArray<IData /*31:0*/, 32> rv32_soc__DOT__regs;  // run-time indexed: storage in Locals
+    VlcuSharedArray<IData /*31:0*/, 32> rv32_soc__DOT__regs;  // run-time indexed: storage in Shared
     // 4 KB per instance: stays in HBM, instance-major
     VlcuGlobalArray<IData /*31:0*/, 1024> rv32_soc__DOT__mem;
     CData /*0:0*/ clk;
@@ -73,11 +73,12 @@ struct Vrv32_soc__cuda final {
         kTouchedWriteBytes = 3 * 4 + 2 + 4 + 20,
     };
 
-    struct Locals final {
-        IData rv32_soc__DOT__regs[32];
+    struct Locals final {};
+    struct Shared final {
+        IData rv32_soc__DOT__regs[32][VLCU_BLOCK];  // 8 KB per CTA, bank = lane: conflict free
     };
-    VLCU_D static void bind(Root& s, Locals& l, const VlcuState& st, uint64_t i) {
-        s.rv32_soc__DOT__regs.bind(l.rv32_soc__DOT__regs);
+    VLCU_D static void bind(Root& s, Locals&, Shared& sh, const VlcuState& st, uint64_t i) {
+        s.rv32_soc__DOT__regs.bind(sh.rv32_soc__DOT__regs, threadIdx.x);
         s.rv32_soc__DOT__mem.bind(st, OFF_mem, i);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
@@ -207,11 +208,13 @@ struct TbRv32Rand final {
     }
     template <class T_Design>
     VLCU_D static void drive(typename T_Design::Root& top, VlcuContext& ctx, const VlcuRunDev& r,
-                             uint64_t, uint64_t) {
+                             uint64_t, uint64_t e) {
         ctx.timeInc(1);
         top.clk = !top.clk;
         const uint64_t resetTime = r.tbArg[0] ? r.tbArg[0] : 16;
-        top.resetn = ctx.time() > resetTime;
+        // RV32_TBF_RESET_PER_RUN (tb_flags bit 0): reset is held for the first resetTime evals
+        // of every vlcu_run (a fuzz campaign: new program, reset, run); otherwise once, by time
+        top.resetn = (r.tbFlags & 1U) ? ((e - r.evalBase) >= resetTime) : (ctx.time() > resetTime);
     }
 };
 // Same clocking, memory image left as loaded by the host (vlcu_set_member "rv32_soc__DOT__mem")
