@@ -203,6 +203,13 @@ const char* vlcu_message_format(const vlcu_model_t* h, uint32_t id);
 int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_bytes);
 uint32_t vlcu_member_offset(const vlcu_model_t* h, int member);
 
+/* Waveform of ONE sampled instance as VCD text, written exactly as VerilatedVcdC would write it
+   for that model instance with a dump() after every eval (include/verilated_vcd_c.cpp:117-129,
+   191-203,317-470,620-690; include/verilated_trace_imp.h): `trace` is the buffer vlcu_run filled
+   (trace_evals x n_samples records), `sample` selects the instance's slot in it. */
+int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_evals,
+                   uint32_t n_samples, uint32_t sample, const char* filename);
+
 /* ---- coverage ------------------------------------------------------------------ */
 uint32_t vlcu_coverage_bins(const vlcu_model_t* h);
 /* key fields of bin i, as passed to VL_COVER_INSERT (include/verilated_cov.h:70) */

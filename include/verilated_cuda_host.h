@@ -77,6 +77,19 @@ struct VlcuCoverPoint final {  // arguments of __vlCoverInsert / __vlCoverToggle
     const char* linescov;
 };
 
+// One statement of the model's trace_init function (what V3TraceDecl.cpp builds and
+// V3EmitCImp.cpp:643-880 prints as VL_TRACE_DECL_* / VL_TRACE_PUSH_PREFIX / VL_TRACE_POP_PREFIX)
+enum VlcuTraceOp : uint8_t { VLCU_TRACE_SIG = 0, VLCU_TRACE_PUSH = 1, VLCU_TRACE_POP = 2 };
+struct VlcuTraceDecl final {
+    uint8_t op;  // VlcuTraceOp
+    uint8_t bussed;  // declared with a [msb:lsb] range (DECL_BUS/QUAD/WIDE) vs DECL_BIT
+    const char* name;  // signal or scope name
+    uint32_t code;  // trace code relative to the model's base (first code is 1)
+    int32_t member;  // index into members[] of the traced variable
+    int32_t elem;  // element of an unpacked array (declared as name[elem]), else -1
+    int32_t msb, lsb;
+};
+
 struct VlcuDesignInfo final {
     const char* name;  // design name used with vlcu_create()
     const char* topName;  // Verilog top module
@@ -95,6 +108,8 @@ struct VlcuDesignInfo final {
     uint32_t nMessages;
     const char* const* plusargs;  // $test$plusargs strings by index
     uint32_t nPlusargs;
+    const VlcuTraceDecl* traceDecls;  // trace_init, in declaration order (nullptr: not traced)
+    uint32_t nTraceDecls;
 };
 
 #if defined(__CUDACC__) || defined(VLCU_HOST_RUNTIME)

@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
 }
 
 // The cycle loop: nEvals x { testbench drive; eval_step; observe }
-template <class T_Design, class T_Tb>
+// kObserve = false is the throughput form: no per-eval output capture, no waveform sampling,
+// no stop-on-finish test -- the loop body is drive + eval_step + signature only, with a 32-bit
+// trip count; vlcu_run picks it whenever the run descriptor asks for none of those.
+template <class T_Design, class T_Tb, bool kObserve>
 __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuModelDev m, VlcuRunDev r) {
     __shared__ typename T_Design::Shared shared;
     const uint64_t inst = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -110,30 +113,41 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
     if (r.flags & VLCU_RUN_TB_BEGIN) {
         T_Tb::template begin<T_Design>(root, ctx, r, inst, m.instBase + inst);
     }
-    // Is this instance sampled for waveform tracing?
-    int slot = -1;
-    for (uint32_t s = 0; s < r.nSamples; ++s) {
-        if (r.sampleIds[s] == inst) slot = static_cast<int>(s);
-    }
     uint64_t evalsDone = 0;
-    for (uint64_t e = 0; e < r.nEvals; ++e) {
-        // A host testbench loops "while (!contextp->gotFinish())" (sim_main.cpp:71)
-        if ((r.flags & VLCU_RUN_STOP_ON_FINISH) && ctx.gotFinish()) break;
-        T_Tb::template drive<T_Design>(root, ctx, r, inst, r.evalBase + e);
-        vlcu_eval_step<T_Design>(&root, ctx);
-        ++evalsDone;
-        sig = T_Design::outputs_sig(root, sig);
-        if (r.obs && e < r.obsEvals) {
-            T_Design::store_outputs_row(root, r.obs + e * T_Design::kOutWords * r.npad, r.npad,
-                                        inst);
+    if (!kObserve) {
+        // Runs longer than 2^32 evals are split by the host (vlcu_run)
+        const uint32_t nEvals = static_cast<uint32_t>(r.nEvals);
+        for (uint32_t e = 0; e < nEvals; ++e) {
+            T_Tb::template drive<T_Design>(root, ctx, r, inst, r.evalBase + e);
+            vlcu_eval_step<T_Design>(&root, ctx);
+            sig = T_Design::outputs_sig(root, sig);
         }
-        if (slot >= 0 && e < r.traceEvals) {
-            uint8_t* const recp
-                = r.trace + (e * r.nSamples + slot) * (T_Design::kStateBytes + VLCU_TRACE_HDR);
-            reinterpret_cast<uint64_t*>(recp)[0] = ctx.time();
-            reinterpret_cast<uint32_t*>(recp)[2] = ctx.m_status;
-            reinterpret_cast<uint32_t*>(recp)[3] = 1;  // record valid
-            T_Design::store(root, VlcuState{recp + VLCU_TRACE_HDR, 1}, 0);
+        evalsDone = nEvals;
+    } else {
+        // Is this instance sampled for waveform tracing?
+        int slot = -1;
+        for (uint32_t s = 0; s < r.nSamples; ++s) {
+            if (r.sampleIds[s] == inst) slot = static_cast<int>(s);
+        }
+        for (uint64_t e = 0; e < r.nEvals; ++e) {
+            // A host testbench loops "while (!contextp->gotFinish())" (sim_main.cpp:71)
+            if ((r.flags & VLCU_RUN_STOP_ON_FINISH) && ctx.gotFinish()) break;
+            T_Tb::template drive<T_Design>(root, ctx, r, inst, r.evalBase + e);
+            vlcu_eval_step<T_Design>(&root, ctx);
+            ++evalsDone;
+            sig = T_Design::outputs_sig(root, sig);
+            if (r.obs && e < r.obsEvals) {
+                T_Design::store_outputs_row(root, r.obs + e * T_Design::kOutWords * r.npad, r.npad,
+                                            inst);
+            }
+            if (slot >= 0 && e < r.traceEvals) {
+                uint8_t* const recp
+                    = r.trace + (e * r.nSamples + slot) * (T_Design::kStateBytes + VLCU_TRACE_HDR);
+                reinterpret_cast<uint64_t*>(recp)[0] = ctx.time();
+                reinterpret_cast<uint32_t*>(recp)[2] = ctx.m_status;
+                reinterpret_cast<uint32_t*>(recp)[3] = 1;  // record valid
+                T_Design::store(root, VlcuState{recp + VLCU_TRACE_HDR, 1}, 0);
+            }
         }
     }
     T_Design::store(root, m.state, inst);
@@ -171,7 +185,13 @@ class VlcuDesignImpl final : public VlcuDesignOps {
     bool tryRun(const char* tb, const VlcuModelDev& m, const VlcuRunDev& r, cudaStream_t stream,
                 cudaError_t& err) const {
         if (strcmp(tb, T_Tb::name()) != 0) return false;
-        vlcu_k_run<T_Design, T_Tb><<<blocksFor(m.n), VLCU_BLOCK, 0, stream>>>(m, r);
+        const bool observe = r.obs || r.nSamples || (r.flags & VLCU_RUN_STOP_ON_FINISH)
+                             || r.nEvals > 0xffffffffULL;
+        if (observe) {
+            vlcu_k_run<T_Design, T_Tb, true><<<blocksFor(m.n), VLCU_BLOCK, 0, stream>>>(m, r);
+        } else {
+            vlcu_k_run<T_Design, T_Tb, false><<<blocksFor(m.n), VLCU_BLOCK, 0, stream>>>(m, r);
+        }
         err = cudaGetLastError();
         return true;
     }

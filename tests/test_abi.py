@@ -49,3 +49,16 @@ def test_product_does_not_link_the_oracle():
     out = subprocess.run(["ldd", os.path.join(ROOT, "verilator_b200", "libverilated_cuda.so")],
                          capture_output=True, text=True).stdout
     assert "vlref" not in out and "verilated_ref" not in out
+
+
+def test_cxx_binding_compiles_and_fails_loudly_without_a_gpu():
+    """include/verilated_cuda_model.h (the Vtop-shaped C++ binding) builds against the product
+    library; without a device the testbench must stop with the no-CPU-path error."""
+    import subprocess
+    from verilator_b200 import abi
+    exe = os.path.join(ROOT, "tests", "cxx", "sim_main_batch")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    if abi.lib.vlcu_device_count() > 0:
+        pytest.skip("a GPU is present; the run itself is covered by the gpu tests")
+    res = subprocess.run([exe, "4", "10", "/dev/null"], capture_output=True, text=True)
+    assert res.returncode == 1 and "no CPU path" in res.stderr

@@ -118,6 +118,25 @@ def test_host_driven_eval_like_a_cpp_testbench(abi):
         check_status(m.status(), want.status)
 
 
+def test_cxx_testbench_through_the_model_binding(abi, tmp_path):
+    """sim_main.cpp's loop written in C++ against include/verilated_cuda_model.h (the Vtop-shaped
+    binding over the C ABI): every port value of every eval equals the oracle's."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cxx", "sim_main_batch")
+    n, evals = 48, 60
+    out = str(tmp_path / "ports.bin")
+    res = subprocess.run([exe, str(n), str(evals), out], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip() == f"finished=1 time={evals} first_finish=17"
+    rec = np.dtype([("small", "u1"), ("quad", "<u8"), ("wide", "<u4", 3)])
+    got = np.fromfile(out, dtype=rec).reshape(evals, n)
+    want = O.mtc_run(n, evals, rand_reset=2, trace_plusarg=True, obs_evals=evals)
+    assert (got["small"] == want.obs[:, 0, :]).all()
+    assert (got["quad"] == (want.obs[:, 1].astype(np.uint64) | (want.obs[:, 2].astype(np.uint64) << 32))).all()
+    assert (got["wide"] == want.obs[:, 3:6].transpose(0, 2, 1)).all()
+
+
 def test_trace_testbench_with_host_stimulus_rows(abi):
     """Generic 'trace' testbench: stimulus rows [eval][in_word][instance] from the host."""
     n, evals = 130, 80
@@ -144,6 +163,28 @@ def test_trace_testbench_with_host_stimulus_rows(abi):
         obs, _ = m.run("trace", evals, stim=stim, obs_evals=evals)
         assert (obs == want.obs).all()
         check_status(m.status(), want.status)
+
+
+@pytest.mark.parametrize("stop_on_finish,period", [(False, 0), (False, 40), (True, 0)])
+def test_vcd_of_sampled_instances_equals_the_reference_writer(abi, tmp_path, stop_on_finish, period):
+    """R8: waveforms of sampled instances.  The device samples full state after every eval;
+    vlcu_vcd_write turns the records into VCD text, which must be byte-identical to what the
+    reference's own VerilatedVcdC writes for the same instance (dump(time) after every eval)."""
+    n, evals = 96, 400
+    samples = [0, 41, 95]
+    flags = abi.RUNF_TB_BEGIN | (abi.RUNF_STOP_ON_FINISH if stop_on_finish else 0)
+    with abi.Model("make_tracing_c", n, seed=9, rand_reset=2, msg_cap=4, plusargs="+trace") as m:
+        _, trace = m.run("sim_main", evals, flags=flags, tb_seed=77, tb_flags=1, tb_arg=(period, 0, 0, 0),
+                         samples=samples, trace_evals=evals)
+        for k, inst in enumerate(samples):
+            ref_path, our_path = str(tmp_path / f"ref{inst}.vcd"), str(tmp_path / f"our{inst}.vcd")
+            O.mtc_run(n, evals, seed=9, rand_reset=2, stop_on_finish=stop_on_finish, tb_seed=77,
+                      per_instance=True, reset_period=period, trace_plusarg=True, vcd_path=ref_path,
+                      vcd_instance=inst)
+            m.vcd_write(trace, k, our_path)
+            ours, want = open(our_path).read(), open(ref_path).read()
+            assert want.count("\n#") > 10 and "$var wire 70" in want
+            assert ours == want, (inst, ours[:600], want[:600])
 
 
 def test_x_initial_unique_reset_values(abi):

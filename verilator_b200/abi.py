@@ -111,6 +111,7 @@ SIGNATURES = {
                                     ctypes.POINTER(c_cp)]),
     "vlcu_coverage_reduce": (c_i32, [_H, c_vp]),
     "vlcu_coverage_write": (c_i32, [_H, c_vp, c_cp]),
+    "vlcu_vcd_write": (c_i32, [_H, c_vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_cp]),
     "vlcu_comm_unique_id": (c_i32, [c_vp]),
     "vlcu_comm_init": (c_i32, [_H, c_vp, c_i32, c_i32]),
     "vlcu_comm_destroy": (c_i32, [_H]),
@@ -340,6 +341,12 @@ class Model:
         out = np.zeros(self.coverage_bins(), dtype=np.uint64)
         _check(lib.vlcu_coverage_reduce(self.h, out.ctypes.data))
         return out
+
+    def vcd_write(self, trace, sample, filename):
+        """trace: the uint8 [trace_evals][n_samples][record] array run() returned."""
+        trace = np.ascontiguousarray(trace, dtype=np.uint8)
+        _check(lib.vlcu_vcd_write(self.h, trace.ctypes.data, trace.shape[0], trace.shape[1], sample,
+                                  filename.encode()))
 
     def coverage_write(self, counts, filename):
         counts = np.ascontiguousarray(counts, dtype=np.uint64)

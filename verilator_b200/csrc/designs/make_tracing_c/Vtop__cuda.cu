@@ -104,6 +104,26 @@ std::vector<VlcuMemberDesc> makeCovMembers() {
 }
 #undef M
 
+// trace_init_top (V3TraceDecl.cpp): ports at the model's root scope, again inside `top` (same
+// codes: V3Trace de-duplicates identical values), then the inlined `sub`
+#define SIG(name, code, member, bussed, msb, lsb) {VLCU_TRACE_SIG, bussed, name, code, member, -1, msb, lsb}
+#define PORTS_ \
+    SIG("clk", 1, 0, 0, 0, 0), SIG("reset_l", 2, 1, 0, 0, 0), SIG("out_small", 3, 2, 1, 1, 0), \
+    SIG("out_quad", 4, 3, 1, 39, 0), SIG("out_wide", 6, 4, 1, 69, 0), SIG("in_small", 9, 5, 1, 1, 0), \
+    SIG("in_quad", 10, 6, 1, 39, 0), SIG("in_wide", 12, 7, 1, 69, 0)
+const VlcuTraceDecl kTraceDecls[] = {
+    PORTS_,
+    {VLCU_TRACE_PUSH, 0, "top", 0, -1, -1, 0, 0},
+    PORTS_,
+    {VLCU_TRACE_PUSH, 0, "sub", 0, -1, -1, 0, 0},
+    SIG("clk", 1, 0, 0, 0, 0), SIG("reset_l", 2, 1, 0, 0, 0), SIG("count_c", 15, 8, 1, 31, 0),
+    {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
+    {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
+};
+#undef PORTS_
+#undef SIG
+const uint32_t kNTraceDecls = sizeof(kTraceDecls) / sizeof(kTraceDecls[0]);
+
 // Coverage registrations, in bin order: what Vtop___024root::__Vconfigure would pass to
 // __vlCoverToggleInsert / __vlCoverInsert (V3EmitCImp.cpp:179-262, V3EmitCFunc.h:179-215,895-927)
 struct CoverTables final {
@@ -167,7 +187,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         "make_tracing_c", "top", members.data(), static_cast<uint32_t>(members.size()),
         kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes, 0, 0,
         nullptr, 0, 0,
-        kMessages, 4, kPlusargs, 1};
+        kMessages, 4, kPlusargs, 1, kTraceDecls, kNTraceDecls};
     return s;
 }
 const VlcuDesignInfo& Vtop_cov__cuda::info() {
@@ -177,7 +197,7 @@ const VlcuDesignInfo& Vtop_cov__cuda::info() {
         kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes, 0, 0,
         coverTables().points.data(), static_cast<uint32_t>(coverTables().points.size()),
         OFF___Vcoverage,
-        kMessages, 4, kPlusargs, 1};
+        kMessages, 4, kPlusargs, 1, kTraceDecls, kNTraceDecls};
     return s;
 }
 

@@ -255,10 +255,35 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         {"rv32_soc__DOT__mem", "rv32_soc.mem", VLCU_MEMBER_MEMORY, 4, 0, 1024, 32, 31, 0, T::OFF_mem},
         {"__Vtrigprevexpr___TOP__clk__0", nullptr, VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_prev_clk},
     };
+    // trace_init: ports at the root scope, the same signals plus the internal registers inside
+    // `rv32_soc`; regs[] (32 entries <= --trace-max-array) element by element, mem[] not traced
+    static std::vector<VlcuTraceDecl> decls;
+    if (decls.empty()) {
+        const auto ports = [&]() {
+            uint32_t code = 1;
+            for (int mi = 0; mi < 10; ++mi) {
+                const VlcuMemberDesc& md = members[mi];
+                decls.push_back({VLCU_TRACE_SIG, static_cast<uint8_t>(md.width > 1), md.name, code, mi,
+                                 -1, md.msb, md.lsb});
+                code += (md.width + 31) / 32;
+            }
+            return code;
+        };
+        ports();
+        decls.push_back({VLCU_TRACE_PUSH, 0, "rv32_soc", 0, -1, -1, 0, 0});
+        uint32_t code = ports();
+        const char* const names[] = {"pc", "insn", "ld_addr", "instret", "state"};
+        for (int k = 0; k < 5; ++k) {
+            const VlcuMemberDesc& md = members[10 + k];
+            decls.push_back({VLCU_TRACE_SIG, 1, names[k], code++, 10 + k, -1, md.msb, md.lsb});
+        }
+        for (int e = 0; e < 32; ++e) decls.push_back({VLCU_TRACE_SIG, 1, "regs", code++, 15, e, 31, 0});
+        decls.push_back({VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0});
+    }
     static const VlcuDesignInfo s = {
         "rv32i", "rv32_soc", members, sizeof(members) / sizeof(members[0]),
         kStateBytes, kInWords, kOutWords, kInBytes, kOutBytes, kTouchedReadBytes, kTouchedWriteBytes,
-        nullptr, 0, 0, nullptr, 0, nullptr, 0};
+        nullptr, 0, 0, nullptr, 0, nullptr, 0, decls.data(), static_cast<uint32_t>(decls.size())};
     return s;
 }
 

@@ -973,6 +973,128 @@ int vlcu_coverage_write(const vlcu_model_t* h, const uint64_t* counts, const cha
 }
 
 //-------------------------------------------------------------------------
+// Waveforms: VCD text of one sampled instance from the trace records of vlcu_run.
+// Restates, for the subset a Verilated model uses (bit / bus / quad / wide / array elements):
+//   header + declarations   include/verilated_vcd_c.cpp:117-129, 317-450
+//   identifier codes        include/verilated_vcd_c.cpp:400-426  ('!' + code % 94, least digit first)
+//   time stamps             include/verilated_vcd_c.cpp:191-203  (an empty one is overwritten)
+//   full dump on the first call, changes afterwards, signals in code order
+//                           include/verilated_trace_imp.h (dump / runCallbacks, full* / chg*)
+//   value text              include/verilated_vcd_c.cpp:620-690  (all `bits` digits, MSB first)
+
+namespace {
+struct VcdSig final {
+    uint32_t code;
+    uint32_t offset;  // byte offset of the value inside a packed state record
+    uint32_t elemBytes, words, bits;
+    bool bit;  // declared with DECL_BIT
+};
+std::string vcdIdent(uint32_t code) {
+    std::string id;
+    do {
+        id += static_cast<char>('!' + (code % 94));
+        code /= 94;
+    } while (code--);
+    return id;
+}
+void vcdValue(std::string& out, const VcdSig& sg, const uint8_t* valp, const std::string& ident) {
+    if (sg.bit) {
+        out += static_cast<char>('0' | (valp[0] & 1));
+    } else {
+        out += 'b';
+        for (int b = static_cast<int>(sg.bits) - 1; b >= 0; --b) {
+            out += static_cast<char>('0' | ((valp[b >> 3] >> (b & 7)) & 1));  // little endian storage
+        }
+    }
+    if (sg.bits != 1) out += ' ';  // 1-bit values have no separator before the identifier
+    out += ident;
+    out += '\n';
+}
+}  // namespace
+
+int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_evals,
+                   uint32_t n_samples, uint32_t sample, const char* filename) {
+    if (!h || !trace || !filename || sample >= n_samples) return fail(VLCU_E_ARG, "bad argument");
+    const VlcuDesignInfo& info = *h->infop;
+    if (!info.traceDecls) return fail(VLCU_E_STATE, "design has no trace declarations");
+    std::string out = "$version Generated by VerilatedVcd $end\n$timescale 1ps $end\n";
+    int indent = 1;
+    const auto printIndent = [&](int change) {
+        if (change < 0) indent += change;
+        out.append(static_cast<size_t>(indent), ' ');
+        if (change > 0) indent += change;
+    };
+    printIndent(1);
+    out += "$scope module TOP $end\n";  // the model's name()
+    std::map<uint32_t, VcdSig> sigs;  // by code: the dump order
+    const uint32_t baseCode = 1;  // VerilatedTrace::nextCode() starts at 1
+    for (uint32_t d = 0; d < info.nTraceDecls; ++d) {
+        const VlcuTraceDecl& td = info.traceDecls[d];
+        if (td.op == VLCU_TRACE_PUSH) {
+            printIndent(1);
+            out += std::string{"$scope module "} + td.name + " $end\n";
+        } else if (td.op == VLCU_TRACE_POP) {
+            printIndent(-1);
+            out += "$upscope $end\n";
+        } else {
+            const VlcuMemberDesc& md = info.members[td.member];
+            const uint32_t bits
+                = static_cast<uint32_t>((td.msb > td.lsb ? td.msb - td.lsb : td.lsb - td.msb) + 1);
+            const uint32_t code = baseCode + td.code;
+            printIndent(0);
+            out += "$var wire " + std::to_string(bits) + ' ' + vcdIdent(code) + ' ' + td.name;
+            if (td.elem >= 0) out += '[' + std::to_string(td.elem) + ']';
+            if (td.bussed) out += " [" + std::to_string(td.msb) + ':' + std::to_string(td.lsb) + ']';
+            out += " $end\n";
+            VcdSig sg;
+            sg.code = code;
+            sg.elemBytes = md.elemBytes;
+            sg.words = td.elem >= 0 ? 1 : md.elems;
+            sg.offset = md.soaOffset + (td.elem >= 0 ? td.elem * md.elemBytes : 0);
+            sg.bits = bits;
+            sg.bit = !td.bussed;
+            sigs.emplace(code, sg);
+        }
+    }
+    printIndent(-1);
+    out += "$upscope $end\n";
+    out += "$enddefinitions $end\n\n\n";
+
+    const size_t recBytes = static_cast<size_t>(info.stateBytes) + VLCU_TRACE_HDR;
+    const uint8_t* const basep = static_cast<const uint8_t*>(trace);
+    const uint8_t* prevp = nullptr;
+    uint64_t lastTime = 0;
+    size_t timeBegin = std::string::npos, timeEnd = std::string::npos;
+    for (uint64_t e = 0; e < trace_evals; ++e) {
+        const uint8_t* const recp = basep + (e * n_samples + sample) * recBytes;
+        uint64_t time;
+        uint32_t valid;
+        memcpy(&time, recp, sizeof(time));
+        memcpy(&valid, recp + 12, sizeof(valid));
+        if (!valid) continue;  // the instance had stopped (stop-on-finish)
+        if (prevp && time <= lastTime) continue;  // "dump at same time" is skipped by dump()
+        // emitTimeChange: a time stamp nothing followed is overwritten
+        if (timeBegin != std::string::npos && timeEnd == out.size()) out.resize(timeBegin);
+        timeBegin = out.size();
+        out += '#' + std::to_string(time) + '\n';
+        timeEnd = out.size();
+        const uint8_t* const valsp = recp + VLCU_TRACE_HDR;
+        for (const auto& it : sigs) {
+            const VcdSig& sg = it.second;
+            const size_t nbytes = static_cast<size_t>(sg.elemBytes) * sg.words;
+            if (prevp && !memcmp(valsp + sg.offset, prevp + sg.offset, nbytes)) continue;
+            vcdValue(out, sg, valsp + sg.offset, vcdIdent(sg.code));
+        }
+        prevp = valsp;
+        lastTime = time;
+    }
+    std::ofstream os{filename, std::ios::binary};
+    if (os.fail()) return fail(VLCU_E_IO, std::string{"Can't write '"} + filename + "'");
+    os << out;
+    return os.good() ? VLCU_OK : fail(VLCU_E_IO, "write failed");
+}
+
+//-------------------------------------------------------------------------
 // Multi-GPU
 
 int vlcu_comm_unique_id(void* id_out) {
