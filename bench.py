@@ -47,6 +47,15 @@ WORKLOADS = {
     # BASELINE.json configs[1]: RV32I core, 65,536 instances, each a random-seeded program.
     # PicoRV32 itself is not vendored in the reference and cannot be Verilated here (no bison/flex),
     # so the workload is this repo's PicoRV32-class core rv32_soc.v
+    # BASELINE.json configs[4] in miniature: a --coverage campaign (line + toggle + user cover
+    # points) whose per-instance counters are reduced on the device and summed across GPUs by
+    # NCCL; VeeR-EH1 is not vendored, the only --coverage design available is make_tracing_c
+    "cov_campaign": dict(
+        design="make_tracing_c_cov", tb="sim_main", instances=65536, cycles=2048, tb_flags=1,
+        tb_arg=(128, 0, 0, 0), rand_reset=2, inputs=("in_small", "in_quad", "in_wide"), coverage=True,
+        note="examples/make_tracing_c built --coverage (527 bins/instance), per-instance random "
+             "stimulus offsets, reset every 128 time units; e2e adds the on-device coverage "
+             "reduction + ncclAllReduce + coverage.dat write per step"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -108,17 +117,10 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def dist_setup(n_gpus):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
+def dist_setup(n_gpus, backend="nccl"):
+    from verilator_b200 import shard
+    rank, world, local = shard.env_rank_world()
+    dist = shard.init_process_group(backend, local) if world > 1 else None
     return rank, world, local, dist
 
 
@@ -128,12 +130,8 @@ def barrier(dist):
 
 
 def allmax(dist, x, local):
-    if dist is None:
-        return x
-    import torch
-    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    from verilator_b200 import shard
+    return shard.allreduce_max(dist, x, local)
 
 
 def pinned_array(abi, shape, dtype):
@@ -149,28 +147,33 @@ def pinned_array(abi, shape, dtype):
 
 def cpu_reference_run(wl, sample_instances, cycles, threads):
     """Times the reference model (restated Vtop against the genuine runtime, oracle/_ref) on the
-    host cores: one instance per thread at a time, as docs/guide/verilating.rst:232-236."""
+    host cores: one instance per thread at a time, as docs/guide/verilating.rst:232-236.
+    Returns (instance-cycles/s, seconds): the seconds are the slowest worker thread's time
+    inside the cycle loops only -- model construction, program generation and final() are
+    excluded."""
+    import ctypes as C
     import oracle_util as O
-    t0 = time.perf_counter()
     if wl["design"] == "rv32i":
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads)
     else:
         O.mtc_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                   per_instance=bool(wl["tb_flags"] & 1), reset_period=wl["tb_arg"][0], threads=threads)
-    dt = time.perf_counter() - t0
+    fn = O.ref().vlref_last_loop_seconds
+    fn.restype = C.c_double
+    dt = float(fn())
     return sample_instances * cycles / dt, dt
 
 
 def run_reference(args, wl):
-    rank, world, local, dist = dist_setup(args.gpus)
-    if rank != 0:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:  # the CPU arm runs on rank 0 alone; the other ranks exit without work
         return
     threads = os.cpu_count() or 1
     # bounded sample: ~1-2 s of CPU work per step
     cycles = min(wl["cycles"], 4096)
     probe, _ = cpu_reference_run(wl, threads, 512, threads)
-    sample = max(threads, int(probe * 1.5 / cycles) // threads * threads)
+    sample = max(threads, int(probe * 3.0 / cycles) // threads * threads)  # ~3 s per step
     for _ in range(args.warmup):
         cpu_reference_run(wl, sample, cycles, threads)
     t_total, units = 0.0, 0
@@ -206,6 +209,10 @@ def run_ours(args, wl):
                   rand_reset=wl["rand_reset"], msg_cap=2)
     run_kw = dict(tb_seed=3, tb_flags=wl["tb_flags"], tb_arg=wl["tb_arg"])
     m.run(wl["tb"], 0, flags=abi.RUNF_TB_BEGIN, **run_kw)  # initial port values
+    coverage = bool(wl.get("coverage"))
+    if coverage and dist is not None:
+        from verilator_b200 import shard
+        shard.attach_coverage_comm(m, dist, local)  # NCCL communicator for the counter sum
 
     def step():
         m.run(wl["tb"], evals, **run_kw)
@@ -248,10 +255,14 @@ def run_ours(args, wl):
         arr, _ptr = pinned_array(abi, (n, elems), {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[eb])
         arr[:] = m.get_member(name).reshape(n, elems)
         ins[name] = arr
+    cov_path = os.path.join(ROOT, "gpurun_out", "coverage.dat")
+    os.makedirs(os.path.dirname(cov_path), exist_ok=True)
     sig_host, _ = pinned_array(abi, (n,), np.uint64)
     st_host, _ = pinned_array(abi, (n,), abi.STATUS_DTYPE)
     h2d = sum(a.nbytes for a in ins.values()) + (images.nbytes if images is not None else 0)
     d2h = sig_host.nbytes + st_host.nbytes + (regs_host.nbytes if images is not None else 0)
+    if coverage:
+        d2h += 8 * m.coverage_bins()
     e2e_tb = "rv32_host" if images is not None else wl["tb"]
     # rv32i: one e2e step = one fuzz round: new program images from the host, reset, run
     e2e_flags = abi.RUNF_TB_BEGIN if images is not None else 0
@@ -270,6 +281,12 @@ def run_ours(args, wl):
         if images is not None:
             ri = m.members["rv32_soc__DOT__regs"][0]
             abi._check(abi.lib.vlcu_get_member(m.h, ri, regs_host.ctypes.data, regs_host.strides[0]))
+        if coverage:
+            # per-instance u32 counters -> u64 per bin on the device, NCCL sum across shards,
+            # merged coverage.dat written by rank 0 (verilated_cov.cpp:368-438 format)
+            sums = m.coverage_reduce()
+            if rank == 0:
+                m.coverage_write(sums, cov_path)
 
     e2e_step()
     barrier(dist)

@@ -11,6 +11,7 @@
 #include "Vtop.h"
 #include "Vtop___024root.h"
 #include "verilated_vcd_c.h"
+#include "ref_timing.h"
 
 #include <atomic>
 #include <cstring>
@@ -110,6 +111,7 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
     }
     uint64_t sig = 0xcbf29ce484222325ULL;
     uint32_t msgCount = 0;
+    const VlrefLoopTimer* const timerp = new VlrefLoopTimer;
     for (uint64_t e = 0; e < p.nEvals; ++e) {
         if ((p.runFlags & 2U) && contextp->gotFinish()) break;
         contextp->timeInc(1);
@@ -156,6 +158,7 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
             rowp[5 * p.n + i] = top->out_wide[2];
         }
     }
+    delete timerp;
     top->final();
     if (tfp) tfp->close();
     if (p.sigs) p.sigs[i] = sig;
@@ -207,8 +210,10 @@ extern "C" int vlref_mtc_run(uint64_t n, uint64_t instBase, uint64_t seedBase, i
              covSums, vcdPath, vcdInstance, covPath, covInstance, &console};
     if (threads < 1) threads = 1;
     std::vector<std::vector<uint64_t>> cov(threads, std::vector<uint64_t>(527, 0));
+    vlref_loop_seconds_begin();
     if (threads == 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i, cov[0]);
+        vlref_loop_seconds_thread_done();
     } else {
         std::atomic<uint64_t> next{0};
         std::vector<std::thread> pool;
@@ -219,6 +224,7 @@ extern "C" int vlref_mtc_run(uint64_t n, uint64_t instBase, uint64_t seedBase, i
                     if (i >= n) break;
                     runOne(p, i, cov[t]);
                 }
+                vlref_loop_seconds_thread_done();
             });
         }
         for (auto& th : pool) th.join();

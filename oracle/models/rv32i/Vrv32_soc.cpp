@@ -10,6 +10,7 @@
 //   src/V3EmitCFunc.cpp:524-677.
 // The design logic is pinned independently by tests/rv32_iss.py.
 #include "verilated.h"
+#include "ref_timing.h"
 
 #include <atomic>
 #include <cstring>
@@ -215,6 +216,7 @@ void runOne(const Rv32Params& p, uint64_t i) {
         } else {
             rv32_gen_program(top->rootp->rv32_soc__DOT__mem, (p.tbSeed + round) ^ (p.instBase + i));
         }
+        const VlrefLoopTimer timer;
         for (uint64_t e = 0; e < p.nEvals; ++e) {
             contextp->timeInc(1);
             top->clk = !top->clk;
@@ -267,8 +269,10 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                               uint32_t rounds) {
     const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
                        obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds};
+    vlref_loop_seconds_begin();
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);
+        vlref_loop_seconds_thread_done();
     } else {
         std::atomic<uint64_t> next{0};
         std::vector<std::thread> pool;
@@ -279,6 +283,7 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                     if (i >= n) break;
                     runOne(p, i);
                 }
+                vlref_loop_seconds_thread_done();
             });
         }
         for (auto& th : pool) th.join();

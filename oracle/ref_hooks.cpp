@@ -75,3 +75,19 @@ void vl_fatal(const char* filename, int linenum, const char* hier, const char* m
         ++t_eventsp->fatal_count;
     }
 }
+
+// Cycle-loop timing shared by the model harnesses (ref_timing.h)
+#include "ref_timing.h"
+#include <mutex>
+static std::mutex s_loopMutex;
+static double s_loopSeconds = 0.0;
+void vlref_loop_seconds_begin() {
+    const std::lock_guard<std::mutex> lock{s_loopMutex};
+    s_loopSeconds = 0.0;
+}
+void vlref_loop_seconds_thread_done() {
+    const std::lock_guard<std::mutex> lock{s_loopMutex};
+    if (VlrefLoopTimer::threadTotal() > s_loopSeconds) s_loopSeconds = VlrefLoopTimer::threadTotal();
+    VlrefLoopTimer::threadTotal() = 0.0;
+}
+extern "C" double vlref_last_loop_seconds() { return s_loopSeconds; }
