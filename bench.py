@@ -165,6 +165,15 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     return sample_instances * cycles / dt, dt
 
 
+def cpu_sample_size(wl, cycles, threads, budget_s):
+    """Instances for a CPU sample whose WHOLE call (construction included) takes ~budget_s."""
+    cpu_reference_run(wl, threads, cycles, threads)  # load the library, warm the allocator
+    t0 = time.perf_counter()
+    cpu_reference_run(wl, 4 * threads, cycles, threads)
+    wall = max(time.perf_counter() - t0, 1e-3)
+    return max(threads, int(4 * threads * budget_s / wall) // threads * threads)
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:  # the CPU arm runs on rank 0 alone; the other ranks exit without work
@@ -172,8 +181,7 @@ def run_reference(args, wl):
     threads = os.cpu_count() or 1
     # bounded sample: ~1-2 s of CPU work per step
     cycles = min(wl["cycles"], 4096)
-    probe, _ = cpu_reference_run(wl, threads, 512, threads)
-    sample = max(threads, int(probe * 3.0 / cycles) // threads * threads)  # ~3 s per step
+    sample = cpu_sample_size(wl, cycles, threads, 4.0)  # ~4 s of wall time per step
     for _ in range(args.warmup):
         cpu_reference_run(wl, sample, cycles, threads)
     t_total, units = 0.0, 0
@@ -321,9 +329,8 @@ def run_ours(args, wl):
     threads = os.cpu_count() or 1
     cpu = None
     if not args.no_cpu_baseline:
-        probe, _ = cpu_reference_run(wl, threads, 512, threads)
         c_cycles = min(cycles, 4096)
-        sample = max(threads, int(probe * 12 / c_cycles) // threads * threads)
+        sample = cpu_sample_size(wl, c_cycles, threads, 15.0)
         cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)
         cpu = {"value": cpu_value, "unit": UNIT, "cores": threads,
                "kind": "port (restated Vtop for the design, genuine verilated runtime)",
