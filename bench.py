@@ -53,7 +53,7 @@ WORKLOADS = {
     "cov_campaign": dict(
         design="make_tracing_c_cov", tb="sim_main", instances=65536, cycles=2048, tb_flags=1,
         tb_arg=(128, 0, 0, 0), rand_reset=2, inputs=("in_small", "in_quad", "in_wide"), coverage=True,
-        note="examples/make_tracing_c built --coverage (527 bins/instance), per-instance random "
+        note="examples/make_tracing_c built --coverage (543 bins/instance), per-instance random "
              "stimulus offsets, reset every 128 time units; e2e adds the on-device coverage "
              "reduction + ncclAllReduce + coverage.dat write per step"),
     "rv32i": dict(

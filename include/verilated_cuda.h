@@ -235,17 +235,84 @@ struct VlcuContext final {
     }
 };
 
-// Emitted-code spellings (V3EmitCFunc.h:1359-1376 prints VL_FINISH_MT/VL_STOP_MT
-// with file, line, hier; on the device the file/hier strings stay on the host)
+// Older hand-written spellings
 #define VLCU_FINISH(ctx, line) (ctx).finish(line)
 #define VLCU_STOP(ctx, line, maybe) (ctx).stop(line, maybe)
 #define VLCU_FATAL(ctx, line, code) (ctx).fatal(line, code)
 
 //=========================================================================
+// What the text printed by EmitCFunc expects from "verilated.h", for device code printed by
+// V3EmitCuda.  Every emitted function has `VlcuContext& vlCtx` in scope (parameter) and a
+// `typedef <return type> VlcuFuncRet`.
+
+// VL_FINISH_MT / VL_STOP_MT / VL_FATAL_MT (V3EmitCFunc.h:1359-1376; include/verilated.cpp:245-266):
+// the file and hierarchy strings are compile-time literals that only the host needs
+VLCU_HD void vlcu_finish_mt(VlcuContext& ctx, const char*, int line, const char*) {
+    ctx.finish(static_cast<uint32_t>(line));
+}
+VLCU_HD void vlcu_stop_mt(VlcuContext& ctx, const char*, int line, const char*, bool maybe = true) {
+    ctx.stop(static_cast<uint32_t>(line), maybe);
+}
+VLCU_HD void vlcu_fatal_mt(VlcuContext& ctx, const char*, int line, const char*, const char* msgp) {
+    // The scheduler's only fatal is the convergence guard (V3SchedUtil.cpp:80-104)
+    const bool converge = msgp[0] == 'D' && msgp[1] == 'I' && msgp[2] == 'D' && msgp[3] == 'N';
+    ctx.fatal(static_cast<uint32_t>(line), converge ? VLCU_FATAL_DIDNOTCONVERGE : VLCU_FATAL_USER);
+}
+#define VL_FINISH_MT(...) vlcu_finish_mt(vlCtx, __VA_ARGS__)
+#define VL_STOP_MT(...) vlcu_stop_mt(vlCtx, __VA_ARGS__)
+// The C++ model aborts the process here; an instance instead leaves the function it is in
+// (the region loops are inside _eval / _eval_settle) with its fatal flag set
+#define VL_FATAL_MT(...) \
+    do { \
+        vlcu_fatal_mt(vlCtx, __VA_ARGS__); \
+        return VlcuFuncRet(); \
+    } while (0)
+// $time scaled to the module's time unit (V3EmitCFunc.h:1404-1412; verilated.h VL_TIME_UNITED_Q)
+#define VL_TIME_UNITED_Q(scale) (vlCtx.time() / static_cast<QData>(scale))
+#define VL_TIME_Q() (vlCtx.time())
+
+// vlSymsp->_vm_contextp__->...  inside literal C text of the scheduler (assert control,
+// debug()) resolves against the instance's context through this stand-in for Vtop__Syms
+enum class VerilatedAssertCtlQuery : uint8_t {
+    ASSERT_CTL_ON,
+    ASSERT_CTL_KILL,
+    ASSERT_CTL_PASS_ON_VACUOUS,
+    ASSERT_CTL_PASS_ON_NONVACUOUS,
+    ASSERT_CTL_FAIL_ON,
+};
+struct VlcuSymsCtxShim final {
+    VlcuContext* m_ctxp;
+    // VerilatedContext::assertCtlGet (include/verilated.cpp:3180-3198) with the run-time
+    // defaults: everything on, nothing killed
+    VLCU_HD uint32_t assertCtlGet(VerilatedAssertCtlQuery query, uint32_t types, uint32_t directives) const {
+        if (!types || !directives) return 0;
+        return query == VerilatedAssertCtlQuery::ASSERT_CTL_KILL ? 0U : 1U;
+    }
+    VLCU_HD int debug() const { return 0; }
+    VLCU_HD const VlcuSymsCtxShim* operator->() const { return this; }
+};
+struct VlcuSymsShim final {
+    VlcuSymsCtxShim _vm_contextp__;
+    VLCU_HD explicit VlcuSymsShim(VlcuContext* ctxp)
+        : _vm_contextp__{ctxp} {}
+    VLCU_HD const char* name() const { return "TOP"; }
+};
+
+// $display argument as logged (low 64 bits of a wide value)
+template <typename T>
+VLCU_HD uint64_t vlcu_msg_arg(T value) {
+    return static_cast<uint64_t>(value);
+}
+template <size_t N>
+VLCU_HD uint64_t vlcu_msg_arg(const VlWide<N>& value) {
+    return N > 1 ? (static_cast<uint64_t>(value[1]) << 32) | value[0] : value[0];
+}
+
+//=========================================================================
 // X-initial reset values (verilated.cpp:577-635); 'ctx' supplies what the
 // host code reads from Verilated::threadContextp()
 
-VLCU_HD IData VL_SCOPED_RAND_RESET_I(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+VLCU_HD IData vlcu_scoped_rand_reset_i(const VlcuContext& ctx, int obits, uint64_t scopeHash,
                                      uint64_t salt) {
     if (ctx.randReset() == 0) return 0;
     IData data = ~0U;
@@ -255,7 +322,7 @@ VLCU_HD IData VL_SCOPED_RAND_RESET_I(const VlcuContext& ctx, int obits, uint64_t
     }
     return data & VL_MASK_I(obits);
 }
-VLCU_HD QData VL_SCOPED_RAND_RESET_Q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+VLCU_HD QData vlcu_scoped_rand_reset_q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
                                      uint64_t salt) {
     if (ctx.randReset() == 0) return 0;
     QData data = ~0ULL;
@@ -265,7 +332,7 @@ VLCU_HD QData VL_SCOPED_RAND_RESET_Q(const VlcuContext& ctx, int obits, uint64_t
     }
     return data & VL_MASK_Q(obits);
 }
-VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_W(const VlcuContext& ctx, int obits, WDataOutP outwp,
+VLCU_HD WDataOutP vlcu_scoped_rand_reset_w(const VlcuContext& ctx, int obits, WDataOutP outwp,
                                          uint64_t scopeHash, uint64_t salt) {
     const int words = VL_WORDS_I(obits);
     if (ctx.randReset() == 0) {
@@ -280,17 +347,17 @@ VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_W(const VlcuContext& ctx, int obits, WDat
     outwp[words - 1] &= VL_MASK_E(obits);
     return outwp;
 }
-VLCU_HD IData VL_SCOPED_RAND_RESET_ASSIGN_I(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+VLCU_HD IData vlcu_scoped_rand_reset_assign_i(const VlcuContext& ctx, int obits, uint64_t scopeHash,
                                             uint64_t salt) {
     VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
     return static_cast<IData>(rng.rand64()) & VL_MASK_I(obits);
 }
-VLCU_HD QData VL_SCOPED_RAND_RESET_ASSIGN_Q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
+VLCU_HD QData vlcu_scoped_rand_reset_assign_q(const VlcuContext& ctx, int obits, uint64_t scopeHash,
                                             uint64_t salt) {
     VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
     return rng.rand64() & VL_MASK_Q(obits);
 }
-VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_ASSIGN_W(const VlcuContext& ctx, int obits,
+VLCU_HD WDataOutP vlcu_scoped_rand_reset_assign_w(const VlcuContext& ctx, int obits,
                                                 WDataOutP outwp, uint64_t scopeHash,
                                                 uint64_t salt) {
     VlRNG rng{ctx.randSeed() ^ scopeHash ^ salt};
@@ -299,6 +366,27 @@ VLCU_HD WDataOutP VL_SCOPED_RAND_RESET_ASSIGN_W(const VlcuContext& ctx, int obit
     outwp[words - 1] = static_cast<EData>(rng.rand64()) & VL_MASK_E(obits);
     return outwp;
 }
+
+#ifndef VL_ATTR_UNUSED
+#define VL_ATTR_UNUSED __attribute__((unused))
+#endif
+// verilated_funcs.h VL_ZERO_RESET_W: zero every limb
+VLCU_HD WDataOutP VL_ZERO_RESET_W(int obits, WDataOutP outwp) {
+    for (int i = 0; i < VL_WORDS_I(obits); ++i) outwp[i] = 0;
+    return outwp;
+}
+
+// Spellings printed by EmitCFunc::emitVarReset (V3EmitCFunc.cpp:524-666): the context is implicit
+#define VL_SCOPED_RAND_RESET_I(obits, scopeHash, salt) vlcu_scoped_rand_reset_i(vlCtx, obits, scopeHash, salt)
+#define VL_SCOPED_RAND_RESET_Q(obits, scopeHash, salt) vlcu_scoped_rand_reset_q(vlCtx, obits, scopeHash, salt)
+#define VL_SCOPED_RAND_RESET_W(obits, outwp, scopeHash, salt) \
+    vlcu_scoped_rand_reset_w(vlCtx, obits, outwp, scopeHash, salt)
+#define VL_SCOPED_RAND_RESET_ASSIGN_I(obits, scopeHash, salt) \
+    vlcu_scoped_rand_reset_assign_i(vlCtx, obits, scopeHash, salt)
+#define VL_SCOPED_RAND_RESET_ASSIGN_Q(obits, scopeHash, salt) \
+    vlcu_scoped_rand_reset_assign_q(vlCtx, obits, scopeHash, salt)
+#define VL_SCOPED_RAND_RESET_ASSIGN_W(obits, outwp, scopeHash, salt) \
+    vlcu_scoped_rand_reset_assign_w(vlCtx, obits, outwp, scopeHash, salt)
 
 //=========================================================================
 // Structure-of-arrays state block

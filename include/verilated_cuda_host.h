@@ -90,6 +90,44 @@ struct VlcuTraceDecl final {
     int32_t msb, lsb;
 };
 
+#ifdef __cplusplus
+#include <string>
+#include <vector>
+// Builder of the coverage-point table from the registrations V3EmitCuda prints, one call per
+// __vlCoverInsert / __vlCoverToggleInsert of the C++ model (V3EmitCImp.cpp:179-262): a toggle
+// registration expands to two bins per bit, "name[bit]:1->0" then ":0->1"
+struct VlcuCoverTable final {
+    std::vector<VlcuCoverPoint> points;
+    std::vector<std::string> comments;  // owns the generated comment strings
+    void resize(size_t bins) {
+        points.assign(bins, VlcuCoverPoint{"", 0, 0, "", "", "", ""});
+        comments.assign(bins, std::string{});
+    }
+    void other(int bin, const char* file, int line, int column, const char* hier, const char* page,
+               const char* comment, const char* linescov) {
+        points[bin] = VlcuCoverPoint{file, line, column, hier, page, nullptr, linescov};
+        comments[bin] = comment;
+    }
+    void toggle(int bin, int begin, int end, int ranged, const char* file, int line, int column,
+                const char* hier, const char* page, const char* comment) {
+        const int step = (end >= begin) ? 1 : -1;
+        for (int i = begin; i != end + step; i += step) {
+            for (int j = 0; j < 2; ++j) {
+                std::string c = comment;
+                if (ranged) c += '[' + std::to_string(i) + ']';
+                c += j ? ":0->1" : ":1->0";
+                points[bin] = VlcuCoverPoint{file, line, column, hier, page, nullptr, ""};
+                comments[bin] = c;
+                ++bin;
+            }
+        }
+    }
+    void finish() {
+        for (size_t i = 0; i < points.size(); ++i) points[i].comment = comments[i].c_str();
+    }
+};
+#endif
+
 struct VlcuDesignInfo final {
     const char* name;  // design name used with vlcu_create()
     const char* topName;  // Verilog top module

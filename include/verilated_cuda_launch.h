@@ -226,4 +226,8 @@ public:
     static VlcuDesignImpl<Design, ##__VA_ARGS__> s_vlcuDesign_##Design; \
     static const int s_vlcuDesignReg_##Design = vlcu_register_design(&s_vlcuDesign_##Design)
 
+// Same, with the argument list macro-expanded first (the emitted model passes the testbench
+// list as a macro: VLCU_REGISTER_DESIGN_X(Vtop__cuda VLCU_TESTBENCHES))
+#define VLCU_REGISTER_DESIGN_X(...) VLCU_REGISTER_DESIGN(__VA_ARGS__)
+
 #endif  // guard

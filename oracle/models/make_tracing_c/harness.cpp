@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE (not product code) -- oracle-side testbench harness.
 //
-// Runs N independent instances of the restated reference model of
-// examples/make_tracing_c (Vtop.cpp, against the genuine runtime) through
+// Runs N independent instances of the GENUINE Verilated model of examples/make_tracing_c
+// (oracle/_ref/gen/make_tracing_c/Vtop*.cpp, written by the reference's own V3Sched/V3Order/
+// V3EmitC through oracle/_ref/verilator_lite, linked with the reference's runtime) through
 // the stimulus of examples/make_tracing_c/sim_main.cpp:52-106, one
 // VerilatedContext + Vtop per instance as docs/guide/verilating.rst:232-236
 // allows, and records what the GPU path is compared against: every output
@@ -35,6 +36,8 @@ struct StatusRec {  // == vlcu_status_t (include/verilated_cuda_abi.h)
     uint32_t pad_;
 };
 
+constexpr int kCovBins = sizeof(Vtop___024root::__Vcoverage) / sizeof(uint32_t);
+
 inline uint64_t sigMix(uint64_t sig, uint32_t word) { return (sig ^ word) * 0x100000001b3ULL; }
 
 struct Params {
@@ -51,7 +54,7 @@ struct Params {
     uint64_t* sigs;
     StatusRec* status;
     uint32_t* finalState;  // [n][4]: count_c, clk, reset_l, in_quad lo (spot checks)
-    uint64_t* covSums;  // [527]
+    uint64_t* covSums;  // [vlref_mtc_cov_bins()]
     const char* vcdPath;
     int64_t vcdInstance;
     const char* covPath;  // coverage.dat of instance covInstance via the genuine writer
@@ -186,7 +189,7 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
         p.finalState[i * 4 + 2] = top->reset_l;
         p.finalState[i * 4 + 3] = static_cast<uint32_t>(top->in_quad);
     }
-    for (int b = 0; b < 527; ++b) covLocal[b] += top->rootp->__Vcoverage[b];
+    for (int b = 0; b < kCovBins; ++b) covLocal[b] += top->rootp->__Vcoverage[b];
     if (p.covPath && p.covInstance == static_cast<int64_t>(i)) {
         contextp->coveragep()->write(p.covPath);
     }
@@ -196,6 +199,8 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
 }
 
 }  // namespace
+
+extern "C" int vlref_mtc_cov_bins() { return kCovBins; }
 
 extern "C" int vlref_mtc_run(uint64_t n, uint64_t instBase, uint64_t seedBase, int randReset,
                              uint64_t nEvals, uint32_t runFlags, uint64_t tbSeed, uint32_t tbFlags,
@@ -209,7 +214,7 @@ extern "C" int vlref_mtc_run(uint64_t n, uint64_t instBase, uint64_t seedBase, i
              tracePlusarg, obs, obsEvals, sigs, static_cast<StatusRec*>(status), finalState,
              covSums, vcdPath, vcdInstance, covPath, covInstance, &console};
     if (threads < 1) threads = 1;
-    std::vector<std::vector<uint64_t>> cov(threads, std::vector<uint64_t>(527, 0));
+    std::vector<std::vector<uint64_t>> cov(threads, std::vector<uint64_t>(kCovBins, 0));
     vlref_loop_seconds_begin();
     if (threads == 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i, cov[0]);
@@ -230,7 +235,7 @@ extern "C" int vlref_mtc_run(uint64_t n, uint64_t instBase, uint64_t seedBase, i
         for (auto& th : pool) th.join();
     }
     if (covSums) {
-        for (int b = 0; b < 527; ++b) {
+        for (int b = 0; b < kCovBins; ++b) {
             covSums[b] = 0;
             for (int t = 0; t < threads; ++t) covSums[b] += cov[t][b];
         }

@@ -1,0 +1,145 @@
+// TEST INFRASTRUCTURE (not product code) -- oracle-side testbench harness for rv32_soc.v.
+//
+// Runs N independent instances of the GENUINE Verilated model (oracle/_ref/gen/rv32i/
+// Vrv32_soc*.cpp, written by the reference's own scheduler and emitter through
+// oracle/_ref/verilator_lite, linked with the reference's runtime), one VerilatedContext +
+// Vrv32_soc per instance (docs/guide/verilating.rst:232-236), with the stimulus of the device
+// testbenches TbRv32Rand / TbRv32Host (verilator_b200/csrc/designs/rv32i/rv32_tb.h).
+#include "Vrv32_soc.h"
+#include "Vrv32_soc___024root.h"
+#include "ref_timing.h"
+
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "rv32_program.h"
+
+//=============================================================================
+// Harness: N instances, the stimulus of the device testbenches TbRv32Rand / TbRv32Host
+
+namespace {
+inline uint64_t sigMix(uint64_t sig, uint32_t word) { return (sig ^ word) * 0x100000001b3ULL; }
+
+struct Rv32Params {
+    uint64_t n, instBase, seedBase;
+    int randReset;
+    uint64_t nEvals, tbSeed;
+    uint32_t resetTime;
+    const uint32_t* memImages;  // [n][1024] or null -> generated from tbSeed ^ global index
+    uint32_t* obs;  // [eval][8][n]
+    uint64_t obsEvals;
+    uint64_t* sigs;
+    uint64_t* times;
+    uint32_t* finalRegs;  // [n][32]
+    uint32_t* finalMem;  // [n][1024]
+    uint32_t* finalScalars;  // [n][8]: pc, insn, ld_addr, instret, state, trap, retired, clk
+    // Campaign mode (tb flag RV32_TBF_RESET_PER_RUN of the device testbench): `rounds` runs of
+    // nEvals evals on the same model; each run begins with clk = resetn = 0, a fresh program
+    // from (tbSeed + round) ^ index, and resetn low for the first resetTime evals OF THAT RUN
+    uint32_t rounds;
+};
+
+void runOne(const Rv32Params& p, uint64_t i) {
+    const std::unique_ptr<VerilatedContext> contextp{new VerilatedContext};
+    Verilated::threadContextp(contextp.get());
+    contextp->randReset(p.randReset);
+    contextp->randSeed(static_cast<int>(p.seedBase ^ (p.instBase + i)));
+    const char* argv[] = {"oracle"};
+    contextp->commandArgs(1, argv);
+    const std::unique_ptr<Vrv32_soc> top{new Vrv32_soc{contextp.get(), "TOP"}};
+    const uint64_t resetTime = p.resetTime ? p.resetTime : 16;
+    uint64_t sig = 0xcbf29ce484222325ULL;
+    const uint32_t rounds = p.rounds ? p.rounds : 1;
+    for (uint32_t round = 0; round < rounds; ++round) {
+        top->clk = 0;
+        top->resetn = 0;
+        if (p.memImages) {
+            for (int w = 0; w < 1024; ++w) top->rootp->rv32_soc__DOT__mem[w] = p.memImages[i * 1024 + w];
+        } else {
+            rv32_gen_program(top->rootp->rv32_soc__DOT__mem, (p.tbSeed + round) ^ (p.instBase + i));
+        }
+        const VlrefLoopTimer timer;
+        for (uint64_t e = 0; e < p.nEvals; ++e) {
+            contextp->timeInc(1);
+            top->clk = !top->clk;
+            top->resetn = p.rounds ? (e >= resetTime) : (contextp->time() > resetTime);
+            top->eval();
+            sig = sigMix(sig, (static_cast<uint32_t>(top->trap) << 6) | (static_cast<uint32_t>(top->mem_valid) << 5)
+                                  | (static_cast<uint32_t>(top->mem_instr) << 4) | top->mem_wstrb);
+            sig = sigMix(sig, top->mem_addr);
+            sig = sigMix(sig, top->mem_wdata);
+            sig = sigMix(sig, top->mem_rdata);
+            sig = sigMix(sig, top->retired);
+            const uint64_t ge = round * p.nEvals + e;
+            if (p.obs && ge < p.obsEvals) {
+                uint32_t* const rowp = p.obs + ge * 8 * p.n;
+                rowp[0 * p.n + i] = top->trap;
+                rowp[1 * p.n + i] = top->mem_valid;
+                rowp[2 * p.n + i] = top->mem_instr;
+                rowp[3 * p.n + i] = top->mem_addr;
+                rowp[4 * p.n + i] = top->mem_wdata;
+                rowp[5 * p.n + i] = top->mem_wstrb;
+                rowp[6 * p.n + i] = top->mem_rdata;
+                rowp[7 * p.n + i] = top->retired;
+            }
+        }
+    }
+    top->final();
+    if (p.sigs) p.sigs[i] = sig;
+    if (p.times) p.times[i] = contextp->time();
+    const Vrv32_soc___024root& r = *top->rootp;
+    if (p.finalRegs) {
+        for (int k = 0; k < 32; ++k) p.finalRegs[i * 32 + k] = r.rv32_soc__DOT__regs[k];
+    }
+    if (p.finalMem) {
+        for (int k = 0; k < 1024; ++k) p.finalMem[i * 1024 + k] = r.rv32_soc__DOT__mem[k];
+    }
+    if (p.finalScalars) {
+        uint32_t* const s = p.finalScalars + i * 8;
+        s[0] = r.rv32_soc__DOT__pc, s[1] = r.rv32_soc__DOT__insn, s[2] = r.rv32_soc__DOT__ld_addr;
+        s[3] = r.rv32_soc__DOT__instret, s[4] = r.rv32_soc__DOT__state, s[5] = r.trap;
+        s[6] = r.retired, s[7] = r.clk;
+    }
+}
+}  // namespace
+
+extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, int randReset,
+                              uint64_t nEvals, uint64_t tbSeed, uint32_t resetTime,
+                              const uint32_t* memImages, uint32_t* obs, uint64_t obsEvals,
+                              uint64_t* sigs, uint64_t* times, uint32_t* finalRegs,
+                              uint32_t* finalMem, uint32_t* finalScalars, int threads,
+                              uint32_t rounds) {
+    const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
+                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds};
+    vlref_loop_seconds_begin();
+    if (threads <= 1) {
+        for (uint64_t i = 0; i < n; ++i) runOne(p, i);
+        vlref_loop_seconds_thread_done();
+    } else {
+        std::atomic<uint64_t> next{0};
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; ++t) {
+            pool.emplace_back([&]() {
+                for (;;) {
+                    const uint64_t i = next.fetch_add(1);
+                    if (i >= n) break;
+                    runOne(p, i);
+                }
+                vlref_loop_seconds_thread_done();
+            });
+        }
+        for (auto& th : pool) th.join();
+    }
+    return 0;
+}
+
+// The program generator alone (for the instruction-set-simulator cross check)
+extern "C" void vlref_rv32_gen_program(uint64_t seed, uint32_t* out1024) {
+    VlUnpacked<IData, 1024> mem;
+    rv32_gen_program(mem, seed);
+    for (int k = 0; k < 1024; ++k) out1024[k] = mem[k];
+}

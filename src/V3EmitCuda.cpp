@@ -1,0 +1,788 @@
+// -*- mode: C++; c-file-style: "cc-mode" -*-
+//*************************************************************************
+// DESCRIPTION: Verilator: Emit the batched CUDA (sm_100a) model of the design
+//
+// V3EmitCuda prints, from the scheduled AST that V3EmitCFunc/V3EmitCImp print as
+// Vtop___024root*.cpp, one translation unit <prefix>__cuda.cu in which
+//
+//   * struct <prefix>___024root is the per-instance model image (the class
+//     EmitCHeader::emitDesignVarDecls prints, V3EmitCHeaders.cpp:73-143), held by ONE CUDA
+//     thread: scalars and VlWide values in registers, run-time indexed arrays behind
+//     VlcuSharedArray / VlcuLocalArray / VlcuGlobalArray handles;
+//   * struct <prefix>__cuda is the design policy include/verilated_cuda_launch.h drives:
+//     the structure-of-arrays slot table (OFF_*), load/store between the SoA block in HBM
+//     and the image, port row packing, every CFunc reachable from eval() as a
+//     `__device__ static` function, and the host tables (members, coverage points,
+//     $display formats, $test$plusargs strings, trace declarations);
+//   * the statements and expressions inside those functions are printed by the very visitor
+//     that prints the C++ model (this class derives from EmitCFunc, V3EmitCFunc.h:118), so
+//     every VL_* operator call, cast, mask and temporary is spelled exactly as in
+//     Vtop___024root__0.cpp; only what touches the host runtime is redirected:
+//        function headers / calls     gain the per-instance context  `VlcuContext& vlCtx`
+//        $display/$write              -> vlCtx.writef(format id, args): formatted on the host
+//        $test$plusargs               -> vlCtx.testPlusArg(index): resolved at vlcu_create()
+//        $dumpfile/$dumpvars          -> host side (vlcu_run trace sampling + vlcu_vcd_write)
+//        VL_FINISH_MT/VL_STOP_MT/VL_FATAL_MT, VL_TIME_UNITED_Q, VL_SCOPED_RAND_RESET_*,
+//        vlSymsp->_vm_contextp__->...  are macros / a shim of verilated_cuda.h
+//
+// The model must be a single $root class (the default for small designs; pass --flatten
+// otherwise); non-inlined child module classes are reported as unsupported.
+//*************************************************************************
+
+#include "V3PchAstNoMT.h"
+
+#include "V3EmitCuda.h"
+
+#include "V3EmitC.h"
+#include "V3EmitCBase.h"
+#include "V3EmitCFunc.h"
+#include "V3Stats.h"
+#include "V3String.h"
+
+#include <map>
+#include <set>
+
+VL_DEFINE_DEBUG_FUNCTIONS;
+
+namespace {
+
+enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL };
+
+struct CudaMember final {
+    const AstVar* varp = nullptr;
+    string name;  // C++ member name
+    string hier;  // Verilog name
+    int kind = 3;  // VlcuMemberKind: 0 in, 1 out, 2 inout, 3 state, 4 coverage, 5 memory
+    int elemBytes = 4;
+    uint32_t words = 1;  // 32-bit words of one (wide) element, else 1
+    uint32_t depth = 1;  // array elements, else 1
+    bool isArray = false;
+    bool isWide = false;
+    uint32_t width = 1;  // bits of one element
+    int msb = 0, lsb = 0;
+    CudaStorage storage = CudaStorage::REG;
+    uint32_t offset = 0;
+    string elemCType;  // CData SData IData QData (EData for wide limbs)
+    string elemDecl;  // C type of one element as the model declares it
+    uint32_t elems() const { return depth * words; }
+    uint32_t bytes() const { return elems() * elemBytes; }
+};
+
+// Which module arrays are indexed with something that is not a constant
+class CudaIndexVisitor final : public VNVisitorConst {
+    std::set<const AstVar*>& m_runtimeIndexed;
+    void visit(AstArraySel* nodep) override {
+        if (!VN_IS(nodep->bitp(), Const)) {
+            const AstNode* fromp = nodep->fromp();
+            while (const AstArraySel* const selp = VN_CAST(fromp, ArraySel)) fromp = selp->fromp();
+            if (const AstVarRef* const refp = VN_CAST(fromp, VarRef)) m_runtimeIndexed.insert(refp->varp());
+        }
+        iterateChildrenConst(nodep);
+    }
+    void visit(AstNode* nodep) override { iterateChildrenConst(nodep); }
+
+public:
+    CudaIndexVisitor(const AstNodeModule* modp, std::set<const AstVar*>& out)
+        : m_runtimeIndexed{out} {
+        iterateConst(const_cast<AstNodeModule*>(modp));
+    }
+};
+
+// Persistent bytes the non-slow (per eval) functions reference: scalars and wide values once if
+// read / once if written, arrays once per select site ("touched memory words only").
+// This is the static S_state_rd / S_state_wr the roofline model of bench.py uses.
+class CudaTouchVisitor final : public VNVisitorConst {
+    std::map<const AstVar*, std::pair<uint32_t, uint32_t>>& m_sites;  // var -> (read, write) sites
+    bool m_underSel = false;
+    void visit(AstCFunc* nodep) override {
+        if (nodep->slow() || nodep->isTrace() || !nodep->ifdef().empty()) return;
+        iterateChildrenConst(nodep);
+    }
+    void visit(AstArraySel* nodep) override {
+        {
+            VL_RESTORER(m_underSel);
+            m_underSel = true;
+            iterateConst(nodep->fromp());
+        }
+        iterateConst(nodep->bitp());
+    }
+    void visit(AstVarRef* nodep) override {
+        std::pair<uint32_t, uint32_t>& site = m_sites[nodep->varp()];
+        const bool isArray = VN_IS(nodep->varp()->dtypep()->skipRefp(), UnpackArrayDType);
+        if (nodep->access().isReadOrRW()) site.first = (isArray && m_underSel) ? site.first + 1 : std::max(site.first, 1U);
+        if (nodep->access().isWriteOrRW()) site.second = (isArray && m_underSel) ? site.second + 1 : std::max(site.second, 1U);
+    }
+    void visit(AstNode* nodep) override { iterateChildrenConst(nodep); }
+
+public:
+    CudaTouchVisitor(const AstNodeModule* modp, std::map<const AstVar*, std::pair<uint32_t, uint32_t>>& out)
+        : m_sites{out} {
+        iterateConst(const_cast<AstNodeModule*>(modp));
+    }
+};
+
+class EmitCudaModel final : public EmitCFunc {
+    // STATE
+    const AstNodeModule* const m_topModp;
+    const string m_rootName;  // Vtop___024root
+    const string m_designName;  // Vtop__cuda
+    std::vector<CudaMember> m_members;
+    std::map<const AstVar*, size_t> m_memberOf;
+    std::vector<string> m_messages;
+    std::vector<string> m_plusargs;
+    int m_coverBins = 0;
+    uint32_t m_stateBytes = 0;
+    bool m_coverTableMode = false;  // visiting _configure_coverage: print table rows
+    std::vector<string> m_traceRows;
+
+    // METHODS
+    static string quoted(const string& s) { return "\"" + V3OutFormatter::quoteNameControls(s) + "\""; }
+    const AstCFunc* findFunc(const string& name) const {
+        for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (const AstCFunc* const funcp = VN_CAST(nodep, CFunc)) {
+                if (funcp->name() == name) return funcp;
+            }
+        }
+        return nullptr;
+    }
+    bool isDeviceFunc(const AstCFunc* funcp) const {
+        // The selection of EmitCImp::emitCFuncImp (V3EmitCImp.cpp:410-425), minus what only the
+        // host can run
+        if (funcp->isTrace()) return false;
+        if (funcp->dpiImportPrototype() || funcp->dpiExportDispatcher()) return false;
+        if (funcp->isConstructor() || funcp->isDestructor()) return false;
+        if (!funcp->ifdef().empty()) return false;  // VL_DEBUG only (_eval_debug_assertions, dumps)
+        const string& name = funcp->name();
+        if (name.find("_dump_triggers") != string::npos) return false;
+        if (name == "_configure_coverage" || name == "__Vconfigure") return false;
+        return true;
+    }
+
+    // ---- layout ----------------------------------------------------------------
+    void analyzeVar(const AstVar* varp, const std::set<const AstVar*>& runtimeIndexed) {
+        CudaMember m;
+        m.varp = varp;
+        m.name = varp->nameProtect();
+        m.hier = varp->prettyName();
+        if (varp->isPrimaryIO()) {
+            m.kind = varp->isInout() ? 2 : varp->isWritable() ? 1 : 0;
+        }
+        const AstNodeDType* dtp = varp->dtypep()->skipRefp();
+        if (const AstUnpackArrayDType* const adtp = VN_CAST(dtp, UnpackArrayDType)) {
+            m.isArray = true;
+            m.depth = adtp->elementsConst();
+            dtp = adtp->subDTypep()->skipRefp();
+            if (VN_IS(dtp, UnpackArrayDType)) {
+                varp->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: multidimensional unpacked array "
+                                                << varp->prettyNameQ());
+                return;
+            }
+        }
+        if (!dtp->isIntegralOrPacked()) {
+            varp->v3warn(E_UNSUPPORTED,
+                         "Unsupported: --cuda: variable of non-integral type " << varp->prettyNameQ());
+            return;
+        }
+        m.width = dtp->width();
+        m.elemDecl = dtp->cType("", false, false);
+        if (const AstBasicDType* const bdtp = dtp->basicp()) {
+            m.msb = bdtp->hi();
+            m.lsb = bdtp->lo();
+        } else {
+            m.msb = m.width - 1;
+        }
+        if (dtp->isWide()) {
+            m.isWide = true;
+            m.words = dtp->widthWords();
+            m.elemBytes = 4;
+            m.elemCType = "EData";
+        } else if (m.width <= 8) {
+            m.elemBytes = 1, m.elemCType = "CData";
+        } else if (m.width <= 16) {
+            m.elemBytes = 2, m.elemCType = "SData";
+        } else if (m.width <= 32) {
+            m.elemBytes = 4, m.elemCType = "IData";
+        } else {
+            m.elemBytes = 8, m.elemCType = "QData";
+        }
+        if (m.isArray) {
+            // Where a per-instance array lives (DESIGN.md "run-time indexed arrays"):
+            //   registers      small and only ever indexed with constants (trigger vectors)
+            //   shared memory  small and run-time indexed: [index][lane] is bank-conflict free
+            //   local memory   medium: thread private, L1 resident
+            //   HBM            large memories, instance-major so one instance's accesses share sectors
+            const bool runtime = runtimeIndexed.count(varp) != 0;
+            const uint32_t bytes = m.bytes();
+            if (!runtime && m.elems() <= 16) {
+                m.storage = CudaStorage::REG;
+            } else if (runtime && bytes <= 256 && !m.isWide) {
+                m.storage = CudaStorage::SHARED;
+            } else if (bytes <= 2048) {
+                m.storage = CudaStorage::LOCAL;
+            } else {
+                m.storage = CudaStorage::GLOBAL;
+                m.kind = 5;
+            }
+        }
+        m_members.push_back(m);
+    }
+    void computeLayout() {
+        std::set<const AstVar*> runtimeIndexed;
+        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed}; }
+        for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (const AstVar* const varp = VN_CAST(nodep, Var)) {
+                // Same test as EmitCHeader::emitDesignVarDecls (V3EmitCHeaders.cpp:133-135)
+                if (varp->isIO() || varp->isSignal() || varp->isClassMember() || varp->isTemp()
+                    || varp->isGenVar()) {
+                    if (varp->isStatic()) continue;
+                    analyzeVar(varp, runtimeIndexed);
+                }
+            } else if (const AstCell* const cellp = VN_CAST(nodep, Cell)) {
+                cellp->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: module instance "
+                                                 << cellp->prettyNameQ()
+                                                 << " was not inlined; use --flatten");
+            }
+        }
+        // Coverage bins of this module: the counters are one more (local memory) array
+        m_topModp->foreach([&](const AstNodeCoverDecl* declp) {
+            m_coverBins = std::max(m_coverBins, declp->localBinNum() + declp->size());
+        });
+        // Offsets: largest elements first so that every array start is aligned for its type
+        // (an offset is multiplied by the padded instance count, a multiple of 128)
+        uint32_t offset = 0;
+        for (const int bytes : {8, 4, 2, 1}) {
+            for (CudaMember& m : m_members) {
+                if (m.elemBytes != bytes) continue;
+                m.offset = offset;
+                offset += m.bytes();
+            }
+            if (bytes == 4 && m_coverBins) {
+                CudaMember cov;
+                cov.name = "__Vcoverage";
+                cov.kind = 4;
+                cov.elemBytes = 4;
+                cov.depth = m_coverBins;
+                cov.isArray = true;
+                cov.width = 32;
+                cov.msb = 31;
+                cov.storage = CudaStorage::LOCAL;
+                cov.elemCType = "uint32_t";
+                cov.elemDecl = "uint32_t";
+                cov.offset = offset;
+                offset += cov.bytes();
+                m_pendingCoverage = cov;
+            }
+        }
+        if (m_coverBins) m_members.push_back(m_pendingCoverage);
+        m_stateBytes = (offset + 7U) & ~7U;
+        // Touched bytes per eval (static)
+        std::map<const AstVar*, std::pair<uint32_t, uint32_t>> sites;
+        { const CudaTouchVisitor visitor{m_topModp, sites}; }
+        for (const CudaMember& m : m_members) {
+            if (!m.varp) continue;
+            const auto it = sites.find(m.varp);
+            if (it == sites.end()) continue;
+            const uint32_t elemBytes = m.words * m.elemBytes;
+            if (m.isArray) {
+                m_touchedRead += std::min(m.bytes(), it->second.first * elemBytes);
+                m_touchedWrite += std::min(m.bytes(), it->second.second * elemBytes);
+            } else {
+                m_touchedRead += it->second.first ? elemBytes : 0;
+                m_touchedWrite += it->second.second ? elemBytes : 0;
+            }
+        }
+        for (size_t i = 0; i < m_members.size(); ++i) {
+            if (m_members[i].varp) m_memberOf[m_members[i].varp] = i;
+        }
+    }
+    CudaMember m_pendingCoverage;
+    uint32_t m_touchedRead = 0, m_touchedWrite = 0;
+
+    // ---- model struct ------------------------------------------------------------
+    static string handleDecl(const CudaMember& m) {
+        const string depth = cvtToStr(m.depth);
+        switch (m.storage) {
+        case CudaStorage::SHARED: return "VlcuSharedArray<" + m.elemDecl + ", " + depth + "> " + m.name;
+        case CudaStorage::LOCAL: return "VlcuLocalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
+        case CudaStorage::GLOBAL: return "VlcuGlobalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
+        default: return "";
+        }
+    }
+    void emitRootStruct() {
+        puts("\n// The model image of one instance (Vtop___024root of the C++ model), held by one thread\n");
+        puts("struct " + m_rootName + " final {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.storage == CudaStorage::REG) {
+                puts(m.varp->vlArgType(true, false, false) + ";\n");
+            } else {
+                puts(handleDecl(m) + ";");
+                puts(m.storage == CudaStorage::SHARED  ? "  // run-time indexed: shared memory [index][lane]\n"
+                     : m.storage == CudaStorage::LOCAL ? "  // thread-local memory\n"
+                                                       : "  // stays in HBM, instance-major\n");
+            }
+        }
+        puts("const char* vlNamep;\n");
+        puts("};\n");
+    }
+
+    // ---- SoA load / store ----------------------------------------------------------
+    void emitLoadStore(bool load) {
+        puts(load ? "VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {\n"
+                  : "VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.storage == CudaStorage::GLOBAL) continue;
+            const string off = "OFF_" + m.name;
+            if (!m.isArray && !m.isWide) {
+                puts(load ? "s." + m.name + " = st.ld<" + m.elemCType + ">(" + off + ", i);\n"
+                          : "st.st<" + m.elemCType + ">(" + off + ", i, s." + m.name + ");\n");
+            } else if (!m.isArray) {
+                puts(load ? "st.ldW(" + off + ", i, s." + m.name + ");\n"
+                          : "st.stW(" + off + ", i, s." + m.name + ");\n");
+            } else if (!m.isWide) {
+                puts("for (uint32_t e = 0; e < " + cvtToStr(m.depth) + "; ++e) ");
+                puts(load ? "s." + m.name + "[e] = st.ldE<" + m.elemCType + ">(" + off + ", e, i);\n"
+                          : "st.stE<" + m.elemCType + ">(" + off + ", e, i, s." + m.name + "[e]);\n");
+            } else {
+                const string words = cvtToStr(m.words);
+                puts("for (uint32_t e = 0; e < " + cvtToStr(m.depth) + "; ++e) {\n");
+                puts("for (uint32_t w = 0; w < " + words + "; ++w) ");
+                puts(load ? "s." + m.name + "[e][w] = st.ldE<EData>(" + off + ", e * " + words + " + w, i);\n"
+                          : "st.stE<EData>(" + off + ", e * " + words + " + w, i, s." + m.name + "[e][w]);\n");
+                puts("}\n");
+            }
+        }
+        puts("}\n");
+    }
+
+    // ---- port rows --------------------------------------------------------------------
+    static uint32_t rowWords(const CudaMember& m) { return m.isWide ? m.words : (m.elemBytes == 8 ? 2 : 1); }
+    static string maskOf(int bits) {
+        if (bits >= 32) return "0xffffffffU";
+        std::ostringstream os;
+        os << "0x" << std::hex << ((1ULL << bits) - 1ULL) << "U";
+        return os.str();
+    }
+    void emitPortRows() {
+        uint32_t inWords = 0, outWords = 0, inBytes = 0, outBytes = 0;
+        // One 32-bit row word per limb; values are masked to the declared width on ingest (the
+        // C++ model assumes clean inputs, V3CCtors.cpp:240-280)
+        puts("VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.kind != 0 && m.kind != 2) continue;
+            if (m.isArray) continue;
+            const string w0 = "rowp[" + cvtToStr(inWords) + " * stride + i]";
+            if (m.isWide) {
+                for (uint32_t w = 0; w < m.words; ++w) {
+                    const int bits = (w == m.words - 1) ? (m.width - 32 * w) : 32;
+                    puts("s." + m.name + "[" + cvtToStr(w) + "] = rowp[" + cvtToStr(inWords + w)
+                         + " * stride + i] & " + maskOf(bits) + ";\n");
+                }
+            } else if (m.elemBytes == 8) {
+                puts("s." + m.name + " = (static_cast<QData>(rowp[" + cvtToStr(inWords + 1) + " * stride + i] & "
+                     + maskOf(m.width - 32) + ") << 32) | " + w0 + ";\n");
+            } else {
+                puts("s." + m.name + " = static_cast<" + m.elemCType + ">(" + w0 + " & " + maskOf(m.width) + ");\n");
+            }
+            inWords += rowWords(m);
+            inBytes += m.bytes();
+        }
+        puts("}\n");
+        string sigBody;
+        puts("VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.kind != 1 && m.kind != 2) continue;
+            if (m.isArray) continue;
+            for (uint32_t w = 0; w < rowWords(m); ++w) {
+                string value;
+                if (m.isWide) {
+                    value = "s." + m.name + "[" + cvtToStr(w) + "]";
+                } else if (m.elemBytes == 8) {
+                    value = "static_cast<uint32_t>(s." + m.name + (w ? " >> 32)" : ")");
+                } else {
+                    value = "s." + m.name;
+                }
+                puts("rowp[" + cvtToStr(outWords + w) + " * stride + i] = " + value + ";\n");
+                sigBody += "sig = vlcu_sig_mix(sig, " + value + ");\n";
+            }
+            outWords += rowWords(m);
+            outBytes += m.bytes();
+        }
+        puts("}\n");
+        puts("VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {\n" + sigBody + "return sig;\n}\n");
+        m_sizes = "kInWords = " + cvtToStr(inWords) + ", kOutWords = " + cvtToStr(outWords)
+                  + ", kInBytes = " + cvtToStr(inBytes) + ", kOutBytes = " + cvtToStr(outBytes);
+    }
+    string m_sizes;
+
+    // ---- functions -----------------------------------------------------------------------
+    string cudaFuncArgs(const AstCFunc* nodep) {
+        // cFuncArgs (V3EmitCBase.cpp:97-133) with the context after the self pointer
+        string args;
+        if (nodep->isLoose() && !nodep->isStatic()) args += m_rootName + "* vlSelf, VlcuContext& vlCtx";
+        if (!nodep->argTypes().empty()) {
+            if (!args.empty()) args += ", ";
+            args += nodep->argTypes();
+        }
+        for (const AstNode* stmtp = nodep->argsp(); stmtp; stmtp = stmtp->nextp()) {
+            if (const AstVar* const portp = VN_CAST(stmtp, Var)) {
+                if (portp->isIO() && !portp->isFuncReturn()) {
+                    if (!args.empty()) args += ", ";
+                    args += portp->vlArgType(true, false, true);
+                }
+            }
+        }
+        return args;
+    }
+
+    // VISITORS
+    using EmitCFunc::visit;
+    void visit(AstCFunc* nodep) override {
+        // EmitCFunc::visit(AstCFunc*) (V3EmitCFunc.h:398-500) for a device function
+        VL_RESTORER(m_useSelfForThis);
+        VL_RESTORER(m_cfuncp);
+        m_cfuncp = nodep;
+        puts("\n");
+        putns(nodep, "VLCU_D static " + nodep->rtnTypeVoid() + " " + funcNameProtect(nodep, m_topModp) + "("
+                         + cudaFuncArgs(nodep) + ") {\n");
+        // VL_FATAL_MT leaves the function (the C++ model aborts the process there)
+        puts("typedef " + nodep->rtnTypeVoid() + " VlcuFuncRet;\n");
+        if (nodep->isLoose() && !nodep->isStatic()) {
+            m_useSelfForThis = true;
+            m_usevlSelfRef = true;
+            puts("auto& vlSelfRef = *vlSelf;\n");
+            // literal C text of the scheduler refers to vlSymsp->_vm_contextp__
+            puts("const VlcuSymsShim vlSymsShim{&vlCtx};\n");
+            puts("const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;\n");
+        }
+        for (AstNode* subnodep = nodep->argsp(); subnodep; subnodep = subnodep->nextp()) {
+            if (AstVar* const varp = VN_CAST(subnodep, Var)) {
+                if (varp->isFuncReturn()) emitVarDecl(varp);
+            }
+        }
+        if (nodep->varsp()) {
+            putsDecoration(nodep, "// Locals\n");
+            iterateAndNextConstNull(nodep->varsp());
+        }
+        if (nodep->stmtsp()) {
+            putsDecoration(nodep, "// Body\n");
+            iterateAndNextConstNull(nodep->stmtsp());
+        }
+        m_usevlSelfRef = false;
+        puts("}\n");
+    }
+    void visit(AstCCall* nodep) override {
+        // EmitCFunc::visit(AstCCall*) + emitCCallArgs (V3EmitCFunc.h:753-779, V3EmitCFunc.cpp:368-395)
+        const AstCFunc* const funcp = nodep->funcp();
+        UASSERT_OBJ(funcp->isLoose() || funcp->isStatic(), nodep, "--cuda: call to a proper method");
+        putnbs(nodep, "");
+        putns(nodep, funcNameProtect(funcp, m_topModp));
+        puts("(");
+        bool comma = false;
+        if (funcp->isLoose() && !funcp->isStatic()) {
+            puts("vlSelf, vlCtx");
+            comma = true;
+        }
+        putCommaIterateNext(nodep->argsp(), comma);
+        puts(")");
+    }
+    void visit(AstDisplay* nodep) override {
+        // $display/$write/$error text: the instance logs (format id, arguments); the host formats
+        // it (vlcu_messages).  %m is resolved here, as displayNode passes it (V3EmitCFunc.cpp:310-317)
+        string text = nodep->fmtp()->text();
+        if (nodep->addNewline()) text += "\n";
+        if (const AstScopeName* const scopenamep = nodep->fmtp()->scopeNamep()) {
+            const string scope = "TOP." + scopenamep->scopePrettySymName();
+            string::size_type pos;
+            while ((pos = text.find("%m")) != string::npos) text.replace(pos, 2, scope);
+        }
+        size_t id = 0;
+        for (; id < m_messages.size(); ++id) {
+            if (m_messages[id] == text) break;
+        }
+        if (id == m_messages.size()) m_messages.push_back(text);
+        int nargs = 0;
+        for (AstNode* argp = nodep->fmtp()->exprsp(); argp; argp = argp->nextp()) ++nargs;
+        if (nargs > 4) nodep->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: more than 4 $display arguments");
+        putns(nodep, "vlCtx.writef(" + cvtToStr(id) + "U, " + cvtToStr(nargs) + "U");
+        for (AstNode* argp = nodep->fmtp()->exprsp(); argp; argp = argp->nextp()) {
+            AstSFormatArg* const fargp = VN_CAST(argp, SFormatArg);
+            AstNode* const subargp = fargp ? fargp->exprp() : argp;
+            puts(", vlcu_msg_arg(");
+            iterateConst(subargp);
+            puts(")");
+        }
+        puts(");\n");
+    }
+    void visit(AstDumpCtl* nodep) override {
+        putsDecoration(nodep, "// $dumpfile/$dumpvars: waveforms are written on the host (vlcu_vcd_write)\n");
+    }
+    void visit(AstTestPlusArgs* nodep) override {
+        const AstConst* const constp = VN_CAST(nodep->searchp(), Const);
+        if (!constp) {
+            nodep->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: $test$plusargs of a non-constant string");
+            puts("0U");
+            return;
+        }
+        const string text = constp->num().toString();
+        size_t id = 0;
+        for (; id < m_plusargs.size(); ++id) {
+            if (m_plusargs[id] == text) break;
+        }
+        if (id == m_plusargs.size()) m_plusargs.push_back(text);
+        putns(nodep, "static_cast<IData>(vlCtx.testPlusArg(" + cvtToStr(id) + "U))");
+    }
+    // _configure_coverage: each registration becomes a row of the host coverage table
+    void visit(AstCoverOtherDecl* nodep) override {
+        if (!m_coverTableMode) return;
+        puts("t.other(" + cvtToStr(nodep->localBinNum()) + ", ");
+        putsQuoted(protect(nodep->fileline()->filename()));
+        puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", "
+             + cvtToStr(nodep->offset() + nodep->fileline()->firstColumn()) + ", ");
+        putsQuoted((!nodep->hier().empty() ? "." : "") + nodep->hier());
+        puts(", ");
+        putsQuoted(nodep->page());
+        puts(", ");
+        putsQuoted(nodep->comment());
+        puts(", ");
+        putsQuoted(nodep->linescov());
+        puts(");\n");
+    }
+    void visit(AstCoverToggleDecl* nodep) override {
+        if (!m_coverTableMode) return;
+        puts("t.toggle(" + cvtToStr(nodep->localBinNum()) + ", " + cvtToStr(nodep->range().right()) + ", "
+             + cvtToStr(nodep->range().left()) + ", " + cvtToStr(nodep->range().ranged()) + ", ");
+        putsQuoted(protect(nodep->fileline()->filename()));
+        puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", " + cvtToStr(nodep->fileline()->firstColumn())
+             + ", ");
+        putsQuoted((!nodep->hier().empty() ? "." : "") + nodep->hier());
+        puts(", ");
+        putsQuoted(nodep->page());
+        puts(", ");
+        putsQuoted(nodep->comment());
+        puts(");\n");
+    }
+
+    // ---- trace declarations (trace_init_top and the functions it calls) -------------------
+    void traceRows(const AstNode* stmtsp) {
+        for (const AstNode* nodep = stmtsp; nodep; nodep = nodep->nextp()) {
+            if (const AstTracePushPrefix* const pushp = VN_CAST(nodep, TracePushPrefix)) {
+                m_traceRows.push_back("{VLCU_TRACE_PUSH, 0, " + quoted(pushp->prefix()) + ", 0, -1, -1, 0, 0}");
+            } else if (VN_IS(nodep, TracePopPrefix)) {
+                m_traceRows.push_back("{VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}");
+            } else if (const AstTraceDecl* const declp = VN_CAST(nodep, TraceDecl)) {
+                traceDeclRow(declp);
+            } else if (const AstStmtExpr* const stmtp = VN_CAST(nodep, StmtExpr)) {
+                if (const AstCCall* const callp = VN_CAST(stmtp->exprp(), CCall)) traceRows(callp->funcp()->stmtsp());
+            } else if (const AstCCall* const callp = VN_CAST(nodep, CCall)) {
+                traceRows(callp->funcp()->stmtsp());
+            }
+        }
+    }
+    void traceDeclRow(const AstTraceDecl* declp) {
+        // The traced value must be a model variable (or one element of one)
+        const AstNode* valuep = declp->valuep();
+        int elem = -1;
+        if (const AstArraySel* const selp = VN_CAST(valuep, ArraySel)) {
+            if (const AstConst* const idxp = VN_CAST(selp->bitp(), Const)) {
+                elem = idxp->toSInt();
+                valuep = selp->fromp();
+            }
+        }
+        const AstVarRef* const refp = VN_CAST(valuep, VarRef);
+        const auto it = refp ? m_memberOf.find(refp->varp()) : m_memberOf.end();
+        if (it == m_memberOf.end()) return;  // an expression or constant: not sampled
+        const CudaMember& m = m_members[it->second];
+        const VNumRange& bits = declp->bitRange();
+        const int msb = bits.ranged() ? bits.left() : 0;
+        const int lsb = bits.ranged() ? bits.right() : 0;
+        const uint32_t codeWords = (m.width + 31) / 32;
+        if (declp->arrayRange().ranged() && elem < 0) {
+            for (int i = 0; i < declp->arrayRange().elements(); ++i) {
+                m_traceRows.push_back("{VLCU_TRACE_SIG, " + cvtToStr(bits.ranged() ? 1 : 0) + ", "
+                                      + quoted(declp->showname()) + ", " + cvtToStr(declp->code() + i * codeWords)
+                                      + ", " + cvtToStr(it->second) + ", " + cvtToStr(i) + ", " + cvtToStr(msb)
+                                      + ", " + cvtToStr(lsb) + "}");
+            }
+        } else {
+            m_traceRows.push_back("{VLCU_TRACE_SIG, " + cvtToStr(bits.ranged() ? 1 : 0) + ", "
+                                  + quoted(declp->showname()) + ", " + cvtToStr(declp->code()) + ", "
+                                  + cvtToStr(it->second) + ", " + cvtToStr(elem) + ", " + cvtToStr(msb) + ", "
+                                  + cvtToStr(lsb) + "}");
+        }
+    }
+
+    // ---- the file ---------------------------------------------------------------------------
+    void emitWrapper(const string& wrapper, const string& funcName, bool withCtxOnly = false) {
+        const AstCFunc* const funcp = findFunc(funcName);
+        puts("VLCU_D static void " + wrapper + "(Root* vlSelf, VlcuContext& vlCtx) {");
+        if (funcp && isDeviceFunc(funcp)) {
+            puts(" " + funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx); }\n");
+        } else {
+            puts(" (void)vlSelf; (void)vlCtx; }\n");
+        }
+        (void)withCtxOnly;
+    }
+    void emitAll() {
+        const string fileName = v3Global.opt.makeDir() + "/" + m_designName + ".cu";
+        AstCFile* const cfilep = new AstCFile{v3Global.rootp()->fileline(), fileName};
+        cfilep->support(true);
+        openOutputFile(cfilep, "Batched CUDA model (one instance per thread) for include/verilated_cuda.h");
+        puts("// Design '" + v3Global.rootp()->topModulep()->prettyName() + "' printed by V3EmitCuda; compile with\n");
+        puts("//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include\n");
+        puts("\n#include \"verilated_cuda_launch.h\"\n");
+        puts("\n#include <vector>\n");
+        puts("\n// Name the design registers under with vlcu_create()\n");
+        puts("#ifndef VLCU_DESIGN_NAME\n#define VLCU_DESIGN_NAME " + quoted(v3Global.opt.prefix()) + "\n#endif\n");
+        emitRootStruct();
+
+        puts("\nstruct " + m_designName + " final {\n");
+        puts("typedef " + m_rootName + " Root;\n");
+        // Slot table
+        puts("// Structure-of-arrays slot table: byte offset per instance of every persistent member\n");
+        puts("enum : uint32_t {\n");
+        for (const CudaMember& m : m_members) puts("OFF_" + m.name + " = " + cvtToStr(m.offset) + ",\n");
+        puts("kStateBytes = " + cvtToStr(m_stateBytes) + ",  // S_persist\n");
+        puts("kTouchedReadBytes = " + cvtToStr(m_touchedRead) + ",  // S_state_rd: persistent bytes one eval can read\n");
+        puts("kTouchedWriteBytes = " + cvtToStr(m_touchedWrite) + ",  // S_state_wr\n");
+        // port rows are emitted later but the enum needs the sizes: collect first
+        V3OutCFile* const realOfp = ofp();
+        (void)realOfp;
+        puts("};\n");
+        // Storage of the arrays that are not in registers
+        puts("struct Locals final {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.storage == CudaStorage::LOCAL) puts(m.elemDecl + " " + m.name + "[" + cvtToStr(m.depth) + "];\n");
+        }
+        puts("};\n");
+        puts("struct Shared final {\n");
+        for (const CudaMember& m : m_members) {
+            if (m.storage == CudaStorage::SHARED) {
+                puts(m.elemDecl + " " + m.name + "[" + cvtToStr(m.depth) + "][VLCU_BLOCK];\n");
+            }
+        }
+        puts("};\n");
+        puts("VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {\n");
+        puts("(void)l; (void)sh; (void)st; (void)i;\n");
+        puts("s.vlNamep = \"TOP\";\n");
+        for (const CudaMember& m : m_members) {
+            if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
+            if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
+            if (m.storage == CudaStorage::GLOBAL) puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
+        }
+        puts("}\n");
+        emitLoadStore(true);
+        emitLoadStore(false);
+        emitPortRows();
+        puts("enum : uint32_t { " + m_sizes + " };\n");
+
+        // Device functions
+        for (AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (AstCFunc* const funcp = VN_CAST(nodep, CFunc)) {
+                if (isDeviceFunc(funcp)) iterateConst(funcp);
+            }
+        }
+        // Entry points of the launch templates = what Vtop::eval_step() calls
+        // (EmitCModel::emitStandardMethods1, V3EmitCModel.cpp:403-437)
+        puts("\n");
+        emitWrapper("ctor_var_reset", "_ctor_var_reset");
+        emitWrapper("eval_static", "_eval_static");
+        emitWrapper("eval_initial", "_eval_initial");
+        emitWrapper("eval_settle", "_eval_settle");
+        emitWrapper("eval", "_eval");
+        emitWrapper("eval_final", "_eval_final");
+        puts("\nstatic const VlcuDesignInfo& info();\n");
+        puts("};\n");
+
+        emitHostTables();
+        puts("\n// The device testbenches of this design (the user's C++ main loop, on the GPU)\n");
+        puts("#ifdef VLCU_TESTBENCH_INCLUDE\n#include VLCU_TESTBENCH_INCLUDE\n#endif\n");
+        puts("#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB\n");
+        puts("#define VLCU_TESTBENCHES\n#endif\n");
+        puts("VLCU_REGISTER_DESIGN_X(" + m_designName + " VLCU_TESTBENCHES);\n");
+        closeOutputFile();
+    }
+    void emitHostTables() {
+        // The user's top module: first component of the internal signals' hierarchical names
+        string topName = v3Global.opt.prefix();
+        for (const CudaMember& m : m_members) {
+            const string::size_type dot = m.hier.find('.');
+            if (m.varp && dot != string::npos && m.hier[0] != '_') {
+                topName = m.hier.substr(0, dot);
+                break;
+            }
+        }
+        puts("\n//======================================================================\n");
+        puts("// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime\n");
+        puts("\nconst VlcuDesignInfo& " + m_designName + "::info() {\n");
+        puts("typedef " + m_designName + " T;\n");
+        puts("// name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset\n");
+        puts("static const VlcuMemberDesc members[] = {\n");
+        for (const CudaMember& m : m_members) {
+            static const char* const kinds[]
+                = {"VLCU_MEMBER_IN", "VLCU_MEMBER_OUT", "VLCU_MEMBER_INOUT", "VLCU_MEMBER_STATE",
+                   "VLCU_MEMBER_COVERAGE", "VLCU_MEMBER_MEMORY"};
+            puts("{" + quoted(m.name) + ", " + (m.varp ? quoted(m.hier) : string{"nullptr"}) + ", " + kinds[m.kind]
+                 + ", " + cvtToStr(m.elemBytes) + ", 0, " + cvtToStr(m.elems()) + ", " + cvtToStr(m.width) + ", "
+                 + cvtToStr(m.msb) + ", " + cvtToStr(m.lsb) + ", T::OFF_" + m.name + "},\n");
+        }
+        puts("};\n");
+        // Coverage
+        if (m_coverBins) {
+            puts("static VlcuCoverTable t;\n");
+            puts("if (t.points.empty()) {\n");
+            puts("t.resize(" + cvtToStr(m_coverBins) + ");\n");
+            if (const AstCFunc* const funcp = findFunc("_configure_coverage")) {
+                VL_RESTORER(m_coverTableMode);
+                m_coverTableMode = true;
+                for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
+                    if (VN_IS(stmtp, NodeCoverDecl)) iterateConst(stmtp);
+                }
+            }
+            puts("t.finish();\n");
+            puts("}\n");
+        }
+        // Messages and plusargs
+        puts("static const char* const messages[] = {");
+        for (const string& s : m_messages) puts(quoted(s) + ", ");
+        puts("nullptr};\n");
+        puts("static const char* const plusargs[] = {");
+        for (const string& s : m_plusargs) puts(quoted(s) + ", ");
+        puts("nullptr};\n");
+        // Trace declarations
+        if (const AstCFunc* const funcp = findFunc("trace_init_top")) traceRows(funcp->stmtsp());
+        puts("static const VlcuTraceDecl traceDecls[] = {\n");
+        for (const string& row : m_traceRows) puts(row + ",\n");
+        puts("{VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}};  // (terminator, not counted)\n");
+        puts("static const VlcuDesignInfo s = {\n");
+        puts("VLCU_DESIGN_NAME, " + quoted(topName) + ", members, sizeof(members) / sizeof(members[0]),\n");
+        puts("T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, "
+             "T::kTouchedWriteBytes,\n");
+        if (m_coverBins) {
+            puts("t.points.data(), static_cast<uint32_t>(t.points.size()), T::OFF___Vcoverage,\n");
+        } else {
+            puts("nullptr, 0, 0,\n");
+        }
+        puts("messages, " + cvtToStr(m_messages.size()) + ", plusargs, " + cvtToStr(m_plusargs.size()) + ",\n");
+        puts(m_traceRows.empty() ? "nullptr, 0};\n" : "traceDecls, " + cvtToStr(m_traceRows.size()) + "};\n");
+        puts("return s;\n}\n");
+    }
+
+public:
+    EmitCudaModel()
+        : m_topModp{v3Global.rootp()->topModulep()}
+        , m_rootName{EmitCUtil::prefixNameProtect(v3Global.rootp()->topModulep())}
+        , m_designName{v3Global.opt.prefix() + "__cuda"} {
+        m_modp = m_topModp;
+        computeLayout();
+        emitAll();
+        V3Stats::addStat("CUDA model, persistent bytes per instance", m_stateBytes);
+    }
+};
+
+}  // namespace
+
+void V3EmitCuda::emitCuda() {
+    UINFO(2, __FUNCTION__ << ":");
+    const EmitCParentModule emitCParentModule;  // user4p -> parent module, as V3EmitC::emitcImp does
+    { const EmitCudaModel emitter; }
+}

@@ -76,7 +76,7 @@ def mtc_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, stop_on_finish=False,
     r.sigs = np.zeros(n, dtype=np.uint64)
     r.status = np.zeros(n, dtype=STATUS_DTYPE)
     r.final = np.zeros((n, 4), dtype=np.uint32)
-    r.cov = np.zeros(527, dtype=np.uint64)
+    r.cov = np.zeros(ref().vlref_mtc_cov_bins(), dtype=np.uint64)
     con = ctypes.create_string_buffer(1 << 16)
     rc = ref().vlref_mtc_run(
         n, inst_base, seed, rand_reset, n_evals, 2 if stop_on_finish else 0, tb_seed,

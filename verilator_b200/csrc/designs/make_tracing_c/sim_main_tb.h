@@ -63,4 +63,7 @@ struct TbSimMain final {
     }
 };
 
+// Registered with the design (VLCU_REGISTER_DESIGN at the end of the emitted model)
+#define VLCU_TESTBENCHES , TbSimMain
+
 #endif  // guard
