@@ -68,10 +68,13 @@ void runOne(const Rv32Params& p, uint64_t i) {
             top->clk = !top->clk;
             top->resetn = p.rounds ? (e >= resetTime) : (contextp->time() > resetTime);
             top->eval();
-            sig = sigMix(sig, (static_cast<uint32_t>(top->trap) << 6) | (static_cast<uint32_t>(top->mem_valid) << 5)
-                                  | (static_cast<uint32_t>(top->mem_instr) << 4) | top->mem_wstrb);
+            // every output port in source order, as the emitted outputs_sig() does
+            sig = sigMix(sig, top->trap);
+            sig = sigMix(sig, top->mem_valid);
+            sig = sigMix(sig, top->mem_instr);
             sig = sigMix(sig, top->mem_addr);
             sig = sigMix(sig, top->mem_wdata);
+            sig = sigMix(sig, top->mem_wstrb);
             sig = sigMix(sig, top->mem_rdata);
             sig = sigMix(sig, top->retired);
             const uint64_t ge = round * p.nEvals + e;

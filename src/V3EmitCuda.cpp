@@ -362,14 +362,30 @@ class EmitCudaModel final : public EmitCFunc {
         os << "0x" << std::hex << ((1ULL << bits) - 1ULL) << "U";
         return os.str();
     }
+    // Ports in SOURCE declaration order (V3VariableOrder has sorted the members by size): the
+    // order of the stimulus / observation rows and of the output signature
+    std::vector<const CudaMember*> portsInSourceOrder() const {
+        std::vector<const CudaMember*> ports;
+        for (const CudaMember& m : m_members) {
+            if (m.varp && m.kind <= 2 && !m.isArray) ports.push_back(&m);
+        }
+        std::stable_sort(ports.begin(), ports.end(), [](const CudaMember* ap, const CudaMember* bp) {
+            const FileLine* const afl = ap->varp->fileline();
+            const FileLine* const bfl = bp->varp->fileline();
+            if (afl->lineno() != bfl->lineno()) return afl->lineno() < bfl->lineno();
+            return afl->firstColumn() < bfl->firstColumn();
+        });
+        return ports;
+    }
     void emitPortRows() {
         uint32_t inWords = 0, outWords = 0, inBytes = 0, outBytes = 0;
+        const std::vector<const CudaMember*> ports = portsInSourceOrder();
         // One 32-bit row word per limb; values are masked to the declared width on ingest (the
         // C++ model assumes clean inputs, V3CCtors.cpp:240-280)
         puts("VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {\n");
-        for (const CudaMember& m : m_members) {
+        for (const CudaMember* const mp : ports) {
+            const CudaMember& m = *mp;
             if (m.kind != 0 && m.kind != 2) continue;
-            if (m.isArray) continue;
             const string w0 = "rowp[" + cvtToStr(inWords) + " * stride + i]";
             if (m.isWide) {
                 for (uint32_t w = 0; w < m.words; ++w) {
@@ -389,9 +405,9 @@ class EmitCudaModel final : public EmitCFunc {
         puts("}\n");
         string sigBody;
         puts("VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {\n");
-        for (const CudaMember& m : m_members) {
+        for (const CudaMember* const mp : ports) {
+            const CudaMember& m = *mp;
             if (m.kind != 1 && m.kind != 2) continue;
-            if (m.isArray) continue;
             for (uint32_t w = 0; w < rowWords(m); ++w) {
                 string value;
                 if (m.isWide) {

@@ -145,26 +145,26 @@ struct Vtop_nocov__cuda final {
         s.clk = static_cast<CData>(rowp[0 * stride + i] & 0x1U);
         s.reset_l = static_cast<CData>(rowp[1 * stride + i] & 0x1U);
         s.in_small = static_cast<CData>(rowp[2 * stride + i] & 0x3U);
-        s.in_wide[0] = rowp[3 * stride + i] & 0xffffffffU;
-        s.in_wide[1] = rowp[4 * stride + i] & 0xffffffffU;
-        s.in_wide[2] = rowp[5 * stride + i] & 0x3fU;
-        s.in_quad = (static_cast<QData>(rowp[7 * stride + i] & 0xffU) << 32) | rowp[6 * stride + i];
+        s.in_quad = (static_cast<QData>(rowp[4 * stride + i] & 0xffU) << 32) | rowp[3 * stride + i];
+        s.in_wide[0] = rowp[5 * stride + i] & 0xffffffffU;
+        s.in_wide[1] = rowp[6 * stride + i] & 0xffffffffU;
+        s.in_wide[2] = rowp[7 * stride + i] & 0x3fU;
     }
     VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
         rowp[0 * stride + i] = s.out_small;
-        rowp[1 * stride + i] = s.out_wide[0];
-        rowp[2 * stride + i] = s.out_wide[1];
-        rowp[3 * stride + i] = s.out_wide[2];
-        rowp[4 * stride + i] = static_cast<uint32_t>(s.out_quad);
-        rowp[5 * stride + i] = static_cast<uint32_t>(s.out_quad >> 32);
+        rowp[1 * stride + i] = static_cast<uint32_t>(s.out_quad);
+        rowp[2 * stride + i] = static_cast<uint32_t>(s.out_quad >> 32);
+        rowp[3 * stride + i] = s.out_wide[0];
+        rowp[4 * stride + i] = s.out_wide[1];
+        rowp[5 * stride + i] = s.out_wide[2];
     }
     VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
         sig = vlcu_sig_mix(sig, s.out_small);
+        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad));
+        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad >> 32));
         sig = vlcu_sig_mix(sig, s.out_wide[0]);
         sig = vlcu_sig_mix(sig, s.out_wide[1]);
         sig = vlcu_sig_mix(sig, s.out_wide[2]);
-        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad));
-        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad >> 32));
         return sig;
     }
     enum : uint32_t { kInWords = 8, kOutWords = 6, kInBytes = 23, kOutBytes = 21 };

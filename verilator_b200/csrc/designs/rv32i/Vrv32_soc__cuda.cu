@@ -250,9 +250,9 @@ struct Vrv32_soc__cuda final {
         rowp[0 * stride + i] = s.trap;
         rowp[1 * stride + i] = s.mem_valid;
         rowp[2 * stride + i] = s.mem_instr;
-        rowp[3 * stride + i] = s.mem_wstrb;
-        rowp[4 * stride + i] = s.mem_addr;
-        rowp[5 * stride + i] = s.mem_wdata;
+        rowp[3 * stride + i] = s.mem_addr;
+        rowp[4 * stride + i] = s.mem_wdata;
+        rowp[5 * stride + i] = s.mem_wstrb;
         rowp[6 * stride + i] = s.mem_rdata;
         rowp[7 * stride + i] = s.retired;
     }
@@ -260,9 +260,9 @@ struct Vrv32_soc__cuda final {
         sig = vlcu_sig_mix(sig, s.trap);
         sig = vlcu_sig_mix(sig, s.mem_valid);
         sig = vlcu_sig_mix(sig, s.mem_instr);
-        sig = vlcu_sig_mix(sig, s.mem_wstrb);
         sig = vlcu_sig_mix(sig, s.mem_addr);
         sig = vlcu_sig_mix(sig, s.mem_wdata);
+        sig = vlcu_sig_mix(sig, s.mem_wstrb);
         sig = vlcu_sig_mix(sig, s.mem_rdata);
         sig = vlcu_sig_mix(sig, s.retired);
         return sig;
