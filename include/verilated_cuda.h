@@ -298,6 +298,18 @@ struct VlcuSymsShim final {
     VLCU_HD const char* name() const { return "TOP"; }
 };
 
+// Trace sampling: the value of one traced signal, stored at its trace code (what
+// VerilatedTraceBuffer::full{Bit,CData,SData,IData,QData,WData} copy to oldp[code],
+// include/verilated_trace_imp.h)
+VLCU_HD void vlcu_trace_set(uint32_t* codep, IData value) { codep[0] = value; }
+VLCU_HD void vlcu_trace_set(uint32_t* codep, QData value) {
+    codep[0] = static_cast<uint32_t>(value);
+    codep[1] = static_cast<uint32_t>(value >> 32);
+}
+VLCU_HD void vlcu_trace_set_w(uint32_t* codep, int words, WDataInP valuep) {
+    for (int w = 0; w < words; ++w) codep[w] = valuep[w];
+}
+
 // $display argument as logged (low 64 bits of a wide value)
 template <typename T>
 VLCU_HD uint64_t vlcu_msg_arg(T value) {

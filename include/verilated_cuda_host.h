@@ -21,6 +21,7 @@ enum : uint32_t {
     VLCU_RUN_STOP_ON_FINISH = 1u << 1,  // an instance stops evaluating once gotFinish() is set
 };
 #define VLCU_TRACE_HDR 16  // bytes before the state record in a trace sample: u64 time, u32 status, u32 valid
+// A trace sample = [header][packed state, kStateBytes][trace words, kTraceWords x u32]
 
 // Per-launch parameters of the cycle-loop kernel
 struct VlcuRunDev final {
@@ -77,16 +78,28 @@ struct VlcuCoverPoint final {  // arguments of __vlCoverInsert / __vlCoverToggle
     const char* linescov;
 };
 
-// One statement of the model's trace_init function (what V3TraceDecl.cpp builds and
-// V3EmitCImp.cpp:643-880 prints as VL_TRACE_DECL_* / VL_TRACE_PUSH_PREFIX / VL_TRACE_POP_PREFIX)
+// One statement of the model's trace_init functions (what V3TraceDecl.cpp builds and
+// V3EmitCImp.cpp:643-700,842-857 prints as VL_TRACE_DECL_* / VL_TRACE_PUSH_PREFIX /
+// VL_TRACE_POP_PREFIX), flattened: dtype functions are expanded at their call sites.
 enum VlcuTraceOp : uint8_t { VLCU_TRACE_SIG = 0, VLCU_TRACE_PUSH = 1, VLCU_TRACE_POP = 2 };
+// VerilatedTracePrefixType (include/verilated_trace.h:50-60)
+enum VlcuTracePrefix : int32_t {
+    VLCU_PREFIX_ARRAY_PACKED = 0,
+    VLCU_PREFIX_ARRAY_UNPACKED = 1,
+    VLCU_PREFIX_ROOTIO_WRAPPER = 2,
+    VLCU_PREFIX_SCOPE_MODULE = 3,
+    VLCU_PREFIX_SCOPE_INTERFACE = 4,
+    VLCU_PREFIX_STRUCT_PACKED = 5,
+    VLCU_PREFIX_STRUCT_UNPACKED = 6,
+    VLCU_PREFIX_UNION_PACKED = 7,
+};
 struct VlcuTraceDecl final {
     uint8_t op;  // VlcuTraceOp
-    uint8_t bussed;  // declared with a [msb:lsb] range (DECL_BUS/QUAD/WIDE) vs DECL_BIT
-    const char* name;  // signal or scope name
-    uint32_t code;  // trace code relative to the model's base (first code is 1)
-    int32_t member;  // index into members[] of the traced variable
-    int32_t elem;  // element of an unpacked array (declared as name[elem]), else -1
+    uint8_t bussed;  // SIG: declared with a [msb:lsb] range (DECL_BUS/QUAD/WIDE) vs DECL_BIT
+    const char* name;  // signal or prefix name
+    uint32_t code;  // SIG: trace code relative to the model's base = word index in a trace sample
+    int32_t arg;  // SIG: width in bits;  PUSH: VlcuTracePrefix
+    int32_t elem;  // SIG: index of an unpacked array element (declared as name[elem]), else -1
     int32_t msb, lsb;
 };
 
@@ -148,6 +161,9 @@ struct VlcuDesignInfo final {
     uint32_t nPlusargs;
     const VlcuTraceDecl* traceDecls;  // trace_init, in declaration order (nullptr: not traced)
     uint32_t nTraceDecls;
+    uint32_t traceWords;  // 32-bit words of one trace sample (the model's trace codes)
+    const uint32_t* traceOrder;  // trace codes in the order the model's trace functions dump them
+    uint32_t nTraceOrder;
 };
 
 #if defined(__CUDACC__) || defined(VLCU_HOST_RUNTIME)

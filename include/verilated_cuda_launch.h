@@ -141,12 +141,16 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
                                             inst);
             }
             if (slot >= 0 && e < r.traceEvals) {
-                uint8_t* const recp
-                    = r.trace + (e * r.nSamples + slot) * (T_Design::kStateBytes + VLCU_TRACE_HDR);
+                constexpr uint64_t kRecBytes
+                    = VLCU_TRACE_HDR + T_Design::kStateBytes + 4ULL * T_Design::kTraceWords;
+                uint8_t* const recp = r.trace + (e * r.nSamples + slot) * kRecBytes;
                 reinterpret_cast<uint64_t*>(recp)[0] = ctx.time();
                 reinterpret_cast<uint32_t*>(recp)[2] = ctx.m_status;
                 reinterpret_cast<uint32_t*>(recp)[3] = 1;  // record valid
                 T_Design::store(root, VlcuState{recp + VLCU_TRACE_HDR, 1}, 0);
+                // the model's trace_full functions, storing by trace code (tfp->dump(time))
+                T_Design::trace_sample(&root, ctx,
+                                       reinterpret_cast<uint32_t*>(recp + VLCU_TRACE_HDR + T_Design::kStateBytes));
             }
         }
     }

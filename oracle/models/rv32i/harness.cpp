@@ -7,6 +7,7 @@
 // testbenches TbRv32Rand / TbRv32Host (verilator_b200/csrc/designs/rv32i/rv32_tb.h).
 #include "Vrv32_soc.h"
 #include "Vrv32_soc___024root.h"
+#include "verilated_vcd_c.h"
 #include "ref_timing.h"
 
 #include <atomic>
@@ -41,6 +42,8 @@ struct Rv32Params {
     // nEvals evals on the same model; each run begins with clk = resetn = 0, a fresh program
     // from (tbSeed + round) ^ index, and resetn low for the first resetTime evals OF THAT RUN
     uint32_t rounds;
+    const char* vcdPath;  // waveform of instance vcdInstance through the reference's VerilatedVcdC
+    int64_t vcdInstance;
 };
 
 void runOne(const Rv32Params& p, uint64_t i) {
@@ -50,7 +53,14 @@ void runOne(const Rv32Params& p, uint64_t i) {
     contextp->randSeed(static_cast<int>(p.seedBase ^ (p.instBase + i)));
     const char* argv[] = {"oracle"};
     contextp->commandArgs(1, argv);
+    contextp->traceEverOn(true);
     const std::unique_ptr<Vrv32_soc> top{new Vrv32_soc{contextp.get(), "TOP"}};
+    std::unique_ptr<VerilatedVcdC> tfp;
+    if (p.vcdPath && p.vcdInstance == static_cast<int64_t>(i)) {
+        tfp.reset(new VerilatedVcdC);
+        top->trace(tfp.get(), 99);
+        tfp->open(p.vcdPath);
+    }
     const uint64_t resetTime = p.resetTime ? p.resetTime : 16;
     uint64_t sig = 0xcbf29ce484222325ULL;
     const uint32_t rounds = p.rounds ? p.rounds : 1;
@@ -68,6 +78,7 @@ void runOne(const Rv32Params& p, uint64_t i) {
             top->clk = !top->clk;
             top->resetn = p.rounds ? (e >= resetTime) : (contextp->time() > resetTime);
             top->eval();
+            if (tfp) tfp->dump(contextp->time());
             // every output port in source order, as the emitted outputs_sig() does
             sig = sigMix(sig, top->trap);
             sig = sigMix(sig, top->mem_valid);
@@ -92,6 +103,7 @@ void runOne(const Rv32Params& p, uint64_t i) {
         }
     }
     top->final();
+    if (tfp) tfp->close();
     if (p.sigs) p.sigs[i] = sig;
     if (p.times) p.times[i] = contextp->time();
     const Vrv32_soc___024root& r = *top->rootp;
@@ -115,9 +127,9 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                               const uint32_t* memImages, uint32_t* obs, uint64_t obsEvals,
                               uint64_t* sigs, uint64_t* times, uint32_t* finalRegs,
                               uint32_t* finalMem, uint32_t* finalScalars, int threads,
-                              uint32_t rounds) {
+                              uint32_t rounds, const char* vcdPath, int64_t vcdInstance) {
     const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
-                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds};
+                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds, vcdPath, vcdInstance};
     vlref_loop_seconds_begin();
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);

@@ -579,53 +579,168 @@ class EmitCudaModel final : public EmitCFunc {
     }
 
     // ---- trace declarations (trace_init_top and the functions it calls) -------------------
-    void traceRows(const AstNode* stmtsp) {
+    // Flattened: a declaration with a dtype function (V3EmitCImp.cpp:647-652) is expanded at the
+    // call site, with the name and base code the call passes ("name", "c+code")
+    void traceRows(const AstNode* stmtsp, const string& dtypeName, uint32_t codeBase) {
         for (const AstNode* nodep = stmtsp; nodep; nodep = nodep->nextp()) {
             if (const AstTracePushPrefix* const pushp = VN_CAST(nodep, TracePushPrefix)) {
-                m_traceRows.push_back("{VLCU_TRACE_PUSH, 0, " + quoted(pushp->prefix()) + ", 0, -1, -1, 0, 0}");
+                // an unquoted prefix is the `name` parameter of a dtype function
+                const string name = pushp->quotedPrefix() ? pushp->prefix() : dtypeName;
+                m_traceRows.push_back("{VLCU_TRACE_PUSH, 0, " + quoted(name) + ", 0, VLCU_PREFIX_"
+                                      + pushp->prefixType().ascii() + ", -1, " + cvtToStr(pushp->left()) + ", "
+                                      + cvtToStr(pushp->right()) + "}");
             } else if (VN_IS(nodep, TracePopPrefix)) {
-                m_traceRows.push_back("{VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}");
+                m_traceRows.push_back("{VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}");
             } else if (const AstTraceDecl* const declp = VN_CAST(nodep, TraceDecl)) {
-                traceDeclRow(declp);
+                if (const AstCCall* const callp = declp->dtypeCallp()) {
+                    traceRows(callp->funcp()->stmtsp(), declp->showname(), codeBase + declp->code());
+                } else {
+                    traceDeclRow(declp, codeBase);
+                }
             } else if (const AstStmtExpr* const stmtp = VN_CAST(nodep, StmtExpr)) {
-                if (const AstCCall* const callp = VN_CAST(stmtp->exprp(), CCall)) traceRows(callp->funcp()->stmtsp());
+                if (const AstCCall* const callp = VN_CAST(stmtp->exprp(), CCall)) {
+                    traceRows(callp->funcp()->stmtsp(), dtypeName, codeBase);
+                }
             } else if (const AstCCall* const callp = VN_CAST(nodep, CCall)) {
-                traceRows(callp->funcp()->stmtsp());
+                traceRows(callp->funcp()->stmtsp(), dtypeName, codeBase);
             }
         }
     }
-    void traceDeclRow(const AstTraceDecl* declp) {
-        // The traced value must be a model variable (or one element of one)
-        const AstNode* valuep = declp->valuep();
-        int elem = -1;
-        if (const AstArraySel* const selp = VN_CAST(valuep, ArraySel)) {
-            if (const AstConst* const idxp = VN_CAST(selp->bitp(), Const)) {
-                elem = idxp->toSInt();
-                valuep = selp->fromp();
-            }
-        }
-        const AstVarRef* const refp = VN_CAST(valuep, VarRef);
-        const auto it = refp ? m_memberOf.find(refp->varp()) : m_memberOf.end();
-        if (it == m_memberOf.end()) return;  // an expression or constant: not sampled
-        const CudaMember& m = m_members[it->second];
+    void traceDeclRow(const AstTraceDecl* declp, uint32_t codeBase) {
         const VNumRange& bits = declp->bitRange();
         const int msb = bits.ranged() ? bits.left() : 0;
         const int lsb = bits.ranged() ? bits.right() : 0;
-        const uint32_t codeWords = (m.width + 31) / 32;
-        if (declp->arrayRange().ranged() && elem < 0) {
-            for (int i = 0; i < declp->arrayRange().elements(); ++i) {
-                m_traceRows.push_back("{VLCU_TRACE_SIG, " + cvtToStr(bits.ranged() ? 1 : 0) + ", "
-                                      + quoted(declp->showname()) + ", " + cvtToStr(declp->code() + i * codeWords)
-                                      + ", " + cvtToStr(it->second) + ", " + cvtToStr(i) + ", " + cvtToStr(msb)
-                                      + ", " + cvtToStr(lsb) + "}");
-            }
-        } else {
+        const uint32_t width = declp->widthMin();
+        const int elements = declp->arrayRange().ranged() ? declp->arrayRange().elements() : 1;
+        for (int i = 0; i < elements; ++i) {
+            const uint32_t code = codeBase + declp->code() + i * declp->widthWords();
+            const int elem = declp->arrayRange().ranged() ? (i + declp->arrayRange().lo()) : -1;
             m_traceRows.push_back("{VLCU_TRACE_SIG, " + cvtToStr(bits.ranged() ? 1 : 0) + ", "
-                                  + quoted(declp->showname()) + ", " + cvtToStr(declp->code()) + ", "
-                                  + cvtToStr(it->second) + ", " + cvtToStr(elem) + ", " + cvtToStr(msb) + ", "
-                                  + cvtToStr(lsb) + "}");
+                                  + quoted(declp->showname()) + ", " + cvtToStr(code) + ", " + cvtToStr(width)
+                                  + ", " + cvtToStr(elem) + ", " + cvtToStr(msb) + ", " + cvtToStr(lsb) + "}");
+            m_traceWords = std::max(m_traceWords, code + (width + 31) / 32);
         }
     }
+    // Trace sampling.  The model's trace_full_* / trace_const_* functions (V3Trace.cpp:676-775)
+    // become device functions that store every traced value at its trace code:
+    //   sub function    f(vlSelf, bufp)                       -> f(vlSelf, vlCtx, valsp)
+    //   dtype function  f(vlSelf, bufp, offset, __VdtypeVar)  -> template f(..., valsp, offset, var)
+    static bool isDtypeTraceFunc(const AstCFunc* funcp) {
+        return funcp->argTypes().find("uint32_t offset") != string::npos;
+    }
+    static bool isSampledTraceFunc(const AstCFunc* funcp) {
+        if (!funcp->isTrace()) return false;
+        return funcp->name().compare(0, 11, "trace_full_") == 0 || funcp->name().compare(0, 12, "trace_const_") == 0;
+    }
+    bool m_inDtypeTraceFunc = false;
+    void visit(AstTraceInc* nodep) override {
+        // EmitCTrace::emitTraceChangeOne / emitTraceValue (V3EmitCImp.cpp:741-810)
+        const AstTraceDecl* const declp = nodep->declp();
+        const VNumRange& arrayRange = declp->arrayRange();
+        const int elements = arrayRange.ranged() ? arrayRange.elements() : 1;
+        for (int i = 0; i < elements; ++i) {
+            const uint32_t code = declp->code() + i * declp->widthWords();
+            const string at = string{"valsp + "} + (m_inDtypeTraceFunc ? "offset + " : "") + cvtToStr(code);
+            int arrayindex = i;
+            if (arrayRange.ranged() && !arrayRange.ascending()) arrayindex = arrayRange.elements() - 1 - i;
+            const string index = arrayRange.ranged() ? "[" + cvtToStr(arrayindex) + "]" : "";
+            if (nodep->isWide()) {
+                putns(nodep, "vlcu_trace_set_w(" + at + ", " + cvtToStr(declp->widthWords()) + ", (");
+            } else {
+                putns(nodep, "vlcu_trace_set(" + at + ", static_cast<" + (nodep->isQuad() ? "QData" : "IData") + ">(");
+            }
+            iterateConst(nodep->valuep());
+            puts(index + "));\n");
+        }
+    }
+    // A call from one trace function to another: "bufp[, ...]" + expression arguments
+    void emitTraceCall(const AstCCall* callp) {
+        string rest = callp->argTypes();
+        if (rest.compare(0, 4, "bufp") == 0) rest = rest.substr(4);
+        puts(funcNameProtect(callp->funcp(), m_topModp) + "(vlSelf, vlCtx, valsp" + rest);
+        for (AstNode* argp = callp->argsp(); argp; argp = argp->nextp()) {
+            puts(", ");
+            iterateConst(argp);
+        }
+        puts(");\n");
+    }
+    void emitTraceFunc(AstCFunc* funcp) {
+        VL_RESTORER(m_cfuncp);
+        VL_RESTORER(m_useSelfForThis);
+        VL_RESTORER(m_inDtypeTraceFunc);
+        m_cfuncp = funcp;
+        m_useSelfForThis = true;
+        m_usevlSelfRef = true;
+        m_inDtypeTraceFunc = isDtypeTraceFunc(funcp);
+        puts("\n");
+        if (m_inDtypeTraceFunc) puts("template <class T_DtypeVar>\n");
+        puts("VLCU_D static void " + funcNameProtect(funcp, m_topModp) + "(" + m_rootName
+             + "* vlSelf, VlcuContext& vlCtx, uint32_t* valsp"
+             + (m_inDtypeTraceFunc ? ", uint32_t offset, const T_DtypeVar& __VdtypeVar" : "") + ") {\n");
+        puts("auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;\n");
+        for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
+            if (VN_IS(stmtp, TraceInc)) {
+                iterateConst(stmtp);
+            } else if (const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr)) {
+                if (const AstCCall* const callp = VN_CAST(sep->exprp(), CCall)) emitTraceCall(callp);
+            }
+        }
+        m_usevlSelfRef = false;
+        puts("}\n");
+    }
+    // Dump order of the trace codes: the statements in execution order, through the calls
+    void traceOrderWalk(const AstCFunc* funcp, uint32_t base) {
+        for (const AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
+            if (const AstTraceInc* const incp = VN_CAST(stmtp, TraceInc)) {
+                const AstTraceDecl* const declp = incp->declp();
+                const int elements = declp->arrayRange().ranged() ? declp->arrayRange().elements() : 1;
+                for (int i = 0; i < elements; ++i) m_traceOrder.push_back(base + declp->code() + i * declp->widthWords());
+            } else if (const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr)) {
+                const AstCCall* const callp = VN_CAST(sep->exprp(), CCall);
+                if (!callp || !callp->funcp()->isTrace()) continue;
+                uint32_t calleeBase = base;  // "bufp" / "bufp, offset, __VdtypeVar": same base
+                const string& args = callp->argTypes();
+                const string::size_type comma = args.find(", ");
+                if (comma != string::npos && std::isdigit(args[comma + 2])) {
+                    calleeBase = std::stoul(args.substr(comma + 2));  // "bufp, <code>"
+                }
+                traceOrderWalk(callp->funcp(), calleeBase);
+            }
+        }
+    }
+    void emitTraceSample() {
+        // Sub and dtype functions first (callees), in AST order
+        std::vector<AstCFunc*> tops;
+        for (AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            AstCFunc* const funcp = VN_CAST(nodep, CFunc);
+            if (!funcp || !isSampledTraceFunc(funcp)) continue;
+            if (funcp->isStatic()) {  // top functions take `void* voidSelf` and only call sub functions
+                tops.push_back(funcp);
+            } else {
+                emitTraceFunc(funcp);
+            }
+        }
+        puts("\n// tfp->dump(): every traced value stored at its trace code.  Full functions, then the\n");
+        puts("// constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)\n");
+        puts("VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {\n");
+        puts("(void)vlSelf; (void)vlCtx; (void)valsp;\n");
+        for (const char* const prefix : {"trace_full_", "trace_const_"}) {
+            for (AstCFunc* const funcp : tops) {
+                if (funcp->name().compare(0, strlen(prefix), prefix) != 0) continue;
+                for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
+                    if (const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr)) {
+                        if (const AstCCall* const callp = VN_CAST(sep->exprp(), CCall)) {
+                            puts(funcNameProtect(callp->funcp(), m_topModp) + "(vlSelf, vlCtx, valsp);\n");
+                        }
+                    }
+                }
+                traceOrderWalk(funcp, 0);
+            }
+        }
+        puts("}\n");
+    }
+    uint32_t m_traceWords = 0;
+    std::vector<uint32_t> m_traceOrder;
 
     // ---- the file ---------------------------------------------------------------------------
     void emitWrapper(const string& wrapper, const string& funcName, bool withCtxOnly = false) {
@@ -689,7 +804,8 @@ class EmitCudaModel final : public EmitCFunc {
         emitLoadStore(true);
         emitLoadStore(false);
         emitPortRows();
-        puts("enum : uint32_t { " + m_sizes + " };\n");
+        if (const AstCFunc* const funcp = findFunc("trace_init_top")) traceRows(funcp->stmtsp(), "", 0);
+        puts("enum : uint32_t { " + m_sizes + ", kTraceWords = " + cvtToStr(m_traceWords) + " };\n");
 
         // Device functions
         for (AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
@@ -697,10 +813,20 @@ class EmitCudaModel final : public EmitCFunc {
                 if (isDeviceFunc(funcp)) iterateConst(funcp);
             }
         }
+        emitTraceSample();
         // Entry points of the launch templates = what Vtop::eval_step() calls
         // (EmitCModel::emitStandardMethods1, V3EmitCModel.cpp:403-437)
         puts("\n");
-        emitWrapper("ctor_var_reset", "_ctor_var_reset");
+        // Construction: the member initialiser `uint32_t __Vcoverage[n]{}` of the C++ class
+        // (V3EmitCHeaders.cpp:153-158), then Vtop___024root___ctor_var_reset
+        puts("VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {\n");
+        if (m_coverBins) {
+            puts("for (uint32_t b = 0; b < " + cvtToStr(m_coverBins) + "U; ++b) vlSelf->__Vcoverage[b] = 0U;\n");
+        }
+        if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
+            puts(funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx);\n");
+        }
+        puts("}\n");
         emitWrapper("eval_static", "_eval_static");
         emitWrapper("eval_initial", "_eval_initial");
         emitWrapper("eval_settle", "_eval_settle");
@@ -765,10 +891,13 @@ class EmitCudaModel final : public EmitCFunc {
         for (const string& s : m_plusargs) puts(quoted(s) + ", ");
         puts("nullptr};\n");
         // Trace declarations
-        if (const AstCFunc* const funcp = findFunc("trace_init_top")) traceRows(funcp->stmtsp());
+        // (rows were collected before the device code was printed, for kTraceWords)
         puts("static const VlcuTraceDecl traceDecls[] = {\n");
         for (const string& row : m_traceRows) puts(row + ",\n");
-        puts("{VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}};  // (terminator, not counted)\n");
+        puts("{VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)\n");
+        puts("static const uint32_t traceOrder[] = {");
+        for (const uint32_t code : m_traceOrder) puts(cvtToStr(code) + ", ");
+        puts("0};  // codes in dump order (+ terminator)\n");
         puts("static const VlcuDesignInfo s = {\n");
         puts("VLCU_DESIGN_NAME, " + quoted(topName) + ", members, sizeof(members) / sizeof(members[0]),\n");
         puts("T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, "
@@ -779,7 +908,9 @@ class EmitCudaModel final : public EmitCFunc {
             puts("nullptr, 0, 0,\n");
         }
         puts("messages, " + cvtToStr(m_messages.size()) + ", plusargs, " + cvtToStr(m_plusargs.size()) + ",\n");
-        puts(m_traceRows.empty() ? "nullptr, 0};\n" : "traceDecls, " + cvtToStr(m_traceRows.size()) + "};\n");
+        puts(m_traceRows.empty() ? "nullptr, 0, 0, nullptr, 0};\n"
+                                 : "traceDecls, " + cvtToStr(m_traceRows.size()) + ", T::kTraceWords, traceOrder, "
+                                       + cvtToStr(m_traceOrder.size()) + "};\n");
         puts("return s;\n}\n");
     }
 

@@ -167,7 +167,7 @@ struct Vtop_nocov__cuda final {
         sig = vlcu_sig_mix(sig, s.out_wide[2]);
         return sig;
     }
-    enum : uint32_t { kInWords = 8, kOutWords = 6, kInBytes = 23, kOutBytes = 21 };
+    enum : uint32_t { kInWords = 8, kOutWords = 6, kInBytes = 23, kOutBytes = 21, kTraceWords = 15 };
 
     VLCU_D static void Vtop_nocov___024root___eval_static(Vtop_nocov___024root* vlSelf, VlcuContext& vlCtx) {
         typedef void VlcuFuncRet;
@@ -635,7 +635,29 @@ struct Vtop_nocov__cuda final {
         }
     }
 
-    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) { Vtop_nocov___024root___ctor_var_reset(vlSelf, vlCtx); }
+    VLCU_D static void Vtop_nocov___024root__trace_full_0_sub_0(Vtop_nocov___024root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;
+        vlcu_trace_set(valsp + 0, static_cast<IData>(vlSelfRef.clk));
+        vlcu_trace_set(valsp + 1, static_cast<IData>(vlSelfRef.reset_l));
+        vlcu_trace_set(valsp + 2, static_cast<IData>(vlSelfRef.out_small));
+        vlcu_trace_set(valsp + 3, static_cast<QData>(vlSelfRef.out_quad));
+        vlcu_trace_set_w(valsp + 5, 3, (vlSelfRef.out_wide));
+        vlcu_trace_set(valsp + 8, static_cast<IData>(vlSelfRef.in_small));
+        vlcu_trace_set(valsp + 9, static_cast<QData>(vlSelfRef.in_quad));
+        vlcu_trace_set_w(valsp + 11, 3, (vlSelfRef.in_wide));
+        vlcu_trace_set(valsp + 14, static_cast<IData>(vlSelfRef.top__DOT__sub__DOT__count_c));
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+        Vtop_nocov___024root__trace_full_0_sub_0(vlSelf, vlCtx, valsp);
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vtop_nocov___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
     VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vtop_nocov___024root___eval_static(vlSelf, vlCtx); }
     VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vtop_nocov___024root___eval_initial(vlSelf, vlCtx); }
     VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vtop_nocov___024root___eval_settle(vlSelf, vlCtx); }
@@ -682,19 +704,39 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
     static const char* const messages[] = {"[%0t] Tracing to logs/vlt_dump.vcd...\n\n", "[%0t] Model running...\n\n", "[%0t] %%Error: sub.v:35: Assertion failed in TOP.top.sub.AssertionExample: 'assert' failed.\n", "*-* All Finished *-*\n", nullptr};
     static const char* const plusargs[] = {"trace", nullptr};
     static const VlcuTraceDecl traceDecls[] = {
-        {VLCU_TRACE_PUSH, 0, "$rootio", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_PUSH, 0, "top", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_PUSH, 0, "sub", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}};  // (terminator, not counted)
+        {VLCU_TRACE_PUSH, 0, "$rootio", 0, VLCU_PREFIX_SCOPE_MODULE, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "clk", 0, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "reset_l", 1, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "out_small", 2, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "out_quad", 3, 40, -1, 39, 0},
+        {VLCU_TRACE_SIG, 1, "out_wide", 5, 70, -1, 69, 0},
+        {VLCU_TRACE_SIG, 1, "in_small", 8, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "in_quad", 9, 40, -1, 39, 0},
+        {VLCU_TRACE_SIG, 1, "in_wide", 11, 70, -1, 69, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_PUSH, 0, "top", 0, VLCU_PREFIX_SCOPE_MODULE, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "clk", 0, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "reset_l", 1, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "out_small", 2, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "out_quad", 3, 40, -1, 39, 0},
+        {VLCU_TRACE_SIG, 1, "out_wide", 5, 70, -1, 69, 0},
+        {VLCU_TRACE_SIG, 1, "in_small", 8, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "in_quad", 9, 40, -1, 39, 0},
+        {VLCU_TRACE_SIG, 1, "in_wide", 11, 70, -1, 69, 0},
+        {VLCU_TRACE_PUSH, 0, "sub", 0, VLCU_PREFIX_SCOPE_MODULE, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "clk", 0, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "reset_l", 1, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "count_c", 14, 32, -1, 31, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0, 1, 2, 3, 5, 8, 9, 11, 14, 0};  // codes in dump order (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "top", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0,
         messages, 4, plusargs, 1,
-        traceDecls, 6};
+        traceDecls, 25, T::kTraceWords, traceOrder, 9};
     return s;
 }
 

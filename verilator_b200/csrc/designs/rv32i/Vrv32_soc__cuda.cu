@@ -267,7 +267,7 @@ struct Vrv32_soc__cuda final {
         sig = vlcu_sig_mix(sig, s.retired);
         return sig;
     }
-    enum : uint32_t { kInWords = 2, kOutWords = 8, kInBytes = 2, kOutBytes = 20 };
+    enum : uint32_t { kInWords = 2, kOutWords = 8, kInBytes = 2, kOutBytes = 20, kTraceWords = 88 };
 
     VLCU_D static void Vrv32_soc___024root___eval_static(Vrv32_soc___024root* vlSelf, VlcuContext& vlCtx) {
         typedef void VlcuFuncRet;
@@ -1643,7 +1643,423 @@ struct Vrv32_soc__cuda final {
         }
     }
 
-    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) { Vrv32_soc___024root___ctor_var_reset(vlSelf, vlCtx); }
+    VLCU_D static void Vrv32_soc___024root__trace_const_0_sub_0(Vrv32_soc___024root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;
+        vlcu_trace_set(valsp + 83, static_cast<IData>(0x00000400U));
+        vlcu_trace_set(valsp + 84, static_cast<IData>(0U));
+        vlcu_trace_set(valsp + 85, static_cast<IData>(1U));
+        vlcu_trace_set(valsp + 86, static_cast<IData>(2U));
+        vlcu_trace_set(valsp + 87, static_cast<IData>(3U));
+    }
+
+    VLCU_D static void Vrv32_soc___024root__trace_full_0_sub_0(Vrv32_soc___024root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;
+        vlcu_trace_set(valsp + 0, static_cast<IData>(vlSelfRef.rv32_soc__DOT__instret));
+        Vrv32_soc___024root__trace_full_dtype____0(vlSelf, vlCtx, valsp, 1, vlSelfRef.rv32_soc__DOT__regs);
+        vlcu_trace_set(valsp + 33, static_cast<IData>(vlSelfRef.rv32_soc__DOT__pc));
+        vlcu_trace_set(valsp + 34, static_cast<IData>(vlSelfRef.rv32_soc__DOT__insn));
+        vlcu_trace_set(valsp + 35, static_cast<IData>(vlSelfRef.rv32_soc__DOT__ld_addr));
+        vlcu_trace_set(valsp + 36, static_cast<IData>(vlSelfRef.rv32_soc__DOT__state));
+        vlcu_trace_set(valsp + 37, static_cast<IData>(
+                                                      (0x0000007fU 
+                                                       & vlSelfRef.rv32_soc__DOT__insn)));
+        vlcu_trace_set(valsp + 38, static_cast<IData>(
+                                                      (0x0000001fU 
+                                                       & (vlSelfRef.rv32_soc__DOT__insn 
+                                                          >> 7U))));
+        vlcu_trace_set(valsp + 39, static_cast<IData>(
+                                                      (7U 
+                                                       & (vlSelfRef.rv32_soc__DOT__insn 
+                                                          >> 0x0000000cU))));
+        vlcu_trace_set(valsp + 40, static_cast<IData>(
+                                                      (0x0000001fU 
+                                                       & (vlSelfRef.rv32_soc__DOT__insn 
+                                                          >> 0x0000000fU))));
+        vlcu_trace_set(valsp + 41, static_cast<IData>(
+                                                      (0x0000001fU 
+                                                       & (vlSelfRef.rv32_soc__DOT__insn 
+                                                          >> 0x00000014U))));
+        vlcu_trace_set(valsp + 42, static_cast<IData>(
+                                                      (1U 
+                                                       & (vlSelfRef.rv32_soc__DOT__insn 
+                                                          >> 0x0000001eU))));
+        vlcu_trace_set(valsp + 43, static_cast<IData>(vlSelfRef.rv32_soc__DOT__imm_i));
+        vlcu_trace_set(valsp + 44, static_cast<IData>(
+                                                      (((- (IData)(
+                                                                   (vlSelfRef.rv32_soc__DOT__insn 
+                                                                    >> 0x0000001fU))) 
+                                                        << 0x0000000cU) 
+                                                       | ((0x00000fe0U 
+                                                           & (vlSelfRef.rv32_soc__DOT__insn 
+                                                              >> 0x00000014U)) 
+                                                          | (0x0000001fU 
+                                                             & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                >> 7U))))));
+        vlcu_trace_set(valsp + 45, static_cast<IData>(
+                                                      (((- (IData)(
+                                                                   (vlSelfRef.rv32_soc__DOT__insn 
+                                                                    >> 0x0000001fU))) 
+                                                        << 0x0000000dU) 
+                                                       | ((((2U 
+                                                             & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                >> 0x0000001eU)) 
+                                                            | (1U 
+                                                               & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                  >> 7U))) 
+                                                           << 0x0000000bU) 
+                                                          | ((0x000007e0U 
+                                                              & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                 >> 0x00000014U)) 
+                                                             | (0x0000001eU 
+                                                                & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                   >> 7U)))))));
+        vlcu_trace_set(valsp + 46, static_cast<IData>(
+                                                      (0xfffff000U 
+                                                       & vlSelfRef.rv32_soc__DOT__insn)));
+        vlcu_trace_set(valsp + 47, static_cast<IData>(
+                                                      ((((0x00000ffeU 
+                                                          & ((- (IData)(
+                                                                        (vlSelfRef.rv32_soc__DOT__insn 
+                                                                         >> 0x0000001fU))) 
+                                                             << 1U)) 
+                                                         | (vlSelfRef.rv32_soc__DOT__insn 
+                                                            >> 0x0000001fU)) 
+                                                        << 0x00000014U) 
+                                                       | ((((0x000001feU 
+                                                             & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                >> 0x0000000bU)) 
+                                                            | (1U 
+                                                               & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                  >> 0x00000014U))) 
+                                                           << 0x0000000bU) 
+                                                          | (0x000007feU 
+                                                             & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                >> 0x00000014U))))));
+        vlcu_trace_set(valsp + 48, static_cast<IData>(
+                                                      (0x37U 
+                                                       == 
+                                                       (0x0000007fU 
+                                                        & vlSelfRef.rv32_soc__DOT__insn))));
+        vlcu_trace_set(valsp + 49, static_cast<IData>(
+                                                      (0x17U 
+                                                       == 
+                                                       (0x0000007fU 
+                                                        & vlSelfRef.rv32_soc__DOT__insn))));
+        vlcu_trace_set(valsp + 50, static_cast<IData>(
+                                                      (0x6fU 
+                                                       == 
+                                                       (0x0000007fU 
+                                                        & vlSelfRef.rv32_soc__DOT__insn))));
+        vlcu_trace_set(valsp + 51, static_cast<IData>((IData)(
+                                                              (0x00000067U 
+                                                               == 
+                                                               (0x0000707fU 
+                                                                & vlSelfRef.rv32_soc__DOT__insn)))));
+        vlcu_trace_set(valsp + 52, static_cast<IData>(
+                                                      ((0x63U 
+                                                        == 
+                                                        (0x0000007fU 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)) 
+                                                       & ((2U 
+                                                           != 
+                                                           (7U 
+                                                            & (vlSelfRef.rv32_soc__DOT__insn 
+                                                               >> 0x0000000cU))) 
+                                                          & (3U 
+                                                             != 
+                                                             (7U 
+                                                              & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                 >> 0x0000000cU)))))));
+        vlcu_trace_set(valsp + 53, static_cast<IData>(vlSelfRef.rv32_soc__DOT__is_load));
+        vlcu_trace_set(valsp + 54, static_cast<IData>(vlSelfRef.rv32_soc__DOT__is_store));
+        vlcu_trace_set(valsp + 55, static_cast<IData>(
+                                                      ((0x13U 
+                                                        == 
+                                                        (0x0000007fU 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)) 
+                                                       & ((0U 
+                                                           == 
+                                                           (vlSelfRef.rv32_soc__DOT__insn 
+                                                            >> 0x00000019U)) 
+                                                          | ((1U 
+                                                              != 
+                                                              (7U 
+                                                               & (vlSelfRef.rv32_soc__DOT__insn 
+                                                                  >> 0x0000000cU))) 
+                                                             & (IData)(
+                                                                       ((0x00005000U 
+                                                                         != 
+                                                                         (0x00007000U 
+                                                                          & vlSelfRef.rv32_soc__DOT__insn)) 
+                                                                        | (0x20U 
+                                                                           == 
+                                                                           (vlSelfRef.rv32_soc__DOT__insn 
+                                                                            >> 0x00000019U)))))))));
+        vlcu_trace_set(valsp + 56, static_cast<IData>(vlSelfRef.rv32_soc__DOT__is_alur));
+        vlcu_trace_set(valsp + 57, static_cast<IData>(vlSelfRef.rv32_soc__DOT__rs1_val));
+        vlcu_trace_set(valsp + 58, static_cast<IData>(vlSelfRef.rv32_soc__DOT__rs2_val));
+        vlcu_trace_set(valsp + 59, static_cast<IData>(vlSelfRef.rv32_soc__DOT__alu_b));
+        vlcu_trace_set(valsp + 60, static_cast<IData>(
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.rv32_soc__DOT__alu_b)));
+        vlcu_trace_set(valsp + 61, static_cast<IData>(
+                                                      ((vlSelfRef.rv32_soc__DOT__insn 
+                                                        >> 0x0000001eU) 
+                                                       & (IData)(vlSelfRef.rv32_soc__DOT__is_alur))));
+        vlcu_trace_set(valsp + 62, static_cast<IData>(
+                                                      ((0x00004000U 
+                                                        & vlSelfRef.rv32_soc__DOT__insn)
+                                                        ? 
+                                                       ((0x00002000U 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)
+                                                         ? 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          & vlSelfRef.rv32_soc__DOT__alu_b)
+                                                          : 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          | vlSelfRef.rv32_soc__DOT__alu_b))
+                                                         : 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         ((0x40000000U 
+                                                           & vlSelfRef.rv32_soc__DOT__insn)
+                                                           ? 
+                                                          VL_SHIFTRS_III(32,32,5, vlSelfRef.rv32_soc__DOT__rs1_val, 
+                                                                         (0x0000001fU 
+                                                                          & vlSelfRef.rv32_soc__DOT__alu_b))
+                                                           : 
+                                                          (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                           >> 
+                                                           (0x0000001fU 
+                                                            & vlSelfRef.rv32_soc__DOT__alu_b)))
+                                                          : 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          ^ vlSelfRef.rv32_soc__DOT__alu_b)))
+                                                        : 
+                                                       ((0x00002000U 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)
+                                                         ? 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          < vlSelfRef.rv32_soc__DOT__alu_b)
+                                                          : 
+                                                         VL_LTS_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, vlSelfRef.rv32_soc__DOT__alu_b))
+                                                         : 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          << 
+                                                          (0x0000001fU 
+                                                           & vlSelfRef.rv32_soc__DOT__alu_b))
+                                                          : 
+                                                         (((vlSelfRef.rv32_soc__DOT__insn 
+                                                            >> 0x0000001eU) 
+                                                           & (IData)(vlSelfRef.rv32_soc__DOT__is_alur))
+                                                           ? 
+                                                          (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                           - vlSelfRef.rv32_soc__DOT__alu_b)
+                                                           : 
+                                                          (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                           + vlSelfRef.rv32_soc__DOT__alu_b)))))));
+        vlcu_trace_set(valsp + 63, static_cast<IData>(
+                                                      ((0x00004000U 
+                                                        & vlSelfRef.rv32_soc__DOT__insn)
+                                                        ? 
+                                                       ((0x00002000U 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)
+                                                         ? 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? (IData)(vlSelfRef.__VdfgRegularize_h6e95ff9d_0_0)
+                                                          : 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          < vlSelfRef.rv32_soc__DOT__rs2_val))
+                                                         : 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         VL_GTES_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, vlSelfRef.rv32_soc__DOT__rs2_val)
+                                                          : 
+                                                         VL_LTS_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, vlSelfRef.rv32_soc__DOT__rs2_val)))
+                                                        : 
+                                                       ((0x00002000U 
+                                                         & vlSelfRef.rv32_soc__DOT__insn)
+                                                         ? (IData)(vlSelfRef.__VdfgRegularize_h6e95ff9d_0_0)
+                                                         : 
+                                                        ((0x00001000U 
+                                                          & vlSelfRef.rv32_soc__DOT__insn)
+                                                          ? 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          != vlSelfRef.rv32_soc__DOT__rs2_val)
+                                                          : 
+                                                         (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                                          == vlSelfRef.rv32_soc__DOT__rs2_val))))));
+        vlcu_trace_set(valsp + 64, static_cast<IData>(vlSelfRef.rv32_soc__DOT__ls_addr));
+        vlcu_trace_set(valsp + 65, static_cast<IData>(vlSelfRef.rv32_soc__DOT__ls_misaligned));
+        vlcu_trace_set(valsp + 66, static_cast<IData>(
+                                                      (0x00000400U 
+                                                       <= 
+                                                       (vlSelfRef.rv32_soc__DOT__ls_addr 
+                                                        >> 2U))));
+        vlcu_trace_set(valsp + 67, static_cast<IData>(vlSelfRef.rv32_soc__DOT__st_data));
+        vlcu_trace_set(valsp + 68, static_cast<IData>(vlSelfRef.rv32_soc__DOT__st_strb));
+        vlcu_trace_set(valsp + 69, static_cast<IData>(vlSelfRef.rv32_soc__DOT__mem
+                                                      [
+                                                      (0x000003ffU 
+                                                       & (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                                          >> 2U))]));
+        vlcu_trace_set(valsp + 70, static_cast<IData>(vlSelfRef.rv32_soc__DOT__ld_shift));
+        vlcu_trace_set(valsp + 71, static_cast<IData>(
+                                                      ((0U 
+                                                        == 
+                                                        (7U 
+                                                         & (vlSelfRef.rv32_soc__DOT__insn 
+                                                            >> 0x0000000cU)))
+                                                        ? 
+                                                       (((- (IData)(
+                                                                    (1U 
+                                                                     & (vlSelfRef.rv32_soc__DOT__ld_shift 
+                                                                        >> 7U)))) 
+                                                         << 8U) 
+                                                        | (0x000000ffU 
+                                                           & vlSelfRef.rv32_soc__DOT__ld_shift))
+                                                        : 
+                                                       ((1U 
+                                                         == 
+                                                         (7U 
+                                                          & (vlSelfRef.rv32_soc__DOT__insn 
+                                                             >> 0x0000000cU)))
+                                                         ? 
+                                                        (((- (IData)(
+                                                                     (1U 
+                                                                      & (vlSelfRef.rv32_soc__DOT__ld_shift 
+                                                                         >> 0x0000000fU)))) 
+                                                          << 0x00000010U) 
+                                                         | (0x0000ffffU 
+                                                            & vlSelfRef.rv32_soc__DOT__ld_shift))
+                                                         : 
+                                                        ((4U 
+                                                          == 
+                                                          (7U 
+                                                           & (vlSelfRef.rv32_soc__DOT__insn 
+                                                              >> 0x0000000cU)))
+                                                          ? 
+                                                         (0x000000ffU 
+                                                          & vlSelfRef.rv32_soc__DOT__ld_shift)
+                                                          : 
+                                                         ((5U 
+                                                           == 
+                                                           (7U 
+                                                            & (vlSelfRef.rv32_soc__DOT__insn 
+                                                               >> 0x0000000cU)))
+                                                           ? 
+                                                          (0x0000ffffU 
+                                                           & vlSelfRef.rv32_soc__DOT__ld_shift)
+                                                           : vlSelfRef.rv32_soc__DOT__mem
+                                                          [
+                                                          (0x000003ffU 
+                                                           & (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                                              >> 2U))]))))));
+        vlcu_trace_set(valsp + 72, static_cast<IData>(vlSelfRef.rv32_soc__DOT__pc_bad));
+        vlcu_trace_set(valsp + 73, static_cast<IData>(vlSelfRef.rv32_soc__DOT__exec_ls));
+        vlcu_trace_set(valsp + 74, static_cast<IData>(vlSelfRef.clk));
+        vlcu_trace_set(valsp + 75, static_cast<IData>(vlSelfRef.resetn));
+        vlcu_trace_set(valsp + 76, static_cast<IData>(vlSelfRef.trap));
+        vlcu_trace_set(valsp + 77, static_cast<IData>(vlSelfRef.mem_valid));
+        vlcu_trace_set(valsp + 78, static_cast<IData>(vlSelfRef.mem_instr));
+        vlcu_trace_set(valsp + 79, static_cast<IData>(vlSelfRef.mem_addr));
+        vlcu_trace_set(valsp + 80, static_cast<IData>(vlSelfRef.mem_wdata));
+        vlcu_trace_set(valsp + 81, static_cast<IData>(vlSelfRef.mem_wstrb));
+        vlcu_trace_set(valsp + 82, static_cast<IData>(vlSelfRef.mem_rdata));
+    }
+
+    template <class T_DtypeVar>
+    VLCU_D static void Vrv32_soc___024root__trace_full_dtype____0(Vrv32_soc___024root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp, uint32_t offset, const T_DtypeVar& __VdtypeVar) {
+        auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;
+        vlcu_trace_set(valsp + offset + 0, static_cast<IData>(
+                                                              __VdtypeVar[0]));
+        vlcu_trace_set(valsp + offset + 1, static_cast<IData>(
+                                                              __VdtypeVar[1]));
+        vlcu_trace_set(valsp + offset + 2, static_cast<IData>(
+                                                              __VdtypeVar[2]));
+        vlcu_trace_set(valsp + offset + 3, static_cast<IData>(
+                                                              __VdtypeVar[3]));
+        vlcu_trace_set(valsp + offset + 4, static_cast<IData>(
+                                                              __VdtypeVar[4]));
+        vlcu_trace_set(valsp + offset + 5, static_cast<IData>(
+                                                              __VdtypeVar[5]));
+        vlcu_trace_set(valsp + offset + 6, static_cast<IData>(
+                                                              __VdtypeVar[6]));
+        vlcu_trace_set(valsp + offset + 7, static_cast<IData>(
+                                                              __VdtypeVar[7]));
+        vlcu_trace_set(valsp + offset + 8, static_cast<IData>(
+                                                              __VdtypeVar[8]));
+        vlcu_trace_set(valsp + offset + 9, static_cast<IData>(
+                                                              __VdtypeVar[9]));
+        vlcu_trace_set(valsp + offset + 10, static_cast<IData>(
+                                                               __VdtypeVar[10]));
+        vlcu_trace_set(valsp + offset + 11, static_cast<IData>(
+                                                               __VdtypeVar[11]));
+        vlcu_trace_set(valsp + offset + 12, static_cast<IData>(
+                                                               __VdtypeVar[12]));
+        vlcu_trace_set(valsp + offset + 13, static_cast<IData>(
+                                                               __VdtypeVar[13]));
+        vlcu_trace_set(valsp + offset + 14, static_cast<IData>(
+                                                               __VdtypeVar[14]));
+        vlcu_trace_set(valsp + offset + 15, static_cast<IData>(
+                                                               __VdtypeVar[15]));
+        vlcu_trace_set(valsp + offset + 16, static_cast<IData>(
+                                                               __VdtypeVar[16]));
+        vlcu_trace_set(valsp + offset + 17, static_cast<IData>(
+                                                               __VdtypeVar[17]));
+        vlcu_trace_set(valsp + offset + 18, static_cast<IData>(
+                                                               __VdtypeVar[18]));
+        vlcu_trace_set(valsp + offset + 19, static_cast<IData>(
+                                                               __VdtypeVar[19]));
+        vlcu_trace_set(valsp + offset + 20, static_cast<IData>(
+                                                               __VdtypeVar[20]));
+        vlcu_trace_set(valsp + offset + 21, static_cast<IData>(
+                                                               __VdtypeVar[21]));
+        vlcu_trace_set(valsp + offset + 22, static_cast<IData>(
+                                                               __VdtypeVar[22]));
+        vlcu_trace_set(valsp + offset + 23, static_cast<IData>(
+                                                               __VdtypeVar[23]));
+        vlcu_trace_set(valsp + offset + 24, static_cast<IData>(
+                                                               __VdtypeVar[24]));
+        vlcu_trace_set(valsp + offset + 25, static_cast<IData>(
+                                                               __VdtypeVar[25]));
+        vlcu_trace_set(valsp + offset + 26, static_cast<IData>(
+                                                               __VdtypeVar[26]));
+        vlcu_trace_set(valsp + offset + 27, static_cast<IData>(
+                                                               __VdtypeVar[27]));
+        vlcu_trace_set(valsp + offset + 28, static_cast<IData>(
+                                                               __VdtypeVar[28]));
+        vlcu_trace_set(valsp + offset + 29, static_cast<IData>(
+                                                               __VdtypeVar[29]));
+        vlcu_trace_set(valsp + offset + 30, static_cast<IData>(
+                                                               __VdtypeVar[30]));
+        vlcu_trace_set(valsp + offset + 31, static_cast<IData>(
+                                                               __VdtypeVar[31]));
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+        Vrv32_soc___024root__trace_full_0_sub_0(vlSelf, vlCtx, valsp);
+        Vrv32_soc___024root__trace_const_0_sub_0(vlSelf, vlCtx, valsp);
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vrv32_soc___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
     VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vrv32_soc___024root___eval_static(vlSelf, vlCtx); }
     VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vrv32_soc___024root___eval_initial(vlSelf, vlCtx); }
     VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vrv32_soc___024root___eval_settle(vlSelf, vlCtx); }
@@ -1715,19 +2131,153 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
     static const char* const messages[] = {nullptr};
     static const char* const plusargs[] = {nullptr};
     static const VlcuTraceDecl traceDecls[] = {
-        {VLCU_TRACE_PUSH, 0, "$rootio", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_PUSH, 0, "rv32_soc", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_PUSH, 0, "name", 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, -1, -1, 0, 0}};  // (terminator, not counted)
+        {VLCU_TRACE_PUSH, 0, "$rootio", 0, VLCU_PREFIX_SCOPE_MODULE, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "clk", 74, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "resetn", 75, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "trap", 76, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "mem_valid", 77, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "mem_instr", 78, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "mem_addr", 79, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "mem_wdata", 80, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "mem_wstrb", 81, 4, -1, 3, 0},
+        {VLCU_TRACE_SIG, 1, "mem_rdata", 82, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "retired", 0, 32, -1, 31, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_PUSH, 0, "rv32_soc", 0, VLCU_PREFIX_SCOPE_MODULE, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "MEM_WORDS", 83, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 0, "clk", 74, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "resetn", 75, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "trap", 76, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "mem_valid", 77, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "mem_instr", 78, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "mem_addr", 79, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "mem_wdata", 80, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "mem_wstrb", 81, 4, -1, 3, 0},
+        {VLCU_TRACE_SIG, 1, "mem_rdata", 82, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "retired", 0, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "S_FETCH", 84, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "S_EXEC", 85, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "S_LOAD", 86, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "S_TRAP", 87, 2, -1, 1, 0},
+        {VLCU_TRACE_PUSH, 0, "regs", 0, VLCU_PREFIX_ARRAY_UNPACKED, -1, 0, 31},
+        {VLCU_TRACE_SIG, 1, "", 1, 32, 0, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 2, 32, 1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 3, 32, 2, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 4, 32, 3, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 5, 32, 4, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 6, 32, 5, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 7, 32, 6, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 8, 32, 7, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 9, 32, 8, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 10, 32, 9, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 11, 32, 10, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 12, 32, 11, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 13, 32, 12, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 14, 32, 13, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 15, 32, 14, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 16, 32, 15, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 17, 32, 16, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 18, 32, 17, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 19, 32, 18, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 20, 32, 19, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 21, 32, 20, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 22, 32, 21, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 23, 32, 22, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 24, 32, 23, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 25, 32, 24, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 26, 32, 25, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 27, 32, 26, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 28, 32, 27, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 29, 32, 28, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 30, 32, 29, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 31, 32, 30, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 32, 32, 31, 31, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_PUSH, 0, "", 0, VLCU_PREFIX_ARRAY_UNPACKED, -1, 0, 31},
+        {VLCU_TRACE_SIG, 1, "", 0, 32, 0, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 1, 32, 1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 2, 32, 2, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 3, 32, 3, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 4, 32, 4, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 5, 32, 5, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 6, 32, 6, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 7, 32, 7, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 8, 32, 8, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 9, 32, 9, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 10, 32, 10, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 11, 32, 11, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 12, 32, 12, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 13, 32, 13, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 14, 32, 14, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 15, 32, 15, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 16, 32, 16, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 17, 32, 17, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 18, 32, 18, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 19, 32, 19, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 20, 32, 20, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 21, 32, 21, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 22, 32, 22, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 23, 32, 23, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 24, 32, 24, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 25, 32, 25, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 26, 32, 26, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 27, 32, 27, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 28, 32, 28, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 29, 32, 29, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 30, 32, 30, 31, 0},
+        {VLCU_TRACE_SIG, 1, "", 31, 32, 31, 31, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "pc", 33, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "insn", 34, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "ld_addr", 35, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "instret", 0, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "state", 36, 2, -1, 1, 0},
+        {VLCU_TRACE_SIG, 1, "opcode", 37, 7, -1, 6, 0},
+        {VLCU_TRACE_SIG, 1, "rd", 38, 5, -1, 4, 0},
+        {VLCU_TRACE_SIG, 1, "funct3", 39, 3, -1, 2, 0},
+        {VLCU_TRACE_SIG, 1, "rs1", 40, 5, -1, 4, 0},
+        {VLCU_TRACE_SIG, 1, "rs2", 41, 5, -1, 4, 0},
+        {VLCU_TRACE_SIG, 0, "f7b5", 42, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "imm_i", 43, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "imm_s", 44, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "imm_b", 45, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "imm_u", 46, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "imm_j", 47, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 0, "is_lui", 48, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_auipc", 49, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_jal", 50, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_jalr", 51, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_branch", 52, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_load", 53, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_store", 54, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_alui", 55, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "is_alur", 56, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "rs1_val", 57, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "rs2_val", 58, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "alu_b", 59, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "shamt", 60, 5, -1, 4, 0},
+        {VLCU_TRACE_SIG, 0, "alu_sub", 61, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "alu_out", 62, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 0, "take_branch", 63, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "ls_addr", 64, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 0, "ls_misaligned", 65, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "ls_oob", 66, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 1, "st_data", 67, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "st_strb", 68, 4, -1, 3, 0},
+        {VLCU_TRACE_SIG, 1, "ld_word", 69, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "ld_shift", 70, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 1, "ld_val", 71, 32, -1, 31, 0},
+        {VLCU_TRACE_SIG, 0, "pc_bad", 72, 1, -1, 0, 0},
+        {VLCU_TRACE_SIG, 0, "exec_ls", 73, 1, -1, 0, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 0};  // codes in dump order (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "rv32_soc", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0,
         messages, 0, plusargs, 0,
-        traceDecls, 6};
+        traceDecls, 139, T::kTraceWords, traceOrder, 88};
     return s;
 }
 

@@ -565,7 +565,7 @@ uint32_t vlcu_touched_write_bytes(const vlcu_model_t* h) {
     return h->infop->touchedWriteBytes ? h->infop->touchedWriteBytes : h->infop->stateBytes;
 }
 uint32_t vlcu_trace_record_bytes(const vlcu_model_t* h) {
-    return h ? h->infop->stateBytes + VLCU_TRACE_HDR : 0;
+    return h ? VLCU_TRACE_HDR + h->infop->stateBytes + 4U * h->infop->traceWords : 0;
 }
 
 int vlcu_port_count(const vlcu_model_t* h) { return h ? static_cast<int>(h->ports.size()) : 0; }
@@ -713,7 +713,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
         }
         r.nSamples = d->n_samples;
         r.traceEvals = d->trace_evals < d->n_evals ? d->trace_evals : d->n_evals;
-        traceBytes = static_cast<size_t>(info.stateBytes + VLCU_TRACE_HDR) * r.nSamples
+        traceBytes = static_cast<size_t>(VLCU_TRACE_HDR + info.stateBytes + 4U * info.traceWords) * r.nSamples
                      * r.traceEvals;
         RUN_TRY(cudaMalloc(&dTrace, traceBytes));
         RUN_TRY(cudaMemsetAsync(dTrace, 0, traceBytes, h->stream));
@@ -984,10 +984,10 @@ int vlcu_coverage_write(const vlcu_model_t* h, const uint64_t* counts, const cha
 
 namespace {
 struct VcdSig final {
-    uint32_t code;
-    uint32_t offset;  // byte offset of the value inside a packed state record
-    uint32_t elemBytes, words, bits;
+    uint32_t code;  // word index in the trace sample
+    uint32_t bits;
     bool bit;  // declared with DECL_BIT
+    std::string ident;
 };
 std::string vcdIdent(uint32_t code) {
     std::string id;
@@ -997,18 +997,14 @@ std::string vcdIdent(uint32_t code) {
     } while (code--);
     return id;
 }
-void vcdValue(std::string& out, const VcdSig& sg, const uint8_t* valp, const std::string& ident) {
-    if (sg.bit) {
-        out += static_cast<char>('0' | (valp[0] & 1));
-    } else {
-        out += 'b';
-        for (int b = static_cast<int>(sg.bits) - 1; b >= 0; --b) {
-            out += static_cast<char>('0' | ((valp[b >> 3] >> (b & 7)) & 1));  // little endian storage
-        }
-    }
-    if (sg.bits != 1) out += ' ';  // 1-bit values have no separator before the identifier
-    out += ident;
-    out += '\n';
+std::string vcdLastWord(const std::string& s) {
+    const size_t pos = s.rfind(' ');
+    return pos == std::string::npos ? s : s.substr(pos + 1);
+}
+bool vcdProperScope(int32_t type) {
+    return type == VLCU_PREFIX_SCOPE_MODULE || type == VLCU_PREFIX_SCOPE_INTERFACE
+           || type == VLCU_PREFIX_STRUCT_PACKED || type == VLCU_PREFIX_STRUCT_UNPACKED
+           || type == VLCU_PREFIX_UNION_PACKED;
 }
 }  // namespace
 
@@ -1016,7 +1012,9 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
                    uint32_t n_samples, uint32_t sample, const char* filename) {
     if (!h || !trace || !filename || sample >= n_samples) return fail(VLCU_E_ARG, "bad argument");
     const VlcuDesignInfo& info = *h->infop;
-    if (!info.traceDecls) return fail(VLCU_E_STATE, "design has no trace declarations");
+    if (!info.traceDecls || !info.traceWords) {
+        return fail(VLCU_E_STATE, "design was not Verilated with --trace");
+    }
     std::string out = "$version Generated by VerilatedVcd $end\n$timescale 1ps $end\n";
     int indent = 1;
     const auto printIndent = [&](int change) {
@@ -1024,45 +1022,56 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
         out.append(static_cast<size_t>(indent), ' ');
         if (change > 0) indent += change;
     };
-    printIndent(1);
-    out += "$scope module TOP $end\n";  // the model's name()
-    std::map<uint32_t, VcdSig> sigs;  // by code: the dump order
+    // VerilatedVcd::pushPrefix / popPrefix / declare (include/verilated_vcd_c.cpp:323-450)
+    std::vector<std::pair<std::string, int32_t>> prefixStack{{"", VLCU_PREFIX_SCOPE_MODULE}};
+    const auto pushPrefix = [&](const std::string& name, int32_t type) {
+        const std::string prevPrefix = prefixStack.back().first;
+        if ((name == "$rootio" && !prevPrefix.empty()) || name.empty()) {
+            prefixStack.emplace_back(prevPrefix, VLCU_PREFIX_ROOTIO_WRAPPER);
+            return;
+        }
+        const std::string newPrefix = prevPrefix + name;
+        const bool proper = vcdProperScope(type);
+        if (proper) {
+            printIndent(1);
+            out += "$scope module " + vcdLastWord(newPrefix) + " $end\n";
+        }
+        prefixStack.emplace_back(newPrefix + (proper ? " " : ""), type);
+    };
+    const auto popPrefix = [&]() {
+        if (vcdProperScope(prefixStack.back().second)) {
+            printIndent(-1);
+            out += "$upscope $end\n";
+        }
+        prefixStack.pop_back();
+    };
+    std::map<uint32_t, VcdSig> sigs;  // by trace code
     const uint32_t baseCode = 1;  // VerilatedTrace::nextCode() starts at 1
+    pushPrefix("TOP", VLCU_PREFIX_SCOPE_MODULE);  // the model's name()
     for (uint32_t d = 0; d < info.nTraceDecls; ++d) {
         const VlcuTraceDecl& td = info.traceDecls[d];
         if (td.op == VLCU_TRACE_PUSH) {
-            printIndent(1);
-            out += std::string{"$scope module "} + td.name + " $end\n";
+            pushPrefix(td.name, td.arg);
         } else if (td.op == VLCU_TRACE_POP) {
-            printIndent(-1);
-            out += "$upscope $end\n";
+            popPrefix();
         } else {
-            const VlcuMemberDesc& md = info.members[td.member];
-            const uint32_t bits
-                = static_cast<uint32_t>((td.msb > td.lsb ? td.msb - td.lsb : td.lsb - td.msb) + 1);
-            const uint32_t code = baseCode + td.code;
+            const uint32_t bits = static_cast<uint32_t>(td.arg);
+            const std::string ident = vcdIdent(baseCode + td.code);
+            const std::string hierName = prefixStack.back().first + td.name;
             printIndent(0);
-            out += "$var wire " + std::to_string(bits) + ' ' + vcdIdent(code) + ' ' + td.name;
+            out += "$var wire " + std::to_string(bits) + ' ' + ident + ' ' + vcdLastWord(hierName);
             if (td.elem >= 0) out += '[' + std::to_string(td.elem) + ']';
             if (td.bussed) out += " [" + std::to_string(td.msb) + ':' + std::to_string(td.lsb) + ']';
             out += " $end\n";
-            VcdSig sg;
-            sg.code = code;
-            sg.elemBytes = md.elemBytes;
-            sg.words = td.elem >= 0 ? 1 : md.elems;
-            sg.offset = md.soaOffset + (td.elem >= 0 ? td.elem * md.elemBytes : 0);
-            sg.bits = bits;
-            sg.bit = !td.bussed;
-            sigs.emplace(code, sg);
+            sigs.emplace(td.code, VcdSig{td.code, bits, !td.bussed, ident});
         }
     }
-    printIndent(-1);
-    out += "$upscope $end\n";
+    popPrefix();
     out += "$enddefinitions $end\n\n\n";
 
-    const size_t recBytes = static_cast<size_t>(info.stateBytes) + VLCU_TRACE_HDR;
+    const size_t recBytes = VLCU_TRACE_HDR + static_cast<size_t>(info.stateBytes) + 4U * info.traceWords;
     const uint8_t* const basep = static_cast<const uint8_t*>(trace);
-    const uint8_t* prevp = nullptr;
+    const uint32_t* prevp = nullptr;
     uint64_t lastTime = 0;
     size_t timeBegin = std::string::npos, timeEnd = std::string::npos;
     for (uint64_t e = 0; e < trace_evals; ++e) {
@@ -1078,12 +1087,26 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
         timeBegin = out.size();
         out += '#' + std::to_string(time) + '\n';
         timeEnd = out.size();
-        const uint8_t* const valsp = recp + VLCU_TRACE_HDR;
-        for (const auto& it : sigs) {
-            const VcdSig& sg = it.second;
-            const size_t nbytes = static_cast<size_t>(sg.elemBytes) * sg.words;
-            if (prevp && !memcmp(valsp + sg.offset, prevp + sg.offset, nbytes)) continue;
-            vcdValue(out, sg, valsp + sg.offset, vcdIdent(sg.code));
+        const uint32_t* const valsp
+            = reinterpret_cast<const uint32_t*>(recp + VLCU_TRACE_HDR + info.stateBytes);
+        for (uint32_t k = 0; k < info.nTraceOrder; ++k) {
+            const auto it = sigs.find(info.traceOrder[k]);
+            if (it == sigs.end()) continue;
+            const VcdSig& sg = it->second;
+            const uint32_t words = (sg.bits + 31) / 32;
+            if (prevp && !memcmp(valsp + sg.code, prevp + sg.code, 4U * words)) continue;
+            // emitBit / emitCData..emitWData: all `bits` digits, MSB first
+            if (sg.bit) {
+                out += static_cast<char>('0' | (valsp[sg.code] & 1U));
+            } else {
+                out += 'b';
+                for (int b = static_cast<int>(sg.bits) - 1; b >= 0; --b) {
+                    out += static_cast<char>('0' | ((valsp[sg.code + (b >> 5)] >> (b & 31)) & 1U));
+                }
+            }
+            if (sg.bits != 1) out += ' ';  // 1-bit values have no separator before the identifier
+            out += sg.ident;
+            out += '\n';
         }
         prevp = valsp;
         lastTime = time;
