@@ -211,11 +211,13 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
                    uint32_t n_samples, uint32_t sample, const char* filename);
 
 /* ---- coverage ------------------------------------------------------------------ */
-uint32_t vlcu_coverage_bins(const vlcu_model_t* h);
-/* key fields of bin i, as passed to VL_COVER_INSERT (include/verilated_cov.h:70) */
-int vlcu_coverage_point(const vlcu_model_t* h, uint32_t bin, const char** filename, int* lineno,
-                        int* column, const char** hier, const char** page, const char** comment,
-                        const char** linescov);
+uint32_t vlcu_coverage_bins(const vlcu_model_t* h); /* counters per instance */
+uint32_t vlcu_coverage_points(const vlcu_model_t* h); /* registered points (>= bins: points can share a counter) */
+/* key fields of registration `point`, as passed to VL_COVER_INSERT (include/verilated_cov.h:70),
+   and the counter (bin) it reads */
+int vlcu_coverage_point(const vlcu_model_t* h, uint32_t point, uint32_t* bin, const char** filename,
+                        int* lineno, int* column, const char** hier, const char** page,
+                        const char** comment, const char** linescov);
 /* Sum the per-instance uint32 counters of this shard on the device into uint64 per bin; when a
    communicator is attached (vlcu_comm_init) the per-shard sums are then all-reduced with NCCL. */
 int vlcu_coverage_reduce(vlcu_model_t* h, uint64_t* out /*[bins]*/);

@@ -21,7 +21,9 @@ enum : uint32_t {
     VLCU_RUN_STOP_ON_FINISH = 1u << 1,  // an instance stops evaluating once gotFinish() is set
 };
 #define VLCU_TRACE_HDR 16  // bytes before the state record in a trace sample: u64 time, u32 status, u32 valid
-// A trace sample = [header][packed state, kStateBytes][trace words, kTraceWords x u32]
+// A trace sample = [header][packed state, kStateBytes][trace words, kTraceWords x u32, padded to
+// an even count so that every sample starts 8-byte aligned]
+#define VLCU_TRACE_WORDS_PADDED(words) (((words) + 1U) & ~1U)
 
 // Per-launch parameters of the cycle-loop kernel
 struct VlcuRunDev final {
@@ -69,6 +71,8 @@ struct VlcuMemberDesc final {
 };
 
 struct VlcuCoverPoint final {  // arguments of __vlCoverInsert / __vlCoverToggleInsert
+    uint32_t bin;  // index of the counter in __Vcoverage; several points may share one counter
+                   // (V3CoverageJoin merges toggles of signals that are always equal)
     const char* filename;
     int lineno;
     int column;
@@ -112,14 +116,11 @@ struct VlcuTraceDecl final {
 struct VlcuCoverTable final {
     std::vector<VlcuCoverPoint> points;
     std::vector<std::string> comments;  // owns the generated comment strings
-    void resize(size_t bins) {
-        points.assign(bins, VlcuCoverPoint{"", 0, 0, "", "", "", ""});
-        comments.assign(bins, std::string{});
-    }
     void other(int bin, const char* file, int line, int column, const char* hier, const char* page,
                const char* comment, const char* linescov) {
-        points[bin] = VlcuCoverPoint{file, line, column, hier, page, nullptr, linescov};
-        comments[bin] = comment;
+        points.push_back(VlcuCoverPoint{static_cast<uint32_t>(bin), file, line, column, hier, page,
+                                        nullptr, linescov});
+        comments.push_back(comment);
     }
     void toggle(int bin, int begin, int end, int ranged, const char* file, int line, int column,
                 const char* hier, const char* page, const char* comment) {
@@ -129,8 +130,9 @@ struct VlcuCoverTable final {
                 std::string c = comment;
                 if (ranged) c += '[' + std::to_string(i) + ']';
                 c += j ? ":0->1" : ":1->0";
-                points[bin] = VlcuCoverPoint{file, line, column, hier, page, nullptr, ""};
-                comments[bin] = c;
+                points.push_back(VlcuCoverPoint{static_cast<uint32_t>(bin), file, line, column, hier,
+                                                page, nullptr, ""});
+                comments.push_back(c);
                 ++bin;
             }
         }
@@ -152,9 +154,10 @@ struct VlcuDesignInfo final {
     // Persistent bytes one triggered eval reads / writes (SURVEY 8d S_state_rd / S_state_wr,
     // "touched memory words only"); 0 = the whole state (stateBytes)
     uint32_t touchedReadBytes, touchedWriteBytes;
-    const VlcuCoverPoint* coverPoints;
+    const VlcuCoverPoint* coverPoints;  // registrations, in __Vconfigure order
     uint32_t nCoverPoints;
-    uint32_t coverageSoaOffset;  // of __Vcoverage, if nCoverPoints
+    uint32_t coverBins;  // counters per instance: uint32_t __Vcoverage[coverBins]
+    uint32_t coverageSoaOffset;  // of __Vcoverage, if coverBins
     const char* const* messages;  // $display/$write format strings by id
     uint32_t nMessages;
     const char* const* plusargs;  // $test$plusargs strings by index

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
             }
             if (slot >= 0 && e < r.traceEvals) {
                 constexpr uint64_t kRecBytes
-                    = VLCU_TRACE_HDR + T_Design::kStateBytes + 4ULL * T_Design::kTraceWords;
+                    = VLCU_TRACE_HDR + T_Design::kStateBytes + 4ULL * VLCU_TRACE_WORDS_PADDED(T_Design::kTraceWords);
                 uint8_t* const recp = r.trace + (e * r.nSamples + slot) * kRecBytes;
                 reinterpret_cast<uint64_t*>(recp)[0] = ctx.time();
                 reinterpret_cast<uint32_t*>(recp)[2] = ctx.m_status;

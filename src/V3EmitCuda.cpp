@@ -244,8 +244,8 @@ class EmitCudaModel final : public EmitCFunc {
             }
         }
         // Coverage bins of this module: the counters are one more (local memory) array
-        m_topModp->foreach([&](const AstNodeCoverDecl* declp) {
-            m_coverBins = std::max(m_coverBins, declp->localBinNum() + declp->size());
+        const_cast<AstNodeModule*>(m_topModp)->foreach([&](AstNodeCoverDecl* declp) {
+            m_coverBins = std::max(m_coverBins, declp->dataDeclThisp()->localBinNum() + declp->size());
         });
         // Offsets: largest elements first so that every array start is aligned for its type
         // (an offset is multiplied by the padded instance count, a multiple of 128)
@@ -550,7 +550,7 @@ class EmitCudaModel final : public EmitCFunc {
     // _configure_coverage: each registration becomes a row of the host coverage table
     void visit(AstCoverOtherDecl* nodep) override {
         if (!m_coverTableMode) return;
-        puts("t.other(" + cvtToStr(nodep->localBinNum()) + ", ");
+        puts("t.other(" + cvtToStr(coverageBinNum(nodep)) + ", ");
         putsQuoted(protect(nodep->fileline()->filename()));
         puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", "
              + cvtToStr(nodep->offset() + nodep->fileline()->firstColumn()) + ", ");
@@ -565,7 +565,7 @@ class EmitCudaModel final : public EmitCFunc {
     }
     void visit(AstCoverToggleDecl* nodep) override {
         if (!m_coverTableMode) return;
-        puts("t.toggle(" + cvtToStr(nodep->localBinNum()) + ", " + cvtToStr(nodep->range().right()) + ", "
+        puts("t.toggle(" + cvtToStr(coverageBinNum(nodep)) + ", " + cvtToStr(nodep->range().right()) + ", "
              + cvtToStr(nodep->range().left()) + ", " + cvtToStr(nodep->range().ranged()) + ", ");
         putsQuoted(protect(nodep->fileline()->filename()));
         puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", " + cvtToStr(nodep->fileline()->firstColumn())
@@ -593,12 +593,20 @@ class EmitCudaModel final : public EmitCFunc {
                 m_traceRows.push_back("{VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}");
             } else if (const AstTraceDecl* const declp = VN_CAST(nodep, TraceDecl)) {
                 if (const AstCCall* const callp = declp->dtypeCallp()) {
-                    traceRows(callp->funcp()->stmtsp(), declp->showname(), codeBase + declp->code());
+                    // the call's arguments are `tracep, "<name>"` (V3TraceDecl.cpp:487)
+                    string name = declp->showname();
+                    const string& args = callp->argTypes();
+                    const string::size_type q0 = args.find('"');
+                    const string::size_type q1 = q0 == string::npos ? q0 : args.find('"', q0 + 1);
+                    if (q1 != string::npos) name = args.substr(q0 + 1, q1 - q0 - 1);
+                    traceRows(callp->funcp()->stmtsp(), name, codeBase + declp->code());
                 } else {
                     traceDeclRow(declp, codeBase);
                 }
             } else if (const AstStmtExpr* const stmtp = VN_CAST(nodep, StmtExpr)) {
                 if (const AstCCall* const callp = VN_CAST(stmtp->exprp(), CCall)) {
+                    // a dtype call statement was expanded at its declaration (dtypeCallp) above
+                    if (callp->argTypes().find('"') != string::npos) continue;
                     traceRows(callp->funcp()->stmtsp(), dtypeName, codeBase);
                 }
             } else if (const AstCCall* const callp = VN_CAST(nodep, CCall)) {
@@ -872,10 +880,11 @@ class EmitCudaModel final : public EmitCFunc {
         if (m_coverBins) {
             puts("static VlcuCoverTable t;\n");
             puts("if (t.points.empty()) {\n");
-            puts("t.resize(" + cvtToStr(m_coverBins) + ");\n");
             if (const AstCFunc* const funcp = findFunc("_configure_coverage")) {
                 VL_RESTORER(m_coverTableMode);
+                VL_RESTORER(m_cfuncp);
                 m_coverTableMode = true;
+                m_cfuncp = funcp;  // coverageBinNum() picks the object-local bin inside a member function
                 for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
                     if (VN_IS(stmtp, NodeCoverDecl)) iterateConst(stmtp);
                 }
@@ -903,9 +912,10 @@ class EmitCudaModel final : public EmitCFunc {
         puts("T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, "
              "T::kTouchedWriteBytes,\n");
         if (m_coverBins) {
-            puts("t.points.data(), static_cast<uint32_t>(t.points.size()), T::OFF___Vcoverage,\n");
+            puts("t.points.data(), static_cast<uint32_t>(t.points.size()), " + cvtToStr(m_coverBins)
+                 + ", T::OFF___Vcoverage,\n");
         } else {
-            puts("nullptr, 0, 0,\n");
+            puts("nullptr, 0, 0, 0,\n");
         }
         puts("messages, " + cvtToStr(m_messages.size()) + ", plusargs, " + cvtToStr(m_plusargs.size()) + ",\n");
         puts(m_traceRows.empty() ? "nullptr, 0, 0, nullptr, 0};\n"

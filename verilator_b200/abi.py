@@ -105,7 +105,8 @@ SIGNATURES = {
     "vlcu_message_format": (c_cp, [_H, c_u32]),
     "vlcu_snapshot": (c_i32, [_H, c_u64, c_vp, ctypes.c_size_t]),
     "vlcu_coverage_bins": (c_u32, [_H]),
-    "vlcu_coverage_point": (c_i32, [_H, c_u32, ctypes.POINTER(c_cp), ctypes.POINTER(c_i32),
+    "vlcu_coverage_points": (c_u32, [_H]),
+    "vlcu_coverage_point": (c_i32, [_H, c_u32, ctypes.POINTER(c_u32), ctypes.POINTER(c_cp), ctypes.POINTER(c_i32),
                                     ctypes.POINTER(c_i32), ctypes.POINTER(c_cp),
                                     ctypes.POINTER(c_cp), ctypes.POINTER(c_cp),
                                     ctypes.POINTER(c_cp)]),

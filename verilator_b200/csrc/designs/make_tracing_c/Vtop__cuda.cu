@@ -1057,7 +1057,6 @@ const VlcuDesignInfo& Vtop__cuda::info() {
     };
     static VlcuCoverTable t;
     if (t.points.empty()) {
-        t.resize(543);
         t.toggle(0, 0, 0, 0, "/root/reference/examples/make_tracing_c/top.v", 13, 11, ".top", "v_toggle/top", "clk");
         t.toggle(2, 0, 0, 0, "/root/reference/examples/make_tracing_c/top.v", 14, 11, ".top", "v_toggle/top", "reset_l");
         t.toggle(4, 0, 1, 1, "/root/reference/examples/make_tracing_c/top.v", 16, 23, ".top", "v_toggle/top", "out_small");
@@ -1082,7 +1081,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         t.other(465, "/root/reference/examples/make_tracing_c/top.v", 37, 6, ".top", "v_branch/top", "else", "");
         t.other(466, "/root/reference/examples/make_tracing_c/top.v", 36, 3, ".top", "v_line/top", "block", "36,42");
         t.toggle(0, 0, 0, 0, "/root/reference/examples/make_tracing_c/sub.v", 9, 11, ".top.sub", "v_toggle/sub", "clk");
-        t.toggle(0, 0, 0, 0, "/root/reference/examples/make_tracing_c/sub.v", 10, 11, ".top.sub", "v_toggle/sub", "reset_l");
+        t.toggle(2, 0, 0, 0, "/root/reference/examples/make_tracing_c/sub.v", 10, 11, ".top.sub", "v_toggle/sub", "reset_l");
         t.toggle(467, 0, 31, 1, "/root/reference/examples/make_tracing_c/sub.v", 14, 14, ".top.sub", "v_toggle/sub", "count_c");
         t.other(531, "/root/reference/examples/make_tracing_c/sub.v", 24, 7, ".top.sub", "v_branch/sub", "if", "24,27-28");
         t.other(532, "/root/reference/examples/make_tracing_c/sub.v", 24, 8, ".top.sub", "v_branch/sub", "else", "");
@@ -1131,7 +1130,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "top", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
-        t.points.data(), static_cast<uint32_t>(t.points.size()), T::OFF___Vcoverage,
+        t.points.data(), static_cast<uint32_t>(t.points.size()), 543, T::OFF___Vcoverage,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9};
     return s;

@@ -734,7 +734,7 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "top", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
-        nullptr, 0, 0,
+        nullptr, 0, 0, 0,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9};
     return s;

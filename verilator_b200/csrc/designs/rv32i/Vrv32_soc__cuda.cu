@@ -2193,40 +2193,6 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         {VLCU_TRACE_SIG, 1, "", 31, 32, 30, 31, 0},
         {VLCU_TRACE_SIG, 1, "", 32, 32, 31, 31, 0},
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
-        {VLCU_TRACE_PUSH, 0, "", 0, VLCU_PREFIX_ARRAY_UNPACKED, -1, 0, 31},
-        {VLCU_TRACE_SIG, 1, "", 0, 32, 0, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 1, 32, 1, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 2, 32, 2, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 3, 32, 3, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 4, 32, 4, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 5, 32, 5, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 6, 32, 6, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 7, 32, 7, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 8, 32, 8, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 9, 32, 9, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 10, 32, 10, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 11, 32, 11, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 12, 32, 12, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 13, 32, 13, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 14, 32, 14, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 15, 32, 15, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 16, 32, 16, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 17, 32, 17, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 18, 32, 18, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 19, 32, 19, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 20, 32, 20, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 21, 32, 21, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 22, 32, 22, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 23, 32, 23, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 24, 32, 24, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 25, 32, 25, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 26, 32, 26, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 27, 32, 27, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 28, 32, 28, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 29, 32, 29, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 30, 32, 30, 31, 0},
-        {VLCU_TRACE_SIG, 1, "", 31, 32, 31, 31, 0},
-        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
         {VLCU_TRACE_SIG, 1, "pc", 33, 32, -1, 31, 0},
         {VLCU_TRACE_SIG, 1, "insn", 34, 32, -1, 31, 0},
         {VLCU_TRACE_SIG, 1, "ld_addr", 35, 32, -1, 31, 0},
@@ -2275,9 +2241,9 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "rv32_soc", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
-        nullptr, 0, 0,
+        nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        traceDecls, 139, T::kTraceWords, traceOrder, 88};
+        traceDecls, 105, T::kTraceWords, traceOrder, 88};
     return s;
 }
 

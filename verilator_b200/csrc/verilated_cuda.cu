@@ -478,8 +478,8 @@ vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, 
         return bail(e, "cudaMalloc(sigs)");
     if ((e = cudaMalloc(&h->dEvalsDone, sizeof(uint64_t) * h->npad)) != cudaSuccess)
         return bail(e, "cudaMalloc(evalsDone)");
-    if (h->infop->nCoverPoints) {
-        if ((e = cudaMalloc(&h->dCovSums, sizeof(uint64_t) * h->infop->nCoverPoints))
+    if (h->infop->coverBins) {
+        if ((e = cudaMalloc(&h->dCovSums, sizeof(uint64_t) * h->infop->coverBins))
             != cudaSuccess)
             return bail(e, "cudaMalloc(covSums)");
     }
@@ -565,7 +565,7 @@ uint32_t vlcu_touched_write_bytes(const vlcu_model_t* h) {
     return h->infop->touchedWriteBytes ? h->infop->touchedWriteBytes : h->infop->stateBytes;
 }
 uint32_t vlcu_trace_record_bytes(const vlcu_model_t* h) {
-    return h ? VLCU_TRACE_HDR + h->infop->stateBytes + 4U * h->infop->traceWords : 0;
+    return h ? VLCU_TRACE_HDR + h->infop->stateBytes + 4U * VLCU_TRACE_WORDS_PADDED(h->infop->traceWords) : 0;
 }
 
 int vlcu_port_count(const vlcu_model_t* h) { return h ? static_cast<int>(h->ports.size()) : 0; }
@@ -713,7 +713,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
         }
         r.nSamples = d->n_samples;
         r.traceEvals = d->trace_evals < d->n_evals ? d->trace_evals : d->n_evals;
-        traceBytes = static_cast<size_t>(VLCU_TRACE_HDR + info.stateBytes + 4U * info.traceWords) * r.nSamples
+        traceBytes = static_cast<size_t>(VLCU_TRACE_HDR + info.stateBytes + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords)) * r.nSamples
                      * r.traceEvals;
         RUN_TRY(cudaMalloc(&dTrace, traceBytes));
         RUN_TRY(cudaMemsetAsync(dTrace, 0, traceBytes, h->stream));
@@ -855,12 +855,14 @@ int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_byte
 //-------------------------------------------------------------------------
 // Coverage
 
-uint32_t vlcu_coverage_bins(const vlcu_model_t* h) { return h ? h->infop->nCoverPoints : 0; }
-int vlcu_coverage_point(const vlcu_model_t* h, uint32_t bin, const char** filename, int* lineno,
-                        int* column, const char** hier, const char** page, const char** comment,
-                        const char** linescov) {
-    if (!h || bin >= h->infop->nCoverPoints) return fail(VLCU_E_ARG, "bad coverage bin");
-    const VlcuCoverPoint& p = h->infop->coverPoints[bin];
+uint32_t vlcu_coverage_bins(const vlcu_model_t* h) { return h ? h->infop->coverBins : 0; }
+uint32_t vlcu_coverage_points(const vlcu_model_t* h) { return h ? h->infop->nCoverPoints : 0; }
+int vlcu_coverage_point(const vlcu_model_t* h, uint32_t point, uint32_t* bin, const char** filename,
+                        int* lineno, int* column, const char** hier, const char** page,
+                        const char** comment, const char** linescov) {
+    if (!h || point >= h->infop->nCoverPoints) return fail(VLCU_E_ARG, "bad coverage point");
+    const VlcuCoverPoint& p = h->infop->coverPoints[point];
+    if (bin) *bin = p.bin;
     if (filename) *filename = p.filename;
     if (lineno) *lineno = p.lineno;
     if (column) *column = p.column;
@@ -872,7 +874,7 @@ int vlcu_coverage_point(const vlcu_model_t* h, uint32_t bin, const char** filena
 }
 int vlcu_coverage_reduce(vlcu_model_t* h, uint64_t* out) {
     if (!h || !out) return fail(VLCU_E_ARG, "null argument");
-    const uint32_t bins = h->infop->nCoverPoints;
+    const uint32_t bins = h->infop->coverBins;
     if (!bins) return fail(VLCU_E_STATE, "design was not built with coverage");
     DeviceGuard guard{h->device};
     const uint32_t* const covp = reinterpret_cast<const uint32_t*>(
@@ -958,10 +960,10 @@ int vlcu_coverage_write(const vlcu_model_t* h, const uint64_t* counts, const cha
         if (!hier.empty() && hier[0] == '.') hier = hier.substr(1);
         const auto it = events.find(name);
         if (it != events.end()) {
-            it->second.second += counts[b];
+            it->second.second += counts[p.bin];
             it->second.first = covCombineHier(it->second.first, hier);
         } else {
-            events.emplace(name, std::make_pair(hier, counts[b]));
+            events.emplace(name, std::make_pair(hier, counts[p.bin]));
         }
     }
     for (const auto& ev : events) {
@@ -1069,7 +1071,7 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
     popPrefix();
     out += "$enddefinitions $end\n\n\n";
 
-    const size_t recBytes = VLCU_TRACE_HDR + static_cast<size_t>(info.stateBytes) + 4U * info.traceWords;
+    const size_t recBytes = VLCU_TRACE_HDR + static_cast<size_t>(info.stateBytes) + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords);
     const uint8_t* const basep = static_cast<const uint8_t*>(trace);
     const uint32_t* prevp = nullptr;
     uint64_t lastTime = 0;
