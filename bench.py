@@ -146,7 +146,7 @@ def pinned_array(abi, shape, dtype):
 
 
 def cpu_reference_run(wl, sample_instances, cycles, threads):
-    """Times the reference model (restated Vtop against the genuine runtime, oracle/_ref) on the
+    """Times the reference model (the genuine Verilated C++ model + genuine runtime, oracle/_ref/libvlref.so) on the
     host cores: one instance per thread at a time, as docs/guide/verilating.rst:232-236.
     Returns (instance-cycles/s, seconds): the seconds are the slowest worker thread's time
     inside the cycle loops only -- model construction, program generation and final() are
@@ -199,7 +199,7 @@ def run_reference(args, wl):
         "config": {"workload": args.workload, "design": wl["design"], "note": wl["note"],
                    "instances_per_step": sample, "cycles_per_step": cycles},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
-                         "kind": "port (restated Vtop for the design, genuine verilated runtime)",
+                         "kind": "reference",
                          "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -333,7 +333,7 @@ def run_ours(args, wl):
         sample = cpu_sample_size(wl, c_cycles, threads, 15.0)
         cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)
         cpu = {"value": cpu_value, "unit": UNIT, "cores": threads,
-               "kind": "port (restated Vtop for the design, genuine verilated runtime)",
+               "kind": "reference",
                "sample": f"{sample} instances x {c_cycles} cycles, {cpu_dt:.1f} s, "
                          f"{threads} threads, one instance per thread at a time"}
 
