@@ -147,13 +147,13 @@ VLCU_HD WDataOutP VL_ASSIGN_W(int obits, WDataOutP owp, WDataInP lwp) {
 }
 
 // Single-bit assignment; rhs must be clean (verilated_funcs.h:471-505)
-VLCU_HD void VL_ASSIGNBIT_II(int bit, CData& lhsr, IData rhs) {
+VLCU_HD void VL_ASSIGNBIT_II(int bit, VlcuMem8& lhsr, IData rhs) {
     const int b = VL_BITBIT_I(bit);
-    lhsr = static_cast<CData>((lhsr & ~(1U << b)) | (rhs << b));
+    lhsr = static_cast<VlcuMem8>((lhsr & ~(1U << b)) | (rhs << b));
 }
-VLCU_HD void VL_ASSIGNBIT_II(int bit, SData& lhsr, IData rhs) {
+VLCU_HD void VL_ASSIGNBIT_II(int bit, VlcuMem16& lhsr, IData rhs) {
     const int b = VL_BITBIT_I(bit);
-    lhsr = static_cast<SData>((lhsr & ~(1U << b)) | (rhs << b));
+    lhsr = static_cast<VlcuMem16>((lhsr & ~(1U << b)) | (rhs << b));
 }
 VLCU_HD void VL_ASSIGNBIT_II(int bit, IData& lhsr, IData rhs) {
     const int b = VL_BITBIT_I(bit);
@@ -168,11 +168,11 @@ VLCU_HD void VL_ASSIGNBIT_WI(int bit, WDataOutP owp, IData rhs) {
     EData& w = owp[VL_BITWORD_E(bit)];
     w = (w & ~(1U << b)) | (rhs << b);
 }
-VLCU_HD void VL_ASSIGNBIT_IO(int bit, CData& lhsr) {
-    lhsr = static_cast<CData>(lhsr | (1U << VL_BITBIT_I(bit)));
+VLCU_HD void VL_ASSIGNBIT_IO(int bit, VlcuMem8& lhsr) {
+    lhsr = static_cast<VlcuMem8>(lhsr | (1U << VL_BITBIT_I(bit)));
 }
-VLCU_HD void VL_ASSIGNBIT_IO(int bit, SData& lhsr) {
-    lhsr = static_cast<SData>(lhsr | (1U << VL_BITBIT_I(bit)));
+VLCU_HD void VL_ASSIGNBIT_IO(int bit, VlcuMem16& lhsr) {
+    lhsr = static_cast<VlcuMem16>(lhsr | (1U << VL_BITBIT_I(bit)));
 }
 VLCU_HD void VL_ASSIGNBIT_IO(int bit, IData& lhsr) { lhsr |= (1U << VL_BITBIT_I(bit)); }
 VLCU_HD void VL_ASSIGNBIT_QO(int bit, QData& lhsr) { lhsr |= (1ULL << VL_BITBIT_Q(bit)); }
@@ -818,11 +818,11 @@ VLCU_HD IData vlcu_insert32(IData dst, IData ld, int hbit, int lbit, int rbits) 
     const IData field = VL_MASK_I(hbit - lbit + 1) << lbit;
     return (dst & ~field) | ((ld << lbit) & field & VL_MASK_I(rbits));
 }
-VLCU_HD void _vl_insert_II(CData& lhsr, IData ld, int hbit, int lbit, int rbits) {
-    lhsr = static_cast<CData>(vlcu_insert32(lhsr, ld, hbit, lbit, rbits));
+VLCU_HD void _vl_insert_II(VlcuMem8& lhsr, IData ld, int hbit, int lbit, int rbits) {
+    lhsr = static_cast<VlcuMem8>(vlcu_insert32(lhsr, ld, hbit, lbit, rbits));
 }
-VLCU_HD void _vl_insert_II(SData& lhsr, IData ld, int hbit, int lbit, int rbits) {
-    lhsr = static_cast<SData>(vlcu_insert32(lhsr, ld, hbit, lbit, rbits));
+VLCU_HD void _vl_insert_II(VlcuMem16& lhsr, IData ld, int hbit, int lbit, int rbits) {
+    lhsr = static_cast<VlcuMem16>(vlcu_insert32(lhsr, ld, hbit, lbit, rbits));
 }
 VLCU_HD void _vl_insert_II(IData& lhsr, IData ld, int hbit, int lbit, int rbits) {
     lhsr = vlcu_insert32(lhsr, ld, hbit, lbit, rbits);
@@ -1399,10 +1399,10 @@ VLCU_HD WDataOutP VL_SEL_WWII(int obits, int lbits, WDataOutP owp, WDataInP lwp,
 //=========================================================================
 // Range assignment (verilated_funcs.h:3346-3461); rhs may be dirty
 
-VLCU_HD void VL_ASSIGNSEL_II(int rbits, int obits, int lsb, CData& lhsr, IData rhs) {
+VLCU_HD void VL_ASSIGNSEL_II(int rbits, int obits, int lsb, VlcuMem8& lhsr, IData rhs) {
     _vl_insert_II(lhsr, rhs, lsb + obits - 1, lsb, rbits);
 }
-VLCU_HD void VL_ASSIGNSEL_II(int rbits, int obits, int lsb, SData& lhsr, IData rhs) {
+VLCU_HD void VL_ASSIGNSEL_II(int rbits, int obits, int lsb, VlcuMem16& lhsr, IData rhs) {
     _vl_insert_II(lhsr, rhs, lsb + obits - 1, lsb, rbits);
 }
 VLCU_HD void VL_ASSIGNSEL_II(int rbits, int obits, int lsb, IData& lhsr, IData rhs) {
@@ -1425,10 +1425,10 @@ VLCU_HD void VL_ASSIGNSEL_WW(int rbits, int obits, int lsb, WDataOutP iowp, WDat
 }
 
 // Select-then-assign: copy rhs[roffset +: obits] to the low bits of lhs
-VLCU_HD void VL_SELASSIGN_II(int rbits, int obits, CData& lhsr, IData rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_II(int rbits, int obits, VlcuMem8& lhsr, IData rhs, int roffset) {
     _vl_insert_II(lhsr, rhs >> roffset, obits - 1, 0, rbits);
 }
-VLCU_HD void VL_SELASSIGN_II(int rbits, int obits, SData& lhsr, IData rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_II(int rbits, int obits, VlcuMem16& lhsr, IData rhs, int roffset) {
     _vl_insert_II(lhsr, rhs >> roffset, obits - 1, 0, rbits);
 }
 VLCU_HD void VL_SELASSIGN_II(int rbits, int obits, IData& lhsr, IData rhs, int roffset) {
@@ -1442,10 +1442,10 @@ VLCU_HD void vlcu_selassign_iq(int rbits, int obits, T_Narrow& lhsr, QData rhs, 
     lhsr = static_cast<T_Narrow>((lhsr & ~field)
                                  | (static_cast<T_Narrow>(rhs >> roffset) & (field & clean)));
 }
-VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, CData& lhsr, QData rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, VlcuMem8& lhsr, QData rhs, int roffset) {
     vlcu_selassign_iq(rbits, obits, lhsr, rhs, roffset);
 }
-VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, SData& lhsr, QData rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, VlcuMem16& lhsr, QData rhs, int roffset) {
     vlcu_selassign_iq(rbits, obits, lhsr, rhs, roffset);
 }
 VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, IData& lhsr, QData rhs, int roffset) {
@@ -1454,15 +1454,15 @@ VLCU_HD void VL_SELASSIGN_IQ(int rbits, int obits, IData& lhsr, QData rhs, int r
 VLCU_HD void VL_SELASSIGN_QQ(int rbits, int obits, QData& lhsr, QData rhs, int roffset) {
     _vl_insert_QQ(lhsr, rhs >> roffset, obits - 1, 0, rbits);
 }
-VLCU_HD void VL_SELASSIGN_IW(int rbits, int obits, CData& lhsr, WDataInP rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_IW(int rbits, int obits, VlcuMem8& lhsr, WDataInP rhs, int roffset) {
     IData l = lhsr;
     _vl_insert_IW(l, rhs, roffset + obits - 1, roffset, rbits);
-    lhsr = static_cast<CData>(l);
+    lhsr = static_cast<VlcuMem8>(l);
 }
-VLCU_HD void VL_SELASSIGN_IW(int rbits, int obits, SData& lhsr, WDataInP rhs, int roffset) {
+VLCU_HD void VL_SELASSIGN_IW(int rbits, int obits, VlcuMem16& lhsr, WDataInP rhs, int roffset) {
     IData l = lhsr;
     _vl_insert_IW(l, rhs, roffset + obits - 1, roffset, rbits);
-    lhsr = static_cast<SData>(l);
+    lhsr = static_cast<VlcuMem16>(l);
 }
 VLCU_HD void VL_SELASSIGN_IW(int rbits, int obits, IData& lhsr, WDataInP rhs, int roffset) {
     _vl_insert_IW(lhsr, rhs, roffset + obits - 1, roffset, rbits);

@@ -49,8 +49,22 @@
 //=========================================================================
 // Basic integer types (same C storage classes as the host model)
 
-typedef uint8_t CData;  ///< Data representing 'bit' of 1-8 packed bits
-typedef uint16_t SData;  ///< Data representing 'bit' of 9-16 packed bits
+// Narrow values in MEMORY (the SoA block, arrays, the host interface) keep the host model's
+// C storage classes; narrow values in the per-thread model image and in temporaries are held in
+// full 32-bit registers.  A GPU register is 32 bits wide: with uint8_t/uint16_t scalars every read
+// costs a zero-extension (PRMT/LOP3) because the compiler cannot assume the upper register bits
+// are clear.  This is safe because V3Clean reasons about cleanliness with a C++ width of at
+// least 32 bits (cppWidth(), src/V3Clean.cpp:53-61): emitted code never relies on an 8/16-bit
+// container truncating a value, it masks explicitly wherever upper bits matter.
+typedef uint8_t VlcuMem8;
+typedef uint16_t VlcuMem16;
+#ifndef VLCU_NARROW_STORAGE_TYPES
+typedef uint32_t CData;  ///< Data representing 'bit' of 1-8 packed bits (32-bit register)
+typedef uint32_t SData;  ///< Data representing 'bit' of 9-16 packed bits (32-bit register)
+#else
+typedef VlcuMem8 CData;
+typedef VlcuMem16 SData;
+#endif
 typedef uint32_t IData;  ///< Data representing 'bit' of 17-32 packed bits
 typedef uint64_t QData;  ///< Data representing 'bit' of 33-64 packed bits
 typedef uint32_t EData;  ///< Data representing one element of WData array
@@ -202,11 +216,11 @@ class VlNBACommitQueue final {
     VLCU_HD static void blend(QData& ref, const QData& v, const QData& m) {
         ref = (v & m) | (ref & ~m);
     }
-    VLCU_HD static void blend(SData& ref, const SData& v, const SData& m) {
-        ref = static_cast<SData>((v & m) | (ref & ~m));
+    VLCU_HD static void blend(VlcuMem16& ref, const VlcuMem16& v, const VlcuMem16& m) {
+        ref = static_cast<VlcuMem16>((v & m) | (ref & ~m));
     }
-    VLCU_HD static void blend(CData& ref, const CData& v, const CData& m) {
-        ref = static_cast<CData>((v & m) | (ref & ~m));
+    VLCU_HD static void blend(VlcuMem8& ref, const VlcuMem8& v, const VlcuMem8& m) {
+        ref = static_cast<VlcuMem8>((v & m) | (ref & ~m));
     }
     template <size_t N>
     VLCU_HD static void blend(VlWide<N>& ref, const VlWide<N>& v, const VlWide<N>& m) {

@@ -197,9 +197,11 @@ class EmitCudaModel final : public EmitCFunc {
             m.elemBytes = 4;
             m.elemCType = "EData";
         } else if (m.width <= 8) {
-            m.elemBytes = 1, m.elemCType = "CData";
+            // in memory a narrow value keeps the host model's storage class; in the image it is a
+            // 32-bit register (include/verilated_cuda_types.h)
+            m.elemBytes = 1, m.elemCType = "VlcuMem8";
         } else if (m.width <= 16) {
-            m.elemBytes = 2, m.elemCType = "SData";
+            m.elemBytes = 2, m.elemCType = "VlcuMem16";
         } else if (m.width <= 32) {
             m.elemBytes = 4, m.elemCType = "IData";
         } else {
@@ -222,6 +224,7 @@ class EmitCudaModel final : public EmitCFunc {
             } else {
                 m.storage = CudaStorage::GLOBAL;
                 m.kind = 5;
+                if (!m.isWide && m.elemBytes < 4) m.elemDecl = m.elemCType;  // HBM layout = host layout
             }
         }
         m_members.push_back(m);

@@ -58,13 +58,13 @@ OPTEST_FN void optest_rand_one(RandReq* r) {
     ctx.m_randSeed = r->seed;
     ctx.m_randReset = static_cast<uint32_t>(r->randReset);
     if (r->kind == 0) {
-        r->out[0] = VL_SCOPED_RAND_RESET_I(ctx, r->obits, r->scopeHash, r->salt);
+        r->out[0] = vlcu_scoped_rand_reset_i(ctx, r->obits, r->scopeHash, r->salt);
     } else if (r->kind == 1) {
-        const QData q = VL_SCOPED_RAND_RESET_Q(ctx, r->obits, r->scopeHash, r->salt);
+        const QData q = vlcu_scoped_rand_reset_q(ctx, r->obits, r->scopeHash, r->salt);
         r->out[0] = static_cast<uint32_t>(q);
         r->out[1] = static_cast<uint32_t>(q >> 32);
     } else {
-        VL_SCOPED_RAND_RESET_W(ctx, r->obits, r->out, r->scopeHash, r->salt);
+        vlcu_scoped_rand_reset_w(ctx, r->obits, r->out, r->scopeHash, r->salt);
     }
     if (r->key[0]) r->keyHash = VL_MURMUR64_HASH(r->key);
 }

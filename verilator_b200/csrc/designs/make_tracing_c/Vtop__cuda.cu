@@ -116,25 +116,25 @@ struct Vtop__cuda final {
         s.__Vcoverage.bind(l.__Vcoverage);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
-        s.clk = st.ld<CData>(OFF_clk, i);
-        s.reset_l = st.ld<CData>(OFF_reset_l, i);
-        s.out_small = st.ld<CData>(OFF_out_small, i);
-        s.in_small = st.ld<CData>(OFF_in_small, i);
-        s.top__DOT____VlemCond_0 = st.ld<CData>(OFF_top__DOT____VlemCond_0, i);
-        s.top__DOT____Vtogcov__clk = st.ld<CData>(OFF_top__DOT____Vtogcov__clk, i);
-        s.top__DOT____Vtogcov__reset_l = st.ld<CData>(OFF_top__DOT____Vtogcov__reset_l, i);
-        s.top__DOT____Vtogcov__out_small = st.ld<CData>(OFF_top__DOT____Vtogcov__out_small, i);
-        s.top__DOT____Vtogcov__in_small = st.ld<CData>(OFF_top__DOT____Vtogcov__in_small, i);
-        s.__VstlFirstIteration = st.ld<CData>(OFF___VstlFirstIteration, i);
-        s.__VstlPhaseResult = st.ld<CData>(OFF___VstlPhaseResult, i);
-        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<CData>(OFF___Vtrigprevexpr___TOP__clk__0, i);
-        s.__Vtrigprevexpr___TOP__reset_l__0 = st.ld<CData>(OFF___Vtrigprevexpr___TOP__reset_l__0, i);
-        s.__Vtrigprevexpr___TOP__in_small__0 = st.ld<CData>(OFF___Vtrigprevexpr___TOP__in_small__0, i);
-        s.__VicoDidInit = st.ld<CData>(OFF___VicoDidInit, i);
-        s.__VicoPhaseResult = st.ld<CData>(OFF___VicoPhaseResult, i);
-        s.__Vtrigprevexpr___TOP__clk__1 = st.ld<CData>(OFF___Vtrigprevexpr___TOP__clk__1, i);
-        s.__VactPhaseResult = st.ld<CData>(OFF___VactPhaseResult, i);
-        s.__VnbaPhaseResult = st.ld<CData>(OFF___VnbaPhaseResult, i);
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.reset_l = st.ld<VlcuMem8>(OFF_reset_l, i);
+        s.out_small = st.ld<VlcuMem8>(OFF_out_small, i);
+        s.in_small = st.ld<VlcuMem8>(OFF_in_small, i);
+        s.top__DOT____VlemCond_0 = st.ld<VlcuMem8>(OFF_top__DOT____VlemCond_0, i);
+        s.top__DOT____Vtogcov__clk = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__clk, i);
+        s.top__DOT____Vtogcov__reset_l = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__reset_l, i);
+        s.top__DOT____Vtogcov__out_small = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__out_small, i);
+        s.top__DOT____Vtogcov__in_small = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__in_small, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__Vtrigprevexpr___TOP__reset_l__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__reset_l__0, i);
+        s.__Vtrigprevexpr___TOP__in_small__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__in_small__0, i);
+        s.__VicoDidInit = st.ld<VlcuMem8>(OFF___VicoDidInit, i);
+        s.__VicoPhaseResult = st.ld<VlcuMem8>(OFF___VicoPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__1 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
         st.ldW(OFF_out_wide, i, s.out_wide);
         st.ldW(OFF_in_wide, i, s.in_wide);
         st.ldW(OFF_top__DOT____VlemCond_2, i, s.top__DOT____VlemCond_2);
@@ -158,25 +158,25 @@ struct Vtop__cuda final {
         for (uint32_t e = 0; e < 543; ++e) s.__Vcoverage[e] = st.ldE<uint32_t>(OFF___Vcoverage, e, i);
     }
     VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
-        st.st<CData>(OFF_clk, i, s.clk);
-        st.st<CData>(OFF_reset_l, i, s.reset_l);
-        st.st<CData>(OFF_out_small, i, s.out_small);
-        st.st<CData>(OFF_in_small, i, s.in_small);
-        st.st<CData>(OFF_top__DOT____VlemCond_0, i, s.top__DOT____VlemCond_0);
-        st.st<CData>(OFF_top__DOT____Vtogcov__clk, i, s.top__DOT____Vtogcov__clk);
-        st.st<CData>(OFF_top__DOT____Vtogcov__reset_l, i, s.top__DOT____Vtogcov__reset_l);
-        st.st<CData>(OFF_top__DOT____Vtogcov__out_small, i, s.top__DOT____Vtogcov__out_small);
-        st.st<CData>(OFF_top__DOT____Vtogcov__in_small, i, s.top__DOT____Vtogcov__in_small);
-        st.st<CData>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
-        st.st<CData>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
-        st.st<CData>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
-        st.st<CData>(OFF___Vtrigprevexpr___TOP__reset_l__0, i, s.__Vtrigprevexpr___TOP__reset_l__0);
-        st.st<CData>(OFF___Vtrigprevexpr___TOP__in_small__0, i, s.__Vtrigprevexpr___TOP__in_small__0);
-        st.st<CData>(OFF___VicoDidInit, i, s.__VicoDidInit);
-        st.st<CData>(OFF___VicoPhaseResult, i, s.__VicoPhaseResult);
-        st.st<CData>(OFF___Vtrigprevexpr___TOP__clk__1, i, s.__Vtrigprevexpr___TOP__clk__1);
-        st.st<CData>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
-        st.st<CData>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_reset_l, i, s.reset_l);
+        st.st<VlcuMem8>(OFF_out_small, i, s.out_small);
+        st.st<VlcuMem8>(OFF_in_small, i, s.in_small);
+        st.st<VlcuMem8>(OFF_top__DOT____VlemCond_0, i, s.top__DOT____VlemCond_0);
+        st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__clk, i, s.top__DOT____Vtogcov__clk);
+        st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__reset_l, i, s.top__DOT____Vtogcov__reset_l);
+        st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__out_small, i, s.top__DOT____Vtogcov__out_small);
+        st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__in_small, i, s.top__DOT____Vtogcov__in_small);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__reset_l__0, i, s.__Vtrigprevexpr___TOP__reset_l__0);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__in_small__0, i, s.__Vtrigprevexpr___TOP__in_small__0);
+        st.st<VlcuMem8>(OFF___VicoDidInit, i, s.__VicoDidInit);
+        st.st<VlcuMem8>(OFF___VicoPhaseResult, i, s.__VicoPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i, s.__Vtrigprevexpr___TOP__clk__1);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
         st.stW(OFF_out_wide, i, s.out_wide);
         st.stW(OFF_in_wide, i, s.in_wide);
         st.stW(OFF_top__DOT____VlemCond_2, i, s.top__DOT____VlemCond_2);
@@ -200,9 +200,9 @@ struct Vtop__cuda final {
         for (uint32_t e = 0; e < 543; ++e) st.stE<uint32_t>(OFF___Vcoverage, e, i, s.__Vcoverage[e]);
     }
     VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
-        s.clk = static_cast<CData>(rowp[0 * stride + i] & 0x1U);
-        s.reset_l = static_cast<CData>(rowp[1 * stride + i] & 0x1U);
-        s.in_small = static_cast<CData>(rowp[2 * stride + i] & 0x3U);
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+        s.reset_l = static_cast<VlcuMem8>(rowp[1 * stride + i] & 0x1U);
+        s.in_small = static_cast<VlcuMem8>(rowp[2 * stride + i] & 0x3U);
         s.in_quad = (static_cast<QData>(rowp[4 * stride + i] & 0xffU) << 32) | rowp[3 * stride + i];
         s.in_wide[0] = rowp[5 * stride + i] & 0xffffffffU;
         s.in_wide[1] = rowp[6 * stride + i] & 0xffffffffU;

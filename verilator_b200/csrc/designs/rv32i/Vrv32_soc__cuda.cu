@@ -139,30 +139,30 @@ struct Vrv32_soc__cuda final {
         s.rv32_soc__DOT__regs.bind(sh.rv32_soc__DOT__regs, threadIdx.x);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
-        s.clk = st.ld<CData>(OFF_clk, i);
-        s.resetn = st.ld<CData>(OFF_resetn, i);
-        s.trap = st.ld<CData>(OFF_trap, i);
-        s.mem_valid = st.ld<CData>(OFF_mem_valid, i);
-        s.mem_instr = st.ld<CData>(OFF_mem_instr, i);
-        s.mem_wstrb = st.ld<CData>(OFF_mem_wstrb, i);
-        s.rv32_soc__DOT__state = st.ld<CData>(OFF_rv32_soc__DOT__state, i);
-        s.rv32_soc__DOT__is_jalr = st.ld<CData>(OFF_rv32_soc__DOT__is_jalr, i);
-        s.rv32_soc__DOT__is_branch = st.ld<CData>(OFF_rv32_soc__DOT__is_branch, i);
-        s.rv32_soc__DOT__is_load = st.ld<CData>(OFF_rv32_soc__DOT__is_load, i);
-        s.rv32_soc__DOT__is_store = st.ld<CData>(OFF_rv32_soc__DOT__is_store, i);
-        s.rv32_soc__DOT__is_alui = st.ld<CData>(OFF_rv32_soc__DOT__is_alui, i);
-        s.rv32_soc__DOT__is_alur = st.ld<CData>(OFF_rv32_soc__DOT__is_alur, i);
-        s.rv32_soc__DOT__take_branch = st.ld<CData>(OFF_rv32_soc__DOT__take_branch, i);
-        s.rv32_soc__DOT__ls_misaligned = st.ld<CData>(OFF_rv32_soc__DOT__ls_misaligned, i);
-        s.rv32_soc__DOT__st_strb = st.ld<CData>(OFF_rv32_soc__DOT__st_strb, i);
-        s.rv32_soc__DOT__pc_bad = st.ld<CData>(OFF_rv32_soc__DOT__pc_bad, i);
-        s.rv32_soc__DOT__exec_ls = st.ld<CData>(OFF_rv32_soc__DOT__exec_ls, i);
-        s.__VdfgRegularize_h6e95ff9d_0_0 = st.ld<CData>(OFF___VdfgRegularize_h6e95ff9d_0_0, i);
-        s.__VstlFirstIteration = st.ld<CData>(OFF___VstlFirstIteration, i);
-        s.__VstlPhaseResult = st.ld<CData>(OFF___VstlPhaseResult, i);
-        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<CData>(OFF___Vtrigprevexpr___TOP__clk__0, i);
-        s.__VactPhaseResult = st.ld<CData>(OFF___VactPhaseResult, i);
-        s.__VnbaPhaseResult = st.ld<CData>(OFF___VnbaPhaseResult, i);
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.resetn = st.ld<VlcuMem8>(OFF_resetn, i);
+        s.trap = st.ld<VlcuMem8>(OFF_trap, i);
+        s.mem_valid = st.ld<VlcuMem8>(OFF_mem_valid, i);
+        s.mem_instr = st.ld<VlcuMem8>(OFF_mem_instr, i);
+        s.mem_wstrb = st.ld<VlcuMem8>(OFF_mem_wstrb, i);
+        s.rv32_soc__DOT__state = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__state, i);
+        s.rv32_soc__DOT__is_jalr = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_jalr, i);
+        s.rv32_soc__DOT__is_branch = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_branch, i);
+        s.rv32_soc__DOT__is_load = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_load, i);
+        s.rv32_soc__DOT__is_store = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_store, i);
+        s.rv32_soc__DOT__is_alui = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_alui, i);
+        s.rv32_soc__DOT__is_alur = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_alur, i);
+        s.rv32_soc__DOT__take_branch = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__take_branch, i);
+        s.rv32_soc__DOT__ls_misaligned = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__ls_misaligned, i);
+        s.rv32_soc__DOT__st_strb = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__st_strb, i);
+        s.rv32_soc__DOT__pc_bad = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__pc_bad, i);
+        s.rv32_soc__DOT__exec_ls = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__exec_ls, i);
+        s.__VdfgRegularize_h6e95ff9d_0_0 = st.ld<VlcuMem8>(OFF___VdfgRegularize_h6e95ff9d_0_0, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
         s.mem_addr = st.ld<IData>(OFF_mem_addr, i);
         s.mem_wdata = st.ld<IData>(OFF_mem_wdata, i);
         s.mem_rdata = st.ld<IData>(OFF_mem_rdata, i);
@@ -188,33 +188,33 @@ struct Vrv32_soc__cuda final {
         for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
         for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
         for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
-        for (uint32_t e = 0; e < 2; ++e) s.__Vm_traceActivity[e] = st.ldE<CData>(OFF___Vm_traceActivity, e, i);
+        for (uint32_t e = 0; e < 2; ++e) s.__Vm_traceActivity[e] = st.ldE<VlcuMem8>(OFF___Vm_traceActivity, e, i);
     }
     VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
-        st.st<CData>(OFF_clk, i, s.clk);
-        st.st<CData>(OFF_resetn, i, s.resetn);
-        st.st<CData>(OFF_trap, i, s.trap);
-        st.st<CData>(OFF_mem_valid, i, s.mem_valid);
-        st.st<CData>(OFF_mem_instr, i, s.mem_instr);
-        st.st<CData>(OFF_mem_wstrb, i, s.mem_wstrb);
-        st.st<CData>(OFF_rv32_soc__DOT__state, i, s.rv32_soc__DOT__state);
-        st.st<CData>(OFF_rv32_soc__DOT__is_jalr, i, s.rv32_soc__DOT__is_jalr);
-        st.st<CData>(OFF_rv32_soc__DOT__is_branch, i, s.rv32_soc__DOT__is_branch);
-        st.st<CData>(OFF_rv32_soc__DOT__is_load, i, s.rv32_soc__DOT__is_load);
-        st.st<CData>(OFF_rv32_soc__DOT__is_store, i, s.rv32_soc__DOT__is_store);
-        st.st<CData>(OFF_rv32_soc__DOT__is_alui, i, s.rv32_soc__DOT__is_alui);
-        st.st<CData>(OFF_rv32_soc__DOT__is_alur, i, s.rv32_soc__DOT__is_alur);
-        st.st<CData>(OFF_rv32_soc__DOT__take_branch, i, s.rv32_soc__DOT__take_branch);
-        st.st<CData>(OFF_rv32_soc__DOT__ls_misaligned, i, s.rv32_soc__DOT__ls_misaligned);
-        st.st<CData>(OFF_rv32_soc__DOT__st_strb, i, s.rv32_soc__DOT__st_strb);
-        st.st<CData>(OFF_rv32_soc__DOT__pc_bad, i, s.rv32_soc__DOT__pc_bad);
-        st.st<CData>(OFF_rv32_soc__DOT__exec_ls, i, s.rv32_soc__DOT__exec_ls);
-        st.st<CData>(OFF___VdfgRegularize_h6e95ff9d_0_0, i, s.__VdfgRegularize_h6e95ff9d_0_0);
-        st.st<CData>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
-        st.st<CData>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
-        st.st<CData>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
-        st.st<CData>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
-        st.st<CData>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_resetn, i, s.resetn);
+        st.st<VlcuMem8>(OFF_trap, i, s.trap);
+        st.st<VlcuMem8>(OFF_mem_valid, i, s.mem_valid);
+        st.st<VlcuMem8>(OFF_mem_instr, i, s.mem_instr);
+        st.st<VlcuMem8>(OFF_mem_wstrb, i, s.mem_wstrb);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__state, i, s.rv32_soc__DOT__state);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_jalr, i, s.rv32_soc__DOT__is_jalr);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_branch, i, s.rv32_soc__DOT__is_branch);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_load, i, s.rv32_soc__DOT__is_load);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_store, i, s.rv32_soc__DOT__is_store);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_alui, i, s.rv32_soc__DOT__is_alui);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_alur, i, s.rv32_soc__DOT__is_alur);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__take_branch, i, s.rv32_soc__DOT__take_branch);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__ls_misaligned, i, s.rv32_soc__DOT__ls_misaligned);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__st_strb, i, s.rv32_soc__DOT__st_strb);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__pc_bad, i, s.rv32_soc__DOT__pc_bad);
+        st.st<VlcuMem8>(OFF_rv32_soc__DOT__exec_ls, i, s.rv32_soc__DOT__exec_ls);
+        st.st<VlcuMem8>(OFF___VdfgRegularize_h6e95ff9d_0_0, i, s.__VdfgRegularize_h6e95ff9d_0_0);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
         st.st<IData>(OFF_mem_addr, i, s.mem_addr);
         st.st<IData>(OFF_mem_wdata, i, s.mem_wdata);
         st.st<IData>(OFF_mem_rdata, i, s.mem_rdata);
@@ -240,11 +240,11 @@ struct Vrv32_soc__cuda final {
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
-        for (uint32_t e = 0; e < 2; ++e) st.stE<CData>(OFF___Vm_traceActivity, e, i, s.__Vm_traceActivity[e]);
+        for (uint32_t e = 0; e < 2; ++e) st.stE<VlcuMem8>(OFF___Vm_traceActivity, e, i, s.__Vm_traceActivity[e]);
     }
     VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
-        s.clk = static_cast<CData>(rowp[0 * stride + i] & 0x1U);
-        s.resetn = static_cast<CData>(rowp[1 * stride + i] & 0x1U);
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+        s.resetn = static_cast<VlcuMem8>(rowp[1 * stride + i] & 0x1U);
     }
     VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
         rowp[0 * stride + i] = s.trap;
