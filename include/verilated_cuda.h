@@ -543,11 +543,14 @@ VLCU_D void vlcu_eval_step(typename T_Design::Root* rootp, VlcuContext& ctx) {
     T_Design::eval(rootp, ctx);
 }
 
-// Running 64-bit signature of observed output words (FNV-1a style); lets a
-// K-cycle fused run be checked against the oracle without storing every port
-// value of every instance every cycle.
-VLCU_HD uint64_t vlcu_sig_mix(uint64_t sig, uint32_t word) {
-    return (sig ^ word) * 0x100000001b3ULL;
+// Running 64-bit signature of the output ports; lets a K-cycle fused run be checked against the
+// oracle without storing every port value of every instance every cycle.  Per eval the output
+// words are folded into a 32-bit FNV-1a accumulator (one LOP3 + one IMAD per word), which is then
+// mixed into the 64-bit signature once (FNV-1a, 64-bit prime).
+#define VLCU_SIG_ACC_INIT 0x811c9dc5U
+VLCU_HD uint32_t vlcu_sig_word(uint32_t acc, uint32_t word) { return (acc ^ word) * 0x01000193U; }
+VLCU_HD uint64_t vlcu_sig_mix(uint64_t sig, uint32_t acc) {
+    return (sig ^ acc) * 0x100000001b3ULL;
 }
 #define VLCU_SIG_INIT 0xcbf29ce484222325ULL
 

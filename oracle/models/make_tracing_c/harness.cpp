@@ -38,7 +38,9 @@ struct StatusRec {  // == vlcu_status_t (include/verilated_cuda_abi.h)
 
 constexpr int kCovBins = sizeof(Vtop___024root::__Vcoverage) / sizeof(uint32_t);
 
-inline uint64_t sigMix(uint64_t sig, uint32_t word) { return (sig ^ word) * 0x100000001b3ULL; }
+// the signature of include/verilated_cuda.h (vlcu_sig_word / vlcu_sig_mix)
+inline uint32_t sigWord(uint32_t acc, uint32_t word) { return (acc ^ word) * 0x01000193U; }
+inline uint64_t sigMix(uint64_t sig, uint32_t acc) { return (sig ^ acc) * 0x100000001b3ULL; }
 
 struct Params {
     uint64_t n, instBase, seedBase;
@@ -145,12 +147,14 @@ void runOne(const Params& p, uint64_t i, std::vector<uint64_t>& covLocal) {
             }
         }
         if (tfp) tfp->dump(contextp->time());
-        sig = sigMix(sig, top->out_small);
-        sig = sigMix(sig, static_cast<uint32_t>(top->out_quad));
-        sig = sigMix(sig, static_cast<uint32_t>(top->out_quad >> 32));
-        sig = sigMix(sig, top->out_wide[0]);
-        sig = sigMix(sig, top->out_wide[1]);
-        sig = sigMix(sig, top->out_wide[2]);
+        uint32_t acc = 0x811c9dc5U;
+        acc = sigWord(acc, top->out_small);
+        acc = sigWord(acc, static_cast<uint32_t>(top->out_quad));
+        acc = sigWord(acc, static_cast<uint32_t>(top->out_quad >> 32));
+        acc = sigWord(acc, top->out_wide[0]);
+        acc = sigWord(acc, top->out_wide[1]);
+        acc = sigWord(acc, top->out_wide[2]);
+        sig = sigMix(sig, acc);
         if (p.obs && e < p.obsEvals) {
             uint32_t* const rowp = p.obs + e * 6 * p.n;
             rowp[0 * p.n + i] = top->out_small;

@@ -23,7 +23,9 @@
 // Harness: N instances, the stimulus of the device testbenches TbRv32Rand / TbRv32Host
 
 namespace {
-inline uint64_t sigMix(uint64_t sig, uint32_t word) { return (sig ^ word) * 0x100000001b3ULL; }
+// the signature of include/verilated_cuda.h (vlcu_sig_word / vlcu_sig_mix)
+inline uint32_t sigWord(uint32_t acc, uint32_t word) { return (acc ^ word) * 0x01000193U; }
+inline uint64_t sigMix(uint64_t sig, uint32_t acc) { return (sig ^ acc) * 0x100000001b3ULL; }
 
 struct Rv32Params {
     uint64_t n, instBase, seedBase;
@@ -80,14 +82,16 @@ void runOne(const Rv32Params& p, uint64_t i) {
             top->eval();
             if (tfp) tfp->dump(contextp->time());
             // every output port in source order, as the emitted outputs_sig() does
-            sig = sigMix(sig, top->trap);
-            sig = sigMix(sig, top->mem_valid);
-            sig = sigMix(sig, top->mem_instr);
-            sig = sigMix(sig, top->mem_addr);
-            sig = sigMix(sig, top->mem_wdata);
-            sig = sigMix(sig, top->mem_wstrb);
-            sig = sigMix(sig, top->mem_rdata);
-            sig = sigMix(sig, top->retired);
+            uint32_t acc = 0x811c9dc5U;
+            acc = sigWord(acc, top->trap);
+            acc = sigWord(acc, top->mem_valid);
+            acc = sigWord(acc, top->mem_instr);
+            acc = sigWord(acc, top->mem_addr);
+            acc = sigWord(acc, top->mem_wdata);
+            acc = sigWord(acc, top->mem_wstrb);
+            acc = sigWord(acc, top->mem_rdata);
+            acc = sigWord(acc, top->retired);
+            sig = sigMix(sig, acc);
             const uint64_t ge = round * p.nEvals + e;
             if (p.obs && ge < p.obsEvals) {
                 uint32_t* const rowp = p.obs + ge * 8 * p.n;

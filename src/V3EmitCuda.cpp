@@ -421,13 +421,14 @@ class EmitCudaModel final : public EmitCFunc {
                     value = "s." + m.name;
                 }
                 puts("rowp[" + cvtToStr(outWords + w) + " * stride + i] = " + value + ";\n");
-                sigBody += "sig = vlcu_sig_mix(sig, " + value + ");\n";
+                sigBody += "acc = vlcu_sig_word(acc, " + value + ");\n";
             }
             outWords += rowWords(m);
             outBytes += m.bytes();
         }
         puts("}\n");
-        puts("VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {\n" + sigBody + "return sig;\n}\n");
+        puts("VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {\nuint32_t acc = VLCU_SIG_ACC_INIT;\n"
+             + sigBody + "return vlcu_sig_mix(sig, acc);\n}\n");
         m_sizes = "kInWords = " + cvtToStr(inWords) + ", kOutWords = " + cvtToStr(outWords)
                   + ", kInBytes = " + cvtToStr(inBytes) + ", kOutBytes = " + cvtToStr(outBytes);
     }

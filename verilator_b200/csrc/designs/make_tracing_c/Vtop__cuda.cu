@@ -217,13 +217,14 @@ struct Vtop__cuda final {
         rowp[5 * stride + i] = s.out_wide[2];
     }
     VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
-        sig = vlcu_sig_mix(sig, s.out_small);
-        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad));
-        sig = vlcu_sig_mix(sig, static_cast<uint32_t>(s.out_quad >> 32));
-        sig = vlcu_sig_mix(sig, s.out_wide[0]);
-        sig = vlcu_sig_mix(sig, s.out_wide[1]);
-        sig = vlcu_sig_mix(sig, s.out_wide[2]);
-        return sig;
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        acc = vlcu_sig_word(acc, s.out_small);
+        acc = vlcu_sig_word(acc, static_cast<uint32_t>(s.out_quad));
+        acc = vlcu_sig_word(acc, static_cast<uint32_t>(s.out_quad >> 32));
+        acc = vlcu_sig_word(acc, s.out_wide[0]);
+        acc = vlcu_sig_word(acc, s.out_wide[1]);
+        acc = vlcu_sig_word(acc, s.out_wide[2]);
+        return vlcu_sig_mix(sig, acc);
     }
     enum : uint32_t { kInWords = 8, kOutWords = 6, kInBytes = 23, kOutBytes = 21, kTraceWords = 15 };
 

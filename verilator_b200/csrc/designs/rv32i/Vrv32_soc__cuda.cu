@@ -257,15 +257,16 @@ struct Vrv32_soc__cuda final {
         rowp[7 * stride + i] = s.retired;
     }
     VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
-        sig = vlcu_sig_mix(sig, s.trap);
-        sig = vlcu_sig_mix(sig, s.mem_valid);
-        sig = vlcu_sig_mix(sig, s.mem_instr);
-        sig = vlcu_sig_mix(sig, s.mem_addr);
-        sig = vlcu_sig_mix(sig, s.mem_wdata);
-        sig = vlcu_sig_mix(sig, s.mem_wstrb);
-        sig = vlcu_sig_mix(sig, s.mem_rdata);
-        sig = vlcu_sig_mix(sig, s.retired);
-        return sig;
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        acc = vlcu_sig_word(acc, s.trap);
+        acc = vlcu_sig_word(acc, s.mem_valid);
+        acc = vlcu_sig_word(acc, s.mem_instr);
+        acc = vlcu_sig_word(acc, s.mem_addr);
+        acc = vlcu_sig_word(acc, s.mem_wdata);
+        acc = vlcu_sig_word(acc, s.mem_wstrb);
+        acc = vlcu_sig_word(acc, s.mem_rdata);
+        acc = vlcu_sig_word(acc, s.retired);
+        return vlcu_sig_mix(sig, acc);
     }
     enum : uint32_t { kInWords = 2, kOutWords = 8, kInBytes = 2, kOutBytes = 20, kTraceWords = 88 };
 
