@@ -56,6 +56,13 @@ WORKLOADS = {
         note="examples/make_tracing_c built --coverage (543 bins/instance), per-instance random "
              "stimulus offsets, reset every 128 time units; e2e adds the on-device coverage "
              "reduction + ncclAllReduce + coverage.dat write per step"),
+    # BASELINE.json configs[3] class: wide-bus, VlWide-heavy path, 4,096 instances (OpenTitan is
+    # not vendored; wide_bus.v is this repo's 256-bit datapath block)
+    "wide_bus": dict(
+        design="wide_bus", tb="wide_rand", instances=4096, cycles=8192, tb_flags=0,
+        tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
+        note="wide_bus.v (own RTL): 256-bit add/sub/mul/variable shifts/compares/part-select per "
+             "cycle, fresh random inputs every cycle from VlRNG"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -155,6 +162,9 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     import oracle_util as O
     if wl["design"] == "rv32i":
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+                   threads=threads)
+    elif wl["design"] == "wide_bus":
+        O.wide_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads)
     else:
         O.mtc_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,

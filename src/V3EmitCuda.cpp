@@ -454,8 +454,38 @@ class EmitCudaModel final : public EmitCFunc {
         return args;
     }
 
+    // ---- constant pool (V3EmitCConstPool.cpp:44-92): wide constants and V3Table tables as
+    // device-resident read-only data, under the names the function bodies use
+    bool m_constInitMode = false;
+    void emitConstPool() {
+        const AstConstPool* const poolp = v3Global.rootp()->constPoolp();
+        std::vector<const AstVar*> varps;
+        for (AstNode* nodep = poolp->modp()->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (const AstVar* const varp = VN_CAST(nodep, Var)) varps.push_back(varp);
+        }
+        if (varps.empty()) return;
+        std::stable_sort(varps.begin(), varps.end(),
+                         [](const AstVar* ap, const AstVar* bp) { return ap->name() < bp->name(); });
+        puts("\n// Constant pool\n");
+        VL_RESTORER(m_constInitMode);
+        m_constInitMode = true;
+        for (const AstVar* const varp : varps) {
+            const string name = EmitCUtil::topClassName() + "__ConstPool__" + varp->nameProtect();
+            putns(varp, "static __device__ const " + varp->dtypep()->cType(name, false, false) + " = ");
+            iterateConst(varp->valuep());
+            puts(";\n");
+        }
+    }
+
     // VISITORS
     using EmitCFunc::visit;
+    void visit(AstConst* nodep) override {
+        if (m_constInitMode) {
+            EmitCConstInit::visit(nodep);  // initializer form: VlWide<N>{{...}}
+        } else {
+            EmitCFunc::visit(nodep);
+        }
+    }
     void visit(AstCFunc* nodep) override {
         // EmitCFunc::visit(AstCFunc*) (V3EmitCFunc.h:398-500) for a device function
         VL_RESTORER(m_useSelfForThis);
@@ -690,11 +720,17 @@ class EmitCudaModel final : public EmitCFunc {
              + "* vlSelf, VlcuContext& vlCtx, uint32_t* valsp"
              + (m_inDtypeTraceFunc ? ", uint32_t offset, const T_DtypeVar& __VdtypeVar" : "") + ") {\n");
         puts("auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;\n");
+        if (funcp->varsp()) iterateAndNextConstNull(funcp->varsp());  // wide temporaries
         for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
-            if (VN_IS(stmtp, TraceInc)) {
+            const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr);
+            const AstCCall* const callp = sep ? VN_CAST(sep->exprp(), CCall) : nullptr;
+            if (callp && callp->funcp()->isTrace()) {
+                emitTraceCall(callp);
+            } else if (VN_IS(stmtp, CStmt)) {
+                // literal host text (the `oldp` pointer of the trace buffer): not needed
+            } else {
+                // AstTraceInc (store by code), or a statement computing a wide temporary for one
                 iterateConst(stmtp);
-            } else if (const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr)) {
-                if (const AstCCall* const callp = VN_CAST(sep->exprp(), CCall)) emitTraceCall(callp);
             }
         }
         m_usevlSelfRef = false;
@@ -776,6 +812,7 @@ class EmitCudaModel final : public EmitCFunc {
         puts("\n#include <vector>\n");
         puts("\n// Name the design registers under with vlcu_create()\n");
         puts("#ifndef VLCU_DESIGN_NAME\n#define VLCU_DESIGN_NAME " + quoted(v3Global.opt.prefix()) + "\n#endif\n");
+        emitConstPool();
         emitRootStruct();
 
         puts("\nstruct " + m_designName + " final {\n");

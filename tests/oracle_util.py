@@ -139,3 +139,28 @@ def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_tim
     if not obs_evals:
         r.obs = None
     return r
+
+
+# ---- wide_bus (oracle/models/wide_bus) ---------------------------------------------------
+class WideResult:
+    pass
+
+
+def wide_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_time=0, obs_evals=0,
+             threads=1, vcd_path=None, vcd_instance=-1):
+    """Genuine Verilated wide_bus model, stimulus of the device testbench TbWideRand."""
+    lib = ref()
+    lib.vlref_wide_run.restype = i32
+    lib.vlref_wide_run.argtypes = [u64, u64, u64, i32, u64, u64, u32, vp, u64, vp, vp, cp, i64, i32]
+    r = WideResult()
+    r.obs = np.zeros((max(obs_evals, 1), 19, n), dtype=np.uint32)
+    r.sigs = np.zeros(n, dtype=np.uint64)
+    r.acc = np.zeros((n, 8), dtype=np.uint32)
+    rc = lib.vlref_wide_run(n, inst_base, seed, rand_reset, n_evals, tb_seed, reset_time,
+                            r.obs.ctypes.data if obs_evals else None, obs_evals, r.sigs.ctypes.data,
+                            r.acc.ctypes.data, vcd_path.encode() if vcd_path else None, vcd_instance,
+                            threads)
+    assert rc == 0
+    if not obs_evals:
+        r.obs = None
+    return r
