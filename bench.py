@@ -364,10 +364,13 @@ def run_ours(args, wl):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "vlcu_k_run", "algorithmic_bytes_per_instance_cycle": b_alg,
-                     "note": "B_alg = 2*(S_state_rd+S_state_wr) + 2*(S_in+S_out) with touched-only state bytes; "
-                             "the K-cycle fused kernel keeps registers/flops on chip across the step, so "
-                             "measured DRAM traffic (traffic) is below B_alg and frac can exceed 1 "
-                             "(see DESIGN.md, roofline section)"},
+                     "dram_gbs_from_traffic": (traffic / (mean_ms / 1e3) / 1e9) if traffic else None,
+                     "note": "achieved = B_alg x instance-cycles/s, B_alg = 2*(S_state_rd+S_state_wr) + 2*(S_in+S_out) "
+                             "(SURVEY 8d; S_* printed by V3EmitCuda): the bandwidth an eval-per-launch "
+                             "implementation would have to stream.  The K-cycle fused kernel keeps that state "
+                             "on chip, so the DRAM bytes it really moves (traffic, ncu) are far below B_alg, "
+                             "frac can exceed 1, and the kernel is bound by instruction issue / latency at the "
+                             "BASELINE instance count, not by HBM (profiles/README.md)"},
         "cpu_baseline": cpu,
     }))
     m.close()
