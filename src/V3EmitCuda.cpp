@@ -39,6 +39,7 @@
 #include "V3Stats.h"
 #include "V3String.h"
 
+#include <fstream>
 #include <map>
 #include <set>
 
@@ -293,6 +294,16 @@ class EmitCudaModel final : public EmitCFunc {
                 m_touchedRead += it->second.first ? elemBytes : 0;
                 m_touchedWrite += it->second.second ? elemBytes : 0;
             }
+        }
+        // Member table order: the primary ports first, in source order (= the order of
+        // vlcu_port_info() and of the stimulus / observation row words), then everything else
+        {
+            std::vector<CudaMember> ordered;
+            for (const CudaMember* const mp : portsInSourceOrder()) ordered.push_back(*mp);
+            for (const CudaMember& m : m_members) {
+                if (!(m.varp && m.kind <= 2 && !m.isArray)) ordered.push_back(m);
+            }
+            m_members.swap(ordered);
         }
         for (size_t i = 0; i < m_members.size(); ++i) {
             if (m_members[i].varp) m_memberOf[m_members[i].varp] = i;
@@ -885,12 +896,25 @@ class EmitCudaModel final : public EmitCFunc {
         puts("};\n");
 
         emitHostTables();
+        emitPortsInc();
         puts("\n// The device testbenches of this design (the user's C++ main loop, on the GPU)\n");
         puts("#ifdef VLCU_TESTBENCH_INCLUDE\n#include VLCU_TESTBENCH_INCLUDE\n#endif\n");
         puts("#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB\n");
         puts("#define VLCU_TESTBENCHES\n#endif\n");
         puts("VLCU_REGISTER_DESIGN_X(" + m_designName + " VLCU_TESTBENCHES);\n");
         closeOutputFile();
+    }
+    // <prefix>__ports.inc: the primary ports in source order as X-macro calls, for generic host
+    // harnesses that drive the C++ model with the same stimulus / observation rows
+    void emitPortsInc() {
+        const string fileName = v3Global.opt.makeDir() + "/" + v3Global.opt.prefix() + "__ports.inc";
+        std::ofstream os{fileName};
+        os << "// Primary ports of " << v3Global.opt.prefix() << " in source order (printed by V3EmitCuda)\n";
+        os << "// VLCU_PORT_IN / VLCU_PORT_OUT (member name, width in bits, 32-bit row words)\n";
+        for (const CudaMember* const mp : portsInSourceOrder()) {
+            os << (mp->kind == 1 ? "VLCU_PORT_OUT(" : "VLCU_PORT_IN(") << mp->name << ", " << mp->width << ", "
+               << rowWords(*mp) << ")\n";
+        }
     }
     void emitHostTables() {
         // The user's top module: first component of the internal signals' hierarchical names

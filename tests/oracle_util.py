@@ -164,3 +164,30 @@ def wide_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_tim
     if not obs_evals:
         r.obs = None
     return r
+
+
+# ---- generic harness (oracle/models/generic): any design, "trace" testbench ------------------
+def generic_words(design):
+    """(input row words, output row words) of a design built with the generic harness."""
+    fn = getattr(ref(), f"vlref_{design}_run")
+    fn.restype = i32
+    fn.argtypes = [u64, u64, u64, i32, u64, vp, vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32), i32]
+    iw, ow = i32(0), i32(0)
+    fn(0, 0, 0, 0, 0, None, None, None, ctypes.byref(iw), ctypes.byref(ow), 1)
+    return iw.value, ow.value
+
+
+def generic_run(design, stim, inst_base=0, seed=1, rand_reset=2, threads=1):
+    """stim: uint32 [evals][in_words][n] (exactly n columns).  Returns (obs [evals][out_words][n],
+    sigs [n]) from the genuine Verilated model driven like the CUDA runtime's "trace" testbench."""
+    iw, ow = generic_words(design)
+    stim = np.ascontiguousarray(stim, dtype=np.uint32)
+    evals, words, n = stim.shape
+    assert words == iw, (words, iw)
+    obs = np.zeros((evals, ow, n), dtype=np.uint32)
+    sigs = np.zeros(n, dtype=np.uint64)
+    fn = getattr(ref(), f"vlref_{design}_run")
+    rc = fn(n, inst_base, seed, rand_reset, evals, stim.ctypes.data, obs.ctypes.data, sigs.ctypes.data,
+            None, None, threads)
+    assert rc == 0
+    return obs, sigs

@@ -49,6 +49,7 @@ STATUS_DTYPE = np.dtype([
     ("msg_count", "<u4"), ("pad_", "<u4")])
 MSG_DTYPE = np.dtype([("time", "<u8"), ("id", "<u4"), ("nargs", "<u4"), ("args", "<u8", 4)])
 
+DIR_IN, DIR_OUT, DIR_INOUT = 0, 1, 2
 RUNF_TB_BEGIN, RUNF_STOP_ON_FINISH, RUNF_STIM_DEVICE, RUNF_OBS_DEVICE, RUNF_STIM_BROADCAST = (
     1, 2, 4, 8, 16)
 ST_DIDINIT, ST_FINISH, ST_ERROR, ST_STOPPED, ST_FATAL, ST_MSGDROP = 1, 2, 4, 8, 16, 32

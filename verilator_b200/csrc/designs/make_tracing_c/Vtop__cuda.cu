@@ -17,7 +17,11 @@ struct Vtop___024root final {
     CData/*0:0*/ clk;
     CData/*0:0*/ reset_l;
     CData/*1:0*/ out_small;
+    QData/*39:0*/ out_quad;
+    VlWide<3>/*69:0*/ out_wide;
     CData/*1:0*/ in_small;
+    QData/*39:0*/ in_quad;
+    VlWide<3>/*69:0*/ in_wide;
     CData/*1:0*/ top__DOT____VlemCond_0;
     CData/*0:0*/ top__DOT____Vtogcov__clk;
     CData/*0:0*/ top__DOT____Vtogcov__reset_l;
@@ -33,8 +37,6 @@ struct Vtop___024root final {
     CData/*0:0*/ __Vtrigprevexpr___TOP__clk__1;
     CData/*0:0*/ __VactPhaseResult;
     CData/*0:0*/ __VnbaPhaseResult;
-    VlWide<3>/*69:0*/ out_wide;
-    VlWide<3>/*69:0*/ in_wide;
     VlWide<3>/*69:0*/ top__DOT____VlemCond_2;
     VlWide<3>/*69:0*/ top__DOT____Vtogcov__out_wide;
     VlWide<3>/*69:0*/ top__DOT____Vtogcov__in_wide;
@@ -43,8 +45,6 @@ struct Vtop___024root final {
     IData/*31:0*/ __Vsampled_TOP__top__DOT__sub__DOT__count_c;
     VlWide<3>/*69:0*/ __Vtrigprevexpr___TOP__in_wide__0;
     IData/*31:0*/ __VactIterCount;
-    QData/*39:0*/ out_quad;
-    QData/*39:0*/ in_quad;
     QData/*39:0*/ top__DOT____VlemCond_1;
     QData/*39:0*/ top__DOT____Vtogcov__out_quad;
     QData/*39:0*/ top__DOT____Vtogcov__in_quad;
@@ -64,7 +64,11 @@ struct Vtop__cuda final {
         OFF_clk = 2348,
         OFF_reset_l = 2349,
         OFF_out_small = 2350,
+        OFF_out_quad = 0,
+        OFF_out_wide = 88,
         OFF_in_small = 2351,
+        OFF_in_quad = 8,
+        OFF_in_wide = 100,
         OFF_top__DOT____VlemCond_0 = 2352,
         OFF_top__DOT____Vtogcov__clk = 2353,
         OFF_top__DOT____Vtogcov__reset_l = 2354,
@@ -80,8 +84,6 @@ struct Vtop__cuda final {
         OFF___Vtrigprevexpr___TOP__clk__1 = 2364,
         OFF___VactPhaseResult = 2365,
         OFF___VnbaPhaseResult = 2366,
-        OFF_out_wide = 88,
-        OFF_in_wide = 100,
         OFF_top__DOT____VlemCond_2 = 112,
         OFF_top__DOT____Vtogcov__out_wide = 124,
         OFF_top__DOT____Vtogcov__in_wide = 136,
@@ -90,8 +92,6 @@ struct Vtop__cuda final {
         OFF___Vsampled_TOP__top__DOT__sub__DOT__count_c = 156,
         OFF___Vtrigprevexpr___TOP__in_wide__0 = 160,
         OFF___VactIterCount = 172,
-        OFF_out_quad = 0,
-        OFF_in_quad = 8,
         OFF_top__DOT____VlemCond_1 = 16,
         OFF_top__DOT____Vtogcov__out_quad = 24,
         OFF_top__DOT____Vtogcov__in_quad = 32,
@@ -119,7 +119,11 @@ struct Vtop__cuda final {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
         s.reset_l = st.ld<VlcuMem8>(OFF_reset_l, i);
         s.out_small = st.ld<VlcuMem8>(OFF_out_small, i);
+        s.out_quad = st.ld<QData>(OFF_out_quad, i);
+        st.ldW(OFF_out_wide, i, s.out_wide);
         s.in_small = st.ld<VlcuMem8>(OFF_in_small, i);
+        s.in_quad = st.ld<QData>(OFF_in_quad, i);
+        st.ldW(OFF_in_wide, i, s.in_wide);
         s.top__DOT____VlemCond_0 = st.ld<VlcuMem8>(OFF_top__DOT____VlemCond_0, i);
         s.top__DOT____Vtogcov__clk = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__clk, i);
         s.top__DOT____Vtogcov__reset_l = st.ld<VlcuMem8>(OFF_top__DOT____Vtogcov__reset_l, i);
@@ -135,8 +139,6 @@ struct Vtop__cuda final {
         s.__Vtrigprevexpr___TOP__clk__1 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i);
         s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
         s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
-        st.ldW(OFF_out_wide, i, s.out_wide);
-        st.ldW(OFF_in_wide, i, s.in_wide);
         st.ldW(OFF_top__DOT____VlemCond_2, i, s.top__DOT____VlemCond_2);
         st.ldW(OFF_top__DOT____Vtogcov__out_wide, i, s.top__DOT____Vtogcov__out_wide);
         st.ldW(OFF_top__DOT____Vtogcov__in_wide, i, s.top__DOT____Vtogcov__in_wide);
@@ -145,8 +147,6 @@ struct Vtop__cuda final {
         s.__Vsampled_TOP__top__DOT__sub__DOT__count_c = st.ld<IData>(OFF___Vsampled_TOP__top__DOT__sub__DOT__count_c, i);
         st.ldW(OFF___Vtrigprevexpr___TOP__in_wide__0, i, s.__Vtrigprevexpr___TOP__in_wide__0);
         s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
-        s.out_quad = st.ld<QData>(OFF_out_quad, i);
-        s.in_quad = st.ld<QData>(OFF_in_quad, i);
         s.top__DOT____VlemCond_1 = st.ld<QData>(OFF_top__DOT____VlemCond_1, i);
         s.top__DOT____Vtogcov__out_quad = st.ld<QData>(OFF_top__DOT____Vtogcov__out_quad, i);
         s.top__DOT____Vtogcov__in_quad = st.ld<QData>(OFF_top__DOT____Vtogcov__in_quad, i);
@@ -161,7 +161,11 @@ struct Vtop__cuda final {
         st.st<VlcuMem8>(OFF_clk, i, s.clk);
         st.st<VlcuMem8>(OFF_reset_l, i, s.reset_l);
         st.st<VlcuMem8>(OFF_out_small, i, s.out_small);
+        st.st<QData>(OFF_out_quad, i, s.out_quad);
+        st.stW(OFF_out_wide, i, s.out_wide);
         st.st<VlcuMem8>(OFF_in_small, i, s.in_small);
+        st.st<QData>(OFF_in_quad, i, s.in_quad);
+        st.stW(OFF_in_wide, i, s.in_wide);
         st.st<VlcuMem8>(OFF_top__DOT____VlemCond_0, i, s.top__DOT____VlemCond_0);
         st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__clk, i, s.top__DOT____Vtogcov__clk);
         st.st<VlcuMem8>(OFF_top__DOT____Vtogcov__reset_l, i, s.top__DOT____Vtogcov__reset_l);
@@ -177,8 +181,6 @@ struct Vtop__cuda final {
         st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i, s.__Vtrigprevexpr___TOP__clk__1);
         st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
         st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
-        st.stW(OFF_out_wide, i, s.out_wide);
-        st.stW(OFF_in_wide, i, s.in_wide);
         st.stW(OFF_top__DOT____VlemCond_2, i, s.top__DOT____VlemCond_2);
         st.stW(OFF_top__DOT____Vtogcov__out_wide, i, s.top__DOT____Vtogcov__out_wide);
         st.stW(OFF_top__DOT____Vtogcov__in_wide, i, s.top__DOT____Vtogcov__in_wide);
@@ -187,8 +189,6 @@ struct Vtop__cuda final {
         st.st<IData>(OFF___Vsampled_TOP__top__DOT__sub__DOT__count_c, i, s.__Vsampled_TOP__top__DOT__sub__DOT__count_c);
         st.stW(OFF___Vtrigprevexpr___TOP__in_wide__0, i, s.__Vtrigprevexpr___TOP__in_wide__0);
         st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
-        st.st<QData>(OFF_out_quad, i, s.out_quad);
-        st.st<QData>(OFF_in_quad, i, s.in_quad);
         st.st<QData>(OFF_top__DOT____VlemCond_1, i, s.top__DOT____VlemCond_1);
         st.st<QData>(OFF_top__DOT____Vtogcov__out_quad, i, s.top__DOT____Vtogcov__out_quad);
         st.st<QData>(OFF_top__DOT____Vtogcov__in_quad, i, s.top__DOT____Vtogcov__in_quad);
@@ -1018,7 +1018,11 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"reset_l", "reset_l", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_reset_l},
         {"out_small", "out_small", VLCU_MEMBER_OUT, 1, 0, 1, 2, 1, 0, T::OFF_out_small},
+        {"out_quad", "out_quad", VLCU_MEMBER_OUT, 8, 0, 1, 40, 39, 0, T::OFF_out_quad},
+        {"out_wide", "out_wide", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_wide},
         {"in_small", "in_small", VLCU_MEMBER_IN, 1, 0, 1, 2, 1, 0, T::OFF_in_small},
+        {"in_quad", "in_quad", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_in_quad},
+        {"in_wide", "in_wide", VLCU_MEMBER_IN, 4, 0, 3, 70, 69, 0, T::OFF_in_wide},
         {"top__DOT____VlemCond_0", "top.__VlemCond_0", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF_top__DOT____VlemCond_0},
         {"top__DOT____Vtogcov__clk", "top.__Vtogcov__clk", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_top__DOT____Vtogcov__clk},
         {"top__DOT____Vtogcov__reset_l", "top.__Vtogcov__reset_l", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_top__DOT____Vtogcov__reset_l},
@@ -1034,8 +1038,6 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         {"__Vtrigprevexpr___TOP__clk__1", "__Vtrigprevexpr___TOP__clk__1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__1},
         {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
         {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
-        {"out_wide", "out_wide", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_wide},
-        {"in_wide", "in_wide", VLCU_MEMBER_IN, 4, 0, 3, 70, 69, 0, T::OFF_in_wide},
         {"top__DOT____VlemCond_2", "top.__VlemCond_2", VLCU_MEMBER_STATE, 4, 0, 3, 70, 69, 0, T::OFF_top__DOT____VlemCond_2},
         {"top__DOT____Vtogcov__out_wide", "top.__Vtogcov__out_wide", VLCU_MEMBER_STATE, 4, 0, 3, 70, 69, 0, T::OFF_top__DOT____Vtogcov__out_wide},
         {"top__DOT____Vtogcov__in_wide", "top.__Vtogcov__in_wide", VLCU_MEMBER_STATE, 4, 0, 3, 70, 69, 0, T::OFF_top__DOT____Vtogcov__in_wide},
@@ -1044,8 +1046,6 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         {"__Vsampled_TOP__top__DOT__sub__DOT__count_c", "__Vsampled_TOP__top.sub.count_c", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___Vsampled_TOP__top__DOT__sub__DOT__count_c},
         {"__Vtrigprevexpr___TOP__in_wide__0", "__Vtrigprevexpr___TOP__in_wide__0", VLCU_MEMBER_STATE, 4, 0, 3, 70, 69, 0, T::OFF___Vtrigprevexpr___TOP__in_wide__0},
         {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
-        {"out_quad", "out_quad", VLCU_MEMBER_OUT, 8, 0, 1, 40, 39, 0, T::OFF_out_quad},
-        {"in_quad", "in_quad", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_in_quad},
         {"top__DOT____VlemCond_1", "top.__VlemCond_1", VLCU_MEMBER_STATE, 8, 0, 1, 40, 39, 0, T::OFF_top__DOT____VlemCond_1},
         {"top__DOT____Vtogcov__out_quad", "top.__Vtogcov__out_quad", VLCU_MEMBER_STATE, 8, 0, 1, 40, 39, 0, T::OFF_top__DOT____Vtogcov__out_quad},
         {"top__DOT____Vtogcov__in_quad", "top.__Vtogcov__in_quad", VLCU_MEMBER_STATE, 8, 0, 1, 40, 39, 0, T::OFF_top__DOT____Vtogcov__in_quad},

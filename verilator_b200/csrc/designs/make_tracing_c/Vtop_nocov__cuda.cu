@@ -17,7 +17,11 @@ struct Vtop_nocov___024root final {
     CData/*0:0*/ clk;
     CData/*0:0*/ reset_l;
     CData/*1:0*/ out_small;
+    QData/*39:0*/ out_quad;
+    VlWide<3>/*69:0*/ out_wide;
     CData/*1:0*/ in_small;
+    QData/*39:0*/ in_quad;
+    VlWide<3>/*69:0*/ in_wide;
     CData/*0:0*/ __VstlFirstIteration;
     CData/*0:0*/ __VstlPhaseResult;
     CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
@@ -28,13 +32,9 @@ struct Vtop_nocov___024root final {
     CData/*0:0*/ __Vtrigprevexpr___TOP__clk__1;
     CData/*0:0*/ __VactPhaseResult;
     CData/*0:0*/ __VnbaPhaseResult;
-    VlWide<3>/*69:0*/ out_wide;
-    VlWide<3>/*69:0*/ in_wide;
     IData/*31:0*/ top__DOT__sub__DOT__count_c;
     VlWide<3>/*69:0*/ __Vtrigprevexpr___TOP__in_wide__0;
     IData/*31:0*/ __VactIterCount;
-    QData/*39:0*/ out_quad;
-    QData/*39:0*/ in_quad;
     QData/*39:0*/ __Vtrigprevexpr___TOP__in_quad__0;
     VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
     VlUnpacked<QData/*63:0*/, 2> __VicoTriggered;
@@ -50,7 +50,11 @@ struct Vtop_nocov__cuda final {
         OFF_clk = 108,
         OFF_reset_l = 109,
         OFF_out_small = 110,
+        OFF_out_quad = 0,
+        OFF_out_wide = 64,
         OFF_in_small = 111,
+        OFF_in_quad = 8,
+        OFF_in_wide = 76,
         OFF___VstlFirstIteration = 112,
         OFF___VstlPhaseResult = 113,
         OFF___Vtrigprevexpr___TOP__clk__0 = 114,
@@ -61,13 +65,9 @@ struct Vtop_nocov__cuda final {
         OFF___Vtrigprevexpr___TOP__clk__1 = 119,
         OFF___VactPhaseResult = 120,
         OFF___VnbaPhaseResult = 121,
-        OFF_out_wide = 64,
-        OFF_in_wide = 76,
         OFF_top__DOT__sub__DOT__count_c = 88,
         OFF___Vtrigprevexpr___TOP__in_wide__0 = 92,
         OFF___VactIterCount = 104,
-        OFF_out_quad = 0,
-        OFF_in_quad = 8,
         OFF___Vtrigprevexpr___TOP__in_quad__0 = 16,
         OFF___VstlTriggered = 24,
         OFF___VicoTriggered = 32,
@@ -89,7 +89,11 @@ struct Vtop_nocov__cuda final {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
         s.reset_l = st.ld<VlcuMem8>(OFF_reset_l, i);
         s.out_small = st.ld<VlcuMem8>(OFF_out_small, i);
+        s.out_quad = st.ld<QData>(OFF_out_quad, i);
+        st.ldW(OFF_out_wide, i, s.out_wide);
         s.in_small = st.ld<VlcuMem8>(OFF_in_small, i);
+        s.in_quad = st.ld<QData>(OFF_in_quad, i);
+        st.ldW(OFF_in_wide, i, s.in_wide);
         s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
         s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
         s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
@@ -100,13 +104,9 @@ struct Vtop_nocov__cuda final {
         s.__Vtrigprevexpr___TOP__clk__1 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i);
         s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
         s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
-        st.ldW(OFF_out_wide, i, s.out_wide);
-        st.ldW(OFF_in_wide, i, s.in_wide);
         s.top__DOT__sub__DOT__count_c = st.ld<IData>(OFF_top__DOT__sub__DOT__count_c, i);
         st.ldW(OFF___Vtrigprevexpr___TOP__in_wide__0, i, s.__Vtrigprevexpr___TOP__in_wide__0);
         s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
-        s.out_quad = st.ld<QData>(OFF_out_quad, i);
-        s.in_quad = st.ld<QData>(OFF_in_quad, i);
         s.__Vtrigprevexpr___TOP__in_quad__0 = st.ld<QData>(OFF___Vtrigprevexpr___TOP__in_quad__0, i);
         for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
         for (uint32_t e = 0; e < 2; ++e) s.__VicoTriggered[e] = st.ldE<QData>(OFF___VicoTriggered, e, i);
@@ -117,7 +117,11 @@ struct Vtop_nocov__cuda final {
         st.st<VlcuMem8>(OFF_clk, i, s.clk);
         st.st<VlcuMem8>(OFF_reset_l, i, s.reset_l);
         st.st<VlcuMem8>(OFF_out_small, i, s.out_small);
+        st.st<QData>(OFF_out_quad, i, s.out_quad);
+        st.stW(OFF_out_wide, i, s.out_wide);
         st.st<VlcuMem8>(OFF_in_small, i, s.in_small);
+        st.st<QData>(OFF_in_quad, i, s.in_quad);
+        st.stW(OFF_in_wide, i, s.in_wide);
         st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
         st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
         st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
@@ -128,13 +132,9 @@ struct Vtop_nocov__cuda final {
         st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__1, i, s.__Vtrigprevexpr___TOP__clk__1);
         st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
         st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
-        st.stW(OFF_out_wide, i, s.out_wide);
-        st.stW(OFF_in_wide, i, s.in_wide);
         st.st<IData>(OFF_top__DOT__sub__DOT__count_c, i, s.top__DOT__sub__DOT__count_c);
         st.stW(OFF___Vtrigprevexpr___TOP__in_wide__0, i, s.__Vtrigprevexpr___TOP__in_wide__0);
         st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
-        st.st<QData>(OFF_out_quad, i, s.out_quad);
-        st.st<QData>(OFF_in_quad, i, s.in_quad);
         st.st<QData>(OFF___Vtrigprevexpr___TOP__in_quad__0, i, s.__Vtrigprevexpr___TOP__in_quad__0);
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
         for (uint32_t e = 0; e < 2; ++e) st.stE<QData>(OFF___VicoTriggered, e, i, s.__VicoTriggered[e]);
@@ -678,7 +678,11 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"reset_l", "reset_l", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_reset_l},
         {"out_small", "out_small", VLCU_MEMBER_OUT, 1, 0, 1, 2, 1, 0, T::OFF_out_small},
+        {"out_quad", "out_quad", VLCU_MEMBER_OUT, 8, 0, 1, 40, 39, 0, T::OFF_out_quad},
+        {"out_wide", "out_wide", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_wide},
         {"in_small", "in_small", VLCU_MEMBER_IN, 1, 0, 1, 2, 1, 0, T::OFF_in_small},
+        {"in_quad", "in_quad", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_in_quad},
+        {"in_wide", "in_wide", VLCU_MEMBER_IN, 4, 0, 3, 70, 69, 0, T::OFF_in_wide},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
         {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -689,13 +693,9 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
         {"__Vtrigprevexpr___TOP__clk__1", "__Vtrigprevexpr___TOP__clk__1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__1},
         {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
         {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
-        {"out_wide", "out_wide", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_wide},
-        {"in_wide", "in_wide", VLCU_MEMBER_IN, 4, 0, 3, 70, 69, 0, T::OFF_in_wide},
         {"top__DOT__sub__DOT__count_c", "top.sub.count_c", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_top__DOT__sub__DOT__count_c},
         {"__Vtrigprevexpr___TOP__in_wide__0", "__Vtrigprevexpr___TOP__in_wide__0", VLCU_MEMBER_STATE, 4, 0, 3, 70, 69, 0, T::OFF___Vtrigprevexpr___TOP__in_wide__0},
         {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
-        {"out_quad", "out_quad", VLCU_MEMBER_OUT, 8, 0, 1, 40, 39, 0, T::OFF_out_quad},
-        {"in_quad", "in_quad", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_in_quad},
         {"__Vtrigprevexpr___TOP__in_quad__0", "__Vtrigprevexpr___TOP__in_quad__0", VLCU_MEMBER_STATE, 8, 0, 1, 40, 39, 0, T::OFF___Vtrigprevexpr___TOP__in_quad__0},
         {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
         {"__VicoTriggered", "__VicoTriggered", VLCU_MEMBER_STATE, 8, 0, 2, 64, 63, 0, T::OFF___VicoTriggered},

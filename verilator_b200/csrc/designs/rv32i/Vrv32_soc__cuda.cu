@@ -19,7 +19,11 @@ struct Vrv32_soc___024root final {
     CData/*0:0*/ trap;
     CData/*0:0*/ mem_valid;
     CData/*0:0*/ mem_instr;
+    IData/*31:0*/ mem_addr;
+    IData/*31:0*/ mem_wdata;
     CData/*3:0*/ mem_wstrb;
+    IData/*31:0*/ mem_rdata;
+    IData/*31:0*/ retired;
     CData/*1:0*/ rv32_soc__DOT__state;
     CData/*0:0*/ rv32_soc__DOT__is_jalr;
     CData/*0:0*/ rv32_soc__DOT__is_branch;
@@ -38,10 +42,6 @@ struct Vrv32_soc___024root final {
     CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
     CData/*0:0*/ __VactPhaseResult;
     CData/*0:0*/ __VnbaPhaseResult;
-    IData/*31:0*/ mem_addr;
-    IData/*31:0*/ mem_wdata;
-    IData/*31:0*/ mem_rdata;
-    IData/*31:0*/ retired;
     IData/*31:0*/ rv32_soc__DOT__pc;
     IData/*31:0*/ rv32_soc__DOT__insn;
     IData/*31:0*/ rv32_soc__DOT__ld_addr;
@@ -77,7 +77,11 @@ struct Vrv32_soc__cuda final {
         OFF_trap = 4334,
         OFF_mem_valid = 4335,
         OFF_mem_instr = 4336,
+        OFF_mem_addr = 24,
+        OFF_mem_wdata = 28,
         OFF_mem_wstrb = 4337,
+        OFF_mem_rdata = 32,
+        OFF_retired = 36,
         OFF_rv32_soc__DOT__state = 4338,
         OFF_rv32_soc__DOT__is_jalr = 4339,
         OFF_rv32_soc__DOT__is_branch = 4340,
@@ -96,10 +100,6 @@ struct Vrv32_soc__cuda final {
         OFF___Vtrigprevexpr___TOP__clk__0 = 4353,
         OFF___VactPhaseResult = 4354,
         OFF___VnbaPhaseResult = 4355,
-        OFF_mem_addr = 24,
-        OFF_mem_wdata = 28,
-        OFF_mem_rdata = 32,
-        OFF_retired = 36,
         OFF_rv32_soc__DOT__pc = 40,
         OFF_rv32_soc__DOT__insn = 44,
         OFF_rv32_soc__DOT__ld_addr = 48,
@@ -144,7 +144,11 @@ struct Vrv32_soc__cuda final {
         s.trap = st.ld<VlcuMem8>(OFF_trap, i);
         s.mem_valid = st.ld<VlcuMem8>(OFF_mem_valid, i);
         s.mem_instr = st.ld<VlcuMem8>(OFF_mem_instr, i);
+        s.mem_addr = st.ld<IData>(OFF_mem_addr, i);
+        s.mem_wdata = st.ld<IData>(OFF_mem_wdata, i);
         s.mem_wstrb = st.ld<VlcuMem8>(OFF_mem_wstrb, i);
+        s.mem_rdata = st.ld<IData>(OFF_mem_rdata, i);
+        s.retired = st.ld<IData>(OFF_retired, i);
         s.rv32_soc__DOT__state = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__state, i);
         s.rv32_soc__DOT__is_jalr = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_jalr, i);
         s.rv32_soc__DOT__is_branch = st.ld<VlcuMem8>(OFF_rv32_soc__DOT__is_branch, i);
@@ -163,10 +167,6 @@ struct Vrv32_soc__cuda final {
         s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
         s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
         s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
-        s.mem_addr = st.ld<IData>(OFF_mem_addr, i);
-        s.mem_wdata = st.ld<IData>(OFF_mem_wdata, i);
-        s.mem_rdata = st.ld<IData>(OFF_mem_rdata, i);
-        s.retired = st.ld<IData>(OFF_retired, i);
         s.rv32_soc__DOT__pc = st.ld<IData>(OFF_rv32_soc__DOT__pc, i);
         s.rv32_soc__DOT__insn = st.ld<IData>(OFF_rv32_soc__DOT__insn, i);
         s.rv32_soc__DOT__ld_addr = st.ld<IData>(OFF_rv32_soc__DOT__ld_addr, i);
@@ -196,7 +196,11 @@ struct Vrv32_soc__cuda final {
         st.st<VlcuMem8>(OFF_trap, i, s.trap);
         st.st<VlcuMem8>(OFF_mem_valid, i, s.mem_valid);
         st.st<VlcuMem8>(OFF_mem_instr, i, s.mem_instr);
+        st.st<IData>(OFF_mem_addr, i, s.mem_addr);
+        st.st<IData>(OFF_mem_wdata, i, s.mem_wdata);
         st.st<VlcuMem8>(OFF_mem_wstrb, i, s.mem_wstrb);
+        st.st<IData>(OFF_mem_rdata, i, s.mem_rdata);
+        st.st<IData>(OFF_retired, i, s.retired);
         st.st<VlcuMem8>(OFF_rv32_soc__DOT__state, i, s.rv32_soc__DOT__state);
         st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_jalr, i, s.rv32_soc__DOT__is_jalr);
         st.st<VlcuMem8>(OFF_rv32_soc__DOT__is_branch, i, s.rv32_soc__DOT__is_branch);
@@ -215,10 +219,6 @@ struct Vrv32_soc__cuda final {
         st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
         st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
         st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
-        st.st<IData>(OFF_mem_addr, i, s.mem_addr);
-        st.st<IData>(OFF_mem_wdata, i, s.mem_wdata);
-        st.st<IData>(OFF_mem_rdata, i, s.mem_rdata);
-        st.st<IData>(OFF_retired, i, s.retired);
         st.st<IData>(OFF_rv32_soc__DOT__pc, i, s.rv32_soc__DOT__pc);
         st.st<IData>(OFF_rv32_soc__DOT__insn, i, s.rv32_soc__DOT__insn);
         st.st<IData>(OFF_rv32_soc__DOT__ld_addr, i, s.rv32_soc__DOT__ld_addr);
@@ -2082,7 +2082,11 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         {"trap", "trap", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_trap},
         {"mem_valid", "mem_valid", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_mem_valid},
         {"mem_instr", "mem_instr", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_mem_instr},
+        {"mem_addr", "mem_addr", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_addr},
+        {"mem_wdata", "mem_wdata", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_wdata},
         {"mem_wstrb", "mem_wstrb", VLCU_MEMBER_OUT, 1, 0, 1, 4, 3, 0, T::OFF_mem_wstrb},
+        {"mem_rdata", "mem_rdata", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_rdata},
+        {"retired", "retired", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_retired},
         {"rv32_soc__DOT__state", "rv32_soc.state", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF_rv32_soc__DOT__state},
         {"rv32_soc__DOT__is_jalr", "rv32_soc.is_jalr", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_rv32_soc__DOT__is_jalr},
         {"rv32_soc__DOT__is_branch", "rv32_soc.is_branch", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_rv32_soc__DOT__is_branch},
@@ -2101,10 +2105,6 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
         {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
         {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
-        {"mem_addr", "mem_addr", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_addr},
-        {"mem_wdata", "mem_wdata", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_wdata},
-        {"mem_rdata", "mem_rdata", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_mem_rdata},
-        {"retired", "retired", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_retired},
         {"rv32_soc__DOT__pc", "rv32_soc.pc", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_rv32_soc__DOT__pc},
         {"rv32_soc__DOT__insn", "rv32_soc.insn", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_rv32_soc__DOT__insn},
         {"rv32_soc__DOT__ld_addr", "rv32_soc.ld_addr", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_rv32_soc__DOT__ld_addr},

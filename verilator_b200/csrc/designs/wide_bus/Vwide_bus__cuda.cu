@@ -29,9 +29,14 @@ struct Vwide_bus___024root final {
     CData/*0:0*/ in_valid;
     CData/*2:0*/ in_op;
     CData/*7:0*/ in_shift;
+    VlWide<8>/*255:0*/ in_data;
     CData/*0:0*/ out_valid;
     CData/*0:0*/ out_lt;
     CData/*0:0*/ out_lts;
+    SData/*8:0*/ out_ones;
+    VlWide<3>/*69:0*/ out_slice;
+    VlWide<4>/*127:0*/ out_hash;
+    VlWide<8>/*255:0*/ out_data;
     CData/*7:0*/ wide_bus__DOT__sh;
     CData/*2:0*/ wide_bus__DOT__op;
     CData/*0:0*/ wide_bus__DOT__vld;
@@ -40,11 +45,6 @@ struct Vwide_bus___024root final {
     CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
     CData/*0:0*/ __VactPhaseResult;
     CData/*0:0*/ __VnbaPhaseResult;
-    SData/*8:0*/ out_ones;
-    VlWide<8>/*255:0*/ in_data;
-    VlWide<3>/*69:0*/ out_slice;
-    VlWide<4>/*127:0*/ out_hash;
-    VlWide<8>/*255:0*/ out_data;
     VlWide<8>/*255:0*/ wide_bus__DOT__acc;
     VlWide<8>/*255:0*/ wide_bus__DOT__stage;
     VlWide<4>/*127:0*/ wide_bus__DOT__hash;
@@ -68,9 +68,14 @@ struct Vwide_bus__cuda final {
         OFF_in_valid = 284,
         OFF_in_op = 285,
         OFF_in_shift = 286,
+        OFF_in_data = 24,
         OFF_out_valid = 287,
         OFF_out_lt = 288,
         OFF_out_lts = 289,
+        OFF_out_ones = 280,
+        OFF_out_slice = 56,
+        OFF_out_hash = 68,
+        OFF_out_data = 84,
         OFF_wide_bus__DOT__sh = 290,
         OFF_wide_bus__DOT__op = 291,
         OFF_wide_bus__DOT__vld = 292,
@@ -79,11 +84,6 @@ struct Vwide_bus__cuda final {
         OFF___Vtrigprevexpr___TOP__clk__0 = 295,
         OFF___VactPhaseResult = 296,
         OFF___VnbaPhaseResult = 297,
-        OFF_out_ones = 280,
-        OFF_in_data = 24,
-        OFF_out_slice = 56,
-        OFF_out_hash = 68,
-        OFF_out_data = 84,
         OFF_wide_bus__DOT__acc = 116,
         OFF_wide_bus__DOT__stage = 148,
         OFF_wide_bus__DOT__hash = 180,
@@ -113,9 +113,14 @@ struct Vwide_bus__cuda final {
         s.in_valid = st.ld<VlcuMem8>(OFF_in_valid, i);
         s.in_op = st.ld<VlcuMem8>(OFF_in_op, i);
         s.in_shift = st.ld<VlcuMem8>(OFF_in_shift, i);
+        st.ldW(OFF_in_data, i, s.in_data);
         s.out_valid = st.ld<VlcuMem8>(OFF_out_valid, i);
         s.out_lt = st.ld<VlcuMem8>(OFF_out_lt, i);
         s.out_lts = st.ld<VlcuMem8>(OFF_out_lts, i);
+        s.out_ones = st.ld<VlcuMem16>(OFF_out_ones, i);
+        st.ldW(OFF_out_slice, i, s.out_slice);
+        st.ldW(OFF_out_hash, i, s.out_hash);
+        st.ldW(OFF_out_data, i, s.out_data);
         s.wide_bus__DOT__sh = st.ld<VlcuMem8>(OFF_wide_bus__DOT__sh, i);
         s.wide_bus__DOT__op = st.ld<VlcuMem8>(OFF_wide_bus__DOT__op, i);
         s.wide_bus__DOT__vld = st.ld<VlcuMem8>(OFF_wide_bus__DOT__vld, i);
@@ -124,11 +129,6 @@ struct Vwide_bus__cuda final {
         s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
         s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
         s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
-        s.out_ones = st.ld<VlcuMem16>(OFF_out_ones, i);
-        st.ldW(OFF_in_data, i, s.in_data);
-        st.ldW(OFF_out_slice, i, s.out_slice);
-        st.ldW(OFF_out_hash, i, s.out_hash);
-        st.ldW(OFF_out_data, i, s.out_data);
         st.ldW(OFF_wide_bus__DOT__acc, i, s.wide_bus__DOT__acc);
         st.ldW(OFF_wide_bus__DOT__stage, i, s.wide_bus__DOT__stage);
         st.ldW(OFF_wide_bus__DOT__hash, i, s.wide_bus__DOT__hash);
@@ -147,9 +147,14 @@ struct Vwide_bus__cuda final {
         st.st<VlcuMem8>(OFF_in_valid, i, s.in_valid);
         st.st<VlcuMem8>(OFF_in_op, i, s.in_op);
         st.st<VlcuMem8>(OFF_in_shift, i, s.in_shift);
+        st.stW(OFF_in_data, i, s.in_data);
         st.st<VlcuMem8>(OFF_out_valid, i, s.out_valid);
         st.st<VlcuMem8>(OFF_out_lt, i, s.out_lt);
         st.st<VlcuMem8>(OFF_out_lts, i, s.out_lts);
+        st.st<VlcuMem16>(OFF_out_ones, i, s.out_ones);
+        st.stW(OFF_out_slice, i, s.out_slice);
+        st.stW(OFF_out_hash, i, s.out_hash);
+        st.stW(OFF_out_data, i, s.out_data);
         st.st<VlcuMem8>(OFF_wide_bus__DOT__sh, i, s.wide_bus__DOT__sh);
         st.st<VlcuMem8>(OFF_wide_bus__DOT__op, i, s.wide_bus__DOT__op);
         st.st<VlcuMem8>(OFF_wide_bus__DOT__vld, i, s.wide_bus__DOT__vld);
@@ -158,11 +163,6 @@ struct Vwide_bus__cuda final {
         st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
         st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
         st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
-        st.st<VlcuMem16>(OFF_out_ones, i, s.out_ones);
-        st.stW(OFF_in_data, i, s.in_data);
-        st.stW(OFF_out_slice, i, s.out_slice);
-        st.stW(OFF_out_hash, i, s.out_hash);
-        st.stW(OFF_out_data, i, s.out_data);
         st.stW(OFF_wide_bus__DOT__acc, i, s.wide_bus__DOT__acc);
         st.stW(OFF_wide_bus__DOT__stage, i, s.wide_bus__DOT__stage);
         st.stW(OFF_wide_bus__DOT__hash, i, s.wide_bus__DOT__hash);
@@ -1041,9 +1041,14 @@ const VlcuDesignInfo& Vwide_bus__cuda::info() {
         {"in_valid", "in_valid", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_in_valid},
         {"in_op", "in_op", VLCU_MEMBER_IN, 1, 0, 1, 3, 2, 0, T::OFF_in_op},
         {"in_shift", "in_shift", VLCU_MEMBER_IN, 1, 0, 1, 8, 7, 0, T::OFF_in_shift},
+        {"in_data", "in_data", VLCU_MEMBER_IN, 4, 0, 8, 256, 255, 0, T::OFF_in_data},
         {"out_valid", "out_valid", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_out_valid},
         {"out_lt", "out_lt", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_out_lt},
         {"out_lts", "out_lts", VLCU_MEMBER_OUT, 1, 0, 1, 1, 0, 0, T::OFF_out_lts},
+        {"out_ones", "out_ones", VLCU_MEMBER_OUT, 2, 0, 1, 9, 8, 0, T::OFF_out_ones},
+        {"out_slice", "out_slice", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_slice},
+        {"out_hash", "out_hash", VLCU_MEMBER_OUT, 4, 0, 4, 128, 127, 0, T::OFF_out_hash},
+        {"out_data", "out_data", VLCU_MEMBER_OUT, 4, 0, 8, 256, 255, 0, T::OFF_out_data},
         {"wide_bus__DOT__sh", "wide_bus.sh", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_wide_bus__DOT__sh},
         {"wide_bus__DOT__op", "wide_bus.op", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_wide_bus__DOT__op},
         {"wide_bus__DOT__vld", "wide_bus.vld", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_wide_bus__DOT__vld},
@@ -1052,11 +1057,6 @@ const VlcuDesignInfo& Vwide_bus__cuda::info() {
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
         {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
         {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
-        {"out_ones", "out_ones", VLCU_MEMBER_OUT, 2, 0, 1, 9, 8, 0, T::OFF_out_ones},
-        {"in_data", "in_data", VLCU_MEMBER_IN, 4, 0, 8, 256, 255, 0, T::OFF_in_data},
-        {"out_slice", "out_slice", VLCU_MEMBER_OUT, 4, 0, 3, 70, 69, 0, T::OFF_out_slice},
-        {"out_hash", "out_hash", VLCU_MEMBER_OUT, 4, 0, 4, 128, 127, 0, T::OFF_out_hash},
-        {"out_data", "out_data", VLCU_MEMBER_OUT, 4, 0, 8, 256, 255, 0, T::OFF_out_data},
         {"wide_bus__DOT__acc", "wide_bus.acc", VLCU_MEMBER_STATE, 4, 0, 8, 256, 255, 0, T::OFF_wide_bus__DOT__acc},
         {"wide_bus__DOT__stage", "wide_bus.stage", VLCU_MEMBER_STATE, 4, 0, 8, 256, 255, 0, T::OFF_wide_bus__DOT__stage},
         {"wide_bus__DOT__hash", "wide_bus.hash", VLCU_MEMBER_STATE, 4, 0, 4, 128, 127, 0, T::OFF_wide_bus__DOT__hash},
