@@ -50,11 +50,20 @@ WORKLOADS = {
     # BASELINE.json configs[4] in miniature: a --coverage campaign (line + toggle + user cover
     # points) whose per-instance counters are reduced on the device and summed across GPUs by
     # NCCL; VeeR-EH1 is not vendored, the only --coverage design available is make_tracing_c
-    "cov_campaign": dict(
+    "cov_campaign_mtc": dict(
         design="make_tracing_c_cov", tb="sim_main", instances=65536, cycles=2048, tb_flags=1,
         tb_arg=(128, 0, 0, 0), rand_reset=2, inputs=("in_small", "in_quad", "in_wide"), coverage=True,
         note="examples/make_tracing_c built --coverage (543 bins/instance), per-instance random "
              "stimulus offsets, reset every 128 time units; e2e adds the on-device coverage "
+             "reduction + ncclAllReduce + coverage.dat write per step"),
+    # the same campaign on the RV32I core (VeeR-EH1 is not vendored): --coverage build, 1,664
+    # counters per instance, 16,384 instances per GPU as configs[2]/[4] say, fresh random program +
+    # reset every step (device generated), counters summed on the device and across GPUs by NCCL
+    "cov_campaign": dict(
+        design="rv32i_cov", tb="rv32_rand", instances=16384, cycles=1024, tb_flags=1,
+        tb_arg=(16, 0, 0, 0), rand_reset=2, inputs=(), coverage=True, fresh_program_per_step=True,
+        note="rv32_soc.v built --coverage (1,664 line/toggle/branch/expression counters per instance), "
+             "fuzz campaign: fresh random program + reset every step; e2e adds the on-device coverage "
              "reduction + ncclAllReduce + coverage.dat write per step"),
     # BASELINE.json configs[3] class: wide-bus, VlWide-heavy path, 4,096 instances (OpenTitan is
     # not vendored; wide_bus.v is this repo's 256-bit datapath block)
@@ -160,9 +169,10 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     excluded."""
     import ctypes as C
     import oracle_util as O
-    if wl["design"] == "rv32i":
+    if wl["design"] in ("rv32i", "rv32i_cov"):
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
-                   threads=threads)
+                   threads=threads, cov=wl["design"] == "rv32i_cov",
+                   rounds=1 if wl.get("fresh_program_per_step") else 0, reset_time=wl["tb_arg"][0])
     elif wl["design"] == "wide_bus":
         O.wide_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads)
@@ -232,8 +242,14 @@ def run_ours(args, wl):
         from verilator_b200 import shard
         shard.attach_coverage_comm(m, dist, local)  # NCCL communicator for the counter sum
 
+    step_no = [0]
+
     def step():
-        m.run(wl["tb"], evals, **run_kw)
+        if wl.get("fresh_program_per_step"):
+            step_no[0] += 1
+            m.run(wl["tb"], evals, flags=abi.RUNF_TB_BEGIN, **dict(run_kw, tb_seed=3 + step_no[0]))
+        else:
+            m.run(wl["tb"], evals, **run_kw)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -263,7 +279,7 @@ def run_ours(args, wl):
     # ---- end to end through the C ABI with host buffers -------------------------------
     ins = {}
     images = None
-    if wl["design"] == "rv32i":
+    if wl["design"] in ("rv32i", "rv32i_cov") and not wl.get("fresh_program_per_step"):
         # the per-step input of a fuzz step is a fresh program image per instance
         images, _ptr = pinned_array(abi, (n, 1024), np.uint32)
         images[:] = m.get_member("rv32_soc__DOT__mem")
@@ -293,7 +309,10 @@ def run_ours(args, wl):
         if images is not None:
             mi = m.members["rv32_soc__DOT__mem"][0]
             abi._check(abi.lib.vlcu_set_member(m.h, mi, images.ctypes.data, images.strides[0]))
-        m.run(e2e_tb, evals, flags=e2e_flags, **e2e_kw)
+        if wl.get("fresh_program_per_step"):
+            step()
+        else:
+            m.run(e2e_tb, evals, flags=e2e_flags, **e2e_kw)
         abi._check(abi.lib.vlcu_signatures(m.h, sig_host.ctypes.data))
         abi._check(abi.lib.vlcu_status(m.h, st_host.ctypes.data))
         if images is not None:

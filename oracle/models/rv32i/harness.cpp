@@ -5,8 +5,21 @@
 // oracle/_ref/verilator_lite, linked with the reference's runtime), one VerilatedContext +
 // Vrv32_soc per instance (docs/guide/verilating.rst:232-236), with the stimulus of the device
 // testbenches TbRv32Rand / TbRv32Host (verilator_b200/csrc/designs/rv32i/rv32_tb.h).
+// Compiled twice: as is for the plain model (vlref_rv32_run), and with
+//   -DRV32_COV=1 for the --coverage build Vrv32_cov (vlref_rv32cov_run), which also returns the
+//   per-bin sums of the instances' coverage counters and can write one instance's coverage.dat
+//   through the reference's own writer.
+#ifdef RV32_COV
+#include "Vrv32_cov.h"
+#include "Vrv32_cov___024root.h"
+#include "verilated_cov.h"
+#define Vrv32_soc Vrv32_cov
+#define Vrv32_soc___024root Vrv32_cov___024root
+#define vlref_rv32_run vlref_rv32cov_run
+#else
 #include "Vrv32_soc.h"
 #include "Vrv32_soc___024root.h"
+#endif
 #include "verilated_vcd_c.h"
 #include "ref_timing.h"
 
@@ -46,7 +59,14 @@ struct Rv32Params {
     uint32_t rounds;
     const char* vcdPath;  // waveform of instance vcdInstance through the reference's VerilatedVcdC
     int64_t vcdInstance;
+    uint64_t* covSums;  // (RV32_COV) [bins] summed over the instances, or null
+    const char* covPath;  // (RV32_COV) coverage.dat of instance covInstance
+    int64_t covInstance;
 };
+#ifdef RV32_COV
+constexpr int kCovBins = sizeof(Vrv32_soc___024root::__Vcoverage) / sizeof(uint32_t);
+std::atomic<uint64_t> g_cov[kCovBins];
+#endif
 
 void runOne(const Rv32Params& p, uint64_t i) {
     const std::unique_ptr<VerilatedContext> contextp{new VerilatedContext};
@@ -108,6 +128,12 @@ void runOne(const Rv32Params& p, uint64_t i) {
     }
     top->final();
     if (tfp) tfp->close();
+#ifdef RV32_COV
+    if (p.covSums) {
+        for (int b = 0; b < kCovBins; ++b) g_cov[b].fetch_add(top->rootp->__Vcoverage[b], std::memory_order_relaxed);
+    }
+    if (p.covPath && p.covInstance == static_cast<int64_t>(i)) contextp->coveragep()->write(p.covPath);
+#endif
     if (p.sigs) p.sigs[i] = sig;
     if (p.times) p.times[i] = contextp->time();
     const Vrv32_soc___024root& r = *top->rootp;
@@ -131,9 +157,14 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                               const uint32_t* memImages, uint32_t* obs, uint64_t obsEvals,
                               uint64_t* sigs, uint64_t* times, uint32_t* finalRegs,
                               uint32_t* finalMem, uint32_t* finalScalars, int threads,
-                              uint32_t rounds, const char* vcdPath, int64_t vcdInstance) {
+                              uint32_t rounds, const char* vcdPath, int64_t vcdInstance,
+                              uint64_t* covSums, const char* covPath, int64_t covInstance) {
+#ifdef RV32_COV
+    for (int b = 0; b < kCovBins; ++b) g_cov[b] = 0;
+#endif
     const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
-                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds, vcdPath, vcdInstance};
+                       obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds, vcdPath, vcdInstance,
+                       covSums, covPath, covInstance};
     vlref_loop_seconds_begin();
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);
@@ -153,12 +184,21 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
         }
         for (auto& th : pool) th.join();
     }
+#ifdef RV32_COV
+    if (covSums) {
+        for (int b = 0; b < kCovBins; ++b) covSums[b] = g_cov[b];
+    }
+#endif
     return 0;
 }
 
+#ifdef RV32_COV
+extern "C" int vlref_rv32cov_bins() { return kCovBins; }
+#else
 // The program generator alone (for the instruction-set-simulator cross check)
 extern "C" void vlref_rv32_gen_program(uint64_t seed, uint32_t* out1024) {
     VlUnpacked<IData, 1024> mem;
     rv32_gen_program(mem, seed);
     for (int k = 0; k < 1024; ++k) out1024[k] = mem[k];
 }
+#endif

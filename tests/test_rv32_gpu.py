@@ -57,6 +57,31 @@ def test_campaign_rounds_fresh_program_and_reset_per_run(abi):
         check_final_state(m, want)
 
 
+def test_coverage_fuzz_campaign_counters_and_file(abi, tmp_path):
+    """BASELINE.json config 5 in miniature: the --coverage build of the core (line, toggle,
+    branch and expression points: 1,664 counters per instance) run as a fuzz campaign -- fresh
+    random program and reset every round -- with the counters summed on the device.  The sums
+    must equal the sum over the genuine C++ model's instances, and one instance's coverage.dat
+    must be byte-identical to what the reference's VerilatedCov writes."""
+    n, evals, rounds = 120, 500, 3
+    want = O.rv32_run(n, evals, seed=5, rand_reset=2, tb_seed=40, reset_time=6, rounds=rounds, cov=True)
+    with abi.Model("rv32i_cov", n, seed=5, rand_reset=2) as m:
+        for k in range(rounds):
+            m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=40 + k, tb_flags=1, tb_arg=(6, 0, 0, 0))
+        sums = m.coverage_reduce()
+        assert m.coverage_bins() == len(want.cov) == 1664
+        assert (sums == want.cov).all()
+        assert (m.signatures() == want.sigs).all()
+        assert (sums > 0).sum() > 800  # the campaign really toggles most of the design
+    ref_path, gpu_path = str(tmp_path / "ref.dat"), str(tmp_path / "gpu.dat")
+    O.rv32_run(1, evals, seed=5, rand_reset=2, tb_seed=40, reset_time=6, rounds=1, cov=True,
+               cov_path=ref_path, cov_instance=0)
+    with abi.Model("rv32i_cov", 1, seed=5, rand_reset=2) as m:
+        m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=40, tb_flags=1, tb_arg=(6, 0, 0, 0))
+        m.coverage_write(m.coverage_reduce(), gpu_path)
+    assert open(gpu_path, "rb").read() == open(ref_path, "rb").read()
+
+
 def test_x_initial_reset_of_arrays_and_scalars(abi):
     want = O.rv32_run(300, 0, inst_base=77, seed=123, rand_reset=2, want_mem=True)
     with abi.Model("rv32i", 300, inst_base=77, seed=123, rand_reset=2) as m:
