@@ -96,31 +96,88 @@ VLCU_HD uint64_t VL_MURMUR64_HASH(const char* key) {
 }
 
 //=========================================================================
+// Coverage counters (uint32_t __Vcoverage[nBins] of the C++ model, V3EmitCHeaders.cpp:153-158).
+// They stay in HBM, in the SoA block as cov[bin][instance]: a warp bumping bin n for its 32
+// instances touches one 128-byte line, and the bump is a fire-and-forget reduction (RED.ADD, no
+// return value), so the eval code never waits for a counter.  Keeping them thread-local instead
+// makes every `++__Vcoverage[n]` a dependent load-add-store that misses L1 as soon as a design has
+// more than a few hundred points (1,664 for the RV32I core = 6.6 KB per thread).
+struct VlcuCovRef final {
+    uint32_t* m_p;
+    VLCU_HD void operator++() const {
+#ifdef __CUDA_ARCH__
+        atomicAdd(m_p, 1U);  // result unused: compiles to RED; the address is private to this thread
+#else
+        ++*m_p;
+#endif
+    }
+    VLCU_HD void operator=(uint32_t value) const { *m_p = value; }
+    VLCU_HD operator uint32_t() const { return *m_p; }
+};
+struct VlcuCovPtr {
+    uint32_t* m_basep;  // counter 0 of this instance
+    uint64_t m_stride;  // padded instance count (elements between consecutive bins)
+    VLCU_HD VlcuCovRef operator[](size_t bin) const { return VlcuCovRef{m_basep + bin * m_stride}; }
+    VLCU_HD VlcuCovPtr operator+(size_t bin) const { return VlcuCovPtr{m_basep + bin * m_stride, m_stride}; }
+};
+// (VlcuCovArray, the bindable member type, is defined with VlcuState below)
+
+VLCU_HD int vlcu_ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffs(static_cast<int>(x)) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+VLCU_HD int vlcu_ctz64(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffsll(static_cast<long long>(x)) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+//=========================================================================
 // Toggle coverage (verilated_cov.h:78-105): two counters per bit, index
 // 2*bit + new value, bumped when the bit changed.  Counters wrap (uint32).
 
-VLCU_HD void VL_COV_TOGGLE_CHG_ST_I(int width, uint32_t* covp, IData newData, IData oldData) {
-    const IData chg = newData ^ oldData;
-    for (int i = 0; i < width; ++i) covp[2 * i + ((newData >> i) & 1)] += (chg >> i) & 1;
+// The host loops over all `width` bits and adds 0 or 1; here only the bits that changed are
+// visited (same counters, same increments): a signal typically toggles a few bits per eval.
+template <class T_CovP>
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_I(int width, T_CovP covp, IData newData, IData oldData) {
+    IData chg = newData ^ oldData;
+    if (width < 32) chg &= (1U << width) - 1U;
+    while (chg) {
+        const int i = vlcu_ctz32(chg);
+        chg &= chg - 1U;
+        ++covp[2 * i + ((newData >> i) & 1U)];
+    }
 }
-VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, uint32_t* covp, QData newData, QData oldData) {
-    const QData chg = newData ^ oldData;
-    for (int i = 0; i < width; ++i) {
-        covp[2 * i + static_cast<int>((newData >> i) & 1)] += static_cast<uint32_t>((chg >> i) & 1);
+template <class T_CovP>
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, T_CovP covp, QData newData, QData oldData) {
+    QData chg = newData ^ oldData;
+    if (width < 64) chg &= (1ULL << width) - 1ULL;
+    while (chg) {
+        const int i = vlcu_ctz64(chg);
+        chg &= chg - 1ULL;
+        ++covp[2 * i + static_cast<int>((newData >> i) & 1ULL)];
     }
 }
 // NOTE (bug-compatible): the host runtime's inner loop runs j up to width - 32*w, i.e. past
 // 31 for every word but the last, and shifts a 32-bit word by j.  That is undefined in C++;
 // as built by the reference's default flags (scalar x86 `shr`, count taken mod 32) the low
-// words are therefore counted again into the counters of higher bits.  Reproduced here with
-// an explicit (j & 31) so the device gives the same counts as the reference binary.
-VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, uint32_t* covp, WDataInP newData,
-                                    WDataInP oldData) {
+// words are therefore counted again into the counters of higher bits: changed bit b of word w
+// bumps the counters of bits w*32 + b, w*32 + b + 32, ... below `width`.  Reproduced here.
+template <class T_CovP>
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, T_CovP covp, WDataInP newData, WDataInP oldData) {
     for (int w = 0; w < VL_WORDS_I(width); ++w) {
-        const EData chg = newData[w] ^ oldData[w];
-        if (!chg) continue;
-        for (int j = 0; j < width - w * 32; ++j) {
-            covp[(w * 32 + j) * 2 + ((newData[w] >> (j & 31)) & 1)] += (chg >> (j & 31)) & 1;
+        EData chg = newData[w] ^ oldData[w];
+        const int limit = width - w * 32;  // j < limit
+        while (chg) {
+            const int b = vlcu_ctz32(chg);
+            chg &= chg - 1U;
+            const uint32_t bit = (newData[w] >> b) & 1U;
+            for (int j = b; j < limit; j += 32) ++covp[(w * 32 + j) * 2 + bit];
         }
     }
 }
@@ -457,6 +514,16 @@ struct VlcuGlobalArray final {
     VLCU_HD T_Value& operator[](size_t index) { return m_basep[index]; }
     VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index]; }
     VLCU_HD constexpr size_t size() const { return N_Depth; }
+};
+
+// The coverage counter array of a model image: see VlcuCovPtr
+template <size_t N_Bins>
+struct VlcuCovArray final : public VlcuCovPtr {
+    VLCU_HD void bind(const VlcuState& st, uint32_t soaOffset, uint64_t inst) {
+        m_basep = st.ptr<uint32_t>(soaOffset) + inst;
+        m_stride = st.npad;
+    }
+    VLCU_HD constexpr size_t size() const { return N_Bins; }
 };
 
 // A small array that is indexed with run-time values (a register file, coverage counters).

@@ -47,7 +47,7 @@ VL_DEFINE_DEBUG_FUNCTIONS;
 
 namespace {
 
-enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL };
+enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL, COVER };
 
 struct CudaMember final {
     const AstVar* varp = nullptr;
@@ -269,7 +269,7 @@ class EmitCudaModel final : public EmitCFunc {
                 cov.isArray = true;
                 cov.width = 32;
                 cov.msb = 31;
-                cov.storage = CudaStorage::LOCAL;
+                cov.storage = CudaStorage::COVER;  // stays in the SoA block, bumped with RED.ADD
                 cov.elemCType = "uint32_t";
                 cov.elemDecl = "uint32_t";
                 cov.offset = offset;
@@ -319,6 +319,7 @@ class EmitCudaModel final : public EmitCFunc {
         case CudaStorage::SHARED: return "VlcuSharedArray<" + m.elemDecl + ", " + depth + "> " + m.name;
         case CudaStorage::LOCAL: return "VlcuLocalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
         case CudaStorage::GLOBAL: return "VlcuGlobalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
+        case CudaStorage::COVER: return "VlcuCovArray<" + depth + "> " + m.name;
         default: return "";
         }
     }
@@ -332,6 +333,7 @@ class EmitCudaModel final : public EmitCFunc {
                 puts(handleDecl(m) + ";");
                 puts(m.storage == CudaStorage::SHARED  ? "  // run-time indexed: shared memory [index][lane]\n"
                      : m.storage == CudaStorage::LOCAL ? "  // thread-local memory\n"
+                     : m.storage == CudaStorage::COVER ? "  // stays in HBM as cov[bin][instance], RED.ADD\n"
                                                        : "  // stays in HBM, instance-major\n");
             }
         }
@@ -344,7 +346,7 @@ class EmitCudaModel final : public EmitCFunc {
         puts(load ? "VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {\n"
                   : "VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {\n");
         for (const CudaMember& m : m_members) {
-            if (m.storage == CudaStorage::GLOBAL) continue;
+            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER) continue;
             const string off = "OFF_" + m.name;
             if (!m.isArray && !m.isWide) {
                 puts(load ? "s." + m.name + " = st.ld<" + m.elemCType + ">(" + off + ", i);\n"
@@ -858,7 +860,9 @@ class EmitCudaModel final : public EmitCFunc {
         for (const CudaMember& m : m_members) {
             if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
             if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
-            if (m.storage == CudaStorage::GLOBAL) puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
+            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER) {
+                puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
+            }
         }
         puts("}\n");
         emitLoadStore(true);

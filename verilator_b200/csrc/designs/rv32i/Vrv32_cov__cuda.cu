@@ -127,7 +127,7 @@ struct Vrv32_cov___024root final {
     VlUnpacked<QData/*63:0*/, 2> __VicoTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
-    VlcuLocalArray<uint32_t, 1664> __Vcoverage;  // thread-local memory
+    VlcuCovArray<1664> __Vcoverage;  // stays in HBM as cov[bin][instance], RED.ADD
     const char* vlNamep;
 };
 
@@ -254,7 +254,6 @@ struct Vrv32_cov__cuda final {
         kTouchedWriteBytes = 322,  // S_state_wr
     };
     struct Locals final {
-        uint32_t __Vcoverage[1664];
     };
     struct Shared final {
         IData/*31:0*/ rv32_soc__DOT__regs[32][VLCU_BLOCK];
@@ -264,7 +263,7 @@ struct Vrv32_cov__cuda final {
         s.vlNamep = "TOP";
         s.rv32_soc__DOT__mem.bind(st, OFF_rv32_soc__DOT__mem, i);
         s.rv32_soc__DOT__regs.bind(sh.rv32_soc__DOT__regs, threadIdx.x);
-        s.__Vcoverage.bind(l.__Vcoverage);
+        s.__Vcoverage.bind(st, OFF___Vcoverage, i);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
@@ -379,7 +378,6 @@ struct Vrv32_cov__cuda final {
         for (uint32_t e = 0; e < 2; ++e) s.__VicoTriggered[e] = st.ldE<QData>(OFF___VicoTriggered, e, i);
         for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
         for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
-        for (uint32_t e = 0; e < 1664; ++e) s.__Vcoverage[e] = st.ldE<uint32_t>(OFF___Vcoverage, e, i);
     }
     VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
         st.st<VlcuMem8>(OFF_clk, i, s.clk);
@@ -494,7 +492,6 @@ struct Vrv32_cov__cuda final {
         for (uint32_t e = 0; e < 2; ++e) st.stE<QData>(OFF___VicoTriggered, e, i, s.__VicoTriggered[e]);
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
         for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
-        for (uint32_t e = 0; e < 1664; ++e) st.stE<uint32_t>(OFF___Vcoverage, e, i, s.__Vcoverage[e]);
     }
     VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
         s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
