@@ -116,9 +116,24 @@ struct VlcuCovRef final {
 };
 struct VlcuCovPtr {
     uint32_t* m_basep;  // counter 0 of this instance
-    uint64_t m_stride;  // padded instance count (elements between consecutive bins)
-    VLCU_HD VlcuCovRef operator[](size_t bin) const { return VlcuCovRef{m_basep + bin * m_stride}; }
-    VLCU_HD VlcuCovPtr operator+(size_t bin) const { return VlcuCovPtr{m_basep + bin * m_stride, m_stride}; }
+    uint32_t m_stride;  // padded instance count (elements between consecutive bins)
+    // The stride as seen at a point of use.  The empty volatile asm keeps the compiler from
+    // treating the counter addresses as loop invariants of the cycle loop: hoisted, the thousands
+    // of 64-bit addresses of a covered design would all be live across the loop and spill.
+    VLCU_HD uint32_t stride() const {
+        uint32_t s = m_stride;
+#ifdef __CUDA_ARCH__
+        asm volatile("" : "+r"(s));
+#endif
+        return s;
+    }
+    // 32 x 32 -> 64-bit products: one IMAD.WIDE per counter address
+    VLCU_HD VlcuCovRef operator[](size_t bin) const {
+        return VlcuCovRef{m_basep + static_cast<uint64_t>(stride()) * static_cast<uint32_t>(bin)};
+    }
+    VLCU_HD VlcuCovPtr operator+(size_t bin) const {
+        return VlcuCovPtr{m_basep + static_cast<uint64_t>(stride()) * static_cast<uint32_t>(bin), m_stride};
+    }
 };
 // (VlcuCovArray, the bindable member type, is defined with VlcuState below)
 
@@ -142,26 +157,70 @@ VLCU_HD int vlcu_ctz64(uint64_t x) {
 // 2*bit + new value, bumped when the bit changed.  Counters wrap (uint32).
 
 // The host loops over all `width` bits and adds 0 or 1; here only the bits that changed are
-// visited (same counters, same increments): a signal typically toggles a few bits per eval.
+// visited (same counters, same increments).
+
+// Counter 2*i + 1 for every set bit i of `rise`, counter 2*i for every set bit i of `fall`
+// (covp points at the signal's counter 0).  Both bit sets are walked in the same loop: two
+// independent chains per iteration, and the loop-carried dependency is only "clear the lowest
+// set bit" (two ALU operations) -- the bit index (FLO) and the address are off that chain.
+VLCU_HD void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t rise, uint32_t fall) {
+#ifdef __CUDA_ARCH__
+    // bytes between the counters of consecutive bits (two bins): fits 32 bits for any shard
+    // below 2^29 instances; the product with the bit number is formed in 64 bits
+    const uint32_t stride = covp.stride();
+    uint32_t step = stride * 8U;
+    uint64_t fallp = reinterpret_cast<uint64_t>(covp.m_basep);
+    uint64_t risep = fallp + static_cast<uint64_t>(stride) * 4U;
+    asm volatile("" : "+l"(risep), "+l"(fallp), "+r"(step));  // formed once, not per iteration
+    while (rise | fall) {
+        const uint32_t riseNext = rise & (rise - 1U), fallNext = fall & (fall - 1U);
+        const uint32_t riseBit = rise ^ riseNext, fallBit = fall ^ fallNext;  // one-hot or 0
+        uint32_t ri, fi;
+        asm("bfind.u32 %0, %1;" : "=r"(ri) : "r"(riseBit));
+        asm("bfind.u32 %0, %1;" : "=r"(fi) : "r"(fallBit));
+        // predicated REDs: no branch inside the loop body
+        asm volatile(
+            "{\n"
+            ".reg .pred p, q;\n"
+            "setp.ne.u32 p, %2, 0;\n"
+            "setp.ne.u32 q, %3, 0;\n"
+            "@p red.global.add.u32 [%0], 1;\n"
+            "@q red.global.add.u32 [%1], 1;\n"
+            "}\n" ::"l"(risep + static_cast<uint64_t>(ri) * step),
+            "l"(fallp + static_cast<uint64_t>(fi) * step), "r"(riseBit), "r"(fallBit)
+            : "memory");
+        rise = riseNext;
+        fall = fallNext;
+    }
+#else
+    for (uint32_t bits = rise | fall; bits; bits &= bits - 1U) {
+        const int i = vlcu_ctz32(bits);
+        ++covp[2 * i + ((rise >> i) & 1U)];
+    }
+#endif
+}
+VLCU_HD void vlcu_cov_bump_bits(uint32_t* covp, uint32_t rise, uint32_t fall) {
+    for (uint32_t bits = rise | fall; bits; bits &= bits - 1U) {
+        const int i = vlcu_ctz32(bits);
+        ++covp[2 * i + ((rise >> i) & 1U)];
+    }
+}
 template <class T_CovP>
 VLCU_HD void VL_COV_TOGGLE_CHG_ST_I(int width, T_CovP covp, IData newData, IData oldData) {
     IData chg = newData ^ oldData;
     if (width < 32) chg &= (1U << width) - 1U;
-    while (chg) {
-        const int i = vlcu_ctz32(chg);
-        chg &= chg - 1U;
-        ++covp[2 * i + ((newData >> i) & 1U)];
-    }
+    if (!chg) return;
+    vlcu_cov_bump_bits(covp, chg & newData, chg & ~newData);  // 0 -> 1: counter 2*bit + 1
 }
 template <class T_CovP>
 VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, T_CovP covp, QData newData, QData oldData) {
     QData chg = newData ^ oldData;
     if (width < 64) chg &= (1ULL << width) - 1ULL;
-    while (chg) {
-        const int i = vlcu_ctz64(chg);
-        chg &= chg - 1ULL;
-        ++covp[2 * i + static_cast<int>((newData >> i) & 1ULL)];
-    }
+    if (!chg) return;
+    const uint32_t chgLo = static_cast<uint32_t>(chg), chgHi = static_cast<uint32_t>(chg >> 32);
+    const uint32_t newLo = static_cast<uint32_t>(newData), newHi = static_cast<uint32_t>(newData >> 32);
+    vlcu_cov_bump_bits(covp, chgLo & newLo, chgLo & ~newLo);
+    vlcu_cov_bump_bits(covp + 64, chgHi & newHi, chgHi & ~newHi);
 }
 // NOTE (bug-compatible): the host runtime's inner loop runs j up to width - 32*w, i.e. past
 // 31 for every word but the last, and shifts a 32-bit word by j.  That is undefined in C++;
@@ -521,7 +580,7 @@ template <size_t N_Bins>
 struct VlcuCovArray final : public VlcuCovPtr {
     VLCU_HD void bind(const VlcuState& st, uint32_t soaOffset, uint64_t inst) {
         m_basep = st.ptr<uint32_t>(soaOffset) + inst;
-        m_stride = st.npad;
+        m_stride = static_cast<uint32_t>(st.npad);
     }
     VLCU_HD constexpr size_t size() const { return N_Bins; }
 };

@@ -100,6 +100,8 @@ typedef struct {
 #define VLCU_RUNF_STIM_DEVICE 0x4u /* stim points to device memory */
 #define VLCU_RUNF_OBS_DEVICE 0x8u /* obs points to device memory */
 #define VLCU_RUNF_STIM_BROADCAST 0x10u /* one stimulus row serves all instances */
+#define VLCU_RUNF_BULK_1D 0x40u /* "trace": stage rows with per-word 1-D bulk copies instead of 2-D tensor tiles */
+#define VLCU_RUNF_NO_STREAM 0x20u /* "trace": read/write rows with plain global accesses instead of TMA-staged stages */
 
 typedef struct {
     const char* tb; /* testbench: "none", "trace", or a design-specific one */
@@ -137,6 +139,15 @@ const char* vlcu_design_name(int index);
    (plain malloc'ed memory works too, pinned memory makes the copies asynchronous DMA) */
 void* vlcu_host_alloc(size_t bytes);
 void vlcu_host_free(void* ptr);
+
+/* Device buffers for stimulus / observation rows that stay resident in HBM between runs
+   (VLCU_RUNF_STIM_DEVICE / VLCU_RUNF_OBS_DEVICE) */
+void* vlcu_device_alloc(vlcu_model_t* h, size_t bytes);
+void vlcu_device_free(vlcu_model_t* h, void* ptr);
+int vlcu_device_copy(vlcu_model_t* h, void* dst, const void* src, size_t bytes, int to_device);
+/* vlcu_run with host-resident "trace" stimulus larger than two chunks streams it through the
+   device in eval-chunks of about `bytes` (default 64 MB; 0 = always stage the whole run) */
+int vlcu_set_pipeline_chunk(vlcu_model_t* h, size_t bytes);
 
 /* ---- model life cycle -------------------------------------------------- */
 /* n_instances models of `design` on CUDA device `device`; instance i of this shard has global
@@ -177,6 +188,16 @@ int vlcu_member_index(const vlcu_model_t* h, const char* name);
 int vlcu_member_info(const vlcu_model_t* h, int member, vlcu_port_info_t* out);
 int vlcu_set_member(vlcu_model_t* h, int member, const void* src, size_t stride_bytes);
 int vlcu_get_member(vlcu_model_t* h, int member, void* dst, size_t stride_bytes);
+/* Asynchronous ingest for pipelined campaigns: vlcu_stage_member starts the host->device copy of
+ * a member's NEXT value (src in page-locked memory, see vlcu_host_alloc) on a copy stream into a
+ * staging buffer while a vlcu_run is still computing; vlcu_commit_staged enqueues, on the
+ * model's stream, the move of everything staged into the state.  Neither call blocks the host;
+ * src must stay unchanged until the first synchronising call after the commit.  mask_width != 0
+ * masks to the declared width as vlcu_set_input does.  No reference counterpart: it is
+ * "top->port = value" for the next batch, issued early. */
+int vlcu_stage_member(vlcu_model_t* h, int member, const void* src, size_t stride_bytes,
+                      int mask_width);
+int vlcu_commit_staged(vlcu_model_t* h);
 /* Raw device pointer + padded instance stride of a member's SoA array */
 int vlcu_member_device_ptr(vlcu_model_t* h, int member, void** ptr, uint64_t* npad);
 

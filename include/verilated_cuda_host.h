@@ -19,11 +19,21 @@
 enum : uint32_t {
     VLCU_RUN_TB_BEGIN = 1u << 0,  // call the testbench's begin() first (initial port values)
     VLCU_RUN_STOP_ON_FINISH = 1u << 1,  // an instance stops evaluating once gotFinish() is set
+    VLCU_RUN_BULK_1D = 1u << 6,  // "trace" runs: per-word 1-D bulk copies instead of 2-D tensor tiles
+    VLCU_RUN_NO_STREAM = 1u << 5,  // "trace" runs: direct global accesses instead of TMA-staged rows
 };
 #define VLCU_TRACE_HDR 16  // bytes before the state record in a trace sample: u64 time, u32 status, u32 valid
 // A trace sample = [header][packed state, kStateBytes][trace words, kTraceWords x u32, padded to
 // an even count so that every sample starts 8-byte aligned]
 #define VLCU_TRACE_WORDS_PADDED(words) (((words) + 1U) & ~1U)
+
+// TMA tensor maps (CUtensorMap, 128 bytes each) of a "trace" run's stimulus and observation
+// rows seen as 2-D uint32 tensors [eval * words + word][instance]; box = {VLCU_BLOCK instances,
+// all words of one eval}.  Encoded by the runtime per launch, passed to the kernel by value.
+struct alignas(64) VlcuRowMaps final {
+    uint64_t in[16];
+    uint64_t out[16];
+};
 
 // Per-launch parameters of the cycle-loop kernel
 struct VlcuRunDev final {
@@ -47,6 +57,7 @@ struct VlcuRunDev final {
     uint32_t tbFlags;
     uint32_t tbArg[4];
     void* tbPtr[2];
+    const VlcuRowMaps* rowMaps;  // HOST pointer (launch-time only) or null: no tensor maps
 };
 
 enum VlcuMemberKind : uint8_t {

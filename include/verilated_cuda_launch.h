@@ -30,7 +30,9 @@
 #include "verilated_cuda_host.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 //=========================================================================
 // Built-in testbenches usable with any design
@@ -61,7 +63,8 @@ struct VlcuTbTrace final {
                              uint64_t inst, uint64_t e) {
         ctx.timeInc(1);
         const uint64_t stride = r.stimBroadcast ? 1 : r.npad;
-        const uint32_t* rowp = r.stim + e * T_Design::kInWords * stride;
+        // rows are relative to this run: row 0 drives the run's first eval
+        const uint32_t* rowp = r.stim + (e - r.evalBase) * T_Design::kInWords * stride;
         T_Design::load_inputs_row(root, rowp, stride, r.stimBroadcast ? 0 : inst);
     }
 };
@@ -160,6 +163,189 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
     if (r.evalsDone) r.evalsDone[inst] += evalsDone;
 }
 
+//=========================================================================
+// Port streaming: "trace" testbench with per-instance stimulus rows and (optionally) every
+// output port captured after every eval -- the per-cycle port parity path, and the one workload
+// whose bytes really stream through HBM every eval (S_in + S_out per instance-eval).
+//
+// Rows are staged through shared memory by the TMA unit: one elected thread per CTA issues 1-D
+// bulk copies (cp.async.bulk, SASS UBLKCP) of the CTA's 64-instance segment of each input word
+// kDepth evals ahead, completion is signalled on one mbarrier per stage; output words are
+// written to a shared stage and leave with bulk stores (cp.async.bulk.global.shared::cta), so
+// the eval loop itself never waits on a global load and issues no global store.
+
+VLCU_D uint32_t vlcu_smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+VLCU_D void vlcu_mbar_init(uint64_t* barp, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vlcu_smem_addr(barp)), "r"(count)
+                 : "memory");
+}
+VLCU_D void vlcu_mbar_expect_tx(uint64_t* barp, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vlcu_smem_addr(barp)),
+                 "r"(bytes)
+                 : "memory");
+}
+VLCU_D void vlcu_mbar_wait(uint64_t* barp, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(vlcu_smem_addr(barp)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared, completion counted in bytes on the mbarrier
+VLCU_D void vlcu_bulk_load(void* smemDst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* barp) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            vlcu_smem_addr(smemDst)),
+        "l"(gsrc), "r"(bytes), "r"(vlcu_smem_addr(barp))
+        : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+VLCU_D void vlcu_bulk_store(void* gdst, const void* smemSrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(vlcu_smem_addr(smemSrc)), "r"(bytes)
+                 : "memory");
+}
+// 2-D tensor tile: one TMA instruction moves the CTA's segment of every word of one eval
+VLCU_D void vlcu_tma_load_2d(void* smemDst, const void* tmapp, uint32_t x, uint32_t y, uint64_t* barp) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            vlcu_smem_addr(smemDst)),
+        "l"(tmapp), "r"(x), "r"(y), "r"(vlcu_smem_addr(barp))
+        : "memory");
+}
+VLCU_D void vlcu_tma_store_2d(const void* tmapp, uint32_t x, uint32_t y, const void* smemSrc) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmapp),
+                 "r"(x), "r"(y), "r"(vlcu_smem_addr(smemSrc))
+                 : "memory");
+}
+VLCU_D void vlcu_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+VLCU_D void vlcu_bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+VLCU_D void vlcu_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA)
+VLCU_D void vlcu_fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Pipeline depth: as many evals in flight as fit in 28 KB of shared memory per CTA (7 CTAs/SM)
+template <class T_Design>
+struct VlcuStreamCfg final {
+    static constexpr uint32_t kInStage = (T_Design::kInWords ? T_Design::kInWords : 1) * VLCU_BLOCK;  // words
+    static constexpr uint32_t kOutStage = (T_Design::kOutWords ? T_Design::kOutWords : 1) * VLCU_BLOCK;
+    static constexpr uint32_t kStageBytes = 4 * (kInStage + kOutStage);
+    static constexpr int kDepth = kStageBytes * 8 <= 28672 ? 8 : kStageBytes * 4 <= 28672 ? 4 : 2;
+    static constexpr bool kFits = kStageBytes * 2 + sizeof(typename T_Design::Shared) <= 40960;
+};
+
+template <class T_Design, bool kObs, bool kTensor>
+__global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS)
+    vlcu_k_stream(VlcuModelDev m, VlcuRunDev r, const __grid_constant__ VlcuRowMaps maps) {
+    typedef VlcuStreamCfg<T_Design> Cfg;
+    constexpr int kDepth = Cfg::kDepth;
+    constexpr uint32_t kSegBytes = VLCU_BLOCK * 4;  // one word of the CTA's instances
+    __shared__ typename T_Design::Shared shared;
+    __shared__ __align__(128) uint32_t s_in[kDepth][Cfg::kInStage];
+    __shared__ __align__(128) uint32_t s_out[kObs ? kDepth : 1][Cfg::kOutStage];
+    __shared__ __align__(8) uint64_t s_full[kDepth];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t ctaBase = blockIdx.x * static_cast<uint64_t>(VLCU_BLOCK);
+    const uint64_t inst = ctaBase + tid;
+    const bool valid = inst < m.n;  // rows are padded to npad, so the copies stay in bounds
+    const uint32_t nEvals = static_cast<uint32_t>(r.nEvals);
+    const uint32_t* const stimBase = r.stim + ctaBase;
+    uint32_t* const obsBase = r.obs + ctaBase;
+
+    // producer: one stage = the CTA's segment of every input word of one eval
+    const auto issueLoads = [&](uint32_t e) {
+        const uint32_t s = e % kDepth;
+        vlcu_mbar_expect_tx(&s_full[s], T_Design::kInWords * kSegBytes);
+        if (kTensor) {
+            vlcu_tma_load_2d(&s_in[s][0], &maps.in, static_cast<uint32_t>(ctaBase),
+                             e * T_Design::kInWords, &s_full[s]);
+            return;
+        }
+        const uint32_t* const rowp = stimBase + static_cast<uint64_t>(e) * T_Design::kInWords * r.npad;
+#pragma unroll
+        for (uint32_t w = 0; w < T_Design::kInWords; ++w) {
+            vlcu_bulk_load(&s_in[s][w * VLCU_BLOCK], rowp + w * r.npad, kSegBytes, &s_full[s]);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kDepth; ++s) vlcu_mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        vlcu_fence_async_smem();
+    }
+    __syncthreads();
+    if (tid == 0 && T_Design::kInWords) {
+        for (uint32_t e = 0; e < static_cast<uint32_t>(kDepth) && e < nEvals; ++e) issueLoads(e);
+    }
+
+    typename T_Design::Root root;
+    typename T_Design::Locals locals;
+    VlcuContext ctx;
+    const uint64_t instc = valid ? inst : 0;  // padding lanes shadow instance 0 and store nothing
+    vlcu_ctx_load(ctx, m, instc);
+    T_Design::bind(root, locals, shared, m.state, instc);
+    T_Design::load(root, m.state, instc);
+    uint64_t sig = r.sigs[instc];
+    for (uint32_t e = 0; e < nEvals; ++e) {
+        const uint32_t s = e % kDepth;
+        if (T_Design::kInWords) {
+            vlcu_mbar_wait(&s_full[s], (e / kDepth) & 1U);
+            ctx.timeInc(1);
+            T_Design::load_inputs_row(root, &s_in[s][0], VLCU_BLOCK, tid);
+        } else {
+            ctx.timeInc(1);
+        }
+        if (valid) {  // padding lanes must not bump coverage counters or memories
+            vlcu_eval_step<T_Design>(&root, ctx);
+            sig = T_Design::outputs_sig(root, sig);
+        }
+        if (kObs) {
+            T_Design::store_outputs_row(root, &s_out[kObs ? s : 0][0], VLCU_BLOCK, tid);
+            vlcu_fence_async_smem();
+            // stage s+1 is written next iteration: its bulk stores (issued kDepth-1 evals ago)
+            // must have finished reading shared memory
+            if (tid == 0) vlcu_bulk_wait_read<kDepth - 2>();
+        }
+        __syncthreads();  // inputs of stage s consumed by all, outputs of stage s complete
+        if (tid == 0) {
+            if (kObs && kTensor) {
+                vlcu_tma_store_2d(&maps.out, static_cast<uint32_t>(ctaBase), e * T_Design::kOutWords,
+                                  &s_out[kObs ? s : 0][0]);
+                vlcu_bulk_commit();
+            } else if (kObs) {
+                uint32_t* const rowp = obsBase + static_cast<uint64_t>(e) * T_Design::kOutWords * r.npad;
+#pragma unroll
+                for (uint32_t w = 0; w < T_Design::kOutWords; ++w) {
+                    vlcu_bulk_store(rowp + w * r.npad, &s_out[kObs ? s : 0][w * VLCU_BLOCK], kSegBytes);
+                }
+                vlcu_bulk_commit();
+            }
+            if (T_Design::kInWords && e + kDepth < nEvals) issueLoads(e + kDepth);
+        }
+    }
+    if (kObs && tid == 0) vlcu_bulk_wait_all();
+    if (valid) {
+        T_Design::store(root, m.state, inst);
+        vlcu_ctx_store(ctx);
+        r.sigs[inst] = sig;
+        if (r.evalsDone) r.evalsDone[inst] += nEvals;
+    }
+}
+
 // Vtop::final(): run the design's final blocks
 template <class T_Design>
 __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_final(VlcuModelDev m) {
@@ -185,10 +371,44 @@ class VlcuDesignImpl final : public VlcuDesignOps {
     static unsigned blocksFor(uint64_t n) {
         return static_cast<unsigned>((n + VLCU_BLOCK - 1) / VLCU_BLOCK);
     }
+    // The TMA-staged port streaming kernel serves "trace" runs that capture either every eval's
+    // outputs or none and sample no waveforms (VLCU_RUNF_NO_STREAM forces the direct-access kernel)
+    static bool tryStream(const VlcuModelDev& m, const VlcuRunDev& r, cudaStream_t stream) {
+        return tryStreamImpl(m, r, stream, std::integral_constant<bool, VlcuStreamCfg<T_Design>::kFits>{});
+    }
+    static bool tryStreamImpl(const VlcuModelDev&, const VlcuRunDev&, cudaStream_t, std::false_type) {
+        return false;
+    }
+    static bool tryStreamImpl(const VlcuModelDev& m, const VlcuRunDev& r, cudaStream_t stream,
+                              std::true_type) {
+        if ((r.flags & VLCU_RUN_NO_STREAM) || r.stimBroadcast || r.nSamples || (r.flags & VLCU_RUN_STOP_ON_FINISH)
+            || r.nEvals > 0xffffffffULL || r.nEvals == 0) {
+            return false;
+        }
+        const bool obs = r.obs != nullptr;
+        if (obs && r.obsEvals != r.nEvals) return false;
+        const bool tensor = r.rowMaps && !(r.flags & VLCU_RUN_BULK_1D);
+        const VlcuRowMaps maps = r.rowMaps ? *r.rowMaps : VlcuRowMaps{};
+        const unsigned grid = blocksFor(m.n);
+        if (obs && tensor) {
+            vlcu_k_stream<T_Design, true, true><<<grid, VLCU_BLOCK, 0, stream>>>(m, r, maps);
+        } else if (obs) {
+            vlcu_k_stream<T_Design, true, false><<<grid, VLCU_BLOCK, 0, stream>>>(m, r, maps);
+        } else if (tensor) {
+            vlcu_k_stream<T_Design, false, true><<<grid, VLCU_BLOCK, 0, stream>>>(m, r, maps);
+        } else {
+            vlcu_k_stream<T_Design, false, false><<<grid, VLCU_BLOCK, 0, stream>>>(m, r, maps);
+        }
+        return true;
+    }
     template <class T_Tb>
     bool tryRun(const char* tb, const VlcuModelDev& m, const VlcuRunDev& r, cudaStream_t stream,
                 cudaError_t& err) const {
         if (strcmp(tb, T_Tb::name()) != 0) return false;
+        if (std::is_same<T_Tb, VlcuTbTrace>::value && tryStream(m, r, stream)) {
+            err = cudaGetLastError();
+            return true;
+        }
         const bool observe = r.obs || r.nSamples || (r.flags & VLCU_RUN_STOP_ON_FINISH)
                              || r.nEvals > 0xffffffffULL;
         if (observe) {

@@ -33,6 +33,8 @@
 
 #include "V3EmitCuda.h"
 
+#include "V3File.h"
+
 #include "V3EmitC.h"
 #include "V3EmitCBase.h"
 #include "V3EmitCFunc.h"
@@ -901,6 +903,7 @@ class EmitCudaModel final : public EmitCFunc {
 
         emitHostTables();
         emitPortsInc();
+        emitMk();
         puts("\n// The device testbenches of this design (the user's C++ main loop, on the GPU)\n");
         puts("#ifdef VLCU_TESTBENCH_INCLUDE\n#include VLCU_TESTBENCH_INCLUDE\n#endif\n");
         puts("#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB\n");
@@ -919,6 +922,37 @@ class EmitCudaModel final : public EmitCFunc {
             os << (mp->kind == 1 ? "VLCU_PORT_OUT(" : "VLCU_PORT_IN(") << mp->name << ", " << mp->width << ", "
                << rowWords(*mp) << ")\n";
         }
+    }
+    // <prefix>__cuda.mk: what V3EmitMk's <prefix>.mk is for the C++ model -- the design's
+    // settings, then the generic nvcc rules of include/verilated_cuda.mk
+    void emitMk() {
+        const string prefix = v3Global.opt.prefix();
+        V3OutMkFile of{v3Global.opt.makeDir() + "/" + prefix + "__cuda.mk"};
+        of.putsHeader();
+        of.puts("# DESCRIPTION: Verilator output: Makefile for building the batched CUDA model\n");
+        of.puts("#\n");
+        of.puts("# Execute this makefile from the object directory:\n");
+        of.puts("#    make -f " + prefix + "__cuda.mk [VLCU_TESTBENCH=my_tb.h] [VLCU_DESIGN=name]\n");
+        of.puts("# It builds lib" + prefix + "__cuda.so: this design's device code + the batch runtime behind\n");
+        of.puts("# the C ABI of verilated_cuda_abi.h.\n");
+        of.puts("\n### Constants...\n");
+        of.puts("# Path to Verilator kit (from $VERILATOR_ROOT)\n");
+        of.puts("VERILATOR_ROOT ?= " + V3Options::getenvVERILATOR_ROOT() + "\n");
+        of.puts("# Where verilated_cuda*.h, verilated_cuda.cu and verilated_cuda.mk live\n");
+        of.puts("VLCU_ROOT ?= $(VERILATOR_ROOT)\n");
+        of.puts("\n### Switches...\n");
+        of.puts("# Generated module classes prefix (from --prefix)\n");
+        of.puts("VM_PREFIX = " + prefix + "\n");
+        of.puts("# Name the design registers under (vlcu_create(design, ...))\n");
+        of.puts("VLCU_DESIGN ?= " + prefix + "\n");
+        of.puts("# Header with the design's device testbenches (optional; see verilated_cuda_launch.h)\n");
+        of.puts("VLCU_TESTBENCH ?=\n");
+        of.puts("# Coverage counters per instance (from --coverage)\n");
+        of.puts("VLCU_COVER_BINS = " + cvtToStr(m_coverBins) + "\n");
+        of.puts("# Persistent bytes per instance\n");
+        of.puts("VLCU_STATE_BYTES = " + cvtToStr(m_stateBytes) + "\n");
+        of.puts("\n### Include the generic rules...\n");
+        of.puts("include $(VLCU_ROOT)/include/verilated_cuda.mk\n");
     }
     void emitHostTables() {
         // The user's top module: first component of the internal signals' hierarchical names
@@ -1006,6 +1040,8 @@ public:
 };
 
 }  // namespace
+
+bool V3EmitCuda::s_enabled = false;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

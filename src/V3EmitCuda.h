@@ -7,8 +7,9 @@
 // Verilator.cpp:647) and writes <prefix>__cuda.cu: the design as device code for
 // include/verilated_cuda*.h, one model instance per CUDA thread.
 //
-// Hooking it into verilator_bin is one call beside V3EmitC::emitcFiles()
-// (Verilator.cpp:679); see INTEGRATION.md.
+// Hooked into verilator_bin by integration/verilator-cuda.patch: the --cuda option
+// (V3Options.cpp) and one call after V3EmitC::emitcImp() (Verilator.cpp:662); see INTEGRATION.md.
+// Also writes <prefix>__cuda.mk (nvcc rules, cf. V3EmitMk) and <prefix>__ports.inc.
 //*************************************************************************
 
 #ifndef VERILATOR_V3EMITCUDA_H_
@@ -20,6 +21,12 @@
 class V3EmitCuda final {
 public:
     static void emitCuda() VL_MT_DISABLED;
+    // --cuda / --no-cuda
+    static void enable(bool flag) { s_enabled = flag; }
+    static bool enabled() { return s_enabled; }
+
+private:
+    static bool s_enabled;
 };
 
 #endif  // Guard

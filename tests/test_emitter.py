@@ -32,7 +32,7 @@ needs_vlite = pytest.mark.skipif(not (os.path.exists(VLITE) and os.path.isdir(RE
 @pytest.mark.parametrize("model,source,flags", CASES)
 def test_committed_model_is_what_the_emitter_prints(tmp_path, model, source, flags):
     mdir = str(tmp_path / "obj")
-    cmd = [VLITE, "--cc", "--no-std", "--no-std-waiver", "-x-assign", "fast", "--Mdir", mdir, *flags, source]
+    cmd = [VLITE, "--cc", "--cuda", "--no-std", "--no-std-waiver", "-x-assign", "fast", "--Mdir", mdir, *flags, source]
     res = subprocess.run(cmd, cwd=os.path.join(ROOT, "oracle"), capture_output=True, text=True,
                          env=dict(os.environ, VERILATOR_ROOT=REF))
     assert res.returncode == 0, res.stdout + res.stderr
@@ -76,9 +76,57 @@ module two (input clk, input [7:0] d, output [7:0] q);
   leaf u (.clk(clk), .d(d), .q(q));
 endmodule
 """)
-    res = subprocess.run([VLITE, "--cc", "--no-std", "--no-std-waiver", "--Mdir", str(tmp_path / "o"),
+    res = subprocess.run([VLITE, "--cc", "--cuda", "--no-std", "--no-std-waiver", "--Mdir", str(tmp_path / "o"),
                           "--top-module", "two", str(src)],
                          capture_output=True, text=True, env=dict(os.environ, VERILATOR_ROOT=REF))
     # (the lite front end treats the no_inline pragma as a comment, so `leaf` is inlined)
     assert res.returncode == 0, res.stdout + res.stderr
     assert os.path.exists(tmp_path / "o" / "Vtwo__cuda.cu")
+
+
+@needs_vlite
+def test_cuda_option_gates_the_emitter(tmp_path):
+    """--cuda is a real option of the compiler (integration/verilator-cuda.patch): without it
+    only the C++ model is written."""
+    src = tmp_path / "g.v"
+    src.write_text("module g (input clk, input d, output reg q);\n  always @(posedge clk) q <= d;\nendmodule\n")
+    for flag, expect in ((None, False), ("--cuda", True), ("--no-cuda", False)):
+        mdir = tmp_path / ("o" + (flag or "none").strip("-"))
+        cmd = [VLITE, "--cc", "--no-std", "--no-std-waiver", "--Mdir", str(mdir)] + ([flag] if flag else []) + [str(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, VERILATOR_ROOT=REF))
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert os.path.exists(mdir / "Vg.cpp")
+        assert os.path.exists(mdir / "Vg__cuda.cu") == expect
+        assert os.path.exists(mdir / "Vg__cuda.mk") == expect
+
+
+@needs_vlite
+def test_verilate_and_build_in_one_step(tmp_path):
+    """bin/verilator_cuda = `verilator --cc --cuda` + `make -f <prefix>__cuda.mk`
+    (rules in include/verilated_cuda.mk) gives a loadable lib<prefix>__cuda.so that registers
+    the design and exports the C ABI."""
+    import shutil
+    import sys
+    if not shutil.which("nvcc"):
+        pytest.skip("nvcc not on PATH")
+    src = tmp_path / "cnt.v"
+    src.write_text("""
+module cnt (input clk, input rst, input [15:0] step, output reg [31:0] acc);
+  always @(posedge clk) if (rst) acc <= 0; else acc <= acc + {16'd0, step};
+endmodule
+""")
+    mdir = tmp_path / "obj_dir"
+    res = subprocess.run([os.path.join(ROOT, "bin", "verilator_cuda"), "--design", "counter", "--Mdir", str(mdir),
+                          "--prefix", "Vcnt", str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    # a fresh process: this one may already hold libverilated_cuda.so with the same symbols
+    probe = (
+        "import ctypes, sys\n"
+        "lib = ctypes.CDLL(sys.argv[1])\n"
+        "lib.vlcu_design_name.restype = ctypes.c_char_p\n"
+        "assert lib.vlcu_design_count() == 1 and lib.vlcu_design_name(0) == b'counter'\n"
+        "for sym in ('vlcu_create', 'vlcu_run', 'vlcu_set_input', 'vlcu_get_output', 'vlcu_coverage_reduce'):\n"
+        "    getattr(lib, sym)\n"
+    )
+    res = subprocess.run([sys.executable, "-c", probe, str(mdir / "libVcnt__cuda.so")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr

@@ -165,6 +165,71 @@ def test_trace_testbench_with_host_stimulus_rows(abi):
         check_status(m.status(), want.status)
 
 
+def random_rows(m, evals, seed):
+    """Random stimulus rows for make_tracing_c (clk toggling, a reset pulse, random data ports)."""
+    rng = np.random.default_rng(seed)
+    stim = rng.integers(0, 1 << 32, size=(evals, m.in_words, m.npad), dtype=np.uint64).astype(np.uint32)
+    stim[:, 0, :] = (np.arange(evals, dtype=np.uint32) & 1)[:, None] ^ 1
+    stim[:, 1, :] = (rng.random((evals, m.npad)) < 0.97)
+    return stim
+
+
+def test_port_streaming_kernel_and_host_pipeline_equal_the_direct_kernel(abi):
+    """The same rows through (a) the direct-access kernel, (b) the streaming kernel with 2-D tensor
+    TMA tiles and with 1-D bulk copies, (c) the streaming kernels without output capture, (d) vlcu_run's chunked host pipeline and
+    (e) device-resident row buffers give the same ports after every eval, state and signatures;
+    (a) is the form the other tests check against the reference model."""
+    n, evals = 1000, 333  # not multiples of the CTA size / pipeline depth / chunk size
+    with abi.Model("make_tracing_c", n, rand_reset=2, seed=9) as m:
+        stim = random_rows(m, evals, 21)
+
+        def fresh():
+            m.reset()
+            m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=4, tb_flags=1)
+
+        fresh()
+        obs_a, _ = m.run("trace", evals, stim=stim, obs_evals=evals, flags=abi.RUNF_NO_STREAM)
+        sig_a, st_a, rec_a = m.signatures(), m.status(), m.snapshot(n - 1)
+        fresh()
+        obs_b, _ = m.run("trace", evals, stim=stim, obs_evals=evals)
+        assert (obs_b == obs_a).all()
+        assert (m.signatures() == sig_a).all() and (m.status() == st_a).all()
+        assert (m.snapshot(n - 1) == rec_a).all()
+        fresh()
+        obs_c, _ = m.run("trace", evals, stim=stim, obs_evals=evals, flags=abi.RUNF_BULK_1D)
+        assert (obs_c == obs_a).all() and (m.signatures() == sig_a).all()
+        for flags in (0, abi.RUNF_BULK_1D):
+            fresh()
+            m.run("trace", evals, stim=stim, flags=flags)
+            assert (m.signatures() == sig_a).all() and (m.snapshot(n - 1) == rec_a).all()
+        # two consecutive runs: rows are relative to each run
+        fresh()
+        o1, _ = m.run("trace", 100, stim=stim[:100], obs_evals=100)
+        o2, _ = m.run("trace", evals - 100, stim=stim[100:], obs_evals=evals - 100)
+        assert (np.concatenate([o1, o2]) == obs_a).all() and (m.signatures() == sig_a).all()
+        # chunked host pipeline: 8 evals per chunk
+        fresh()
+        m.set_pipeline_chunk(1)
+        obs_d, _ = m.run("trace", evals, stim=stim, obs_evals=evals)
+        assert (obs_d == obs_a).all() and (m.signatures() == sig_a).all()
+        fresh()
+        m.run("trace", evals, stim=stim)
+        assert (m.signatures() == sig_a).all() and (m.snapshot(n - 1) == rec_a).all()
+        m.set_pipeline_chunk(64 << 20)
+        # device-resident rows
+        fresh()
+        d_stim = abi.lib.vlcu_device_alloc(m.h, stim.nbytes)
+        obs_e = np.zeros((evals, m.out_words, m.npad), dtype=np.uint32)
+        d_obs = abi.lib.vlcu_device_alloc(m.h, obs_e.nbytes)
+        assert d_stim and d_obs
+        abi._check(abi.lib.vlcu_device_copy(m.h, d_stim, stim.ctypes.data, stim.nbytes, 1))
+        m.run_rows(evals, d_stim, d_obs, flags=abi.RUNF_STIM_DEVICE | abi.RUNF_OBS_DEVICE)
+        abi._check(abi.lib.vlcu_device_copy(m.h, obs_e.ctypes.data, d_obs, obs_e.nbytes, 0))
+        assert (obs_e[:, :, :n] == obs_a).all() and (m.signatures() == sig_a).all()
+        abi.lib.vlcu_device_free(m.h, d_stim)
+        abi.lib.vlcu_device_free(m.h, d_obs)
+
+
 @pytest.mark.parametrize("stop_on_finish,period", [(False, 0), (False, 40), (True, 0)])
 def test_vcd_of_sampled_instances_equals_the_reference_writer(abi, tmp_path, stop_on_finish, period):
     """R8: waveforms of sampled instances.  The device samples full state after every eval;

@@ -121,6 +121,47 @@ def test_host_loaded_memory_images_and_iss(abi):
             assert sim.pc == int(pc[i])
 
 
+def pinned(abi, shape, dtype):
+    import ctypes
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = abi.lib.vlcu_host_alloc(nbytes)
+    assert ptr
+    return np.frombuffer((ctypes.c_uint8 * nbytes).from_address(ptr), dtype=dtype).reshape(shape)
+
+
+def test_pipelined_rounds_staged_while_the_previous_round_runs(abi):
+    """vlcu_stage_member / vlcu_commit_staged: the images of round r+1 are copied while round r
+    computes and must neither disturb round r nor differ from a synchronous vlcu_set_member."""
+    n, evals, rounds = 192, 400, 3
+    sets = [np.stack([O.rv32_gen_program(5000 + 97 * r + i) for i in range(n)]) for r in range(rounds)]
+    wants = [O.rv32_run(n, evals, seed=6, rand_reset=2, mem_images=img, want_mem=True) for img in sets]
+    bufs = [pinned(abi, (n, 1024), np.uint32) for _ in range(2)]
+    with abi.Model("rv32i", n, seed=6, rand_reset=2) as m:
+        bufs[0][:] = sets[0]
+        m.stage_member("rv32_soc__DOT__mem", bufs[0])
+        for r in range(rounds):
+            m.reset()  # every round starts from a freshly constructed model, as the oracle's does
+            m.commit_staged()
+            m.run("rv32_host", evals, flags=abi.RUNF_TB_BEGIN)
+            if r + 1 < rounds:  # in flight together with the kernel above
+                bufs[(r + 1) & 1][:] = sets[r + 1]
+                m.stage_member("rv32_soc__DOT__mem", bufs[(r + 1) & 1])
+            assert (m.signatures() == wants[r].sigs).all(), r
+            check_final_state(m, wants[r])
+    # ports take the scatter path, masked to their width like vlcu_set_input
+    with abi.Model("make_tracing_c", n) as m:
+        q = pinned(abi, (n, 1), np.uint64)
+        q[:, 0] = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        w = pinned(abi, (n, 3), np.uint32)
+        w[:] = np.arange(3 * n, dtype=np.uint32).reshape(n, 3) * np.uint32(0x01000193) + np.uint32(0xFFFFFF00)
+        m.stage_member("in_quad", q, mask_width=True)
+        m.stage_member("in_wide", w, mask_width=True)
+        m.commit_staged()
+        assert (m.get_member("in_quad") == (q[:, 0] & np.uint64((1 << 40) - 1))).all()
+        got = m.get_member("in_wide")
+        assert (got[:, :2] == w[:, :2]).all() and (got[:, 2] == (w[:, 2] & 0x3F)).all()
+
+
 def test_split_runs_and_snapshot(abi):
     n = 130
     with abi.Model("rv32i", n, seed=6, rand_reset=2) as a, abi.Model("rv32i", n, seed=6, rand_reset=2) as b:

@@ -50,6 +50,8 @@ STATUS_DTYPE = np.dtype([
 MSG_DTYPE = np.dtype([("time", "<u8"), ("id", "<u4"), ("nargs", "<u4"), ("args", "<u8", 4)])
 
 DIR_IN, DIR_OUT, DIR_INOUT = 0, 1, 2
+RUNF_NO_STREAM = 0x20
+RUNF_BULK_1D = 0x40
 RUNF_TB_BEGIN, RUNF_STOP_ON_FINISH, RUNF_STIM_DEVICE, RUNF_OBS_DEVICE, RUNF_STIM_BROADCAST = (
     1, 2, 4, 8, 16)
 ST_DIDINIT, ST_FINISH, ST_ERROR, ST_STOPPED, ST_FATAL, ST_MSGDROP = 1, 2, 4, 8, 16, 32
@@ -65,6 +67,10 @@ SIGNATURES = {
     "vlcu_design_name": (c_cp, [c_i32]),
     "vlcu_host_alloc": (c_vp, [ctypes.c_size_t]),
     "vlcu_host_free": (None, [c_vp]),
+    "vlcu_device_alloc": (c_vp, [_H, ctypes.c_size_t]),
+    "vlcu_device_free": (None, [_H, c_vp]),
+    "vlcu_device_copy": (c_i32, [_H, c_vp, c_vp, ctypes.c_size_t, c_i32]),
+    "vlcu_set_pipeline_chunk": (c_i32, [_H, ctypes.c_size_t]),
     "vlcu_create": (_H, [c_cp, c_u64, c_i32, c_u64, c_u64, c_i32, c_u32, c_cp]),
     "vlcu_destroy": (None, [_H]),
     "vlcu_reset": (c_i32, [_H]),
@@ -89,6 +95,8 @@ SIGNATURES = {
     "vlcu_member_info": (c_i32, [_H, c_i32, ctypes.POINTER(PortInfo)]),
     "vlcu_set_member": (c_i32, [_H, c_i32, c_vp, ctypes.c_size_t]),
     "vlcu_get_member": (c_i32, [_H, c_i32, c_vp, ctypes.c_size_t]),
+    "vlcu_stage_member": (c_i32, [_H, c_i32, c_vp, ctypes.c_size_t, c_i32]),
+    "vlcu_commit_staged": (c_i32, [_H]),
     "vlcu_member_device_ptr": (c_i32, [_H, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]),
     "vlcu_member_offset": (c_u32, [_H, c_i32]),
     "vlcu_time_inc": (c_i32, [_H, c_u64]),
@@ -188,6 +196,10 @@ class Model:
         except Exception:
             pass
 
+    def reset(self):
+        """Re-construct every instance (time 0, _ctor_var_reset with the same seeds)."""
+        _check(lib.vlcu_reset(self.h))
+
     # -- ports ---------------------------------------------------------------
     def _as_port_array(self, info, values):
         _, _, _, eb, elems = info[:5]
@@ -212,6 +224,17 @@ class Model:
         info = self.members[name]
         arr, stride = self._as_port_array(info, values)
         _check(lib.vlcu_set_member(self.h, info[0], arr.ctypes.data, stride))
+
+    def stage_member(self, name, arr, mask_width=False):
+        """Start the asynchronous host->device copy of a member's next value; `arr` is an
+        (n, elems) array in page-locked memory that stays untouched until after commit_staged()
+        and the next synchronising call."""
+        info = self.members[name]
+        assert arr.shape[0] == self.n and arr.flags["C_CONTIGUOUS"]
+        _check(lib.vlcu_stage_member(self.h, info[0], arr.ctypes.data, arr.strides[0], int(mask_width)))
+
+    def commit_staged(self):
+        _check(lib.vlcu_commit_staged(self.h))
 
     def get_member(self, name):
         m, _, _, eb, elems, _ = self.members[name]
@@ -262,6 +285,23 @@ class Model:
         if obs is not None:
             obs = obs[:, :, :self.n]
         return obs, trace
+
+    def run_rows(self, n_evals, stim_ptr, obs_ptr=None, flags=0):
+        """'trace' run over caller-owned row buffers (host pointers, or device pointers with
+        RUNF_STIM_DEVICE / RUNF_OBS_DEVICE): stim uint32 [n_evals][in_words][npad], obs uint32
+        [n_evals][out_words][npad]."""
+        d = RunDesc()
+        d.tb = b"trace"
+        d.n_evals = n_evals
+        d.flags = flags
+        d.stim = stim_ptr
+        if obs_ptr:
+            d.obs = obs_ptr
+            d.obs_evals = n_evals
+        _check(lib.vlcu_run(self.h, ctypes.byref(d)))
+
+    def set_pipeline_chunk(self, nbytes):
+        _check(lib.vlcu_set_pipeline_chunk(self.h, nbytes))
 
     def final(self):
         _check(lib.vlcu_final(self.h))

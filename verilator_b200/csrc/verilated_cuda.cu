@@ -19,6 +19,7 @@
 #include "verilated_cuda_abi.h"
 #include "verilated_cuda_host.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types only; the library is dlopen()ed on first use
@@ -30,6 +31,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <map>
 #include <vector>
 
 static_assert(sizeof(VlcuCtxRec) == sizeof(vlcu_status_t), "status record layouts must agree");
@@ -143,6 +145,19 @@ struct vlcu_model final {
     uint8_t* dStage = nullptr;
     size_t stageBytes = 0;
     uint8_t* dFlush = nullptr;  // L2 flush scratch (vlcu_flush_l2)
+    // Asynchronous input staging (vlcu_stage_member / vlcu_commit_staged)
+    struct Staged final {
+        uint8_t* dBuf = nullptr;  // device copy of the host records, [inst][elems]
+        size_t bytes = 0;
+        bool pending = false;  // a copy was issued and not yet committed
+        bool mask = false;
+    };
+    size_t pipelineChunkBytes = 64u << 20;  // vlcu_run chunking of host stimulus; 0 = off
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evCopied = nullptr;  // last staged copy finished (copy stream)
+    cudaEvent_t evConsumed = nullptr;  // last commit finished reading the staging buffers
+    bool haveConsumed = false;
+    std::map<int, Staged> staged;  // by member index
 };
 
 namespace {
@@ -253,6 +268,50 @@ const VlcuMemberDesc* memberAt(const vlcu_model* h, int member) {
     return &h->infop->members[member];
 }
 
+// Width mask of a member's most significant element (inputs are masked on ingest)
+uint64_t memberTopMask(const VlcuMemberDesc& md, bool maskWidth) {
+    const int topBits = md.width - static_cast<int>(md.elems - 1) * md.elemBytes * 8;
+    const bool isWide = md.elems > 1 && md.kind != VLCU_MEMBER_COVERAGE;
+    return !maskWidth ? ~0ULL
+                      : (isWide || md.elems == 1)
+                            ? ((topBits >= md.elemBytes * 8) ? ~0ULL : ((1ULL << topBits) - 1ULL))
+                            : ~0ULL;
+}
+
+// Device records [inst][elems] (or one record when broadcast) -> the member's SoA rows
+int launchScatter(vlcu_model* h, const VlcuMemberDesc& md, const uint8_t* dsrc, bool broadcast,
+                  uint64_t topMask) {
+    const uint64_t n = h->n;
+    const uint64_t work = n * md.elems;
+    const unsigned threads = 256, blocks = blocksFor(work, threads);
+    void* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+    switch (md.elemBytes) {
+    case 1:
+        k_scatter<uint8_t><<<blocks, threads, 0, h->stream>>>(static_cast<uint8_t*>(soap), dsrc, n,
+                                                              h->npad, md.elems, broadcast,
+                                                              static_cast<uint8_t>(topMask));
+        break;
+    case 2:
+        k_scatter<uint16_t><<<blocks, threads, 0, h->stream>>>(
+            static_cast<uint16_t*>(soap), reinterpret_cast<const uint16_t*>(dsrc), n, h->npad,
+            md.elems, broadcast, static_cast<uint16_t>(topMask));
+        break;
+    case 4:
+        k_scatter<uint32_t><<<blocks, threads, 0, h->stream>>>(
+            static_cast<uint32_t*>(soap), reinterpret_cast<const uint32_t*>(dsrc), n, h->npad,
+            md.elems, broadcast, static_cast<uint32_t>(topMask));
+        break;
+    default:
+        k_scatter<uint64_t><<<blocks, threads, 0, h->stream>>>(
+            static_cast<uint64_t*>(soap), reinterpret_cast<const uint64_t*>(dsrc), n, h->npad,
+            md.elems, broadcast, topMask);
+        break;
+    }
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return VLCU_OK;
+}
+
 int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, void* dst,
                    size_t stride, bool toDevice, bool maskWidth) {
     const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
@@ -284,13 +343,7 @@ int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, voi
     const uint64_t work = n * md.elems;
     const unsigned threads = 256, blocks = blocksFor(work, threads);
     void* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
-    const int topBits = md.width - static_cast<int>(md.elems - 1) * md.elemBytes * 8;
-    const bool isWide = md.elems > 1 && md.kind != VLCU_MEMBER_COVERAGE;
-    const uint64_t topMask
-        = !maskWidth ? ~0ULL
-                     : (isWide || md.elems == 1)
-                           ? ((topBits >= md.elemBytes * 8) ? ~0ULL : ((1ULL << topBits) - 1ULL))
-                           : ~0ULL;
+    const uint64_t topMask = memberTopMask(md, maskWidth);
     if (toDevice) {
         if (broadcast) {
             CUDA_TRY(cudaMemcpyAsync(h->dStage, src, recBytes, cudaMemcpyHostToDevice, h->stream));
@@ -298,30 +351,7 @@ int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, voi
             CUDA_TRY(cudaMemcpy2DAsync(h->dStage, recBytes, src, stride, recBytes, n,
                                        cudaMemcpyHostToDevice, h->stream));
         }
-        switch (md.elemBytes) {
-        case 1:
-            k_scatter<uint8_t><<<blocks, threads, 0, h->stream>>>(
-                static_cast<uint8_t*>(soap), h->dStage, n, h->npad, md.elems, broadcast,
-                static_cast<uint8_t>(topMask));
-            break;
-        case 2:
-            k_scatter<uint16_t><<<blocks, threads, 0, h->stream>>>(
-                static_cast<uint16_t*>(soap), reinterpret_cast<uint16_t*>(h->dStage), n, h->npad,
-                md.elems, broadcast, static_cast<uint16_t>(topMask));
-            break;
-        case 4:
-            k_scatter<uint32_t><<<blocks, threads, 0, h->stream>>>(
-                static_cast<uint32_t*>(soap), reinterpret_cast<uint32_t*>(h->dStage), n, h->npad,
-                md.elems, broadcast, static_cast<uint32_t>(topMask));
-            break;
-        default:
-            k_scatter<uint64_t><<<blocks, threads, 0, h->stream>>>(
-                static_cast<uint64_t*>(soap), reinterpret_cast<uint64_t*>(h->dStage), n, h->npad,
-                md.elems, broadcast, topMask);
-            break;
-        }
-        ++h->launches;
-        CUDA_TRY(cudaGetLastError());
+        if (const int rc = launchScatter(h, md, h->dStage, broadcast, topMask)) return rc;
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     } else {
         switch (md.elemBytes) {
@@ -364,22 +394,144 @@ void fillPortInfo(const VlcuMemberDesc& md, vlcu_port_info_t* out) {
     out->elems = static_cast<int>(md.elems);
 }
 
-int launchRun(vlcu_model* h, const char* tb, VlcuRunDev& r) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no libcuda link)
+typedef CUresult (*VlcuTensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                          const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                          const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+VlcuTensorMapEncodeFn tensorMapEncodeFn() {
+    static const VlcuTensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess
+            || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<VlcuTensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+// rows [evals * words][npad] of uint32 as a 2-D tensor, box = {VLCU_BLOCK, words}
+bool encodeRowMap(uint64_t out[16], const void* basep, uint64_t npad, uint32_t words, uint64_t evals) {
+    const VlcuTensorMapEncodeFn fn = tensorMapEncodeFn();
+    if (!fn || !basep || !words || words > 256 || !evals || words * evals > 0xffffffffULL) return false;
+    if (reinterpret_cast<uintptr_t>(basep) & 15) return false;
+    static_assert(sizeof(CUtensorMap) == 16 * sizeof(uint64_t), "CUtensorMap size");
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {npad, static_cast<cuuint64_t>(words) * evals};
+    const cuuint64_t strides[1] = {npad * sizeof(uint32_t)};
+    const cuuint32_t box[2] = {VLCU_BLOCK, words};
+    const cuuint32_t elemStrides[2] = {1, 1};
+    const CUresult rc = fn(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(basep), dims,
+                           strides, box, elemStrides, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return false;
+    memcpy(out, &map, sizeof(map));
+    return true;
+}
+
+int launchRun(vlcu_model* h, const char* tb, VlcuRunDev& r, bool markStart = true,
+              bool markStop = true) {
     r.npad = h->npad;
+    VlcuRowMaps maps{};
+    r.rowMaps = nullptr;
+    if (!strcmp(tb, "trace") && r.stim && !r.stimBroadcast && !(r.flags & VLCU_RUN_NO_STREAM)
+        && r.nEvals) {
+        bool ok = encodeRowMap(maps.in, r.stim, h->npad, h->infop->inWords, r.nEvals);
+        if (ok && r.obs && r.obsEvals == r.nEvals) {
+            ok = encodeRowMap(maps.out, r.obs, h->npad, h->infop->outWords, r.nEvals);
+        }
+        if (ok) r.rowMaps = &maps;
+    }
     r.sigs = h->dSigs;
     r.evalsDone = h->dEvalsDone;
     r.evalBase = h->evalIndex;
-    CUDA_TRY(cudaEventRecord(h->evStart, h->stream));
+    if (markStart) CUDA_TRY(cudaEventRecord(h->evStart, h->stream));
     const cudaError_t e = h->opsp->launchRun(tb, h->dev, r, h->stream);
     if (e == cudaErrorInvalidValue) {
         return fail(VLCU_E_ARG, std::string{"unknown testbench '"} + tb + "' for design "
                                     + h->infop->name);
     }
     if (e != cudaSuccess) return failCuda(e, "kernel launch");
-    CUDA_TRY(cudaEventRecord(h->evStop, h->stream));
+    if (markStop) CUDA_TRY(cudaEventRecord(h->evStop, h->stream));
     ++h->launches;
     h->haveTiming = true;
     h->evalIndex += r.nEvals;
+    return VLCU_OK;
+}
+
+// "trace" runs whose stimulus (and captured outputs) live in HOST memory and are too large to
+// be worth holding on the device: eval-chunks flow host -> device -> host through two slots on
+// three streams, so the copy-in of chunk c+1, the kernel of chunk c and the copy-out of chunk
+// c-1 overlap (PCIe is full duplex); device memory use is bounded by four chunk buffers.
+int runTracePipelined(vlcu_model* h, const vlcu_run_desc_t* d, VlcuRunDev r, size_t chunkEvals) {
+    const VlcuDesignInfo& info = *h->infop;
+    const size_t inRow = static_cast<size_t>(info.inWords) * h->npad;  // words per eval
+    const size_t outRow = static_cast<size_t>(info.outWords) * h->npad;
+    const bool wantObs = d->obs && d->obs_evals >= d->n_evals && info.outWords;
+    struct Res final {
+        uint32_t* dStim[2] = {nullptr, nullptr};
+        uint32_t* dObs[2] = {nullptr, nullptr};
+        cudaEvent_t evIn[2] = {nullptr, nullptr}, evRun[2] = {nullptr, nullptr},
+                    evOut[2] = {nullptr, nullptr};
+        cudaStream_t outStream = nullptr;
+        ~Res() {
+            for (int b = 0; b < 2; ++b) {
+                cudaFree(dStim[b]);
+                cudaFree(dObs[b]);
+                if (evIn[b]) cudaEventDestroy(evIn[b]);
+                if (evRun[b]) cudaEventDestroy(evRun[b]);
+                if (evOut[b]) cudaEventDestroy(evOut[b]);
+            }
+            if (outStream) cudaStreamDestroy(outStream);
+        }
+    } res;
+    if (!h->copyStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evCopied, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evConsumed, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&res.outStream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaMalloc(&res.dStim[b], inRow * chunkEvals * sizeof(uint32_t)));
+        if (wantObs) CUDA_TRY(cudaMalloc(&res.dObs[b], outRow * chunkEvals * sizeof(uint32_t)));
+        CUDA_TRY(cudaEventCreateWithFlags(&res.evIn[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&res.evRun[b], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&res.evOut[b], cudaEventDisableTiming));
+    }
+    const uint64_t total = d->n_evals;
+    uint64_t chunk = 0;
+    for (uint64_t e0 = 0; e0 < total; e0 += chunkEvals, ++chunk) {
+        const int b = static_cast<int>(chunk & 1);
+        const uint64_t ne = total - e0 < chunkEvals ? total - e0 : chunkEvals;
+        // copy-in: the slot is free once the kernel of chunk c-2 has finished
+        if (chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(h->copyStream, res.evRun[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(res.dStim[b], d->stim + e0 * inRow, inRow * ne * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, h->copyStream));
+        CUDA_TRY(cudaEventRecord(res.evIn[b], h->copyStream));
+        // kernel: needs its stimulus, and the output slot drained by the copy-out of chunk c-2
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, res.evIn[b], 0));
+        if (wantObs && chunk >= 2) CUDA_TRY(cudaStreamWaitEvent(h->stream, res.evOut[b], 0));
+        VlcuRunDev rc = r;
+        rc.nEvals = ne;
+        rc.stim = res.dStim[b];
+        rc.obs = wantObs ? res.dObs[b] : nullptr;
+        rc.obsEvals = wantObs ? ne : 0;
+        if (chunk) rc.flags &= ~static_cast<uint32_t>(VLCU_RUN_TB_BEGIN);
+        if (const int rcode = launchRun(h, "trace", rc, chunk == 0, e0 + ne >= total)) return rcode;
+        CUDA_TRY(cudaEventRecord(res.evRun[b], h->stream));
+        if (wantObs) {
+            CUDA_TRY(cudaStreamWaitEvent(res.outStream, res.evRun[b], 0));
+            CUDA_TRY(cudaMemcpyAsync(d->obs + e0 * outRow, res.dObs[b], outRow * ne * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, res.outStream));
+            CUDA_TRY(cudaEventRecord(res.evOut[b], res.outStream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copyStream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(res.outStream));
     return VLCU_OK;
 }
 
@@ -414,6 +566,35 @@ void* vlcu_host_alloc(size_t bytes) {
 }
 void vlcu_host_free(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+void* vlcu_device_alloc(vlcu_model_t* h, size_t bytes) {
+    if (!h) return nullptr;
+    DeviceGuard guard{h->device};
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(VLCU_E_CUDA, "vlcu_device_alloc: cudaMalloc failed");
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void vlcu_device_free(vlcu_model_t* h, void* ptr) {
+    if (!h || !ptr) return;
+    DeviceGuard guard{h->device};
+    cudaFree(ptr);
+}
+int vlcu_device_copy(vlcu_model_t* h, void* dst, const void* src, size_t bytes, int to_device) {
+    if (!h || !dst || !src) return fail(VLCU_E_ARG, "vlcu_device_copy: null argument");
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                             h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+int vlcu_set_pipeline_chunk(vlcu_model_t* h, size_t bytes) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    h->pipelineChunkBytes = bytes;
+    return VLCU_OK;
 }
 
 vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, uint64_t inst_base,
@@ -519,7 +700,12 @@ void vlcu_destroy(vlcu_model_t* h) {
     if (!h) return;
     DeviceGuard guard{h->device};
     if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+    if (h->copyStream) cudaStreamSynchronize(h->copyStream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto& it : h->staged) cudaFree(it.second.dBuf);
+    if (h->evCopied) cudaEventDestroy(h->evCopied);
+    if (h->evConsumed) cudaEventDestroy(h->evConsumed);
+    if (h->copyStream) cudaStreamDestroy(h->copyStream);
     cudaFree(h->dState);
     cudaFree(h->dCtx);
     cudaFree(h->dMsgs);
@@ -620,6 +806,74 @@ int vlcu_get_member(vlcu_model_t* h, int member, void* dst, size_t stride_bytes)
     if (!mdp || !dst) return fail(VLCU_E_ARG, "bad member");
     return transferMember(h, *mdp, nullptr, dst, stride_bytes, false, false);
 }
+// Asynchronous double-buffered ingest.  vlcu_stage_member() starts the host->device copy of a
+// member's NEXT value on a separate copy stream into a staging buffer (the state is untouched,
+// so a vlcu_run in flight keeps computing); vlcu_commit_staged() moves everything staged into
+// the state on the model's stream, ordered on the device behind the copies (the host never
+// waits).  src must stay valid and unchanged until vlcu_commit_staged + the next sync point.
+int vlcu_stage_member(vlcu_model_t* h, int member, const void* src, size_t stride_bytes,
+                      int mask_width) {
+    const VlcuMemberDesc* const mdp = memberAt(h, member);
+    if (!mdp || !src) return fail(VLCU_E_ARG, "bad member");
+    const size_t recBytes = static_cast<size_t>(mdp->elemBytes) * mdp->elems;
+    if (stride_bytes < recBytes) return fail(VLCU_E_ARG, "stride smaller than one element");
+    DeviceGuard guard{h->device};
+    if (!h->copyStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evCopied, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evConsumed, cudaEventDisableTiming));
+    }
+    vlcu_model::Staged& st = h->staged[member];
+    const size_t bytes = recBytes * h->n;
+    if (st.bytes < bytes) {
+        // a previous commit may still be reading the old buffer
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (st.dBuf) cudaFree(st.dBuf);
+        st.dBuf = nullptr;
+        st.bytes = 0;
+        CUDA_TRY(cudaMalloc(&st.dBuf, bytes));
+        st.bytes = bytes;
+    }
+    // the staging buffer is free once the last commit has consumed it
+    if (h->haveConsumed) CUDA_TRY(cudaStreamWaitEvent(h->copyStream, h->evConsumed, 0));
+    if (stride_bytes == recBytes) {
+        CUDA_TRY(cudaMemcpyAsync(st.dBuf, src, bytes, cudaMemcpyHostToDevice, h->copyStream));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(st.dBuf, recBytes, src, stride_bytes, recBytes, h->n,
+                                   cudaMemcpyHostToDevice, h->copyStream));
+    }
+    st.pending = true;
+    st.mask = mask_width != 0;
+    return VLCU_OK;
+}
+int vlcu_commit_staged(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    if (!h->copyStream) return VLCU_OK;
+    DeviceGuard guard{h->device};
+    bool any = false;
+    for (auto& it : h->staged) any |= it.second.pending;
+    if (!any) return VLCU_OK;
+    CUDA_TRY(cudaEventRecord(h->evCopied, h->copyStream));
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evCopied, 0));
+    for (auto& it : h->staged) {
+        vlcu_model::Staged& st = it.second;
+        if (!st.pending) continue;
+        const VlcuMemberDesc& md = h->infop->members[it.first];
+        const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
+        if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major in HBM already
+            uint8_t* const devp = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+            CUDA_TRY(cudaMemcpyAsync(devp, st.dBuf, recBytes * h->n, cudaMemcpyDeviceToDevice,
+                                     h->stream));
+        } else {
+            if (const int rc = launchScatter(h, md, st.dBuf, false, memberTopMask(md, st.mask)))
+                return rc;
+        }
+        st.pending = false;
+    }
+    CUDA_TRY(cudaEventRecord(h->evConsumed, h->stream));
+    h->haveConsumed = true;
+    return VLCU_OK;
+}
 int vlcu_member_device_ptr(vlcu_model_t* h, int member, void** ptr, uint64_t* npad) {
     const VlcuMemberDesc* const mdp = memberAt(h, member);
     if (!mdp || !ptr) return fail(VLCU_E_ARG, "bad member");
@@ -655,7 +909,8 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     const VlcuDesignInfo& info = *h->infop;
     VlcuRunDev r{};
     r.nEvals = d->n_evals;
-    r.flags = d->flags & (VLCU_RUNF_TB_BEGIN | VLCU_RUNF_STOP_ON_FINISH);
+    r.flags = d->flags & (VLCU_RUNF_TB_BEGIN | VLCU_RUNF_STOP_ON_FINISH | VLCU_RUNF_NO_STREAM
+                          | VLCU_RUNF_BULK_1D);
     r.stimBroadcast = (d->flags & VLCU_RUNF_STIM_BROADCAST) ? 1 : 0;
     r.tbSeed = d->tb_seed;
     r.tbFlags = d->tb_flags;
@@ -682,6 +937,17 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     if (!strcmp(d->tb, "trace")) {
         if (!d->stim) return fail(VLCU_E_ARG, "vlcu_run: the trace testbench needs stim");
         const size_t rowWords = static_cast<size_t>(info.inWords) * (r.stimBroadcast ? 1 : h->npad);
+        // Large host-resident stimulus: stream it in eval-chunks instead of staging it whole
+        const bool hostIo = !(d->flags & VLCU_RUNF_STIM_DEVICE) && !(d->obs && (d->flags & VLCU_RUNF_OBS_DEVICE));
+        const bool plainObs = !d->obs || !d->obs_evals || d->obs_evals >= d->n_evals;
+        const size_t chunkBytes = h->pipelineChunkBytes;
+        const size_t rowBytes = (rowWords + (d->obs ? static_cast<size_t>(info.outWords) * h->npad : 0)) * sizeof(uint32_t);
+        if (hostIo && plainObs && !r.stimBroadcast && !d->n_samples && info.inWords && chunkBytes
+            && !(d->flags & VLCU_RUNF_STOP_ON_FINISH) && rowBytes * d->n_evals > 2 * chunkBytes) {
+            size_t chunkEvals = chunkBytes / rowBytes;
+            if (chunkEvals < 8) chunkEvals = 8;
+            return runTracePipelined(h, d, r, chunkEvals);
+        }
         if (d->flags & VLCU_RUNF_STIM_DEVICE) {
             r.stim = d->stim;
         } else {
