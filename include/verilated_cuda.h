@@ -159,50 +159,35 @@ VLCU_HD int vlcu_ctz64(uint64_t x) {
 // The host loops over all `width` bits and adds 0 or 1; here only the bits that changed are
 // visited (same counters, same increments).
 
-// Counter 2*i + 1 for every set bit i of `rise`, counter 2*i for every set bit i of `fall`
-// (covp points at the signal's counter 0).  Both bit sets are walked in the same loop: two
-// independent chains per iteration, and the loop-carried dependency is only "clear the lowest
-// set bit" (two ALU operations) -- the bit index (FLO) and the address are off that chain.
-VLCU_HD void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t rise, uint32_t fall) {
+// Counter 2*i + (bit i of newData) for every set bit i of `chg` (covp points at the signal's
+// counter 0).  One loop over the changed bits of both polarities -- the trip count of a warp is
+// the largest number of changed bits in any lane, so splitting rising and falling bits into two
+// loops costs more than it saves -- with a minimal body: find the highest set bit, its new value,
+// one multiply-add for the address, the RED.
+VLCU_HD void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
-    // bytes between the counters of consecutive bits (two bins): fits 32 bits for any shard
-    // below 2^29 instances; the product with the bit number is formed in 64 bits
-    const uint32_t stride = covp.stride();
-    uint32_t step = stride * 8U;
-    uint64_t fallp = reinterpret_cast<uint64_t>(covp.m_basep);
-    uint64_t risep = fallp + static_cast<uint64_t>(stride) * 4U;
-    asm volatile("" : "+l"(risep), "+l"(fallp), "+r"(step));  // formed once, not per iteration
-    while (rise | fall) {
-        const uint32_t riseNext = rise & (rise - 1U), fallNext = fall & (fall - 1U);
-        const uint32_t riseBit = rise ^ riseNext, fallBit = fall ^ fallNext;  // one-hot or 0
-        uint32_t ri, fi;
-        asm("bfind.u32 %0, %1;" : "=r"(ri) : "r"(riseBit));
-        asm("bfind.u32 %0, %1;" : "=r"(fi) : "r"(fallBit));
-        // predicated REDs: no branch inside the loop body
-        asm volatile(
-            "{\n"
-            ".reg .pred p, q;\n"
-            "setp.ne.u32 p, %2, 0;\n"
-            "setp.ne.u32 q, %3, 0;\n"
-            "@p red.global.add.u32 [%0], 1;\n"
-            "@q red.global.add.u32 [%1], 1;\n"
-            "}\n" ::"l"(risep + static_cast<uint64_t>(ri) * step),
-            "l"(fallp + static_cast<uint64_t>(fi) * step), "r"(riseBit), "r"(fallBit)
-            : "memory");
-        rise = riseNext;
-        fall = fallNext;
+    // bytes between consecutive counters: fits 32 bits for any shard below 2^30 instances; the
+    // product with the counter number is formed in 64 bits
+    const uint32_t step = covp.stride() * 4U;
+    char* const basep = reinterpret_cast<char*>(covp.m_basep);
+    while (chg) {
+        uint32_t i;  // index of the most significant set bit (FLO)
+        asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(chg));
+        chg ^= 1U << i;
+        const uint32_t counter = 2U * i + ((newData >> i) & 1U);
+        atomicAdd(reinterpret_cast<uint32_t*>(basep + static_cast<uint64_t>(counter) * step), 1U);
     }
 #else
-    for (uint32_t bits = rise | fall; bits; bits &= bits - 1U) {
-        const int i = vlcu_ctz32(bits);
-        ++covp[2 * i + ((rise >> i) & 1U)];
+    for (; chg; chg &= chg - 1U) {
+        const int i = vlcu_ctz32(chg);
+        ++covp[2 * i + ((newData >> i) & 1U)];
     }
 #endif
 }
-VLCU_HD void vlcu_cov_bump_bits(uint32_t* covp, uint32_t rise, uint32_t fall) {
-    for (uint32_t bits = rise | fall; bits; bits &= bits - 1U) {
-        const int i = vlcu_ctz32(bits);
-        ++covp[2 * i + ((rise >> i) & 1U)];
+VLCU_HD void vlcu_cov_bump_bits(uint32_t* covp, uint32_t chg, uint32_t newData) {
+    for (; chg; chg &= chg - 1U) {
+        const int i = vlcu_ctz32(chg);
+        ++covp[2 * i + ((newData >> i) & 1U)];
     }
 }
 template <class T_CovP>
@@ -210,7 +195,7 @@ VLCU_HD void VL_COV_TOGGLE_CHG_ST_I(int width, T_CovP covp, IData newData, IData
     IData chg = newData ^ oldData;
     if (width < 32) chg &= (1U << width) - 1U;
     if (!chg) return;
-    vlcu_cov_bump_bits(covp, chg & newData, chg & ~newData);  // 0 -> 1: counter 2*bit + 1
+    vlcu_cov_bump_bits(covp, chg, newData);
 }
 template <class T_CovP>
 VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, T_CovP covp, QData newData, QData oldData) {
@@ -219,8 +204,8 @@ VLCU_HD void VL_COV_TOGGLE_CHG_ST_Q(int width, T_CovP covp, QData newData, QData
     if (!chg) return;
     const uint32_t chgLo = static_cast<uint32_t>(chg), chgHi = static_cast<uint32_t>(chg >> 32);
     const uint32_t newLo = static_cast<uint32_t>(newData), newHi = static_cast<uint32_t>(newData >> 32);
-    vlcu_cov_bump_bits(covp, chgLo & newLo, chgLo & ~newLo);
-    vlcu_cov_bump_bits(covp + 64, chgHi & newHi, chgHi & ~newHi);
+    vlcu_cov_bump_bits(covp, chgLo, newLo);
+    vlcu_cov_bump_bits(covp + 64, chgHi, newHi);
 }
 // NOTE (bug-compatible): the host runtime's inner loop runs j up to width - 32*w, i.e. past
 // 31 for every word but the last, and shifts a 32-bit word by j.  That is undefined in C++;

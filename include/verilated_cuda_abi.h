@@ -100,6 +100,7 @@ typedef struct {
 #define VLCU_RUNF_STIM_DEVICE 0x4u /* stim points to device memory */
 #define VLCU_RUNF_OBS_DEVICE 0x8u /* obs points to device memory */
 #define VLCU_RUNF_STIM_BROADCAST 0x10u /* one stimulus row serves all instances */
+#define VLCU_RUNF_TRACE_CHANGES 0x80u /* sampled instances record change streams (below) instead of full records */
 #define VLCU_RUNF_BULK_1D 0x40u /* "trace": stage rows with per-word 1-D bulk copies instead of 2-D tensor tiles */
 #define VLCU_RUNF_NO_STREAM 0x20u /* "trace": read/write rows with plain global accesses instead of TMA-staged stages */
 
@@ -118,7 +119,9 @@ typedef struct {
        host buffer of trace_evals * n_samples * vlcu_trace_record_bytes() bytes */
     const uint64_t* sample_instances;
     uint32_t n_samples;
-    uint32_t pad2_;
+    /* VLCU_RUNF_TRACE_CHANGES: trace_out holds n_samples streams of trace_stream_words uint32
+       each (vlcu_vcd_write_changes documents the format); 0 otherwise */
+    uint32_t trace_stream_words;
     void* trace_out;
     uint64_t trace_evals;
     /* parameters interpreted by the design-specific testbench */
@@ -224,12 +227,35 @@ const char* vlcu_message_format(const vlcu_model_t* h, uint32_t id);
 int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_bytes);
 uint32_t vlcu_member_offset(const vlcu_model_t* h, int member);
 
+/* One instance as a verilated_save image (include/verilated_save.h:193-223): the file
+   `VerilatedSave os; os.open(f); os << *top;` writes for a --savable build of the same design,
+   so a failing instance of a campaign can be loaded into the ordinary C++ model with
+   `VerilatedRestore os; os.open(f); os >> *top;` and replayed under a debugger; and the reverse,
+   a state saved by the C++ model loaded into instance `instance`.  The image's randSeed /
+   randReset must be the instance's own.  Not available for --coverage builds (the reference
+   refuses --savable with --coverage). */
+int vlcu_save_instance(vlcu_model_t* h, uint64_t instance, const char* filename);
+int vlcu_restore_instance(vlcu_model_t* h, uint64_t instance, const char* filename);
+/* The bytes of a freshly constructed VerilatedContext's serialized part as this library lays
+   them out (returns their count); for checking against the runtime the images are loaded by */
+int vlcu_save_context_image(void* out, size_t out_bytes);
+
 /* Waveform of ONE sampled instance as VCD text, written exactly as VerilatedVcdC would write it
    for that model instance with a dump() after every eval (include/verilated_vcd_c.cpp:117-129,
    191-203,317-470,620-690; include/verilated_trace_imp.h): `trace` is the buffer vlcu_run filled
    (trace_evals x n_samples records), `sample` selects the instance's slot in it. */
 int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_evals,
                    uint32_t n_samples, uint32_t sample, const char* filename);
+
+/* The same from a change stream (VLCU_RUNF_TRACE_CHANGES): the device compares every trace word
+   with its value at the previous dump and records only the differences, so the device->host copy
+   and the host-side work scale with signal activity, not with design size x evals (the role of
+   the chg* functions of include/verilated_trace.h:384-432).  Stream of one sample, uint32 words:
+   [0] words used  [1] dumps dropped for lack of room  [2] dumps recorded  [3] reserved, then per
+   dump: [0x80000000 | n] [time lo] [time hi] and n x { [trace word index] [value] }; the first
+   dump lists every word.  `streams` is the buffer vlcu_run filled. */
+int vlcu_vcd_write_changes(const vlcu_model_t* h, const uint32_t* streams, uint32_t stream_words,
+                           uint32_t n_samples, uint32_t sample, const char* filename);
 
 /* ---- coverage ------------------------------------------------------------------ */
 uint32_t vlcu_coverage_bins(const vlcu_model_t* h); /* counters per instance */

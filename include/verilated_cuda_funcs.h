@@ -392,30 +392,33 @@ VLCU_HD int _vl_cmps_w(int lbits, WDataInP lwp, WDataInP rwp) {
 #define VL_GTS_IWW(lbits, lwp, rwp) (_vl_cmps_w(lbits, lwp, rwp) > 0)
 #define VL_GTES_IWW(lbits, lwp, rwp) (_vl_cmps_w(lbits, lwp, rwp) >= 0)
 
-// <=64 bit signed compares: sign-extend from lbits to 64 bits, compare as int64
+// Signed compares (verilated_funcs.h VL_GTS_III etc. sign-extend both sides to 64 bits): values
+// of up to 32 bits are moved to the top of a 32-bit register instead (a shift by a constant, none
+// at all for 32-bit operands) and compared as int32 -- the same order, half the instructions.
+VLCU_HD int32_t vlcu_stop32(int lbits, IData v) { return static_cast<int32_t>(v << (32 - lbits)); }
 VLCU_HD int64_t vlcu_sext64(int lbits, QData v) {
-    return static_cast<int64_t>(VL_EXTENDS_QQ(64, lbits, v));
+    return static_cast<int64_t>(v << (64 - lbits)) >> (64 - lbits);
 }
 VLCU_HD IData VL_GTS_III(int lbits, IData lhs, IData rhs) {
-    return vlcu_sext64(lbits, lhs) > vlcu_sext64(lbits, rhs);
+    return vlcu_stop32(lbits, lhs) > vlcu_stop32(lbits, rhs);
 }
 VLCU_HD IData VL_GTS_IQQ(int lbits, QData lhs, QData rhs) {
     return vlcu_sext64(lbits, lhs) > vlcu_sext64(lbits, rhs);
 }
 VLCU_HD IData VL_GTES_III(int lbits, IData lhs, IData rhs) {
-    return vlcu_sext64(lbits, lhs) >= vlcu_sext64(lbits, rhs);
+    return vlcu_stop32(lbits, lhs) >= vlcu_stop32(lbits, rhs);
 }
 VLCU_HD IData VL_GTES_IQQ(int lbits, QData lhs, QData rhs) {
     return vlcu_sext64(lbits, lhs) >= vlcu_sext64(lbits, rhs);
 }
 VLCU_HD IData VL_LTS_III(int lbits, IData lhs, IData rhs) {
-    return vlcu_sext64(lbits, lhs) < vlcu_sext64(lbits, rhs);
+    return vlcu_stop32(lbits, lhs) < vlcu_stop32(lbits, rhs);
 }
 VLCU_HD IData VL_LTS_IQQ(int lbits, QData lhs, QData rhs) {
     return vlcu_sext64(lbits, lhs) < vlcu_sext64(lbits, rhs);
 }
 VLCU_HD IData VL_LTES_III(int lbits, IData lhs, IData rhs) {
-    return vlcu_sext64(lbits, lhs) <= vlcu_sext64(lbits, rhs);
+    return vlcu_stop32(lbits, lhs) <= vlcu_stop32(lbits, rhs);
 }
 VLCU_HD IData VL_LTES_IQQ(int lbits, QData lhs, QData rhs) {
     return vlcu_sext64(lbits, lhs) <= vlcu_sext64(lbits, rhs);
@@ -1244,6 +1247,9 @@ VLCU_HD QData VL_SHIFTR_QQW(int obits, int, int rbits, QData lhs, WDataInP rwp) 
 // Arithmetic right shift: the sign is bit lbits-1 of the input (lbits may be
 // narrower than obits), result not clean above obits only via the sign fill.
 VLCU_HD IData VL_SHIFTRS_III(int obits, int lbits, int, IData lhs, IData rhs) {
+    if (obits == 32 && lbits == 32) {  // the machine's arithmetic shift (clamps the count itself)
+        return static_cast<IData>(static_cast<int32_t>(lhs) >> (rhs < 31U ? rhs : 31U));
+    }
     const IData sign = 0U - (lhs >> (lbits - 1));
     if (VLCU_UNLIKELY(rhs >= 32)) return sign & VL_MASK_I(obits);
     const IData vacated = ~(VL_MASK_I(lbits) >> rhs);

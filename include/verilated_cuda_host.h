@@ -19,6 +19,7 @@
 enum : uint32_t {
     VLCU_RUN_TB_BEGIN = 1u << 0,  // call the testbench's begin() first (initial port values)
     VLCU_RUN_STOP_ON_FINISH = 1u << 1,  // an instance stops evaluating once gotFinish() is set
+    VLCU_RUN_TRACE_CHANGES = 1u << 7,  // sampled instances record change streams, not full records
     VLCU_RUN_BULK_1D = 1u << 6,  // "trace" runs: per-word 1-D bulk copies instead of 2-D tensor tiles
     VLCU_RUN_NO_STREAM = 1u << 5,  // "trace" runs: direct global accesses instead of TMA-staged rows
 };
@@ -58,7 +59,22 @@ struct VlcuRunDev final {
     uint32_t tbArg[4];
     void* tbPtr[2];
     const VlcuRowMaps* rowMaps;  // HOST pointer (launch-time only) or null: no tensor maps
+    // Waveform sampling as change streams (VLCU_RUN_TRACE_CHANGES): `trace` holds one stream of
+    // traceCapWords uint32 per sample, traceScratch 2 x padded trace words per sample (the
+    // current and the previously recorded value of every trace code)
+    uint32_t traceCapWords;
+    uint32_t* traceScratch;
 };
+
+// Change stream of one sampled instance (uint32 words):
+//   [0] words used so far (header included)  [1] overflow: dumps dropped for lack of room
+//   [2] dumps recorded                        [3] reserved
+//   then per dump: [VLCU_TRACE_DUMP_MARK | n] [time lo] [time hi]  n x { [trace word index] [value] }
+// The first dump of a run lists every trace word; later ones only the words whose value differs
+// from the previous dump -- the device-side form of VerilatedTrace's chg* change detection
+// (verilated_trace.h:384-432).
+#define VLCU_TRACE_STREAM_HDR 4U
+#define VLCU_TRACE_DUMP_MARK 0x80000000U
 
 enum VlcuMemberKind : uint8_t {
     VLCU_MEMBER_IN = 0,  // primary input port
@@ -178,6 +194,19 @@ struct VlcuDesignInfo final {
     uint32_t traceWords;  // 32-bit words of one trace sample (the model's trace codes)
     const uint32_t* traceOrder;  // trace codes in the order the model's trace functions dump them
     uint32_t nTraceOrder;
+    // verilated_save image of one instance (what a --savable build's __Vserialize writes,
+    // V3EmitCImp.cpp:277-350): member indices in serialization order and the structure checksum
+    const uint32_t* saveOrder;
+    uint32_t nSaveOrder;
+    uint32_t saveFlags;  // VLCU_SAVE_*
+    uint64_t saveCheckval;  // __Vcheckval
+    const char* saveUnsupported;  // first member this runtime cannot serialize, or nullptr
+    // what the Syms constructor passes to VerilatedContext::timeunit()/timeprecision()
+    // (V3EmitCSyms.cpp:1191-1199), as the context stores them: -power of ten; -1 = not set
+    int saveTimeunit, saveTimeprecision;
+};
+enum : uint32_t {
+    VLCU_SAVE_ACTIVITY = 1u << 0,  // Syms::__Vserialize writes __Vm_activity first (--trace builds)
 };
 
 #if defined(__CUDACC__) || defined(VLCU_HOST_RUNTIME)

@@ -97,6 +97,40 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
     vlcu_ctx_store(ctx);
 }
 
+// tfp->dump(time) of one sampled instance as a change record: the model's
+// trace functions store the current value of every trace code, the words that differ from the
+// previous dump are appended to the instance's stream.  Nothing but the changes crosses PCIe.
+template <class T_Design>
+VLCU_D void vlcu_trace_changes(typename T_Design::Root* rootp, VlcuContext& ctx, const VlcuRunDev& r,
+                               uint32_t slot) {
+    constexpr uint32_t kWords = VLCU_TRACE_WORDS_PADDED(T_Design::kTraceWords);
+    uint32_t* const streamp = reinterpret_cast<uint32_t*>(r.trace) + static_cast<uint64_t>(slot) * r.traceCapWords;
+    uint32_t* const curp = r.traceScratch + static_cast<uint64_t>(slot) * 2U * kWords;
+    uint32_t* const prevp = curp + kWords;
+    T_Design::trace_sample(rootp, ctx, curp);
+    const bool first = streamp[2] == 0;
+    uint32_t used = streamp[0] ? streamp[0] : VLCU_TRACE_STREAM_HDR;  // (the buffer starts zeroed)
+    uint32_t changed = 0;
+    for (uint32_t w = 0; w < T_Design::kTraceWords; ++w) changed += (first || curp[w] != prevp[w]);
+    if (used + 3U + 2U * changed > r.traceCapWords) {
+        streamp[1] += 1U;  // no room: the dump is dropped, prev keeps the last RECORDED values
+        return;
+    }
+    streamp[used++] = VLCU_TRACE_DUMP_MARK | changed;
+    streamp[used++] = static_cast<uint32_t>(ctx.time());
+    streamp[used++] = static_cast<uint32_t>(ctx.time() >> 32);
+    for (uint32_t w = 0; w < T_Design::kTraceWords; ++w) {
+        const uint32_t v = curp[w];
+        if (first || v != prevp[w]) {
+            streamp[used++] = w;
+            streamp[used++] = v;
+            prevp[w] = v;
+        }
+    }
+    streamp[0] = used;
+    streamp[2] += 1U;
+}
+
 // The cycle loop: nEvals x { testbench drive; eval_step; observe }
 // kObserve = false is the throughput form: no per-eval output capture, no waveform sampling,
 // no stop-on-finish test -- the loop body is drive + eval_step + signature only, with a 32-bit
@@ -143,7 +177,9 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
                 T_Design::store_outputs_row(root, r.obs + e * T_Design::kOutWords * r.npad, r.npad,
                                             inst);
             }
-            if (slot >= 0 && e < r.traceEvals) {
+            if (slot >= 0 && e < r.traceEvals && (r.flags & VLCU_RUN_TRACE_CHANGES)) {
+                vlcu_trace_changes<T_Design>(&root, ctx, r, static_cast<uint32_t>(slot));
+            } else if (slot >= 0 && e < r.traceEvals) {
                 constexpr uint64_t kRecBytes
                     = VLCU_TRACE_HDR + T_Design::kStateBytes + 4ULL * VLCU_TRACE_WORDS_PADDED(T_Design::kTraceWords);
                 uint8_t* const recp = r.trace + (e * r.nSamples + slot) * kRecBytes;

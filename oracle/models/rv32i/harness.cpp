@@ -19,6 +19,7 @@
 #else
 #include "Vrv32_soc.h"
 #include "Vrv32_soc___024root.h"
+#include "verilated_save.h"
 #endif
 #include "verilated_vcd_c.h"
 #include "ref_timing.h"
@@ -195,6 +196,68 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
 #ifdef RV32_COV
 extern "C" int vlref_rv32cov_bins() { return kCovBins; }
 #else
+// Save / restore through the reference's own verilated_save (the model is built --savable):
+// one instance, either constructed like instance `globalIndex` of vlref_rv32_run or restored
+// from `restorePath`; runs nEvals more evals of the TbRv32Rand stimulus (resetn by time) and
+// optionally saves the model after the last one.
+extern "C" int vlref_rv32_saverun(uint64_t globalIndex, uint64_t seedBase, int randReset,
+                                  uint64_t tbSeed, uint32_t resetTime, const char* restorePath,
+                                  uint64_t nEvals, const char* savePath, uint32_t* finalRegs,
+                                  uint32_t* finalScalars, uint32_t* finalMem, uint64_t* timeOut) {
+    const std::unique_ptr<VerilatedContext> contextp{new VerilatedContext};
+    Verilated::threadContextp(contextp.get());
+    contextp->randReset(randReset);
+    contextp->randSeed(static_cast<int>(seedBase ^ globalIndex));
+    const char* argv[] = {"oracle"};
+    contextp->commandArgs(1, argv);
+    const std::unique_ptr<Vrv32_soc> top{new Vrv32_soc{contextp.get(), "TOP"}};
+    if (restorePath) {
+        VerilatedRestore os;
+        os.open(restorePath);
+        os >> *top;
+        os.close();
+    } else {
+        top->clk = 0;
+        top->resetn = 0;
+        rv32_gen_program(top->rootp->rv32_soc__DOT__mem, tbSeed ^ globalIndex);
+    }
+    const uint64_t resetAt = resetTime ? resetTime : 16;
+    for (uint64_t e = 0; e < nEvals; ++e) {
+        contextp->timeInc(1);
+        top->clk = !top->clk;
+        top->resetn = contextp->time() > resetAt;
+        top->eval();
+    }
+    if (savePath) {
+        VerilatedSave os;
+        os.open(savePath);
+        os << *top;
+        os.close();
+    }
+    const Vrv32_soc___024root& r = *top->rootp;
+    if (finalRegs) {
+        for (int k = 0; k < 32; ++k) finalRegs[k] = r.rv32_soc__DOT__regs[k];
+    }
+    if (finalMem) {
+        for (int k = 0; k < 1024; ++k) finalMem[k] = r.rv32_soc__DOT__mem[k];
+    }
+    if (finalScalars) {
+        uint32_t* const s = finalScalars;
+        s[0] = r.rv32_soc__DOT__pc, s[1] = r.rv32_soc__DOT__insn, s[2] = r.rv32_soc__DOT__ld_addr;
+        s[3] = r.rv32_soc__DOT__instret, s[4] = r.rv32_soc__DOT__state, s[5] = r.trap;
+        s[6] = r.retired, s[7] = r.clk;
+    }
+    if (timeOut) *timeOut = contextp->time();
+    return 0;
+}
+// The serialized part of a freshly constructed VerilatedContext (verilated.h:402-441,777-778)
+extern "C" int vlref_context_image(void* out, size_t outBytes) {
+    VerilatedContext context;
+    const size_t n = VerilatedContext::serialized1Size();
+    if (outBytes < n) return -1;
+    std::memcpy(out, context.serialized1Ptr(), n);
+    return static_cast<int>(n);
+}
 // The program generator alone (for the instruction-set-simulator cross check)
 extern "C" void vlref_rv32_gen_program(uint64_t seed, uint32_t* out1024) {
     VlUnpacked<IData, 1024> mem;

@@ -44,6 +44,7 @@
 #include <fstream>
 #include <map>
 #include <set>
+#include <sstream>
 
 VL_DEFINE_DEBUG_FUNCTIONS;
 
@@ -313,6 +314,9 @@ class EmitCudaModel final : public EmitCFunc {
     }
     CudaMember m_pendingCoverage;
     uint32_t m_touchedRead = 0, m_touchedWrite = 0;
+    uint32_t m_nSaveOrder = 0;
+    uint64_t m_saveCheckval = 0;
+    string m_saveUnsupported;
 
     // ---- model struct ------------------------------------------------------------
     static string handleDecl(const CudaMember& m) {
@@ -1010,6 +1014,34 @@ class EmitCudaModel final : public EmitCFunc {
         puts("static const uint32_t traceOrder[] = {");
         for (const uint32_t code : m_traceOrder) puts(cvtToStr(code) + ", ");
         puts("0};  // codes in dump order (+ terminator)\n");
+        // verilated_save image: the members EmitCImp::emitSavableImp (V3EmitCImp.cpp:277-350)
+        // would serialize, in its order, and its structure checksum
+        {
+            VHashSha256 hash;
+            string unsupported;
+            puts("static const uint32_t saveOrder[] = {");
+            for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                const AstVar* const varp = VN_CAST(nodep, Var);
+                if (!varp) continue;
+                hash.insert(varp->name());
+                hash.insert(varp->dtypep()->width());
+                if (varp->isParam()) continue;
+                if (varp->isStatic() && varp->isConst()) continue;
+                if (VN_IS(varp->dtypep(), NBACommitQueueDType)) continue;
+                const AstBasicDType* const basicp = varp->dtypeSkipRefp()->basicp();
+                if (basicp && basicp->keyword().isMTaskState()) continue;
+                const auto it = m_memberOf.find(varp);
+                if (it == m_memberOf.end()) {
+                    if (unsupported.empty()) unsupported = varp->name();
+                    continue;
+                }
+                puts(cvtToStr(it->second) + ", ");
+                ++m_nSaveOrder;
+            }
+            puts("0};  // (+ terminator)\n");
+            m_saveCheckval = hash.digestUInt64();
+            m_saveUnsupported = unsupported;
+        }
         puts("static const VlcuDesignInfo s = {\n");
         puts("VLCU_DESIGN_NAME, " + quoted(topName) + ", members, sizeof(members) / sizeof(members[0]),\n");
         puts("T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, "
@@ -1021,9 +1053,22 @@ class EmitCudaModel final : public EmitCFunc {
             puts("nullptr, 0, 0, 0,\n");
         }
         puts("messages, " + cvtToStr(m_messages.size()) + ", plusargs, " + cvtToStr(m_plusargs.size()) + ",\n");
-        puts(m_traceRows.empty() ? "nullptr, 0, 0, nullptr, 0};\n"
+        puts(m_traceRows.empty() ? "nullptr, 0, 0, nullptr, 0,\n"
                                  : "traceDecls, " + cvtToStr(m_traceRows.size()) + ", T::kTraceWords, traceOrder, "
-                                       + cvtToStr(m_traceOrder.size()) + "};\n");
+                                       + cvtToStr(m_traceOrder.size()) + ",\n");
+        {
+            std::ostringstream os;
+            os << "saveOrder, " << m_nSaveOrder << ", " << (v3Global.opt.trace() ? "VLCU_SAVE_ACTIVITY" : "0")
+               << ", 0x" << std::hex << m_saveCheckval << "ULL, "
+               << (m_saveUnsupported.empty() ? string{"nullptr"} : quoted(m_saveUnsupported)) << ", " << std::dec
+               << (v3Global.rootp()->timeunit().isNone() ? -1 : std::abs(v3Global.rootp()->timeunit().powerOfTen()))
+               << ", "
+               << (v3Global.rootp()->timeprecision().isNone()
+                       ? -1
+                       : std::abs(v3Global.rootp()->timeprecision().powerOfTen()))
+               << "};\n";
+            puts(os.str());
+        }
         puts("return s;\n}\n");
     }
 

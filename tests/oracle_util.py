@@ -104,6 +104,10 @@ def _rv32():
         lib.vlref_rv32cov_bins.restype = i32
         lib.vlref_rv32_gen_program.restype = None
         lib.vlref_rv32_gen_program.argtypes = [u64, vp]
+        lib.vlref_rv32_saverun.restype = i32
+        lib.vlref_rv32_saverun.argtypes = [u64, u64, i32, u64, u32, cp, u64, cp, vp, vp, vp, vp]
+        lib.vlref_context_image.restype = i32
+        lib.vlref_context_image.argtypes = [vp, ctypes.c_size_t]
         lib._rv32_ready = True
     return lib
 
@@ -147,6 +151,29 @@ def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_tim
     if not obs_evals:
         r.obs = None
     return r
+
+
+def rv32_saverun(index, n_evals, seed=1, rand_reset=2, tb_seed=0, reset_time=0, restore_path=None,
+                 save_path=None):
+    """One genuine (--savable) model: constructed like global instance `index` or restored from a
+    verilated_save image, run for n_evals evals, optionally saved.  Returns regs, scalars, mem, time."""
+    regs = np.zeros(32, dtype=np.uint32)
+    scalars = np.zeros(8, dtype=np.uint32)
+    mem = np.zeros(1024, dtype=np.uint32)
+    t = np.zeros(1, dtype=np.uint64)
+    rc = _rv32().vlref_rv32_saverun(index, seed, rand_reset, tb_seed, reset_time,
+                                    restore_path.encode() if restore_path else None, n_evals,
+                                    save_path.encode() if save_path else None, regs.ctypes.data,
+                                    scalars.ctypes.data, mem.ctypes.data, t.ctypes.data)
+    assert rc == 0
+    return regs, scalars, mem, int(t[0])
+
+
+def context_image():
+    buf = np.zeros(512, dtype=np.uint8)
+    n = _rv32().vlref_context_image(buf.ctypes.data, buf.size)
+    assert n > 0
+    return buf[:n].copy()
 
 
 # ---- wide_bus (oracle/models/wide_bus) ---------------------------------------------------

@@ -19,7 +19,7 @@ CASES = [  # (committed model, top-level source, extra flags)
     ("make_tracing_c/Vtop_nocov__cuda.cu", f"{REF}/examples/make_tracing_c/top.v",
      ["--trace-vcd", "--assert", "--prefix", "Vtop_nocov", "-y", f"{REF}/examples/make_tracing_c"]),
     ("rv32i/Vrv32_soc__cuda.cu", "../verilator_b200/csrc/designs/rv32i/rv32_soc.v",
-     ["--trace-vcd", "--prefix", "Vrv32_soc"]),
+     ["--trace-vcd", "--savable", "--prefix", "Vrv32_soc"]),
     ("wide_bus/Vwide_bus__cuda.cu", "../verilator_b200/csrc/designs/wide_bus/wide_bus.v",
      ["--trace-vcd", "--prefix", "Vwide_bus"]),
 ]

@@ -250,6 +250,16 @@ def test_vcd_of_sampled_instances_equals_the_reference_writer(abi, tmp_path, sto
             ours, want = open(our_path).read(), open(ref_path).read()
             assert want.count("\n#") > 10 and "$var wire 70" in want
             assert ours == want, (inst, ours[:600], want[:600])
+        # N2: the same waveforms from on-device change detection (only changes leave the device)
+        m.reset()
+        cap = 4 + evals * (3 + 2 * 15)
+        _, streams = m.run("sim_main", evals, flags=flags, tb_seed=77, tb_flags=1, tb_arg=(period, 0, 0, 0),
+                           samples=samples, trace_evals=evals, trace_stream_words=cap)
+        assert (streams[:, 1] == 0).all() and (streams[:, 0] * 4 < trace[:, 0].nbytes // 3).all()
+        for k, inst in enumerate(samples):
+            chg_path = str(tmp_path / f"chg{inst}.vcd")
+            m.vcd_write_changes(streams, k, chg_path)
+            assert open(chg_path).read() == open(str(tmp_path / f"ref{inst}.vcd")).read(), inst
 
 
 def test_x_initial_unique_reset_values(abi):

@@ -212,6 +212,25 @@ def test_vcd_of_sampled_cores_equals_the_reference_writer(abi, tmp_path):
             ours, want = open(our_path).read(), open(ref_path).read()
             assert "regs[31] [31:0]" in want and want.count("\n#") > evals // 2
             assert ours == want, (inst, ours[:800], want[:800])
+        # N2: on-device change detection.  Full records carry 4.3 KB of state + 88 trace words per
+        # eval; the change stream a few words per eval
+        m.reset()
+        cap = 4 + evals * (3 + 2 * 88)
+        _, streams = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=5, samples=samples,
+                           trace_evals=evals, trace_stream_words=cap)
+        assert (streams[:, 1] == 0).all() and (streams[:, 2] == evals).all()
+        assert streams[:, 0].max() * 4 * 8 < trace[:, 0].nbytes
+        for k, inst in enumerate(samples):
+            chg_path = str(tmp_path / f"chg{inst}.vcd")
+            m.vcd_write_changes(streams, k, chg_path)
+            assert open(chg_path).read() == open(str(tmp_path / f"ref{inst}.vcd")).read(), inst
+        # a stream too small for the run: dumps are dropped, counted, and the writer refuses
+        m.reset()
+        _, small = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=5, samples=samples,
+                         trace_evals=evals, trace_stream_words=600)
+        assert (small[:, 1] > 0).all() and (small[:, 0] <= 600).all()
+        with pytest.raises(RuntimeError, match="overflow"):
+            m.vcd_write_changes(small, 0, str(tmp_path / "small.vcd"))
 
 
 def test_full_batch_signatures_sample_against_oracle(abi):

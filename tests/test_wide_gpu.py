@@ -58,6 +58,14 @@ def test_vcd_equals_the_reference_writer(abi, tmp_path):
             ours, want = open(our_path).read(), open(ref_path).read()
             assert "$var wire 256" in want
             assert ours == want, (inst, ours[:600], want[:600])
+        m.reset()
+        _, streams = m.run("wide_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=8, samples=samples,
+                           trace_evals=evals, trace_stream_words=4 + evals * (3 + 2 * 102))
+        assert (streams[:, 1] == 0).all()
+        for k, inst in enumerate(samples):
+            chg_path = str(tmp_path / f"chg{inst}.vcd")
+            m.vcd_write_changes(streams, k, chg_path)
+            assert open(chg_path).read() == open(str(tmp_path / f"ref{inst}.vcd")).read(), inst
 
 
 def test_full_batch_sampled_against_the_genuine_model(abi):

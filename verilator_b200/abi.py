@@ -36,7 +36,7 @@ class PortInfo(ctypes.Structure):
 class RunDesc(ctypes.Structure):
     _fields_ = [("tb", c_cp), ("n_evals", c_u64), ("flags", c_u32), ("pad_", c_u32),
                 ("stim", c_vp), ("obs", c_vp), ("obs_evals", c_u64),
-                ("sample_instances", c_vp), ("n_samples", c_u32), ("pad2_", c_u32),
+                ("sample_instances", c_vp), ("n_samples", c_u32), ("trace_stream_words", c_u32),
                 ("trace_out", c_vp), ("trace_evals", c_u64),
                 ("tb_seed", c_u64), ("tb_flags", c_u32), ("tb_arg", c_u32 * 4), ("pad3_", c_u32)]
 
@@ -52,6 +52,7 @@ MSG_DTYPE = np.dtype([("time", "<u8"), ("id", "<u4"), ("nargs", "<u4"), ("args",
 DIR_IN, DIR_OUT, DIR_INOUT = 0, 1, 2
 RUNF_NO_STREAM = 0x20
 RUNF_BULK_1D = 0x40
+RUNF_TRACE_CHANGES = 0x80
 RUNF_TB_BEGIN, RUNF_STOP_ON_FINISH, RUNF_STIM_DEVICE, RUNF_OBS_DEVICE, RUNF_STIM_BROADCAST = (
     1, 2, 4, 8, 16)
 ST_DIDINIT, ST_FINISH, ST_ERROR, ST_STOPPED, ST_FATAL, ST_MSGDROP = 1, 2, 4, 8, 16, 32
@@ -113,6 +114,9 @@ SIGNATURES = {
     "vlcu_messages": (c_i32, [_H, c_u64, c_vp, c_u32, ctypes.POINTER(c_u32)]),
     "vlcu_message_format": (c_cp, [_H, c_u32]),
     "vlcu_snapshot": (c_i32, [_H, c_u64, c_vp, ctypes.c_size_t]),
+    "vlcu_save_instance": (c_i32, [_H, c_u64, c_cp]),
+    "vlcu_restore_instance": (c_i32, [_H, c_u64, c_cp]),
+    "vlcu_save_context_image": (c_i32, [c_vp, ctypes.c_size_t]),
     "vlcu_coverage_bins": (c_u32, [_H]),
     "vlcu_coverage_points": (c_u32, [_H]),
     "vlcu_coverage_point": (c_i32, [_H, c_u32, ctypes.POINTER(c_u32), ctypes.POINTER(c_cp), ctypes.POINTER(c_i32),
@@ -122,6 +126,7 @@ SIGNATURES = {
     "vlcu_coverage_reduce": (c_i32, [_H, c_vp]),
     "vlcu_coverage_write": (c_i32, [_H, c_vp, c_cp]),
     "vlcu_vcd_write": (c_i32, [_H, c_vp, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_cp]),
+    "vlcu_vcd_write_changes": (c_i32, [_H, c_vp, c_u32, c_u32, c_u32, c_cp]),
     "vlcu_comm_unique_id": (c_i32, [c_vp]),
     "vlcu_comm_init": (c_i32, [_H, c_vp, c_i32, c_i32]),
     "vlcu_comm_destroy": (c_i32, [_H]),
@@ -250,9 +255,10 @@ class Model:
         _check(lib.vlcu_eval(self.h))
 
     def run(self, tb, n_evals, flags=0, stim=None, obs_evals=0, samples=None, trace_evals=0,
-            tb_seed=0, tb_flags=0, tb_arg=(0, 0, 0, 0)):
+            tb_seed=0, tb_flags=0, tb_arg=(0, 0, 0, 0), trace_stream_words=0):
         """Returns (obs, trace): obs is uint32 [obs_evals][out_words][n] or None; trace is a
-        uint8 array [trace_evals][n_samples][record_bytes] or None."""
+        uint8 array [trace_evals][n_samples][record_bytes] or None -- or, with
+        trace_stream_words, the uint32 change streams [n_samples][trace_stream_words]."""
         d = RunDesc()
         d.tb = tb.encode()
         d.n_evals = n_evals
@@ -272,7 +278,12 @@ class Model:
             samples = np.ascontiguousarray(samples, dtype=np.uint64)
             keep.append(samples)
             rec = lib.vlcu_trace_record_bytes(self.h)
-            trace = np.zeros((trace_evals, len(samples), rec), dtype=np.uint8)
+            if trace_stream_words:
+                trace = np.zeros((len(samples), trace_stream_words), dtype=np.uint32)
+                d.flags |= RUNF_TRACE_CHANGES
+                d.trace_stream_words = trace_stream_words
+            else:
+                trace = np.zeros((trace_evals, len(samples), rec), dtype=np.uint8)
             d.sample_instances = samples.ctypes.data
             d.n_samples = len(samples)
             d.trace_out = trace.ctypes.data
@@ -369,6 +380,13 @@ class Model:
         _check(lib.vlcu_snapshot(self.h, instance, out.ctypes.data, out.nbytes))
         return out
 
+    def save_instance(self, instance, filename):
+        """Write instance `instance` as a verilated_save image a --savable C++ model can restore."""
+        _check(lib.vlcu_save_instance(self.h, instance, filename.encode()))
+
+    def restore_instance(self, instance, filename):
+        _check(lib.vlcu_restore_instance(self.h, instance, filename.encode()))
+
     def record_member(self, record, name):
         """Extract one member from a packed state record (snapshot or trace sample body)."""
         _, _, _, eb, elems, off = self.members[name]
@@ -389,6 +407,12 @@ class Model:
         trace = np.ascontiguousarray(trace, dtype=np.uint8)
         _check(lib.vlcu_vcd_write(self.h, trace.ctypes.data, trace.shape[0], trace.shape[1], sample,
                                   filename.encode()))
+
+    def vcd_write_changes(self, streams, sample, filename):
+        """streams: the uint32 [n_samples][trace_stream_words] array run(trace_stream_words=) returned."""
+        streams = np.ascontiguousarray(streams, dtype=np.uint32)
+        _check(lib.vlcu_vcd_write_changes(self.h, streams.ctypes.data, streams.shape[1], streams.shape[0],
+                                          sample, filename.encode()))
 
     def coverage_write(self, counts, filename):
         counts = np.ascontiguousarray(counts, dtype=np.uint64)

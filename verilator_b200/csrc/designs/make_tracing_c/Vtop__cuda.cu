@@ -1125,12 +1125,14 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0, 1, 2, 3, 5, 8, 9, 11, 14, 0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 4, 7, 23, 24, 25, 26, 27, 28, 29, 30, 3, 6, 31, 32, 33, 34, 35, 36, 37, 38, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "top", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         t.points.data(), static_cast<uint32_t>(t.points.size()), 543, T::OFF___Vcoverage,
         messages, 4, plusargs, 1,
-        traceDecls, 25, T::kTraceWords, traceOrder, 9};
+        traceDecls, 25, T::kTraceWords, traceOrder, 9,
+        saveOrder, 39, VLCU_SAVE_ACTIVITY, 0x63e469006938c01ULL, nullptr, 12, 12};
     return s;
 }
 

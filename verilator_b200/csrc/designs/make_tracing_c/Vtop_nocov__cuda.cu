@@ -732,12 +732,14 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0, 1, 2, 3, 5, 8, 9, 11, 14, 0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 4, 7, 18, 19, 20, 3, 6, 21, 22, 23, 24, 25, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "top", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 1,
-        traceDecls, 25, T::kTraceWords, traceOrder, 9};
+        traceDecls, 25, T::kTraceWords, traceOrder, 9,
+        saveOrder, 26, VLCU_SAVE_ACTIVITY, 0xa090add8b4f5237eULL, nullptr, 12, 12};
     return s;
 }
 

@@ -2239,12 +2239,14 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 7, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 5, 6, 8, 9, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "rv32_soc", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        traceDecls, 105, T::kTraceWords, traceOrder, 88};
+        traceDecls, 105, T::kTraceWords, traceOrder, 88,
+        saveOrder, 51, VLCU_SAVE_ACTIVITY, 0xe66f28a6807d2675ULL, nullptr, 12, 12};
     return s;
 }
 

@@ -1090,12 +1090,14 @@ const VlcuDesignInfo& Vt01_alu__cuda::info() {
     static const VlcuTraceDecl traceDecls[] = {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 8, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 3, 9, 23, 4, 5, 10, 24, 25, 26, 27, 6, 7, 11, 28, 29, 30, 31, 32, 33, 34, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "t01_alu", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        nullptr, 0, 0, nullptr, 0};
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 35, 0, 0x7c8d40b046c830b9ULL, nullptr, 12, 12};
     return s;
 }
 

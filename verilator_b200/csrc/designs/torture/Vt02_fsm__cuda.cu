@@ -711,12 +711,14 @@ const VlcuDesignInfo& Vt02_fsm__cuda::info() {
     static const VlcuTraceDecl traceDecls[] = {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 8, 21, 22, 23, 24, 25, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "t02_fsm", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        nullptr, 0, 0, nullptr, 0};
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 26, 0, 0x3b73d8ee909aca3fULL, nullptr, 12, 12};
     return s;
 }
 

@@ -744,12 +744,14 @@ const VlcuDesignInfo& Vt05_wide__cuda::info() {
     static const VlcuTraceDecl traceDecls[] = {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 4, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 1, 2, 3, 5, 6, 8, 18, 19, 20, 21, 22, 23, 24, 25, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "Vt05_wide", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        nullptr, 0, 0, nullptr, 0};
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 26, 0, 0x553002b1b73e24f0ULL, nullptr, 12, 12};
     return s;
 }
 

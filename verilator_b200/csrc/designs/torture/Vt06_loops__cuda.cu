@@ -703,12 +703,14 @@ const VlcuDesignInfo& Vt06_loops__cuda::info() {
     static const VlcuTraceDecl traceDecls[] = {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 4, 7, 8, 9, 10, 11, 2, 3, 5, 6, 12, 13, 14, 15, 16, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "t06_loops", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        nullptr, 0, 0, nullptr, 0};
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 17, 0, 0x63e44c3fb0276468ULL, nullptr, 12, 12};
     return s;
 }
 

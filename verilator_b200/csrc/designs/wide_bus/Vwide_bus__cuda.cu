@@ -1119,12 +1119,14 @@ const VlcuDesignInfo& Vwide_bus__cuda::info() {
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0},
         {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
     static const uint32_t traceOrder[] = {0, 1, 5, 13, 21, 22, 23, 31, 39, 47, 55, 63, 67, 75, 83, 84, 85, 86, 87, 88, 96, 97, 98, 99, 0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 6, 7, 8, 13, 14, 15, 16, 17, 18, 19, 20, 9, 5, 10, 11, 12, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 0};  // (+ terminator)
     static const VlcuDesignInfo s = {
         VLCU_DESIGN_NAME, "wide_bus", members, sizeof(members) / sizeof(members[0]),
         T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
-        traceDecls, 45, T::kTraceWords, traceOrder, 24};
+        traceDecls, 45, T::kTraceWords, traceOrder, 24,
+        saveOrder, 32, VLCU_SAVE_ACTIVITY, 0x2819d23c62a96db6ULL, nullptr, 12, 12};
     return s;
 }
 

@@ -28,6 +28,8 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
+#include <iterator>
 #include <map>
 #include <sstream>
 #include <string>
@@ -222,6 +224,24 @@ __global__ void k_snapshot(uint8_t* __restrict__ dst, const uint8_t* __restrict_
             const uint64_t src = instMajor ? ((inst * elems + e) * eb + byte)
                                            : ((e * npad + inst) * eb + byte);
             dst[off + b] = basep[src];
+        }
+    }
+}
+
+// The inverse: one instance's packed record back into the SoA block
+__global__ void k_restore(uint8_t* __restrict__ state, const uint8_t* __restrict__ src, uint64_t npad,
+                          uint64_t inst, const uint32_t* __restrict__ table, uint32_t nMembers) {
+    // table: per member {soaOffset, elemBytes, elems, instanceMajor | skip << 1}
+    for (uint32_t m = blockIdx.x; m < nMembers; m += gridDim.x) {
+        const uint32_t off = table[m * 4 + 0], eb = table[m * 4 + 1], elems = table[m * 4 + 2];
+        const bool instMajor = (table[m * 4 + 3] & 1U) != 0;
+        if (table[m * 4 + 3] & 2U) continue;  // member not part of the image
+        uint8_t* const basep = state + static_cast<uint64_t>(off) * npad;
+        for (uint64_t b = threadIdx.x; b < static_cast<uint64_t>(eb) * elems; b += blockDim.x) {
+            const uint64_t e = b / eb, byte = b % eb;
+            const uint64_t dst = instMajor ? ((inst * elems + e) * eb + byte)
+                                           : ((e * npad + inst) * eb + byte);
+            basep[dst] = src[off + b];
         }
     }
 }
@@ -910,7 +930,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     VlcuRunDev r{};
     r.nEvals = d->n_evals;
     r.flags = d->flags & (VLCU_RUNF_TB_BEGIN | VLCU_RUNF_STOP_ON_FINISH | VLCU_RUNF_NO_STREAM
-                          | VLCU_RUNF_BULK_1D);
+                          | VLCU_RUNF_BULK_1D | VLCU_RUNF_TRACE_CHANGES);
     r.stimBroadcast = (d->flags & VLCU_RUNF_STIM_BROADCAST) ? 1 : 0;
     r.tbSeed = d->tb_seed;
     r.tbFlags = d->tb_flags;
@@ -920,11 +940,13 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     uint32_t* dObs = nullptr;
     uint8_t* dTrace = nullptr;
     uint64_t* dSamples = nullptr;
+    uint32_t* dScratch = nullptr;
     const auto cleanup = [&]() {
         cudaFree(dStim);
         cudaFree(dObs);
         cudaFree(dTrace);
         cudaFree(dSamples);
+        cudaFree(dScratch);
     };
 #define RUN_TRY(expr) \
     do { \
@@ -979,8 +1001,27 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
         }
         r.nSamples = d->n_samples;
         r.traceEvals = d->trace_evals < d->n_evals ? d->trace_evals : d->n_evals;
-        traceBytes = static_cast<size_t>(VLCU_TRACE_HDR + info.stateBytes + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords)) * r.nSamples
-                     * r.traceEvals;
+        if (d->flags & VLCU_RUNF_TRACE_CHANGES) {
+            if (!info.traceWords) {
+                cleanup();
+                return fail(VLCU_E_STATE, "vlcu_run: design was not Verilated with --trace");
+            }
+            if (d->trace_stream_words < VLCU_TRACE_STREAM_HDR + 3U + 2U * info.traceWords) {
+                cleanup();
+                return fail(VLCU_E_ARG, "vlcu_run: trace_stream_words cannot hold even the first dump");
+            }
+            r.traceCapWords = d->trace_stream_words;
+            traceBytes = sizeof(uint32_t) * r.traceCapWords * r.nSamples;
+            const size_t scratchBytes
+                = sizeof(uint32_t) * 2U * VLCU_TRACE_WORDS_PADDED(info.traceWords) * r.nSamples;
+            RUN_TRY(cudaMalloc(&dScratch, scratchBytes));
+            RUN_TRY(cudaMemsetAsync(dScratch, 0, scratchBytes, h->stream));
+            r.traceScratch = dScratch;
+        } else {
+            traceBytes = static_cast<size_t>(VLCU_TRACE_HDR + info.stateBytes
+                                             + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords))
+                         * r.nSamples * r.traceEvals;
+        }
         RUN_TRY(cudaMalloc(&dTrace, traceBytes));
         RUN_TRY(cudaMemsetAsync(dTrace, 0, traceBytes, h->stream));
         RUN_TRY(cudaMalloc(&dSamples, sizeof(uint64_t) * r.nSamples));
@@ -1114,6 +1155,233 @@ int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_byte
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, h->dStage, info.stateBytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+
+
+//-------------------------------------------------------------------------
+// verilated_save images
+//
+// One instance's state in the format VerilatedSave writes for `os << *top` of a --savable build
+// of the same design (include/verilated_save.cpp:56-58,87-120,256-270; V3EmitCSyms.cpp:1564-1582;
+// V3EmitCImp.cpp:277-350), so that a failing instance of a GPU campaign can be loaded into the
+// ordinary C++ model (`VerilatedRestore os; os.open(f); os >> *top;`) and replayed under a
+// debugger -- and the other way round.
+//
+//   "verilatorsave02\n"
+//   [bool __Vm_activity]            (--trace builds)
+//   bool  __Vm_didInit
+//   u64   __Vcheckval               structure checksum of the module's variables
+//   VerilatedContext::Serialized    raw struct bytes (layout restated below)
+//   u32 len + bytes                 timeFormatSuffix
+//   u32 len + bytes                 dumpfile
+//   members in __Vserialize order   1/2/4/8-byte scalars, arrays element by element, wide values
+//                                   word by word
+//   "vltsaved"
+
+// VerilatedContext::Serialized of this reference revision (include/verilated.h:402-441) as the
+// x86-64 ABI lays it out: 160 bytes.  kCtxDefault is the image of a freshly constructed context
+// (tests/test_save.py compares it, and every offset below, with the genuine runtime).
+enum : size_t {
+    CTXS_SIZE = 160,
+    CTXS_TIME = 0,  // uint64_t m_time
+    CTXS_ASSERT_ON = 8,  // uint32 m_assertOn, m_assertLock, m_assertPassOnVacuous, ..NonVacuous, m_assertFailOn
+    CTXS_ASSERT_KILL = 28,  // uint32 m_assertKill[24]
+    CTXS_CALC_UNUSED = 124,  // bool x6: m_calcUnusedSigs, m_fatalOnError, m_fatalOnVpiError,
+    CTXS_FATAL_ON_ERROR = 125,  //          m_gotError, m_gotFinish, m_quiet
+    CTXS_FATAL_ON_VPI_ERROR = 126,
+    CTXS_GOT_ERROR = 127,
+    CTXS_GOT_FINISH = 128,
+    CTXS_QUIET = 129,
+    CTXS_TIMEUNIT = 130,  // int8 m_timeunit, m_timeprecision
+    CTXS_TIMEPRECISION = 131,
+    CTXS_ERROR_COUNT = 132,  // int x7: m_errorCount, m_errorLimit, m_randReset, m_randSeed,
+    CTXS_ERROR_LIMIT = 136,  //         m_timeFormatUnits, m_timeFormatPrecision, m_timeFormatWidth
+    CTXS_RAND_RESET = 140,
+    CTXS_RAND_SEED = 144,
+    CTXS_TIMEFORMAT_UNITS = 148,
+    CTXS_TIMEFORMAT_PRECISION = 152,
+    CTXS_TIMEFORMAT_WIDTH = 156,
+};
+static void ctxDefaultImage(uint8_t out[CTXS_SIZE]) {
+    memset(out, 0, CTXS_SIZE);
+    const uint32_t ones = 0xffffffffU, zero = 0U;
+    memcpy(out + CTXS_ASSERT_ON + 0, &ones, 4);  // m_assertOn: everything enabled
+    memcpy(out + CTXS_ASSERT_ON + 4, &zero, 4);  // m_assertLock
+    memcpy(out + CTXS_ASSERT_ON + 8, &ones, 4);  // m_assertPassOnVacuous
+    memcpy(out + CTXS_ASSERT_ON + 12, &ones, 4);  // m_assertPassOnNonvacuous
+    memcpy(out + CTXS_ASSERT_ON + 16, &ones, 4);  // m_assertFailOn
+    out[CTXS_FATAL_ON_ERROR] = 1;
+    out[CTXS_FATAL_ON_VPI_ERROR] = 1;
+    out[CTXS_TIMEUNIT] = static_cast<uint8_t>(-12);  // picoseconds until _Vconfigure says otherwise
+    out[CTXS_TIMEPRECISION] = static_cast<uint8_t>(-12);
+    const int32_t one = 1, unitsNone = 99, width = 20;
+    memcpy(out + CTXS_ERROR_LIMIT, &one, 4);
+    memcpy(out + CTXS_RAND_SEED, &one, 4);
+    memcpy(out + CTXS_TIMEFORMAT_UNITS, &unitsNone, 4);
+    memcpy(out + CTXS_TIMEFORMAT_WIDTH, &width, 4);
+}
+static const char kSaveHeader[] = "verilatorsave02\n";
+static const char kSaveTrailer[] = "vltsaved";
+
+int vlcu_save_context_image(void* out, size_t out_bytes) {
+    if (!out || out_bytes < CTXS_SIZE) return fail(VLCU_E_ARG, "buffer too small");
+    ctxDefaultImage(static_cast<uint8_t*>(out));
+    return static_cast<int>(CTXS_SIZE);
+}
+
+static int saveCheck(const vlcu_model_t* h, uint64_t instance) {
+    if (!h || instance >= h->n) return fail(VLCU_E_ARG, "bad argument");
+    const VlcuDesignInfo& info = *h->infop;
+    if (!info.saveOrder || !info.nSaveOrder) return fail(VLCU_E_STATE, "design has no save table");
+    if (info.saveUnsupported) {
+        return fail(VLCU_E_STATE, std::string{"cannot serialize member '"} + info.saveUnsupported + "'");
+    }
+    if (info.coverBins) {
+        return fail(VLCU_E_STATE, "--savable and --coverage exclude each other (V3Options.cpp:1069)");
+    }
+    return VLCU_OK;
+}
+
+int vlcu_save_instance(vlcu_model_t* h, uint64_t instance, const char* filename) {
+    if (const int rc = saveCheck(h, instance)) return rc;
+    if (!filename) return fail(VLCU_E_ARG, "null filename");
+    const VlcuDesignInfo& info = *h->infop;
+    DeviceGuard guard{h->device};
+    std::vector<uint8_t> rec(info.stateBytes);
+    if (const int rc = vlcu_snapshot(h, instance, rec.data(), rec.size())) return rc;
+    VlcuCtxRec ctx;
+    CUDA_TRY(cudaMemcpyAsync(&ctx, h->dCtx + instance, sizeof(ctx), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    std::string out;
+    const auto put = [&out](const void* p, size_t n) { out.append(static_cast<const char*>(p), n); };
+    put(kSaveHeader, sizeof(kSaveHeader) - 1);
+    const uint8_t didInit = (ctx.status & VLCU_ST_DIDINIT) ? 1 : 0;
+    if (info.saveFlags & VLCU_SAVE_ACTIVITY) put(&didInit, 1);  // eval_step sets __Vm_activity; only a dump clears it
+    put(&didInit, 1);
+    put(&info.saveCheckval, 8);
+    uint8_t cimg[CTXS_SIZE];
+    ctxDefaultImage(cimg);
+    memcpy(cimg + CTXS_TIME, &ctx.time, 8);
+    if (info.saveTimeunit >= 0) cimg[CTXS_TIMEUNIT] = static_cast<uint8_t>(info.saveTimeunit);
+    if (info.saveTimeprecision >= 0) cimg[CTXS_TIMEPRECISION] = static_cast<uint8_t>(info.saveTimeprecision);
+    cimg[CTXS_GOT_ERROR] = (ctx.status & VLCU_ST_ERROR) ? 1 : 0;
+    cimg[CTXS_GOT_FINISH] = (ctx.status & VLCU_ST_FINISH) ? 1 : 0;
+    const int32_t errorCount = static_cast<int32_t>(ctx.errorCount);
+    const int32_t errorLimit = static_cast<int32_t>(h->dev.errorLimit);
+    const int32_t randReset = static_cast<int32_t>(h->dev.randReset);
+    const int32_t randSeed = static_cast<int32_t>(h->dev.seedBase ^ (h->dev.instBase + instance));
+    memcpy(cimg + CTXS_ERROR_COUNT, &errorCount, 4);
+    memcpy(cimg + CTXS_ERROR_LIMIT, &errorLimit, 4);
+    memcpy(cimg + CTXS_RAND_RESET, &randReset, 4);
+    memcpy(cimg + CTXS_RAND_SEED, &randSeed, 4);
+    put(cimg, CTXS_SIZE);
+    const uint32_t emptyLen = 0;
+    put(&emptyLen, 4);  // timeFormatSuffix ""
+    put(&emptyLen, 4);  // dumpfile ""
+    for (uint32_t k = 0; k < info.nSaveOrder; ++k) {
+        const VlcuMemberDesc& md = info.members[info.saveOrder[k]];
+        put(rec.data() + md.soaOffset, static_cast<size_t>(md.elemBytes) * md.elems);
+    }
+    put(kSaveTrailer, sizeof(kSaveTrailer) - 1);
+    std::ofstream os{filename, std::ios::binary};
+    if (os.fail()) return fail(VLCU_E_IO, std::string{"Can't write '"} + filename + "'");
+    os << out;
+    return os.good() ? VLCU_OK : fail(VLCU_E_IO, "write failed");
+}
+
+int vlcu_restore_instance(vlcu_model_t* h, uint64_t instance, const char* filename) {
+    if (const int rc = saveCheck(h, instance)) return rc;
+    if (!filename) return fail(VLCU_E_ARG, "null filename");
+    const VlcuDesignInfo& info = *h->infop;
+    std::ifstream is{filename, std::ios::binary};
+    if (is.fail()) return fail(VLCU_E_IO, std::string{"Can't read '"} + filename + "'");
+    const std::string in{std::istreambuf_iterator<char>{is}, std::istreambuf_iterator<char>{}};
+    size_t pos = 0;
+    bool short_ = false;
+    const auto get = [&](void* p, size_t n) {
+        if (pos + n > in.size()) {
+            short_ = true;
+            memset(p, 0, n);
+            return;
+        }
+        memcpy(p, in.data() + pos, n);
+        pos += n;
+    };
+    char hdr[sizeof(kSaveHeader) - 1];
+    get(hdr, sizeof(hdr));
+    if (short_ || memcmp(hdr, kSaveHeader, sizeof(hdr))) {
+        return fail(VLCU_E_IO, "Can't deserialize; file has wrong header signature");
+    }
+    uint8_t activity = 0, didInit = 0;
+    if (info.saveFlags & VLCU_SAVE_ACTIVITY) get(&activity, 1);
+    get(&didInit, 1);
+    uint64_t checkval = 0;
+    get(&checkval, 8);
+    if (short_ || checkval != info.saveCheckval) {
+        return fail(VLCU_E_STATE, "Can't deserialize; the save file is of a different model (checksum)");
+    }
+    uint8_t cimg[CTXS_SIZE];
+    get(cimg, CTXS_SIZE);
+    for (int k = 0; k < 2; ++k) {  // timeFormatSuffix, dumpfile
+        uint32_t len = 0;
+        get(&len, 4);
+        if (pos + len > in.size()) short_ = true;
+        pos += len;
+    }
+    std::vector<uint8_t> rec(info.stateBytes, 0);
+    std::vector<uint32_t> table(info.nMembers * 4);
+    for (uint32_t m = 0; m < info.nMembers; ++m) {
+        table[m * 4 + 0] = info.members[m].soaOffset;
+        table[m * 4 + 1] = info.members[m].elemBytes;
+        table[m * 4 + 2] = info.members[m].elems;
+        table[m * 4 + 3] = (info.members[m].kind == VLCU_MEMBER_MEMORY ? 1U : 0U) | 2U;  // skipped unless listed
+    }
+    for (uint32_t k = 0; k < info.nSaveOrder && !short_; ++k) {
+        const uint32_t m = info.saveOrder[k];
+        const VlcuMemberDesc& md = info.members[m];
+        get(rec.data() + md.soaOffset, static_cast<size_t>(md.elemBytes) * md.elems);
+        table[m * 4 + 3] &= ~2U;
+    }
+    char trl[sizeof(kSaveTrailer) - 1];
+    get(trl, sizeof(trl));
+    if (short_ || memcmp(trl, kSaveTrailer, sizeof(trl)) || pos != in.size()) {
+        return fail(VLCU_E_IO, "Can't deserialize; file has wrong end-of-file signature");
+    }
+    // per-shard settings a single instance cannot change
+    int32_t randReset, randSeed;
+    memcpy(&randReset, cimg + CTXS_RAND_RESET, 4);
+    memcpy(&randSeed, cimg + CTXS_RAND_SEED, 4);
+    if (static_cast<uint32_t>(randReset) != h->dev.randReset
+        || randSeed != static_cast<int32_t>(h->dev.seedBase ^ (h->dev.instBase + instance))) {
+        return fail(VLCU_E_STATE, "the image's randReset/randSeed are not those of this instance "
+                                  "(create the model with the seed and instance base of the saved run)");
+    }
+    DeviceGuard guard{h->device};
+    const size_t tableBytes = table.size() * sizeof(uint32_t);
+    const size_t tableOff = (static_cast<size_t>(info.stateBytes) + 15) & ~size_t{15};
+    if (const int rc = ensureStage(h, tableOff + tableBytes)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->dStage, rec.data(), info.stateBytes, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->dStage + tableOff, table.data(), tableBytes, cudaMemcpyHostToDevice,
+                             h->stream));
+    k_restore<<<info.nMembers < 64 ? info.nMembers : 64, 128, 0, h->stream>>>(
+        h->dState, h->dStage, h->npad, instance, reinterpret_cast<const uint32_t*>(h->dStage + tableOff),
+        info.nMembers);
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    VlcuCtxRec ctx;
+    CUDA_TRY(cudaMemcpyAsync(&ctx, h->dCtx + instance, sizeof(ctx), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(&ctx.time, cimg + CTXS_TIME, 8);
+    int32_t errorCount;
+    memcpy(&errorCount, cimg + CTXS_ERROR_COUNT, 4);
+    ctx.errorCount = static_cast<uint32_t>(errorCount);
+    ctx.status &= ~(VLCU_ST_DIDINIT | VLCU_ST_FINISH | VLCU_ST_ERROR);
+    if (didInit) ctx.status |= VLCU_ST_DIDINIT;
+    if (cimg[CTXS_GOT_FINISH]) ctx.status |= VLCU_ST_FINISH;
+    if (cimg[CTXS_GOT_ERROR]) ctx.status |= VLCU_ST_ERROR;
+    CUDA_TRY(cudaMemcpyAsync(h->dCtx + instance, &ctx, sizeof(ctx), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return VLCU_OK;
 }
@@ -1276,9 +1544,11 @@ bool vcdProperScope(int32_t type) {
 }
 }  // namespace
 
-int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_evals,
-                   uint32_t n_samples, uint32_t sample, const char* filename) {
-    if (!h || !trace || !filename || sample >= n_samples) return fail(VLCU_E_ARG, "bad argument");
+// One dump(time) call of the sampled instance: the time and the value of every trace word.
+// Returns false when there are no more dumps.
+typedef std::function<bool(uint64_t& time, const uint32_t*& valsp)> VcdDumpSource;
+
+static int vcdWriteCore(const vlcu_model_t* h, const VcdDumpSource& nextDump, const char* filename) {
     const VlcuDesignInfo& info = *h->infop;
     if (!info.traceDecls || !info.traceWords) {
         return fail(VLCU_E_STATE, "design was not Verilated with --trace");
@@ -1337,26 +1607,20 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
     popPrefix();
     out += "$enddefinitions $end\n\n\n";
 
-    const size_t recBytes = VLCU_TRACE_HDR + static_cast<size_t>(info.stateBytes) + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords);
-    const uint8_t* const basep = static_cast<const uint8_t*>(trace);
+    // values at the last dump that was written (a private copy: the source may reuse its buffer)
+    std::vector<uint32_t> prev(info.traceWords);
     const uint32_t* prevp = nullptr;
     uint64_t lastTime = 0;
     size_t timeBegin = std::string::npos, timeEnd = std::string::npos;
-    for (uint64_t e = 0; e < trace_evals; ++e) {
-        const uint8_t* const recp = basep + (e * n_samples + sample) * recBytes;
-        uint64_t time;
-        uint32_t valid;
-        memcpy(&time, recp, sizeof(time));
-        memcpy(&valid, recp + 12, sizeof(valid));
-        if (!valid) continue;  // the instance had stopped (stop-on-finish)
+    uint64_t time = 0;
+    const uint32_t* valsp = nullptr;
+    while (nextDump(time, valsp)) {
         if (prevp && time <= lastTime) continue;  // "dump at same time" is skipped by dump()
         // emitTimeChange: a time stamp nothing followed is overwritten
         if (timeBegin != std::string::npos && timeEnd == out.size()) out.resize(timeBegin);
         timeBegin = out.size();
         out += '#' + std::to_string(time) + '\n';
         timeEnd = out.size();
-        const uint32_t* const valsp
-            = reinterpret_cast<const uint32_t*>(recp + VLCU_TRACE_HDR + info.stateBytes);
         for (uint32_t k = 0; k < info.nTraceOrder; ++k) {
             const auto it = sigs.find(info.traceOrder[k]);
             if (it == sigs.end()) continue;
@@ -1376,13 +1640,83 @@ int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_eval
             out += sg.ident;
             out += '\n';
         }
-        prevp = valsp;
+        memcpy(prev.data(), valsp, sizeof(uint32_t) * info.traceWords);
+        prevp = prev.data();
         lastTime = time;
     }
     std::ofstream os{filename, std::ios::binary};
     if (os.fail()) return fail(VLCU_E_IO, std::string{"Can't write '"} + filename + "'");
     os << out;
     return os.good() ? VLCU_OK : fail(VLCU_E_IO, "write failed");
+}
+
+int vlcu_vcd_write(const vlcu_model_t* h, const void* trace, uint64_t trace_evals,
+                   uint32_t n_samples, uint32_t sample, const char* filename) {
+    if (!h || !trace || !filename || sample >= n_samples) return fail(VLCU_E_ARG, "bad argument");
+    const VlcuDesignInfo& info = *h->infop;
+    const size_t recBytes = VLCU_TRACE_HDR + static_cast<size_t>(info.stateBytes)
+                            + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords);
+    const uint8_t* const basep = static_cast<const uint8_t*>(trace);
+    uint64_t e = 0;
+    return vcdWriteCore(
+        h,
+        [&](uint64_t& time, const uint32_t*& valsp) {
+            for (; e < trace_evals; ++e) {
+                const uint8_t* const recp = basep + (e * n_samples + sample) * recBytes;
+                uint32_t valid;
+                memcpy(&valid, recp + 12, sizeof(valid));
+                if (!valid) continue;  // the instance had stopped (stop-on-finish)
+                memcpy(&time, recp, sizeof(time));
+                valsp = reinterpret_cast<const uint32_t*>(recp + VLCU_TRACE_HDR + info.stateBytes);
+                ++e;
+                return true;
+            }
+            return false;
+        },
+        filename);
+}
+
+int vlcu_vcd_write_changes(const vlcu_model_t* h, const uint32_t* streams, uint32_t stream_words,
+                           uint32_t n_samples, uint32_t sample, const char* filename) {
+    if (!h || !streams || !filename || sample >= n_samples || stream_words < VLCU_TRACE_STREAM_HDR) {
+        return fail(VLCU_E_ARG, "bad argument");
+    }
+    const VlcuDesignInfo& info = *h->infop;
+    const uint32_t* const sp = streams + static_cast<size_t>(sample) * stream_words;
+    const uint32_t used = sp[0] ? sp[0] : VLCU_TRACE_STREAM_HDR;
+    if (used > stream_words) return fail(VLCU_E_ARG, "corrupt trace stream: used > capacity");
+    if (sp[1]) {
+        return fail(VLCU_E_STATE, "trace stream overflowed: " + std::to_string(sp[1])
+                                      + " dump(s) dropped; give vlcu_run a larger trace_stream_words");
+    }
+    std::vector<uint32_t> vals(info.traceWords, 0U);  // running value of every trace word
+    uint32_t pos = VLCU_TRACE_STREAM_HDR;
+    bool corrupt = false;
+    const int rc = vcdWriteCore(
+        h,
+        [&](uint64_t& time, const uint32_t*& valsp) {
+            if (pos >= used) return false;
+            const uint32_t head = sp[pos];
+            const uint32_t n = head & ~VLCU_TRACE_DUMP_MARK;
+            if (!(head & VLCU_TRACE_DUMP_MARK) || pos + 3U + 2U * static_cast<uint64_t>(n) > used) {
+                corrupt = true;
+                return false;
+            }
+            time = sp[pos + 1] | (static_cast<uint64_t>(sp[pos + 2]) << 32);
+            pos += 3;
+            for (uint32_t k = 0; k < n; ++k, pos += 2) {
+                if (sp[pos] >= info.traceWords) {
+                    corrupt = true;
+                    return false;
+                }
+                vals[sp[pos]] = sp[pos + 1];
+            }
+            valsp = vals.data();
+            return true;
+        },
+        filename);
+    if (corrupt) return fail(VLCU_E_ARG, "corrupt trace stream");
+    return rc;
 }
 
 //-------------------------------------------------------------------------
