@@ -81,6 +81,14 @@ WORKLOADS = {
         note="make_tracing_c, 'trace' testbench: stimulus rows [eval][in_word][instance] (random data "
              "ports, toggling clk) resident in HBM, every output port captured after every eval into "
              "[eval][out_word][instance]; rows staged through shared memory by cp.async.bulk (TMA)"),
+    # BASELINE.json configs[2] class (VeeR-EH1 is not vendored): 16,384 instances running the SAME
+    # program, differing only in their --x-initial unique reset values (randSeed = base ^ index)
+    "x_initial": dict(
+        design="rv32i", tb="rv32_rand", instances=16384, cycles=4096, tb_flags=2,
+        tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(), same_program=True,
+        note="rv32_soc.v, one program image for all instances; instances differ only in the "
+             "x-initial unique reset values of registers and register file (VL_SCOPED_RAND_RESET_* "
+             "from randSeed = 1 ^ instance)"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -181,7 +189,8 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     if wl["design"] in ("rv32i", "rv32i_cov"):
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads, cov=wl["design"] == "rv32i_cov",
-                   rounds=1 if wl.get("fresh_program_per_step") else 0, reset_time=wl["tb_arg"][0])
+                   rounds=1 if wl.get("fresh_program_per_step") else 0, reset_time=wl["tb_arg"][0],
+                   same_program=bool(wl.get("same_program")))
     elif wl["design"] == "wide_bus":
         O.wide_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads)

@@ -63,6 +63,7 @@ struct Rv32Params {
     uint64_t* covSums;  // (RV32_COV) [bins] summed over the instances, or null
     const char* covPath;  // (RV32_COV) coverage.dat of instance covInstance
     int64_t covInstance;
+    uint32_t sameProgram;  // tb flag RV32_TBF_SAME_PROGRAM: the program seed ignores the instance index
 };
 #ifdef RV32_COV
 constexpr int kCovBins = sizeof(Vrv32_soc___024root::__Vcoverage) / sizeof(uint32_t);
@@ -93,7 +94,8 @@ void runOne(const Rv32Params& p, uint64_t i) {
         if (p.memImages) {
             for (int w = 0; w < 1024; ++w) top->rootp->rv32_soc__DOT__mem[w] = p.memImages[i * 1024 + w];
         } else {
-            rv32_gen_program(top->rootp->rv32_soc__DOT__mem, (p.tbSeed + round) ^ (p.instBase + i));
+            rv32_gen_program(top->rootp->rv32_soc__DOT__mem,
+                             p.sameProgram ? (p.tbSeed + round) : ((p.tbSeed + round) ^ (p.instBase + i)));
         }
         const VlrefLoopTimer timer;
         for (uint64_t e = 0; e < p.nEvals; ++e) {
@@ -159,13 +161,14 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
                               uint64_t* sigs, uint64_t* times, uint32_t* finalRegs,
                               uint32_t* finalMem, uint32_t* finalScalars, int threads,
                               uint32_t rounds, const char* vcdPath, int64_t vcdInstance,
-                              uint64_t* covSums, const char* covPath, int64_t covInstance) {
+                              uint64_t* covSums, const char* covPath, int64_t covInstance,
+                              uint32_t sameProgram) {
 #ifdef RV32_COV
     for (int b = 0; b < kCovBins; ++b) g_cov[b] = 0;
 #endif
     const Rv32Params p{n, instBase, seedBase, randReset, nEvals, tbSeed, resetTime, memImages,
                        obs, obsEvals, sigs, times, finalRegs, finalMem, finalScalars, rounds, vcdPath, vcdInstance,
-                       covSums, covPath, covInstance};
+                       covSums, covPath, covInstance, sameProgram};
     vlref_loop_seconds_begin();
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);

@@ -97,7 +97,7 @@ def _rv32():
     lib = ref()
     if not getattr(lib, "_rv32_ready", False):
         lib.vlref_rv32_run.restype = i32
-        sig = [u64, u64, u64, i32, u64, u64, u32, vp, vp, u64, vp, vp, vp, vp, vp, i32, u32, cp, i64, vp, cp, i64]
+        sig = [u64, u64, u64, i32, u64, u64, u32, vp, vp, u64, vp, vp, vp, vp, vp, i32, u32, cp, i64, vp, cp, i64, u32]
         lib.vlref_rv32_run.argtypes = sig
         lib.vlref_rv32cov_run.restype = i32
         lib.vlref_rv32cov_run.argtypes = sig
@@ -124,7 +124,7 @@ class Rv32Result:
 
 def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_time=0, mem_images=None,
              obs_evals=0, want_mem=False, threads=1, rounds=0, vcd_path=None, vcd_instance=-1, cov=False,
-             cov_path=None, cov_instance=-1):
+             cov_path=None, cov_instance=-1, same_program=False):
     """rounds=0: one run, resetn released when time() > reset_time (default 16).
     rounds=k>0: campaign mode, k runs of n_evals evals on the same models, each with a fresh
     program from (tb_seed + round) ^ index and resetn low for the run's first reset_time evals
@@ -146,7 +146,8 @@ def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_tim
         r.obs.ctypes.data if obs_evals else None, obs_evals, r.sigs.ctypes.data, r.times.ctypes.data,
         r.regs.ctypes.data, r.mem.ctypes.data if want_mem else None, r.scalars.ctypes.data, threads,
         rounds, vcd_path.encode() if vcd_path else None, vcd_instance,
-        r.cov.ctypes.data if cov else None, cov_path.encode() if cov_path else None, cov_instance)
+        r.cov.ctypes.data if cov else None, cov_path.encode() if cov_path else None, cov_instance,
+        1 if same_program else 0)
     assert rc == 0
     if not obs_evals:
         r.obs = None

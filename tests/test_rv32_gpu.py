@@ -42,6 +42,21 @@ def test_ports_every_eval_match_oracle(abi, rand_reset, reset_time):
         check_final_state(m, want)
 
 
+def test_same_program_x_initial_unique_divergence_only(abi):
+    """BASELINE config 3's setup: every instance runs the same program; they differ only in the
+    x-initial unique reset values (randSeed = seed ^ global index)."""
+    n, evals = 200, 700
+    want = O.rv32_run(n, evals, inst_base=300, seed=12, rand_reset=2, tb_seed=40, same_program=True,
+                      obs_evals=evals, want_mem=True)
+    with abi.Model("rv32i", n, inst_base=300, seed=12, rand_reset=2) as m:
+        obs, _ = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=40, tb_flags=2, obs_evals=evals)
+        assert (obs == want.obs).all()
+        check_final_state(m, want)
+        assert (m.signatures() == want.sigs).all()
+        mem0 = O.rv32_gen_program(40)
+        assert len(np.unique(want.sigs)) > 1  # the reset values did make instances differ
+
+
 def test_campaign_rounds_fresh_program_and_reset_per_run(abi):
     """Fuzz-campaign form used by bench.py's e2e leg: every vlcu_run starts a fresh program and
     holds reset for the run's first evals (tb_flags bit 0), state otherwise carried over."""

@@ -17,7 +17,9 @@ struct TbRv32Rand final {
                              uint64_t, uint64_t globalInst) {
         top.clk = 0;
         top.resetn = 0;
-        rv32_gen_program(top.rv32_soc__DOT__mem, r.tbSeed ^ globalInst);
+        // RV32_TBF_SAME_PROGRAM (tb_flags bit 1): one program image for all instances, so that
+        // they differ only in their --x-initial unique reset values (BASELINE config 3's setup)
+        rv32_gen_program(top.rv32_soc__DOT__mem, (r.tbFlags & 2U) ? r.tbSeed : (r.tbSeed ^ globalInst));
     }
     template <class T_Design>
     VLCU_D static void drive(typename T_Design::Root& top, VlcuContext& ctx, const VlcuRunDev& r,
