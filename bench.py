@@ -397,6 +397,17 @@ def run_ours(args, wl):
                "kind": "reference",
                "sample": f"{sample} instances x {c_cycles} cycles, {cpu_dt:.1f} s, "
                          f"{threads} threads, one instance per thread at a time"}
+        if wl["design"] == "rv32i" and not wl.get("same_program"):
+            # SURVEY 8(d) baseline (ii): ONE instance of the --threads 4 build (V3Order's mtasks on
+            # the runtime's thread pool); for a design this small the synchronisation dominates
+            import oracle_util as O
+            mt_cycles = 20000
+            O.rv32_run(1, 2 * 2000, seed=1, rand_reset=wl["rand_reset"], tb_seed=3, mtasks=True)
+            t0 = time.perf_counter()
+            O.rv32_run(1, 2 * mt_cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3, mtasks=True)
+            cpu["single_instance_threads4"] = {
+                "value": mt_cycles / (time.perf_counter() - t0), "unit": UNIT, "threads": 4,
+                "sample": f"1 instance x {mt_cycles} cycles, model Verilated with --threads 4"}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -16,6 +16,13 @@
 #define Vrv32_soc Vrv32_cov
 #define Vrv32_soc___024root Vrv32_cov___024root
 #define vlref_rv32_run vlref_rv32cov_run
+#elif defined(RV32_THR)
+// the --threads 4 build: ONE instance spread over 4 host threads (SURVEY 8(d) CPU baseline ii)
+#include "Vrv32_thr.h"
+#include "Vrv32_thr___024root.h"
+#define Vrv32_soc Vrv32_thr
+#define Vrv32_soc___024root Vrv32_thr___024root
+#define vlref_rv32_run vlref_rv32thr_run
 #else
 #include "Vrv32_soc.h"
 #include "Vrv32_soc___024root.h"
@@ -78,13 +85,18 @@ void runOne(const Rv32Params& p, uint64_t i) {
     const char* argv[] = {"oracle"};
     contextp->commandArgs(1, argv);
     contextp->traceEverOn(true);
+#ifdef RV32_THR
+    contextp->threads(4);
+#endif
     const std::unique_ptr<Vrv32_soc> top{new Vrv32_soc{contextp.get(), "TOP"}};
     std::unique_ptr<VerilatedVcdC> tfp;
+#ifndef RV32_THR
     if (p.vcdPath && p.vcdInstance == static_cast<int64_t>(i)) {
         tfp.reset(new VerilatedVcdC);
         top->trace(tfp.get(), 99);
         tfp->open(p.vcdPath);
     }
+#endif
     const uint64_t resetTime = p.resetTime ? p.resetTime : 16;
     uint64_t sig = 0xcbf29ce484222325ULL;
     const uint32_t rounds = p.rounds ? p.rounds : 1;
@@ -198,6 +210,7 @@ extern "C" int vlref_rv32_run(uint64_t n, uint64_t instBase, uint64_t seedBase, 
 
 #ifdef RV32_COV
 extern "C" int vlref_rv32cov_bins() { return kCovBins; }
+#elif defined(RV32_THR)
 #else
 // Save / restore through the reference's own verilated_save (the model is built --savable):
 // one instance, either constructed like instance `globalIndex` of vlref_rv32_run or restored

@@ -101,6 +101,8 @@ def _rv32():
         lib.vlref_rv32_run.argtypes = sig
         lib.vlref_rv32cov_run.restype = i32
         lib.vlref_rv32cov_run.argtypes = sig
+        lib.vlref_rv32thr_run.restype = i32
+        lib.vlref_rv32thr_run.argtypes = sig
         lib.vlref_rv32cov_bins.restype = i32
         lib.vlref_rv32_gen_program.restype = None
         lib.vlref_rv32_gen_program.argtypes = [u64, vp]
@@ -124,7 +126,7 @@ class Rv32Result:
 
 def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_time=0, mem_images=None,
              obs_evals=0, want_mem=False, threads=1, rounds=0, vcd_path=None, vcd_instance=-1, cov=False,
-             cov_path=None, cov_instance=-1, same_program=False):
+             cov_path=None, cov_instance=-1, same_program=False, mtasks=False):
     """rounds=0: one run, resetn released when time() > reset_time (default 16).
     rounds=k>0: campaign mode, k runs of n_evals evals on the same models, each with a fresh
     program from (tb_seed + round) ^ index and resetn low for the run's first reset_time evals
@@ -140,7 +142,7 @@ def rv32_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, reset_tim
         mem_images = np.ascontiguousarray(mem_images, dtype=np.uint32).reshape(n, 1024)
     lib = _rv32()
     r.cov = np.zeros(lib.vlref_rv32cov_bins(), dtype=np.uint64) if cov else None
-    rc = (lib.vlref_rv32cov_run if cov else lib.vlref_rv32_run)(
+    rc = (lib.vlref_rv32cov_run if cov else lib.vlref_rv32thr_run if mtasks else lib.vlref_rv32_run)(
         n, inst_base, seed, rand_reset, n_evals, tb_seed, reset_time,
         mem_images.ctypes.data if mem_images is not None else None,
         r.obs.ctypes.data if obs_evals else None, obs_evals, r.sigs.ctypes.data, r.times.ctypes.data,
