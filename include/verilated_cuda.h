@@ -607,6 +607,42 @@ struct VlcuSharedArray final {
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
+// Multidimensional unpacked arrays (VlUnpacked<VlUnpacked<T, D1>, D0> in the C++ model): stored
+// flat, row-major, in one of the 1-D array classes above; m[i0][i1]... walks down a chain of views
+// that folds the indices into the flat element number.
+template <class T_Flat, size_t... N_Dims>
+struct VlcuDimView;
+template <class T_Flat, size_t N_Dim>
+struct VlcuDimView<T_Flat, N_Dim> final {  // last dimension: yields the element
+    T_Flat* m_flatp;
+    size_t m_index;  // flat index of this row's element 0, in units of N_Dim
+    VLCU_HD auto operator[](size_t i) const -> decltype((*m_flatp)[0]) { return (*m_flatp)[m_index * N_Dim + i]; }
+    VLCU_HD constexpr size_t size() const { return N_Dim; }
+};
+template <class T_Flat, size_t N_Dim, size_t... N_Rest>
+struct VlcuDimView<T_Flat, N_Dim, N_Rest...> final {
+    T_Flat* m_flatp;
+    size_t m_index;
+    VLCU_HD VlcuDimView<T_Flat, N_Rest...> operator[](size_t i) const {
+        return VlcuDimView<T_Flat, N_Rest...>{m_flatp, m_index * N_Dim + i};
+    }
+    VLCU_HD constexpr size_t size() const { return N_Dim; }
+};
+// T_Flat: the 1-D array class holding all elements; N_Dim0 x N_Rest...: the declared dimensions
+template <class T_Flat, size_t N_Dim0, size_t... N_Rest>
+struct VlcuMdArray final {
+    T_Flat m_flat;
+    template <class... T_Args>
+    VLCU_HD void bind(T_Args... args) { m_flat.bind(args...); }
+    VLCU_HD T_Flat& flat() { return m_flat; }
+    VLCU_HD const T_Flat& flat() const { return m_flat; }
+    VLCU_HD VlcuDimView<T_Flat, N_Rest...> operator[](size_t i) { return VlcuDimView<T_Flat, N_Rest...>{&m_flat, i}; }
+    VLCU_HD VlcuDimView<const T_Flat, N_Rest...> operator[](size_t i) const {
+        return VlcuDimView<const T_Flat, N_Rest...>{&m_flat, i};
+    }
+    VLCU_HD constexpr size_t size() const { return N_Dim0; }
+};
+
 // Everything a kernel needs to find one model's data
 struct VlcuModelDev final {
     VlcuState state;

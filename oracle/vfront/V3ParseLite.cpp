@@ -871,6 +871,16 @@ class Parser final {
             if (prio) casep->priorityPragma(true);
             return casep;
         }
+        if (t.text == "while") {  // statement_item: yWHILE '(' expr ')' stmt (verilog.y:3716-3720)
+            const Token kw = m_lex.next();
+            const Token lp = expectPunct("(");
+            AstNodeExpr* const condp = parseExpr();
+            expectPunct(")");
+            AstLoop* const loopp = new AstLoop{kw.fl};
+            loopp->addStmtsp(new AstLoopTest{lp.fl, loopp, condp});
+            loopp->addStmtsp(parseStmt());
+            return loopp;
+        }
         if (t.text == "for") {  // statement_item: yFOR (verilog.y:3698-3706)
             const Token kw = m_lex.next();
             expectPunct("(");

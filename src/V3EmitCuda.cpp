@@ -59,7 +59,8 @@ struct CudaMember final {
     int kind = 3;  // VlcuMemberKind: 0 in, 1 out, 2 inout, 3 state, 4 coverage, 5 memory
     int elemBytes = 4;
     uint32_t words = 1;  // 32-bit words of one (wide) element, else 1
-    uint32_t depth = 1;  // array elements, else 1
+    uint32_t depth = 1;  // array elements (all dimensions), else 1
+    std::vector<uint32_t> dims;  // declared unpacked dimensions, outermost first
     bool isArray = false;
     bool isWide = false;
     uint32_t width = 1;  // bits of one element
@@ -173,13 +174,13 @@ class EmitCudaModel final : public EmitCFunc {
         }
         const AstNodeDType* dtp = varp->dtypep()->skipRefp();
         if (const AstUnpackArrayDType* const adtp = VN_CAST(dtp, UnpackArrayDType)) {
+            // VlUnpacked<VlUnpacked<T, D1>, D0>: kept flat, row-major (VlcuMdArray)
             m.isArray = true;
-            m.depth = adtp->elementsConst();
-            dtp = adtp->subDTypep()->skipRefp();
-            if (VN_IS(dtp, UnpackArrayDType)) {
-                varp->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: multidimensional unpacked array "
-                                                << varp->prettyNameQ());
-                return;
+            m.depth = 1;
+            for (const AstUnpackArrayDType* ap = adtp; ap; ap = VN_CAST(dtp, UnpackArrayDType)) {
+                m.dims.push_back(ap->elementsConst());
+                m.depth *= ap->elementsConst();
+                dtp = ap->subDTypep()->skipRefp();
             }
         }
         if (!dtp->isIntegralOrPacked()) {
@@ -219,7 +220,7 @@ class EmitCudaModel final : public EmitCFunc {
             //   HBM            large memories, instance-major so one instance's accesses share sectors
             const bool runtime = runtimeIndexed.count(varp) != 0;
             const uint32_t bytes = m.bytes();
-            if (!runtime && m.elems() <= 16) {
+            if (!runtime && m.elems() <= 16 && m.dims.size() == 1) {
                 m.storage = CudaStorage::REG;
             } else if (runtime && bytes <= 256 && !m.isWide) {
                 m.storage = CudaStorage::SHARED;
@@ -321,13 +322,18 @@ class EmitCudaModel final : public EmitCFunc {
     // ---- model struct ------------------------------------------------------------
     static string handleDecl(const CudaMember& m) {
         const string depth = cvtToStr(m.depth);
+        string flat;
         switch (m.storage) {
-        case CudaStorage::SHARED: return "VlcuSharedArray<" + m.elemDecl + ", " + depth + "> " + m.name;
-        case CudaStorage::LOCAL: return "VlcuLocalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
-        case CudaStorage::GLOBAL: return "VlcuGlobalArray<" + m.elemDecl + ", " + depth + "> " + m.name;
+        case CudaStorage::SHARED: flat = "VlcuSharedArray<" + m.elemDecl + ", " + depth + ">"; break;
+        case CudaStorage::LOCAL: flat = "VlcuLocalArray<" + m.elemDecl + ", " + depth + ">"; break;
+        case CudaStorage::GLOBAL: flat = "VlcuGlobalArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::COVER: return "VlcuCovArray<" + depth + "> " + m.name;
         default: return "";
         }
+        if (m.dims.size() <= 1) return flat + " " + m.name;
+        string dims;
+        for (const uint32_t d : m.dims) dims += ", " + cvtToStr(d);
+        return "VlcuMdArray<" + flat + dims + "> " + m.name;
     }
     void emitRootStruct() {
         puts("\n// The model image of one instance (Vtop___024root of the C++ model), held by one thread\n");
@@ -361,15 +367,17 @@ class EmitCudaModel final : public EmitCFunc {
                 puts(load ? "st.ldW(" + off + ", i, s." + m.name + ");\n"
                           : "st.stW(" + off + ", i, s." + m.name + ");\n");
             } else if (!m.isWide) {
+                const string arr = "s." + m.name + (m.dims.size() > 1 ? ".flat()" : "");
                 puts("for (uint32_t e = 0; e < " + cvtToStr(m.depth) + "; ++e) ");
-                puts(load ? "s." + m.name + "[e] = st.ldE<" + m.elemCType + ">(" + off + ", e, i);\n"
-                          : "st.stE<" + m.elemCType + ">(" + off + ", e, i, s." + m.name + "[e]);\n");
+                puts(load ? arr + "[e] = st.ldE<" + m.elemCType + ">(" + off + ", e, i);\n"
+                          : "st.stE<" + m.elemCType + ">(" + off + ", e, i, " + arr + "[e]);\n");
             } else {
+                const string arr = "s." + m.name + (m.dims.size() > 1 ? ".flat()" : "");
                 const string words = cvtToStr(m.words);
                 puts("for (uint32_t e = 0; e < " + cvtToStr(m.depth) + "; ++e) {\n");
                 puts("for (uint32_t w = 0; w < " + words + "; ++w) ");
-                puts(load ? "s." + m.name + "[e][w] = st.ldE<EData>(" + off + ", e * " + words + " + w, i);\n"
-                          : "st.stE<EData>(" + off + ", e * " + words + " + w, i, s." + m.name + "[e][w]);\n");
+                puts(load ? arr + "[e][w] = st.ldE<EData>(" + off + ", e * " + words + " + w, i);\n"
+                          : "st.stE<EData>(" + off + ", e * " + words + " + w, i, " + arr + "[e][w]);\n");
                 puts("}\n");
             }
         }
