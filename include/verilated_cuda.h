@@ -246,7 +246,7 @@ enum : uint32_t {
     VLCU_FATAL_USER = 3,  // $fatal
 };
 
-#define VLCU_MSG_ARGS 4
+#define VLCU_MSG_ARGS 8
 struct VlcuMsg {  // one logged $display/$write, formatted later on the host
     uint64_t time;
     uint32_t id;  // index into the design's message-format table
@@ -322,13 +322,15 @@ struct VlcuContext final {
     }
     // $display/$write/$error text: log (id, args) for host-side formatting
     VLCU_HD void writef(uint32_t id, uint32_t nargs = 0, uint64_t a0 = 0, uint64_t a1 = 0,
-                        uint64_t a2 = 0, uint64_t a3 = 0) {
+                        uint64_t a2 = 0, uint64_t a3 = 0, uint64_t a4 = 0, uint64_t a5 = 0,
+                        uint64_t a6 = 0, uint64_t a7 = 0) {
         if (m_msgCount < m_msgCap) {
             VlcuMsg& msg = m_msgp[m_msgCount];
             msg.time = m_time;
             msg.id = id;
             msg.nargs = nargs;
             msg.args[0] = a0, msg.args[1] = a1, msg.args[2] = a2, msg.args[3] = a3;
+            msg.args[4] = a4, msg.args[5] = a5, msg.args[6] = a6, msg.args[7] = a7;
         } else {
             m_status |= VLCU_ST_MSGDROP;
         }

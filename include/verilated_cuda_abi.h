@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VLCU_ABI_VERSION 1
+#define VLCU_ABI_VERSION 2
 
 enum {
     VLCU_OK = 0,
@@ -91,7 +91,7 @@ typedef struct {
     uint64_t time;
     uint32_t id; /* index for vlcu_message_format() */
     uint32_t nargs;
-    uint64_t args[4];
+    uint64_t args[8];
 } vlcu_msg_t;
 
 /* vlcu_run flags */

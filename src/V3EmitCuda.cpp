@@ -579,7 +579,7 @@ class EmitCudaModel final : public EmitCFunc {
         if (id == m_messages.size()) m_messages.push_back(text);
         int nargs = 0;
         for (AstNode* argp = nodep->fmtp()->exprsp(); argp; argp = argp->nextp()) ++nargs;
-        if (nargs > 4) nodep->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: more than 4 $display arguments");
+        if (nargs > 8) nodep->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: more than 8 $display arguments");
         putns(nodep, "vlCtx.writef(" + cvtToStr(id) + "U, " + cvtToStr(nargs) + "U");
         for (AstNode* argp = nodep->fmtp()->exprsp(); argp; argp = argp->nextp()) {
             AstSFormatArg* const fargp = VN_CAST(argp, SFormatArg);

@@ -230,6 +230,23 @@ def test_port_streaming_kernel_and_host_pipeline_equal_the_direct_kernel(abi):
         abi.lib.vlcu_device_free(m.h, d_obs)
 
 
+@pytest.mark.parametrize("evals", [1, 2, 7, 8, 9, 17])
+@pytest.mark.parametrize("n", [1, 64, 65, 257])
+def test_port_streaming_pipeline_edges(abi, n, evals):
+    """Fewer evals than pipeline stages, exactly one pipeline's worth, one more; a single
+    instance, exactly one CTA, one instance more than a CTA."""
+    with abi.Model("make_tracing_c", n, rand_reset=2, seed=3) as m:
+        stim = random_rows(m, evals, 100 * n + evals)
+        m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=4, tb_flags=1)
+        obs_a, _ = m.run("trace", evals, stim=stim, obs_evals=evals, flags=abi.RUNF_NO_STREAM)
+        sig_a = m.signatures()
+        for flags in (0, abi.RUNF_BULK_1D):
+            m.reset()
+            m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=4, tb_flags=1)
+            obs_b, _ = m.run("trace", evals, stim=stim, obs_evals=evals, flags=flags)
+            assert (obs_b == obs_a).all() and (m.signatures() == sig_a).all()
+
+
 @pytest.mark.parametrize("stop_on_finish,period", [(False, 0), (False, 40), (True, 0)])
 def test_vcd_of_sampled_instances_equals_the_reference_writer(abi, tmp_path, stop_on_finish, period):
     """R8: waveforms of sampled instances.  The device samples full state after every eval;

@@ -47,7 +47,7 @@ STATUS_DTYPE = np.dtype([
     ("finish_count", "<u4"), ("stop_count", "<u4"), ("fatal_count", "<u4"),
     ("first_stop_line", "<u4"), ("first_fatal_line", "<u4"), ("fatal_code", "<u4"),
     ("msg_count", "<u4"), ("pad_", "<u4")])
-MSG_DTYPE = np.dtype([("time", "<u8"), ("id", "<u4"), ("nargs", "<u4"), ("args", "<u8", 4)])
+MSG_DTYPE = np.dtype([("time", "<u8"), ("id", "<u4"), ("nargs", "<u4"), ("args", "<u8", 8)])
 
 DIR_IN, DIR_OUT, DIR_INOUT = 0, 1, 2
 RUNF_NO_STREAM = 0x20
