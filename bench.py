@@ -89,6 +89,23 @@ WORKLOADS = {
         note="rv32_soc.v, one program image for all instances; instances differ only in the "
              "x-initial unique reset values of registers and register file (VL_SCOPED_RAND_RESET_* "
              "from randSeed = 1 ^ instance)"),
+    # State streaming: 4 KB of state per instance, all of it read and rewritten
+    # every clock cycle by a 1,023-iteration loop; 303,104 instances (= 2 waves of 148 SMs x 16
+    # resident 64-thread CTAs) = 1.2 GB of state, so every cycle streams it from and to HBM.  V3EmitCuda keeps the array [element][instance] because
+    # its only run-time index is the loop counter; state_stream_im is the same design emitted with
+    # --no-cuda-array-layout (instance-major, as a data-indexed memory would be).
+    "state_stream": dict(
+        design="t10_bigstate", tb="trace", instances=303104, cycles=16, tb_flags=0,
+        tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(), rows=True, state_bytes_per_cycle=8192,
+        cpu_cycles=1024,  # the CPU sample runs longer per instance, or construction would dominate it
+        note="t10_bigstate.v: 1,024 x 32-bit mixing pipeline, every element read and rewritten each "
+             "clock cycle; array kept [element][instance] in the SoA state block (VlcuStateArray)"),
+    "state_stream_im": dict(
+        design="t10_bigstate_im", ref_design="t10_bigstate", tb="trace", instances=303104, cycles=16,
+        tb_flags=0, tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(), rows=True, state_bytes_per_cycle=8192,
+        cpu_cycles=1024,
+        note="t10_bigstate.v emitted with --no-cuda-array-layout: the array instance-major in HBM "
+             "(VlcuGlobalArray), the layout chosen for data-indexed memories"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -186,6 +203,16 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     excluded."""
     import ctypes as C
     import oracle_util as O
+    if wl["design"].startswith("t10_"):
+        design = wl.get("ref_design", wl["design"])
+        in_w, _ = O.generic_words(design)
+        rng = np.random.default_rng(7)
+        stim = rng.integers(0, 1 << 32, size=(2 * cycles, in_w, sample_instances), dtype=np.uint64).astype(np.uint32)
+        stim[:, 0, :] = ((np.arange(2 * cycles, dtype=np.uint32) & 1) ^ 1)[:, None]
+        t0 = time.perf_counter()
+        O.generic_run(design, stim, seed=1, rand_reset=wl["rand_reset"], threads=threads)
+        dt = time.perf_counter() - t0  # (construction included: 1,024 reset values per instance)
+        return sample_instances * cycles / dt, dt
     if wl["design"] in ("rv32i", "rv32i_cov"):
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads, cov=wl["design"] == "rv32i_cov",
@@ -218,7 +245,7 @@ def run_reference(args, wl):
         return
     threads = os.cpu_count() or 1
     # bounded sample: ~1-2 s of CPU work per step
-    cycles = min(wl["cycles"], 4096)
+    cycles = wl.get("cpu_cycles", min(wl["cycles"], 4096))
     sample = cpu_sample_size(wl, cycles, threads, 4.0)  # ~4 s of wall time per step
     for _ in range(args.warmup):
         cpu_reference_run(wl, sample, cycles, threads)
@@ -449,7 +476,9 @@ def run_rows(args, wl):
     evals = 2 * cycles
     m = abi.Model(wl["design"], n, device=local, inst_base=rank * n, seed=1,
                   rand_reset=wl["rand_reset"], msg_cap=2)
-    m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=3, tb_flags=1)
+    mtc = wl["design"] == "make_tracing_c"
+    if mtc:
+        m.run("sim_main", 0, flags=abi.RUNF_TB_BEGIN, tb_seed=3, tb_flags=1)
     in_w, out_w, npad = m.in_words, m.out_words, m.npad
     stim, _ = pinned_array(abi, (evals, in_w, npad), np.uint32)
     obs, _ = pinned_array(abi, (evals, out_w, npad), np.uint32)
@@ -459,10 +488,13 @@ def run_rows(args, wl):
         k = min(64, evals - e0)
         stim[e0:e0 + k] = np.roll(block[:k], e0 // 64 * 4099, axis=2)
     stim[:, 0, :] = ((np.arange(evals, dtype=np.uint32) & 1) ^ 1)[:, None]  # clk
+    if not mtc:
+        pass  # every other input word stays random
     # reset_l: low for one clock period in three, so that sub.v's counter never reaches its
     # $finish threshold (count_c >= 3, sub.v:24-29) nor the assertion's (sub.v:35) -- the same
     # device BASELINE config 1 documents for runs longer than the shipped example
-    stim[:, 1, :] = ((np.arange(evals, dtype=np.uint32) // 2) % 3 != 0)[:, None]
+    if mtc:
+        stim[:, 1, :] = ((np.arange(evals, dtype=np.uint32) // 2) % 3 != 0)[:, None]
     d_stim = abi.lib.vlcu_device_alloc(m.h, stim.nbytes)
     d_obs = abi.lib.vlcu_device_alloc(m.h, obs.nbytes)
     if not d_stim or not d_obs:
@@ -527,7 +559,7 @@ def run_rows(args, wl):
     mean_ms = sum(ev_ms) / len(ev_ms)
     # bytes that stream per instance-cycle: the port rows of two evals.  S_in/S_out in C storage
     # bytes and as laid out (one 32-bit word per port limb).
-    b_alg = 2 * (m.in_bytes + m.out_bytes)
+    b_alg = 2 * (m.in_bytes + m.out_bytes) + wl.get("state_bytes_per_cycle", 0)
     b_rows = 2 * 4 * (in_w + out_w)
     achieved = n * cycles * b_alg / (mean_ms / 1e3) / 1e9
     rows_gbs = npad * cycles * b_rows / (mean_ms / 1e3) / 1e9
@@ -539,7 +571,7 @@ def run_rows(args, wl):
     threads = os.cpu_count() or 1
     cpu = None
     if not args.no_cpu_baseline:
-        c_cycles = min(cycles, 4096)
+        c_cycles = wl.get("cpu_cycles", min(cycles, 4096))
         sample = cpu_sample_size(wl, c_cycles, threads, 15.0)
         cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)
         cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "reference",
@@ -568,7 +600,12 @@ def run_rows(args, wl):
                      "row_bytes_per_instance_cycle": b_rows, "row_gbs": rows_gbs,
                      "row_frac": rows_gbs / peak,
                      "dram_gbs_from_traffic": (traffic / (mean_ms / 1e3) / 1e9) if traffic else None,
-                     "note": "state stays on chip across the fused evals, so the bytes that must stream are "
+                     "note": ("the state (4 KB per instance, 1 GB per GPU) cannot stay on chip: every clock "
+                              "cycle reads and rewrites all of it once (the rising-edge eval; the falling-edge "
+                              "eval touches none), so B_alg = S_state_rd + S_state_wr = 8,192 B per "
+                              "instance-cycle + 2*(S_in+S_out) for the port rows (SURVEY 8d)")
+                     if wl.get("state_bytes_per_cycle") else
+                             "state stays on chip across the fused evals, so the bytes that must stream are "
                              "the port rows: achieved = 2*(S_in+S_out) x instance-cycles/s with S in C storage "
                              "bytes (SURVEY 8d); row_gbs counts the rows as laid out (a 32-bit word per port "
                              "limb, padded instance stride)"},

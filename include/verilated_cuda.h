@@ -562,6 +562,28 @@ struct VlcuGlobalArray final {
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
+// A large array that stays in the SoA state block as it is at rest, [element][instance]: every
+// lane of a warp touching the SAME element (a loop index, a constant) is one fully coalesced
+// 32 x sizeof(T) byte run.  V3EmitCuda picks this layout for arrays whose run-time indices do not
+// depend on design signals, and VlcuGlobalArray (instance-major) for data-dependent indices, where
+// consecutive accesses of one instance should share sectors instead.
+template <typename T_Value, size_t N_Depth>
+struct VlcuStateArray final {
+    T_Value* m_basep;  // element 0 of this instance
+    uint32_t m_stride;  // padded instance count (elements between consecutive indices)
+    VLCU_HD void bind(const VlcuState& st, uint32_t soaOffset, uint64_t inst) {
+        m_basep = st.ptr<T_Value>(soaOffset) + inst;
+        m_stride = static_cast<uint32_t>(st.npad);
+    }
+    VLCU_HD T_Value& operator[](size_t index) {
+        return m_basep[static_cast<uint64_t>(m_stride) * static_cast<uint32_t>(index)];
+    }
+    VLCU_HD const T_Value& operator[](size_t index) const {
+        return m_basep[static_cast<uint64_t>(m_stride) * static_cast<uint32_t>(index)];
+    }
+    VLCU_HD constexpr size_t size() const { return N_Depth; }
+};
+
 // The coverage counter array of a model image: see VlcuCovPtr
 template <size_t N_Bins>
 struct VlcuCovArray final : public VlcuCovPtr {

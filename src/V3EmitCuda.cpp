@@ -50,7 +50,7 @@ VL_DEFINE_DEBUG_FUNCTIONS;
 
 namespace {
 
-enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL, COVER };
+enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL, INTERLEAVED, COVER };
 
 struct CudaMember final {
     const AstVar* varp = nullptr;
@@ -74,21 +74,36 @@ struct CudaMember final {
 };
 
 // Which module arrays are indexed with something that is not a constant
+// ... and which of those with an index that depends on a design signal (a member of the model),
+// i.e. that differs between instances; an index made of function-local variables and constants
+// (a loop counter) is the same in every lane of a warp.
 class CudaIndexVisitor final : public VNVisitorConst {
     std::set<const AstVar*>& m_runtimeIndexed;
+    std::set<const AstVar*>& m_dataIndexed;
+    static bool dependsOnMember(const AstNode* nodep) {
+        bool member = false;
+        nodep->foreach([&](const AstVarRef* refp) {
+            if (!refp->varp()->isFuncLocal()) member = true;
+        });
+        return member;
+    }
     void visit(AstArraySel* nodep) override {
         if (!VN_IS(nodep->bitp(), Const)) {
             const AstNode* fromp = nodep->fromp();
             while (const AstArraySel* const selp = VN_CAST(fromp, ArraySel)) fromp = selp->fromp();
-            if (const AstVarRef* const refp = VN_CAST(fromp, VarRef)) m_runtimeIndexed.insert(refp->varp());
+            if (const AstVarRef* const refp = VN_CAST(fromp, VarRef)) {
+                m_runtimeIndexed.insert(refp->varp());
+                if (dependsOnMember(nodep->bitp())) m_dataIndexed.insert(refp->varp());
+            }
         }
         iterateChildrenConst(nodep);
     }
     void visit(AstNode* nodep) override { iterateChildrenConst(nodep); }
 
 public:
-    CudaIndexVisitor(const AstNodeModule* modp, std::set<const AstVar*>& out)
-        : m_runtimeIndexed{out} {
+    CudaIndexVisitor(const AstNodeModule* modp, std::set<const AstVar*>& out, std::set<const AstVar*>& dataOut)
+        : m_runtimeIndexed{out}
+        , m_dataIndexed{dataOut} {
         iterateConst(const_cast<AstNodeModule*>(modp));
     }
 };
@@ -133,6 +148,7 @@ class EmitCudaModel final : public EmitCFunc {
     const string m_designName;  // Vtop__cuda
     std::vector<CudaMember> m_members;
     std::map<const AstVar*, size_t> m_memberOf;
+    std::set<const AstVar*> m_dataIndexed;  // arrays with an index that differs between instances
     std::vector<string> m_messages;
     std::vector<string> m_plusargs;
     int m_coverBins = 0;
@@ -226,6 +242,11 @@ class EmitCudaModel final : public EmitCFunc {
                 m.storage = CudaStorage::SHARED;
             } else if (bytes <= 2048) {
                 m.storage = CudaStorage::LOCAL;
+            } else if (!m.isWide && !m_dataIndexed.count(varp) && V3EmitCuda::layoutSelection()) {
+                // large, and every run-time index is the same in all instances (loop counters):
+                // leave it in the SoA block, [element][instance], so that a warp's access coalesces
+                m.storage = CudaStorage::INTERLEAVED;
+                if (m.elemBytes < 4) m.elemDecl = m.elemCType;
             } else {
                 m.storage = CudaStorage::GLOBAL;
                 m.kind = 5;
@@ -236,7 +257,7 @@ class EmitCudaModel final : public EmitCFunc {
     }
     void computeLayout() {
         std::set<const AstVar*> runtimeIndexed;
-        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed}; }
+        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed, m_dataIndexed}; }
         for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
             if (const AstVar* const varp = VN_CAST(nodep, Var)) {
                 // Same test as EmitCHeader::emitDesignVarDecls (V3EmitCHeaders.cpp:133-135)
@@ -327,6 +348,7 @@ class EmitCudaModel final : public EmitCFunc {
         case CudaStorage::SHARED: flat = "VlcuSharedArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::LOCAL: flat = "VlcuLocalArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::GLOBAL: flat = "VlcuGlobalArray<" + m.elemDecl + ", " + depth + ">"; break;
+        case CudaStorage::INTERLEAVED: flat = "VlcuStateArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::COVER: return "VlcuCovArray<" + depth + "> " + m.name;
         default: return "";
         }
@@ -346,6 +368,8 @@ class EmitCudaModel final : public EmitCFunc {
                 puts(m.storage == CudaStorage::SHARED  ? "  // run-time indexed: shared memory [index][lane]\n"
                      : m.storage == CudaStorage::LOCAL ? "  // thread-local memory\n"
                      : m.storage == CudaStorage::COVER ? "  // stays in HBM as cov[bin][instance], RED.ADD\n"
+                     : m.storage == CudaStorage::INTERLEAVED
+                         ? "  // stays in HBM, [element][instance]: instance-uniform indices coalesce\n"
                                                        : "  // stays in HBM, instance-major\n");
             }
         }
@@ -358,7 +382,10 @@ class EmitCudaModel final : public EmitCFunc {
         puts(load ? "VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {\n"
                   : "VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {\n");
         for (const CudaMember& m : m_members) {
-            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER) continue;
+            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER
+                || m.storage == CudaStorage::INTERLEAVED) {
+                continue;
+            }
             const string off = "OFF_" + m.name;
             if (!m.isArray && !m.isWide) {
                 puts(load ? "s." + m.name + " = st.ld<" + m.elemCType + ">(" + off + ", i);\n"
@@ -874,7 +901,8 @@ class EmitCudaModel final : public EmitCFunc {
         for (const CudaMember& m : m_members) {
             if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
             if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
-            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER) {
+            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER
+                || m.storage == CudaStorage::INTERLEAVED) {
                 puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
             }
         }
@@ -1095,6 +1123,7 @@ public:
 }  // namespace
 
 bool V3EmitCuda::s_enabled = false;
+bool V3EmitCuda::s_layoutSelection = true;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -24,9 +24,14 @@ public:
     // --cuda / --no-cuda
     static void enable(bool flag) { s_enabled = flag; }
     static bool enabled() { return s_enabled; }
+    // --cuda-array-layout / --no-cuda-array-layout: per-array choice between [element][instance]
+    // and instance-major placement of large arrays (off: always instance-major)
+    static void layoutSelection(bool flag) { s_layoutSelection = flag; }
+    static bool layoutSelection() { return s_layoutSelection; }
 
 private:
     static bool s_enabled;
+    static bool s_layoutSelection;
 };
 
 #endif  // Guard

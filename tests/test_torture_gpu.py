@@ -13,7 +13,7 @@ import oracle_util as O
 
 pytestmark = pytest.mark.gpu
 
-DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray"]
+DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate"]
 
 
 @pytest.fixture(scope="module")
@@ -63,15 +63,20 @@ def random_stimulus(m, abi, n, evals, rng, hold=None):
     return stim
 
 
-@pytest.mark.parametrize("design", DESIGNS)
+# CUDA-only variants: (registered design, the design whose genuine model is the reference)
+VARIANTS = {"t10_bigstate_im": "t10_bigstate"}  # --no-cuda-array-layout: instance-major array
+
+
+@pytest.mark.parametrize("design", DESIGNS + sorted(VARIANTS))
 @pytest.mark.parametrize("rand_reset", [2, 0])
 def test_every_port_every_eval_matches_the_genuine_model(abi, design, rand_reset):
     n, evals = 96, 600
-    rng = np.random.default_rng(hash(design) % (1 << 32))
+    ref_design = VARIANTS.get(design, design)
+    rng = np.random.default_rng(hash(ref_design) % (1 << 32))
     with abi.Model(design, n, seed=17, rand_reset=rand_reset) as m:
         stim = random_stimulus(m, abi, n, evals, rng)
-        want_obs, want_sigs = O.generic_run(design, stim[:, :, :n], seed=17, rand_reset=rand_reset, threads=4)
-        assert (m.in_words, m.out_words) == O.generic_words(design)
+        want_obs, want_sigs = O.generic_run(ref_design, stim[:, :, :n], seed=17, rand_reset=rand_reset, threads=4)
+        assert (m.in_words, m.out_words) == O.generic_words(ref_design)
         obs, _ = m.run("trace", evals, stim=stim, obs_evals=evals)
         bad = np.argwhere(obs[:, :, :n] != want_obs)
         assert len(bad) == 0, (design, bad[:5].tolist())

@@ -1,0 +1,364 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt10_bigstate_im"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt10_bigstate_im___024root final {
+    CData/*0:0*/ clk;
+    IData/*31:0*/ din;
+    SData/*9:0*/ sel;
+    IData/*31:0*/ acc;
+    IData/*31:0*/ tap;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ __VactIterCount;
+    VlcuGlobalArray<IData/*31:0*/, 1024> t10_bigstate__DOT__taps;  // stays in HBM, instance-major
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt10_bigstate_im__cuda final {
+    typedef Vt10_bigstate_im___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 4130,
+        OFF_din = 16,
+        OFF_sel = 4128,
+        OFF_acc = 20,
+        OFF_tap = 24,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 4131,
+        OFF___VactPhaseResult = 4132,
+        OFF___VnbaPhaseResult = 4133,
+        OFF___VactIterCount = 28,
+        OFF_t10_bigstate__DOT__taps = 32,
+        OFF___VactTriggered = 0,
+        OFF___VnbaTriggered = 8,
+        kStateBytes = 4136,  // S_persist
+        kTouchedReadBytes = 56,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 39,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+        s.t10_bigstate__DOT__taps.bind(st, OFF_t10_bigstate__DOT__taps, i);
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.din = st.ld<IData>(OFF_din, i);
+        s.sel = st.ld<VlcuMem16>(OFF_sel, i);
+        s.acc = st.ld<IData>(OFF_acc, i);
+        s.tap = st.ld<IData>(OFF_tap, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<IData>(OFF_din, i, s.din);
+        st.st<VlcuMem16>(OFF_sel, i, s.sel);
+        st.st<IData>(OFF_acc, i, s.acc);
+        st.st<IData>(OFF_tap, i, s.tap);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+        s.din = static_cast<IData>(rowp[1 * stride + i] & 0xffffffffU);
+        s.sel = static_cast<VlcuMem16>(rowp[2 * stride + i] & 0x3ffU);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+        rowp[0 * stride + i] = s.acc;
+        rowp[1 * stride + i] = s.tap;
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        acc = vlcu_sig_word(acc, s.acc);
+        acc = vlcu_sig_word(acc, s.tap);
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 3, kOutWords = 2, kInBytes = 7, kOutBytes = 8, kTraceWords = 0 };
+
+    VLCU_D static void Vt10_bigstate_im___024root___eval_static(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___eval_initial(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___eval_final(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___eval_settle(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static bool Vt10_bigstate_im___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt10_bigstate_im___024root___eval_phase__act(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt10_bigstate_im___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt10_bigstate_im___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt10_bigstate_im___024root___eval_phase__nba(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt10_bigstate_im___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _nba_sequent__TOP__0
+                        IData/*31:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i = 0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i = 0x000003ffU;
+                        while (VL_LTS_III(32, 0U, __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i)) {
+                            vlSelfRef.t10_bigstate__DOT__taps[(0x000003ffU 
+                                                               & __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i)] 
+                                = (vlSelfRef.t10_bigstate__DOT__taps
+                                   [(0x000003ffU & 
+                                     (__Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i 
+                                      - (IData)(1U)))] 
+                                   ^ ((vlSelfRef.t10_bigstate__DOT__taps
+                                       [(0x000003ffU 
+                                         & __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i)] 
+                                       << 1U) | (vlSelfRef.t10_bigstate__DOT__taps
+                                                 [(0x000003ffU 
+                                                   & __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i)] 
+                                                 >> 0x1fU)));
+                            __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i 
+                                = (__Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0_t10_bigstate__DOT__unnamedblk1__DOT__i 
+                                   - (IData)(1U));
+                        }
+                        vlSelfRef.t10_bigstate__DOT__taps[0U] 
+                            = vlSelfRef.din;
+                        vlSelfRef.acc = (vlSelfRef.acc 
+                                         + vlSelfRef.t10_bigstate__DOT__taps[1023U]);
+                        vlSelfRef.tap = (vlSelfRef.t10_bigstate__DOT__taps[512U] 
+                                         ^ vlSelfRef.t10_bigstate__DOT__taps[1U]);
+                    }
+                }
+            }
+            Vt10_bigstate_im___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___eval(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt10_bigstate_im___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("../verilator_b200/csrc/designs/torture/t10_bigstate.v", 6, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt10_bigstate_im___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("../verilator_b200/csrc/designs/torture/t10_bigstate.v", 6, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt10_bigstate_im___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt10_bigstate_im___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt10_bigstate_im___024root___ctor_var_reset(Vt10_bigstate_im___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->din = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 15192908731043726583ull);
+        vlSelf->sel = VL_SCOPED_RAND_RESET_I(10, __VscopeHash, 14660815779230110548ull);
+        vlSelf->acc = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 14651699267163694450ull);
+        vlSelf->tap = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 13933190746779120222ull);
+        for (int __Vi0 = 0; __Vi0 < 1024; ++__Vi0) {
+            vlSelf->t10_bigstate__DOT__taps[__Vi0] = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 11503233808722400224ull);
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt10_bigstate_im___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt10_bigstate_im___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt10_bigstate_im___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt10_bigstate_im___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt10_bigstate_im___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt10_bigstate_im___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt10_bigstate_im__cuda::info() {
+    typedef Vt10_bigstate_im__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"din", "din", VLCU_MEMBER_IN, 4, 0, 1, 32, 31, 0, T::OFF_din},
+        {"sel", "sel", VLCU_MEMBER_IN, 2, 0, 1, 10, 9, 0, T::OFF_sel},
+        {"acc", "acc", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_acc},
+        {"tap", "tap", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_tap},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"t10_bigstate__DOT__taps", "t10_bigstate.taps", VLCU_MEMBER_MEMORY, 4, 0, 1024, 32, 31, 0, T::OFF_t10_bigstate__DOT__taps},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 5, 6, 7, 2, 1, 3, 4, 8, 9, 10, 11, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t10_bigstate", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 0, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 12, 0, 0xd2ccd3d2441ea87bULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt10_bigstate_im__cuda VLCU_TESTBENCHES);
