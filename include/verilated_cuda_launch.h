@@ -281,7 +281,9 @@ struct VlcuStreamCfg final {
     static constexpr uint32_t kInStage = (T_Design::kInWords ? T_Design::kInWords : 1) * VLCU_BLOCK;  // words
     static constexpr uint32_t kOutStage = (T_Design::kOutWords ? T_Design::kOutWords : 1) * VLCU_BLOCK;
     static constexpr uint32_t kStageBytes = 4 * (kInStage + kOutStage);
-    static constexpr int kDepth = kStageBytes * 8 <= 28672 ? 8 : kStageBytes * 4 <= 28672 ? 4 : 2;
+    // per-CTA budget: 28 KB at the default 7 CTAs per SM, less when more CTAs are to be resident
+    static constexpr uint32_t kBudget = VLCU_MIN_BLOCKS <= 7 ? 28672U : (227U * 1024U / VLCU_MIN_BLOCKS - 1024U - 512U);
+    static constexpr int kDepth = kStageBytes * 8 <= kBudget ? 8 : kStageBytes * 4 <= kBudget ? 4 : 2;
     static constexpr bool kFits = kStageBytes * 2 + sizeof(typename T_Design::Shared) <= 40960;
 };
 

@@ -862,6 +862,21 @@ class EmitCudaModel final : public EmitCFunc {
         openOutputFile(cfilep, "Batched CUDA model (one instance per thread) for include/verilated_cuda.h");
         puts("// Design '" + v3Global.rootp()->topModulep()->prettyName() + "' printed by V3EmitCuda; compile with\n");
         puts("//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include\n");
+        {
+            // Occupancy target of the kernels (verilated_cuda_launch.h: __launch_bounds__(64,
+            // VLCU_MIN_BLOCKS), default 7 = 146 registers per thread).  A design that keeps almost
+            // nothing in registers -- its state is in memory-class arrays -- is bound by memory
+            // latency: compile it for 32 resident CTAs per SM (32 registers per thread, all 64
+            // warp slots) so that more loads are in flight.
+            uint32_t regBytes = 0;
+            for (const CudaMember& m : m_members) {
+                if (m.storage == CudaStorage::REG) regBytes += std::max<uint32_t>(m.bytes(), 4);
+            }
+            if (regBytes <= 64) {
+                puts("\n// " + cvtToStr(regBytes) + " bytes of register-resident state: latency-bound, compile for full occupancy\n");
+                puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 32\n#endif\n");
+            }
+        }
         puts("\n#include \"verilated_cuda_launch.h\"\n");
         puts("\n#include <vector>\n");
         puts("\n// Name the design registers under with vlcu_create()\n");

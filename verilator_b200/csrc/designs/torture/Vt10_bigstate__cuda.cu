@@ -3,6 +3,11 @@
 // Design '$root' printed by V3EmitCuda; compile with
 //   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
 
+// 52 bytes of register-resident state: latency-bound, compile for full occupancy
+#ifndef VLCU_MIN_BLOCKS
+#define VLCU_MIN_BLOCKS 32
+#endif
+
 #include "verilated_cuda_launch.h"
 
 #include <vector>
