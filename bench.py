@@ -170,6 +170,8 @@ class ClockSampler(threading.Thread):
 def dist_setup(n_gpus, backend="nccl"):
     from verilator_b200 import shard
     rank, world, local = shard.env_rank_world()
+    if world > 1:
+        shard.bind_to_gpu_numa_node(local)  # staging buffers in the GPU's own NUMA node
     dist = shard.init_process_group(backend, local) if world > 1 else None
     return rank, world, local, dist
 
@@ -416,7 +418,7 @@ def run_ours(args, wl):
     # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------
     threads = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (a reported baseline: rank 0, N=1 only)
         c_cycles = min(cycles, 4096)
         sample = cpu_sample_size(wl, c_cycles, threads, 15.0)
         cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)
@@ -570,7 +572,7 @@ def run_rows(args, wl):
         pass
     threads = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (a reported baseline: rank 0, N=1 only)
         c_cycles = wl.get("cpu_cycles", min(cycles, 4096))
         sample = cpu_sample_size(wl, c_cycles, threads, 15.0)
         cpu_value, cpu_dt = cpu_reference_run(wl, sample, c_cycles, threads)

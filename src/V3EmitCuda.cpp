@@ -893,9 +893,6 @@ class EmitCudaModel final : public EmitCFunc {
         puts("kStateBytes = " + cvtToStr(m_stateBytes) + ",  // S_persist\n");
         puts("kTouchedReadBytes = " + cvtToStr(m_touchedRead) + ",  // S_state_rd: persistent bytes one eval can read\n");
         puts("kTouchedWriteBytes = " + cvtToStr(m_touchedWrite) + ",  // S_state_wr\n");
-        // port rows are emitted later but the enum needs the sizes: collect first
-        V3OutCFile* const realOfp = ofp();
-        (void)realOfp;
         puts("};\n");
         // Storage of the arrays that are not in registers
         puts("struct Locals final {\n");
