@@ -13,7 +13,8 @@ import oracle_util as O
 
 pytestmark = pytest.mark.gpu
 
-DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate"]
+DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate",
+           "rnd01", "rnd02", "rnd03", "rnd04"]
 
 
 @pytest.fixture(scope="module")
