@@ -116,8 +116,10 @@ module cnt (input clk, input rst, input [15:0] step, output reg [31:0] acc);
 endmodule
 """)
     mdir = tmp_path / "obj_dir"
+    # (the lite front end cannot parse include/verilated_std.sv: --no-std)
     res = subprocess.run([os.path.join(ROOT, "bin", "verilator_cuda"), "--design", "counter", "--Mdir", str(mdir),
-                          "--prefix", "Vcnt", str(src)], capture_output=True, text=True)
+                          "--prefix", "Vcnt", "--no-std", "--no-std-waiver", str(src)], capture_output=True,
+                         text=True, env=dict(os.environ, VERILATOR_BIN=VLITE, VERILATOR_ROOT=REF))
     assert res.returncode == 0, res.stdout + res.stderr
     # a fresh process: this one may already hold libverilated_cuda.so with the same symbols
     probe = (
