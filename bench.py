@@ -29,6 +29,26 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: everything native libraries print there
+    (NCCL's version banner, for one) is sent to stderr; emit_json() writes to the real stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, line)
 for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
@@ -258,7 +278,7 @@ def run_reference(args, wl):
         units += sample * cycles
     value = units / t_total
     sample_txt = f"{sample} instances x {cycles} cycles per step on {threads} host threads"
-    print(json.dumps({
+    emit_json(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -438,7 +458,7 @@ def run_ours(args, wl):
                 "value": mt_cycles / (time.perf_counter() - t0), "unit": UNIT, "threads": 4,
                 "sample": f"1 instance x {mt_cycles} cycles, model Verilated with --threads 4"}
 
-    print(json.dumps({
+    emit_json(({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -579,7 +599,7 @@ def run_rows(args, wl):
         cpu = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "reference",
                "sample": f"{sample} instances x {c_cycles} cycles, {cpu_dt:.1f} s, {threads} threads, "
                          "one instance per thread at a time, stimulus generated in the harness"}
-    print(json.dumps({
+    emit_json(({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -632,6 +652,7 @@ def main():
                     help="ports_stream A/B: rows staged by 2-D tensor TMA tiles (default), by per-word 1-D "
                          "bulk copies, or read/written with plain global accesses")
     args = ap.parse_args()
+    claim_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, wl)
