@@ -220,6 +220,14 @@ uint64_t vlcu_launch_count(const vlcu_model_t* h); /* kernels launched so far by
 int vlcu_status(vlcu_model_t* h, vlcu_status_t* out /*[n_instances]*/);
 int vlcu_signatures(vlcu_model_t* h, uint64_t* out /*[n_instances]*/);
 int vlcu_reset_signatures(vlcu_model_t* h);
+/* The same read-backs without stalling the host: signatures, status records and the listed
+   members (host layout of vlcu_get_member, tightly packed) as they are once the work issued so far
+   has run, copied aside on the device and sent to the host on a separate stream.  Returns at once;
+   launch the next vlcu_run, then vlcu_results_wait() before reading the destinations (page-locked
+   memory, see vlcu_host_alloc).  sigs_out / status_out may be NULL.  One read-back at a time. */
+int vlcu_results_begin(vlcu_model_t* h, uint64_t* sigs_out, vlcu_status_t* status_out, int n_members,
+                       const int* members, void* const* member_dsts);
+int vlcu_results_wait(vlcu_model_t* h);
 int vlcu_messages(vlcu_model_t* h, uint64_t instance, vlcu_msg_t* out, uint32_t cap,
                   uint32_t* count);
 const char* vlcu_message_format(const vlcu_model_t* h, uint32_t id);

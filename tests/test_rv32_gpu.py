@@ -163,6 +163,24 @@ def test_pipelined_rounds_staged_while_the_previous_round_runs(abi):
                 m.stage_member("rv32_soc__DOT__mem", bufs[(r + 1) & 1])
             assert (m.signatures() == wants[r].sigs).all(), r
             check_final_state(m, wants[r])
+    # asynchronous read-back: results of round r are fetched while round r+1 computes
+    with abi.Model("rv32i", n, seed=6, rand_reset=2) as m:
+        res = [(pinned(abi, (n,), np.uint64), pinned(abi, (n,), abi.STATUS_DTYPE), pinned(abi, (n, 32), np.uint32),
+                pinned(abi, (n, 1024), np.uint32)) for _ in range(2)]
+        for r in range(rounds):
+            m.reset()
+            m.set_member("rv32_soc__DOT__mem", sets[r])
+            m.run("rv32_host", evals, flags=abi.RUNF_TB_BEGIN)
+            if r > 0:
+                m.results_wait()
+                sg, st, rg, mm = res[(r - 1) & 1]
+                assert (sg == wants[r - 1].sigs).all() and (rg == wants[r - 1].regs).all()
+                assert (mm == wants[r - 1].mem).all() and (st["time"] == evals).all()
+            sg, st, rg, mm = res[r & 1]
+            m.results_begin(sg, st, [("rv32_soc__DOT__regs", rg), ("rv32_soc__DOT__mem", mm)])
+        m.results_wait()
+        sg, st, rg, mm = res[(rounds - 1) & 1]
+        assert (sg == wants[-1].sigs).all() and (rg == wants[-1].regs).all() and (mm == wants[-1].mem).all()
     # ports take the scatter path, masked to their width like vlcu_set_input
     with abi.Model("make_tracing_c", n) as m:
         q = pinned(abi, (n, 1), np.uint64)

@@ -111,6 +111,8 @@ SIGNATURES = {
     "vlcu_status": (c_i32, [_H, c_vp]),
     "vlcu_signatures": (c_i32, [_H, c_vp]),
     "vlcu_reset_signatures": (c_i32, [_H]),
+    "vlcu_results_begin": (c_i32, [_H, c_vp, c_vp, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_vp)]),
+    "vlcu_results_wait": (c_i32, [_H]),
     "vlcu_messages": (c_i32, [_H, c_u64, c_vp, c_u32, ctypes.POINTER(c_u32)]),
     "vlcu_message_format": (c_cp, [_H, c_u32]),
     "vlcu_snapshot": (c_i32, [_H, c_u64, c_vp, ctypes.c_size_t]),
@@ -341,6 +343,18 @@ class Model:
         out = np.zeros(self.n, dtype=np.uint64)
         _check(lib.vlcu_signatures(self.h, out.ctypes.data))
         return out
+
+    def results_begin(self, sigs=None, status=None, members=()):
+        """Start the asynchronous read-back of signatures (uint64 [n]), status (STATUS_DTYPE [n]) and
+        `members` = [(name, array [n][elems])...] into page-locked arrays; results_wait() completes it."""
+        k = len(members)
+        idx = (c_i32 * max(k, 1))(*[self.members[name][0] for name, _ in members])
+        dsts = (c_vp * max(k, 1))(*[arr.ctypes.data for _, arr in members])
+        _check(lib.vlcu_results_begin(self.h, sigs.ctypes.data if sigs is not None else None,
+                                      status.ctypes.data if status is not None else None, k, idx, dsts))
+
+    def results_wait(self):
+        _check(lib.vlcu_results_wait(self.h))
 
     def messages(self, instance, cap=64):
         out = np.zeros(cap, dtype=MSG_DTYPE)

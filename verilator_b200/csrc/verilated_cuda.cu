@@ -160,6 +160,13 @@ struct vlcu_model final {
     cudaEvent_t evConsumed = nullptr;  // last commit finished reading the staging buffers
     bool haveConsumed = false;
     std::map<int, Staged> staged;  // by member index
+    // Asynchronous result read-back (vlcu_results_begin / vlcu_results_wait)
+    cudaStream_t resStream = nullptr;
+    cudaEvent_t evCaptured = nullptr;  // compute stream: the results were copied aside
+    cudaEvent_t evFetched = nullptr;  // result stream: the previous read-back reached the host
+    bool fetchPending = false;
+    uint8_t* dRes = nullptr;  // device-side copy of the results being read back
+    size_t resBytes = 0;
 };
 
 namespace {
@@ -723,6 +730,11 @@ void vlcu_destroy(vlcu_model_t* h) {
     if (h->copyStream) cudaStreamSynchronize(h->copyStream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& it : h->staged) cudaFree(it.second.dBuf);
+    if (h->resStream) cudaStreamSynchronize(h->resStream);
+    cudaFree(h->dRes);
+    if (h->evCaptured) cudaEventDestroy(h->evCaptured);
+    if (h->evFetched) cudaEventDestroy(h->evFetched);
+    if (h->resStream) cudaStreamDestroy(h->resStream);
     if (h->evCopied) cudaEventDestroy(h->evCopied);
     if (h->evConsumed) cudaEventDestroy(h->evConsumed);
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
@@ -1097,6 +1109,117 @@ int vlcu_signatures(vlcu_model_t* h, uint64_t* out) {
     CUDA_TRY(cudaMemcpyAsync(out, h->dSigs, sizeof(uint64_t) * h->n, cudaMemcpyDeviceToHost,
                              h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return VLCU_OK;
+}
+// Asynchronous result read-back for pipelined campaigns.  vlcu_results_begin() copies the
+// signatures, the status records and the listed members aside ON THE DEVICE, ordered behind the
+// work already issued on the model's stream (a few MB at HBM speed), and starts their
+// device->host copies on a separate stream; it returns at once, so the next vlcu_run can be
+// launched while the results travel.  vlcu_results_wait() blocks until they have arrived.  One
+// read-back can be in flight; destinations should be page-locked (vlcu_host_alloc).
+int vlcu_results_begin(vlcu_model_t* h, uint64_t* sigs_out, vlcu_status_t* status_out, int n_members,
+                       const int* members, void* const* member_dsts) {
+    if (!h || n_members < 0 || (n_members && (!members || !member_dsts))) {
+        return fail(VLCU_E_ARG, "vlcu_results_begin: bad argument");
+    }
+    DeviceGuard guard{h->device};
+    if (!h->resStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->resStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evCaptured, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evFetched, cudaEventDisableTiming));
+    }
+    const uint64_t n = h->n;
+    size_t need = 0;
+    const size_t sigOff = need;
+    if (sigs_out) need += sizeof(uint64_t) * n;
+    const size_t ctxOff = need;
+    if (status_out) need += sizeof(VlcuCtxRec) * n;
+    std::vector<size_t> memOff(n_members);
+    for (int k = 0; k < n_members; ++k) {
+        const VlcuMemberDesc* const mdp = memberAt(h, members[k]);
+        if (!mdp || !member_dsts[k]) return fail(VLCU_E_ARG, "vlcu_results_begin: bad member");
+        need = (need + 15) & ~size_t{15};
+        memOff[k] = need;
+        need += static_cast<size_t>(mdp->elemBytes) * mdp->elems * n;
+    }
+    if (need > h->resBytes) {
+        if (h->fetchPending) CUDA_TRY(cudaStreamSynchronize(h->resStream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        cudaFree(h->dRes);
+        h->dRes = nullptr;
+        h->resBytes = 0;
+        CUDA_TRY(cudaMalloc(&h->dRes, need));
+        h->resBytes = need;
+    }
+    // the previous read-back must have left the device buffer before it is overwritten
+    if (h->fetchPending) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->evFetched, 0));
+    if (sigs_out) {
+        CUDA_TRY(cudaMemcpyAsync(h->dRes + sigOff, h->dSigs, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice,
+                                 h->stream));
+    }
+    if (status_out) {
+        CUDA_TRY(cudaMemcpyAsync(h->dRes + ctxOff, h->dCtx, sizeof(VlcuCtxRec) * n, cudaMemcpyDeviceToDevice,
+                                 h->stream));
+    }
+    for (int k = 0; k < n_members; ++k) {
+        const VlcuMemberDesc& md = h->infop->members[members[k]];
+        const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
+        const uint8_t* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+        if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major already
+            CUDA_TRY(cudaMemcpyAsync(h->dRes + memOff[k], soap, recBytes * n, cudaMemcpyDeviceToDevice,
+                                     h->stream));
+            continue;
+        }
+        const unsigned threads = 256, blocks = blocksFor(n * md.elems, threads);
+        switch (md.elemBytes) {
+        case 1:
+            k_gather<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dRes + memOff[k], soap, n, h->npad, md.elems);
+            break;
+        case 2:
+            k_gather<uint16_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint16_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint16_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        case 4:
+            k_gather<uint32_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint32_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint32_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        default:
+            k_gather<uint64_t><<<blocks, threads, 0, h->stream>>>(
+                reinterpret_cast<uint64_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint64_t*>(soap), n,
+                h->npad, md.elems);
+            break;
+        }
+        ++h->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(h->evCaptured, h->stream));
+    CUDA_TRY(cudaStreamWaitEvent(h->resStream, h->evCaptured, 0));
+    if (sigs_out) {
+        CUDA_TRY(cudaMemcpyAsync(sigs_out, h->dRes + sigOff, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost,
+                                 h->resStream));
+    }
+    if (status_out) {
+        CUDA_TRY(cudaMemcpyAsync(status_out, h->dRes + ctxOff, sizeof(VlcuCtxRec) * n, cudaMemcpyDeviceToHost,
+                                 h->resStream));
+    }
+    for (int k = 0; k < n_members; ++k) {
+        const VlcuMemberDesc& md = h->infop->members[members[k]];
+        CUDA_TRY(cudaMemcpyAsync(member_dsts[k], h->dRes + memOff[k],
+                                 static_cast<size_t>(md.elemBytes) * md.elems * n, cudaMemcpyDeviceToHost,
+                                 h->resStream));
+    }
+    CUDA_TRY(cudaEventRecord(h->evFetched, h->resStream));
+    h->fetchPending = true;
+    return VLCU_OK;
+}
+int vlcu_results_wait(vlcu_model_t* h) {
+    if (!h) return fail(VLCU_E_ARG, "null model");
+    if (!h->fetchPending) return VLCU_OK;
+    DeviceGuard guard{h->device};
+    CUDA_TRY(cudaEventSynchronize(h->evFetched));
+    h->fetchPending = false;
     return VLCU_OK;
 }
 int vlcu_reset_signatures(vlcu_model_t* h) {
