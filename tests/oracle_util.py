@@ -1,7 +1,8 @@
 """Bindings to the ORACLE (oracle/_ref/libvlref.so) -- TEST INFRASTRUCTURE.
 
 libvlref.so = the reference's own runtime (include/verilated*.cpp compiled from
-/root/reference) + the restated reference models under oracle/models/.
+/root/reference) + the GENUINE Verilated C++ models the reference's own compiler
+(oracle/_ref/verilator_lite) writes for each design + the harnesses under oracle/models/.
 """
 import ctypes
 import os
@@ -70,7 +71,7 @@ class MtcResult:
 def mtc_run(n, n_evals, inst_base=0, seed=1, rand_reset=2, stop_on_finish=False, tb_seed=0,
             per_instance=False, reset_period=0, trace_plusarg=False, obs_evals=0, vcd_path=None,
             vcd_instance=-1, cov_path=None, cov_instance=-1, threads=1):
-    """Run the restated reference model of examples/make_tracing_c for n instances."""
+    """Run the genuine Verilated model of examples/make_tracing_c for n instances."""
     r = MtcResult()
     r.obs = np.zeros((max(obs_evals, 1), 6, n), dtype=np.uint32)
     r.sigs = np.zeros(n, dtype=np.uint64)

@@ -1,8 +1,8 @@
 """Parity of the batched CUDA evaluator with the oracle for examples/make_tracing_c
 (BASELINE.json config 1), through the C ABI (include/verilated_cuda_abi.h).
 
-Oracle = restated reference model against the genuine runtime (oracle/models/make_tracing_c,
-pinned by tests/test_oracle.py).  Bit-exact: every output port of every instance after every
+Oracle = the genuine Verilated C++ model (written by the reference's own compiler) against the
+genuine runtime, driven by oracle/models/make_tracing_c/harness.cpp; pinned by tests/test_oracle.py.  Bit-exact: every output port of every instance after every
 eval, context flags, $display records, coverage counters, coverage.dat text.
 """
 import json

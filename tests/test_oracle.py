@@ -3,7 +3,8 @@
 * operator level: oracle/_ref/libvlref.so is the reference's own runtime; its PRNG / x-initial
   values must reproduce the reference regression golden t_x_rand_stability.out
   (tests/golden/x_rand_stability.json, extracted by tests/golden/gen_x_rand_stability.py).
-* design level: the restated model of examples/make_tracing_c must agree with an independent
+* design level: the genuine Verilated model of examples/make_tracing_c (built through the lite
+  front end) must agree with an independent
   behavioural model of the Verilog (tests/golden/make_tracing_c_ports.json) and print the
   "*-* All Finished *-*" line the example's Makefile checks for.
 * the host-compiled device PRNG/hash restatement must agree with both.
@@ -61,7 +62,7 @@ def test_vlrng_stream_matches_reference():
         assert (a == b).all() and len(set(a.tolist())) == 8
 
 
-def test_restated_model_matches_behavioural_golden():
+def test_genuine_model_matches_behavioural_golden():
     gold = json.load(open(os.path.join(GOLD, "make_tracing_c_ports.json")))["default"]
     r = O.mtc_run(1, gold["n_evals"], rand_reset=2, obs_evals=gold["n_evals"])
     rows = np.array(gold["rows"], dtype=np.uint64)
@@ -72,14 +73,14 @@ def test_restated_model_matches_behavioural_golden():
     assert int(r.final[0, 0]) == gold["rows"][-1][6]
 
 
-def test_restated_model_console_and_finish_like_sim_main():
+def test_genuine_model_console_and_finish_like_sim_main():
     r = O.mtc_run(1, 1000, rand_reset=2, stop_on_finish=True, trace_plusarg=True)
     assert r.console.endswith("*-* All Finished *-*\n")
     assert "[1] Model running..." in r.console and "[1] Tracing to logs/vlt_dump.vcd..." in r.console
     assert int(r.status["time"][0]) == 17  # sim_main's loop ends at the first gotFinish()
 
 
-def test_restated_model_long_run_with_periodic_reset():
+def test_genuine_model_long_run_with_periodic_reset():
     gold = json.load(open(os.path.join(GOLD, "make_tracing_c_ports.json")))["period128"]
     r = O.mtc_run(1, gold["n_evals"], rand_reset=2, reset_period=128, obs_evals=gold["n_evals"])
     rows = np.array(gold["rows_last"], dtype=np.uint64)
