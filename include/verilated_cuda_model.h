@@ -106,6 +106,45 @@ public:
         return out;
     }
 
+    // PIPELINED CAMPAIGNS: the next batch's inputs travel while this batch computes, and this
+    // batch's results while the next one computes (page-locked buffers: vlcu_host_alloc)
+    int member(const char* name) const {
+        const int m = vlcu_member_index(m_h, name);
+        check(m < 0 ? m : VLCU_OK, name);
+        return m;
+    }
+    void stage(int member, const void* src, size_t strideBytes, bool maskWidth = true) {
+        check(vlcu_stage_member(m_h, member, src, strideBytes, maskWidth ? 1 : 0), "vlcu_stage_member");
+    }
+    void commitStaged() { check(vlcu_commit_staged(m_h), "vlcu_commit_staged"); }
+    void resultsBegin(uint64_t* sigs, vlcu_status_t* status, const std::vector<int>& members = {},
+                      const std::vector<void*>& dsts = {}) {
+        check(vlcu_results_begin(m_h, sigs, status, static_cast<int>(members.size()), members.data(),
+                                 dsts.data()),
+              "vlcu_results_begin");
+    }
+    void resultsWait() { check(vlcu_results_wait(m_h), "vlcu_results_wait"); }
+
+    // SAVE / RESTORE  (VerilatedSave os; os << *top;  /  VerilatedRestore os; os >> *top;  for one
+    // instance, in the reference's file format: include/verilated_save.h:193-223)
+    void save(uint64_t instance, const char* filename) {
+        check(vlcu_save_instance(m_h, instance, filename), "vlcu_save_instance");
+    }
+    void restore(uint64_t instance, const char* filename) {
+        check(vlcu_restore_instance(m_h, instance, filename), "vlcu_restore_instance");
+    }
+
+    // WAVEFORMS  (tfp->dump(time) of a sampled instance; `trace` / `streams` as vlcu_run filled them)
+    void vcdWrite(const void* trace, uint64_t traceEvals, uint32_t nSamples, uint32_t sample,
+                  const char* filename) {
+        check(vlcu_vcd_write(m_h, trace, traceEvals, nSamples, sample, filename), "vlcu_vcd_write");
+    }
+    void vcdWriteChanges(const uint32_t* streams, uint32_t streamWords, uint32_t nSamples, uint32_t sample,
+                         const char* filename) {
+        check(vlcu_vcd_write_changes(m_h, streams, streamWords, nSamples, sample, filename),
+              "vlcu_vcd_write_changes");
+    }
+
     // COVERAGE  (contextp->coveragep()->write(filename) for the sum over all instances)
     std::vector<uint64_t> coverageReduce() {
         std::vector<uint64_t> out(vlcu_coverage_bins(m_h));
