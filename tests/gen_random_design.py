@@ -102,7 +102,7 @@ class Gen:
         return self.operand(depth)
 
 
-def generate(seed, name):
+def generate(seed, name, wires=12, depth=2):
     g = Gen(seed)
     r = g.r
     out = [f"// {name}: random design, python tests/gen_random_design.py {seed} {name}",
@@ -127,9 +127,9 @@ def generate(seed, name):
         regs.append((f"r{i}", w))
     body.append("  reg [23:0] mem [0:15];")
     g.sigs.extend(regs)
-    for i in range(12):
+    for i in range(wires):
         w = r.choice(WIDTHS)
-        body.append(f"  wire [{w - 1}:0] w{i} = {g.expr(2)};")
+        body.append(f"  wire [{w - 1}:0] w{i} = {g.expr(depth)};")
         g.sigs.append((f"w{i}", w))
     body.append("  always @(posedge clk) begin")
     for name_, w in regs:
@@ -150,4 +150,5 @@ def generate(seed, name):
 
 
 if __name__ == "__main__":
-    sys.stdout.write(generate(int(sys.argv[1]), sys.argv[2]))
+    # optional: number of wires and expression depth (the committed designs use the defaults)
+    sys.stdout.write(generate(int(sys.argv[1]), sys.argv[2], *(int(a) for a in sys.argv[3:5])))
