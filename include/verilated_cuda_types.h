@@ -182,94 +182,101 @@ struct VlUnpacked final {
 };
 
 //=========================================================================
-// VlNBACommitQueue -- deferred array-element writes, committed in program
-// order at the end of the NBA region.  The host runtime grows a std::vector;
-// a CUDA thread cannot, so the capacity is a template argument that the
-// emitter derives from the static bound of the enclosing loop.  Overflow is
-// reported through 'overflowed()' and raised as a per-instance fatal by the
-// caller, never silently dropped.
+// VlNBACommitQueue -- deferred array-element writes (V3Delayed's ValueQueue schemes,
+// V3Delayed.cpp:47-110), committed in program order at the end of the NBA region
+// (verilated_types.h:1854-1977).  Same template head and enqueue()/commit() calls as the host
+// class, so the text EmitCFunc prints compiles against it.  Differences a CUDA thread imposes:
+//  - the host class grows a std::vector; here the capacity is a template argument (V3EmitCuda
+//    derives it from the size of the target array) and an overflow is recorded, raised by the
+//    model's eval wrapper as a per-instance fatal (VLCU_FATAL_NBAQ_OVERFLOW), never dropped
+//    silently;
+//  - the entries live in thread-local memory OUTSIDE the model image (T_Design::Locals, bound
+//    like VlcuLocalArray): an indexed array inside the image would push the whole image out of
+//    registers;
+//  - commit() takes whichever array class the emitter chose for the target (VlUnpacked,
+//    VlcuSharedArray, VlcuLocalArray, VlcuGlobalArray, VlcuStateArray, VlcuMdArray): anything
+//    indexable with N_Rank operator[] calls.
 
-template <typename T_Element, size_t N_Rank, size_t N_Capacity, bool Partial>
+template <typename T_Target, bool Partial, typename T_Element, size_t N_Rank, size_t N_Capacity = 32>
 class VlNBACommitQueue final {
+public:
     struct Entry final {
         T_Element value;
-        T_Element mask;
+        T_Element mask;  // (Partial only)
         uint32_t indices[N_Rank];
     };
-    Entry m_pending[N_Capacity];
+    struct Store final {
+        Entry pending[N_Capacity];
+    };
+
+private:
+    Store* m_storep = nullptr;
     uint32_t m_size = 0;
     bool m_overflow = false;
 
-    template <typename T_Target>
-    VLCU_HD static T_Element& element(T_Target& target, const uint32_t* idx) {
-        return elementAt(target, idx, 0);
+    template <size_t I, typename T_Array>
+    VLCU_HD static decltype(auto) at(T_Array&& arr, const uint32_t* idx) {
+        if constexpr (I + 1 == N_Rank) {
+            return (arr[idx[I]]);
+        } else {
+            return at<I + 1>(arr[idx[I]], idx);
+        }
     }
-    VLCU_HD static T_Element& elementAt(T_Element& leaf, const uint32_t*, size_t) { return leaf; }
-    template <typename T_Sub, size_t N>
-    VLCU_HD static T_Element& elementAt(VlUnpacked<T_Sub, N>& arr, const uint32_t* idx,
-                                        size_t dim) {
-        return elementAt(arr[idx[dim]], idx, dim + 1);
-    }
-    VLCU_HD static void blend(IData& ref, const IData& v, const IData& m) {
-        ref = (v & m) | (ref & ~m);
-    }
-    VLCU_HD static void blend(QData& ref, const QData& v, const QData& m) {
-        ref = (v & m) | (ref & ~m);
-    }
-    VLCU_HD static void blend(VlcuMem16& ref, const VlcuMem16& v, const VlcuMem16& m) {
-        ref = static_cast<VlcuMem16>((v & m) | (ref & ~m));
-    }
-    VLCU_HD static void blend(VlcuMem8& ref, const VlcuMem8& v, const VlcuMem8& m) {
-        ref = static_cast<VlcuMem8>((v & m) | (ref & ~m));
+    template <typename T_Ref, typename T_Val>
+    VLCU_HD static void blend(T_Ref& ref, const T_Val& v, const T_Val& m) {
+        ref = static_cast<T_Ref>((v & m) | (ref & ~m));
     }
     template <size_t N>
     VLCU_HD static void blend(VlWide<N>& ref, const VlWide<N>& v, const VlWide<N>& m) {
         for (size_t i = 0; i < N; ++i) ref[i] = (v[i] & m[i]) | (ref[i] & ~m[i]);
     }
+    template <typename... T_Args>
+    VLCU_HD Entry* push(T_Args... indices) {
+        static_assert(sizeof...(indices) == N_Rank, "one index per unpacked dimension");
+        if (m_size >= N_Capacity) {
+            m_overflow = true;
+            return nullptr;
+        }
+        Entry* const ep = &m_storep->pending[m_size++];
+        const uint32_t tmp[] = {static_cast<uint32_t>(indices)...};
+        for (size_t i = 0; i < N_Rank; ++i) ep->indices[i] = tmp[i];
+        return ep;
+    }
 
 public:
-    VLCU_HD void clear() {
+    VLCU_HD void bind(Store* storep) {
+        m_storep = storep;
         m_size = 0;
         m_overflow = false;
     }
     VLCU_HD bool overflowed() const { return m_overflow; }
     VLCU_HD uint32_t size() const { return m_size; }
 
-    // Whole-element form: enqueue(value, i0[, i1...])
+    // Whole-element form (Partial == false): enqueue(value, i0[, i1...])
+    // Partial-element form (Partial == true): enqueue(value, mask, i0[, i1...])
     template <typename... T_Args>
-    VLCU_HD void enqueue(const T_Element& value, T_Args... indices) {
-        static_assert(!Partial || sizeof...(indices) == N_Rank + 0 || true, "");
-        if (m_size >= N_Capacity) {
-            m_overflow = true;
-            return;
+    VLCU_HD void enqueue(const T_Element& value, T_Args... rest) {
+        if constexpr (Partial) {
+            enqueuePartial(value, rest...);
+        } else {
+            if (Entry* const ep = push(rest...)) ep->value = value;
         }
-        Entry& e = m_pending[m_size++];
-        e.value = value;
-        const uint32_t tmp[] = {static_cast<uint32_t>(indices)...};
-        for (size_t i = 0; i < N_Rank; ++i) e.indices[i] = tmp[i];
     }
-    // Partial-element form: enqueueMasked(value, mask, i0[, i1...])
     template <typename... T_Args>
-    VLCU_HD void enqueueMasked(const T_Element& value, const T_Element& mask, T_Args... indices) {
-        if (m_size >= N_Capacity) {
-            m_overflow = true;
-            return;
+    VLCU_HD void enqueuePartial(const T_Element& value, const T_Element& mask, T_Args... indices) {
+        if (Entry* const ep = push(indices...)) {
+            ep->value = value;
+            ep->mask = mask;
         }
-        Entry& e = m_pending[m_size++];
-        e.value = value;
-        e.mask = mask;
-        const uint32_t tmp[] = {static_cast<uint32_t>(indices)...};
-        for (size_t i = 0; i < N_Rank; ++i) e.indices[i] = tmp[i];
     }
     template <typename T_Commit>
     VLCU_HD void commit(T_Commit& target) {
         for (uint32_t n = 0; n < m_size; ++n) {
-            Entry& e = m_pending[n];
-            T_Element& ref = element(target, e.indices);
-            if (Partial) {
-                blend(ref, e.value, e.mask);
+            const Entry& e = m_storep->pending[n];
+            if constexpr (Partial) {
+                blend(at<0>(target, e.indices), e.value, e.mask);
             } else {
-                ref = e.value;
+                at<0>(target, e.indices) = e.value;
             }
         }
         m_size = 0;

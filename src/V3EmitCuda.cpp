@@ -149,6 +149,7 @@ class EmitCudaModel final : public EmitCFunc {
     std::vector<CudaMember> m_members;
     std::map<const AstVar*, size_t> m_memberOf;
     std::set<const AstVar*> m_dataIndexed;  // arrays with an index that differs between instances
+    std::vector<std::pair<string, string>> m_nbaQueues;  // VlNBACommitQueue members: name, device type
     std::vector<string> m_messages;
     std::vector<string> m_plusargs;
     int m_coverBins = 0;
@@ -189,6 +190,22 @@ class EmitCudaModel final : public EmitCFunc {
             m.kind = varp->isInout() ? 2 : varp->isWritable() ? 1 : 0;
         }
         const AstNodeDType* dtp = varp->dtypep()->skipRefp();
+        if (const AstNBACommitQueueDType* const qdtp = VN_CAST(dtp, NBACommitQueueDType)) {
+            // V3Delayed's ValueQueue scheme: not persistent (empty between evals), so no slot in
+            // the state block; entries in thread-local memory, capacity from the target's size
+            uint32_t elems = 1;
+            for (const AstNodeDType* tp = qdtp->subDTypep()->skipRefp(); VN_IS(tp, UnpackArrayDType);
+                 tp = VN_AS(tp, UnpackArrayDType)->subDTypep()->skipRefp()) {
+                elems *= VN_AS(tp, UnpackArrayDType)->elementsConst();
+            }
+            const uint32_t capacity = std::min<uint32_t>(std::max<uint32_t>(2 * elems, 16), 256);
+            string type = dtp->cType("", false, false);
+            const string::size_type close = type.rfind('>');
+            UASSERT_OBJ(close != string::npos, varp, "unexpected VlNBACommitQueue type text");
+            type.insert(close, ", " + cvtToStr(capacity));
+            m_nbaQueues.emplace_back(varp->nameProtect(), type);
+            return;
+        }
         if (const AstUnpackArrayDType* const adtp = VN_CAST(dtp, UnpackArrayDType)) {
             // VlUnpacked<VlUnpacked<T, D1>, D0>: kept flat, row-major (VlcuMdArray)
             m.isArray = true;
@@ -372,6 +389,9 @@ class EmitCudaModel final : public EmitCFunc {
                          ? "  // stays in HBM, [element][instance]: instance-uniform indices coalesce\n"
                                                        : "  // stays in HBM, instance-major\n");
             }
+        }
+        for (const auto& q : m_nbaQueues) {
+            puts(q.second + " " + q.first + ";  // entries in thread-local memory (Locals)\n");
         }
         puts("const char* vlNamep;\n");
         puts("};\n");
@@ -899,6 +919,7 @@ class EmitCudaModel final : public EmitCFunc {
         for (const CudaMember& m : m_members) {
             if (m.storage == CudaStorage::LOCAL) puts(m.elemDecl + " " + m.name + "[" + cvtToStr(m.depth) + "];\n");
         }
+        for (const auto& q : m_nbaQueues) puts(q.second + "::Store " + q.first + ";\n");
         puts("};\n");
         puts("struct Shared final {\n");
         for (const CudaMember& m : m_members) {
@@ -910,6 +931,7 @@ class EmitCudaModel final : public EmitCFunc {
         puts("VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {\n");
         puts("(void)l; (void)sh; (void)st; (void)i;\n");
         puts("s.vlNamep = \"TOP\";\n");
+        for (const auto& q : m_nbaQueues) puts("s." + q.first + ".bind(&l." + q.first + ");\n");
         for (const CudaMember& m : m_members) {
             if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
             if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
@@ -948,7 +970,19 @@ class EmitCudaModel final : public EmitCFunc {
         emitWrapper("eval_static", "_eval_static");
         emitWrapper("eval_initial", "_eval_initial");
         emitWrapper("eval_settle", "_eval_settle");
-        emitWrapper("eval", "_eval");
+        if (m_nbaQueues.empty()) {
+            emitWrapper("eval", "_eval");
+        } else {
+            // a full commit queue cannot grow on the device: the instance takes a fatal instead
+            puts("VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) {\n");
+            if (const AstCFunc* const funcp = findFunc("_eval")) {
+                puts(funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx);\n");
+            }
+            for (const auto& q : m_nbaQueues) {
+                puts("if (VL_UNLIKELY(vlSelf->" + q.first + ".overflowed())) vlCtx.fatal(0, VLCU_FATAL_NBAQ_OVERFLOW);\n");
+            }
+            puts("}\n");
+        }
         emitWrapper("eval_final", "_eval_final");
         puts("\nstatic const VlcuDesignInfo& info();\n");
         puts("};\n");
