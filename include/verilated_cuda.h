@@ -54,6 +54,11 @@ public:
         m_s0 = vlcu_splitmix64(x);
         m_s1 = vlcu_splitmix64(x);
     }
+    VLCU_HD VlRNG(uint64_t s0, uint64_t s1)
+        : m_s0{s0}
+        , m_s1{s1} {}
+    VLCU_HD uint64_t s0() const { return m_s0; }
+    VLCU_HD uint64_t s1() const { return m_s1; }
     VLCU_HD uint64_t rand64() {
         const uint64_t result = vlcu_rotl64(m_s0 * 5, 7) * 9;
         const uint64_t t = m_s1 ^ m_s0;
@@ -278,6 +283,7 @@ struct VlcuContext final {
     uint32_t m_errorLimit;
     // Cold part, in HBM
     VlcuCtxRec* m_recp;
+    uint64_t* m_rngp;  // this instance's $random / $urandom generator state {s0, s1}
     VlcuMsg* m_msgp;  // this instance's slice of the message log
     uint32_t m_msgCap;
 
@@ -337,6 +343,23 @@ struct VlcuContext final {
         ++m_msgCount;
     }
 };
+
+VLCU_HD uint64_t vlcu_rng_rand64(VlcuContext& ctx) {
+    VlRNG rng{ctx.m_rngp[0], ctx.m_rngp[1]};
+    const uint64_t result = rng.rand64();
+    ctx.m_rngp[0] = rng.s0();
+    ctx.m_rngp[1] = rng.s1();
+    return result;
+}
+// (function-like macros: the emitted call has no context argument; every device function of a
+// model has `vlCtx` in scope)
+#define VL_RANDOM_I() static_cast<IData>(vlcu_rng_rand64(vlCtx))
+#define VL_RANDOM_Q() static_cast<QData>(vlcu_rng_rand64(vlCtx))
+#define VL_RANDOM_W(obits, outwp) vlcu_random_w(vlCtx, (obits), (outwp))
+VLCU_HD WDataOutP vlcu_random_w(VlcuContext& ctx, int obits, WDataOutP outwp) {
+    for (int i = 0; i < VL_WORDS_I(obits); ++i) outwp[i] = static_cast<EData>(vlcu_rng_rand64(ctx));
+    return outwp;  // (last word is unclean, as on the host)
+}
 
 // Older hand-written spellings
 #define VLCU_FINISH(ctx, line) (ctx).finish(line)
@@ -679,11 +702,27 @@ struct VlcuModelDev final {
     uint32_t msgCap;
     uint32_t plusargs;
     uint32_t errorLimit;
+    uint64_t* rng;  // [instance][2]: $random / $urandom generator state
 };
+
+// $random / $urandom (VL_RANDOM_I/Q/W, verilated_funcs.h:90-91, verilated.cpp:537-555).  The
+// host draws from a thread-local generator that is reseeded from the context's seed whenever a
+// seed is set (verilated.cpp:537-549), i.e. with one model per thread each model has its own
+// stream seeded with randSeedDefault64() (verilated.cpp:3701-3707).  Here each instance owns its
+// generator state (two words in HBM, touched only when the design calls $random).
+VLCU_HD void vlcu_rng_seed(uint64_t* statep, uint64_t randSeed) {
+    // randSeed() is an int: the 64-bit seed is (seed << 32) ^ seed with sign extension
+    const uint64_t s = static_cast<uint64_t>(static_cast<int64_t>(static_cast<int32_t>(randSeed)));
+    const VlRNG rng{(s << 32) ^ s};
+    statep[0] = rng.s0();
+    statep[1] = rng.s1();
+}
+VLCU_HD uint64_t vlcu_rng_rand64(VlcuContext& ctx);
 
 VLCU_HD void vlcu_ctx_load(VlcuContext& ctx, const VlcuModelDev& m, uint64_t inst) {
     VlcuCtxRec* const recp = &m.ctxRecs[inst];
     ctx.m_recp = recp;
+    ctx.m_rngp = m.rng + 2 * inst;
     ctx.m_time = recp->time;
     ctx.m_status = recp->status;
     ctx.m_msgCount = recp->msgCount;

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(VLCU_BLOCK) vlcu_k_reset(VlcuModelDev m) {
     if (inst >= m.n) return;
     VlcuCtxRec* const recp = &m.ctxRecs[inst];
     *recp = VlcuCtxRec{};
+    vlcu_rng_seed(m.rng + 2 * inst, m.seedBase ^ (m.instBase + inst));
     VlcuContext ctx;
     vlcu_ctx_load(ctx, m, inst);
     typename T_Design::Root root;

@@ -50,6 +50,9 @@ void getPort(const VlWide<N>& port, uint32_t* out) {
     for (size_t w = 0; w < N; ++w) out[w] = port[w];
 }
 
+// an inout port is driven from the stimulus row like an input and observed like an output
+#define VLCU_PORT_INOUT(name, width, words) VLCU_PORT_IN(name, width, words) VLCU_PORT_OUT(name, width, words)
+
 constexpr int kInWords = 0
 #define VLCU_PORT_IN(name, width, words) +words
 #define VLCU_PORT_OUT(name, width, words)

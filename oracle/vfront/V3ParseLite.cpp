@@ -992,6 +992,22 @@ class Parser final {
             if (argsp) VL_DO_DANGLING(argsp->deleteTree(), argsp);
             return new AstStop{name.fl, false};
         }
+        if (name.text == "$error") {  // yD_ERROR (verilog.y:4319-4322)
+            AstNode* const dispp = new AstDisplay{name.fl, VDisplayType::DT_ERROR, nullptr, argsp};
+            dispp->addNext(new AstStop{name.fl, false});
+            return VN_AS(dispp, NodeStmt);
+        }
+        if (name.text == "$fatal") {  // yD_FATAL: the first argument is the finish number (verilog.y:4323-4331)
+            AstNodeExpr* restp = nullptr;
+            if (argsp) {
+                restp = VN_CAST(argsp->nextp(), NodeExpr);
+                if (restp) restp->unlinkFrBackWithNext();
+                VL_DO_DANGLING(argsp->deleteTree(), argsp);
+            }
+            AstNode* const dispp = new AstDisplay{name.fl, VDisplayType::DT_FATAL, nullptr, restp};
+            dispp->addNext(new AstStop{name.fl, true});
+            return VN_AS(dispp, NodeStmt);
+        }
         if (name.text == "$dumpfile") return new AstDumpCtl{name.fl, VDumpCtlType::FILE, argsp};
         if (name.text == "$dumpvars") {
             return new AstDumpCtl{name.fl, VDumpCtlType::VARS, argsp ? argsp : new AstConst{name.fl, 0}};
@@ -1202,6 +1218,10 @@ class Parser final {
         if (name.text == "$time") {
             need(0);
             return new AstTime{name.fl, VTimescale{VTimescale::NONE}};
+        }
+        if (name.text == "$urandom" || name.text == "$random") {  // yD_URANDOM / yD_RANDOM parenE (verilog.y:4516-4559)
+            need(0);
+            return new AstRand{name.fl, nullptr, name.text == "$urandom"};
         }
         if (name.text == "$signed") { need(1); return new AstSigned{name.fl, args[0]}; }
         if (name.text == "$unsigned") { need(1); return new AstUnsigned{name.fl, args[0]}; }

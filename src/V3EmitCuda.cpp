@@ -1003,10 +1003,10 @@ class EmitCudaModel final : public EmitCFunc {
         const string fileName = v3Global.opt.makeDir() + "/" + v3Global.opt.prefix() + "__ports.inc";
         std::ofstream os{fileName};
         os << "// Primary ports of " << v3Global.opt.prefix() << " in source order (printed by V3EmitCuda)\n";
-        os << "// VLCU_PORT_IN / VLCU_PORT_OUT (member name, width in bits, 32-bit row words)\n";
+        os << "// VLCU_PORT_IN / VLCU_PORT_OUT / VLCU_PORT_INOUT (member name, width in bits, 32-bit row words)\n";
         for (const CudaMember* const mp : portsInSourceOrder()) {
-            os << (mp->kind == 1 ? "VLCU_PORT_OUT(" : "VLCU_PORT_IN(") << mp->name << ", " << mp->width << ", "
-               << rowWords(*mp) << ")\n";
+            os << (mp->kind == 1 ? "VLCU_PORT_OUT(" : mp->kind == 2 ? "VLCU_PORT_INOUT(" : "VLCU_PORT_IN(")
+               << mp->name << ", " << mp->width << ", " << rowWords(*mp) << ")\n";
         }
     }
     // <prefix>__cuda.mk: what V3EmitMk's <prefix>.mk is for the C++ model -- the design's

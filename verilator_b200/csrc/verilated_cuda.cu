@@ -132,6 +132,7 @@ struct vlcu_model final {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     uint8_t* dState = nullptr;
     VlcuCtxRec* dCtx = nullptr;
+    uint64_t* dRng = nullptr;  // [npad][2] $random generator states
     VlcuMsg* dMsgs = nullptr;
     uint64_t* dSigs = nullptr;
     uint64_t* dEvalsDone = nullptr;
@@ -678,6 +679,8 @@ vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, 
         return bail(e, "cudaMemset(state)");
     if ((e = cudaMalloc(&h->dCtx, sizeof(VlcuCtxRec) * h->npad)) != cudaSuccess)
         return bail(e, "cudaMalloc(ctx)");
+    if ((e = cudaMalloc(&h->dRng, 2 * sizeof(uint64_t) * h->npad)) != cudaSuccess)
+        return bail(e, "cudaMalloc(rng)");
     if (msg_cap) {
         if ((e = cudaMalloc(&h->dMsgs, sizeof(VlcuMsg) * msg_cap * h->n)) != cudaSuccess)
             return bail(e, "cudaMalloc(msgs)");
@@ -708,6 +711,7 @@ vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, 
     }
     h->dev.state = VlcuState{h->dState, h->npad};
     h->dev.ctxRecs = h->dCtx;
+    h->dev.rng = h->dRng;
     h->dev.msgs = h->dMsgs;
     h->dev.n = h->n;
     h->dev.instBase = inst_base;
@@ -740,6 +744,7 @@ void vlcu_destroy(vlcu_model_t* h) {
     if (h->copyStream) cudaStreamDestroy(h->copyStream);
     cudaFree(h->dState);
     cudaFree(h->dCtx);
+    cudaFree(h->dRng);
     cudaFree(h->dMsgs);
     cudaFree(h->dSigs);
     cudaFree(h->dEvalsDone);
