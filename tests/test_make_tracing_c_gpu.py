@@ -344,3 +344,34 @@ def test_large_batch_signature_properties(abi):
     with abi.Model("make_tracing_c", 4096, seed=1, rand_reset=2) as m:
         m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_arg=(128, 0, 0, 0))
         assert len(np.unique(m.signatures())) == 1
+
+
+def test_huge_batches_index_arithmetic(abi):
+    """2^25 + 5 instances: element offsets beyond 2^32 bytes in the state block, samples at both
+    ends against the oracle.  2^22 + 5 instances: port rows streamed for a batch whose row stride
+    exceeds 2^22 elements.  Neither is a multiple of the CTA or padding size."""
+    n, evals = (1 << 25) + 5, 32
+    with abi.Model("make_tracing_c", n, seed=1, rand_reset=2, msg_cap=0) as m:
+        assert m.npad * lib_state_bytes(abi, m) > (1 << 32)
+        m.run("sim_main", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=3, tb_flags=1, tb_arg=(16, 0, 0, 0))
+        sig = m.signatures()
+        for base in (0, (1 << 24) + 77, n - 8):
+            want = O.mtc_run(8, evals, inst_base=base, seed=1, rand_reset=2, tb_seed=3, per_instance=True,
+                             reset_period=16)
+            assert (sig[base:base + 8] == want.sigs).all(), base
+    n = (1 << 22) + 5
+    with abi.Model("make_tracing_c", n, seed=1, rand_reset=2, msg_cap=0) as m:
+        stim = np.zeros((8, m.in_words, m.npad), dtype=np.uint32)
+        stim[:, 0, :] = ((np.arange(8) & 1) ^ 1)[:, None]
+        stim[:, 1, :] = 1
+        stim[:, 3, :] = (np.arange(m.npad, dtype=np.uint64) * 2654435761 & 0xffffffff).astype(np.uint32)[None, :]
+        obs_a, _ = m.run("trace", 8, stim=stim, obs_evals=8, flags=abi.RUNF_NO_STREAM)
+        sig_a = m.signatures()
+        m.reset()
+        obs_b, _ = m.run("trace", 8, stim=stim, obs_evals=8)
+        assert (obs_a == obs_b).all() and (m.signatures() == sig_a).all()
+        assert len(np.unique(obs_a[7, 1, :])) > 1000
+
+
+def lib_state_bytes(abi, m):
+    return abi.lib.vlcu_state_bytes(m.h)
