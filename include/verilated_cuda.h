@@ -582,6 +582,29 @@ struct VlcuGlobalArray final {
     }
     VLCU_HD T_Value& operator[](size_t index) { return m_basep[index]; }
     VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index]; }
+    // `a = b` between two arrays of the model copies the ELEMENTS (the handle itself is set by
+    // bind() only): V3Sched's `__Vtrigprevexpr = signal` relies on it
+    VlcuGlobalArray() = default;
+    VlcuGlobalArray(const VlcuGlobalArray&) = default;
+    VLCU_HD VlcuGlobalArray& operator=(const VlcuGlobalArray& that) {
+        assign(that);
+        return *this;
+    }
+    // whole-array change detection / copy (trigger computation, V3SenExprBuilder.h:253-260)
+    template <class T_Other>
+    VLCU_HD bool neq(const T_Other& that) const {
+        bool differs = false;
+        for (size_t i = 0; i < N_Depth; ++i) differs |= ((*this)[i] != that[i]);
+        return differs;
+    }
+    template <class T_Other>
+    VLCU_HD void assign(const T_Other& that) {
+        for (size_t i = 0; i < N_Depth; ++i) (*this)[i] = that[i];
+    }
+    template <class T_Other>
+    VLCU_HD bool operator==(const T_Other& that) const { return !neq(that); }
+    template <class T_Other>
+    VLCU_HD bool operator!=(const T_Other& that) const { return neq(that); }
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
@@ -604,6 +627,29 @@ struct VlcuStateArray final {
     VLCU_HD const T_Value& operator[](size_t index) const {
         return m_basep[static_cast<uint64_t>(m_stride) * static_cast<uint32_t>(index)];
     }
+    // `a = b` between two arrays of the model copies the ELEMENTS (the handle itself is set by
+    // bind() only): V3Sched's `__Vtrigprevexpr = signal` relies on it
+    VlcuStateArray() = default;
+    VlcuStateArray(const VlcuStateArray&) = default;
+    VLCU_HD VlcuStateArray& operator=(const VlcuStateArray& that) {
+        assign(that);
+        return *this;
+    }
+    // whole-array change detection / copy (trigger computation, V3SenExprBuilder.h:253-260)
+    template <class T_Other>
+    VLCU_HD bool neq(const T_Other& that) const {
+        bool differs = false;
+        for (size_t i = 0; i < N_Depth; ++i) differs |= ((*this)[i] != that[i]);
+        return differs;
+    }
+    template <class T_Other>
+    VLCU_HD void assign(const T_Other& that) {
+        for (size_t i = 0; i < N_Depth; ++i) (*this)[i] = that[i];
+    }
+    template <class T_Other>
+    VLCU_HD bool operator==(const T_Other& that) const { return !neq(that); }
+    template <class T_Other>
+    VLCU_HD bool operator!=(const T_Other& that) const { return neq(that); }
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
@@ -628,6 +674,29 @@ struct VlcuLocalArray final {
     VLCU_HD void bind(T_Value* storagep) { m_basep = storagep; }
     VLCU_HD T_Value& operator[](size_t index) { return m_basep[index]; }
     VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index]; }
+    // `a = b` between two arrays of the model copies the ELEMENTS (the handle itself is set by
+    // bind() only): V3Sched's `__Vtrigprevexpr = signal` relies on it
+    VlcuLocalArray() = default;
+    VlcuLocalArray(const VlcuLocalArray&) = default;
+    VLCU_HD VlcuLocalArray& operator=(const VlcuLocalArray& that) {
+        assign(that);
+        return *this;
+    }
+    // whole-array change detection / copy (trigger computation, V3SenExprBuilder.h:253-260)
+    template <class T_Other>
+    VLCU_HD bool neq(const T_Other& that) const {
+        bool differs = false;
+        for (size_t i = 0; i < N_Depth; ++i) differs |= ((*this)[i] != that[i]);
+        return differs;
+    }
+    template <class T_Other>
+    VLCU_HD void assign(const T_Other& that) {
+        for (size_t i = 0; i < N_Depth; ++i) (*this)[i] = that[i];
+    }
+    template <class T_Other>
+    VLCU_HD bool operator==(const T_Other& that) const { return !neq(that); }
+    template <class T_Other>
+    VLCU_HD bool operator!=(const T_Other& that) const { return neq(that); }
     VLCU_HD constexpr size_t size() const { return N_Depth; }
     VLCU_HD operator T_Value*() { return m_basep; }
     VLCU_HD operator const T_Value*() const { return m_basep; }
@@ -651,6 +720,29 @@ struct VlcuSharedArray final {
     VLCU_HD void bind(T_Value (*storagep)[VLCU_BLOCK], unsigned lane) { m_basep = &storagep[0][lane]; }
     VLCU_HD T_Value& operator[](size_t index) { return m_basep[index * VLCU_BLOCK]; }
     VLCU_HD const T_Value& operator[](size_t index) const { return m_basep[index * VLCU_BLOCK]; }
+    // `a = b` between two arrays of the model copies the ELEMENTS (the handle itself is set by
+    // bind() only): V3Sched's `__Vtrigprevexpr = signal` relies on it
+    VlcuSharedArray() = default;
+    VlcuSharedArray(const VlcuSharedArray&) = default;
+    VLCU_HD VlcuSharedArray& operator=(const VlcuSharedArray& that) {
+        assign(that);
+        return *this;
+    }
+    // whole-array change detection / copy (trigger computation, V3SenExprBuilder.h:253-260)
+    template <class T_Other>
+    VLCU_HD bool neq(const T_Other& that) const {
+        bool differs = false;
+        for (size_t i = 0; i < N_Depth; ++i) differs |= ((*this)[i] != that[i]);
+        return differs;
+    }
+    template <class T_Other>
+    VLCU_HD void assign(const T_Other& that) {
+        for (size_t i = 0; i < N_Depth; ++i) (*this)[i] = that[i];
+    }
+    template <class T_Other>
+    VLCU_HD bool operator==(const T_Other& that) const { return !neq(that); }
+    template <class T_Other>
+    VLCU_HD bool operator!=(const T_Other& that) const { return neq(that); }
     VLCU_HD constexpr size_t size() const { return N_Depth; }
 };
 
@@ -683,6 +775,16 @@ struct VlcuMdArray final {
     VLCU_HD void bind(T_Args... args) { m_flat.bind(args...); }
     VLCU_HD T_Flat& flat() { return m_flat; }
     VLCU_HD const T_Flat& flat() const { return m_flat; }
+    VlcuMdArray() = default;
+    VlcuMdArray(const VlcuMdArray&) = default;
+    VLCU_HD VlcuMdArray& operator=(const VlcuMdArray& that) {  // element copy, see the 1-D classes
+        m_flat.assign(that.m_flat);
+        return *this;
+    }
+    VLCU_HD bool neq(const VlcuMdArray& that) const { return m_flat.neq(that.m_flat); }
+    VLCU_HD void assign(const VlcuMdArray& that) { m_flat.assign(that.m_flat); }
+    VLCU_HD bool operator==(const VlcuMdArray& that) const { return !neq(that); }
+    VLCU_HD bool operator!=(const VlcuMdArray& that) const { return neq(that); }
     VLCU_HD VlcuDimView<T_Flat, N_Rest...> operator[](size_t i) { return VlcuDimView<T_Flat, N_Rest...>{&m_flat, i}; }
     VLCU_HD VlcuDimView<const T_Flat, N_Rest...> operator[](size_t i) const {
         return VlcuDimView<const T_Flat, N_Rest...>{&m_flat, i};

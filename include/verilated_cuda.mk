@@ -17,7 +17,7 @@ NVCC ?= nvcc
 # Blackwell B200 only: no fallback architectures, no PTX JIT
 VLCU_ARCH ?= -gencode arch=compute_100a,code=sm_100a
 VLCU_OPT ?= -O3
-VLCU_NVCCFLAGS ?= -std=c++17 $(VLCU_OPT) -lineinfo -Xcompiler -fPIC -diag-suppress 177,186
+VLCU_NVCCFLAGS ?= -std=c++17 $(VLCU_OPT) -lineinfo -Xcompiler -fPIC -diag-suppress 177,186,550
 VLCU_INCLUDE ?= $(VLCU_ROOT)/include
 # the runtime source: beside the headers in an installed kit, under verilator_b200/csrc in the
 # development tree

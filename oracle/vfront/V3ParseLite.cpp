@@ -40,6 +40,7 @@
 
 #include <cctype>
 #include <deque>
+#include <map>
 #include <fstream>
 #include <set>
 #include <sstream>
@@ -82,6 +83,228 @@ public:
     string removeDefines(const string& text) override { return text; }
     void dumpDefines(std::ostream&) override {}
     void candidateDefines(VSpellCheck*) override {}
+};
+
+
+//======================================================================
+// Text macros: the part of V3PreProc the test designs need (`define with and without arguments,
+// `undef, `ifdef/`ifndef/`elsif/`else/`endif; VERILATOR, verilator, verilator3 and SYSTEMVERILOG are
+// predefined).  Line structure is kept
+// (a directive line becomes an empty line, continued defines leave empty lines) so that FileLines
+// still point at the source.
+
+class MacroExpander final {
+    struct Macro final {
+        bool hasArgs = false;
+        std::vector<std::string> params;
+        std::string body;
+    };
+    std::map<std::string, Macro> m_macros;
+
+    static bool idStart(char c) { return std::isalpha(static_cast<unsigned char>(c)) || c == '_'; }
+    static bool idChar(char c) { return std::isalnum(static_cast<unsigned char>(c)) || c == '_' || c == '$'; }
+    static std::string trim(const std::string& s) {
+        size_t a = 0, b = s.size();
+        while (a < b && std::isspace(static_cast<unsigned char>(s[a]))) ++a;
+        while (b > a && std::isspace(static_cast<unsigned char>(s[b - 1]))) --b;
+        return s.substr(a, b - a);
+    }
+    // expand the macro uses in one piece of text (no directives inside)
+    std::string expand(const std::string& in, int depth = 0) const {
+        if (depth > 40) return in;
+        std::string out;
+        for (size_t i = 0; i < in.size();) {
+            const char c = in[i];
+            if (c == '"') {  // string literal: copied verbatim
+                size_t j = i + 1;
+                while (j < in.size() && in[j] != '"') j += (in[j] == '\\') ? 2 : 1;
+                out.append(in, i, std::min(j + 1, in.size()) - i);
+                i = std::min(j + 1, in.size());
+            } else if (c == '/' && i + 1 < in.size() && in[i + 1] == '/') {
+                size_t j = in.find('\n', i);
+                if (j == std::string::npos) j = in.size();
+                i = j;  // line comment dropped (it may sit inside a macro body)
+            } else if (c == '`' && i + 1 < in.size() && idStart(in[i + 1])) {
+                size_t j = i + 1;
+                while (j < in.size() && idChar(in[j])) ++j;
+                const std::string name = in.substr(i + 1, j - i - 1);
+                const auto it = m_macros.find(name);
+                if (it == m_macros.end()) {  // `line, `timescale ...: left for the lexer
+                    out.append(in, i, j - i);
+                    i = j;
+                    continue;
+                }
+                const Macro& m = it->second;
+                std::string body = m.body;
+                if (m.hasArgs) {
+                    size_t k = j;
+                    while (k < in.size() && std::isspace(static_cast<unsigned char>(in[k]))) ++k;
+                    if (k < in.size() && in[k] == '(') {
+                        std::vector<std::string> args;
+                        std::string cur;
+                        int nest = 0;
+                        size_t q = k + 1;
+                        for (; q < in.size(); ++q) {
+                            const char a = in[q];
+                            if (a == '"') {
+                                const size_t e = in.find('"', q + 1);
+                                cur.append(in, q, (e == std::string::npos ? in.size() : e + 1) - q);
+                                q = (e == std::string::npos) ? in.size() : e;
+                                continue;
+                            }
+                            if (a == '(' || a == '[' || a == '{') ++nest;
+                            if (a == ')' || a == ']' || a == '}') {
+                                if (a == ')' && nest == 0) break;
+                                --nest;
+                            }
+                            if (a == ',' && nest == 0) {
+                                args.push_back(trim(cur));
+                                cur.clear();
+                            } else {
+                                cur += a;
+                            }
+                        }
+                        args.push_back(trim(cur));
+                        j = std::min(q + 1, in.size());
+                        // substitute parameters by name (identifier boundaries)
+                        std::string sub;
+                        for (size_t b = 0; b < body.size();) {
+                            if (idStart(body[b])) {
+                                size_t e = b;
+                                while (e < body.size() && idChar(body[e])) ++e;
+                                const std::string id = body.substr(b, e - b);
+                                size_t pi = 0;
+                                for (; pi < m.params.size(); ++pi) {
+                                    if (m.params[pi] == id) break;
+                                }
+                                sub += (pi < m.params.size() && pi < args.size()) ? args[pi] : id;
+                                b = e;
+                            } else if (body[b] == '`' && b + 1 < body.size() && body[b + 1] == '"') {
+                                sub += '"';  // `" : string quote inside a macro
+                                b += 2;
+                            } else if (body[b] == '`' && b + 1 < body.size() && body[b + 1] == '`') {
+                                b += 2;  // `` : token paste
+                            } else {
+                                sub += body[b++];
+                            }
+                        }
+                        body = sub;
+                    }
+                }
+                out += expand(body, depth + 1);
+                i = j;
+            } else {
+                out += c;
+                ++i;
+            }
+        }
+        return out;
+    }
+
+public:
+    MacroExpander() {  // V3PreShell.cpp:53-60
+        m_macros["VERILATOR"].body = "1";
+        m_macros["verilator"].body = "1";
+        m_macros["verilator3"].body = "1";
+        m_macros["SYSTEMVERILOG"].body = "1";
+    }
+    std::string run(const std::string& src) {
+        std::string out;
+        std::vector<std::pair<bool, bool>> conds;  // (this branch active, some branch taken)
+        const auto active = [&]() {
+            for (const auto& c : conds) {
+                if (!c.first) return false;
+            }
+            return true;
+        };
+        size_t pos = 0;
+        while (pos < src.size()) {
+            size_t eol = src.find('\n', pos);
+            if (eol == std::string::npos) eol = src.size();
+            std::string line = src.substr(pos, eol - pos);
+            int extraLines = 0;
+            const std::string t = trim(line);
+            const auto directive = [&](const char* name) {
+                const size_t n = std::strlen(name);
+                return t.compare(0, n, name) == 0 && (t.size() == n || !idChar(t[n]));
+            };
+            if (directive("`define")) {
+                // continuation lines
+                while (!line.empty() && line.back() == '\\' && eol < src.size()) {
+                    line.pop_back();
+                    const size_t next = src.find('\n', eol + 1);
+                    const size_t e2 = (next == std::string::npos) ? src.size() : next;
+                    line += ' ' + src.substr(eol + 1, e2 - eol - 1);
+                    eol = e2;
+                    ++extraLines;
+                }
+                if (active()) {
+                    std::string rest = trim(trim(line).substr(7));
+                    size_t k = 0;
+                    while (k < rest.size() && idChar(rest[k])) ++k;
+                    const std::string name = rest.substr(0, k);
+                    Macro m;
+                    if (k < rest.size() && rest[k] == '(') {
+                        m.hasArgs = true;
+                        const size_t close = rest.find(')', k);
+                        std::string plist = rest.substr(k + 1, close - k - 1);
+                        std::istringstream is{plist};
+                        std::string p;
+                        while (std::getline(is, p, ',')) {
+                            p = trim(p);
+                            const size_t eq = p.find('=');
+                            if (eq != std::string::npos) p = trim(p.substr(0, eq));
+                            m.params.push_back(p);
+                        }
+                        k = (close == std::string::npos) ? rest.size() : close + 1;
+                    }
+                    m.body = trim(rest.substr(k));
+                    const size_t cmt = m.body.find("//");
+                    if (cmt != std::string::npos && m.body.find('"') == std::string::npos) m.body = trim(m.body.substr(0, cmt));
+                    m_macros[name] = m;
+                }
+                out += '\n';
+            } else if (directive("`undef")) {
+                if (active()) m_macros.erase(trim(t.substr(6)));
+                out += '\n';
+            } else if (directive("`ifdef") || directive("`ifndef")) {
+                const bool neg = directive("`ifndef");
+                std::string name = trim(t.substr(neg ? 7 : 6));
+                size_t k = 0;
+                while (k < name.size() && idChar(name[k])) ++k;
+                name = name.substr(0, k);
+                const bool on = (m_macros.count(name) != 0) != neg;
+                conds.emplace_back(on, on);
+                out += '\n';
+            } else if (directive("`elsif")) {
+                std::string name = trim(t.substr(6));
+                size_t k = 0;
+                while (k < name.size() && idChar(name[k])) ++k;
+                name = name.substr(0, k);
+                if (!conds.empty()) {
+                    const bool on = !conds.back().second && m_macros.count(name) != 0;
+                    conds.back().first = on;
+                    conds.back().second = conds.back().second || on;
+                }
+                out += '\n';
+            } else if (directive("`else")) {
+                if (!conds.empty()) {
+                    conds.back().first = !conds.back().second;
+                    conds.back().second = true;
+                }
+                out += '\n';
+            } else if (directive("`endif")) {
+                if (!conds.empty()) conds.pop_back();
+                out += '\n';
+            } else {
+                if (active()) out += expand(line);
+                out += '\n';
+            }
+            for (int k = 0; k < extraLines; ++k) out += '\n';
+            pos = eol + 1;
+        }
+        return out;
+    }
 };
 
 //======================================================================
@@ -461,8 +684,19 @@ class Parser final {
         modp->hasParameterList(hasParamList);
         if (acceptPunct("(")) {  // portsStarE: '(' list_of_ports ')' (verilog.y:1329-1332)
             varReset(VVarType::PORT, 1);
-            m_pinAnsi = true;
-            if (!isPunct(")")) {
+            // list_of_ports of plain identifiers: the Verilog-1995 form, directions and types
+            // follow as port_declaration module items (verilog.y:1424-1437, 1540-1575)
+            const bool nonAnsi = m_lex.peek().kind == Tok::ID && !isKw("input") && !isKw("output")
+                                 && !isKw("inout") && !isKw("wire") && !isKw("reg") && !isKw("logic")
+                                 && !isKw("bit") && !isKw("integer") && !isKw("int") && !isKw("signed")
+                                 && !isKw("unsigned");
+            m_pinAnsi = !nonAnsi;
+            if (nonAnsi) {
+                do {
+                    const Token name = expectId();
+                    modp->addStmtsp(new AstPort{name.fl, m_pinNum++, name.text});
+                } while (acceptPunct(","));
+            } else if (!isPunct(")")) {
                 do { parsePort(modp); } while (acceptPunct(","));
             }
             expectPunct(")");
@@ -559,6 +793,28 @@ class Parser final {
             AstNode* listp = nullptr;
             do { listp = AstNode::addNext(listp, static_cast<AstNode*>(parseParamAssignment())); } while (acceptPunct(","));
             expectPunct(";");
+            return listp;
+        }
+        if (t.text == "input" || t.text == "output" || t.text == "inout") {
+            // port_declaration (verilog.y:1540-1575): port_directionReset port_declNetE
+            // [data_type | signingE rangeList] list_of_variable_decl_assignments
+            const Token dir = m_lex.next();
+            varReset(VVarType::UNKNOWN, m_pinNum);
+            m_varIO = dir.text == "input"    ? VDirection::INPUT
+                      : dir.text == "output" ? VDirection::OUTPUT
+                                             : VDirection::INOUT;
+            if (acceptKw("wire")) m_varDecl = VVarType::WIRE;
+            if (AstNodeDType* const dtp = parseDataTypeE()) {
+                setDType(dtp);
+                m_varDeclTyped = true;
+            } else if (isKw("signed") || isKw("unsigned") || isPunct("[")) {
+                const VSigning sign = parseSigningE();
+                AstRange* const rangep = isPunct("[") ? parseRange() : nullptr;
+                FileLine* const dfl = rangep ? rangep->fileline() : m_lex.peek().fl;
+                setDType(addRange(new AstBasicDType{dfl, VBasicDTypeKwd::LOGIC_IMPLICIT, sign}, rangep));
+            }
+            AstNode* const listp = parseDeclList(false);
+            varReset(VVarType::UNKNOWN, m_pinNum);
             return listp;
         }
         if (t.text == "wire") {  // net_declaration (verilog.y:1856-1875, 1888-1902)
@@ -1288,7 +1544,8 @@ void V3Parse::parseFile(FileLine* fileline, const string& modname, bool inLibrar
         v3Global.rootp()->addModulesp(nodep);
         return;
     }
-    Lexer lexer{fileline, impp->text};
+    MacroExpander macros;
+    Lexer lexer{fileline, macros.run(impp->text)};
     Parser parser{lexer, impp->rootp, inLibrary, libname};
     parser.parseDescriptions();
 }

@@ -80,6 +80,18 @@ struct CudaMember final {
 class CudaIndexVisitor final : public VNVisitorConst {
     std::set<const AstVar*>& m_runtimeIndexed;
     std::set<const AstVar*>& m_dataIndexed;
+    std::set<const AstVar*>& m_wholeRef;  // arrays passed to a function as a whole
+    void visit(AstCCall* nodep) override {
+        // (the trace functions of array data types are printed as templates over the array class,
+        // they take whichever handle the array has)
+        const bool traceFunc = nodep->funcp()->name().find("trace") != string::npos;
+        for (const AstNode* argp = traceFunc ? nullptr : nodep->argsp(); argp; argp = argp->nextp()) {
+            if (const AstVarRef* const refp = VN_CAST(argp, VarRef)) {
+                if (VN_IS(refp->varp()->dtypep()->skipRefp(), UnpackArrayDType)) m_wholeRef.insert(refp->varp());
+            }
+        }
+        iterateChildrenConst(nodep);
+    }
     static bool dependsOnMember(const AstNode* nodep) {
         bool member = false;
         nodep->foreach([&](const AstVarRef* refp) {
@@ -101,9 +113,11 @@ class CudaIndexVisitor final : public VNVisitorConst {
     void visit(AstNode* nodep) override { iterateChildrenConst(nodep); }
 
 public:
-    CudaIndexVisitor(const AstNodeModule* modp, std::set<const AstVar*>& out, std::set<const AstVar*>& dataOut)
+    CudaIndexVisitor(const AstNodeModule* modp, std::set<const AstVar*>& out, std::set<const AstVar*>& dataOut,
+                     std::set<const AstVar*>& wholeOut)
         : m_runtimeIndexed{out}
-        , m_dataIndexed{dataOut} {
+        , m_dataIndexed{dataOut}
+        , m_wholeRef{wholeOut} {
         iterateConst(const_cast<AstNodeModule*>(modp));
     }
 };
@@ -149,6 +163,7 @@ class EmitCudaModel final : public EmitCFunc {
     std::vector<CudaMember> m_members;
     std::map<const AstVar*, size_t> m_memberOf;
     std::set<const AstVar*> m_dataIndexed;  // arrays with an index that differs between instances
+    std::set<const AstVar*> m_wholeRef;  // arrays some function takes as a whole (VlUnpacked<>& parameter)
     std::vector<std::pair<string, string>> m_nbaQueues;  // VlNBACommitQueue members: name, device type
     std::vector<string> m_messages;
     std::vector<string> m_plusargs;
@@ -253,7 +268,11 @@ class EmitCudaModel final : public EmitCFunc {
             //   HBM            large memories, instance-major so one instance's accesses share sectors
             const bool runtime = runtimeIndexed.count(varp) != 0;
             const uint32_t bytes = m.bytes();
-            if (!runtime && m.elems() <= 16 && m.dims.size() == 1) {
+            if (m_wholeRef.count(varp) && bytes <= 256 && m.dims.size() == 1) {
+                // handed to functions as VlUnpacked<>& (trigger vectors of several words): stays a
+                // plain member of the image; the callees' loops over it have constant trip counts
+                m.storage = CudaStorage::REG;
+            } else if (!runtime && m.elems() <= 16 && m.dims.size() == 1) {
                 m.storage = CudaStorage::REG;
             } else if (runtime && bytes <= 256 && !m.isWide) {
                 m.storage = CudaStorage::SHARED;
@@ -274,7 +293,7 @@ class EmitCudaModel final : public EmitCFunc {
     }
     void computeLayout() {
         std::set<const AstVar*> runtimeIndexed;
-        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed, m_dataIndexed}; }
+        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed, m_dataIndexed, m_wholeRef}; }
         for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
             if (const AstVar* const varp = VN_CAST(nodep, Var)) {
                 // Same test as EmitCHeader::emitDesignVarDecls (V3EmitCHeaders.cpp:133-135)

@@ -1,0 +1,1973 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_math_concat"
+#endif
+
+// Constant pool
+static __device__ const VlWide<8>/*255:0*/ Vt_math_concat__ConstPool__CONST_h6bf974be_0 = VlWide<8>{{
+        0xc9f395b8, 0x0a48e039, 0xdddbdad2, 0xe236ddfd,
+        0xe2bd68c3, 0x982646c8, 0x3d5fe51a, 0x0e17c88f
+}};
+static __device__ const VlWide<8>/*255:0*/ Vt_math_concat__ConstPool__CONST_hc278fede_0 = VlWide<8>{{
+        0x147e7f26, 0x7491f3da, 0x42b14853, 0x45e0eb76,
+        0x2413d770, 0xde489bab, 0x6c843d35, 0xed388e64
+}};
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_math_concat___024root final {
+    CData/*0:0*/ clk;
+    CData/*0:0*/ __VstlFirstIteration;
+    CData/*0:0*/ __VstlPhaseResult;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ t__DOT__cyc;
+    VlWide<8>/*255:0*/ t__DOT__i;
+    VlWide<8>/*255:0*/ t__DOT__q;
+    IData/*31:0*/ __VactIterCount;
+    VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_math_concat__cuda final {
+    typedef Vt_math_concat___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 96,
+        OFF___VstlFirstIteration = 97,
+        OFF___VstlPhaseResult = 98,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 99,
+        OFF___VactPhaseResult = 100,
+        OFF___VnbaPhaseResult = 101,
+        OFF_t__DOT__cyc = 24,
+        OFF_t__DOT__i = 28,
+        OFF_t__DOT__q = 60,
+        OFF___VactIterCount = 92,
+        OFF___VstlTriggered = 0,
+        OFF___VactTriggered = 8,
+        OFF___VnbaTriggered = 16,
+        kStateBytes = 104,  // S_persist
+        kTouchedReadBytes = 92,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 91,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.t__DOT__cyc = st.ld<IData>(OFF_t__DOT__cyc, i);
+        st.ldW(OFF_t__DOT__i, i, s.t__DOT__i);
+        st.ldW(OFF_t__DOT__q, i, s.t__DOT__q);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.stW(OFF_t__DOT__i, i, s.t__DOT__i);
+        st.stW(OFF_t__DOT__q, i, s.t__DOT__q);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_math_concat___024root___eval_static(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_math_concat___024root___eval_initial(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_initial__TOP
+            vlSelfRef.t__DOT__cyc = 1U;
+        }
+    }
+
+    VLCU_D static void Vt_math_concat___024root___eval_final(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_math_concat___024root___eval_settle(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VstlIterCount;
+        // Body
+        __VstlIterCount = 0U;
+        vlSelfRef.__VstlFirstIteration = 1U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VstlIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_math_concat___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_math_concat.v", 7, "", "DIDNOTCONVERGE: Settle region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VstlIterCount = ((IData)(1U) + __VstlIterCount);
+            vlSelfRef.__VstlPhaseResult = Vt_math_concat___024root___eval_phase__stl(vlSelf, vlCtx);
+            vlSelfRef.__VstlFirstIteration = 0U;
+        } while (vlSelfRef.__VstlPhaseResult);
+    }
+
+    VLCU_D static bool Vt_math_concat___024root___trigger_anySet__stl(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_concat___024root___stl_sequent__TOP__0(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.t__DOT__q[0U] = ((((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                >> 7U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 6U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[7U] 
+                                                       >> 0x0000001bU)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x0000000dU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000000aU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x0000000bU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000012U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000018U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 6U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x00000010U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001bU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000000aU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[3U] 
+                                               >> 0x00000019U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 0x0000001bU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[6U] 
+                                                   >> 0x0000001bU))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000011U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000000fU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000001bU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 6U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000dU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                   >> 0x0000001dU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[2U] 
+                                                        >> 0x00000018U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000011U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[3U] 
+                                                          >> 0x00000010U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[7U] 
+                                                            >> 8U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[0U] 
+                                                          >> 6U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000015U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[1U] 
+                                                           >> 0x0000001eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[2U] 
+                                                             >> 0x0000001dU)))))));
+        vlSelfRef.t__DOT__q[1U] = ((((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                >> 6U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000001dU))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[0U] 
+                                                       >> 8U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x0000000eU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000011U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000015U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 9U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 1U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 5U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000fU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x0000000cU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000018U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000fU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 0x0000001aU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[4U] 
+                                                   >> 0x00000017U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000019U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001eU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000015U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 5U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 2U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 5U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000aU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 2U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 8U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000011U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[5U] 
+                                                          >> 6U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[6U] 
+                                                            >> 0x0000000aU))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[3U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[5U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[4U] 
+                                                           >> 0x00000012U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[0U] 
+                                                             >> 0x0000000dU)))))));
+        vlSelfRef.t__DOT__q[2U] = ((((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                >> 0x00000011U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x0000001eU))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[1U] 
+                                                       >> 0x00000019U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[7U] 
+                                                         >> 6U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & vlSelfRef.t__DOT__i[0U])) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 6U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x0000000bU))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000015U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 0x00000019U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x00000014U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x00000010U))) 
+                                          << 4U)) | 
+                                        ((((2U & vlSelfRef.t__DOT__i[1U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000000dU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000eU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x00000010U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x0000001dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001dU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000013U)) 
+                                           | (vlSelfRef.t__DOT__i[0U] 
+                                              >> 0x0000001fU)) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000017U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001cU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                 >> 1U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x00000013U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 0x0000001cU)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000018U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000014U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 7U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[5U] 
+                                                            >> 0x00000018U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[0U] 
+                                                           >> 0x0000001aU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[0U] 
+                                                             >> 2U)))))));
+        vlSelfRef.t__DOT__q[3U] = ((((((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                >> 9U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 3U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[2U] 
+                                                       >> 0x00000016U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[1U] 
+                                                         >> 0x0000001bU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000014U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001bU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 7U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[2U] 
+                                                   >> 6U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x00000010U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000cU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000018U)) 
+                                           | (vlSelfRef.t__DOT__i[5U] 
+                                              >> 0x0000001fU)) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000001eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000017U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                 >> 9U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                   >> 0x00000011U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x0000001bU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000dU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000016U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 2U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 9U))) 
+                                          << 2U) | 
+                                         ((2U & vlSelfRef.t__DOT__i[2U]) 
+                                          | (1U & (vlSelfRef.t__DOT__i[2U] 
+                                                   >> 0x00000014U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[4U] 
+                                                        >> 0x00000018U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 0x0000001eU))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 0x00000014U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[6U] 
+                                                            >> 5U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000013U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000012U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[3U] 
+                                                           << 1U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[3U] 
+                                                             >> 0x00000016U)))))));
+        vlSelfRef.t__DOT__q[4U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x00000014U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 1U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[3U] 
+                                                       >> 0x00000017U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[6U] 
+                                                         >> 0x0000001cU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 3U)) 
+                                           | (vlSelfRef.t__DOT__i[4U] 
+                                              >> 0x0000001fU)) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 8U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x00000017U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000017U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x00000018U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x0000000eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000000aU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000011U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000000fU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                 >> 4U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 3U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 3U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x00000012U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000001eU))) 
+                                          << 4U)) | 
+                                        ((8U & (vlSelfRef.t__DOT__i[2U] 
+                                                >> 9U)) 
+                                         | ((4U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x0000001aU)) 
+                                            | (3U & 
+                                               (vlSelfRef.t__DOT__i[4U] 
+                                                >> 0x00000015U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[7U] 
+                                                        >> 0x0000000aU)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 3U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 0x00000019U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[4U] 
+                                                            >> 6U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & vlSelfRef.t__DOT__i[1U])) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[1U] 
+                                                           >> 0x0000001bU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[4U] 
+                                                             >> 0x00000010U)))))));
+        vlSelfRef.t__DOT__q[5U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 3U)) 
+                                         | (1U & vlSelfRef.t__DOT__i[2U])) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[2U] 
+                                                       >> 0x00000015U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[6U] 
+                                                         >> 1U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000016U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000eU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 0x0000000aU)) 
+                                          | (1U & vlSelfRef.t__DOT__i[4U])))) 
+                                     << 0x00000018U) 
+                                    | ((((8U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x0000001bU)) 
+                                         | ((4U & (vlSelfRef.t__DOT__i[7U] 
+                                                   >> 7U)) 
+                                            | (3U & 
+                                               (vlSelfRef.t__DOT__i[0U] 
+                                                >> 0x00000016U)))) 
+                                        << 0x00000014U) 
+                                       | ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                   >> 6U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[3U] 
+                                                >> 0x0000000cU))) 
+                                           << 0x00000012U) 
+                                          | (((2U & 
+                                               (vlSelfRef.t__DOT__i[1U] 
+                                                >> 0x0000001cU)) 
+                                              | (1U 
+                                                 & (vlSelfRef.t__DOT__i[4U] 
+                                                    >> 0x0000000bU))) 
+                                             << 0x00000010U)))) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000013U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000bU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001aU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000000eU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                 >> 0x0000001eU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x0000000dU))))) 
+                                       << 8U) | (((
+                                                   (8U 
+                                                    & (vlSelfRef.t__DOT__i[6U] 
+                                                       >> 0x0000000dU)) 
+                                                   | ((4U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000014U)) 
+                                                      | (3U 
+                                                         & (vlSelfRef.t__DOT__i[0U] 
+                                                            >> 0x00000018U)))) 
+                                                  << 4U) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 0x00000013U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[2U] 
+                                                            >> 0x0000000fU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x00000015U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[4U] 
+                                                             >> 0x0000000eU)))))));
+        vlSelfRef.t__DOT__q[6U] = ((((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                >> 0x0000001eU)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 3U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[7U] 
+                                                       << 1U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x00000013U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000001dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x00000012U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                 >> 2U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 2U))))) 
+                                     << 0x00000018U) 
+                                    | ((((8U & (vlSelfRef.t__DOT__i[6U] 
+                                                >> 0x0000001aU)) 
+                                         | ((6U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 7U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[3U] 
+                                                >> 0x0000000bU)))) 
+                                        << 0x00000014U) 
+                                       | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000014U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[2U] 
+                                                >> 2U))) 
+                                           << 0x00000012U) 
+                                          | (((2U & 
+                                               (vlSelfRef.t__DOT__i[0U] 
+                                                >> 0x00000013U)) 
+                                              | (1U 
+                                                 & (vlSelfRef.t__DOT__i[5U] 
+                                                    >> 0x0000000eU))) 
+                                             << 0x00000010U)))) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 9U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 4U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 2U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 9U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 6U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 2U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x00000019U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x0000000eU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 0x00000019U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000012U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 7U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[1U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 0x00000012U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[7U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x0000000eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[5U] 
+                                                             >> 0x00000017U)))))));
+        vlSelfRef.t__DOT__q[7U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x0000000fU)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 8U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[3U] 
+                                                       >> 0x0000001dU)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[5U] 
+                                                         >> 0x00000011U))) 
+                                                  << 4U)) 
+                                      | ((((2U & vlSelfRef.t__DOT__i[3U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[3U] 
+                                               >> 0x0000001bU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                 >> 6U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 7U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x0000001bU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x0000001aU))) 
+                                          << 6U) | 
+                                         (((2U & vlSelfRef.t__DOT__i[0U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x00000014U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000010U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x0000001cU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000010U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000000eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x00000018U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 1U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x0000000dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 6U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 3U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[7U] 
+                                                   >> 0x0000000aU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[3U] 
+                                                        >> 0x00000012U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[0U] 
+                                                          >> 8U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 4U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 3U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 8U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[4U] 
+                                                            >> 2U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x0000001eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[3U] 
+                                                             >> 0x0000001aU)))))));
+    }
+
+    VLCU_D static bool Vt_math_concat___024root___eval_phase__stl(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VstlExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__stl
+            vlSelfRef.__VstlTriggered[0U] = ((0xfffffffffffffffeULL 
+                                              & vlSelfRef.__VstlTriggered[0U]) 
+                                             | (IData)((IData)(vlSelfRef.__VstlFirstIteration)));
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_math_concat___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+        }
+#endif
+        __VstlExecute = Vt_math_concat___024root___trigger_anySet__stl(vlSelfRef.__VstlTriggered);
+        if (__VstlExecute) {
+            {
+                // Inlined CFunc: _eval_stl
+                if ((1ULL & vlSelfRef.__VstlTriggered[0U])) {
+                    Vt_math_concat___024root___stl_sequent__TOP__0(vlSelf, vlCtx);
+                }
+            }
+        }
+        return (__VstlExecute);
+    }
+
+    VLCU_D static bool Vt_math_concat___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_concat___024root___nba_sequent__TOP__0(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __Vdly__t__DOT__cyc;
+        __Vdly__t__DOT__cyc = 0;
+        // Body
+        __Vdly__t__DOT__cyc = vlSelfRef.t__DOT__cyc;
+        if ((0U != vlSelfRef.t__DOT__cyc)) {
+            __Vdly__t__DOT__cyc = ((IData)(1U) + vlSelfRef.t__DOT__cyc);
+            if ((1U == vlSelfRef.t__DOT__cyc)) {
+                VL_ASSIGN_W(256, vlSelfRef.t__DOT__i, Vt_math_concat__ConstPool__CONST_hc278fede_0);
+            }
+            if ((2U == vlSelfRef.t__DOT__cyc)) {
+                if (VL_UNLIKELY(((0U != ((((((((0x820baa84U 
+                                                ^ vlSelfRef.t__DOT__q[0U]) 
+                                               | (0x35f2c7bdU 
+                                                  ^ vlSelfRef.t__DOT__q[1U])) 
+                                              | (0x31e8eb21U 
+                                                 ^ vlSelfRef.t__DOT__q[2U])) 
+                                             | (0x67d1eb31U 
+                                                ^ vlSelfRef.t__DOT__q[3U])) 
+                                            | (0x293710bbU 
+                                               ^ vlSelfRef.t__DOT__q[4U])) 
+                                           | (0x4ad22809U 
+                                              ^ vlSelfRef.t__DOT__q[5U])) 
+                                          | (0x0cf2d7faU 
+                                             ^ vlSelfRef.t__DOT__q[6U])) 
+                                         | (0x697bad4bU 
+                                            ^ vlSelfRef.t__DOT__q[7U])))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_concat.v", 65, "");
+                }
+                VL_ASSIGN_W(256, vlSelfRef.t__DOT__i, Vt_math_concat__ConstPool__CONST_h6bf974be_0);
+            }
+            if ((3U == vlSelfRef.t__DOT__cyc)) {
+                if (VL_UNLIKELY(((0U != ((((((((0x483f602cU 
+                                                ^ vlSelfRef.t__DOT__q[0U]) 
+                                               | (0xdadfb1faU 
+                                                  ^ vlSelfRef.t__DOT__q[1U])) 
+                                              | (0xc8323612U 
+                                                 ^ vlSelfRef.t__DOT__q[2U])) 
+                                             | (0x773b4fceU 
+                                                ^ vlSelfRef.t__DOT__q[3U])) 
+                                            | (0xdc8b29fdU 
+                                               ^ vlSelfRef.t__DOT__q[4U])) 
+                                           | (0x353d16ddU 
+                                              ^ vlSelfRef.t__DOT__q[5U])) 
+                                          | (0x78b3e942U 
+                                             ^ vlSelfRef.t__DOT__q[6U])) 
+                                         | (0x320eda50U 
+                                            ^ vlSelfRef.t__DOT__q[7U])))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_concat.v", 68, "");
+                }
+            }
+            if (VL_UNLIKELY(((4U == vlSelfRef.t__DOT__cyc)))) {
+                vlCtx.writef(0U, 0U);
+                VL_FINISH_MT("/root/reference/test_regress/t/t_math_concat.v", 72, "");
+            }
+        }
+        vlSelfRef.t__DOT__cyc = __Vdly__t__DOT__cyc;
+        vlSelfRef.t__DOT__q[0U] = ((((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                >> 7U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 6U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[7U] 
+                                                       >> 0x0000001bU)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x0000000dU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000000aU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x0000000bU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000012U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000018U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 6U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x00000010U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001bU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000000aU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[3U] 
+                                               >> 0x00000019U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 0x0000001bU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[6U] 
+                                                   >> 0x0000001bU))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000011U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000000fU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000001bU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 6U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000dU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                   >> 0x0000001dU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[2U] 
+                                                        >> 0x00000018U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000011U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[3U] 
+                                                          >> 0x00000010U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[7U] 
+                                                            >> 8U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[0U] 
+                                                          >> 6U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000015U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[1U] 
+                                                           >> 0x0000001eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[2U] 
+                                                             >> 0x0000001dU)))))));
+        vlSelfRef.t__DOT__q[1U] = ((((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                >> 6U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000001dU))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[0U] 
+                                                       >> 8U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x0000000eU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000011U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000015U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 9U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 1U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 5U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000fU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x0000000cU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000018U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000fU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                 >> 0x0000001aU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[4U] 
+                                                   >> 0x00000017U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000019U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001eU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000015U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 5U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 2U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 5U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000aU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 2U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 8U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000011U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[5U] 
+                                                          >> 6U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[6U] 
+                                                            >> 0x0000000aU))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[3U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[5U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[4U] 
+                                                           >> 0x00000012U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[0U] 
+                                                             >> 0x0000000dU)))))));
+        vlSelfRef.t__DOT__q[2U] = ((((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                >> 0x00000011U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x0000001eU))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[1U] 
+                                                       >> 0x00000019U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[7U] 
+                                                         >> 6U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & vlSelfRef.t__DOT__i[0U])) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 6U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x0000000bU))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000015U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 0x00000019U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x00000014U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x00000010U))) 
+                                          << 4U)) | 
+                                        ((((2U & vlSelfRef.t__DOT__i[1U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000000dU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 0x0000000eU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x00000010U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x0000001dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001dU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000013U)) 
+                                           | (vlSelfRef.t__DOT__i[0U] 
+                                              >> 0x0000001fU)) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000017U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001cU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                 >> 1U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x00000013U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 0x0000001cU)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000018U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000014U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 7U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[5U] 
+                                                            >> 0x00000018U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[0U] 
+                                                           >> 0x0000001aU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[0U] 
+                                                             >> 2U)))))));
+        vlSelfRef.t__DOT__q[3U] = ((((((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                >> 9U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 3U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[2U] 
+                                                       >> 0x00000016U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[1U] 
+                                                         >> 0x0000001bU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000014U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000001bU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 7U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[2U] 
+                                                   >> 6U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x00000010U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000cU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000018U)) 
+                                           | (vlSelfRef.t__DOT__i[5U] 
+                                              >> 0x0000001fU)) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000001eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000017U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                 >> 9U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[0U] 
+                                                   >> 0x00000011U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 0x0000001bU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000dU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000016U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[5U] 
+                                               >> 2U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 9U))) 
+                                          << 2U) | 
+                                         ((2U & vlSelfRef.t__DOT__i[2U]) 
+                                          | (1U & (vlSelfRef.t__DOT__i[2U] 
+                                                   >> 0x00000014U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[4U] 
+                                                        >> 0x00000018U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 0x0000001eU))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 0x00000014U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[6U] 
+                                                            >> 5U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000013U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 0x00000012U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[3U] 
+                                                           << 1U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[3U] 
+                                                             >> 0x00000016U)))))));
+        vlSelfRef.t__DOT__q[4U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x00000014U)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 1U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[3U] 
+                                                       >> 0x00000017U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[6U] 
+                                                         >> 0x0000001cU))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 3U)) 
+                                           | (vlSelfRef.t__DOT__i[4U] 
+                                              >> 0x0000001fU)) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 8U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x00000017U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000017U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x00000018U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x0000000eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000000aU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 0x00000011U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[4U] 
+                                               >> 0x0000000fU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                 >> 4U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 3U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 3U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x00000012U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 0x00000012U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000001eU))) 
+                                          << 4U)) | 
+                                        ((8U & (vlSelfRef.t__DOT__i[2U] 
+                                                >> 9U)) 
+                                         | ((4U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x0000001aU)) 
+                                            | (3U & 
+                                               (vlSelfRef.t__DOT__i[4U] 
+                                                >> 0x00000015U))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[7U] 
+                                                        >> 0x0000000aU)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 3U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 0x00000019U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[4U] 
+                                                            >> 6U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 3U)) 
+                                                      | (1U 
+                                                         & vlSelfRef.t__DOT__i[1U])) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[1U] 
+                                                           >> 0x0000001bU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[4U] 
+                                                             >> 0x00000010U)))))));
+        vlSelfRef.t__DOT__q[5U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 3U)) 
+                                         | (1U & vlSelfRef.t__DOT__i[2U])) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[2U] 
+                                                       >> 0x00000015U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[6U] 
+                                                         >> 1U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x00000016U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 0x0000000eU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                 >> 0x0000000aU)) 
+                                          | (1U & vlSelfRef.t__DOT__i[4U])))) 
+                                     << 0x00000018U) 
+                                    | ((((8U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x0000001bU)) 
+                                         | ((4U & (vlSelfRef.t__DOT__i[7U] 
+                                                   >> 7U)) 
+                                            | (3U & 
+                                               (vlSelfRef.t__DOT__i[0U] 
+                                                >> 0x00000016U)))) 
+                                        << 0x00000014U) 
+                                       | ((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                   >> 6U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[3U] 
+                                                >> 0x0000000cU))) 
+                                           << 0x00000012U) 
+                                          | (((2U & 
+                                               (vlSelfRef.t__DOT__i[1U] 
+                                                >> 0x0000001cU)) 
+                                              | (1U 
+                                                 & (vlSelfRef.t__DOT__i[4U] 
+                                                    >> 0x0000000bU))) 
+                                             << 0x00000010U)))) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 0x00000013U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x0000000bU))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000000cU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x0000001aU))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x0000000eU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                 >> 0x0000001eU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                   >> 0x0000000dU))))) 
+                                       << 8U) | (((
+                                                   (8U 
+                                                    & (vlSelfRef.t__DOT__i[6U] 
+                                                       >> 0x0000000dU)) 
+                                                   | ((4U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 0x00000014U)) 
+                                                      | (3U 
+                                                         & (vlSelfRef.t__DOT__i[0U] 
+                                                            >> 0x00000018U)))) 
+                                                  << 4U) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 0x00000013U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[2U] 
+                                                            >> 0x0000000fU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x00000015U)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[4U] 
+                                                             >> 0x0000000eU)))))));
+        vlSelfRef.t__DOT__q[6U] = ((((((((2U & (vlSelfRef.t__DOT__i[6U] 
+                                                >> 0x0000001eU)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[6U] 
+                                                  >> 3U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[7U] 
+                                                       << 1U)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[2U] 
+                                                         >> 0x00000013U))) 
+                                                  << 4U)) 
+                                      | ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 0x0000001dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x00000012U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                 >> 2U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 2U))))) 
+                                     << 0x00000018U) 
+                                    | ((((8U & (vlSelfRef.t__DOT__i[6U] 
+                                                >> 0x0000001aU)) 
+                                         | ((6U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 7U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[3U] 
+                                                >> 0x0000000bU)))) 
+                                        << 0x00000014U) 
+                                       | ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000014U)) 
+                                            | (1U & 
+                                               (vlSelfRef.t__DOT__i[2U] 
+                                                >> 2U))) 
+                                           << 0x00000012U) 
+                                          | (((2U & 
+                                               (vlSelfRef.t__DOT__i[0U] 
+                                                >> 0x00000013U)) 
+                                              | (1U 
+                                                 & (vlSelfRef.t__DOT__i[5U] 
+                                                    >> 0x0000000eU))) 
+                                             << 0x00000010U)))) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 9U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 4U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 2U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 9U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[2U] 
+                                                  >> 6U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[6U] 
+                                               >> 2U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x00000019U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[3U] 
+                                                   >> 0x0000000eU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[5U] 
+                                                        >> 0x00000019U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[6U] 
+                                                          >> 0x00000012U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[1U] 
+                                                          >> 7U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[1U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[7U] 
+                                                          >> 0x00000012U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[7U] 
+                                                            >> 0x0000000cU))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x0000000eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[5U] 
+                                                             >> 0x00000017U)))))));
+        vlSelfRef.t__DOT__q[7U] = ((((((((2U & (vlSelfRef.t__DOT__i[5U] 
+                                                >> 0x0000000fU)) 
+                                         | (1U & (vlSelfRef.t__DOT__i[5U] 
+                                                  >> 8U))) 
+                                        << 6U) | ((
+                                                   (2U 
+                                                    & (vlSelfRef.t__DOT__i[3U] 
+                                                       >> 0x0000001dU)) 
+                                                   | (1U 
+                                                      & (vlSelfRef.t__DOT__i[5U] 
+                                                         >> 0x00000011U))) 
+                                                  << 4U)) 
+                                      | ((((2U & vlSelfRef.t__DOT__i[3U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[3U] 
+                                               >> 0x0000001bU))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[7U] 
+                                                 >> 6U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 7U))))) 
+                                     << 0x00000018U) 
+                                    | ((((((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 0x0000001bU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[0U] 
+                                               >> 0x0000001aU))) 
+                                          << 6U) | 
+                                         (((2U & vlSelfRef.t__DOT__i[0U]) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 0x00000014U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 0x00000010U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                 >> 0x0000001cU)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[1U] 
+                                                   >> 0x00000010U))))) 
+                                       << 0x00000010U)) 
+                                   | (((((((2U & (vlSelfRef.t__DOT__i[3U] 
+                                                  >> 0x0000000eU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[2U] 
+                                               >> 0x00000018U))) 
+                                          << 6U) | 
+                                         (((2U & (vlSelfRef.t__DOT__i[4U] 
+                                                  >> 4U)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[7U] 
+                                               >> 1U))) 
+                                          << 4U)) | 
+                                        ((((2U & (vlSelfRef.t__DOT__i[1U] 
+                                                  >> 0x0000000dU)) 
+                                           | (1U & 
+                                              (vlSelfRef.t__DOT__i[1U] 
+                                               >> 6U))) 
+                                          << 2U) | 
+                                         ((2U & (vlSelfRef.t__DOT__i[0U] 
+                                                 >> 3U)) 
+                                          | (1U & (vlSelfRef.t__DOT__i[7U] 
+                                                   >> 0x0000000aU))))) 
+                                       << 8U) | (((
+                                                   ((2U 
+                                                     & (vlSelfRef.t__DOT__i[3U] 
+                                                        >> 0x00000012U)) 
+                                                    | (1U 
+                                                       & (vlSelfRef.t__DOT__i[0U] 
+                                                          >> 8U))) 
+                                                   << 6U) 
+                                                  | (((2U 
+                                                       & (vlSelfRef.t__DOT__i[2U] 
+                                                          >> 4U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[3U] 
+                                                            >> 3U))) 
+                                                     << 4U)) 
+                                                 | ((((2U 
+                                                       & (vlSelfRef.t__DOT__i[4U] 
+                                                          >> 8U)) 
+                                                      | (1U 
+                                                         & (vlSelfRef.t__DOT__i[4U] 
+                                                            >> 2U))) 
+                                                     << 2U) 
+                                                    | ((2U 
+                                                        & (vlSelfRef.t__DOT__i[7U] 
+                                                           >> 0x0000001eU)) 
+                                                       | (1U 
+                                                          & (vlSelfRef.t__DOT__i[3U] 
+                                                             >> 0x0000001aU)))))));
+    }
+
+    VLCU_D static void Vt_math_concat___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt_math_concat___024root___eval_phase__act(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_math_concat___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_math_concat___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_concat___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt_math_concat___024root___eval_phase__nba(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_math_concat___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    Vt_math_concat___024root___nba_sequent__TOP__0(vlSelf, vlCtx);
+                }
+            }
+            Vt_math_concat___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_math_concat___024root___eval(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_math_concat___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_math_concat.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_math_concat___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_math_concat.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_math_concat___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_math_concat___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_math_concat___024root___ctor_var_reset(Vt_math_concat___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->t__DOT__cyc = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 15508623621340971111ull);
+        VL_SCOPED_RAND_RESET_W(256, vlSelf->t__DOT__i, __VscopeHash, 8181117886251660215ull);
+        VL_SCOPED_RAND_RESET_W(256, vlSelf->t__DOT__q, __VscopeHash, 4790251044348089774ull);
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VstlTriggered[__Vi0] = 0;
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_math_concat___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_concat___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_concat___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_concat___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_concat___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_concat___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_math_concat__cuda::info() {
+    typedef Vt_math_concat__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
+        {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__cyc},
+        {"t__DOT__i", "t.i", VLCU_MEMBER_STATE, 4, 0, 8, 256, 255, 0, T::OFF_t__DOT__i},
+        {"t__DOT__q", "t.q", VLCU_MEMBER_STATE, 4, 0, 8, 256, 255, 0, T::OFF_t__DOT__q},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 1, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 13, 0, 0xac53cb927fecff3bULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_math_concat__cuda VLCU_TESTBENCHES);

@@ -1,0 +1,1067 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_math_repl"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_math_repl___024root final {
+    CData/*0:0*/ clk;
+    CData/*0:0*/ t__DOT__b;
+    CData/*0:0*/ __VstlFirstIteration;
+    CData/*0:0*/ __VstlPhaseResult;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ t__DOT__cyc;
+    IData/*31:0*/ t__DOT__src1;
+    IData/*31:0*/ t__DOT__src0;
+    IData/*31:0*/ t__DOT__sr;
+    IData/*31:0*/ t__DOT__mask;
+    IData/*31:0*/ t__DOT__dualasr;
+    IData/*31:0*/ t__DOT__sl_mask;
+    IData/*31:0*/ t__DOT__sr_mask;
+    IData/*31:0*/ __VactIterCount;
+    QData/*63:0*/ t__DOT__rf;
+    QData/*63:0*/ t__DOT__rf2;
+    QData/*63:0*/ t__DOT__biu;
+    VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_math_repl__cuda final {
+    typedef Vt_math_repl___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 84,
+        OFF_t__DOT__b = 85,
+        OFF___VstlFirstIteration = 86,
+        OFF___VstlPhaseResult = 87,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 88,
+        OFF___VactPhaseResult = 89,
+        OFF___VnbaPhaseResult = 90,
+        OFF_t__DOT__cyc = 48,
+        OFF_t__DOT__src1 = 52,
+        OFF_t__DOT__src0 = 56,
+        OFF_t__DOT__sr = 60,
+        OFF_t__DOT__mask = 64,
+        OFF_t__DOT__dualasr = 68,
+        OFF_t__DOT__sl_mask = 72,
+        OFF_t__DOT__sr_mask = 76,
+        OFF___VactIterCount = 80,
+        OFF_t__DOT__rf = 0,
+        OFF_t__DOT__rf2 = 8,
+        OFF_t__DOT__biu = 16,
+        OFF___VstlTriggered = 24,
+        OFF___VactTriggered = 32,
+        OFF___VnbaTriggered = 40,
+        kStateBytes = 96,  // S_persist
+        kTouchedReadBytes = 81,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 80,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.t__DOT__b = st.ld<VlcuMem8>(OFF_t__DOT__b, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.t__DOT__cyc = st.ld<IData>(OFF_t__DOT__cyc, i);
+        s.t__DOT__src1 = st.ld<IData>(OFF_t__DOT__src1, i);
+        s.t__DOT__src0 = st.ld<IData>(OFF_t__DOT__src0, i);
+        s.t__DOT__sr = st.ld<IData>(OFF_t__DOT__sr, i);
+        s.t__DOT__mask = st.ld<IData>(OFF_t__DOT__mask, i);
+        s.t__DOT__dualasr = st.ld<IData>(OFF_t__DOT__dualasr, i);
+        s.t__DOT__sl_mask = st.ld<IData>(OFF_t__DOT__sl_mask, i);
+        s.t__DOT__sr_mask = st.ld<IData>(OFF_t__DOT__sr_mask, i);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        s.t__DOT__rf = st.ld<QData>(OFF_t__DOT__rf, i);
+        s.t__DOT__rf2 = st.ld<QData>(OFF_t__DOT__rf2, i);
+        s.t__DOT__biu = st.ld<QData>(OFF_t__DOT__biu, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_t__DOT__b, i, s.t__DOT__b);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.st<IData>(OFF_t__DOT__src1, i, s.t__DOT__src1);
+        st.st<IData>(OFF_t__DOT__src0, i, s.t__DOT__src0);
+        st.st<IData>(OFF_t__DOT__sr, i, s.t__DOT__sr);
+        st.st<IData>(OFF_t__DOT__mask, i, s.t__DOT__mask);
+        st.st<IData>(OFF_t__DOT__dualasr, i, s.t__DOT__dualasr);
+        st.st<IData>(OFF_t__DOT__sl_mask, i, s.t__DOT__sl_mask);
+        st.st<IData>(OFF_t__DOT__sr_mask, i, s.t__DOT__sr_mask);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        st.st<QData>(OFF_t__DOT__rf, i, s.t__DOT__rf);
+        st.st<QData>(OFF_t__DOT__rf2, i, s.t__DOT__rf2);
+        st.st<QData>(OFF_t__DOT__biu, i, s.t__DOT__biu);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_math_repl___024root___eval_static(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_math_repl___024root___eval_initial(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_initial__TOP
+            vlSelfRef.t__DOT__cyc = 1U;
+        }
+    }
+
+    VLCU_D static void Vt_math_repl___024root___eval_final(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_math_repl___024root___eval_settle(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VstlIterCount;
+        // Body
+        __VstlIterCount = 0U;
+        vlSelfRef.__VstlFirstIteration = 1U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VstlIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_math_repl___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_math_repl.v", 7, "", "DIDNOTCONVERGE: Settle region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VstlIterCount = ((IData)(1U) + __VstlIterCount);
+            vlSelfRef.__VstlPhaseResult = Vt_math_repl___024root___eval_phase__stl(vlSelf, vlCtx);
+            vlSelfRef.__VstlFirstIteration = 0U;
+        } while (vlSelfRef.__VstlPhaseResult);
+    }
+
+    VLCU_D static bool Vt_math_repl___024root___trigger_anySet__stl(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_repl___024root___stl_sequent__TOP__0(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VdfgRegularize_h6e95ff9d_0_0;
+        __VdfgRegularize_h6e95ff9d_0_0 = 0;
+        IData/*31:0*/ __VdfgRegularize_h6e95ff9d_0_1;
+        __VdfgRegularize_h6e95ff9d_0_1 = 0;
+        // Body
+        vlSelfRef.t__DOT__sl_mask = ((IData)(0xffffffffU) 
+                                     << (0x0000001fU 
+                                         & vlSelfRef.t__DOT__src1));
+        vlSelfRef.t__DOT__sr_mask = ((((((((2U & (((IData)(1U) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 1U))) 
+                                          << 6U) | 
+                                         (((2U & (((IData)(0xffffffffU) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  >> 1U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 3U))) 
+                                          << 4U)) | 
+                                        ((((2U & (((IData)(0xffffffffU) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  >> 3U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 5U))) 
+                                          << 2U) | 
+                                         ((2U & (((IData)(0xffffffffU) 
+                                                  << 
+                                                  (0x0000001fU 
+                                                   & vlSelfRef.t__DOT__src1)) 
+                                                 >> 5U)) 
+                                          | (1U & (
+                                                   ((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 7U))))) 
+                                       << 0x00000018U) 
+                                      | ((((((2U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 7U)) 
+                                             | (1U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 9U))) 
+                                            << 6U) 
+                                           | (((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 9U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x0000000bU))) 
+                                              << 4U)) 
+                                          | ((((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x0000000bU)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x0000000dU))) 
+                                              << 2U) 
+                                             | ((2U 
+                                                 & (((IData)(0xffffffffU) 
+                                                     << 
+                                                     (0x0000001fU 
+                                                      & vlSelfRef.t__DOT__src1)) 
+                                                    >> 0x0000000dU)) 
+                                                | (1U 
+                                                   & (((IData)(0xffffffffU) 
+                                                       << 
+                                                       (0x0000001fU 
+                                                        & vlSelfRef.t__DOT__src1)) 
+                                                      >> 0x0000000fU))))) 
+                                         << 0x00000010U)) 
+                                     | (((((((2U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 0x0000000fU)) 
+                                             | (1U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000011U))) 
+                                            << 6U) 
+                                           | (((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000011U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x00000013U))) 
+                                              << 4U)) 
+                                          | ((((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000013U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x00000015U))) 
+                                              << 2U) 
+                                             | ((2U 
+                                                 & (((IData)(0xffffffffU) 
+                                                     << 
+                                                     (0x0000001fU 
+                                                      & vlSelfRef.t__DOT__src1)) 
+                                                    >> 0x00000015U)) 
+                                                | (1U 
+                                                   & (((IData)(0xffffffffU) 
+                                                       << 
+                                                       (0x0000001fU 
+                                                        & vlSelfRef.t__DOT__src1)) 
+                                                      >> 0x00000017U))))) 
+                                         << 8U) | (
+                                                   ((((2U 
+                                                       & (((IData)(0xffffffffU) 
+                                                           << 
+                                                           (0x0000001fU 
+                                                            & vlSelfRef.t__DOT__src1)) 
+                                                          >> 0x00000017U)) 
+                                                      | (1U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x00000019U))) 
+                                                     << 6U) 
+                                                    | (((2U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x00000019U)) 
+                                                        | (1U 
+                                                           & (((IData)(0xffffffffU) 
+                                                               << 
+                                                               (0x0000001fU 
+                                                                & vlSelfRef.t__DOT__src1)) 
+                                                              >> 0x0000001bU))) 
+                                                       << 4U)) 
+                                                   | ((((2U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x0000001bU)) 
+                                                        | (1U 
+                                                           & (((IData)(0xffffffffU) 
+                                                               << 
+                                                               (0x0000001fU 
+                                                                & vlSelfRef.t__DOT__src1)) 
+                                                              >> 0x0000001dU))) 
+                                                       << 2U) 
+                                                      | ((2U 
+                                                          & (((IData)(0xffffffffU) 
+                                                              << 
+                                                              (0x0000001fU 
+                                                               & vlSelfRef.t__DOT__src1)) 
+                                                             >> 0x0000001dU)) 
+                                                         | (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x0000001fU))))));
+        __VdfgRegularize_h6e95ff9d_0_1 = (((- (IData)(
+                                                      (vlSelfRef.t__DOT__src0 
+                                                       >> 0x0000001fU))) 
+                                           << 0x00000010U) 
+                                          | (0x0000ffffU 
+                                             & (- (IData)(
+                                                          (1U 
+                                                           & (vlSelfRef.t__DOT__src0 
+                                                              >> 0x0000000fU))))));
+        __VdfgRegularize_h6e95ff9d_0_0 = ((IData)((vlSelfRef.t__DOT__biu 
+                                                   >> 0x00000020U)) 
+                                          & (- (IData)((IData)(vlSelfRef.t__DOT__b))));
+        vlSelfRef.t__DOT__dualasr = ((0U != (vlSelfRef.t__DOT__src1 
+                                             >> 4U))
+                                      ? __VdfgRegularize_h6e95ff9d_0_1
+                                      : ((vlSelfRef.t__DOT__sr 
+                                          & ((0xffff0000U 
+                                              & vlSelfRef.t__DOT__mask) 
+                                             | (vlSelfRef.t__DOT__mask 
+                                                >> 0x00000010U))) 
+                                         | (__VdfgRegularize_h6e95ff9d_0_1 
+                                            & (((~ 
+                                                 (vlSelfRef.t__DOT__mask 
+                                                  >> 0x00000010U)) 
+                                                << 0x00000010U) 
+                                               | (0x0000ffffU 
+                                                  & (~ 
+                                                     (vlSelfRef.t__DOT__mask 
+                                                      >> 0x00000010U)))))));
+        vlSelfRef.t__DOT__rf = (((QData)((IData)(__VdfgRegularize_h6e95ff9d_0_0)) 
+                                 << 0x00000020U) | (QData)((IData)(
+                                                                   (- (IData)((IData)(vlSelfRef.t__DOT__b))))));
+        vlSelfRef.t__DOT__rf2 = (((QData)((IData)(__VdfgRegularize_h6e95ff9d_0_0)) 
+                                  << 0x00000020U) | (QData)((IData)(
+                                                                    (~ 
+                                                                     (- (IData)((IData)(vlSelfRef.t__DOT__b)))))));
+    }
+
+    VLCU_D static bool Vt_math_repl___024root___eval_phase__stl(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VstlExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__stl
+            vlSelfRef.__VstlTriggered[0U] = ((0xfffffffffffffffeULL 
+                                              & vlSelfRef.__VstlTriggered[0U]) 
+                                             | (IData)((IData)(vlSelfRef.__VstlFirstIteration)));
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_math_repl___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+        }
+#endif
+        __VstlExecute = Vt_math_repl___024root___trigger_anySet__stl(vlSelfRef.__VstlTriggered);
+        if (__VstlExecute) {
+            {
+                // Inlined CFunc: _eval_stl
+                if ((1ULL & vlSelfRef.__VstlTriggered[0U])) {
+                    Vt_math_repl___024root___stl_sequent__TOP__0(vlSelf, vlCtx);
+                }
+            }
+        }
+        return (__VstlExecute);
+    }
+
+    VLCU_D static bool Vt_math_repl___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_repl___024root___nba_sequent__TOP__0(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VdfgRegularize_h6e95ff9d_0_0;
+        __VdfgRegularize_h6e95ff9d_0_0 = 0;
+        IData/*31:0*/ __VdfgRegularize_h6e95ff9d_0_1;
+        __VdfgRegularize_h6e95ff9d_0_1 = 0;
+        IData/*31:0*/ __Vdly__t__DOT__cyc;
+        __Vdly__t__DOT__cyc = 0;
+        CData/*0:0*/ __Vdly__t__DOT__b;
+        __Vdly__t__DOT__b = 0;
+        // Body
+        __Vdly__t__DOT__cyc = vlSelfRef.t__DOT__cyc;
+        __Vdly__t__DOT__b = vlSelfRef.t__DOT__b;
+        if ((0U != vlSelfRef.t__DOT__cyc)) {
+            __Vdly__t__DOT__cyc = ((IData)(1U) + vlSelfRef.t__DOT__cyc);
+            if ((1U == vlSelfRef.t__DOT__cyc)) {
+                vlSelfRef.t__DOT__biu = 0x12451282abadee00ULL;
+                __Vdly__t__DOT__b = 0U;
+                vlSelfRef.t__DOT__src1 = 1U;
+                vlSelfRef.t__DOT__src0 = 0x9a4f1235U;
+                vlSelfRef.t__DOT__sr = 0x0f19f567U;
+                vlSelfRef.t__DOT__mask = 0x7af07ab4U;
+            }
+            if ((2U == vlSelfRef.t__DOT__cyc)) {
+                if (VL_UNLIKELY(((0ULL != vlSelfRef.t__DOT__rf)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 75, "");
+                }
+                vlSelfRef.t__DOT__biu = 0x12453382abad8801ULL;
+                if (VL_UNLIKELY(((0x00000000ffffffffULL 
+                                  != vlSelfRef.t__DOT__rf2)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 76, "");
+                }
+                vlSelfRef.t__DOT__src1 = 0x0010000fU;
+                vlSelfRef.t__DOT__src0 = 0x028aa336U;
+                vlSelfRef.t__DOT__sr = 0x42ad0377U;
+                vlSelfRef.t__DOT__mask = 0x1ab3b906U;
+                if (VL_UNLIKELY(((0x8f1f7060U != vlSelfRef.t__DOT__dualasr)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 81, "");
+                }
+                if (VL_UNLIKELY(((0xfffffffeU != vlSelfRef.t__DOT__sl_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 82, "");
+                }
+                if (VL_UNLIKELY(((0x7fffffffU != vlSelfRef.t__DOT__sr_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 83, "");
+                }
+                if (VL_UNLIKELY(((0U != (((- (IData)((IData)(vlSelfRef.t__DOT__b))) 
+                                          | (- (IData)((IData)(vlSelfRef.t__DOT__b)))) 
+                                         | (- (IData)((IData)(vlSelfRef.t__DOT__b)))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 84, "");
+                }
+                __Vdly__t__DOT__b = 1U;
+            }
+            if ((3U == vlSelfRef.t__DOT__cyc)) {
+                if (VL_UNLIKELY(((0x12453382ffffffffULL 
+                                  != vlSelfRef.t__DOT__rf)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 89, "");
+                }
+                vlSelfRef.t__DOT__biu = 0x1242238277ad8802ULL;
+                if (VL_UNLIKELY(((0x1245338200000000ULL 
+                                  != vlSelfRef.t__DOT__rf2)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 90, "");
+                }
+                vlSelfRef.t__DOT__src1 = 0x0000000fU;
+                vlSelfRef.t__DOT__src0 = 0x5c158f71U;
+                vlSelfRef.t__DOT__sr = 0x7076c40aU;
+                vlSelfRef.t__DOT__mask = 0x33eb3d44U;
+                if (VL_UNLIKELY(((0x0000ffffU != vlSelfRef.t__DOT__dualasr)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 95, "");
+                }
+                if (VL_UNLIKELY(((0xffff8000U != vlSelfRef.t__DOT__sl_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 96, "");
+                }
+                if (VL_UNLIKELY(((0x0001ffffU != vlSelfRef.t__DOT__sr_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 97, "");
+                }
+                if (VL_UNLIKELY(((0U != (((~ (- (IData)((IData)(vlSelfRef.t__DOT__b)))) 
+                                          | (~ (- (IData)((IData)(vlSelfRef.t__DOT__b))))) 
+                                         | (~ (- (IData)((IData)(vlSelfRef.t__DOT__b))))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 98, "");
+                }
+                __Vdly__t__DOT__b = 1U;
+            }
+            if (VL_UNLIKELY(((4U == vlSelfRef.t__DOT__cyc)))) {
+                if (VL_UNLIKELY(((0x12422382ffffffffULL 
+                                  != vlSelfRef.t__DOT__rf)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 101, "");
+                }
+                if (VL_UNLIKELY(((0x1242238200000000ULL 
+                                  != vlSelfRef.t__DOT__rf2)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 102, "");
+                }
+                if (VL_UNLIKELY(((0x3062cc1eU != vlSelfRef.t__DOT__dualasr)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 103, "");
+                }
+                if (VL_UNLIKELY(((0xffff8000U != vlSelfRef.t__DOT__sl_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 104, "");
+                }
+                if (VL_UNLIKELY(((0x0001ffffU != vlSelfRef.t__DOT__sr_mask)))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 105, "");
+                }
+                vlCtx.writef(0U, 0U);
+                if (VL_UNLIKELY(((0U != (((~ (- (IData)((IData)(vlSelfRef.t__DOT__b)))) 
+                                          | (~ (- (IData)((IData)(vlSelfRef.t__DOT__b))))) 
+                                         | (~ (- (IData)((IData)(vlSelfRef.t__DOT__b))))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_math_repl.v", 107, "");
+                }
+                VL_FINISH_MT("/root/reference/test_regress/t/t_math_repl.v", 108, "");
+            }
+        }
+        vlSelfRef.t__DOT__cyc = __Vdly__t__DOT__cyc;
+        vlSelfRef.t__DOT__b = __Vdly__t__DOT__b;
+        __VdfgRegularize_h6e95ff9d_0_1 = (((- (IData)(
+                                                      (vlSelfRef.t__DOT__src0 
+                                                       >> 0x0000001fU))) 
+                                           << 0x00000010U) 
+                                          | (0x0000ffffU 
+                                             & (- (IData)(
+                                                          (1U 
+                                                           & (vlSelfRef.t__DOT__src0 
+                                                              >> 0x0000000fU))))));
+        vlSelfRef.t__DOT__sl_mask = ((IData)(0xffffffffU) 
+                                     << (0x0000001fU 
+                                         & vlSelfRef.t__DOT__src1));
+        vlSelfRef.t__DOT__sr_mask = ((((((((2U & (((IData)(1U) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  << 1U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 1U))) 
+                                          << 6U) | 
+                                         (((2U & (((IData)(0xffffffffU) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  >> 1U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 3U))) 
+                                          << 4U)) | 
+                                        ((((2U & (((IData)(0xffffffffU) 
+                                                   << 
+                                                   (0x0000001fU 
+                                                    & vlSelfRef.t__DOT__src1)) 
+                                                  >> 3U)) 
+                                           | (1U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 5U))) 
+                                          << 2U) | 
+                                         ((2U & (((IData)(0xffffffffU) 
+                                                  << 
+                                                  (0x0000001fU 
+                                                   & vlSelfRef.t__DOT__src1)) 
+                                                 >> 5U)) 
+                                          | (1U & (
+                                                   ((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 7U))))) 
+                                       << 0x00000018U) 
+                                      | ((((((2U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 7U)) 
+                                             | (1U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 9U))) 
+                                            << 6U) 
+                                           | (((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 9U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x0000000bU))) 
+                                              << 4U)) 
+                                          | ((((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x0000000bU)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x0000000dU))) 
+                                              << 2U) 
+                                             | ((2U 
+                                                 & (((IData)(0xffffffffU) 
+                                                     << 
+                                                     (0x0000001fU 
+                                                      & vlSelfRef.t__DOT__src1)) 
+                                                    >> 0x0000000dU)) 
+                                                | (1U 
+                                                   & (((IData)(0xffffffffU) 
+                                                       << 
+                                                       (0x0000001fU 
+                                                        & vlSelfRef.t__DOT__src1)) 
+                                                      >> 0x0000000fU))))) 
+                                         << 0x00000010U)) 
+                                     | (((((((2U & 
+                                              (((IData)(0xffffffffU) 
+                                                << 
+                                                (0x0000001fU 
+                                                 & vlSelfRef.t__DOT__src1)) 
+                                               >> 0x0000000fU)) 
+                                             | (1U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000011U))) 
+                                            << 6U) 
+                                           | (((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000011U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x00000013U))) 
+                                              << 4U)) 
+                                          | ((((2U 
+                                                & (((IData)(0xffffffffU) 
+                                                    << 
+                                                    (0x0000001fU 
+                                                     & vlSelfRef.t__DOT__src1)) 
+                                                   >> 0x00000013U)) 
+                                               | (1U 
+                                                  & (((IData)(0xffffffffU) 
+                                                      << 
+                                                      (0x0000001fU 
+                                                       & vlSelfRef.t__DOT__src1)) 
+                                                     >> 0x00000015U))) 
+                                              << 2U) 
+                                             | ((2U 
+                                                 & (((IData)(0xffffffffU) 
+                                                     << 
+                                                     (0x0000001fU 
+                                                      & vlSelfRef.t__DOT__src1)) 
+                                                    >> 0x00000015U)) 
+                                                | (1U 
+                                                   & (((IData)(0xffffffffU) 
+                                                       << 
+                                                       (0x0000001fU 
+                                                        & vlSelfRef.t__DOT__src1)) 
+                                                      >> 0x00000017U))))) 
+                                         << 8U) | (
+                                                   ((((2U 
+                                                       & (((IData)(0xffffffffU) 
+                                                           << 
+                                                           (0x0000001fU 
+                                                            & vlSelfRef.t__DOT__src1)) 
+                                                          >> 0x00000017U)) 
+                                                      | (1U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x00000019U))) 
+                                                     << 6U) 
+                                                    | (((2U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x00000019U)) 
+                                                        | (1U 
+                                                           & (((IData)(0xffffffffU) 
+                                                               << 
+                                                               (0x0000001fU 
+                                                                & vlSelfRef.t__DOT__src1)) 
+                                                              >> 0x0000001bU))) 
+                                                       << 4U)) 
+                                                   | ((((2U 
+                                                         & (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x0000001bU)) 
+                                                        | (1U 
+                                                           & (((IData)(0xffffffffU) 
+                                                               << 
+                                                               (0x0000001fU 
+                                                                & vlSelfRef.t__DOT__src1)) 
+                                                              >> 0x0000001dU))) 
+                                                       << 2U) 
+                                                      | ((2U 
+                                                          & (((IData)(0xffffffffU) 
+                                                              << 
+                                                              (0x0000001fU 
+                                                               & vlSelfRef.t__DOT__src1)) 
+                                                             >> 0x0000001dU)) 
+                                                         | (((IData)(0xffffffffU) 
+                                                             << 
+                                                             (0x0000001fU 
+                                                              & vlSelfRef.t__DOT__src1)) 
+                                                            >> 0x0000001fU))))));
+        __VdfgRegularize_h6e95ff9d_0_0 = ((IData)((vlSelfRef.t__DOT__biu 
+                                                   >> 0x00000020U)) 
+                                          & (- (IData)((IData)(vlSelfRef.t__DOT__b))));
+        vlSelfRef.t__DOT__dualasr = ((0U != (vlSelfRef.t__DOT__src1 
+                                             >> 4U))
+                                      ? __VdfgRegularize_h6e95ff9d_0_1
+                                      : ((vlSelfRef.t__DOT__sr 
+                                          & ((0xffff0000U 
+                                              & vlSelfRef.t__DOT__mask) 
+                                             | (vlSelfRef.t__DOT__mask 
+                                                >> 0x00000010U))) 
+                                         | (__VdfgRegularize_h6e95ff9d_0_1 
+                                            & (((~ 
+                                                 (vlSelfRef.t__DOT__mask 
+                                                  >> 0x00000010U)) 
+                                                << 0x00000010U) 
+                                               | (0x0000ffffU 
+                                                  & (~ 
+                                                     (vlSelfRef.t__DOT__mask 
+                                                      >> 0x00000010U)))))));
+        vlSelfRef.t__DOT__rf = (((QData)((IData)(__VdfgRegularize_h6e95ff9d_0_0)) 
+                                 << 0x00000020U) | (QData)((IData)(
+                                                                   (- (IData)((IData)(vlSelfRef.t__DOT__b))))));
+        vlSelfRef.t__DOT__rf2 = (((QData)((IData)(__VdfgRegularize_h6e95ff9d_0_0)) 
+                                  << 0x00000020U) | (QData)((IData)(
+                                                                    (~ 
+                                                                     (- (IData)((IData)(vlSelfRef.t__DOT__b)))))));
+    }
+
+    VLCU_D static void Vt_math_repl___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt_math_repl___024root___eval_phase__act(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_math_repl___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_math_repl___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt_math_repl___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt_math_repl___024root___eval_phase__nba(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_math_repl___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    Vt_math_repl___024root___nba_sequent__TOP__0(vlSelf, vlCtx);
+                }
+            }
+            Vt_math_repl___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_math_repl___024root___eval(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_math_repl___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_math_repl.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_math_repl___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_math_repl.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_math_repl___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_math_repl___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_math_repl___024root___ctor_var_reset(Vt_math_repl___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->t__DOT__cyc = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 15508623621340971111ull);
+        vlSelf->t__DOT__rf = VL_SCOPED_RAND_RESET_Q(64, __VscopeHash, 1327397155087044534ull);
+        vlSelf->t__DOT__rf2 = VL_SCOPED_RAND_RESET_Q(64, __VscopeHash, 4613431645903877921ull);
+        vlSelf->t__DOT__biu = VL_SCOPED_RAND_RESET_Q(64, __VscopeHash, 17185135913512039957ull);
+        vlSelf->t__DOT__b = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 11816130287683444364ull);
+        vlSelf->t__DOT__src1 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 11963153284776517329ull);
+        vlSelf->t__DOT__src0 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 17992167717701705815ull);
+        vlSelf->t__DOT__sr = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 2750434385867559212ull);
+        vlSelf->t__DOT__mask = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 15404644188980875732ull);
+        vlSelf->t__DOT__dualasr = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 6067696294317704601ull);
+        vlSelf->t__DOT__sl_mask = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 4482627689896951934ull);
+        vlSelf->t__DOT__sr_mask = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 16712329548423682682ull);
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VstlTriggered[__Vi0] = 0;
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_math_repl___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_repl___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_repl___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_repl___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_repl___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_math_repl___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_math_repl__cuda::info() {
+    typedef Vt_math_repl__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"t__DOT__b", "t.b", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__b},
+        {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
+        {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__cyc},
+        {"t__DOT__src1", "t.src1", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__src1},
+        {"t__DOT__src0", "t.src0", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__src0},
+        {"t__DOT__sr", "t.sr", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__sr},
+        {"t__DOT__mask", "t.mask", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__mask},
+        {"t__DOT__dualasr", "t.dualasr", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__dualasr},
+        {"t__DOT__sl_mask", "t.sl_mask", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__sl_mask},
+        {"t__DOT__sr_mask", "t.sr_mask", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__sr_mask},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"t__DOT__rf", "t.rf", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF_t__DOT__rf},
+        {"t__DOT__rf2", "t.rf2", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF_t__DOT__rf2},
+        {"t__DOT__biu", "t.biu", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF_t__DOT__biu},
+        {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 1, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 22, 0, 0xc6a204c5b5e66a70ULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_math_repl__cuda VLCU_TESTBENCHES);

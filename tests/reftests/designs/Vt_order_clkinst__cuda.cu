@@ -1,0 +1,716 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_order_clkinst"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_order_clkinst___024root final {
+    CData/*0:0*/ clk;
+    CData/*0:0*/ t__DOT__c1_start;
+    CData/*7:0*/ t__DOT__cyc;
+    CData/*0:0*/ __VstlFirstIteration;
+    CData/*0:0*/ __VstlPhaseResult;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__t__DOT__c1_start__0;
+    CData/*0:0*/ __Vtrigprevexpr_h83885254__0;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactDidInit;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ t__DOT__c1_count;
+    IData/*31:0*/ t__DOT__s2_count;
+    IData/*31:0*/ t__DOT__c3_count;
+    IData/*31:0*/ t__DOT__c3__DOT__runnerm1;
+    IData/*31:0*/ t__DOT__c3__DOT__runner;
+    IData/*31:0*/ t__DOT__c1__DOT__runnerm1;
+    IData/*31:0*/ t__DOT__c1__DOT__runner;
+    IData/*31:0*/ t__DOT__s2__DOT__runnerm1;
+    IData/*31:0*/ t__DOT__s2__DOT__runner;
+    IData/*31:0*/ __Vdly__t__DOT__s2__DOT__runner;
+    IData/*31:0*/ __Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0;
+    IData/*31:0*/ __Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0;
+    IData/*31:0*/ __Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0;
+    IData/*31:0*/ __VactIterCount;
+    VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
+    VlUnpacked<QData/*63:0*/, 3> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 2> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_order_clkinst__cuda final {
+    typedef Vt_order_clkinst___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 104,
+        OFF_t__DOT__c1_start = 105,
+        OFF_t__DOT__cyc = 106,
+        OFF___VstlFirstIteration = 107,
+        OFF___VstlPhaseResult = 108,
+        OFF___Vtrigprevexpr___TOP__t__DOT__c1_start__0 = 109,
+        OFF___Vtrigprevexpr_h83885254__0 = 110,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 111,
+        OFF___VactDidInit = 112,
+        OFF___VactPhaseResult = 113,
+        OFF___VnbaPhaseResult = 114,
+        OFF_t__DOT__c1_count = 48,
+        OFF_t__DOT__s2_count = 52,
+        OFF_t__DOT__c3_count = 56,
+        OFF_t__DOT__c3__DOT__runnerm1 = 60,
+        OFF_t__DOT__c3__DOT__runner = 64,
+        OFF_t__DOT__c1__DOT__runnerm1 = 68,
+        OFF_t__DOT__c1__DOT__runner = 72,
+        OFF_t__DOT__s2__DOT__runnerm1 = 76,
+        OFF_t__DOT__s2__DOT__runner = 80,
+        OFF___Vdly__t__DOT__s2__DOT__runner = 84,
+        OFF___Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0 = 88,
+        OFF___Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0 = 92,
+        OFF___Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0 = 96,
+        OFF___VactIterCount = 100,
+        OFF___VstlTriggered = 0,
+        OFF___VactTriggered = 8,
+        OFF___VnbaTriggered = 32,
+        kStateBytes = 120,  // S_persist
+        kTouchedReadBytes = 105,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 96,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.t__DOT__c1_start = st.ld<VlcuMem8>(OFF_t__DOT__c1_start, i);
+        s.t__DOT__cyc = st.ld<VlcuMem8>(OFF_t__DOT__cyc, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__t__DOT__c1_start__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__t__DOT__c1_start__0, i);
+        s.__Vtrigprevexpr_h83885254__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr_h83885254__0, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactDidInit = st.ld<VlcuMem8>(OFF___VactDidInit, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.t__DOT__c1_count = st.ld<IData>(OFF_t__DOT__c1_count, i);
+        s.t__DOT__s2_count = st.ld<IData>(OFF_t__DOT__s2_count, i);
+        s.t__DOT__c3_count = st.ld<IData>(OFF_t__DOT__c3_count, i);
+        s.t__DOT__c3__DOT__runnerm1 = st.ld<IData>(OFF_t__DOT__c3__DOT__runnerm1, i);
+        s.t__DOT__c3__DOT__runner = st.ld<IData>(OFF_t__DOT__c3__DOT__runner, i);
+        s.t__DOT__c1__DOT__runnerm1 = st.ld<IData>(OFF_t__DOT__c1__DOT__runnerm1, i);
+        s.t__DOT__c1__DOT__runner = st.ld<IData>(OFF_t__DOT__c1__DOT__runner, i);
+        s.t__DOT__s2__DOT__runnerm1 = st.ld<IData>(OFF_t__DOT__s2__DOT__runnerm1, i);
+        s.t__DOT__s2__DOT__runner = st.ld<IData>(OFF_t__DOT__s2__DOT__runner, i);
+        s.__Vdly__t__DOT__s2__DOT__runner = st.ld<IData>(OFF___Vdly__t__DOT__s2__DOT__runner, i);
+        s.__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0 = st.ld<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0, i);
+        s.__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0 = st.ld<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0, i);
+        s.__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0 = st.ld<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0, i);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
+        for (uint32_t e = 0; e < 3; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 2; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_t__DOT__c1_start, i, s.t__DOT__c1_start);
+        st.st<VlcuMem8>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__t__DOT__c1_start__0, i, s.__Vtrigprevexpr___TOP__t__DOT__c1_start__0);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr_h83885254__0, i, s.__Vtrigprevexpr_h83885254__0);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactDidInit, i, s.__VactDidInit);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF_t__DOT__c1_count, i, s.t__DOT__c1_count);
+        st.st<IData>(OFF_t__DOT__s2_count, i, s.t__DOT__s2_count);
+        st.st<IData>(OFF_t__DOT__c3_count, i, s.t__DOT__c3_count);
+        st.st<IData>(OFF_t__DOT__c3__DOT__runnerm1, i, s.t__DOT__c3__DOT__runnerm1);
+        st.st<IData>(OFF_t__DOT__c3__DOT__runner, i, s.t__DOT__c3__DOT__runner);
+        st.st<IData>(OFF_t__DOT__c1__DOT__runnerm1, i, s.t__DOT__c1__DOT__runnerm1);
+        st.st<IData>(OFF_t__DOT__c1__DOT__runner, i, s.t__DOT__c1__DOT__runner);
+        st.st<IData>(OFF_t__DOT__s2__DOT__runnerm1, i, s.t__DOT__s2__DOT__runnerm1);
+        st.st<IData>(OFF_t__DOT__s2__DOT__runner, i, s.t__DOT__s2__DOT__runner);
+        st.st<IData>(OFF___Vdly__t__DOT__s2__DOT__runner, i, s.__Vdly__t__DOT__s2__DOT__runner);
+        st.st<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0, i, s.__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0);
+        st.st<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0, i, s.__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0);
+        st.st<IData>(OFF___Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0, i, s.__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
+        for (uint32_t e = 0; e < 3; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 2; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_order_clkinst___024root___eval_static(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_static__TOP
+            vlSelfRef.t__DOT__c3_count = 0U;
+            vlSelfRef.t__DOT__c1_count = 0U;
+        }
+        vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1_start__0 
+            = vlSelfRef.t__DOT__c1_start;
+        vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0 
+            = vlSelfRef.t__DOT__s2__DOT__runnerm1;
+        vlSelfRef.__Vtrigprevexpr_h83885254__0 = (1U 
+                                                  & vlSelfRef.t__DOT__s2_count);
+        vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0 
+            = vlSelfRef.t__DOT__c3__DOT__runnerm1;
+        vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0 
+            = vlSelfRef.t__DOT__c1__DOT__runnerm1;
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___eval_initial(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_initial__TOP
+            vlSelfRef.t__DOT__c1_start = 0U;
+            vlSelfRef.t__DOT__cyc = 0U;
+            vlSelfRef.t__DOT__c3__DOT__runner = 0U;
+            vlSelfRef.t__DOT__c1__DOT__runner = 0U;
+            vlSelfRef.t__DOT__s2_count = 0U;
+            vlSelfRef.t__DOT__s2__DOT__runner = 0U;
+        }
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___eval_final(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___eval_settle(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VstlIterCount;
+        // Body
+        __VstlIterCount = 0U;
+        vlSelfRef.__VstlFirstIteration = 1U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VstlIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_order_clkinst___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_order_clkinst.v", 7, "", "DIDNOTCONVERGE: Settle region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VstlIterCount = ((IData)(1U) + __VstlIterCount);
+            vlSelfRef.__VstlPhaseResult = Vt_order_clkinst___024root___eval_phase__stl(vlSelf, vlCtx);
+            vlSelfRef.__VstlFirstIteration = 0U;
+        } while (vlSelfRef.__VstlPhaseResult);
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___trigger_anySet__stl(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___eval_phase__stl(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VstlExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__stl
+            vlSelfRef.__VstlTriggered[0U] = ((0xfffffffffffffffeULL 
+                                              & vlSelfRef.__VstlTriggered[0U]) 
+                                             | (IData)((IData)(vlSelfRef.__VstlFirstIteration)));
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_order_clkinst___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+        }
+#endif
+        __VstlExecute = Vt_order_clkinst___024root___trigger_anySet__stl(vlSelfRef.__VstlTriggered);
+        if (__VstlExecute) {
+            {
+                // Inlined CFunc: _eval_stl
+                if ((1ULL & vlSelfRef.__VstlTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _stl_sequent__TOP__0
+                        vlSelfRef.t__DOT__c3__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__c3__DOT__runner 
+                               - (IData)(1U));
+                        vlSelfRef.t__DOT__c1__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__c1__DOT__runner 
+                               - (IData)(1U));
+                        vlSelfRef.t__DOT__s2__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__s2__DOT__runner 
+                               - (IData)(1U));
+                    }
+                }
+            }
+        }
+        return (__VstlExecute);
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___eval_triggers_ext__act(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx, const VlUnpacked<QData/*63:0*/, 2> &latched) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VactTrigPreLoopCounter;
+        // Body
+        __VactTrigPreLoopCounter = 0U;
+        do {
+            vlSelfRef.__VactTriggered[((IData)(2U) 
+                                       + __VactTrigPreLoopCounter)] 
+                = (vlSelfRef.__VactTriggered[__VactTrigPreLoopCounter] 
+                   & (~ latched[__VactTrigPreLoopCounter]));
+            __VactTrigPreLoopCounter = ((IData)(1U) 
+                                        + __VactTrigPreLoopCounter);
+        } while ((1U > __VactTrigPreLoopCounter));
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 2> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((2U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___trigger_orInto__act_ext_vec(VlUnpacked<QData/*63:0*/, 2> &out, const VlUnpacked<QData/*63:0*/, 3> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((1U >= n));
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___eval_phase__act(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VactExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            (((vlSelfRef.t__DOT__s2__DOT__runnerm1 
+                                                               != vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0) 
+                                                              << 1U) 
+                                                             | ((IData)(vlSelfRef.t__DOT__c1_start) 
+                                                                & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1_start__0))))));
+            vlSelfRef.__VactTriggered[1U] = (QData)((IData)(
+                                                            (((((IData)(vlSelfRef.clk) 
+                                                                & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0))) 
+                                                               << 3U) 
+                                                              | ((vlSelfRef.t__DOT__c1__DOT__runnerm1 
+                                                                  != vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0) 
+                                                                 << 2U)) 
+                                                             | (((vlSelfRef.t__DOT__c3__DOT__runnerm1 
+                                                                  != vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0) 
+                                                                 << 1U) 
+                                                                | (1U 
+                                                                   & (vlSelfRef.t__DOT__s2_count 
+                                                                      & (~ (IData)(vlSelfRef.__Vtrigprevexpr_h83885254__0))))))));
+            vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1_start__0 
+                = vlSelfRef.t__DOT__c1_start;
+            vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0 
+                = vlSelfRef.t__DOT__s2__DOT__runnerm1;
+            vlSelfRef.__Vtrigprevexpr_h83885254__0 
+                = (1U & vlSelfRef.t__DOT__s2_count);
+            vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0 
+                = vlSelfRef.t__DOT__c3__DOT__runnerm1;
+            vlSelfRef.__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0 
+                = vlSelfRef.t__DOT__c1__DOT__runnerm1;
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+            if (VL_UNLIKELY(((1U & (~ (IData)(vlSelfRef.__VactDidInit)))))) {
+                vlSelfRef.__VactDidInit = 1U;
+                vlSelfRef.__VactTriggered[0U] = (2ULL 
+                                                 | vlSelfRef.__VactTriggered[0U]);
+                vlSelfRef.__VactTriggered[1U] = (2ULL 
+                                                 | vlSelfRef.__VactTriggered[1U]);
+                vlSelfRef.__VactTriggered[1U] = (4ULL 
+                                                 | vlSelfRef.__VactTriggered[1U]);
+            }
+        }
+        Vt_order_clkinst___024root___eval_triggers_ext__act(vlSelf, vlCtx, vlSelfRef.__VnbaTriggered);
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_order_clkinst___024root___dump_triggers__act_ext(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_order_clkinst___024root___trigger_orInto__act_ext_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        __VactExecute = Vt_order_clkinst___024root___trigger_anySet__act_ext(vlSelfRef.__VactTriggered);
+        if (__VactExecute) {
+            {
+                // Inlined CFunc: _eval_act
+                if ((3ULL & vlSelfRef.__VactTriggered[2U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__0
+                        vlSelfRef.__Vdly__t__DOT__s2__DOT__runner 
+                            = vlSelfRef.t__DOT__s2__DOT__runner;
+                    }
+                }
+                if ((1ULL & vlSelfRef.__VactTriggered[1U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__1
+                        vlSelfRef.t__DOT__c3_count = 0U;
+                        vlSelfRef.t__DOT__c3__DOT__runner = 3U;
+                    }
+                }
+                if ((1ULL & vlSelfRef.__VactTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__2
+                        vlSelfRef.t__DOT__c1_count = 0U;
+                        vlSelfRef.t__DOT__s2_count = 0U;
+                        vlSelfRef.t__DOT__c1__DOT__runner = 3U;
+                        vlSelfRef.__Vdly__t__DOT__s2__DOT__runner = 3U;
+                    }
+                }
+                if ((2ULL & vlSelfRef.__VactTriggered[1U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__3
+                        if (VL_UNLIKELY(((0U < vlSelfRef.t__DOT__c3__DOT__runner)))) {
+                            vlSelfRef.t__DOT__c3_count 
+                                = ((IData)(1U) + vlSelfRef.t__DOT__c3_count);
+                            vlSelfRef.t__DOT__c3__DOT__runner 
+                                = vlSelfRef.t__DOT__c3__DOT__runnerm1;
+                            vlCtx.writef(0U, 2U, vlcu_msg_arg(vlSelfRef.t__DOT__c3_count), vlcu_msg_arg(vlSelfRef.t__DOT__c3__DOT__runnerm1));
+                        }
+                    }
+                }
+                if ((4ULL & vlSelfRef.__VactTriggered[1U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__4
+                        if (VL_UNLIKELY(((0U < vlSelfRef.t__DOT__c1__DOT__runner)))) {
+                            vlSelfRef.t__DOT__c1_count 
+                                = ((IData)(1U) + vlSelfRef.t__DOT__c1_count);
+                            vlSelfRef.t__DOT__c1__DOT__runner 
+                                = vlSelfRef.t__DOT__c1__DOT__runnerm1;
+                            vlCtx.writef(1U, 2U, vlcu_msg_arg(vlSelfRef.t__DOT__c1_count), vlcu_msg_arg(vlSelfRef.t__DOT__c1__DOT__runnerm1));
+                        }
+                    }
+                }
+                if ((2ULL & vlSelfRef.__VactTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _act_sequent__TOP__5
+                        if (VL_UNLIKELY(((0U < vlSelfRef.t__DOT__s2__DOT__runner)))) {
+                            vlSelfRef.t__DOT__s2_count 
+                                = ((IData)(1U) + vlSelfRef.t__DOT__s2_count);
+                            vlCtx.writef(2U, 2U, vlcu_msg_arg(vlSelfRef.t__DOT__s2_count), vlcu_msg_arg(vlSelfRef.t__DOT__s2__DOT__runnerm1));
+                            vlSelfRef.__Vdly__t__DOT__s2__DOT__runner 
+                                = vlSelfRef.t__DOT__s2__DOT__runnerm1;
+                        }
+                    }
+                }
+                if ((3ULL & vlSelfRef.__VactTriggered[1U])) {
+                    {
+                        // Inlined CFunc: _act_comb__TOP__0
+                        vlSelfRef.t__DOT__c3__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__c3__DOT__runner 
+                               - (IData)(1U));
+                    }
+                }
+                if (((4ULL & vlSelfRef.__VactTriggered[1U]) 
+                     | (1ULL & vlSelfRef.__VactTriggered[0U]))) {
+                    {
+                        // Inlined CFunc: _act_comb__TOP__1
+                        vlSelfRef.t__DOT__c1__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__c1__DOT__runner 
+                               - (IData)(1U));
+                    }
+                }
+            }
+        }
+        return (__VactExecute);
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___trigger_anySet__act_ext(const VlUnpacked<QData/*63:0*/, 3> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((3U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 2> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((2U > n));
+    }
+
+    VLCU_D static bool Vt_order_clkinst___024root___eval_phase__nba(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_order_clkinst___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((8ULL & vlSelfRef.__VnbaTriggered[1U])) {
+                    {
+                        // Inlined CFunc: _nba_sequent__TOP__0
+                        CData/*7:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc = 0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                            = vlSelfRef.t__DOT__cyc;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                            = (0x000000ffU & ((IData)(1U) 
+                                              + (IData)(vlSelfRef.t__DOT__cyc)));
+                        if ((0U == (IData)(vlSelfRef.t__DOT__cyc))) {
+                            vlSelfRef.t__DOT__c1_start = 0U;
+                        } else if ((1U == (IData)(vlSelfRef.t__DOT__cyc))) {
+                            vlSelfRef.t__DOT__c1_start = 1U;
+                        }
+                        if ((2U == (IData)(vlSelfRef.t__DOT__cyc))) {
+                            if (VL_UNLIKELY(((3U != vlSelfRef.t__DOT__c1_count)))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_order_clkinst.v", 59, "");
+                            }
+                            if (VL_UNLIKELY(((3U != vlSelfRef.t__DOT__s2_count)))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_order_clkinst.v", 60, "");
+                            }
+                            if (VL_UNLIKELY(((3U != vlSelfRef.t__DOT__c3_count)))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_order_clkinst.v", 61, "");
+                            }
+                        } else if (VL_UNLIKELY(((3U 
+                                                 == (IData)(vlSelfRef.t__DOT__cyc))))) {
+                            vlCtx.writef(3U, 0U);
+                            VL_FINISH_MT("/root/reference/test_regress/t/t_order_clkinst.v", 65, "");
+                        }
+                        vlSelfRef.t__DOT__cyc = __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                    }
+                }
+                if ((3ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _nba_sequent__TOP__1
+                        vlSelfRef.t__DOT__s2__DOT__runner 
+                            = vlSelfRef.__Vdly__t__DOT__s2__DOT__runner;
+                        vlSelfRef.t__DOT__s2__DOT__runnerm1 
+                            = (vlSelfRef.t__DOT__s2__DOT__runner 
+                               - (IData)(1U));
+                    }
+                }
+            }
+            Vt_order_clkinst___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___eval(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_order_clkinst___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_order_clkinst.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_order_clkinst___024root___dump_triggers__act_ext(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_order_clkinst.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_order_clkinst___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_order_clkinst___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_order_clkinst___024root___ctor_var_reset(Vt_order_clkinst___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->t__DOT__c1_start = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 6147790110263646937ull);
+        vlSelf->t__DOT__c1_count = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 16823110418178470999ull);
+        vlSelf->t__DOT__s2_count = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 8387070335457916555ull);
+        vlSelf->t__DOT__c3_count = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 14808706992695306613ull);
+        vlSelf->t__DOT__cyc = VL_SCOPED_RAND_RESET_I(8, __VscopeHash, 15508623621340971111ull);
+        vlSelf->t__DOT__c3__DOT__runnerm1 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 6930742258240378354ull);
+        vlSelf->t__DOT__c3__DOT__runner = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 16751812560827638532ull);
+        vlSelf->t__DOT__c1__DOT__runnerm1 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 4793436700657227419ull);
+        vlSelf->t__DOT__c1__DOT__runner = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 2741238353655842286ull);
+        vlSelf->t__DOT__s2__DOT__runnerm1 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 18029280412474555733ull);
+        vlSelf->t__DOT__s2__DOT__runner = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 16898828206911512006ull);
+        vlSelf->__Vdly__t__DOT__s2__DOT__runner = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VstlTriggered[__Vi0] = 0;
+        }
+        for (int __Vi0 = 0; __Vi0 < 3; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__t__DOT__c1_start__0 = 0;
+        vlSelf->__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0 = 0;
+        vlSelf->__Vtrigprevexpr_h83885254__0 = 0;
+        vlSelf->__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0 = 0;
+        vlSelf->__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0 = 0;
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        vlSelf->__VactDidInit = 0;
+        for (int __Vi0 = 0; __Vi0 < 2; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_order_clkinst___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_order_clkinst___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_order_clkinst___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_order_clkinst___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_order_clkinst___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_order_clkinst___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_order_clkinst__cuda::info() {
+    typedef Vt_order_clkinst__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"t__DOT__c1_start", "t.c1_start", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__c1_start},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__cyc},
+        {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
+        {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
+        {"__Vtrigprevexpr___TOP__t__DOT__c1_start__0", "__Vtrigprevexpr___TOP__t.c1_start__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__t__DOT__c1_start__0},
+        {"__Vtrigprevexpr_h83885254__0", "__Vtrigprevexpr_h83885254__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr_h83885254__0},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactDidInit", "__VactDidInit", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactDidInit},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__c1_count", "t.c1_count", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c1_count},
+        {"t__DOT__s2_count", "t.s2_count", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__s2_count},
+        {"t__DOT__c3_count", "t.c3_count", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c3_count},
+        {"t__DOT__c3__DOT__runnerm1", "t.c3.runnerm1", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c3__DOT__runnerm1},
+        {"t__DOT__c3__DOT__runner", "t.c3.runner", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c3__DOT__runner},
+        {"t__DOT__c1__DOT__runnerm1", "t.c1.runnerm1", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c1__DOT__runnerm1},
+        {"t__DOT__c1__DOT__runner", "t.c1.runner", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__c1__DOT__runner},
+        {"t__DOT__s2__DOT__runnerm1", "t.s2.runnerm1", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__s2__DOT__runnerm1},
+        {"t__DOT__s2__DOT__runner", "t.s2.runner", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__s2__DOT__runner},
+        {"__Vdly__t__DOT__s2__DOT__runner", "__Vdly__t.s2.runner", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___Vdly__t__DOT__s2__DOT__runner},
+        {"__Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0", "__Vtrigprevexpr___TOP__t.s2.runnerm1__0", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___Vtrigprevexpr___TOP__t__DOT__s2__DOT__runnerm1__0},
+        {"__Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0", "__Vtrigprevexpr___TOP__t.c3.runnerm1__0", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___Vtrigprevexpr___TOP__t__DOT__c3__DOT__runnerm1__0},
+        {"__Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0", "__Vtrigprevexpr___TOP__t.c1.runnerm1__0", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___Vtrigprevexpr___TOP__t__DOT__c1__DOT__runnerm1__0},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 3, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 2, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"TOP.t.c3 count=%d  runner =%x\n", "TOP.t.c1 count=%d  runner =%x\n", "TOP.t.s2 count=%d  runner<=%x\n", "*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 4, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 28, 0, 0x92fa048cdc30a64aULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_order_clkinst__cuda VLCU_TESTBENCHES);

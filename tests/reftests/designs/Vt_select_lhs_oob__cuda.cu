@@ -1,0 +1,2776 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+// 54 bytes of register-resident state: latency-bound, compile for full occupancy
+#ifndef VLCU_MIN_BLOCKS
+#define VLCU_MIN_BLOCKS 32
+#endif
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_select_lhs_oob"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_select_lhs_oob___024root final {
+    CData/*0:0*/ clk;
+    CData/*6:0*/ t__DOT__mem1d;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ t__DOT__cyc;
+    IData/*31:0*/ t__DOT__wi;
+    IData/*31:0*/ __VactIterCount;
+    VlUnpacked<CData/*6:0*/, 6> t__DOT__mem2d;
+    VlcuMdArray<VlcuLocalArray<CData/*6:0*/, 30>, 5, 6> t__DOT__mem3d;  // thread-local memory
+    VlcuSharedArray<IData/*31:0*/, 7> t__DOT__reg2d;  // run-time indexed: shared memory [index][lane]
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_select_lhs_oob__cuda final {
+    typedef Vt_select_lhs_oob___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 56,
+        OFF_t__DOT__mem1d = 57,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 58,
+        OFF___VactPhaseResult = 59,
+        OFF___VnbaPhaseResult = 60,
+        OFF_t__DOT__cyc = 16,
+        OFF_t__DOT__wi = 20,
+        OFF___VactIterCount = 24,
+        OFF_t__DOT__mem2d = 61,
+        OFF_t__DOT__mem3d = 67,
+        OFF_t__DOT__reg2d = 28,
+        OFF___VactTriggered = 0,
+        OFF___VnbaTriggered = 8,
+        kStateBytes = 104,  // S_persist
+        kTouchedReadBytes = 60,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 35,  // S_state_wr
+    };
+    struct Locals final {
+        CData/*6:0*/ t__DOT__mem3d[30];
+    };
+    struct Shared final {
+        IData/*31:0*/ t__DOT__reg2d[7][VLCU_BLOCK];
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+        s.t__DOT__mem3d.bind(l.t__DOT__mem3d);
+        s.t__DOT__reg2d.bind(sh.t__DOT__reg2d, threadIdx.x);
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.t__DOT__mem1d = st.ld<VlcuMem8>(OFF_t__DOT__mem1d, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.t__DOT__cyc = st.ld<IData>(OFF_t__DOT__cyc, i);
+        s.t__DOT__wi = st.ld<IData>(OFF_t__DOT__wi, i);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        for (uint32_t e = 0; e < 6; ++e) s.t__DOT__mem2d[e] = st.ldE<VlcuMem8>(OFF_t__DOT__mem2d, e, i);
+        for (uint32_t e = 0; e < 30; ++e) s.t__DOT__mem3d.flat()[e] = st.ldE<VlcuMem8>(OFF_t__DOT__mem3d, e, i);
+        for (uint32_t e = 0; e < 7; ++e) s.t__DOT__reg2d[e] = st.ldE<IData>(OFF_t__DOT__reg2d, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_t__DOT__mem1d, i, s.t__DOT__mem1d);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.st<IData>(OFF_t__DOT__wi, i, s.t__DOT__wi);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        for (uint32_t e = 0; e < 6; ++e) st.stE<VlcuMem8>(OFF_t__DOT__mem2d, e, i, s.t__DOT__mem2d[e]);
+        for (uint32_t e = 0; e < 30; ++e) st.stE<VlcuMem8>(OFF_t__DOT__mem3d, e, i, s.t__DOT__mem3d.flat()[e]);
+        for (uint32_t e = 0; e < 7; ++e) st.stE<IData>(OFF_t__DOT__reg2d, e, i, s.t__DOT__reg2d[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval_static(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_static__TOP
+            vlSelfRef.t__DOT__cyc = 0U;
+        }
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval_initial(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        Vt_select_lhs_oob___024root___eval_initial__TOP(vlSelf, vlCtx);
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval_initial__TOP(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        if (VL_UNLIKELY(((1U & (IData)(vlSelfRef.t__DOT__mem1d))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 30, "");
+        }
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (0x7eU & vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (2U | vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (0x7bU & vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (8U | vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (0x6fU & vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (0x20U | vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[0U][0U] = (0x3fU & vlSelfRef.t__DOT__mem3d[0U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (1U | vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (0x7dU & vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (4U | vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (0x77U & vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (0x10U | vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (0x5fU & vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[0U][1U] = (0x40U | vlSelfRef.t__DOT__mem3d[0U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (0x7eU & vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (2U | vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (0x7bU & vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (8U | vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (0x6fU & vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (0x20U | vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[0U][2U] = (0x3fU & vlSelfRef.t__DOT__mem3d[0U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (1U | vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (0x7dU & vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (4U | vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (0x77U & vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (0x10U | vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (0x5fU & vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[0U][3U] = (0x40U | vlSelfRef.t__DOT__mem3d[0U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (0x7eU & vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (2U | vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (0x7bU & vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (8U | vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (0x6fU & vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (0x20U | vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[0U][4U] = (0x3fU & vlSelfRef.t__DOT__mem3d[0U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (1U | vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (0x7dU & vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (4U | vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (0x77U & vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (0x10U | vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (0x5fU & vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[0U][5U] = (0x40U | vlSelfRef.t__DOT__mem3d[0U][5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (1U | vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (0x7dU & vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (4U | vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (0x77U & vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (0x10U | vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (0x5fU & vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[1U][0U] = (0x40U | vlSelfRef.t__DOT__mem3d[1U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (0x7eU & vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (2U | vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (0x7bU & vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (8U | vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (0x6fU & vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (0x20U | vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[1U][1U] = (0x3fU & vlSelfRef.t__DOT__mem3d[1U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (1U | vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (0x7dU & vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (4U | vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (0x77U & vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (0x10U | vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (0x5fU & vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[1U][2U] = (0x40U | vlSelfRef.t__DOT__mem3d[1U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (0x7eU & vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (2U | vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (0x7bU & vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (8U | vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (0x6fU & vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (0x20U | vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[1U][3U] = (0x3fU & vlSelfRef.t__DOT__mem3d[1U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (1U | vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (0x7dU & vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (4U | vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (0x77U & vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (0x10U | vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (0x5fU & vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[1U][4U] = (0x40U | vlSelfRef.t__DOT__mem3d[1U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (0x7eU & vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (2U | vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (0x7bU & vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (8U | vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (0x6fU & vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (0x20U | vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[1U][5U] = (0x3fU & vlSelfRef.t__DOT__mem3d[1U][5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (0x7eU & vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (2U | vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (0x7bU & vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (8U | vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (0x6fU & vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (0x20U | vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[2U][0U] = (0x3fU & vlSelfRef.t__DOT__mem3d[2U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (1U | vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (0x7dU & vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (4U | vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (0x77U & vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (0x10U | vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (0x5fU & vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[2U][1U] = (0x40U | vlSelfRef.t__DOT__mem3d[2U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (0x7eU & vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (2U | vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (0x7bU & vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (8U | vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (0x6fU & vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (0x20U | vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[2U][2U] = (0x3fU & vlSelfRef.t__DOT__mem3d[2U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (1U | vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (0x7dU & vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (4U | vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (0x77U & vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (0x10U | vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (0x5fU & vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[2U][3U] = (0x40U | vlSelfRef.t__DOT__mem3d[2U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (0x7eU & vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (2U | vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (0x7bU & vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (8U | vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (0x6fU & vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (0x20U | vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[2U][4U] = (0x3fU & vlSelfRef.t__DOT__mem3d[2U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (1U | vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (0x7dU & vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (4U | vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (0x77U & vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (0x10U | vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (0x5fU & vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[2U][5U] = (0x40U | vlSelfRef.t__DOT__mem3d[2U][5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (1U | vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (0x7dU & vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (4U | vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (0x77U & vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (0x10U | vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (0x5fU & vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[3U][0U] = (0x40U | vlSelfRef.t__DOT__mem3d[3U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (0x7eU & vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (2U | vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (0x7bU & vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (8U | vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (0x6fU & vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (0x20U | vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[3U][1U] = (0x3fU & vlSelfRef.t__DOT__mem3d[3U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (1U | vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (0x7dU & vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (4U | vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (0x77U & vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (0x10U | vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (0x5fU & vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[3U][2U] = (0x40U | vlSelfRef.t__DOT__mem3d[3U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (0x7eU & vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (2U | vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (0x7bU & vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (8U | vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (0x6fU & vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (0x20U | vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[3U][3U] = (0x3fU & vlSelfRef.t__DOT__mem3d[3U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (1U | vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (0x7dU & vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (4U | vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (0x77U & vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (0x10U | vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (0x5fU & vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[3U][4U] = (0x40U | vlSelfRef.t__DOT__mem3d[3U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (0x7eU & vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (2U | vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (0x7bU & vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (8U | vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (0x6fU & vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (0x20U | vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[3U][5U] = (0x3fU & vlSelfRef.t__DOT__mem3d[3U][5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (0x7eU & vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (2U | vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (0x7bU & vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (8U | vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (0x6fU & vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (0x20U | vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem3d[4U][0U] = (0x3fU & vlSelfRef.t__DOT__mem3d[4U][0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (1U | vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (0x7dU & vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (4U | vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (0x77U & vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (0x10U | vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (0x5fU & vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem3d[4U][1U] = (0x40U | vlSelfRef.t__DOT__mem3d[4U][1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (0x7eU & vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (2U | vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (0x7bU & vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (8U | vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (0x6fU & vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (0x20U | vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem3d[4U][2U] = (0x3fU & vlSelfRef.t__DOT__mem3d[4U][2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (1U | vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (0x7dU & vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (4U | vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (0x77U & vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (0x10U | vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (0x5fU & vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem3d[4U][3U] = (0x40U | vlSelfRef.t__DOT__mem3d[4U][3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (0x7eU & vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (2U | vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (0x7bU & vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (8U | vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (0x6fU & vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (0x20U | vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem3d[4U][4U] = (0x3fU & vlSelfRef.t__DOT__mem3d[4U][4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (1U | vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (0x7dU & vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (4U | vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (0x77U & vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (0x10U | vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (0x5fU & vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem3d[4U][5U] = (0x40U | vlSelfRef.t__DOT__mem3d[4U][5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7eU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (2U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x7bU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (8U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x6fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x20U | vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[0U] = (0x3fU & vlSelfRef.t__DOT__mem2d[0U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (1U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x7dU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (4U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x77U & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x10U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x5fU & vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[1U] = (0x40U | vlSelfRef.t__DOT__mem2d[1U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7eU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (2U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x7bU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (8U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x6fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x20U | vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[2U] = (0x3fU & vlSelfRef.t__DOT__mem2d[2U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (1U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x7dU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (4U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x77U & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x10U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x5fU & vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[3U] = (0x40U | vlSelfRef.t__DOT__mem2d[3U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7eU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (2U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x7bU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (8U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x6fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x20U | vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[4U] = (0x3fU & vlSelfRef.t__DOT__mem2d[4U]);
+        vlSelfRef.t__DOT__mem1d = (0x7eU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (1U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (2U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x7dU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x7bU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (4U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (8U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x77U & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x6fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x10U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x00000020U | (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x5fU & vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = (0x3fU & (IData)(vlSelfRef.t__DOT__mem1d));
+        vlSelfRef.t__DOT__mem2d[5U] = (0x40U | vlSelfRef.t__DOT__mem2d[5U]);
+        vlSelfRef.t__DOT__mem1d = 0x2aU;
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[0U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[0U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[0U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[0U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[0U][1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[0U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[0U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[0U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[0U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[0U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[0U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[0U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[0U][3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[0U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[0U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[0U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[0U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[0U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[0U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[0U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[0U][5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[0U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[0U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[0U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[0U][5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[1U][0U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[1U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][0U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[1U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][0U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[1U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][0U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[1U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][1U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[1U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][1U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[1U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][1U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[1U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[1U][2U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[1U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][2U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[1U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][2U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[1U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][2U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[1U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][3U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[1U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][3U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[1U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][3U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[1U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[1U][4U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[1U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][4U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[1U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][4U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[1U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][4U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[1U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][5U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[1U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][5U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[1U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[1U][5U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[1U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[2U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[2U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[2U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[2U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[2U][1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[2U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[2U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[2U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[2U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[2U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[2U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[2U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[2U][3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[2U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[2U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[2U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[2U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[2U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[2U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[2U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[2U][5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[2U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[2U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[2U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[2U][5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[3U][0U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[3U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][0U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[3U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][0U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[3U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][0U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[3U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][1U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[3U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][1U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[3U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][1U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[3U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[3U][2U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[3U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][2U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[3U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][2U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[3U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][2U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[3U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][3U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[3U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][3U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[3U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][3U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[3U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[3U][4U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[3U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][4U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[3U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][4U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[3U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][4U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[3U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][5U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[3U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][5U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[3U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[3U][5U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[3U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[4U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][0U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[4U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][0U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[4U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][0U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[4U][0U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[4U][1U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[4U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][1U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[4U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][1U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[4U][1U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][1U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[4U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][2U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[4U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][2U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[4U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][2U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[4U][2U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[4U][3U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[4U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][3U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[4U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][3U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[4U][3U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][3U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & vlSelfRef.t__DOT__mem3d[4U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][4U] 
+                                   >> 1U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((4U & vlSelfRef.t__DOT__mem3d[4U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][4U] 
+                                   >> 3U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000010U & vlSelfRef.t__DOT__mem3d[4U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][4U] 
+                                   >> 5U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem2d[4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000040U & vlSelfRef.t__DOT__mem3d[4U][4U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem2d[5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ vlSelfRef.t__DOT__mem3d[4U][5U]))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((2U & vlSelfRef.t__DOT__mem3d[4U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][5U] 
+                                   >> 2U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((8U & vlSelfRef.t__DOT__mem3d[4U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][5U] 
+                                   >> 4U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem2d[5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((0x00000020U & vlSelfRef.t__DOT__mem3d[4U][5U])))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem2d[5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 45, "");
+        }
+        if (VL_UNLIKELY(((1U & (~ (vlSelfRef.t__DOT__mem3d[4U][5U] 
+                                   >> 6U)))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 46, "");
+        }
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval_final(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval_settle(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static bool Vt_select_lhs_oob___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt_select_lhs_oob___024root___eval_phase__act(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_select_lhs_oob___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_select_lhs_oob___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt_select_lhs_oob___024root___eval_phase__nba(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_select_lhs_oob___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _nba_sequent__TOP__0
+                        IData/*31:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc = 0;
+                        IData/*31:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyVal__t__DOT__reg2d__v0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyVal__t__DOT__reg2d__v0 = 0;
+                        CData/*2:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyDim0__t__DOT__reg2d__v0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyDim0__t__DOT__reg2d__v0 = 0;
+                        CData/*0:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlySet__t__DOT__reg2d__v0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlySet__t__DOT__reg2d__v0 = 0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                            = vlSelfRef.t__DOT__cyc;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlySet__t__DOT__reg2d__v0 = 0U;
+                        if ((6U >= (7U & vlSelfRef.t__DOT__wi))) {
+                            __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyVal__t__DOT__reg2d__v0 
+                                = vlSelfRef.t__DOT__cyc;
+                            __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyDim0__t__DOT__reg2d__v0 
+                                = (7U & vlSelfRef.t__DOT__wi);
+                            __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlySet__t__DOT__reg2d__v0 = 1U;
+                        }
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                            = ((IData)(1U) + vlSelfRef.t__DOT__cyc);
+                        if (VL_GTS_III(32, 0x0000000aU, vlSelfRef.t__DOT__cyc)) {
+                            vlSelfRef.t__DOT__wi = 0U;
+                        } else if ((0x0000000aU == vlSelfRef.t__DOT__cyc)) {
+                            vlSelfRef.t__DOT__wi = 1U;
+                        } else if ((0x0000000bU == vlSelfRef.t__DOT__cyc)) {
+                            if (VL_UNLIKELY(((0x0000000aU 
+                                              != vlSelfRef.t__DOT__reg2d[0U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 69, "");
+                            }
+                            vlSelfRef.t__DOT__wi = 6U;
+                        } else if ((0x0000000cU == vlSelfRef.t__DOT__cyc)) {
+                            if (VL_UNLIKELY(((0x0000000aU 
+                                              != vlSelfRef.t__DOT__reg2d[0U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 73, "");
+                            }
+                            if (VL_UNLIKELY(((0x0000000bU 
+                                              != vlSelfRef.t__DOT__reg2d[1U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 74, "");
+                            }
+                            vlSelfRef.t__DOT__wi = 7U;
+                        } else if ((0x0000000dU == vlSelfRef.t__DOT__cyc)) {
+                            if (VL_UNLIKELY(((0x0000000aU 
+                                              != vlSelfRef.t__DOT__reg2d[0U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 78, "");
+                            }
+                            if (VL_UNLIKELY(((0x0000000bU 
+                                              != vlSelfRef.t__DOT__reg2d[1U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 79, "");
+                            }
+                            if (VL_UNLIKELY(((0x0000000cU 
+                                              != vlSelfRef.t__DOT__reg2d[6U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 80, "");
+                            }
+                        } else if ((0x0000000eU == vlSelfRef.t__DOT__cyc)) {
+                            if (VL_UNLIKELY(((0x0000000aU 
+                                              != vlSelfRef.t__DOT__reg2d[0U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 83, "");
+                            }
+                            if (VL_UNLIKELY(((0x0000000bU 
+                                              != vlSelfRef.t__DOT__reg2d[1U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 84, "");
+                            }
+                            if (VL_UNLIKELY(((0x0000000cU 
+                                              != vlSelfRef.t__DOT__reg2d[6U])))) {
+                                VL_STOP_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 85, "");
+                            }
+                        } else if (VL_UNLIKELY(((0x00000063U 
+                                                 == vlSelfRef.t__DOT__cyc)))) {
+                            vlCtx.writef(0U, 0U);
+                            VL_FINISH_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 89, "");
+                        }
+                        vlSelfRef.t__DOT__cyc = __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                        if (__Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlySet__t__DOT__reg2d__v0) {
+                            vlSelfRef.t__DOT__reg2d[__Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyDim0__t__DOT__reg2d__v0] 
+                                = __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___VdlyVal__t__DOT__reg2d__v0;
+                        }
+                    }
+                }
+            }
+            Vt_select_lhs_oob___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___eval(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_select_lhs_oob___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_select_lhs_oob___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_select_lhs_oob.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_select_lhs_oob___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_select_lhs_oob___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_select_lhs_oob___024root___ctor_var_reset(Vt_select_lhs_oob___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->t__DOT__mem1d = VL_SCOPED_RAND_RESET_I(7, __VscopeHash, 12929453845693170549ull);
+        for (int __Vi0 = 0; __Vi0 < 6; ++__Vi0) {
+            vlSelf->t__DOT__mem2d[__Vi0] = VL_SCOPED_RAND_RESET_I(7, __VscopeHash, 9414533067004853680ull);
+        }
+        for (int __Vi0 = 0; __Vi0 < 5; ++__Vi0) {
+            for (int __Vi1 = 0; __Vi1 < 6; ++__Vi1) {
+                vlSelf->t__DOT__mem3d[__Vi0][__Vi1] = VL_SCOPED_RAND_RESET_I(7, __VscopeHash, 14348055384378193688ull);
+            }
+        }
+        vlSelf->t__DOT__wi = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 17740001305571154683ull);
+        for (int __Vi0 = 0; __Vi0 < 7; ++__Vi0) {
+            vlSelf->t__DOT__reg2d[__Vi0] = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 17266674983452652680ull);
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_select_lhs_oob___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_lhs_oob___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_lhs_oob___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_lhs_oob___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_lhs_oob___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_lhs_oob___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_select_lhs_oob__cuda::info() {
+    typedef Vt_select_lhs_oob__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"t__DOT__mem1d", "t.mem1d", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF_t__DOT__mem1d},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__cyc},
+        {"t__DOT__wi", "t.wi", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__wi},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"t__DOT__mem2d", "t.mem2d", VLCU_MEMBER_STATE, 1, 0, 6, 7, 6, 0, T::OFF_t__DOT__mem2d},
+        {"t__DOT__mem3d", "t.mem3d", VLCU_MEMBER_STATE, 1, 0, 30, 7, 6, 0, T::OFF_t__DOT__mem3d},
+        {"t__DOT__reg2d", "t.reg2d", VLCU_MEMBER_STATE, 4, 0, 7, 32, 31, 0, T::OFF_t__DOT__reg2d},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 1, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 13, 0, 0xf9c805d031881fc2ULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_select_lhs_oob__cuda VLCU_TESTBENCHES);

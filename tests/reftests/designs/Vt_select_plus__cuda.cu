@@ -1,0 +1,870 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_select_plus"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_select_plus___024root final {
+    CData/*0:0*/ clk;
+    CData/*6:0*/ t__DOT__bitn;
+    CData/*3:0*/ t__DOT__nibblep;
+    CData/*3:0*/ t__DOT__nibblem;
+    CData/*7:0*/ t__DOT__cyc;
+    CData/*0:0*/ __VstlFirstIteration;
+    CData/*0:0*/ __VstlPhaseResult;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    VlWide<3>/*79:0*/ t__DOT__from;
+    VlWide<3>/*79:0*/ t__DOT__to;
+    IData/*31:0*/ __VactIterCount;
+    VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_select_plus__cuda final {
+    typedef Vt_select_plus___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 52,
+        OFF_t__DOT__bitn = 53,
+        OFF_t__DOT__nibblep = 54,
+        OFF_t__DOT__nibblem = 55,
+        OFF_t__DOT__cyc = 56,
+        OFF___VstlFirstIteration = 57,
+        OFF___VstlPhaseResult = 58,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 59,
+        OFF___VactPhaseResult = 60,
+        OFF___VnbaPhaseResult = 61,
+        OFF_t__DOT__from = 24,
+        OFF_t__DOT__to = 36,
+        OFF___VactIterCount = 48,
+        OFF___VstlTriggered = 0,
+        OFF___VactTriggered = 8,
+        OFF___VnbaTriggered = 16,
+        kStateBytes = 64,  // S_persist
+        kTouchedReadBytes = 52,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 51,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.t__DOT__bitn = st.ld<VlcuMem8>(OFF_t__DOT__bitn, i);
+        s.t__DOT__nibblep = st.ld<VlcuMem8>(OFF_t__DOT__nibblep, i);
+        s.t__DOT__nibblem = st.ld<VlcuMem8>(OFF_t__DOT__nibblem, i);
+        s.t__DOT__cyc = st.ld<VlcuMem8>(OFF_t__DOT__cyc, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        st.ldW(OFF_t__DOT__from, i, s.t__DOT__from);
+        st.ldW(OFF_t__DOT__to, i, s.t__DOT__to);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF_t__DOT__bitn, i, s.t__DOT__bitn);
+        st.st<VlcuMem8>(OFF_t__DOT__nibblep, i, s.t__DOT__nibblep);
+        st.st<VlcuMem8>(OFF_t__DOT__nibblem, i, s.t__DOT__nibblem);
+        st.st<VlcuMem8>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.stW(OFF_t__DOT__from, i, s.t__DOT__from);
+        st.stW(OFF_t__DOT__to, i, s.t__DOT__to);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_select_plus___024root___eval_static(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_select_plus___024root___eval_initial(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_initial__TOP
+            IData/*23:0*/ __Vinline_0__eval_initial__TOP_t__DOT__a;
+            __Vinline_0__eval_initial__TOP_t__DOT__a = 0;
+            vlSelfRef.t__DOT__cyc = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__a = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__a 
+                = (0x00e00000U | __Vinline_0__eval_initial__TOP_t__DOT__a);
+            if (VL_UNLIKELY(((0x00e00000U != __Vinline_0__eval_initial__TOP_t__DOT__a)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 84, "");
+            }
+            __Vinline_0__eval_initial__TOP_t__DOT__a = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__a 
+                = (0x00070000U | __Vinline_0__eval_initial__TOP_t__DOT__a);
+            if (VL_UNLIKELY(((0x00070000U != __Vinline_0__eval_initial__TOP_t__DOT__a)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 89, "");
+            }
+        }
+    }
+
+    VLCU_D static void Vt_select_plus___024root___eval_final(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_select_plus___024root___eval_settle(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VstlIterCount;
+        // Body
+        __VstlIterCount = 0U;
+        vlSelfRef.__VstlFirstIteration = 1U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VstlIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_select_plus___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_select_plus.v", 7, "", "DIDNOTCONVERGE: Settle region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VstlIterCount = ((IData)(1U) + __VstlIterCount);
+            vlSelfRef.__VstlPhaseResult = Vt_select_plus___024root___eval_phase__stl(vlSelf, vlCtx);
+            vlSelfRef.__VstlFirstIteration = 0U;
+        } while (vlSelfRef.__VstlPhaseResult);
+    }
+
+    VLCU_D static bool Vt_select_plus___024root___trigger_anySet__stl(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static bool Vt_select_plus___024root___eval_phase__stl(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VstlExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__stl
+            vlSelfRef.__VstlTriggered[0U] = ((0xfffffffffffffffeULL 
+                                              & vlSelfRef.__VstlTriggered[0U]) 
+                                             | (IData)((IData)(vlSelfRef.__VstlFirstIteration)));
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_select_plus___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+        }
+#endif
+        __VstlExecute = Vt_select_plus___024root___trigger_anySet__stl(vlSelfRef.__VstlTriggered);
+        if (__VstlExecute) {
+            {
+                // Inlined CFunc: _eval_stl
+                if ((1ULL & vlSelfRef.__VstlTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _stl_sequent__TOP__0
+                        vlSelfRef.t__DOT__nibblep = 
+                            ((0x4fU >= (0x0000007fU 
+                                        & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                           - (IData)(4U))))
+                              ? (0x0000000fU & (((0U 
+                                                  == 
+                                                  (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(4U))))
+                                                  ? 0U
+                                                  : 
+                                                 (vlSelfRef.t__DOT__from
+                                                  [
+                                                  (((IData)(3U) 
+                                                    + 
+                                                    (0x0000007fU 
+                                                     & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                        - (IData)(4U)))) 
+                                                   >> 5U)] 
+                                                  << 
+                                                  ((IData)(0x00000020U) 
+                                                   - 
+                                                   (0x0000001fU 
+                                                    & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                       - (IData)(4U)))))) 
+                                                | (vlSelfRef.t__DOT__from
+                                                   [
+                                                   (3U 
+                                                    & (((IData)(vlSelfRef.t__DOT__bitn) 
+                                                        - (IData)(4U)) 
+                                                       >> 5U))] 
+                                                   >> 
+                                                   (0x0000001fU 
+                                                    & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                       - (IData)(4U))))))
+                              : 0U);
+                        vlSelfRef.t__DOT__nibblem = 
+                            ((0x4fU >= (0x0000007fU 
+                                        & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                           - (IData)(7U))))
+                              ? (0x0000000fU & (((0U 
+                                                  == 
+                                                  (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(7U))))
+                                                  ? 0U
+                                                  : 
+                                                 (vlSelfRef.t__DOT__from
+                                                  [
+                                                  (((IData)(3U) 
+                                                    + 
+                                                    (0x0000007fU 
+                                                     & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                        - (IData)(7U)))) 
+                                                   >> 5U)] 
+                                                  << 
+                                                  ((IData)(0x00000020U) 
+                                                   - 
+                                                   (0x0000001fU 
+                                                    & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                       - (IData)(7U)))))) 
+                                                | (vlSelfRef.t__DOT__from
+                                                   [
+                                                   (3U 
+                                                    & (((IData)(vlSelfRef.t__DOT__bitn) 
+                                                        - (IData)(7U)) 
+                                                       >> 5U))] 
+                                                   >> 
+                                                   (0x0000001fU 
+                                                    & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                       - (IData)(7U))))))
+                              : 0U);
+                        vlSelfRef.t__DOT__to[0U] = vlSelfRef.t__DOT__from[0U];
+                        vlSelfRef.t__DOT__to[1U] = vlSelfRef.t__DOT__from[1U];
+                        vlSelfRef.t__DOT__to[2U] = vlSelfRef.t__DOT__from[2U];
+                        if ((0x4fU >= (0x0000007fU 
+                                       & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                          - (IData)(4U))))) {
+                            VL_ASSIGNSEL_WI(80, 4, 
+                                            (0x0000007fU 
+                                             & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                - (IData)(4U))), vlSelfRef.t__DOT__to, 
+                                            (0x0000000fU 
+                                             & (IData)(vlSelfRef.t__DOT__cyc)));
+                        }
+                        if ((0x4fU >= (0x0000007fU 
+                                       & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                          - (IData)(7U))))) {
+                            VL_ASSIGNSEL_WI(80, 4, 
+                                            (0x0000007fU 
+                                             & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                - (IData)(7U))), vlSelfRef.t__DOT__to, 
+                                            (0x0000000fU 
+                                             & (IData)(vlSelfRef.t__DOT__cyc)));
+                        }
+                    }
+                }
+            }
+        }
+        return (__VstlExecute);
+    }
+
+    VLCU_D static bool Vt_select_plus___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_select_plus___024root___nba_sequent__TOP__0(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*7:0*/ __Vdly__t__DOT__cyc;
+        __Vdly__t__DOT__cyc = 0;
+        VlWide<3>/*79:0*/ __Vdly__t__DOT__from;
+        VL_ZERO_W(80, __Vdly__t__DOT__from);
+        // Body
+        __Vdly__t__DOT__cyc = vlSelfRef.t__DOT__cyc;
+        __Vdly__t__DOT__from[0U] = vlSelfRef.t__DOT__from[0U];
+        __Vdly__t__DOT__from[1U] = vlSelfRef.t__DOT__from[1U];
+        __Vdly__t__DOT__from[2U] = vlSelfRef.t__DOT__from[2U];
+        __Vdly__t__DOT__cyc = (0x000000ffU & ((IData)(1U) 
+                                              + (IData)(vlSelfRef.t__DOT__cyc)));
+        if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                      >> 7U)))) {
+            if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                          >> 6U)))) {
+                if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                              >> 5U)))) {
+                    if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                                  >> 4U)))) {
+                        if ((8U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                            if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                                          >> 2U)))) {
+                                if ((1U & (~ ((IData)(vlSelfRef.t__DOT__cyc) 
+                                              >> 1U)))) {
+                                    if (VL_UNLIKELY((
+                                                     (1U 
+                                                      & (IData)(vlSelfRef.t__DOT__cyc))))) {
+                                        vlCtx.writef(0U, 0U);
+                                        VL_FINISH_MT("/root/reference/test_regress/t/t_select_plus.v", 44, "");
+                                    } else {
+                                        __Vdly__t__DOT__from[0U] = 0xcc5b3111U;
+                                        __Vdly__t__DOT__from[1U] = 0xde23a8f5U;
+                                        __Vdly__t__DOT__from[2U] = 0x00004b9aU;
+                                        vlSelfRef.t__DOT__bitn = 0x7fU;
+                                    }
+                                }
+                            }
+                        } else if ((4U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                            if ((2U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                                if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                                    __Vdly__t__DOT__from[0U] = 0x5859fe16U;
+                                    __Vdly__t__DOT__from[1U] = 0x5da3d46bU;
+                                    __Vdly__t__DOT__from[2U] = 0x00003830U;
+                                    vlSelfRef.t__DOT__bitn = 0x43U;
+                                } else {
+                                    __Vdly__t__DOT__from[0U] = 0x5a1f3252U;
+                                    __Vdly__t__DOT__from[1U] = 0x8c5d3d28U;
+                                    __Vdly__t__DOT__from[2U] = 0x00009011U;
+                                    vlSelfRef.t__DOT__bitn = 0x51U;
+                                }
+                            } else if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                                __Vdly__t__DOT__from[0U] = 0x244f84b5U;
+                                __Vdly__t__DOT__from[1U] = 0x6077bf28U;
+                                __Vdly__t__DOT__from[2U] = 0x0000d6e3U;
+                                vlSelfRef.t__DOT__bitn = 6U;
+                            } else {
+                                __Vdly__t__DOT__from[0U] = 0x331370ecU;
+                                __Vdly__t__DOT__from[1U] = 0xfeca3820U;
+                                __Vdly__t__DOT__from[2U] = 0x0000c761U;
+                                vlSelfRef.t__DOT__bitn = 0x53U;
+                            }
+                        } else if ((2U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                            if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                                __Vdly__t__DOT__from[0U] = 0x7614ce3fU;
+                                __Vdly__t__DOT__from[1U] = 0x35f0a775U;
+                                __Vdly__t__DOT__from[2U] = 0x0000c906U;
+                                vlSelfRef.t__DOT__bitn = 0x4fU;
+                            } else {
+                                __Vdly__t__DOT__from[0U] = 0x401e210dU;
+                                __Vdly__t__DOT__from[1U] = 0xc5f34168U;
+                                __Vdly__t__DOT__from[2U] = 0x00003f99U;
+                                vlSelfRef.t__DOT__bitn = 4U;
+                            }
+                        } else if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                            __Vdly__t__DOT__from[0U] = 0xca5dc448U;
+                            __Vdly__t__DOT__from[1U] = 0xce326b11U;
+                            __Vdly__t__DOT__from[2U] = 0x0000efddU;
+                            vlSelfRef.t__DOT__bitn = 8U;
+                        } else {
+                            __Vdly__t__DOT__from[0U] = 0xe48f67daU;
+                            __Vdly__t__DOT__from[1U] = 0x9d779b67U;
+                            __Vdly__t__DOT__from[2U] = 0x00007beaU;
+                            vlSelfRef.t__DOT__bitn = 7U;
+                        }
+                    }
+                }
+            }
+        }
+        if (VL_UNLIKELY(((0x00000080U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+        } else if (VL_UNLIKELY(((0x00000040U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+        } else if (VL_UNLIKELY(((0x00000020U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+        } else if (VL_UNLIKELY(((0x00000010U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+            VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+        } else if ((8U & (IData)(vlSelfRef.t__DOT__cyc))) {
+            if (VL_UNLIKELY(((4U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+            } else if (VL_UNLIKELY(((2U & (IData)(vlSelfRef.t__DOT__cyc))))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 59, "");
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 72, "");
+            } else {
+                if ((1U & (~ (IData)(vlSelfRef.t__DOT__cyc)))) {
+                    if (VL_UNLIKELY(((0U != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 57, "");
+                    }
+                    if (VL_UNLIKELY(((5U != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 57, "");
+                    }
+                }
+                if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                    if (VL_UNLIKELY(((0U != (((0xfffffff0U 
+                                               & (vlSelfRef.t__DOT__to[0U] 
+                                                  ^ vlSelfRef.t__DOT__from[0U])) 
+                                              | (vlSelfRef.t__DOT__to[1U] 
+                                                 ^ vlSelfRef.t__DOT__from[1U])) 
+                                             | (0x0000ffffU 
+                                                & (vlSelfRef.t__DOT__to[2U] 
+                                                   ^ vlSelfRef.t__DOT__from[2U]))))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 71, "");
+                    }
+                } else if (VL_UNLIKELY(((0U != (((vlSelfRef.t__DOT__to[0U] 
+                                                  ^ vlSelfRef.t__DOT__from[0U]) 
+                                                 | (0xd0000000U 
+                                                    ^ 
+                                                    (vlSelfRef.t__DOT__to[1U] 
+                                                     ^ vlSelfRef.t__DOT__from[1U]))) 
+                                                | (4U 
+                                                   ^ 
+                                                   (vlSelfRef.t__DOT__to[2U] 
+                                                    ^ vlSelfRef.t__DOT__from[2U]))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 70, "");
+                }
+            }
+        } else if ((4U & (IData)(vlSelfRef.t__DOT__cyc))) {
+            if ((2U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                    if (VL_UNLIKELY(((4U != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 56, "");
+                    }
+                    if (VL_UNLIKELY(((0U != (((0xfffffff0U 
+                                               & (vlSelfRef.t__DOT__to[0U] 
+                                                  ^ vlSelfRef.t__DOT__from[0U])) 
+                                              | (vlSelfRef.t__DOT__to[1U] 
+                                                 ^ vlSelfRef.t__DOT__from[1U])) 
+                                             | (0x00004c00U 
+                                                ^ (0x0000ffffU 
+                                                   & (vlSelfRef.t__DOT__to[2U] 
+                                                      ^ vlSelfRef.t__DOT__from[2U])))))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 69, "");
+                    }
+                } else {
+                    if (VL_UNLIKELY(((0x0dU != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 55, "");
+                    }
+                    if (VL_UNLIKELY(((0U != (((0x00000020U 
+                                               ^ (0xfffffff0U 
+                                                  & (vlSelfRef.t__DOT__to[0U] 
+                                                     ^ vlSelfRef.t__DOT__from[0U]))) 
+                                              | (vlSelfRef.t__DOT__to[1U] 
+                                                 ^ vlSelfRef.t__DOT__from[1U])) 
+                                             | (0x0000ffffU 
+                                                & (vlSelfRef.t__DOT__to[2U] 
+                                                   ^ vlSelfRef.t__DOT__from[2U]))))))) {
+                        VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 68, "");
+                    }
+                }
+            } else if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                if (VL_UNLIKELY(((0x0cU != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 54, "");
+                }
+                if (VL_UNLIKELY(((0U != (((0xfffffff0U 
+                                           & (vlSelfRef.t__DOT__to[0U] 
+                                              ^ vlSelfRef.t__DOT__from[0U])) 
+                                          | (vlSelfRef.t__DOT__to[1U] 
+                                             ^ vlSelfRef.t__DOT__from[1U])) 
+                                         | (0x00009000U 
+                                            ^ (0x0000ffffU 
+                                               & (vlSelfRef.t__DOT__to[2U] 
+                                                  ^ vlSelfRef.t__DOT__from[2U])))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 67, "");
+                }
+            } else {
+                if (VL_UNLIKELY(((9U != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 53, "");
+                }
+                if (VL_UNLIKELY(((9U != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 53, "");
+                }
+                if (VL_UNLIKELY(((0U != (((vlSelfRef.t__DOT__to[0U] 
+                                           ^ vlSelfRef.t__DOT__from[0U]) 
+                                          | (vlSelfRef.t__DOT__to[1U] 
+                                             ^ vlSelfRef.t__DOT__from[1U])) 
+                                         | (0x00006d00U 
+                                            ^ (vlSelfRef.t__DOT__to[2U] 
+                                               ^ vlSelfRef.t__DOT__from[2U]))))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 66, "");
+                }
+            }
+        } else if ((2U & (IData)(vlSelfRef.t__DOT__cyc))) {
+            if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+                if (VL_UNLIKELY(((0x0dU != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 52, "");
+                }
+                if (VL_UNLIKELY(((0U != (((0x0000000eU 
+                                           ^ (vlSelfRef.t__DOT__to[0U] 
+                                              ^ vlSelfRef.t__DOT__from[0U])) 
+                                          | (vlSelfRef.t__DOT__to[1U] 
+                                             ^ vlSelfRef.t__DOT__from[1U])) 
+                                         | (vlSelfRef.t__DOT__to[2U] 
+                                            ^ vlSelfRef.t__DOT__from[2U])))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 65, "");
+                }
+            } else {
+                if (VL_UNLIKELY(((4U != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 51, "");
+                }
+                if (VL_UNLIKELY(((4U != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 51, "");
+                }
+                if (VL_UNLIKELY(((0U != (((0x0000006cU 
+                                           ^ (vlSelfRef.t__DOT__to[0U] 
+                                              ^ vlSelfRef.t__DOT__from[0U])) 
+                                          | (vlSelfRef.t__DOT__to[1U] 
+                                             ^ vlSelfRef.t__DOT__from[1U])) 
+                                         | (vlSelfRef.t__DOT__to[2U] 
+                                            ^ vlSelfRef.t__DOT__from[2U])))))) {
+                    VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 64, "");
+                }
+            }
+        } else if ((1U & (IData)(vlSelfRef.t__DOT__cyc))) {
+            if (VL_UNLIKELY(((0x0bU != (IData)(vlSelfRef.t__DOT__nibblep))))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 50, "");
+            }
+            if (VL_UNLIKELY(((0x0aU != (IData)(vlSelfRef.t__DOT__nibblem))))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 50, "");
+            }
+            if (VL_UNLIKELY(((0U != (((0x0000005bU 
+                                       ^ (vlSelfRef.t__DOT__to[0U] 
+                                          ^ vlSelfRef.t__DOT__from[0U])) 
+                                      | (vlSelfRef.t__DOT__to[1U] 
+                                         ^ vlSelfRef.t__DOT__from[1U])) 
+                                     | (vlSelfRef.t__DOT__to[2U] 
+                                        ^ vlSelfRef.t__DOT__from[2U])))))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_select_plus.v", 63, "");
+            }
+        }
+        vlSelfRef.t__DOT__cyc = __Vdly__t__DOT__cyc;
+        vlSelfRef.t__DOT__from[0U] = __Vdly__t__DOT__from[0U];
+        vlSelfRef.t__DOT__from[1U] = __Vdly__t__DOT__from[1U];
+        vlSelfRef.t__DOT__from[2U] = __Vdly__t__DOT__from[2U];
+        vlSelfRef.t__DOT__nibblep = ((0x4fU >= (0x0000007fU 
+                                                & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                   - (IData)(4U))))
+                                      ? (0x0000000fU 
+                                         & (((0U == 
+                                              (0x0000001fU 
+                                               & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                  - (IData)(4U))))
+                                              ? 0U : 
+                                             (vlSelfRef.t__DOT__from
+                                              [(((IData)(3U) 
+                                                 + 
+                                                 (0x0000007fU 
+                                                  & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                     - (IData)(4U)))) 
+                                                >> 5U)] 
+                                              << ((IData)(0x00000020U) 
+                                                  - 
+                                                  (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(4U)))))) 
+                                            | (vlSelfRef.t__DOT__from
+                                               [(3U 
+                                                 & (((IData)(vlSelfRef.t__DOT__bitn) 
+                                                     - (IData)(4U)) 
+                                                    >> 5U))] 
+                                               >> (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(4U))))))
+                                      : 0U);
+        vlSelfRef.t__DOT__nibblem = ((0x4fU >= (0x0000007fU 
+                                                & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                   - (IData)(7U))))
+                                      ? (0x0000000fU 
+                                         & (((0U == 
+                                              (0x0000001fU 
+                                               & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                  - (IData)(7U))))
+                                              ? 0U : 
+                                             (vlSelfRef.t__DOT__from
+                                              [(((IData)(3U) 
+                                                 + 
+                                                 (0x0000007fU 
+                                                  & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                     - (IData)(7U)))) 
+                                                >> 5U)] 
+                                              << ((IData)(0x00000020U) 
+                                                  - 
+                                                  (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(7U)))))) 
+                                            | (vlSelfRef.t__DOT__from
+                                               [(3U 
+                                                 & (((IData)(vlSelfRef.t__DOT__bitn) 
+                                                     - (IData)(7U)) 
+                                                    >> 5U))] 
+                                               >> (0x0000001fU 
+                                                   & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                      - (IData)(7U))))))
+                                      : 0U);
+        vlSelfRef.t__DOT__to[0U] = vlSelfRef.t__DOT__from[0U];
+        vlSelfRef.t__DOT__to[1U] = vlSelfRef.t__DOT__from[1U];
+        vlSelfRef.t__DOT__to[2U] = vlSelfRef.t__DOT__from[2U];
+        if ((0x4fU >= (0x0000007fU & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                      - (IData)(4U))))) {
+            VL_ASSIGNSEL_WI(80, 4, (0x0000007fU & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                   - (IData)(4U))), vlSelfRef.t__DOT__to, 
+                            (0x0000000fU & (IData)(vlSelfRef.t__DOT__cyc)));
+        }
+        if ((0x4fU >= (0x0000007fU & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                      - (IData)(7U))))) {
+            VL_ASSIGNSEL_WI(80, 4, (0x0000007fU & ((IData)(vlSelfRef.t__DOT__bitn) 
+                                                   - (IData)(7U))), vlSelfRef.t__DOT__to, 
+                            (0x0000000fU & (IData)(vlSelfRef.t__DOT__cyc)));
+        }
+    }
+
+    VLCU_D static void Vt_select_plus___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt_select_plus___024root___eval_phase__act(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_select_plus___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_select_plus___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt_select_plus___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt_select_plus___024root___eval_phase__nba(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_select_plus___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    Vt_select_plus___024root___nba_sequent__TOP__0(vlSelf, vlCtx);
+                }
+            }
+            Vt_select_plus___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_select_plus___024root___eval(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_select_plus___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_select_plus.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_select_plus___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_select_plus.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_select_plus___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_select_plus___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_select_plus___024root___ctor_var_reset(Vt_select_plus___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        VL_SCOPED_RAND_RESET_W(80, vlSelf->t__DOT__from, __VscopeHash, 13099058492926843938ull);
+        VL_SCOPED_RAND_RESET_W(80, vlSelf->t__DOT__to, __VscopeHash, 6559523519978108007ull);
+        vlSelf->t__DOT__bitn = VL_SCOPED_RAND_RESET_I(7, __VscopeHash, 11424030018270989649ull);
+        vlSelf->t__DOT__nibblep = VL_SCOPED_RAND_RESET_I(4, __VscopeHash, 913346655299895417ull);
+        vlSelf->t__DOT__nibblem = VL_SCOPED_RAND_RESET_I(4, __VscopeHash, 12319316353875279312ull);
+        vlSelf->t__DOT__cyc = VL_SCOPED_RAND_RESET_I(8, __VscopeHash, 15508623621340971111ull);
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VstlTriggered[__Vi0] = 0;
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_select_plus___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_plus___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_plus___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_plus___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_plus___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_select_plus___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_select_plus__cuda::info() {
+    typedef Vt_select_plus__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"t__DOT__bitn", "t.bitn", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF_t__DOT__bitn},
+        {"t__DOT__nibblep", "t.nibblep", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__nibblep},
+        {"t__DOT__nibblem", "t.nibblem", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__nibblem},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__cyc},
+        {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
+        {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__from", "t.from", VLCU_MEMBER_STATE, 4, 0, 3, 80, 83, 4, T::OFF_t__DOT__from},
+        {"t__DOT__to", "t.to", VLCU_MEMBER_STATE, 4, 0, 3, 80, 83, 4, T::OFF_t__DOT__to},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 1, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 16, 0, 0xa20cfb4587de79c2ULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_select_plus__cuda VLCU_TESTBENCHES);

@@ -364,7 +364,7 @@ class Model:
 
     def message_format(self, msg_id):
         s = lib.vlcu_message_format(self.h, msg_id)
-        return s.decode() if s else None
+        return s.decode() if s is not None else None
 
     def format_message(self, msg):
         """Host-side formatting of a logged $display/$write (subset: %%, %0t/%t, %d, %x, %b)."""
