@@ -755,6 +755,107 @@ class Parser final {
         if (acceptPunct("=")) varp->valuep(parseExpr());
     }
 
+    // function_declaration / task_declaration (verilog.y:4637-4660, 4702-4749, 4788-4830):
+    // [automatic] funcId tfGuts: ANSI or Verilog-1995 ports, block item declarations, statements
+    AstNode* parseFTask() {
+        const Token kw = m_lex.next();
+        const bool isFunc = kw.text == "function";
+        VLifetime lifetime = VLifetime::NONE;
+        if (m_lex.peek().kind == Tok::ID && m_lex.peek().text == "automatic") {
+            m_lex.next();
+            lifetime = VLifetime::AUTOMATIC_EXPLICIT;
+        } else if (m_lex.peek().kind == Tok::ID && m_lex.peek().text == "static") {
+            m_lex.next();
+            lifetime = VLifetime::STATIC_EXPLICIT;
+        }
+        AstNodeDType* fvarp = nullptr;
+        if (isFunc) {  // funcId: function_data_type_or_implicit
+            if (AstNodeDType* const dtp = parseDataTypeE()) {
+                fvarp = dtp;
+            } else {
+                const VSigning sign = parseSigningE();
+                AstRange* const rangep = isPunct("[") ? parseRange() : nullptr;
+                FileLine* const dfl = rangep ? rangep->fileline() : m_lex.peek().fl;
+                fvarp = addRange(new AstBasicDType{dfl, VBasicDTypeKwd::LOGIC_IMPLICIT, sign}, rangep);
+            }
+        }
+        const Token name = expectId();
+        AstNodeFTask* ftaskp;
+        if (isFunc) {
+            ftaskp = new AstFunc{name.fl, name.text, nullptr, fvarp};
+        } else {
+            AstTask* const taskp = new AstTask{name.fl, name.text, nullptr};
+            taskp->verilogTask(true);
+            ftaskp = taskp;
+        }
+        ftaskp->lifetime(lifetime);
+        // saved declaration state of the enclosing module
+        const VVarType saveDecl = m_varDecl;
+        const VDirection saveIO = m_varIO;
+        const bool saveAnsi = m_pinAnsi;
+        const int savePin = m_pinNum;
+        const auto portDecl = [&](bool list) {  // direction [type] names
+            const Token dir = m_lex.next();
+            varReset(VVarType::UNKNOWN, m_pinNum);
+            m_varIO = dir.text == "input" ? VDirection::INPUT : dir.text == "output" ? VDirection::OUTPUT : VDirection::INOUT;
+            if (AstNodeDType* const dtp = parseDataTypeE()) {
+                setDType(dtp);
+                m_varDeclTyped = true;
+            } else if (isKw("signed") || isKw("unsigned") || isPunct("[")) {
+                const VSigning sign = parseSigningE();
+                AstRange* const rangep = isPunct("[") ? parseRange() : nullptr;
+                FileLine* const dfl = rangep ? rangep->fileline() : m_lex.peek().fl;
+                setDType(addRange(new AstBasicDType{dfl, VBasicDTypeKwd::LOGIC_IMPLICIT, sign}, rangep));
+            }
+            (void)list;
+        };
+        if (acceptPunct("(")) {  // tf_port_listE
+            varReset(VVarType::UNKNOWN, 0);
+            m_varIO = VDirection::INPUT;
+            while (!isPunct(")")) {
+                if (isKw("input") || isKw("output") || isKw("inout")) portDecl(true);
+                const Token pname = expectId();
+                std::vector<AstRange*> dims;
+                while (isPunct("[")) dims.push_back(parseUnpackedDim());
+                AstVar* const varp = createVariable(pname.fl, pname.text, dims);
+                varp->funcLocal(true);
+                ftaskp->addStmtsp(varp);
+                if (!acceptPunct(",")) break;
+            }
+            expectPunct(")");
+        }
+        expectPunct(";");
+        const char* const endKw = isFunc ? "endfunction" : "endtask";
+        while (!isKw(endKw)) {
+            if (m_lex.peek().kind == Tok::END) syntaxError(m_lex.peek(), endKw);
+            if (isKw("input") || isKw("output") || isKw("inout")) {  // tf_port_declaration
+                portDecl(false);
+                AstNode* const listp = parseDeclList(false);
+                for (AstNode* np = listp; np; np = np->nextp()) {
+                    if (AstVar* const varp = VN_CAST(np, Var)) varp->funcLocal(true);
+                }
+                ftaskp->addStmtsp(listp);
+            } else if (isKw("reg") || isKw("logic") || isKw("integer") || isKw("int") || isKw("bit")) {
+                varReset(VVarType::VAR, 0);  // block_item_declaration
+                setDType(parseDataTypeE());
+                m_varDeclTyped = true;
+                AstNode* const listp = parseDeclList(false);
+                for (AstNode* np = listp; np; np = np->nextp()) {
+                    if (AstVar* const varp = VN_CAST(np, Var)) varp->funcLocal(true);
+                }
+                ftaskp->addStmtsp(listp);
+            } else if (AstNodeStmt* const stmtp = parseStmt()) {
+                ftaskp->addStmtsp(stmtp);
+            }
+        }
+        m_lex.next();
+        if (acceptPunct(":")) expectId();
+        varReset(saveDecl, savePin);
+        m_varIO = saveIO;
+        m_pinAnsi = saveAnsi;
+        return ftaskp;
+    }
+
     // implicit_typeE | data_type after parameter/localparam (parameter_declarationFront :1796-1799)
     void parseParamTypeE() {
         if (AstNodeDType* const dtp = parseDataTypeE()) {
@@ -817,6 +918,7 @@ class Parser final {
             varReset(VVarType::UNKNOWN, m_pinNum);
             return listp;
         }
+        if (t.text == "function" || t.text == "task") return parseFTask();
         if (t.text == "wire") {  // net_declaration (verilog.y:1856-1875, 1888-1902)
             m_lex.next();
             varReset(VVarType::UNKNOWN, 0);
@@ -1196,7 +1298,18 @@ class Parser final {
             m_lex.next();
             return new AstBegin{label.fl, label.text, parseStmt(), false};
         }
-        if (!isReserved(t.text)) return parseAssignStmt();
+        if (!isReserved(t.text)) {
+            // task enable: id ';' or id '(' list_of_argumentsE ')' ';' (verilog.y:4133-4134)
+            const Token& t1 = m_lex.peek(1);
+            if (t1.kind == Tok::PUNCT && (t1.text == ";" || t1.text == "(")) {
+                const Token name = m_lex.next();
+                AstArg* argsp = nullptr;
+                if (acceptPunct("(")) argsp = parseCallArgs();
+                expectPunct(";");
+                return (new AstTaskRef{name.fl, name.text, argsp})->makeStmt();
+            }
+            return parseAssignStmt();
+        }
         syntaxError(t, "statement");
     }
 
@@ -1283,8 +1396,29 @@ class Parser final {
         return parseIdArrayed();
     }
     // idArrayed (verilog.y:6247-6256)
+    // list_of_argumentsE: AstArg per positional argument (verilog.y:5462-5476)
+    AstArg* parseCallArgs() {
+        AstArg* listp = nullptr;
+        if (!isPunct(")")) {
+            do {
+                AstNodeExpr* const exprp = parseExpr();
+                AstArg* const argp = new AstArg{exprp->fileline(), "", exprp};
+                if (listp) {
+                    listp->addNext(argp);
+                } else {
+                    listp = argp;
+                }
+            } while (acceptPunct(","));
+        }
+        expectPunct(")");
+        return listp;
+    }
     AstNodeExpr* parseIdArrayed() {
         const Token name = expectId();
+        if (isPunct("(")) {  // function call: id '(' list_of_argumentsE ')' (verilog.y:4149-4150)
+            m_lex.next();
+            return parseSelects(new AstFuncRef{name.fl, name.text, parseCallArgs()});
+        }
         AstNodeExpr* exprp = new AstParseRef{name.fl, name.text, nullptr, nullptr};
         return parseSelects(exprp);
     }
