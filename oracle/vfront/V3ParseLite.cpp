@@ -755,6 +755,110 @@ class Parser final {
         if (acceptPunct("=")) varp->valuep(parseExpr());
     }
 
+    // genItemOrBegin / genItemBegin / generate_block_or_null / loop_generate_construct /
+    // conditional_generate_construct (if) (verilog.y:2836-2953)
+    AstNode* parseGenItemOrBegin() {
+        if (isKw("begin") || (m_lex.peek().kind == Tok::ID && !isReserved(m_lex.peek().text) && m_lex.peek(1).kind == Tok::PUNCT
+                              && m_lex.peek(1).text == ":" && m_lex.peek(2).kind == Tok::ID && m_lex.peek(2).text == "begin")) {
+            return parseGenBegin();
+        }
+        if (isKw("for")) {
+            const Token kw = m_lex.next();
+            expectPunct("(");
+            AstNode* varp = nullptr;
+            if (acceptKw("genvar")) {  // yGENVAR genvar_identifierDecl '=' constExpr
+                varReset(VVarType::GENVAR, 0);
+                setDType(new AstBasicDType{kw.fl, VBasicDTypeKwd::INTEGER});
+                m_varDeclTyped = true;
+                const Token name = expectId();
+                std::vector<AstRange*> dims;
+                varp = createVariable(name.fl, name.text, dims);
+                const Token eq = expectPunct("=");
+                varp->addNext(new AstAssign{eq.fl, new AstParseRef{name.fl, name.text, nullptr, nullptr}, parseExpr()});
+                varReset(VVarType::UNKNOWN, 0);
+            }
+            AstNode* initp = varp;
+            if (!varp) {
+                const Token name = expectId();
+                const Token eq = expectPunct("=");
+                initp = new AstAssign{eq.fl, new AstParseRef{name.fl, name.text, nullptr, nullptr}, parseExpr()};
+            }
+            expectPunct(";");
+            AstNodeExpr* const condp = parseExpr();
+            expectPunct(";");
+            AstNode* const incp = parseGenvarIteration();
+            expectPunct(")");
+            AstNode* const bodyp = parseGenBlockOrNull();
+            // BEGIN(GENFOR(...)): the begin hides the local genvar (verilog.y:2929-2951)
+            AstGenBlock* const lowerp = VN_CAST(bodyp, GenBlock);
+            AstNode* const itemsp = lowerp && lowerp->itemsp() ? lowerp->itemsp()->unlinkFrBackWithNext() : nullptr;
+            AstGenBlock* const blkp = new AstGenBlock{kw.fl, lowerp ? lowerp->name() : "", nullptr, true};
+            if (VN_IS(initp, Var)) {
+                AstNode* const assignp = initp->nextp();
+                assignp->unlinkFrBackWithNext();
+                blkp->addItemsp(initp);
+                initp = assignp;
+            }
+            blkp->genforp(new AstGenFor{kw.fl, initp, condp, incp, itemsp});
+            if (lowerp) VL_DO_DANGLING(lowerp->deleteTree(), lowerp);
+            return blkp;
+        }
+        if (isKw("if")) {
+            const Token kw = m_lex.next();
+            expectPunct("(");
+            AstNodeExpr* const condp = parseExpr();
+            expectPunct(")");
+            AstNode* const thenp = parseGenBlockOrNull();
+            AstNode* elsep = nullptr;
+            if (acceptKw("else")) elsep = parseGenBlockOrNull();
+            return new AstGenIf{kw.fl, condp, thenp, elsep};
+        }
+        return parseModuleItem();
+    }
+    AstNode* parseGenBegin() {
+        std::string name;
+        FileLine* fl = m_lex.peek().fl;
+        if (!isKw("begin")) {  // id ':' begin
+            name = m_lex.next().text;
+            m_lex.next();
+        }
+        const Token kw = m_lex.next();  // begin
+        if (acceptPunct(":")) {
+            const Token lbl = expectId();
+            name = lbl.text;
+            fl = lbl.fl;
+        }
+        AstNode* listp = nullptr;
+        while (!isKw("end")) {
+            if (m_lex.peek().kind == Tok::END) syntaxError(m_lex.peek(), "'end'");
+            listp = AstNode::addNextNull(listp, parseGenItemOrBegin());
+        }
+        m_lex.next();
+        if (acceptPunct(":")) expectId();
+        if (!listp && name.empty()) return nullptr;
+        return new AstGenBlock{name.empty() ? kw.fl : fl, name, listp, false};
+    }
+    AstNode* parseGenBlockOrNull() {
+        if (isKw("begin") || (m_lex.peek().kind == Tok::ID && m_lex.peek(1).kind == Tok::PUNCT && m_lex.peek(1).text == ":"
+                              && m_lex.peek(2).kind == Tok::ID && m_lex.peek(2).text == "begin")) {
+            return parseGenBegin();
+        }
+        AstNode* const itemp = parseGenItemOrBegin();
+        return itemp ? new AstGenBlock{itemp->fileline(), "", itemp, true} : nullptr;
+    }
+    AstNode* parseGenvarIteration() {  // genvar_iteration (verilog.y:2962-2999), ++/-- included
+        const Token name = expectId();
+        AstParseRef* const refp = new AstParseRef{name.fl, name.text, nullptr, nullptr};
+        const Token op = m_lex.next();
+        const auto ref2 = [&]() { return new AstParseRef{name.fl, name.text, nullptr, nullptr}; };
+        if (op.text == "=") return new AstAssign{op.fl, refp, parseExpr()};
+        if (op.text == "+=") return new AstAssign{op.fl, refp, new AstAdd{op.fl, ref2(), parseExpr()}};
+        if (op.text == "-=") return new AstAssign{op.fl, refp, new AstSub{op.fl, ref2(), parseExpr()}};
+        if (op.text == "++") return new AstAssign{op.fl, refp, new AstAdd{op.fl, ref2(), new AstConst{op.fl, AstConst::StringToParse{}, "'b1"}}};
+        if (op.text == "--") return new AstAssign{op.fl, refp, new AstSub{op.fl, ref2(), new AstConst{op.fl, AstConst::StringToParse{}, "'b1"}}};
+        syntaxError(op, "genvar iteration");
+    }
+
     // function_declaration / task_declaration (verilog.y:4637-4660, 4702-4749, 4788-4830):
     // [automatic] funcId tfGuts: ANSI or Verilog-1995 ports, block item declarations, statements
     AstNode* parseFTask() {
@@ -919,6 +1023,18 @@ class Parser final {
             return listp;
         }
         if (t.text == "function" || t.text == "task") return parseFTask();
+        if (t.text == "generate") {  // generate_region (verilog.y:2823-2826)
+            m_lex.next();
+            AstNode* listp = nullptr;
+            while (!isKw("endgenerate")) {
+                if (m_lex.peek().kind == Tok::END) syntaxError(m_lex.peek(), "'endgenerate'");
+                listp = AstNode::addNextNull(listp, parseGenItemOrBegin());
+            }
+            m_lex.next();
+            return listp;
+        }
+        // loop_generate_construct / conditional_generate_construct outside a generate region
+        if (t.text == "for" || t.text == "if" || t.text == "begin") return parseGenItemOrBegin();
         if (t.text == "wire") {  // net_declaration (verilog.y:1856-1875, 1888-1902)
             m_lex.next();
             varReset(VVarType::UNKNOWN, 0);

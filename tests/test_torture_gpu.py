@@ -1,11 +1,11 @@
-"""Breadth of the emitter + operator library: fifteen hand-written designs and four random ones, each a different corner of
+"""Breadth of the emitter + operator library: sixteen hand-written designs and four random ones, each a different corner of
 what V3Sched/V3Order/V3Expand/V3Table/V3Delayed/V3Unroll produce (scalar signed/unsigned
 mul/div/mod and shifts, case FSM + constant-pool table + casez, byte-enable memories with
 run-time indices, two clocks + negedge + asynchronous reset, 96/130-bit multiply/divide/shift,
 unrolled loops, data-dependent while/for loops + $countones/$onehot/power, arrays of wide and
 64-bit elements with two write ports, multidimensional arrays in every storage class, a 4 KB
 state array streamed by a loop, NBA commit queues, $urandom / $error / $fatal / inout / initial
-ROM / final, derived and gated clocks + latch + signed wide arithmetic, a parameterised module hierarchy, functions and tasks; tests/gen_random_design.py's expression
+ROM / final, derived and gated clocks + latch + signed wide arithmetic, a parameterised module hierarchy, functions and tasks, generate regions; tests/gen_random_design.py's expression
 soups), taken through the reference's own compiler and V3EmitCuda with no hand-written
 code per design, and compared bit for bit with the genuine Verilated C++ model under random
 stimulus on every port at every eval."""
@@ -16,7 +16,7 @@ import oracle_util as O
 
 pytestmark = pytest.mark.gpu
 
-DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate", "t11_nbaq", "t12_sys", "t13_mix", "t14_hier", "t15_func",
+DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate", "t11_nbaq", "t12_sys", "t13_mix", "t14_hier", "t15_func", "t16_gen",
            "rnd01", "rnd02", "rnd03", "rnd04"]
 
 
