@@ -100,6 +100,8 @@ class MacroExpander final {
         std::string body;
     };
     std::map<std::string, Macro> m_macros;
+    std::string m_filename;  // for `__FILE__
+    int m_line = 1;  // for `__LINE__
 
     static bool idStart(char c) { return std::isalpha(static_cast<unsigned char>(c)) || c == '_'; }
     static bool idChar(char c) { return std::isalnum(static_cast<unsigned char>(c)) || c == '_' || c == '$'; }
@@ -128,6 +130,11 @@ class MacroExpander final {
                 size_t j = i + 1;
                 while (j < in.size() && idChar(in[j])) ++j;
                 const std::string name = in.substr(i + 1, j - i - 1);
+                if (name == "__FILE__" || name == "__LINE__") {
+                    out += name == "__FILE__" ? "\"" + m_filename + "\"" : std::to_string(m_line);
+                    i = j;
+                    continue;
+                }
                 const auto it = m_macros.find(name);
                 if (it == m_macros.end()) {  // `line, `timescale ...: left for the lexer
                     out.append(in, i, j - i);
@@ -208,7 +215,9 @@ public:
         m_macros["verilator3"].body = "1";
         m_macros["SYSTEMVERILOG"].body = "1";
     }
-    std::string run(const std::string& src) {
+    std::string run(const std::string& src, const std::string& filename) {
+        m_filename = filename;
+        m_line = 1;
         std::string out;
         std::vector<std::pair<bool, bool>> conds;  // (this branch active, some branch taken)
         const auto active = [&]() {
@@ -301,6 +310,7 @@ public:
                 out += '\n';
             }
             for (int k = 0; k < extraLines; ++k) out += '\n';
+            m_line += 1 + extraLines;
             pos = eol + 1;
         }
         return out;
@@ -531,7 +541,7 @@ class Parser final {
             "signed", "unsigned", "assign", "always", "always_ff", "always_comb", "always_latch", "initial",
             "begin", "end", "if", "else", "case", "casez", "casex", "endcase", "default", "for", "posedge",
             "negedge", "or", "parameter", "localparam", "assert", "cover", "property", "genvar", "generate",
-            "endgenerate", "function", "endfunction", "task", "endtask", "final", "while", "unique", "priority"};
+            "endgenerate", "function", "endfunction", "task", "endtask", "final", "while", "do", "unique", "priority"};
         return kw.count(s) != 0;
     }
 
@@ -1345,6 +1355,16 @@ class Parser final {
             if (prio) casep->priorityPragma(true);
             return casep;
         }
+        if (t.text == "do") {  // yDO stmt yWHILE '(' expr ')' ';' (verilog.y:3701-3704)
+            const Token kw = m_lex.next();
+            AstLoop* const loopp = new AstLoop{kw.fl, parseStmt()};
+            expectKw("while");
+            const Token lp = expectPunct("(");
+            loopp->addContsp(new AstLoopTest{lp.fl, loopp, parseExpr()});
+            expectPunct(")");
+            acceptPunct(";");
+            return loopp;
+        }
         if (t.text == "while") {  // statement_item: yWHILE '(' expr ')' stmt (verilog.y:3716-3720)
             const Token kw = m_lex.next();
             const Token lp = expectPunct("(");
@@ -1795,7 +1815,7 @@ void V3Parse::parseFile(FileLine* fileline, const string& modname, bool inLibrar
         return;
     }
     MacroExpander macros;
-    Lexer lexer{fileline, macros.run(impp->text)};
+    Lexer lexer{fileline, macros.run(impp->text, fileline->filename())};
     Parser parser{lexer, impp->rootp, inLibrary, libname};
     parser.parseDescriptions();
 }

@@ -1,0 +1,554 @@
+// Verilated -*- C++ -*-
+// DESCRIPTION: Verilator output: Batched CUDA model (one instance per thread) for include/verilated_cuda.h
+// Design '$root' printed by V3EmitCuda; compile with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include
+
+#include "verilated_cuda_launch.h"
+
+#include <vector>
+
+// Name the design registers under with vlcu_create()
+#ifndef VLCU_DESIGN_NAME
+#define VLCU_DESIGN_NAME "Vt_for_count"
+#endif
+
+// The model image of one instance (Vtop___024root of the C++ model), held by one thread
+struct Vt_for_count___024root final {
+    CData/*0:0*/ clk;
+    CData/*0:0*/ __VstlFirstIteration;
+    CData/*0:0*/ __VstlPhaseResult;
+    CData/*0:0*/ __Vtrigprevexpr___TOP__clk__0;
+    CData/*0:0*/ __VactPhaseResult;
+    CData/*0:0*/ __VnbaPhaseResult;
+    IData/*31:0*/ t__DOT__cyc;
+    IData/*31:0*/ t__DOT__hit_count;
+    IData/*31:0*/ t__DOT__hit_count3;
+    IData/*31:0*/ t__DOT__wide_for_count;
+    IData/*31:0*/ t__DOT__w;
+    IData/*31:0*/ t__DOT__dw;
+    IData/*31:0*/ __VactIterCount;
+    QData/*63:0*/ t__DOT__cam_lookup_hit_vector;
+    VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
+    VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
+    const char* vlNamep;
+};
+
+struct Vt_for_count__cuda final {
+    typedef Vt_for_count___024root Root;
+    // Structure-of-arrays slot table: byte offset per instance of every persistent member
+    enum : uint32_t {
+        OFF_clk = 60,
+        OFF___VstlFirstIteration = 61,
+        OFF___VstlPhaseResult = 62,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 63,
+        OFF___VactPhaseResult = 64,
+        OFF___VnbaPhaseResult = 65,
+        OFF_t__DOT__cyc = 32,
+        OFF_t__DOT__hit_count = 36,
+        OFF_t__DOT__hit_count3 = 40,
+        OFF_t__DOT__wide_for_count = 44,
+        OFF_t__DOT__w = 48,
+        OFF_t__DOT__dw = 52,
+        OFF___VactIterCount = 56,
+        OFF_t__DOT__cam_lookup_hit_vector = 0,
+        OFF___VstlTriggered = 8,
+        OFF___VactTriggered = 16,
+        OFF___VnbaTriggered = 24,
+        kStateBytes = 72,  // S_persist
+        kTouchedReadBytes = 48,  // S_state_rd: persistent bytes one eval can read
+        kTouchedWriteBytes = 43,  // S_state_wr
+    };
+    struct Locals final {
+    };
+    struct Shared final {
+    };
+    VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
+        (void)l; (void)sh; (void)st; (void)i;
+        s.vlNamep = "TOP";
+    }
+    VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
+        s.clk = st.ld<VlcuMem8>(OFF_clk, i);
+        s.__VstlFirstIteration = st.ld<VlcuMem8>(OFF___VstlFirstIteration, i);
+        s.__VstlPhaseResult = st.ld<VlcuMem8>(OFF___VstlPhaseResult, i);
+        s.__Vtrigprevexpr___TOP__clk__0 = st.ld<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i);
+        s.__VactPhaseResult = st.ld<VlcuMem8>(OFF___VactPhaseResult, i);
+        s.__VnbaPhaseResult = st.ld<VlcuMem8>(OFF___VnbaPhaseResult, i);
+        s.t__DOT__cyc = st.ld<IData>(OFF_t__DOT__cyc, i);
+        s.t__DOT__hit_count = st.ld<IData>(OFF_t__DOT__hit_count, i);
+        s.t__DOT__hit_count3 = st.ld<IData>(OFF_t__DOT__hit_count3, i);
+        s.t__DOT__wide_for_count = st.ld<IData>(OFF_t__DOT__wide_for_count, i);
+        s.t__DOT__w = st.ld<IData>(OFF_t__DOT__w, i);
+        s.t__DOT__dw = st.ld<IData>(OFF_t__DOT__dw, i);
+        s.__VactIterCount = st.ld<IData>(OFF___VactIterCount, i);
+        s.t__DOT__cam_lookup_hit_vector = st.ld<QData>(OFF_t__DOT__cam_lookup_hit_vector, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VstlTriggered[e] = st.ldE<QData>(OFF___VstlTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VactTriggered[e] = st.ldE<QData>(OFF___VactTriggered, e, i);
+        for (uint32_t e = 0; e < 1; ++e) s.__VnbaTriggered[e] = st.ldE<QData>(OFF___VnbaTriggered, e, i);
+    }
+    VLCU_D static void store(const Root& s, const VlcuState& st, uint64_t i) {
+        st.st<VlcuMem8>(OFF_clk, i, s.clk);
+        st.st<VlcuMem8>(OFF___VstlFirstIteration, i, s.__VstlFirstIteration);
+        st.st<VlcuMem8>(OFF___VstlPhaseResult, i, s.__VstlPhaseResult);
+        st.st<VlcuMem8>(OFF___Vtrigprevexpr___TOP__clk__0, i, s.__Vtrigprevexpr___TOP__clk__0);
+        st.st<VlcuMem8>(OFF___VactPhaseResult, i, s.__VactPhaseResult);
+        st.st<VlcuMem8>(OFF___VnbaPhaseResult, i, s.__VnbaPhaseResult);
+        st.st<IData>(OFF_t__DOT__cyc, i, s.t__DOT__cyc);
+        st.st<IData>(OFF_t__DOT__hit_count, i, s.t__DOT__hit_count);
+        st.st<IData>(OFF_t__DOT__hit_count3, i, s.t__DOT__hit_count3);
+        st.st<IData>(OFF_t__DOT__wide_for_count, i, s.t__DOT__wide_for_count);
+        st.st<IData>(OFF_t__DOT__w, i, s.t__DOT__w);
+        st.st<IData>(OFF_t__DOT__dw, i, s.t__DOT__dw);
+        st.st<IData>(OFF___VactIterCount, i, s.__VactIterCount);
+        st.st<QData>(OFF_t__DOT__cam_lookup_hit_vector, i, s.t__DOT__cam_lookup_hit_vector);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VstlTriggered, e, i, s.__VstlTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VactTriggered, e, i, s.__VactTriggered[e]);
+        for (uint32_t e = 0; e < 1; ++e) st.stE<QData>(OFF___VnbaTriggered, e, i, s.__VnbaTriggered[e]);
+    }
+    VLCU_D static void load_inputs_row(Root& s, const uint32_t* rowp, uint64_t stride, uint64_t i) {
+        s.clk = static_cast<VlcuMem8>(rowp[0 * stride + i] & 0x1U);
+    }
+    VLCU_D static void store_outputs_row(const Root& s, uint32_t* rowp, uint64_t stride, uint64_t i) {
+    }
+    VLCU_D static uint64_t outputs_sig(const Root& s, uint64_t sig) {
+        uint32_t acc = VLCU_SIG_ACC_INIT;
+        return vlcu_sig_mix(sig, acc);
+    }
+    enum : uint32_t { kInWords = 1, kOutWords = 0, kInBytes = 1, kOutBytes = 0, kTraceWords = 0 };
+
+    VLCU_D static void Vt_for_count___024root___eval_static(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        vlSelfRef.__Vtrigprevexpr___TOP__clk__0 = vlSelfRef.clk;
+    }
+
+    VLCU_D static void Vt_for_count___024root___eval_initial(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_initial__TOP
+            VlWide<4>/*127:0*/ __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index;
+            VL_ZERO_W(128, __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index);
+            VlWide<4>/*127:0*/ __Vinline_0__eval_initial__TOP___Vtemp_1;
+            VlWide<4>/*127:0*/ __Vinline_0__eval_initial__TOP___Vtemp_2;
+            VlWide<4>/*127:0*/ __Vinline_0__eval_initial__TOP___Vtemp_3;
+            vlSelfRef.t__DOT__wide_for_count = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[0U] = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[1U] = 0U;
+            __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[2U] = 0x000000ffU;
+            __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[3U] = 0U;
+            while (true) {
+                __Vinline_0__eval_initial__TOP___Vtemp_1[0U] = 0x00000100U;
+                __Vinline_0__eval_initial__TOP___Vtemp_1[1U] = 0U;
+                __Vinline_0__eval_initial__TOP___Vtemp_1[2U] = 0x000000ffU;
+                __Vinline_0__eval_initial__TOP___Vtemp_1[3U] = 0U;
+                if (!(VL_GT_W(4, __Vinline_0__eval_initial__TOP___Vtemp_1, __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index))) break;
+                vlSelfRef.t__DOT__wide_for_count = 
+                    ((IData)(1U) + vlSelfRef.t__DOT__wide_for_count);
+                __Vinline_0__eval_initial__TOP___Vtemp_3[0U] = 2U;
+                __Vinline_0__eval_initial__TOP___Vtemp_3[1U] = 0U;
+                __Vinline_0__eval_initial__TOP___Vtemp_3[2U] = 0U;
+                __Vinline_0__eval_initial__TOP___Vtemp_3[3U] = 0U;
+                VL_ADD_W(4, __Vinline_0__eval_initial__TOP___Vtemp_2, __Vinline_0__eval_initial__TOP___Vtemp_3, __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index);
+                __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[0U] 
+                    = __Vinline_0__eval_initial__TOP___Vtemp_2[0U];
+                __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[1U] 
+                    = __Vinline_0__eval_initial__TOP___Vtemp_2[1U];
+                __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[2U] 
+                    = __Vinline_0__eval_initial__TOP___Vtemp_2[2U];
+                __Vinline_0__eval_initial__TOP_t__DOT__wide_for_index[3U] 
+                    = __Vinline_0__eval_initial__TOP___Vtemp_2[3U];
+            }
+            vlSelfRef.t__DOT__cyc = 1U;
+            while (VL_GTS_III(32, 0x0000000aU, vlSelfRef.t__DOT__w)) {
+                vlSelfRef.t__DOT__w = ((IData)(1U) 
+                                       + vlSelfRef.t__DOT__w);
+            }
+            if (VL_UNLIKELY(((0x0000000aU != vlSelfRef.t__DOT__w)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 58, "");
+            }
+            while (VL_GTS_III(32, 0x00000014U, vlSelfRef.t__DOT__w)) {
+                vlSelfRef.t__DOT__w = ((IData)(2U) 
+                                       + vlSelfRef.t__DOT__w);
+            }
+            while (VL_GTS_III(32, 0x00000014U, vlSelfRef.t__DOT__w)) {
+                vlSelfRef.t__DOT__w = ((IData)(0x0001869fU) 
+                                       + vlSelfRef.t__DOT__w);
+            }
+            if (VL_UNLIKELY(((0x00000014U != vlSelfRef.t__DOT__w)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 65, "");
+            }
+            do {
+                vlSelfRef.t__DOT__dw = ((IData)(1U) 
+                                        + vlSelfRef.t__DOT__dw);
+            } while (VL_GTS_III(32, 0x0000000aU, vlSelfRef.t__DOT__dw));
+            if (VL_UNLIKELY(((0x0000000aU != vlSelfRef.t__DOT__dw)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 72, "");
+            }
+            do {
+                vlSelfRef.t__DOT__dw = ((IData)(2U) 
+                                        + vlSelfRef.t__DOT__dw);
+            } while (VL_GTS_III(32, 0x00000014U, vlSelfRef.t__DOT__dw));
+            if (VL_UNLIKELY(((0x00000014U != vlSelfRef.t__DOT__dw)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 74, "");
+            }
+            do {
+                vlSelfRef.t__DOT__dw = ((IData)(5U) 
+                                        + vlSelfRef.t__DOT__dw);
+            } while (VL_GTS_III(32, 0x00000014U, vlSelfRef.t__DOT__dw));
+            if (VL_UNLIKELY(((0x00000019U != vlSelfRef.t__DOT__dw)))) {
+                VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 76, "");
+            }
+        }
+    }
+
+    VLCU_D static void Vt_for_count___024root___eval_final(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+    }
+
+    VLCU_D static void Vt_for_count___024root___eval_settle(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VstlIterCount;
+        // Body
+        __VstlIterCount = 0U;
+        vlSelfRef.__VstlFirstIteration = 1U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VstlIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_for_count___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_for_count.v", 7, "", "DIDNOTCONVERGE: Settle region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VstlIterCount = ((IData)(1U) + __VstlIterCount);
+            vlSelfRef.__VstlPhaseResult = Vt_for_count___024root___eval_phase__stl(vlSelf, vlCtx);
+            vlSelfRef.__VstlFirstIteration = 0U;
+        } while (vlSelfRef.__VstlPhaseResult);
+    }
+
+    VLCU_D static bool Vt_for_count___024root___trigger_anySet__stl(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static bool Vt_for_count___024root___eval_phase__stl(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VstlExecute;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__stl
+            vlSelfRef.__VstlTriggered[0U] = ((0xfffffffffffffffeULL 
+                                              & vlSelfRef.__VstlTriggered[0U]) 
+                                             | (IData)((IData)(vlSelfRef.__VstlFirstIteration)));
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_for_count___024root___dump_triggers__stl(vlSelfRef.__VstlTriggered, "stl"s);
+        }
+#endif
+        __VstlExecute = Vt_for_count___024root___trigger_anySet__stl(vlSelfRef.__VstlTriggered);
+        if (__VstlExecute) {
+            {
+                // Inlined CFunc: _eval_stl
+                if ((1ULL & vlSelfRef.__VstlTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _stl_sequent__TOP__0
+                        vlSelfRef.t__DOT__hit_count 
+                            = VL_COUNTONES_Q(vlSelfRef.t__DOT__cam_lookup_hit_vector);
+                        vlSelfRef.t__DOT__hit_count3 
+                            = VL_COUNTONES_Q((vlSelfRef.t__DOT__cam_lookup_hit_vector 
+                                              >> 1U));
+                    }
+                }
+            }
+        }
+        return (__VstlExecute);
+    }
+
+    VLCU_D static bool Vt_for_count___024root___trigger_anySet__act(const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef bool VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            if (in[n]) {
+                return (1U);
+            }
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+        return (0U);
+    }
+
+    VLCU_D static void Vt_for_count___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = (out[n] | in[n]);
+            n = ((IData)(1U) + n);
+        } while ((0U >= n));
+    }
+
+    VLCU_D static bool Vt_for_count___024root___eval_phase__act(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        {
+            // Inlined CFunc: _eval_triggers_vec__act
+            vlSelfRef.__VactTriggered[0U] = (QData)((IData)(
+                                                            ((IData)(vlSelfRef.clk) 
+                                                             & (~ (IData)(vlSelfRef.__Vtrigprevexpr___TOP__clk__0)))));
+            vlSelfRef.__Vtrigprevexpr___TOP__clk__0 
+                = vlSelfRef.clk;
+        }
+#ifdef VL_DEBUG
+        if (VL_UNLIKELY(vlSymsp->_vm_contextp__->debug())) {
+            Vt_for_count___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+        }
+#endif
+        Vt_for_count___024root___trigger_orInto__act_vec_vec(vlSelfRef.__VnbaTriggered, vlSelfRef.__VactTriggered);
+        return (0U);
+    }
+
+    VLCU_D static void Vt_for_count___024root___trigger_clear__act(VlUnpacked<QData/*63:0*/, 1> &out) {
+        typedef void VlcuFuncRet;
+        // Locals
+        IData/*31:0*/ n;
+        // Body
+        n = 0U;
+        do {
+            out[n] = 0ULL;
+            n = ((IData)(1U) + n);
+        } while ((1U > n));
+    }
+
+    VLCU_D static bool Vt_for_count___024root___eval_phase__nba(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef bool VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        CData/*0:0*/ __VnbaExecute;
+        // Body
+        __VnbaExecute = Vt_for_count___024root___trigger_anySet__act(vlSelfRef.__VnbaTriggered);
+        if (__VnbaExecute) {
+            {
+                // Inlined CFunc: _eval_nba
+                if ((1ULL & vlSelfRef.__VnbaTriggered[0U])) {
+                    {
+                        // Inlined CFunc: _nba_sequent__TOP__0
+                        IData/*31:0*/ __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc = 0;
+                        __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                            = vlSelfRef.t__DOT__cyc;
+                        vlSelfRef.t__DOT__cam_lookup_hit_vector = 0ULL;
+                        if ((0U != vlSelfRef.t__DOT__cyc)) {
+                            __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc 
+                                = ((IData)(1U) + vlSelfRef.t__DOT__cyc);
+                            if ((1U == vlSelfRef.t__DOT__cyc)) {
+                                vlSelfRef.t__DOT__cam_lookup_hit_vector = 0x0001000000010000ULL;
+                            }
+                            if ((2U == vlSelfRef.t__DOT__cyc)) {
+                                if (VL_UNLIKELY(((2U 
+                                                  != vlSelfRef.t__DOT__hit_count)))) {
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 87, "");
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 88, "");
+                                }
+                                vlSelfRef.t__DOT__cam_lookup_hit_vector = 0x0101001000010001ULL;
+                                if (VL_UNLIKELY(((2U 
+                                                  != vlSelfRef.t__DOT__hit_count3)))) {
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 89, "");
+                                }
+                            }
+                            if ((3U == vlSelfRef.t__DOT__cyc)) {
+                                if (VL_UNLIKELY(((5U 
+                                                  != vlSelfRef.t__DOT__hit_count)))) {
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 93, "");
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 94, "");
+                                }
+                                if (VL_UNLIKELY(((4U 
+                                                  != vlSelfRef.t__DOT__hit_count3)))) {
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 95, "");
+                                }
+                                if (VL_UNLIKELY(((0x00000080U 
+                                                  != vlSelfRef.t__DOT__wide_for_count)))) {
+                                    VL_STOP_MT("/root/reference/test_regress/t/t_for_count.v", 96, "");
+                                }
+                            }
+                            if (VL_UNLIKELY(((9U == vlSelfRef.t__DOT__cyc)))) {
+                                vlCtx.writef(0U, 0U);
+                                VL_FINISH_MT("/root/reference/test_regress/t/t_for_count.v", 100, "");
+                            }
+                        }
+                        vlSelfRef.t__DOT__cyc = __Vinline_0__eval_nba___Vinline_0__nba_sequent__TOP__0___Vdly__t__DOT__cyc;
+                        vlSelfRef.t__DOT__hit_count 
+                            = VL_COUNTONES_Q(vlSelfRef.t__DOT__cam_lookup_hit_vector);
+                        vlSelfRef.t__DOT__hit_count3 
+                            = VL_COUNTONES_Q((vlSelfRef.t__DOT__cam_lookup_hit_vector 
+                                              >> 1U));
+                    }
+                }
+            }
+            Vt_for_count___024root___trigger_clear__act(vlSelfRef.__VnbaTriggered);
+        }
+        return (__VnbaExecute);
+    }
+
+    VLCU_D static void Vt_for_count___024root___eval(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Locals
+        IData/*31:0*/ __VnbaIterCount;
+        // Body
+        __VnbaIterCount = 0U;
+        do {
+            if (VL_UNLIKELY(((0x00002710U < __VnbaIterCount)))) {
+#ifdef VL_DEBUG
+                Vt_for_count___024root___dump_triggers__act(vlSelfRef.__VnbaTriggered, "nba"s);
+#endif
+                VL_FATAL_MT("/root/reference/test_regress/t/t_for_count.v", 7, "", "DIDNOTCONVERGE: NBA region did not converge after '--converge-limit' of 10000 tries");
+            }
+            __VnbaIterCount = ((IData)(1U) + __VnbaIterCount);
+            vlSelfRef.__VactIterCount = 0U;
+            do {
+                if (VL_UNLIKELY(((0x00002710U < vlSelfRef.__VactIterCount)))) {
+#ifdef VL_DEBUG
+                    Vt_for_count___024root___dump_triggers__act(vlSelfRef.__VactTriggered, "act"s);
+#endif
+                    VL_FATAL_MT("/root/reference/test_regress/t/t_for_count.v", 7, "", "DIDNOTCONVERGE: Active region did not converge after '--converge-limit' of 10000 tries");
+                }
+                vlSelfRef.__VactIterCount = ((IData)(1U) 
+                                             + vlSelfRef.__VactIterCount);
+                vlSelfRef.__VactPhaseResult = Vt_for_count___024root___eval_phase__act(vlSelf, vlCtx);
+            } while (vlSelfRef.__VactPhaseResult);
+            vlSelfRef.__VnbaPhaseResult = Vt_for_count___024root___eval_phase__nba(vlSelf, vlCtx);
+        } while (vlSelfRef.__VnbaPhaseResult);
+    }
+
+    VLCU_D static void Vt_for_count___024root___ctor_var_reset(Vt_for_count___024root* vlSelf, VlcuContext& vlCtx) {
+        typedef void VlcuFuncRet;
+        auto& vlSelfRef = *vlSelf;
+        const VlcuSymsShim vlSymsShim{&vlCtx};
+        const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;
+        // Body
+        const uint64_t __VscopeHash = VL_MURMUR64_HASH(vlSelf->vlNamep);
+        vlSelf->clk = VL_SCOPED_RAND_RESET_I(1, __VscopeHash, 16707436170211756652ull);
+        vlSelf->t__DOT__cyc = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 15508623621340971111ull);
+        vlSelf->t__DOT__cam_lookup_hit_vector = VL_SCOPED_RAND_RESET_Q(64, __VscopeHash, 13591024166037734216ull);
+        vlSelf->t__DOT__hit_count = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 7291245829820760085ull);
+        vlSelf->t__DOT__hit_count3 = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 13617712717024582291ull);
+        vlSelf->t__DOT__wide_for_count = VL_SCOPED_RAND_RESET_I(32, __VscopeHash, 6403438756536011271ull);
+        vlSelf->t__DOT__w = 0;
+        vlSelf->t__DOT__dw = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VstlTriggered[__Vi0] = 0;
+        }
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VactTriggered[__Vi0] = 0;
+        }
+        vlSelf->__Vtrigprevexpr___TOP__clk__0 = 0;
+        for (int __Vi0 = 0; __Vi0 < 1; ++__Vi0) {
+            vlSelf->__VnbaTriggered[__Vi0] = 0;
+        }
+    }
+
+    // tfp->dump(): every traced value stored at its trace code.  Full functions, then the
+    // constants, as VerilatedTrace::dump runs them the first time (verilated_trace_imp.h:348-358)
+    VLCU_D static void trace_sample(Root* vlSelf, VlcuContext& vlCtx, uint32_t* valsp) {
+        (void)vlSelf; (void)vlCtx; (void)valsp;
+    }
+
+    VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
+        Vt_for_count___024root___ctor_var_reset(vlSelf, vlCtx);
+    }
+    VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vt_for_count___024root___eval_static(vlSelf, vlCtx); }
+    VLCU_D static void eval_initial(Root* vlSelf, VlcuContext& vlCtx) { Vt_for_count___024root___eval_initial(vlSelf, vlCtx); }
+    VLCU_D static void eval_settle(Root* vlSelf, VlcuContext& vlCtx) { Vt_for_count___024root___eval_settle(vlSelf, vlCtx); }
+    VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) { Vt_for_count___024root___eval(vlSelf, vlCtx); }
+    VLCU_D static void eval_final(Root* vlSelf, VlcuContext& vlCtx) { Vt_for_count___024root___eval_final(vlSelf, vlCtx); }
+
+    static const VlcuDesignInfo& info();
+};
+
+//======================================================================
+// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime
+
+const VlcuDesignInfo& Vt_for_count__cuda::info() {
+    typedef Vt_for_count__cuda T;
+    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    static const VlcuMemberDesc members[] = {
+        {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
+        {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
+        {"__VstlPhaseResult", "__VstlPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlPhaseResult},
+        {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
+        {"__VactPhaseResult", "__VactPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VactPhaseResult},
+        {"__VnbaPhaseResult", "__VnbaPhaseResult", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VnbaPhaseResult},
+        {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__cyc},
+        {"t__DOT__hit_count", "t.hit_count", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__hit_count},
+        {"t__DOT__hit_count3", "t.hit_count3", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__hit_count3},
+        {"t__DOT__wide_for_count", "t.wide_for_count", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__wide_for_count},
+        {"t__DOT__w", "t.w", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__w},
+        {"t__DOT__dw", "t.dw", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF_t__DOT__dw},
+        {"__VactIterCount", "__VactIterCount", VLCU_MEMBER_STATE, 4, 0, 1, 32, 31, 0, T::OFF___VactIterCount},
+        {"t__DOT__cam_lookup_hit_vector", "t.cam_lookup_hit_vector", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF_t__DOT__cam_lookup_hit_vector},
+        {"__VstlTriggered", "__VstlTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VstlTriggered},
+        {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
+        {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
+    };
+    static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
+    static const char* const plusargs[] = {nullptr};
+    static const VlcuTraceDecl traceDecls[] = {
+        {VLCU_TRACE_POP, 0, nullptr, 0, 0, -1, 0, 0}};  // (terminator, not counted)
+    static const uint32_t traceOrder[] = {0};  // codes in dump order (+ terminator)
+    static const uint32_t saveOrder[] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 0};  // (+ terminator)
+    static const VlcuDesignInfo s = {
+        VLCU_DESIGN_NAME, "t", members, sizeof(members) / sizeof(members[0]),
+        T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, T::kTouchedWriteBytes,
+        nullptr, 0, 0, 0,
+        messages, 1, plusargs, 0,
+        nullptr, 0, 0, nullptr, 0,
+        saveOrder, 17, 0, 0x884886c1d74fdcbcULL, nullptr, 12, 12};
+    return s;
+}
+
+// The device testbenches of this design (the user's C++ main loop, on the GPU)
+#ifdef VLCU_TESTBENCH_INCLUDE
+#include VLCU_TESTBENCH_INCLUDE
+#endif
+#ifndef VLCU_TESTBENCHES  // the testbench header lists its classes: #define VLCU_TESTBENCHES , TbA, TbB
+#define VLCU_TESTBENCHES
+#endif
+VLCU_REGISTER_DESIGN_X(Vt_for_count__cuda VLCU_TESTBENCHES);
