@@ -1460,10 +1460,26 @@ class Parser final {
             const Token le = m_lex.next();
             return new AstAssignDly{le.fl, lhsp, parseExpr()};
         }
-        if (isPunct("+=") || isPunct("-=")) {
+        {  // foperator_assignment (verilog.y:3798-3820)
+            static const std::pair<const char*, decltype(AstAssignCompound::Add)> ops[]
+                = {{"+=", AstAssignCompound::Add},      {"-=", AstAssignCompound::Sub},
+                   {"*=", AstAssignCompound::Mul},      {"/=", AstAssignCompound::Div},
+                   {"%=", AstAssignCompound::ModDiv},   {"&=", AstAssignCompound::And},
+                   {"|=", AstAssignCompound::Or},       {"^=", AstAssignCompound::Xor},
+                   {"<<=", AstAssignCompound::ShiftL},  {">>=", AstAssignCompound::ShiftR},
+                   {">>>=", AstAssignCompound::ShiftRS}};
+            for (const auto& o : ops) {
+                if (isPunct(o.first)) {
+                    const Token op = m_lex.next();
+                    return new AstAssignCompound{o.second, op.fl, lhsp, parseExpr()};
+                }
+            }
+        }
+        if (isPunct("++") || isPunct("--")) {  // finc_or_dec_expression (verilog.y:3594, 3822-3826)
             const Token op = m_lex.next();
-            return new AstAssignCompound{op.text == "+=" ? AstAssignCompound::Add : AstAssignCompound::Sub,
-                                         op.fl, lhsp, parseExpr()};
+            AstNodeExpr* const exprp = op.text == "++" ? static_cast<AstNodeExpr*>(new AstPostInc{op.fl, lhsp})
+                                                       : static_cast<AstNodeExpr*>(new AstPostDec{op.fl, lhsp});
+            return new AstStmtExpr{lhsp->fileline(), exprp};
         }
         syntaxError(m_lex.peek(), "'=' or '<='");
     }
