@@ -792,6 +792,122 @@ struct VlcuMdArray final {
     VLCU_HD constexpr size_t size() const { return N_Dim0; }
 };
 
+//=========================================================================
+// Tiled model image (designs V3EmitCuda prints in the tiled form: module hierarchy kept, or more
+// state than a thread's registers hold).  The state block is an array of TILES; a tile is the
+// design's <prefix>__Syms struct -- one struct per scope, as in the C++ model -- in which every
+// member is widened to VLCU_TILE slots, one per instance of the tile:
+//
+//     instance i, member m of scope s  ->  base + (i / VLCU_TILE) * sizeof(Syms)
+//                                               + offsetof(Syms, s) + offsetof(Class(s), m)
+//                                               + (i % VLCU_TILE) * sizeof(T)
+//
+// A tile is a warp: the 32 lanes' accesses to a scalar member are one contiguous 32*sizeof(T)-byte
+// run at a compile-time offset from the tile's base, so a member access is ONE load or store with
+// an immediate offset -- no address arithmetic per access, and all members provably distinct.  A
+// warp's whole working set is one contiguous block of HBM (sizeof(Syms) bytes).
+#ifndef VLCU_TILE
+#define VLCU_TILE 32
+#endif
+#if defined(__CUDACC__)
+#define VLCU_DN __device__ __noinline__
+#else
+#define VLCU_DN
+#endif
+
+// This thread's slot in its tile (VLCU_BLOCK is a multiple of VLCU_TILE)
+VLCU_HD uint32_t vlcu_lane() {
+#ifdef __CUDA_ARCH__
+    return threadIdx.x % VLCU_TILE;
+#else
+    return 0;
+#endif
+}
+
+// One value per instance of the tile.  Emitted code names the slot explicitly (`sig.v[vlLane]`);
+// the conversions are for the few places where EmitCFunc prints a variable without going through
+// the AstVarRef visitor (V3EmitCFunc.h:320-345: wide constants assigned in place;
+// V3EmitCFunc.cpp:524-666: the literal text of _ctor_var_reset).
+template <typename T_Value>
+struct VlcuLanes final {
+    T_Value v[VLCU_TILE];
+    VLCU_HD operator T_Value&() { return v[vlcu_lane()]; }
+    VLCU_HD operator const T_Value&() const { return v[vlcu_lane()]; }
+    template <typename T_Rhs>
+    VLCU_HD void operator=(const T_Rhs& rhs) { v[vlcu_lane()] = static_cast<T_Value>(rhs); }
+    template <typename T_Index>
+    VLCU_HD auto operator[](T_Index index) -> decltype((v[0][index])) { return v[vlcu_lane()][index]; }
+};
+template <size_t N_Words>
+struct VlcuLanes<VlWide<N_Words>> final {
+    VlWide<N_Words> v[VLCU_TILE];
+    VLCU_HD operator VlWide<N_Words>&() { return v[vlcu_lane()]; }
+    VLCU_HD operator EData*() { return v[vlcu_lane()].data(); }
+    VLCU_HD operator const EData*() const { return v[vlcu_lane()].data(); }
+    VLCU_HD EData& operator[](size_t index) { return v[vlcu_lane()][index]; }
+};
+
+// A large array kept [element][lane]: an index that is the same in all lanes of a warp (a loop
+// counter) touches one contiguous run.  `arr.lane(vlLane)[i]` is element i of this instance.
+template <typename T_Value, size_t N_Depth>
+struct VlcuLaneArray final {
+    T_Value m[N_Depth][VLCU_TILE];
+    struct View final {
+        T_Value* m_basep;  // &m[0][lane]
+        VLCU_HD T_Value& operator[](size_t index) const { return m_basep[index * VLCU_TILE]; }
+        VLCU_HD constexpr size_t size() const { return N_Depth; }
+        template <class T_Other>
+        VLCU_HD bool neq(const T_Other& that) const {
+            bool differs = false;
+            for (size_t i = 0; i < N_Depth; ++i) differs |= ((*this)[i] != that[i]);
+            return differs;
+        }
+        template <class T_Other>
+        VLCU_HD void assign(const T_Other& that) const {
+            for (size_t i = 0; i < N_Depth; ++i) (*this)[i] = that[i];
+        }
+        // `a = b` between two arrays of the model copies the ELEMENTS
+        VLCU_HD const View& operator=(const View& that) const {
+            assign(that);
+            return *this;
+        }
+        template <class T_Other>
+        VLCU_HD bool operator!=(const T_Other& that) const { return neq(that); }
+        template <class T_Other>
+        VLCU_HD bool operator==(const T_Other& that) const { return !neq(that); }
+    };
+    VLCU_HD View lane(uint32_t lane) { return View{&m[0][lane]}; }
+    VLCU_HD T_Value& operator[](size_t index) { return m[index][vlcu_lane()]; }
+};
+
+// A cell of a module class (the C++ model holds `Vtop_sub* cell`, V3EmitCHeaders.cpp:63-72): the
+// child scope's struct lies at the same distance from the parent scope's struct in every tile and
+// for every instance of the parent class (V3EmitCuda orders Syms depth first), so `cell->sig` is
+// pointer arithmetic on `this`.  T_Info (defined once Syms is complete) gives the member's own
+// offset in the parent and the distance between the two structs.
+template <class T_Child, class T_Info>
+struct VlcuCell final {
+    VLCU_HD T_Child* operator->() {
+        return reinterpret_cast<T_Child*>(reinterpret_cast<char*>(this) - T_Info::kSelf + T_Info::kDelta);
+    }
+    VLCU_HD operator T_Child*() { return operator->(); }
+};
+
+// vlSymsp->_vm_contextp__->... in literal C text of a tiled model (cf. VlcuSymsCtxShim): the
+// queries have run-time-default answers and need no context
+struct VlcuSymsCtxTiled final {
+    VLCU_HD uint32_t assertCtlGet(VerilatedAssertCtlQuery query, uint32_t types, uint32_t directives) const {
+        if (!types || !directives) return 0;
+        return query == VerilatedAssertCtlQuery::ASSERT_CTL_KILL ? 0U : 1U;
+    }
+    VLCU_HD int debug() const { return 0; }
+    VLCU_HD const VlcuSymsCtxTiled* operator->() const { return this; }
+};
+
+// Byte offset, inside a tile, of lane 0 of member `member` of scope `scope`
+#define VLCU_TILE_OFF(Syms, scope, member) \
+    static_cast<uint32_t>(__builtin_offsetof(Syms, scope) + __builtin_offsetof(decltype(Syms::scope), member))
+
 // Everything a kernel needs to find one model's data
 struct VlcuModelDev final {
     VlcuState state;

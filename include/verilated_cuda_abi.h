@@ -124,12 +124,18 @@ typedef struct {
     uint32_t trace_stream_words;
     void* trace_out;
     uint64_t trace_evals;
-    /* parameters interpreted by the design-specific testbench */
+    /* parameters interpreted by the design-specific testbench; the built-in "fuzz" testbench
+       (random stimulus made in the kernel, include/verilated_cuda_launch.h VlcuTbFuzz) takes
+       tb_seed, tb_flags = VLCU_TBF_FUZZ_*, tb_arg[0] = clock periods of reset, tb_arg[1] = bit
+       mask of the input row words that are sparse (non-zero in 1 period of 32) */
     uint64_t tb_seed;
     uint32_t tb_flags;
     uint32_t tb_arg[4];
     uint32_t pad3_;
 } vlcu_run_desc_t;
+#define VLCU_TBF_FUZZ_RESET_LOW 0x1u  /* input row word 1 is an active-low reset */
+#define VLCU_TBF_FUZZ_RESET_HIGH 0x2u /* ... an active-high reset */
+#define VLCU_TBF_FUZZ_UNIFORM 0x4u    /* all instances see the same stimulus */
 
 /* ---- library ---------------------------------------------------------- */
 int vlcu_abi_version(void);
@@ -234,6 +240,11 @@ const char* vlcu_message_format(const vlcu_model_t* h, uint32_t id);
 /* All persistent members of one instance, packed at their vlcu_member_offset() */
 int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_bytes);
 uint32_t vlcu_member_offset(const vlcu_model_t* h, int member);
+/* Instances per tile of the model image: 0 for a structure-of-arrays design (every member is one
+   [element][instance] array over the padded shard), else the design was printed in the tiled
+   form (include/verilated_cuda.h "Tiled model image") and its state block is an array of tiles of
+   vlcu_state_bytes() * vlcu_tile() bytes.  Only vlcu_member_device_ptr() users need to know. */
+uint32_t vlcu_tile(const vlcu_model_t* h);
 
 /* One instance as a verilated_save image (include/verilated_save.h:193-223): the file
    `VerilatedSave os; os.open(f); os << *top;` writes for a --savable build of the same design,

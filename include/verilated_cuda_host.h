@@ -90,11 +90,15 @@ struct VlcuMemberDesc final {
     const char* hierName;  // Verilog hierarchical name (for tracing), or nullptr
     uint8_t kind;
     uint8_t elemBytes;  // 1 CData, 2 SData, 4 IData/EData, 8 QData
-    uint16_t traceCode;  // first VCD code (0 = not traced)
+    uint16_t flags;  // VLCU_MEMBERF_*
     uint32_t elems;  // words of a VlWide, depth of an array, else 1
     uint32_t width;  // bits (of one array element)
     int32_t msb, lsb;  // declared range
-    uint32_t soaOffset;  // byte offset per instance in the SoA block
+    uint32_t soaOffset;  // SoA designs: byte offset per instance in the SoA block (the member starts at
+                         // soaOffset * npad); tiled designs: byte offset of lane 0 inside a tile
+};
+enum : uint16_t {
+    VLCU_MEMBERF_LANE_MAJOR = 1u << 0,  // the elements of one instance are contiguous ([lane][element])
 };
 
 struct VlcuCoverPoint final {  // arguments of __vlCoverInsert / __vlCoverToggleInsert
@@ -204,6 +208,10 @@ struct VlcuDesignInfo final {
     // what the Syms constructor passes to VerilatedContext::timeunit()/timeprecision()
     // (V3EmitCSyms.cpp:1191-1199), as the context stores them: -power of ten; -1 = not set
     int saveTimeunit, saveTimeprecision;
+    // 0: structure of arrays over the whole shard (member m, element e, instance i at
+    //    soaOffset*npad + (e*npad + i)*elemBytes).  Else the model image is tiled: `tile` instances
+    //    per tile of stateBytes*tile bytes (verilated_cuda.h "Tiled model image")
+    uint32_t tile;
 };
 enum : uint32_t {
     VLCU_SAVE_ACTIVITY = 1u << 0,  // Syms::__Vserialize writes __Vm_activity first (--trace builds)

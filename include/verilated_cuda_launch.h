@@ -69,6 +69,54 @@ struct VlcuTbTrace final {
     }
 };
 
+// Random stimulus made in the kernel -- a fuzz campaign needs no stimulus rows at all.  Before
+// eval e (clock period c = e / 2) input word w of instance i is a hash of (tbSeed, i's seed, c, w):
+//   word 0    the clock: 1 on even evals, 0 on odd ones (rising edge first, sim_main.cpp:73-76)
+//   word 1    with VLCU_FUZZ_RESET_LOW / _HIGH: the reset, asserted for the first tbArg[0] periods
+//   tbArg[1]  bit w set: word w is "sparse", non-zero in 1 period out of 32 (interrupt pins)
+//   VLCU_FUZZ_UNIFORM: every instance sees the same stimulus (they differ by --x-initial only,
+//   BASELINE config 3)
+// Ports are masked to their widths by load_inputs_row.  The hash is restated in
+// tests/oracle_util.py (fuzz_rows) for the CPU side.
+enum : uint32_t {
+    VLCU_FUZZ_RESET_LOW = 1u << 0,
+    VLCU_FUZZ_RESET_HIGH = 1u << 1,
+    VLCU_FUZZ_UNIFORM = 1u << 2,
+};
+VLCU_HD uint64_t vlcu_fuzz_mix(uint64_t x) {
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+VLCU_HD uint64_t vlcu_fuzz_draw(uint64_t key, uint64_t period, uint32_t word) {
+    return vlcu_fuzz_mix(key + period * 0x9e3779b97f4a7c15ULL + (static_cast<uint64_t>(word) + 1U) * 0xd1342543de82ef95ULL);
+}
+struct VlcuTbFuzz final {
+    static constexpr const char* name() { return "fuzz"; }
+    template <class T_Design>
+    VLCU_D static void begin(typename T_Design::Root&, VlcuContext&, const VlcuRunDev&, uint64_t,
+                             uint64_t) {}
+    template <class T_Design>
+    VLCU_D static void drive(typename T_Design::Root& root, VlcuContext& ctx, const VlcuRunDev& r,
+                             uint64_t, uint64_t e) {
+        ctx.timeInc(1);
+        constexpr uint32_t kWords = T_Design::kInWords ? T_Design::kInWords : 1;
+        uint32_t row[kWords];
+        const uint64_t period = e >> 1;
+        const uint64_t key = r.tbSeed ^ ((r.tbFlags & VLCU_FUZZ_UNIFORM) ? 0 : vlcu_fuzz_mix(ctx.randSeed() + 1U));
+        VLCU_UNROLL
+        for (uint32_t w = 0; w < kWords; ++w) {
+            const uint64_t draw = vlcu_fuzz_draw(key, period, w);
+            const bool sparse = w < 32 && ((r.tbArg[1] >> w) & 1U);
+            row[w] = (sparse && (draw & 0x1f) != 0) ? 0U : static_cast<uint32_t>(draw >> 32);
+        }
+        row[0] = static_cast<uint32_t>(e & 1U) ^ 1U;
+        if (kWords > 1 && (r.tbFlags & VLCU_FUZZ_RESET_LOW)) row[kWords > 1 ? 1 : 0] = period >= r.tbArg[0];
+        if (kWords > 1 && (r.tbFlags & VLCU_FUZZ_RESET_HIGH)) row[kWords > 1 ? 1 : 0] = period < r.tbArg[0];
+        T_Design::load_inputs_row(root, row, 1, 0);
+    }
+};
+
 //=========================================================================
 // Kernels
 
@@ -153,7 +201,7 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
     }
     uint64_t evalsDone = 0;
     if (!kObserve) {
-        // Runs longer than 2^32 evals are split by the host (vlcu_run)
+        // (tryRun sends runs of 2^32 evals or more to the kObserve form, whose trip count is 64 bits)
         const uint32_t nEvals = static_cast<uint32_t>(r.nEvals);
         for (uint32_t e = 0; e < nEvals; ++e) {
             T_Tb::template drive<T_Design>(root, ctx, r, inst, r.evalBase + e);
@@ -283,9 +331,14 @@ struct VlcuStreamCfg final {
     static constexpr uint32_t kOutStage = (T_Design::kOutWords ? T_Design::kOutWords : 1) * VLCU_BLOCK;
     static constexpr uint32_t kStageBytes = 4 * (kInStage + kOutStage);
     // per-CTA budget: 28 KB at the default 7 CTAs per SM, less when more CTAs are to be resident
-    static constexpr uint32_t kBudget = VLCU_MIN_BLOCKS <= 7 ? 28672U : (227U * 1024U / VLCU_MIN_BLOCKS - 1024U - 512U);
+    // (what the design's own shared-memory arrays take comes off the budget; statically allocated
+    // shared memory is limited to 48 KB per CTA)
+    static constexpr uint32_t kShared = static_cast<uint32_t>(sizeof(typename T_Design::Shared));
+    static constexpr uint32_t kGross = VLCU_MIN_BLOCKS <= 7 ? 28672U : (227U * 1024U / VLCU_MIN_BLOCKS - 1024U - 512U);
+    static constexpr uint32_t kBudget = kGross > kShared ? kGross - kShared : 0U;
     static constexpr int kDepth = kStageBytes * 8 <= kBudget ? 8 : kStageBytes * 4 <= kBudget ? 4 : 2;
-    static constexpr bool kFits = kStageBytes * 2 + sizeof(typename T_Design::Shared) <= 40960;
+    // a tiled design keeps its ports in the tile image: rows are read / written in place
+    static constexpr bool kFits = !T_Design::kTiled && kStageBytes * kDepth + kShared + 256U <= 48U * 1024U;
 };
 
 template <class T_Design, bool kObs, bool kTensor>
@@ -473,13 +526,14 @@ public:
                           cudaStream_t stream) const override {
         cudaError_t err = cudaErrorInvalidValue;
         const bool found = ((tryRun<VlcuTbNone>(tb, m, r, stream, err)
-                             || tryRun<VlcuTbTrace>(tb, m, r, stream, err))
+                             || tryRun<VlcuTbTrace>(tb, m, r, stream, err)
+                             || tryRun<VlcuTbFuzz>(tb, m, r, stream, err))
                             || ... || tryRun<T_Tbs>(tb, m, r, stream, err));
         return found ? err : cudaErrorInvalidValue;
     }
-    int tbCount() const override { return 2 + static_cast<int>(sizeof...(T_Tbs)); }
+    int tbCount() const override { return 3 + static_cast<int>(sizeof...(T_Tbs)); }
     const char* tbName(int i) const override {
-        const char* names[] = {VlcuTbNone::name(), VlcuTbTrace::name(), T_Tbs::name()...};
+        const char* names[] = {VlcuTbNone::name(), VlcuTbTrace::name(), VlcuTbFuzz::name(), T_Tbs::name()...};
         return (i >= 0 && i < tbCount()) ? names[i] : nullptr;
     }
 };

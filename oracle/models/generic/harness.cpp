@@ -8,6 +8,8 @@
 // before eval e every input port is loaded from stimulus row e ([eval][input word][instance],
 // ports in source order, one 32-bit word per limb, values masked to the port width), time
 // advances by one unit, eval(), and every output port is stored to observation row e.
+// The second entry point (-DHARNESS_FUZZ_FN=vlref_<design>_fuzz) plays the "fuzz" testbench
+// (VlcuTbFuzz): the stimulus rows are made here, per instance and eval, from the same hash.
 #include VTOP_H
 #include "ref_timing.h"
 
@@ -72,10 +74,33 @@ struct Params {
     uint64_t n, instBase, seedBase;
     int randReset;
     uint64_t nEvals;
-    const uint32_t* stim;  // [eval][kInWords][n]
+    const uint32_t* stim;  // [eval][kInWords][n], or null: fuzz
     uint32_t* obs;  // [eval][kOutWords][n]
     uint64_t* sigs;
+    // fuzz testbench (VlcuTbFuzz of include/verilated_cuda_launch.h, restated)
+    uint64_t tbSeed = 0;
+    uint32_t tbFlags = 0, resetPeriods = 0, sparseMask = 0;
+    uint64_t obsEvals = ~0ULL;
 };
+
+inline uint64_t fuzzMix(uint64_t x) {
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+    return x ^ (x >> 31);
+}
+void fuzzRow(const Params& p, uint64_t randSeed, uint64_t e, uint32_t* row) {
+    const uint64_t period = e >> 1;
+    const uint64_t key = p.tbSeed ^ ((p.tbFlags & 4U) ? 0 : fuzzMix(randSeed + 1U));
+    for (int w = 0; w < kInWords; ++w) {
+        const uint64_t draw
+            = fuzzMix(key + period * 0x9e3779b97f4a7c15ULL + (static_cast<uint64_t>(w) + 1U) * 0xd1342543de82ef95ULL);
+        const bool sparse = w < 32 && ((p.sparseMask >> w) & 1U);
+        row[w] = (sparse && (draw & 0x1f) != 0) ? 0U : static_cast<uint32_t>(draw >> 32);
+    }
+    row[0] = static_cast<uint32_t>(e & 1U) ^ 1U;
+    if (kInWords > 1 && (p.tbFlags & 1U)) row[1] = period >= p.resetPeriods;
+    if (kInWords > 1 && (p.tbFlags & 2U)) row[1] = period < p.resetPeriods;
+}
 
 void runOne(const Params& p, uint64_t i) {
     const std::unique_ptr<VerilatedContext> contextp{new VerilatedContext};
@@ -89,10 +114,13 @@ void runOne(const Params& p, uint64_t i) {
     const VlrefLoopTimer timer;
     for (uint64_t e = 0; e < p.nEvals; ++e) {
         contextp->timeInc(1);
-        const uint32_t* rowp = p.stim + e * kInWords * p.n + i;
+        uint32_t fuzz[kInWords > 0 ? kInWords : 1];
+        const uint32_t* rowp = p.stim ? p.stim + e * kInWords * p.n + i : fuzz;
+        const uint64_t stride = p.stim ? p.n : 1;
+        if (!p.stim) fuzzRow(p, p.seedBase ^ (p.instBase + i), e, fuzz);
         int k = 0;
 #define VLCU_PORT_IN(name, width, words) \
-    setPort(top->name, width, rowp + static_cast<uint64_t>(k) * p.n, p.n); \
+    setPort(top->name, width, rowp + static_cast<uint64_t>(k) * stride, stride); \
     k += words;
 #define VLCU_PORT_OUT(name, width, words)
 #include PORTS_INC
@@ -111,7 +139,7 @@ void runOne(const Params& p, uint64_t i) {
         uint32_t acc = 0x811c9dc5U;
         for (int j = 0; j < kOutWords; ++j) acc = sigWord(acc, w[j]);
         sig = sigMix(sig, acc);
-        if (p.obs) {
+        if (p.obs && e < p.obsEvals) {
             uint32_t* const orowp = p.obs + e * kOutWords * p.n + i;
             for (int j = 0; j < kOutWords; ++j) orowp[static_cast<uint64_t>(j) * p.n] = w[j];
         }
@@ -121,6 +149,9 @@ void runOne(const Params& p, uint64_t i) {
 }
 }  // namespace
 
+namespace {
+int runAll(const Params& p, int threads);
+}
 extern "C" int HARNESS_FN(uint64_t n, uint64_t instBase, uint64_t seedBase, int randReset,
                           uint64_t nEvals, const uint32_t* stim, uint32_t* obs, uint64_t* sigs,
                           int* inWords, int* outWords, int threads) {
@@ -128,6 +159,25 @@ extern "C" int HARNESS_FN(uint64_t n, uint64_t instBase, uint64_t seedBase, int 
     if (outWords) *outWords = kOutWords;
     if (!stim) return 0;  // query only
     const Params p{n, instBase, seedBase, randReset, nEvals, stim, obs, sigs};
+    return runAll(p, threads);
+}
+#ifdef HARNESS_FUZZ_FN
+extern "C" int HARNESS_FUZZ_FN(uint64_t n, uint64_t instBase, uint64_t seedBase, int randReset,
+                               uint64_t nEvals, uint64_t tbSeed, uint32_t tbFlags, uint32_t resetPeriods,
+                               uint32_t sparseMask, uint32_t* obs, uint64_t obsEvals, uint64_t* sigs,
+                               int threads) {
+    Params p{n, instBase, seedBase, randReset, nEvals, nullptr, obs, sigs};
+    p.tbSeed = tbSeed;
+    p.tbFlags = tbFlags;
+    p.resetPeriods = resetPeriods;
+    p.sparseMask = sparseMask;
+    p.obsEvals = obsEvals;
+    return runAll(p, threads);
+}
+#endif
+namespace {
+int runAll(const Params& p, int threads) {
+    const uint64_t n = p.n;
     vlref_loop_seconds_begin();
     if (threads <= 1) {
         for (uint64_t i = 0; i < n; ++i) runOne(p, i);
@@ -149,3 +199,4 @@ extern "C" int HARNESS_FN(uint64_t n, uint64_t instBase, uint64_t seedBase, int 
     }
     return 0;
 }
+}  // namespace

@@ -320,7 +320,7 @@ public:
 //======================================================================
 // Lexer
 
-enum class Tok : uint8_t { END, ID, SYSID, NUM, STR, PUNCT };
+enum class Tok : uint8_t { END, ID, SYSID, NUM, STR, PUNCT, PRAGMA };
 
 struct Token final {
     Tok kind = Tok::END;
@@ -336,6 +336,8 @@ class Lexer final {
     std::string m_filename;
     FileLine* const m_baseFl;
     std::deque<Token> m_ahead;
+    std::string m_pragma;  // "no_inline_module" / "inline_module" seen by skipSpace()
+    size_t m_pragmaBegin = 0;
 
     FileLine* makeFl(size_t begin, size_t end) const {
         FileLine* const fl = new FileLine{m_baseFl};
@@ -361,6 +363,25 @@ class Lexer final {
             } else if (c == '/' && m_pos + 1 < m_src.size() && m_src[m_pos + 1] == '/') {
                 while (m_pos < m_src.size() && m_src[m_pos] != '\n') ++m_pos;
             } else if (c == '/' && m_pos + 1 < m_src.size() && m_src[m_pos + 1] == '*') {
+                // /*verilator no_inline_module*/ and /*verilator inline_module*/ (verilog.l:832-839;
+                // V3PreProc::comment accepts surrounding blanks): the only meta-comments this
+                // front end turns into tokens, all others stay comments
+                {
+                    const size_t end = m_src.find("*/", m_pos + 2);
+                    if (end != std::string::npos) {
+                        std::string text = m_src.substr(m_pos + 2, end - m_pos - 2);
+                        while (!text.empty() && std::isspace(static_cast<unsigned char>(text.back()))) text.pop_back();
+                        size_t lead = 0;
+                        while (lead < text.size() && std::isspace(static_cast<unsigned char>(text[lead]))) ++lead;
+                        text.erase(0, lead);
+                        if (text == "verilator no_inline_module" || text == "verilator inline_module") {
+                            m_pragma = text.substr(10);
+                            m_pragmaBegin = m_pos;
+                            m_pos = end + 2;
+                            return;
+                        }
+                    }
+                }
                 m_pos += 2;
                 while (m_pos + 1 < m_src.size() && !(m_src[m_pos] == '*' && m_src[m_pos + 1] == '/')) {
                     if (m_src[m_pos] == '\n') {
@@ -399,12 +420,20 @@ class Lexer final {
     Token lexOne() {
         skipSpace();
         Token t;
+        if (!m_pragma.empty()) {  // a meta-comment skipSpace() stopped behind
+            t.kind = Tok::PRAGMA;
+            t.text = m_pragma;
+            t.fl = makeFl(m_pragmaBegin, m_pos);
+            m_pragma.clear();
+            return t;
+        }
         if (m_pos >= m_src.size()) {
             t.fl = makeFl(m_pos, m_pos);
             return t;
         }
         const size_t begin = m_pos;
         const char c = m_src[m_pos];
+
         if (isIdStart(c)) {
             while (m_pos < m_src.size() && isIdChar(m_src[m_pos])) ++m_pos;
             t.kind = Tok::ID;
@@ -999,6 +1028,11 @@ class Parser final {
         if (t.kind == Tok::PUNCT && t.text == ";") {
             m_lex.next();
             return nullptr;
+        }
+        if (t.kind == Tok::PRAGMA) {  // verilog.y:2727-2728 (yVL_INLINE_MODULE / yVL_NO_INLINE_MODULE)
+            const Token kw = m_lex.next();
+            return new AstPragma{kw.fl, kw.text == "inline_module" ? VPragmaType::INLINE_MODULE
+                                                                   : VPragmaType::NO_INLINE_MODULE};
         }
         if (t.kind != Tok::ID) syntaxError(t, "module item");
         if (t.text == "parameter" || t.text == "localparam") {

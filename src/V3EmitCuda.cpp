@@ -25,8 +25,22 @@
 //        VL_FINISH_MT/VL_STOP_MT/VL_FATAL_MT, VL_TIME_UNITED_Q, VL_SCOPED_RAND_RESET_*,
 //        vlSymsp->_vm_contextp__->...  are macros / a shim of verilated_cuda.h
 //
-// The model must be a single $root class (the default for small designs; pass --flatten
-// otherwise); non-inlined child module classes are reported as unsupported.
+// Two forms of the model image, chosen per design (--cuda-stream / --no-cuda-stream, default: by
+// size and hierarchy):
+//
+//   register form   a single $root class whose scalars fit a thread's registers: the image is a
+//                   struct of the thread, loaded from / stored to the SoA block once per launch.
+//   tiled form      designs with non-inlined module instances (V3Descope.cpp:95-125,
+//                   V3EmitCHeaders.cpp:63-72) or with more state than a thread can hold: the image
+//                   stays in HBM.  Every module class becomes a struct whose members are
+//                   VlcuLanes<T> = T[VLCU_TILE], one slot per instance of a TILE of VLCU_TILE
+//                   instances; <prefix>__Syms holds one such struct per scope, exactly as the C++
+//                   Vtop__Syms does, and is the image of one tile.  A member access
+//                   `vlSelfRef.sig.v[vlLane]` is then base + constant + lane*sizeof(T): one
+//                   coalesced, immediate-offset load or store per warp, no address arithmetic, and
+//                   ptxas can tell all members apart.  Functions of a module class take the
+//                   scope's struct (vlSelf) and the tile (vlSymsp), so code is shared between the
+//                   instances of a module the way the C++ model shares it.
 //*************************************************************************
 
 #include "V3PchAstNoMT.h"
@@ -42,6 +56,7 @@
 #include "V3String.h"
 
 #include <fstream>
+#include <functional>
 #include <map>
 #include <set>
 #include <sstream>
@@ -50,7 +65,7 @@ VL_DEFINE_DEBUG_FUNCTIONS;
 
 namespace {
 
-enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL, INTERLEAVED, COVER };
+enum class CudaStorage : uint8_t { REG, SHARED, LOCAL, GLOBAL, INTERLEAVED, COVER, LANES };
 
 struct CudaMember final {
     const AstVar* varp = nullptr;
@@ -69,6 +84,8 @@ struct CudaMember final {
     uint32_t offset = 0;
     string elemCType;  // CData SData IData QData (EData for wide limbs)
     string elemDecl;  // C type of one element as the model declares it
+    string memType;  // tiled form: type of one instance's value in memory (VlUnpacked<VlcuMem8, 4> ...)
+    bool laneMajor = false;  // tiled form: the elements of one instance are contiguous
     uint32_t elems() const { return depth * words; }
     uint32_t bytes() const { return elems() * elemBytes; }
 };
@@ -155,12 +172,38 @@ public:
     }
 };
 
+// Tiled form: a non-root module class and one of its instances (AstScope)
+struct CudaClass final {
+    const AstNodeModule* modp = nullptr;
+    string name;  // Vtop_sub
+    std::vector<CudaMember> members;
+};
+struct CudaScopeInst final {
+    const AstScope* scopep = nullptr;
+    size_t classIdx = 0;  // into m_subClasses
+    string sym;  // member of <prefix>__Syms: TOP__top__DOT__sub
+    string pretty;  // what the Syms constructor passes to ctor(): "top.sub"
+};
+// One row of the host member table
+struct CudaFlatMember final {
+    CudaMember m;
+    string tableName;  // root: the member's name; other scopes: <sym>.<name>
+    string offsetExpr;  // C++ expression of the member's byte offset
+};
+
 class EmitCudaModel final : public EmitCFunc {
     // STATE
     const AstNodeModule* const m_topModp;
     const string m_rootName;  // Vtop___024root
     const string m_designName;  // Vtop__cuda
-    std::vector<CudaMember> m_members;
+    const string m_symsName;  // Vtop__Syms (tiled form)
+    bool m_stream = false;  // tiled form: the image stays in HBM
+    std::vector<CudaMember> m_members;  // of the root class
+    std::vector<CudaClass> m_subClasses;  // tiled form: the other module classes
+    std::vector<CudaScopeInst> m_scopeInsts;  // ... and their instances, in Syms order
+    std::set<const AstVar*> m_laneVars;  // tiled form: members stored as VlcuLanes<T>
+    std::set<const AstVar*> m_laneArrayVars;  // ... as VlcuLaneArray<T, N> ([element][lane])
+    std::vector<CudaFlatMember> m_flat;  // the host member table
     std::map<const AstVar*, size_t> m_memberOf;
     std::set<const AstVar*> m_dataIndexed;  // arrays with an index that differs between instances
     std::set<const AstVar*> m_wholeRef;  // arrays some function takes as a whole (VlUnpacked<>& parameter)
@@ -196,7 +239,18 @@ class EmitCudaModel final : public EmitCFunc {
     }
 
     // ---- layout ----------------------------------------------------------------
-    void analyzeVar(const AstVar* varp, const std::set<const AstVar*>& runtimeIndexed) {
+    // Type of one instance's value of a member in memory (tiled form): the C++ model's type with
+    // 1/2-byte storage classes for narrow elements
+    static string memTypeOf(const AstNodeDType* dtp) {
+        dtp = dtp->skipRefp();
+        if (const AstUnpackArrayDType* const adtp = VN_CAST(dtp, UnpackArrayDType)) {
+            return "VlUnpacked<" + memTypeOf(adtp->subDTypep()) + ", " + cvtToStr(adtp->elementsConst()) + ">";
+        }
+        if (dtp->isWide()) return "VlWide<" + cvtToStr(dtp->widthWords()) + ">";
+        return dtp->width() <= 8 ? "VlcuMem8" : dtp->width() <= 16 ? "VlcuMem16" : dtp->width() <= 32 ? "IData" : "QData";
+    }
+    void analyzeVar(const AstVar* varp, const std::set<const AstVar*>& runtimeIndexed,
+                    std::vector<CudaMember>& out) {
         CudaMember m;
         m.varp = varp;
         m.name = varp->nameProtect();
@@ -212,6 +266,10 @@ class EmitCudaModel final : public EmitCFunc {
             for (const AstNodeDType* tp = qdtp->subDTypep()->skipRefp(); VN_IS(tp, UnpackArrayDType);
                  tp = VN_AS(tp, UnpackArrayDType)->subDTypep()->skipRefp()) {
                 elems *= VN_AS(tp, UnpackArrayDType)->elementsConst();
+            }
+            if (m_stream) {
+                varp->v3warn(E_UNSUPPORTED, "Unsupported: --cuda-stream: NBA commit queue " << varp->prettyNameQ());
+                return;
             }
             const uint32_t capacity = std::min<uint32_t>(std::max<uint32_t>(2 * elems, 16), 256);
             string type = dtp->cType("", false, false);
@@ -260,6 +318,25 @@ class EmitCudaModel final : public EmitCFunc {
         } else {
             m.elemBytes = 8, m.elemCType = "QData";
         }
+        if (m_stream) {
+            // Tiled form: everything stays in HBM.  Scalars are [lane]; wide values and arrays keep
+            // one instance's elements together ([lane][element]: consecutive accesses of ONE
+            // instance share sectors, as VlcuGlobalArray does), except large arrays whose run-time
+            // indices are the same in all instances (loop counters), which are [element][lane]
+            m.memType = memTypeOf(varp->dtypep());
+            m.storage = CudaStorage::LANES;
+            m.laneMajor = m.isArray || m.isWide;
+            if (m.isArray && !m.isWide && m.dims.size() == 1 && m.bytes() > 2048 && !m_dataIndexed.count(varp)
+                && V3EmitCuda::layoutSelection()) {
+                m.storage = CudaStorage::INTERLEAVED;
+                m.laneMajor = false;
+                m_laneArrayVars.insert(varp);
+            } else {
+                m_laneVars.insert(varp);
+            }
+            out.push_back(m);
+            return;
+        }
         if (m.isArray) {
             // Where a per-instance array lives (DESIGN.md "run-time indexed arrays"):
             //   registers      small and only ever indexed with constants (trigger vectors)
@@ -274,7 +351,12 @@ class EmitCudaModel final : public EmitCFunc {
                 m.storage = CudaStorage::REG;
             } else if (!runtime && m.elems() <= 16 && m.dims.size() == 1) {
                 m.storage = CudaStorage::REG;
-            } else if (runtime && bytes <= 256 && !m.isWide) {
+            } else if (runtime && bytes <= 256 && !m.isWide
+                       && m_sharedBytes + m.depth * 4U * 64U <= 16384U) {
+                // (a shared element is a 32-bit register image of the value, one column per thread
+                // of the 64-thread CTA; all shared arrays of a design together stay below 16 KB so
+                // that seven CTAs and the port-row stages still fit an SM)
+                m_sharedBytes += m.depth * 4U * 64U;
                 m.storage = CudaStorage::SHARED;
             } else if (bytes <= 2048) {
                 m.storage = CudaStorage::LOCAL;
@@ -289,24 +371,98 @@ class EmitCudaModel final : public EmitCFunc {
                 if (!m.isWide && m.elemBytes < 4) m.elemDecl = m.elemCType;  // HBM layout = host layout
             }
         }
-        m_members.push_back(m);
+        out.push_back(m);
     }
-    void computeLayout() {
+    // The members of one module class, as EmitCHeader::emitDesignVarDecls selects them
+    // (V3EmitCHeaders.cpp:133-135)
+    void analyzeModule(const AstNodeModule* modp, std::vector<CudaMember>& out) {
         std::set<const AstVar*> runtimeIndexed;
-        { const CudaIndexVisitor visitor{m_topModp, runtimeIndexed, m_dataIndexed, m_wholeRef}; }
-        for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+        { const CudaIndexVisitor visitor{modp, runtimeIndexed, m_dataIndexed, m_wholeRef}; }
+        for (const AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
             if (const AstVar* const varp = VN_CAST(nodep, Var)) {
-                // Same test as EmitCHeader::emitDesignVarDecls (V3EmitCHeaders.cpp:133-135)
                 if (varp->isIO() || varp->isSignal() || varp->isClassMember() || varp->isTemp()
                     || varp->isGenVar()) {
                     if (varp->isStatic()) continue;
-                    analyzeVar(varp, runtimeIndexed);
+                    analyzeVar(varp, runtimeIndexed, out);
                 }
             } else if (const AstCell* const cellp = VN_CAST(nodep, Cell)) {
-                cellp->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: module instance "
-                                                 << cellp->prettyNameQ()
-                                                 << " was not inlined; use --flatten");
+                if (!m_stream) {
+                    cellp->v3warn(E_UNSUPPORTED, "Unsupported: --no-cuda-stream: module instance "
+                                                     << cellp->prettyNameQ()
+                                                     << " was not inlined; use --flatten");
+                }
             }
+        }
+    }
+    // Register-resident bytes the root class would need in the register form
+    uint32_t registerFormBytes() const {
+        uint32_t bytes = 0;
+        for (const AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            const AstVar* const varp = VN_CAST(nodep, Var);
+            if (!varp || varp->isStatic()) continue;
+            if (!(varp->isIO() || varp->isSignal() || varp->isClassMember() || varp->isTemp() || varp->isGenVar())) continue;
+            const AstNodeDType* const dtp = varp->dtypep()->skipRefp();
+            if (VN_IS(dtp, UnpackArrayDType) || !dtp->isIntegralOrPacked()) continue;
+            bytes += dtp->isWide() ? 4 * dtp->widthWords() : dtp->width() <= 32 ? 4 : 8;
+        }
+        return bytes;
+    }
+    void collectHierarchy() {
+        // Every scope by module, as EmitCSyms collects them (V3EmitCSyms.cpp:745-797)
+        for (const AstNodeModule* modp = v3Global.rootp()->modulesp(); modp; modp = VN_AS(modp->nextp(), NodeModule)) {
+            if (modp == m_topModp || EmitCUtil::isConstPoolMod(modp)) continue;
+            std::vector<const AstScope*> scopes;
+            for (const AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                if (const AstScope* const scopep = VN_CAST(nodep, Scope)) scopes.push_back(scopep);
+            }
+            if (scopes.empty()) continue;
+            CudaClass cls;
+            cls.modp = modp;
+            cls.name = EmitCUtil::prefixNameProtect(modp);
+            m_subClasses.push_back(cls);
+            for (const AstScope* const scopep : scopes) {
+                CudaScopeInst inst;
+                inst.scopep = scopep;
+                inst.classIdx = m_subClasses.size() - 1;
+                inst.sym = protect(scopep->nameDotless());
+                inst.pretty = scopep->prettyName();
+                m_scopeInsts.push_back(inst);
+            }
+        }
+        // Syms order: every scope followed by the scopes below it, depth first and by name.  All
+        // instances of a module class then see their child scopes at the same distance, which is
+        // what lets a cell pointer of the C++ class (`vlSelf->cell->sig`, V3Descope.cpp:95-125)
+        // become a compile-time offset (VlcuCell)
+        std::stable_sort(m_scopeInsts.begin(), m_scopeInsts.end(),
+                         [](const CudaScopeInst& a, const CudaScopeInst& b) { return a.sym < b.sym; });
+        std::vector<CudaScopeInst> ordered;
+        const std::function<void(const AstScope*)> below = [&](const AstScope* parentp) {
+            for (const CudaScopeInst& inst : m_scopeInsts) {
+                if (inst.scopep->aboveScopep() != parentp) continue;
+                ordered.push_back(inst);
+                below(inst.scopep);
+            }
+        };
+        below(v3Global.rootp()->topScopep()->scopep());
+        UASSERT_OBJ(ordered.size() == m_scopeInsts.size(), m_topModp, "--cuda: scope not reachable from the top scope");
+        m_scopeInsts.swap(ordered);
+    }
+    // The scope a cell of `parentp` (an instance of the class that declares the cell) leads to
+    const CudaScopeInst* childScope(const AstScope* parentp, const AstCell* cellp) const {
+        for (const CudaScopeInst& inst : m_scopeInsts) {
+            if (inst.scopep->aboveScopep() == parentp && inst.scopep->aboveCellp() == cellp) return &inst;
+        }
+        return nullptr;
+    }
+    void computeLayout() {
+        collectHierarchy();
+        // Which form: the tiled one when the design keeps a module hierarchy, or when its scalars
+        // would not fit a thread's registers anyway
+        m_stream = V3EmitCuda::streamMode() == 1
+                   || (V3EmitCuda::streamMode() < 0 && (!m_scopeInsts.empty() || registerFormBytes() > 1024));
+        analyzeModule(m_topModp, m_members);
+        if (m_stream) {
+            for (CudaClass& cls : m_subClasses) analyzeModule(cls.modp, cls.members);
         }
         // Coverage bins of this module: the counters are one more (local memory) array
         const_cast<AstNodeModule*>(m_topModp)->foreach([&](AstNodeCoverDecl* declp) {
@@ -341,20 +497,31 @@ class EmitCudaModel final : public EmitCFunc {
         if (m_coverBins) m_members.push_back(m_pendingCoverage);
         m_stateBytes = (offset + 7U) & ~7U;
         // Touched bytes per eval (static)
-        std::map<const AstVar*, std::pair<uint32_t, uint32_t>> sites;
-        { const CudaTouchVisitor visitor{m_topModp, sites}; }
-        for (const CudaMember& m : m_members) {
-            if (!m.varp) continue;
-            const auto it = sites.find(m.varp);
-            if (it == sites.end()) continue;
-            const uint32_t elemBytes = m.words * m.elemBytes;
-            if (m.isArray) {
-                m_touchedRead += std::min(m.bytes(), it->second.first * elemBytes);
-                m_touchedWrite += std::min(m.bytes(), it->second.second * elemBytes);
-            } else {
-                m_touchedRead += it->second.first ? elemBytes : 0;
-                m_touchedWrite += it->second.second ? elemBytes : 0;
+        const auto touched = [this](const AstNodeModule* modp, const std::vector<CudaMember>& members,
+                                    uint32_t instances) {
+            std::map<const AstVar*, std::pair<uint32_t, uint32_t>> sites;
+            { const CudaTouchVisitor visitor{modp, sites}; }
+            for (const CudaMember& m : members) {
+                if (!m.varp) continue;
+                const auto it = sites.find(m.varp);
+                if (it == sites.end()) continue;
+                const uint32_t elemBytes = m.words * m.elemBytes;
+                if (m.isArray) {
+                    m_touchedRead += instances * std::min(m.bytes(), it->second.first * elemBytes);
+                    m_touchedWrite += instances * std::min(m.bytes(), it->second.second * elemBytes);
+                } else {
+                    m_touchedRead += it->second.first ? instances * elemBytes : 0;
+                    m_touchedWrite += it->second.second ? instances * elemBytes : 0;
+                }
             }
+        };
+        touched(m_topModp, m_members, 1);
+        for (size_t c = 0; c < m_subClasses.size(); ++c) {
+            uint32_t instances = 0;
+            for (const CudaScopeInst& inst : m_scopeInsts) instances += inst.classIdx == c;
+            // (members of one scope referenced from another scope's functions are counted where
+            // they are declared, once per instance)
+            touched(m_subClasses[c].modp, m_subClasses[c].members, instances);
         }
         // Member table order: the primary ports first, in source order (= the order of
         // vlcu_port_info() and of the stimulus / observation row words), then everything else
@@ -369,8 +536,23 @@ class EmitCudaModel final : public EmitCFunc {
         for (size_t i = 0; i < m_members.size(); ++i) {
             if (m_members[i].varp) m_memberOf[m_members[i].varp] = i;
         }
+        // The host member table: the root's members, then (tiled form) every other scope's
+        for (const CudaMember& m : m_members) {
+            m_flat.push_back(CudaFlatMember{
+                m, m.name, m_stream ? "VLCU_TILE_OFF(" + m_symsName + ", TOP, " + m.name + ")" : "T::OFF_" + m.name});
+        }
+        for (const CudaScopeInst& inst : m_scopeInsts) {
+            for (const CudaMember& m : m_subClasses[inst.classIdx].members) {
+                CudaFlatMember fm{m, inst.sym + "." + m.name,
+                                  "VLCU_TILE_OFF(" + m_symsName + ", " + inst.sym + ", " + m.name + ")"};
+                fm.m.hier = inst.pretty + "." + m.hier;
+                fm.m.kind = m.kind == 5 ? 5 : 3;  // a port of a sub-module is internal state
+                m_flat.push_back(fm);
+            }
+        }
     }
     CudaMember m_pendingCoverage;
+    uint32_t m_sharedBytes = 0;  // shared memory per CTA the SHARED arrays chosen so far take
     uint32_t m_touchedRead = 0, m_touchedWrite = 0;
     uint32_t m_nSaveOrder = 0;
     uint64_t m_saveCheckval = 0;
@@ -414,6 +596,90 @@ class EmitCudaModel final : public EmitCFunc {
         }
         puts("const char* vlNamep;\n");
         puts("};\n");
+    }
+
+    // ---- tiled form: the module classes and Syms as tile images ----------------------------
+    void emitTileClass(const AstNodeModule* modp, const string& name, const std::vector<CudaMember>& members) {
+        // 256-byte aligned: every 4-byte member of every scope starts a 128-byte line
+        for (const AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (const AstCell* const cellp = VN_CAST(nodep, Cell)) puts("struct " + name + "__cell__" + cellp->nameProtect() + ";\n");
+        }
+        puts("struct alignas(256) " + name + " final {\n");
+        // CELLS (V3EmitCHeaders.cpp:63-72): where the C++ class holds a pointer, the child scope
+        // sits at a fixed distance in the tile
+        for (const AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (const AstCell* const cellp = VN_CAST(nodep, Cell)) {
+                puts("VlcuCell<" + EmitCUtil::prefixNameProtect(cellp->modp()) + ", " + name + "__cell__"
+                     + cellp->nameProtect() + "> " + cellp->nameProtect() + ";\n");
+            }
+        }
+        puts("const char* vlNamep;  // (one per tile, set by the reset kernel)\n");
+        for (const int bytes : {8, 4, 2, 1}) {
+            for (const CudaMember& m : members) {
+                if (m.elemBytes != bytes) continue;
+                if (m.storage == CudaStorage::INTERLEAVED) {
+                    puts("VlcuLaneArray<" + m.elemCType + ", " + cvtToStr(m.depth) + "> " + m.name
+                         + ";  // [element][lane]: instance-uniform indices coalesce\n");
+                } else {
+                    puts("VlcuLanes<" + m.memType + "> " + m.name + ";\n");
+                }
+            }
+        }
+        puts("};\n");
+    }
+    void emitTileStructs() {
+        puts("\n// The model image of one TILE of VLCU_TILE instances: the module classes of the C++ model\n");
+        puts("// (V3EmitCHeaders.cpp:73-143) with every member widened to one slot per instance\n");
+        puts("struct " + m_symsName + ";\n");
+        for (const CudaClass& cls : m_subClasses) puts("struct " + cls.name + ";\n");
+        for (const CudaClass& cls : m_subClasses) emitTileClass(cls.modp, cls.name, cls.members);
+        emitTileClass(m_topModp, m_rootName, m_members);
+        puts("\n// One tile = what Vtop__Syms holds for one instance (V3EmitCSyms.cpp:923-982)\n");
+        puts("struct alignas(256) " + m_symsName + " final {\n");
+        puts(m_rootName + " TOP;\n");
+        for (const CudaScopeInst& inst : m_scopeInsts) {
+            puts(m_subClasses[inst.classIdx].name + " " + inst.sym + ";\n");
+        }
+        puts("VlcuSymsCtxTiled _vm_contextp__;  // vlSymsp->_vm_contextp__->... in literal C text\n");
+        puts("VLCU_D const char* name() const { return \"TOP\"; }\n");
+        puts("};\n");
+        // Cell distances: taken from the class's first instance, checked for the others
+        const auto cellInfos = [this](const AstNodeModule* modp, const string& name,
+                                      const std::vector<std::pair<const AstScope*, string>>& insts) {
+            for (const AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                const AstCell* const cellp = VN_CAST(nodep, Cell);
+                if (!cellp) continue;
+                const string delta0 = [&]() -> string {
+                    const CudaScopeInst* const childp = childScope(insts[0].first, cellp);
+                    UASSERT_OBJ(childp, cellp, "--cuda: cell without a scope");
+                    return "(static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", " + childp->sym
+                           + ")) - static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", " + insts[0].second + ")))";
+                }();
+                puts("struct " + name + "__cell__" + cellp->nameProtect() + " final {\n");
+                puts("static constexpr ptrdiff_t kSelf = __builtin_offsetof(" + name + ", " + cellp->nameProtect() + ");\n");
+                puts("static constexpr ptrdiff_t kDelta = " + delta0 + ";\n");
+                puts("};\n");
+                for (size_t i = 1; i < insts.size(); ++i) {
+                    const CudaScopeInst* const childp = childScope(insts[i].first, cellp);
+                    UASSERT_OBJ(childp, cellp, "--cuda: cell without a scope");
+                    puts("static_assert(static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", " + childp->sym
+                         + ")) - static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", " + insts[i].second + ")) == "
+                         + name + "__cell__" + cellp->nameProtect() + "::kDelta, \"cell distance differs between instances\");\n");
+                }
+            }
+        };
+        cellInfos(m_topModp, m_rootName, {{v3Global.rootp()->topScopep()->scopep(), "TOP"}});
+        for (size_t c = 0; c < m_subClasses.size(); ++c) {
+            std::vector<std::pair<const AstScope*, string>> insts;
+            for (const CudaScopeInst& inst : m_scopeInsts) {
+                if (inst.classIdx == c) insts.emplace_back(inst.scopep, inst.sym);
+            }
+            cellInfos(m_subClasses[c].modp, m_subClasses[c].name, insts);
+        }
+    }
+    // How the glue (port rows, signature) names a member of the root class
+    string rootRef(const CudaMember& m) const {
+        return m_stream ? "s.symsp->TOP." + m.name + ".v[s.lane]" : "s." + m.name;
     }
 
     // ---- SoA load / store ----------------------------------------------------------
@@ -486,14 +752,14 @@ class EmitCudaModel final : public EmitCFunc {
             if (m.isWide) {
                 for (uint32_t w = 0; w < m.words; ++w) {
                     const int bits = (w == m.words - 1) ? (m.width - 32 * w) : 32;
-                    puts("s." + m.name + "[" + cvtToStr(w) + "] = rowp[" + cvtToStr(inWords + w)
+                    puts(rootRef(m) + "[" + cvtToStr(w) + "] = rowp[" + cvtToStr(inWords + w)
                          + " * stride + i] & " + maskOf(bits) + ";\n");
                 }
             } else if (m.elemBytes == 8) {
-                puts("s." + m.name + " = (static_cast<QData>(rowp[" + cvtToStr(inWords + 1) + " * stride + i] & "
+                puts(rootRef(m) + " = (static_cast<QData>(rowp[" + cvtToStr(inWords + 1) + " * stride + i] & "
                      + maskOf(m.width - 32) + ") << 32) | " + w0 + ";\n");
             } else {
-                puts("s." + m.name + " = static_cast<" + m.elemCType + ">(" + w0 + " & " + maskOf(m.width) + ");\n");
+                puts(rootRef(m) + " = static_cast<" + m.elemCType + ">(" + w0 + " & " + maskOf(m.width) + ");\n");
             }
             inWords += rowWords(m);
             inBytes += m.bytes();
@@ -507,11 +773,11 @@ class EmitCudaModel final : public EmitCFunc {
             for (uint32_t w = 0; w < rowWords(m); ++w) {
                 string value;
                 if (m.isWide) {
-                    value = "s." + m.name + "[" + cvtToStr(w) + "]";
+                    value = rootRef(m) + "[" + cvtToStr(w) + "]";
                 } else if (m.elemBytes == 8) {
-                    value = "static_cast<uint32_t>(s." + m.name + (w ? " >> 32)" : ")");
+                    value = "static_cast<uint32_t>(" + rootRef(m) + (w ? " >> 32)" : ")");
                 } else {
-                    value = "s." + m.name;
+                    value = m_stream ? "static_cast<uint32_t>(" + rootRef(m) + ")" : rootRef(m);
                 }
                 puts("rowp[" + cvtToStr(outWords + w) + " * stride + i] = " + value + ";\n");
                 sigBody += "acc = vlcu_sig_word(acc, " + value + ");\n";
@@ -531,7 +797,12 @@ class EmitCudaModel final : public EmitCFunc {
     string cudaFuncArgs(const AstCFunc* nodep) {
         // cFuncArgs (V3EmitCBase.cpp:97-133) with the context after the self pointer
         string args;
-        if (nodep->isLoose() && !nodep->isStatic()) args += m_rootName + "* vlSelf, VlcuContext& vlCtx";
+        if (nodep->isLoose() && !nodep->isStatic()) {
+            // the class the function belongs to (V3Descope.cpp:95-125: `vlSelf` is the scope's object)
+            args += EmitCUtil::prefixNameProtect(EmitCParentModule::get(nodep)) + "* vlSelf, ";
+            if (m_stream) args += m_symsName + "* vlSymsp, ";
+            args += "VlcuContext& vlCtx";
+        }
         if (!nodep->argTypes().empty()) {
             if (!args.empty()) args += ", ";
             args += nodep->argTypes();
@@ -585,23 +856,45 @@ class EmitCudaModel final : public EmitCFunc {
         VL_RESTORER(m_cfuncp);
         m_cfuncp = nodep;
         puts("\n");
-        putns(nodep, "VLCU_D static " + nodep->rtnTypeVoid() + " " + funcNameProtect(nodep, m_topModp) + "("
-                         + cudaFuncArgs(nodep) + ") {\n");
+        // Tiled form: the big functions (the leaves V3Order builds, V3OrderCFuncEmitter.h:137-157,
+        // split by --output-split-cfuncs) are real calls, so that nvcc compiles each on its own
+        // and the instances of a module share one copy; the small ones are inlined
+        bool noinline = false;
+        if (m_stream) {
+            size_t nodes = 0;
+            nodep->foreach([&](const AstNode*) { ++nodes; });
+            noinline = nodes > 400;
+        }
+        putns(nodep, string{noinline ? "VLCU_DN" : "VLCU_D"} + " static " + nodep->rtnTypeVoid() + " "
+                         + funcNameProtect(nodep) + "(" + cudaFuncArgs(nodep) + ") {\n");
         // VL_FATAL_MT leaves the function (the C++ model aborts the process there)
         puts("typedef " + nodep->rtnTypeVoid() + " VlcuFuncRet;\n");
         if (nodep->isLoose() && !nodep->isStatic()) {
             m_useSelfForThis = true;
             m_usevlSelfRef = true;
             puts("auto& vlSelfRef = *vlSelf;\n");
-            // literal C text of the scheduler refers to vlSymsp->_vm_contextp__
-            puts("const VlcuSymsShim vlSymsShim{&vlCtx};\n");
-            puts("const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;\n");
+            if (m_stream) {
+                puts("const uint32_t vlLane = vlcu_lane();  // this instance's slot in the tile\n");
+            } else {
+                // literal C text of the scheduler refers to vlSymsp->_vm_contextp__
+                puts("const VlcuSymsShim vlSymsShim{&vlCtx};\n");
+                puts("const VlcuSymsShim* const vlSymsp VL_ATTR_UNUSED = &vlSymsShim;\n");
+            }
         }
         for (AstNode* subnodep = nodep->argsp(); subnodep; subnodep = subnodep->nextp()) {
             if (AstVar* const varp = VN_CAST(subnodep, Var)) {
                 if (varp->isFuncReturn()) emitVarDecl(varp);
             }
         }
+        // EmitCFunc prints `const uint64_t __VscopeHash = ...` once per function and remembers it in
+        // a private flag that only ITS visit(AstCFunc) resets; with several classes each
+        // _ctor_var_reset needs its own, so declare it here and let the body's own (if it comes)
+        // shadow it in an inner block
+        bool scopeHash = false;
+        if (m_stream && nodep->isLoose() && !nodep->isStatic()) {
+            nodep->foreach([&](const AstCReset*) { scopeHash = true; });
+        }
+        if (scopeHash) puts("const uint64_t __VscopeHash VL_ATTR_UNUSED = VL_MURMUR64_HASH(vlSelf->vlNamep);\n{\n");
         if (nodep->varsp()) {
             putsDecoration(nodep, "// Locals\n");
             iterateAndNextConstNull(nodep->varsp());
@@ -610,6 +903,7 @@ class EmitCudaModel final : public EmitCFunc {
             putsDecoration(nodep, "// Body\n");
             iterateAndNextConstNull(nodep->stmtsp());
         }
+        if (scopeHash) puts("}\n");
         m_usevlSelfRef = false;
         puts("}\n");
     }
@@ -618,15 +912,29 @@ class EmitCudaModel final : public EmitCFunc {
         const AstCFunc* const funcp = nodep->funcp();
         UASSERT_OBJ(funcp->isLoose() || funcp->isStatic(), nodep, "--cuda: call to a proper method");
         putnbs(nodep, "");
-        putns(nodep, funcNameProtect(funcp, m_topModp));
+        putns(nodep, funcNameProtect(funcp));
         puts("(");
         bool comma = false;
         if (funcp->isLoose() && !funcp->isStatic()) {
-            puts("vlSelf, vlCtx");
+            if (m_stream) {
+                // the callee's object: `vlSelf` or `(&vlSymsp->TOP__scope)` (V3Descope.cpp:95-125)
+                puts(nodep->selfPointerProtect(m_useSelfForThis) + ", vlSymsp, vlCtx");
+            } else {
+                puts("vlSelf, vlCtx");
+            }
             comma = true;
         }
         putCommaIterateNext(nodep->argsp(), comma);
         puts(")");
+    }
+    void visit(AstVarRef* nodep) override {
+        EmitCFunc::visit(nodep);
+        // Tiled form: a member is one slot per instance of the tile
+        if (m_laneVars.count(nodep->varp())) {
+            puts(".v[vlLane]");
+        } else if (m_laneArrayVars.count(nodep->varp())) {
+            puts(".lane(vlLane)");
+        }
     }
     void visit(AstDisplay* nodep) override {
         // $display/$write/$error text: the instance logs (format id, arguments); the host formats
@@ -671,7 +979,11 @@ class EmitCudaModel final : public EmitCFunc {
         for (; id < m_plusargs.size(); ++id) {
             if (m_plusargs[id] == text) break;
         }
-        if (id == m_plusargs.size()) m_plusargs.push_back(text);
+        if (id == m_plusargs.size()) {
+            // (VlcuContext::m_plusargs is one bit per string)
+            if (m_plusargs.size() >= 32) nodep->v3warn(E_UNSUPPORTED, "Unsupported: --cuda: more than 32 $test$plusargs strings");
+            m_plusargs.push_back(text);
+        }
         putns(nodep, "static_cast<IData>(vlCtx.testPlusArg(" + cvtToStr(id) + "U))");
     }
     // _configure_coverage: each registration becomes a row of the host coverage table
@@ -792,7 +1104,7 @@ class EmitCudaModel final : public EmitCFunc {
     void emitTraceCall(const AstCCall* callp) {
         string rest = callp->argTypes();
         if (rest.compare(0, 4, "bufp") == 0) rest = rest.substr(4);
-        puts(funcNameProtect(callp->funcp(), m_topModp) + "(vlSelf, vlCtx, valsp" + rest);
+        puts(funcNameProtect(callp->funcp()) + "(vlSelf, vlCtx, valsp" + rest);
         for (AstNode* argp = callp->argsp(); argp; argp = argp->nextp()) {
             puts(", ");
             iterateConst(argp);
@@ -809,7 +1121,7 @@ class EmitCudaModel final : public EmitCFunc {
         m_inDtypeTraceFunc = isDtypeTraceFunc(funcp);
         puts("\n");
         if (m_inDtypeTraceFunc) puts("template <class T_DtypeVar>\n");
-        puts("VLCU_D static void " + funcNameProtect(funcp, m_topModp) + "(" + m_rootName
+        puts("VLCU_D static void " + funcNameProtect(funcp) + "(" + m_rootName
              + "* vlSelf, VlcuContext& vlCtx, uint32_t* valsp"
              + (m_inDtypeTraceFunc ? ", uint32_t offset, const T_DtypeVar& __VdtypeVar" : "") + ") {\n");
         puts("auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;\n");
@@ -871,7 +1183,7 @@ class EmitCudaModel final : public EmitCFunc {
                 for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
                     if (const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr)) {
                         if (const AstCCall* const callp = VN_CAST(sep->exprp(), CCall)) {
-                            puts(funcNameProtect(callp->funcp(), m_topModp) + "(vlSelf, vlCtx, valsp);\n");
+                            puts(funcNameProtect(callp->funcp()) + "(vlSelf, vlCtx, valsp);\n");
                         }
                     }
                 }
@@ -884,15 +1196,25 @@ class EmitCudaModel final : public EmitCFunc {
     std::vector<uint32_t> m_traceOrder;
 
     // ---- the file ---------------------------------------------------------------------------
-    void emitWrapper(const string& wrapper, const string& funcName, bool withCtxOnly = false) {
+    // How an entry point hands the root object to the model's functions
+    string entryArgs() const { return m_stream ? "&vlSelf->symsp->TOP, vlSelf->symsp, vlCtx" : "vlSelf, vlCtx"; }
+    void emitWrapper(const string& wrapper, const string& funcName) {
         const AstCFunc* const funcp = findFunc(funcName);
         puts("VLCU_D static void " + wrapper + "(Root* vlSelf, VlcuContext& vlCtx) {");
         if (funcp && isDeviceFunc(funcp)) {
-            puts(" " + funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx); }\n");
+            puts(" " + funcNameProtect(funcp) + "(" + entryArgs() + "); }\n");
         } else {
             puts(" (void)vlSelf; (void)vlCtx; }\n");
         }
-        (void)withCtxOnly;
+    }
+    void emitDeviceFuncs(const AstNodeModule* modp) {
+        VL_RESTORER(m_modp);
+        m_modp = modp;
+        for (AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+            if (AstCFunc* const funcp = VN_CAST(nodep, CFunc)) {
+                if (isDeviceFunc(funcp)) iterateConst(funcp);
+            }
+        }
     }
     void emitAll() {
         const string fileName = v3Global.opt.makeDir() + "/" + m_designName + ".cu";
@@ -901,7 +1223,12 @@ class EmitCudaModel final : public EmitCFunc {
         openOutputFile(cfilep, "Batched CUDA model (one instance per thread) for include/verilated_cuda.h");
         puts("// Design '" + v3Global.rootp()->topModulep()->prettyName() + "' printed by V3EmitCuda; compile with\n");
         puts("//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include\n");
-        {
+        if (m_stream) {
+            puts("\n// Tiled form: the model image stays in HBM (" + cvtToStr(m_scopeInsts.size() + 1)
+                 + " scopes of " + cvtToStr(m_subClasses.size() + 1) + " module classes); its kernels keep almost\n");
+            puts("// nothing in registers and are bound by memory latency: compile for full occupancy\n");
+            puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 16\n#endif\n");
+        } else {
             // Occupancy target of the kernels (verilated_cuda_launch.h: __launch_bounds__(64,
             // VLCU_MIN_BLOCKS), default 7 = 146 registers per thread).  A design that keeps almost
             // nothing in registers -- its state is in memory-class arrays -- is bound by memory
@@ -921,15 +1248,29 @@ class EmitCudaModel final : public EmitCFunc {
         puts("\n// Name the design registers under with vlcu_create()\n");
         puts("#ifndef VLCU_DESIGN_NAME\n#define VLCU_DESIGN_NAME " + quoted(v3Global.opt.prefix()) + "\n#endif\n");
         emitConstPool();
-        emitRootStruct();
+        if (m_stream) {
+            emitTileStructs();
+        } else {
+            emitRootStruct();
+        }
 
         puts("\nstruct " + m_designName + " final {\n");
-        puts("typedef " + m_rootName + " Root;\n");
-        // Slot table
-        puts("// Structure-of-arrays slot table: byte offset per instance of every persistent member\n");
-        puts("enum : uint32_t {\n");
-        for (const CudaMember& m : m_members) puts("OFF_" + m.name + " = " + cvtToStr(m.offset) + ",\n");
-        puts("kStateBytes = " + cvtToStr(m_stateBytes) + ",  // S_persist\n");
+        if (m_stream) {
+            puts("typedef " + m_symsName + " Syms;\n");
+            puts("// What the kernels hold per thread: the instance's tile and its slot in it\n");
+            puts("struct Root final {\nSyms* symsp;\nuint32_t lane;\n};\n");
+            puts("static constexpr bool kTiled = true;\n");
+            puts("enum : uint32_t {\n");
+            puts("kStateBytes = sizeof(Syms) / VLCU_TILE,  // S_persist\n");
+        } else {
+            puts("typedef " + m_rootName + " Root;\n");
+            puts("static constexpr bool kTiled = false;\n");
+            // Slot table
+            puts("// Structure-of-arrays slot table: byte offset per instance of every persistent member\n");
+            puts("enum : uint32_t {\n");
+            for (const CudaMember& m : m_members) puts("OFF_" + m.name + " = " + cvtToStr(m.offset) + ",\n");
+            puts("kStateBytes = " + cvtToStr(m_stateBytes) + ",  // S_persist\n");
+        }
         puts("kTouchedReadBytes = " + cvtToStr(m_touchedRead) + ",  // S_state_rd: persistent bytes one eval can read\n");
         puts("kTouchedWriteBytes = " + cvtToStr(m_touchedWrite) + ",  // S_state_wr\n");
         puts("};\n");
@@ -949,41 +1290,75 @@ class EmitCudaModel final : public EmitCFunc {
         puts("};\n");
         puts("VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {\n");
         puts("(void)l; (void)sh; (void)st; (void)i;\n");
-        puts("s.vlNamep = \"TOP\";\n");
-        for (const auto& q : m_nbaQueues) puts("s." + q.first + ".bind(&l." + q.first + ");\n");
-        for (const CudaMember& m : m_members) {
-            if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
-            if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
-            if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER
-                || m.storage == CudaStorage::INTERLEAVED) {
-                puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
+        if (m_stream) {
+            puts("s.symsp = reinterpret_cast<Syms*>(st.base) + i / VLCU_TILE;\n");
+            puts("s.lane = static_cast<uint32_t>(i % VLCU_TILE);\n");
+            puts("}\n");
+            puts("// (nothing to load or store: the functions work on the image in place)\n");
+            puts("VLCU_D static void load(Root&, const VlcuState&, uint64_t) {}\n");
+            puts("VLCU_D static void store(const Root&, const VlcuState&, uint64_t) {}\n");
+        } else {
+            puts("s.vlNamep = \"TOP\";\n");
+            for (const auto& q : m_nbaQueues) puts("s." + q.first + ".bind(&l." + q.first + ");\n");
+            for (const CudaMember& m : m_members) {
+                if (m.storage == CudaStorage::LOCAL) puts("s." + m.name + ".bind(l." + m.name + ");\n");
+                if (m.storage == CudaStorage::SHARED) puts("s." + m.name + ".bind(sh." + m.name + ", threadIdx.x);\n");
+                if (m.storage == CudaStorage::GLOBAL || m.storage == CudaStorage::COVER
+                    || m.storage == CudaStorage::INTERLEAVED) {
+                    puts("s." + m.name + ".bind(st, OFF_" + m.name + ", i);\n");
+                }
             }
+            puts("}\n");
+            emitLoadStore(true);
+            emitLoadStore(false);
         }
-        puts("}\n");
-        emitLoadStore(true);
-        emitLoadStore(false);
         emitPortRows();
-        if (const AstCFunc* const funcp = findFunc("trace_init_top")) traceRows(funcp->stmtsp(), "", 0);
+        if (!m_stream) {
+            if (const AstCFunc* const funcp = findFunc("trace_init_top")) traceRows(funcp->stmtsp(), "", 0);
+        }
         puts("enum : uint32_t { " + m_sizes + ", kTraceWords = " + cvtToStr(m_traceWords) + " };\n");
 
         // Device functions
-        for (AstNode* nodep = m_topModp->stmtsp(); nodep; nodep = nodep->nextp()) {
-            if (AstCFunc* const funcp = VN_CAST(nodep, CFunc)) {
-                if (isDeviceFunc(funcp)) iterateConst(funcp);
-            }
+        for (const CudaClass& cls : m_subClasses) {
+            if (m_stream) emitDeviceFuncs(cls.modp);
         }
-        emitTraceSample();
+        emitDeviceFuncs(m_topModp);
+        if (m_stream) {
+            // (waveforms of a tiled design: not yet)
+            puts("\nVLCU_D static void trace_sample(Root*, VlcuContext&, uint32_t*) {}\n");
+        } else {
+            emitTraceSample();
+        }
         // Entry points of the launch templates = what Vtop::eval_step() calls
         // (EmitCModel::emitStandardMethods1, V3EmitCModel.cpp:403-437)
         puts("\n");
         // Construction: the member initialiser `uint32_t __Vcoverage[n]{}` of the C++ class
         // (V3EmitCHeaders.cpp:153-158), then Vtop___024root___ctor_var_reset
         puts("VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {\n");
-        if (m_coverBins) {
-            puts("for (uint32_t b = 0; b < " + cvtToStr(m_coverBins) + "U; ++b) vlSelf->__Vcoverage[b] = 0U;\n");
-        }
-        if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
-            puts(funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx);\n");
+        if (m_stream) {
+            // what the Syms constructor does (V3EmitCSyms.cpp:1148-1173): every scope is named
+            // -- the reset values hash the name, V3EmitCFunc.cpp:668-678 -- and constructed
+            puts("Syms* const vlSymsp = vlSelf->symsp;\n");
+            puts("vlSymsp->TOP.vlNamep = \"TOP\";\n");
+            if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
+                puts(funcNameProtect(funcp) + "(&vlSymsp->TOP, vlSymsp, vlCtx);\n");
+            }
+            for (const CudaScopeInst& inst : m_scopeInsts) {
+                puts("vlSymsp->" + inst.sym + ".vlNamep = " + quoted("TOP." + inst.pretty) + ";\n");
+                for (const AstNode* nodep = m_subClasses[inst.classIdx].modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                    const AstCFunc* const funcp = VN_CAST(nodep, CFunc);
+                    if (funcp && funcp->name() == "_ctor_var_reset") {
+                        puts(funcNameProtect(funcp) + "(&vlSymsp->" + inst.sym + ", vlSymsp, vlCtx);\n");
+                    }
+                }
+            }
+        } else {
+            if (m_coverBins) {
+                puts("for (uint32_t b = 0; b < " + cvtToStr(m_coverBins) + "U; ++b) vlSelf->__Vcoverage[b] = 0U;\n");
+            }
+            if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
+                puts(funcNameProtect(funcp) + "(vlSelf, vlCtx);\n");
+            }
         }
         puts("}\n");
         emitWrapper("eval_static", "_eval_static");
@@ -995,7 +1370,7 @@ class EmitCudaModel final : public EmitCFunc {
             // a full commit queue cannot grow on the device: the instance takes a fatal instead
             puts("VLCU_D static void eval(Root* vlSelf, VlcuContext& vlCtx) {\n");
             if (const AstCFunc* const funcp = findFunc("_eval")) {
-                puts(funcNameProtect(funcp, m_topModp) + "(vlSelf, vlCtx);\n");
+                puts(funcNameProtect(funcp) + "(" + entryArgs() + ");\n");
             }
             for (const auto& q : m_nbaQueues) {
                 puts("if (VL_UNLIKELY(vlSelf->" + q.first + ".overflowed())) vlCtx.fatal(0, VLCU_FATAL_NBAQ_OVERFLOW);\n");
@@ -1073,15 +1448,17 @@ class EmitCudaModel final : public EmitCFunc {
         puts("// Host tables: what Vtop.h / Vtop__Syms / __Vconfigure give the host runtime\n");
         puts("\nconst VlcuDesignInfo& " + m_designName + "::info() {\n");
         puts("typedef " + m_designName + " T;\n");
-        puts("// name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset\n");
+        puts("// name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset\n");
         puts("static const VlcuMemberDesc members[] = {\n");
-        for (const CudaMember& m : m_members) {
+        for (const CudaFlatMember& fm : m_flat) {
+            const CudaMember& m = fm.m;
             static const char* const kinds[]
                 = {"VLCU_MEMBER_IN", "VLCU_MEMBER_OUT", "VLCU_MEMBER_INOUT", "VLCU_MEMBER_STATE",
                    "VLCU_MEMBER_COVERAGE", "VLCU_MEMBER_MEMORY"};
-            puts("{" + quoted(m.name) + ", " + (m.varp ? quoted(m.hier) : string{"nullptr"}) + ", " + kinds[m.kind]
-                 + ", " + cvtToStr(m.elemBytes) + ", 0, " + cvtToStr(m.elems()) + ", " + cvtToStr(m.width) + ", "
-                 + cvtToStr(m.msb) + ", " + cvtToStr(m.lsb) + ", T::OFF_" + m.name + "},\n");
+            puts("{" + quoted(fm.tableName) + ", " + (m.varp ? quoted(m.hier) : string{"nullptr"}) + ", " + kinds[m.kind]
+                 + ", " + cvtToStr(m.elemBytes) + ", " + (m.laneMajor ? "VLCU_MEMBERF_LANE_MAJOR" : "0") + ", "
+                 + cvtToStr(m.elems()) + ", " + cvtToStr(m.width) + ", "
+                 + cvtToStr(m.msb) + ", " + cvtToStr(m.lsb) + ", " + fm.offsetExpr + "},\n");
         }
         puts("};\n");
         // Coverage
@@ -1141,6 +1518,7 @@ class EmitCudaModel final : public EmitCFunc {
             }
             puts("0};  // (+ terminator)\n");
             m_saveCheckval = hash.digestUInt64();
+            if (m_stream && unsupported.empty()) unsupported = "(tiled model image)";
             m_saveUnsupported = unsupported;
         }
         puts("static const VlcuDesignInfo s = {\n");
@@ -1167,7 +1545,7 @@ class EmitCudaModel final : public EmitCFunc {
                << (v3Global.rootp()->timeprecision().isNone()
                        ? -1
                        : std::abs(v3Global.rootp()->timeprecision().powerOfTen()))
-               << "};\n";
+               << ", " << (m_stream ? "VLCU_TILE" : "0") << "};\n";
             puts(os.str());
         }
         puts("return s;\n}\n");
@@ -1177,7 +1555,8 @@ public:
     EmitCudaModel()
         : m_topModp{v3Global.rootp()->topModulep()}
         , m_rootName{EmitCUtil::prefixNameProtect(v3Global.rootp()->topModulep())}
-        , m_designName{v3Global.opt.prefix() + "__cuda"} {
+        , m_designName{v3Global.opt.prefix() + "__cuda"}
+        , m_symsName{v3Global.opt.prefix() + "__Syms"} {
         m_modp = m_topModp;
         computeLayout();
         emitAll();
@@ -1189,6 +1568,7 @@ public:
 
 bool V3EmitCuda::s_enabled = false;
 bool V3EmitCuda::s_layoutSelection = true;
+int V3EmitCuda::s_streamMode = -1;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -28,10 +28,16 @@ public:
     // and instance-major placement of large arrays (off: always instance-major)
     static void layoutSelection(bool flag) { s_layoutSelection = flag; }
     static bool layoutSelection() { return s_layoutSelection; }
+    // --cuda-stream / --no-cuda-stream: force the tiled (model image stays in HBM, module
+    // hierarchy kept) or the register form (single $root class held by the thread); default: the
+    // emitter chooses by hierarchy and size
+    static void streamMode(bool flag) { s_streamMode = flag ? 1 : 0; }
+    static int streamMode() { return s_streamMode; }
 
 private:
     static bool s_enabled;
     static bool s_layoutSelection;
+    static int s_streamMode;  // -1 automatic, 0 register form, 1 tiled form
 };
 
 #endif  // Guard

@@ -230,3 +230,63 @@ def generic_run(design, stim, inst_base=0, seed=1, rand_reset=2, threads=1):
             None, None, threads)
     assert rc == 0
     return obs, sigs
+
+
+# ---- "fuzz" testbench (include/verilated_cuda_launch.h VlcuTbFuzz) on the CPU side -------------
+FUZZ_RESET_LOW, FUZZ_RESET_HIGH, FUZZ_UNIFORM = 1, 2, 4
+_M64 = (1 << 64) - 1
+
+
+def _fuzz_mix(x):
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+    return x ^ (x >> np.uint64(31))
+
+
+def fuzz_rows(n, n_evals, in_words, inst_base=0, seed=1, tb_seed=0, tb_flags=0, reset_periods=0,
+              sparse_mask=0, eval_base=0):
+    """The stimulus rows VlcuTbFuzz makes in the kernel, restated with numpy:
+    uint32 [evals][in_words][n]."""
+    with np.errstate(over="ignore"):
+        inst = np.arange(n, dtype=np.uint64) + np.uint64(inst_base)
+        rand_seed = np.uint64(seed) ^ inst  # VlcuContext::randSeed()
+        key = np.uint64(tb_seed) ^ (np.zeros(n, dtype=np.uint64) if tb_flags & FUZZ_UNIFORM
+                                    else _fuzz_mix(rand_seed + np.uint64(1)))
+        e = np.arange(n_evals, dtype=np.uint64) + np.uint64(eval_base)
+        period = e >> np.uint64(1)
+        rows = np.zeros((n_evals, in_words, n), dtype=np.uint32)
+        for w in range(in_words):
+            draw = _fuzz_mix(key[None, :] + period[:, None] * np.uint64(0x9e3779b97f4a7c15)
+                             + np.uint64(((w + 1) * 0xd1342543de82ef95) & _M64))
+            val = (draw >> np.uint64(32)).astype(np.uint32)
+            if w < 32 and (sparse_mask >> w) & 1:
+                val = np.where((draw & np.uint64(0x1f)) != 0, np.uint32(0), val)
+            rows[:, w, :] = val
+        rows[:, 0, :] = ((e & np.uint64(1)) ^ np.uint64(1)).astype(np.uint32)[:, None]
+        if in_words > 1 and tb_flags & FUZZ_RESET_LOW:
+            rows[:, 1, :] = (period >= np.uint64(reset_periods)).astype(np.uint32)[:, None]
+        if in_words > 1 and tb_flags & FUZZ_RESET_HIGH:
+            rows[:, 1, :] = (period < np.uint64(reset_periods)).astype(np.uint32)[:, None]
+    return rows
+
+
+def generic_fuzz(design, n, n_evals, inst_base=0, seed=1, rand_reset=2, tb_seed=0, tb_flags=0,
+                 reset_periods=0, sparse_mask=0, obs_evals=0, threads=1):
+    """The genuine Verilated model driven by the harness's own restatement of the fuzz testbench
+    (no stimulus rows in memory).  Returns (obs [obs_evals][out_words][n] or None, sigs [n])."""
+    _, ow = generic_words(design)
+    fn = getattr(ref(), f"vlref_{design}_fuzz")
+    fn.restype = i32
+    fn.argtypes = [u64, u64, u64, i32, u64, u64, u32, u32, u32, vp, u64, vp, i32]
+    obs = np.zeros((obs_evals, ow, n), dtype=np.uint32) if obs_evals else None
+    sigs = np.zeros(n, dtype=np.uint64)
+    rc = fn(n, inst_base, seed, rand_reset, n_evals, tb_seed, tb_flags, reset_periods, sparse_mask,
+            obs.ctypes.data if obs_evals else None, obs_evals, sigs.ctypes.data, threads)
+    assert rc == 0
+    return obs, sigs
+
+
+def last_loop_seconds():
+    fn = ref().vlref_last_loop_seconds
+    fn.restype = ctypes.c_double
+    return fn()

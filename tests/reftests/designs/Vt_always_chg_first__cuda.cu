@@ -34,6 +34,7 @@ struct Vt_always_chg_first___024root final {
 
 struct Vt_always_chg_first__cuda final {
     typedef Vt_always_chg_first___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 28,
@@ -316,7 +317,7 @@ struct Vt_always_chg_first__cuda final {
 
 const VlcuDesignInfo& Vt_always_chg_first__cuda::info() {
     typedef Vt_always_chg_first__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"fastclk", "fastclk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_fastclk},
@@ -341,7 +342,7 @@ const VlcuDesignInfo& Vt_always_chg_first__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x10ce5447a7957624ULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x10ce5447a7957624ULL, nullptr, 12, 12, 0};
     return s;
 }
 

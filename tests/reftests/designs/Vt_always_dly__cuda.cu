@@ -35,6 +35,7 @@ struct Vt_always_dly___024root final {
 
 struct Vt_always_dly__cuda final {
     typedef Vt_always_dly___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -353,7 +354,7 @@ struct Vt_always_dly__cuda final {
 
 const VlcuDesignInfo& Vt_always_dly__cuda::info() {
     typedef Vt_always_dly__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__prev_wr_clocks", "t.prev_wr_clocks", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__prev_wr_clocks},
@@ -379,7 +380,7 @@ const VlcuDesignInfo& Vt_always_dly__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xdcbbc995b8129b2eULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0xdcbbc995b8129b2eULL, nullptr, 12, 12, 0};
     return s;
 }
 

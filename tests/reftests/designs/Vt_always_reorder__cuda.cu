@@ -36,6 +36,7 @@ struct Vt_always_reorder___024root final {
 
 struct Vt_always_reorder__cuda final {
     typedef Vt_always_reorder___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -327,7 +328,7 @@ struct Vt_always_reorder__cuda final {
 
 const VlcuDesignInfo& Vt_always_reorder__cuda::info() {
     typedef Vt_always_reorder__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -354,7 +355,7 @@ const VlcuDesignInfo& Vt_always_reorder__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xbbc1c41a4ecf7158ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xbbc1c41a4ecf7158ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -48,6 +48,7 @@ struct Vt_always_split_rst___024root final {
 
 struct Vt_always_split_rst__cuda final {
     typedef Vt_always_split_rst___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -560,7 +561,7 @@ struct Vt_always_split_rst__cuda final {
 
 const VlcuDesignInfo& Vt_always_split_rst__cuda::info() {
     typedef Vt_always_split_rst__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__rstn", "t.rstn", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__rstn},
@@ -604,7 +605,7 @@ const VlcuDesignInfo& Vt_always_split_rst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x72ea31a112838193ULL, nullptr, 12, 12};
+        saveOrder, 29, 0, 0x72ea31a112838193ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -39,6 +39,7 @@ struct Vt_always_splitord___024root final {
 
 struct Vt_always_splitord__cuda final {
     typedef Vt_always_splitord___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -513,7 +514,7 @@ struct Vt_always_splitord__cuda final {
 
 const VlcuDesignInfo& Vt_always_splitord__cuda::info() {
     typedef Vt_always_splitord__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -548,7 +549,7 @@ const VlcuDesignInfo& Vt_always_splitord__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x839bb1ba8a306f3fULL, nullptr, 12, 12};
+        saveOrder, 20, 0, 0x839bb1ba8a306f3fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -27,6 +27,7 @@ struct Vt_array_compare___024root final {
 
 struct Vt_array_compare__cuda final {
     typedef Vt_array_compare___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_t__DOT__array_1 = 0,
@@ -203,7 +204,7 @@ struct Vt_array_compare__cuda final {
 
 const VlcuDesignInfo& Vt_array_compare__cuda::info() {
     typedef Vt_array_compare__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"t__DOT__array_1", "t.array_1", VLCU_MEMBER_STATE, 1, 0, 3, 4, 3, 0, T::OFF_t__DOT__array_1},
         {"t__DOT__array_2", "t.array_2", VLCU_MEMBER_STATE, 1, 0, 3, 4, 3, 0, T::OFF_t__DOT__array_2},
@@ -221,7 +222,7 @@ const VlcuDesignInfo& Vt_array_compare__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 3, 0, 0x7d9a61755df4f783ULL, nullptr, 12, 12};
+        saveOrder, 3, 0, 0x7d9a61755df4f783ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -38,6 +38,7 @@ struct Vt_array_mda___024root final {
 
 struct Vt_array_mda__cuda final {
     typedef Vt_array_mda___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 108,
@@ -410,7 +411,7 @@ struct Vt_array_mda__cuda final {
 
 const VlcuDesignInfo& Vt_array_mda__cuda::info() {
     typedef Vt_array_mda__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -439,7 +440,7 @@ const VlcuDesignInfo& Vt_array_mda__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x396f93b4708e9aabULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x396f93b4708e9aabULL, nullptr, 12, 12, 0};
     return s;
 }
 

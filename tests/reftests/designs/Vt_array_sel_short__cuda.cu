@@ -25,6 +25,7 @@ struct Vt_array_sel_short___024root final {
 
 struct Vt_array_sel_short__cuda final {
     typedef Vt_array_sel_short___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_t__DOT__foo = 0,
@@ -136,7 +137,7 @@ struct Vt_array_sel_short__cuda final {
 
 const VlcuDesignInfo& Vt_array_sel_short__cuda::info() {
     typedef Vt_array_sel_short__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"t__DOT__foo", "t.foo", VLCU_MEMBER_STATE, 2, 0, 8, 16, 15, 0, T::OFF_t__DOT__foo},
     };
@@ -152,7 +153,7 @@ const VlcuDesignInfo& Vt_array_sel_short__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0x9a3b087dbf0c2514ULL, nullptr, 12, 12};
+        saveOrder, 1, 0, 0x9a3b087dbf0c2514ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_assert_question___024root final {
 
 struct Vt_assert_question__cuda final {
     typedef Vt_assert_question___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -318,7 +319,7 @@ struct Vt_assert_question__cuda final {
 
 const VlcuDesignInfo& Vt_assert_question__cuda::info() {
     typedef Vt_assert_question__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"sel", "sel", VLCU_MEMBER_IN, 1, 0, 1, 4, 3, 0, T::OFF_sel},
@@ -344,7 +345,7 @@ const VlcuDesignInfo& Vt_assert_question__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x9e158bf2a1918456ULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0x9e158bf2a1918456ULL, nullptr, 12, 12, 0};
     return s;
 }
 

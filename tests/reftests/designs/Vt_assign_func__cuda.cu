@@ -34,6 +34,7 @@ struct Vt_assign_func___024root final {
 
 struct Vt_assign_func__cuda final {
     typedef Vt_assign_func___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 52,
@@ -529,7 +530,7 @@ struct Vt_assign_func__cuda final {
 
 const VlcuDesignInfo& Vt_assign_func__cuda::info() {
     typedef Vt_assign_func__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -559,7 +560,7 @@ const VlcuDesignInfo& Vt_assign_func__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x2208510c11c41db4ULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0x2208510c11c41db4ULL, nullptr, 12, 12, 0};
     return s;
 }
 

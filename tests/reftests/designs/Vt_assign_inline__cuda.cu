@@ -33,6 +33,7 @@ struct Vt_assign_inline___024root final {
 
 struct Vt_assign_inline__cuda final {
     typedef Vt_assign_inline___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -307,7 +308,7 @@ struct Vt_assign_inline__cuda final {
 
 const VlcuDesignInfo& Vt_assign_inline__cuda::info() {
     typedef Vt_assign_inline__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__c_q_r", "t.c_q_r", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__c_q_r},
@@ -331,7 +332,7 @@ const VlcuDesignInfo& Vt_assign_inline__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x37543a136dcb5baULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x37543a136dcb5baULL, nullptr, 12, 12, 0};
     return s;
 }
 

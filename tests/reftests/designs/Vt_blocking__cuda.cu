@@ -34,6 +34,7 @@ struct Vt_blocking___024root final {
 
 struct Vt_blocking__cuda final {
     typedef Vt_blocking___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -414,7 +415,7 @@ struct Vt_blocking__cuda final {
 
 const VlcuDesignInfo& Vt_blocking__cuda::info() {
     typedef Vt_blocking__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__a", "t.a", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__a},
@@ -444,7 +445,7 @@ const VlcuDesignInfo& Vt_blocking__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0xdb5148da9ffd80a2ULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0xdb5148da9ffd80a2ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -32,6 +32,7 @@ struct Vt_case_66bits___024root final {
 
 struct Vt_case_66bits__cuda final {
     typedef Vt_case_66bits___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -298,7 +299,7 @@ struct Vt_case_66bits__cuda final {
 
 const VlcuDesignInfo& Vt_case_66bits__cuda::info() {
     typedef Vt_case_66bits__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -321,7 +322,7 @@ const VlcuDesignInfo& Vt_case_66bits__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xca1ed157e3ed1d2aULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xca1ed157e3ed1d2aULL, nullptr, 12, 12, 0};
     return s;
 }
 

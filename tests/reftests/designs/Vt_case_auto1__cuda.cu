@@ -228,6 +228,7 @@ struct Vt_case_auto1___024root final {
 
 struct Vt_case_auto1__cuda final {
     typedef Vt_case_auto1___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 44,
@@ -652,7 +653,7 @@ struct Vt_case_auto1__cuda final {
 
 const VlcuDesignInfo& Vt_case_auto1__cuda::info() {
     typedef Vt_case_auto1__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__m_state_xr", "t.m_state_xr", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__m_state_xr},
@@ -680,7 +681,7 @@ const VlcuDesignInfo& Vt_case_auto1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xff608caab268cefULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xff608caab268cefULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -73,6 +73,7 @@ struct Vt_case_deep___024root final {
 
 struct Vt_case_deep__cuda final {
     typedef Vt_case_deep___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 116,
@@ -3286,7 +3287,7 @@ struct Vt_case_deep__cuda final {
 
 const VlcuDesignInfo& Vt_case_deep__cuda::info() {
     typedef Vt_case_deep__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_17", "__VdfgRegularize_h6e95ff9d_0_17", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_17},
@@ -3355,7 +3356,7 @@ const VlcuDesignInfo& Vt_case_deep__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 54, 0, 0x77787360b8d7627fULL, nullptr, 12, 12};
+        saveOrder, 54, 0, 0x77787360b8d7627fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -47,6 +47,7 @@ struct Vt_case_itemwidth___024root final {
 
 struct Vt_case_itemwidth__cuda final {
     typedef Vt_case_itemwidth___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -522,7 +523,7 @@ struct Vt_case_itemwidth__cuda final {
 
 const VlcuDesignInfo& Vt_case_itemwidth__cuda::info() {
     typedef Vt_case_itemwidth__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__addr", "t.addr", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF_t__DOT__addr},
@@ -555,7 +556,7 @@ const VlcuDesignInfo& Vt_case_itemwidth__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x1953e327e2fc9fc4ULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0x1953e327e2fc9fc4ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_case_nest___024root final {
 
 struct Vt_case_nest__cuda final {
     typedef Vt_case_nest___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -528,7 +529,7 @@ struct Vt_case_nest__cuda final {
 
 const VlcuDesignInfo& Vt_case_nest__cuda::info() {
     typedef Vt_case_nest__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__out1", "t.out1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__out1},
@@ -557,7 +558,7 @@ const VlcuDesignInfo& Vt_case_nest__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x2255b7bb41ea054eULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x2255b7bb41ea054eULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt_clk_concat3___024root final {
 
 struct Vt_clk_concat3__cuda final {
     typedef Vt_clk_concat3___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk0 = 21,
@@ -313,7 +314,7 @@ struct Vt_clk_concat3__cuda final {
 
 const VlcuDesignInfo& Vt_clk_concat3__cuda::info() {
     typedef Vt_clk_concat3__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk0", "clk0", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk0},
         {"clk1", "clk1", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk1},
@@ -340,7 +341,7 @@ const VlcuDesignInfo& Vt_clk_concat3__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xa67a4c71354645e9ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xa67a4c71354645e9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -38,6 +38,7 @@ struct Vt_clk_condflop___024root final {
 
 struct Vt_clk_condflop__cuda final {
     typedef Vt_clk_condflop___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -469,7 +470,7 @@ struct Vt_clk_condflop__cuda final {
 
 const VlcuDesignInfo& Vt_clk_condflop__cuda::info() {
     typedef Vt_clk_condflop__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__d1", "t.d1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__d1},
@@ -503,7 +504,7 @@ const VlcuDesignInfo& Vt_clk_condflop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x86c87489facfdcc7ULL, nullptr, 12, 12};
+        saveOrder, 19, 0, 0x86c87489facfdcc7ULL, nullptr, 12, 12, 0};
     return s;
 }
 

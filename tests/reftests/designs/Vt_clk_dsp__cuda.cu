@@ -42,6 +42,7 @@ struct Vt_clk_dsp___024root final {
 
 struct Vt_clk_dsp__cuda final {
     typedef Vt_clk_dsp___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 28,
@@ -571,7 +572,7 @@ struct Vt_clk_dsp__cuda final {
 
 const VlcuDesignInfo& Vt_clk_dsp__cuda::info() {
     typedef Vt_clk_dsp__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__cyc},
@@ -609,7 +610,7 @@ const VlcuDesignInfo& Vt_clk_dsp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0x911b6693bd329ef9ULL, nullptr, 12, 12};
+        saveOrder, 23, 0, 0x911b6693bd329ef9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

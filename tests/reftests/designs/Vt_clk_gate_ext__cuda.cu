@@ -34,6 +34,7 @@ struct Vt_clk_gate_ext___024root final {
 
 struct Vt_clk_gate_ext__cuda final {
     typedef Vt_clk_gate_ext___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -316,7 +317,7 @@ struct Vt_clk_gate_ext__cuda final {
 
 const VlcuDesignInfo& Vt_clk_gate_ext__cuda::info() {
     typedef Vt_clk_gate_ext__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__clk_en", "t.clk_en", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__clk_en},
@@ -341,7 +342,7 @@ const VlcuDesignInfo& Vt_clk_gate_ext__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x792b8bca4c0ff647ULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x792b8bca4c0ff647ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt_clk_gated_1___024root final {
 
 struct Vt_clk_gated_1__cuda final {
     typedef Vt_clk_gated_1___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -332,7 +333,7 @@ struct Vt_clk_gated_1__cuda final {
 
 const VlcuDesignInfo& Vt_clk_gated_1__cuda::info() {
     typedef Vt_clk_gated_1__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__gated_clk_en", "t.gated_clk_en", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__gated_clk_en},
@@ -359,7 +360,7 @@ const VlcuDesignInfo& Vt_clk_gated_1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xd399fac5cfc0a55cULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xd399fac5cfc0a55cULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -39,6 +39,7 @@ struct Vt_clk_gen___024root final {
 
 struct Vt_clk_gen__cuda final {
     typedef Vt_clk_gen___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 76,
@@ -485,7 +486,7 @@ struct Vt_clk_gen__cuda final {
 
 const VlcuDesignInfo& Vt_clk_gen__cuda::info() {
     typedef Vt_clk_gen__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__gendlyclk_r", "t.gendlyclk_r", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__gendlyclk_r},
@@ -520,7 +521,7 @@ const VlcuDesignInfo& Vt_clk_gen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x62ad85a9ec1d2fe7ULL, nullptr, 12, 12};
+        saveOrder, 20, 0, 0x62ad85a9ec1d2fe7ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -37,6 +37,7 @@ struct Vt_clk_powerdn___024root final {
 
 struct Vt_clk_powerdn__cuda final {
     typedef Vt_clk_powerdn___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 36,
@@ -572,7 +573,7 @@ struct Vt_clk_powerdn__cuda final {
 
 const VlcuDesignInfo& Vt_clk_powerdn__cuda::info() {
     typedef Vt_clk_powerdn__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__reset_l", "t.reset_l", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__reset_l},
@@ -605,7 +606,7 @@ const VlcuDesignInfo& Vt_clk_powerdn__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x28ea696f4f5177a9ULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0x28ea696f4f5177a9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

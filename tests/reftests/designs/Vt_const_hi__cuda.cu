@@ -89,6 +89,7 @@ struct Vt_const_hi___024root final {
 
 struct Vt_const_hi__cuda final {
     typedef Vt_const_hi___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 288,
@@ -726,7 +727,7 @@ struct Vt_const_hi__cuda final {
 
 const VlcuDesignInfo& Vt_const_hi__cuda::info() {
     typedef Vt_const_hi__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__reg_i", "t.reg_i", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF_t__DOT__reg_i},
@@ -752,7 +753,7 @@ const VlcuDesignInfo& Vt_const_hi__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x6ddc4b72c7b00336ULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0x6ddc4b72c7b00336ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_const_op_red_scope___024root final {
 
 struct Vt_const_op_red_scope__cuda final {
     typedef Vt_const_op_red_scope___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -384,7 +385,7 @@ struct Vt_const_op_red_scope__cuda final {
 
 const VlcuDesignInfo& Vt_const_op_red_scope__cuda::info() {
     typedef Vt_const_op_red_scope__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__out0", "t.out0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__out0},
@@ -413,7 +414,7 @@ const VlcuDesignInfo& Vt_const_op_red_scope__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x635ba2f5afd8da2bULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x635ba2f5afd8da2bULL, nullptr, 12, 12, 0};
     return s;
 }
 

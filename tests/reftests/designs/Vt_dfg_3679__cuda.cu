@@ -33,6 +33,7 @@ struct Vt_dfg_3679___024root final {
 
 struct Vt_dfg_3679__cuda final {
     typedef Vt_dfg_3679___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 44,
@@ -401,7 +402,7 @@ struct Vt_dfg_3679__cuda final {
 
 const VlcuDesignInfo& Vt_dfg_3679__cuda::info() {
     typedef Vt_dfg_3679__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -430,7 +431,7 @@ const VlcuDesignInfo& Vt_dfg_3679__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x9e5c33396fd0ffd8ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x9e5c33396fd0ffd8ULL, nullptr, 12, 12, 0};
     return s;
 }
 

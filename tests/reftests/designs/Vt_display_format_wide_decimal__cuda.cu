@@ -40,6 +40,7 @@ struct Vt_display_format_wide_decimal___024root final {
 
 struct Vt_display_format_wide_decimal__cuda final {
     typedef Vt_display_format_wide_decimal___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 152,
@@ -346,7 +347,7 @@ struct Vt_display_format_wide_decimal__cuda final {
 
 const VlcuDesignInfo& Vt_display_format_wide_decimal__cuda::info() {
     typedef Vt_display_format_wide_decimal__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -370,7 +371,7 @@ const VlcuDesignInfo& Vt_display_format_wide_decimal__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x46d49a369c4c1539ULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x46d49a369c4c1539ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -37,6 +37,7 @@ struct Vt_display_recurse___024root final {
 
 struct Vt_display_recurse__cuda final {
     typedef Vt_display_recurse___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 65560,
@@ -423,7 +424,7 @@ struct Vt_display_recurse__cuda final {
 
 const VlcuDesignInfo& Vt_display_recurse__cuda::info() {
     typedef Vt_display_recurse__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT____VlemCall_3__getb", "t.__VlemCall_3__getb", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT____VlemCall_3__getb},
@@ -451,7 +452,7 @@ const VlcuDesignInfo& Vt_display_recurse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 9, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xc9e185e9a3b65421ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xc9e185e9a3b65421ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt_for_count___024root final {
 
 struct Vt_for_count__cuda final {
     typedef Vt_for_count___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 60,
@@ -508,7 +509,7 @@ struct Vt_for_count__cuda final {
 
 const VlcuDesignInfo& Vt_for_count__cuda::info() {
     typedef Vt_for_count__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -540,7 +541,7 @@ const VlcuDesignInfo& Vt_for_count__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x884886c1d74fdcbcULL, nullptr, 12, 12};
+        saveOrder, 17, 0, 0x884886c1d74fdcbcULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_func_crc___024root final {
 
 struct Vt_func_crc__cuda final {
     typedef Vt_func_crc___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -1883,7 +1884,7 @@ struct Vt_func_crc__cuda final {
 
 const VlcuDesignInfo& Vt_func_crc__cuda::info() {
     typedef Vt_func_crc__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -1912,7 +1913,7 @@ const VlcuDesignInfo& Vt_func_crc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x3a3eb0dd5c930618ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x3a3eb0dd5c930618ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt_func_endian___024root final {
 
 struct Vt_func_endian__cuda final {
     typedef Vt_func_endian___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -670,7 +671,7 @@ struct Vt_func_endian__cuda final {
 
 const VlcuDesignInfo& Vt_func_endian__cuda::info() {
     typedef Vt_func_endian__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_0", "__VdfgRegularize_h6e95ff9d_0_0", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_0},
@@ -702,7 +703,7 @@ const VlcuDesignInfo& Vt_func_endian__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0xa10ff6cf8a285155ULL, nullptr, 12, 12};
+        saveOrder, 17, 0, 0xa10ff6cf8a285155ULL, nullptr, 12, 12, 0};
     return s;
 }
 

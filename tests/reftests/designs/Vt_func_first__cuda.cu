@@ -33,6 +33,7 @@ struct Vt_func_first___024root final {
 
 struct Vt_func_first__cuda final {
     typedef Vt_func_first___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -312,7 +313,7 @@ struct Vt_func_first__cuda final {
 
 const VlcuDesignInfo& Vt_func_first__cuda::info() {
     typedef Vt_func_first__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__cyc},
@@ -336,7 +337,7 @@ const VlcuDesignInfo& Vt_func_first__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x9e8d507ec2512faeULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x9e8d507ec2512faeULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -34,6 +34,7 @@ struct Vt_func_grey___024root final {
 
 struct Vt_func_grey__cuda final {
     typedef Vt_func_grey___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -360,7 +361,7 @@ struct Vt_func_grey__cuda final {
 
 const VlcuDesignInfo& Vt_func_grey__cuda::info() {
     typedef Vt_func_grey__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__g3", "t.g3", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_t__DOT__g3},
@@ -385,7 +386,7 @@ const VlcuDesignInfo& Vt_func_grey__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x97360986d40817c1ULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x97360986d40817c1ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -37,6 +37,7 @@ struct Vt_func_mlog2___024root final {
 
 struct Vt_func_mlog2__cuda final {
     typedef Vt_func_mlog2___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 44,
@@ -584,7 +585,7 @@ struct Vt_func_mlog2__cuda final {
 
 const VlcuDesignInfo& Vt_func_mlog2__cuda::info() {
     typedef Vt_func_mlog2__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -612,7 +613,7 @@ const VlcuDesignInfo& Vt_func_mlog2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x4e23803a339bea9dULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0x4e23803a339bea9dULL, nullptr, 12, 12, 0};
     return s;
 }
 

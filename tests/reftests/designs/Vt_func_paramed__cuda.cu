@@ -33,6 +33,7 @@ struct Vt_func_paramed___024root final {
 
 struct Vt_func_paramed__cuda final {
     typedef Vt_func_paramed___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 38,
@@ -494,7 +495,7 @@ struct Vt_func_paramed__cuda final {
 
 const VlcuDesignInfo& Vt_func_paramed__cuda::info() {
     typedef Vt_func_paramed__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__out_x", "t.out_x", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_t__DOT__out_x},
@@ -523,7 +524,7 @@ const VlcuDesignInfo& Vt_func_paramed__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xfc304cab71eea602ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0xfc304cab71eea602ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_func_plog___024root final {
 
 struct Vt_func_plog__cuda final {
     typedef Vt_func_plog___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -415,7 +416,7 @@ struct Vt_func_plog__cuda final {
 
 const VlcuDesignInfo& Vt_func_plog__cuda::info() {
     typedef Vt_func_plog__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__rst_n", "t.rst_n", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__rst_n},
@@ -446,7 +447,7 @@ const VlcuDesignInfo& Vt_func_plog__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xc51f971ebd0fa08fULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0xc51f971ebd0fa08fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -34,6 +34,7 @@ struct Vt_func_sum___024root final {
 
 struct Vt_func_sum__cuda final {
     typedef Vt_func_sum___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -343,7 +344,7 @@ struct Vt_func_sum__cuda final {
 
 const VlcuDesignInfo& Vt_func_sum__cuda::info() {
     typedef Vt_func_sum__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -368,7 +369,7 @@ const VlcuDesignInfo& Vt_func_sum__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x6759cf82bf5477e7ULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x6759cf82bf5477e7ULL, nullptr, 12, 12, 0};
     return s;
 }
 

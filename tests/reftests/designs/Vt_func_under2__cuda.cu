@@ -32,6 +32,7 @@ struct Vt_func_under2___024root final {
 
 struct Vt_func_under2__cuda final {
     typedef Vt_func_under2___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -279,7 +280,7 @@ struct Vt_func_under2__cuda final {
 
 const VlcuDesignInfo& Vt_func_under2__cuda::info() {
     typedef Vt_func_under2__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"val", "val", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_val},
@@ -302,7 +303,7 @@ const VlcuDesignInfo& Vt_func_under2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xb284b72e9df3828cULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xb284b72e9df3828cULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -32,6 +32,7 @@ struct Vt_func_under___024root final {
 
 struct Vt_func_under__cuda final {
     typedef Vt_func_under___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -303,7 +304,7 @@ struct Vt_func_under__cuda final {
 
 const VlcuDesignInfo& Vt_func_under__cuda::info() {
     typedef Vt_func_under__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__counter", "t.counter", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__counter},
@@ -326,7 +327,7 @@ const VlcuDesignInfo& Vt_func_under__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xf3cb9702e6105dfdULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xf3cb9702e6105dfdULL, nullptr, 12, 12, 0};
     return s;
 }
 

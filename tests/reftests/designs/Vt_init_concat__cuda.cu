@@ -35,6 +35,7 @@ struct Vt_init_concat___024root final {
 
 struct Vt_init_concat__cuda final {
     typedef Vt_init_concat___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -340,7 +341,7 @@ struct Vt_init_concat__cuda final {
 
 const VlcuDesignInfo& Vt_init_concat__cuda::info() {
     typedef Vt_init_concat__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__wr_en", "t.wr_en", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__wr_en},
@@ -366,7 +367,7 @@ const VlcuDesignInfo& Vt_init_concat__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xa178e7f10bed624bULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0xa178e7f10bed624bULL, nullptr, 12, 12, 0};
     return s;
 }
 

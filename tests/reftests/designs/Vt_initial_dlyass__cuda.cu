@@ -37,6 +37,7 @@ struct Vt_initial_dlyass___024root final {
 
 struct Vt_initial_dlyass__cuda final {
     typedef Vt_initial_dlyass___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -344,7 +345,7 @@ struct Vt_initial_dlyass__cuda final {
 
 const VlcuDesignInfo& Vt_initial_dlyass__cuda::info() {
     typedef Vt_initial_dlyass__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdlySet__t__DOT__a__v0", "__VdlySet__t.a__v0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VdlySet__t__DOT__a__v0},
@@ -372,7 +373,7 @@ const VlcuDesignInfo& Vt_initial_dlyass__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x81b5e694b99147f5ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0x81b5e694b99147f5ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_inst_dff___024root final {
 
 struct Vt_inst_dff__cuda final {
     typedef Vt_inst_dff___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -397,7 +398,7 @@ struct Vt_inst_dff__cuda final {
 
 const VlcuDesignInfo& Vt_inst_dff__cuda::info() {
     typedef Vt_inst_dff__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__rst_l", "t.rst_l", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__rst_l},
@@ -428,7 +429,7 @@ const VlcuDesignInfo& Vt_inst_dff__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xf5803a63c3c8f249ULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0xf5803a63c3c8f249ULL, nullptr, 12, 12, 0};
     return s;
 }
 

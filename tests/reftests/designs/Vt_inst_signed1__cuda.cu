@@ -33,6 +33,7 @@ struct Vt_inst_signed1___024root final {
 
 struct Vt_inst_signed1__cuda final {
     typedef Vt_inst_signed1___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -313,7 +314,7 @@ struct Vt_inst_signed1__cuda final {
 
 const VlcuDesignInfo& Vt_inst_signed1__cuda::info() {
     typedef Vt_inst_signed1__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__i", "t.i", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__i},
@@ -337,7 +338,7 @@ const VlcuDesignInfo& Vt_inst_signed1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xba8bc5c7edd22e83ULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0xba8bc5c7edd22e83ULL, nullptr, 12, 12, 0};
     return s;
 }
 

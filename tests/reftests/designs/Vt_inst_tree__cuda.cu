@@ -34,6 +34,7 @@ struct Vt_inst_tree___024root final {
 
 struct Vt_inst_tree__cuda final {
     typedef Vt_inst_tree___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -451,7 +452,7 @@ struct Vt_inst_tree__cuda final {
 
 const VlcuDesignInfo& Vt_inst_tree__cuda::info() {
     typedef Vt_inst_tree__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__printclk", "t.printclk", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__printclk},
@@ -481,7 +482,7 @@ const VlcuDesignInfo& Vt_inst_tree__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x69e049e1d04eee46ULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0x69e049e1d04eee46ULL, nullptr, 12, 12, 0};
     return s;
 }
 

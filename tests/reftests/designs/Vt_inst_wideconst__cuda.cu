@@ -33,6 +33,7 @@ struct Vt_inst_wideconst___024root final {
 
 struct Vt_inst_wideconst__cuda final {
     typedef Vt_inst_wideconst___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -421,7 +422,7 @@ struct Vt_inst_wideconst__cuda final {
 
 const VlcuDesignInfo& Vt_inst_wideconst__cuda::info() {
     typedef Vt_inst_wideconst__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -450,7 +451,7 @@ const VlcuDesignInfo& Vt_inst_wideconst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xb2cf962fb28103abULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0xb2cf962fb28103abULL, nullptr, 12, 12, 0};
     return s;
 }
 

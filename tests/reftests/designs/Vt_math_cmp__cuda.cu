@@ -61,11 +61,11 @@ struct Vt_math_cmp___024root final {
     QData/*62:0*/ t__DOT__p63__DOT__bs;
     VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p128__DOT__results;  // run-time indexed: shared memory [index][lane]
     VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p126__DOT__results;  // run-time indexed: shared memory [index][lane]
-    VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p72__DOT__results;  // run-time indexed: shared memory [index][lane]
-    VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p64__DOT__results;  // run-time indexed: shared memory [index][lane]
-    VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p63__DOT__results;  // run-time indexed: shared memory [index][lane]
-    VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p32__DOT__results;  // run-time indexed: shared memory [index][lane]
-    VlcuMdArray<VlcuSharedArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p4__DOT__results;  // run-time indexed: shared memory [index][lane]
+    VlcuMdArray<VlcuLocalArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p72__DOT__results;  // thread-local memory
+    VlcuMdArray<VlcuLocalArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p64__DOT__results;  // thread-local memory
+    VlcuMdArray<VlcuLocalArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p63__DOT__results;  // thread-local memory
+    VlcuMdArray<VlcuLocalArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p32__DOT__results;  // thread-local memory
+    VlcuMdArray<VlcuLocalArray<CData/*7:0*/, 25>, 5, 5> t__DOT__p4__DOT__results;  // thread-local memory
     VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
@@ -74,6 +74,7 @@ struct Vt_math_cmp___024root final {
 
 struct Vt_math_cmp__cuda final {
     typedef Vt_math_cmp___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 188,
@@ -136,26 +137,26 @@ struct Vt_math_cmp__cuda final {
         kTouchedWriteBytes = 201,  // S_state_wr
     };
     struct Locals final {
+        CData/*7:0*/ t__DOT__p72__DOT__results[25];
+        CData/*7:0*/ t__DOT__p64__DOT__results[25];
+        CData/*7:0*/ t__DOT__p63__DOT__results[25];
+        CData/*7:0*/ t__DOT__p32__DOT__results[25];
+        CData/*7:0*/ t__DOT__p4__DOT__results[25];
     };
     struct Shared final {
         CData/*7:0*/ t__DOT__p128__DOT__results[25][VLCU_BLOCK];
         CData/*7:0*/ t__DOT__p126__DOT__results[25][VLCU_BLOCK];
-        CData/*7:0*/ t__DOT__p72__DOT__results[25][VLCU_BLOCK];
-        CData/*7:0*/ t__DOT__p64__DOT__results[25][VLCU_BLOCK];
-        CData/*7:0*/ t__DOT__p63__DOT__results[25][VLCU_BLOCK];
-        CData/*7:0*/ t__DOT__p32__DOT__results[25][VLCU_BLOCK];
-        CData/*7:0*/ t__DOT__p4__DOT__results[25][VLCU_BLOCK];
     };
     VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
         (void)l; (void)sh; (void)st; (void)i;
         s.vlNamep = "TOP";
         s.t__DOT__p128__DOT__results.bind(sh.t__DOT__p128__DOT__results, threadIdx.x);
         s.t__DOT__p126__DOT__results.bind(sh.t__DOT__p126__DOT__results, threadIdx.x);
-        s.t__DOT__p72__DOT__results.bind(sh.t__DOT__p72__DOT__results, threadIdx.x);
-        s.t__DOT__p64__DOT__results.bind(sh.t__DOT__p64__DOT__results, threadIdx.x);
-        s.t__DOT__p63__DOT__results.bind(sh.t__DOT__p63__DOT__results, threadIdx.x);
-        s.t__DOT__p32__DOT__results.bind(sh.t__DOT__p32__DOT__results, threadIdx.x);
-        s.t__DOT__p4__DOT__results.bind(sh.t__DOT__p4__DOT__results, threadIdx.x);
+        s.t__DOT__p72__DOT__results.bind(l.t__DOT__p72__DOT__results);
+        s.t__DOT__p64__DOT__results.bind(l.t__DOT__p64__DOT__results);
+        s.t__DOT__p63__DOT__results.bind(l.t__DOT__p63__DOT__results);
+        s.t__DOT__p32__DOT__results.bind(l.t__DOT__p32__DOT__results);
+        s.t__DOT__p4__DOT__results.bind(l.t__DOT__p4__DOT__results);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
@@ -1801,7 +1802,7 @@ struct Vt_math_cmp__cuda final {
 
 const VlcuDesignInfo& Vt_math_cmp__cuda::info() {
     typedef Vt_math_cmp__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__index_a", "t.index_a", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_t__DOT__index_a},
@@ -1871,7 +1872,7 @@ const VlcuDesignInfo& Vt_math_cmp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 8, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 55, 0, 0x4abfb8a786cb87a9ULL, nullptr, 12, 12};
+        saveOrder, 55, 0, 0x4abfb8a786cb87a9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

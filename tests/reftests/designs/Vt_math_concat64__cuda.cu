@@ -33,6 +33,7 @@ struct Vt_math_concat64___024root final {
 
 struct Vt_math_concat64__cuda final {
     typedef Vt_math_concat64___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 72,
@@ -1316,7 +1317,7 @@ struct Vt_math_concat64__cuda final {
 
 const VlcuDesignInfo& Vt_math_concat64__cuda::info() {
     typedef Vt_math_concat64__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -1345,7 +1346,7 @@ const VlcuDesignInfo& Vt_math_concat64__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x9246ce20bf52d8bdULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x9246ce20bf52d8bdULL, nullptr, 12, 12, 0};
     return s;
 }
 

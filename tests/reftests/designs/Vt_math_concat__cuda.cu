@@ -42,6 +42,7 @@ struct Vt_math_concat___024root final {
 
 struct Vt_math_concat__cuda final {
     typedef Vt_math_concat___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 96,
@@ -1931,7 +1932,7 @@ struct Vt_math_concat__cuda final {
 
 const VlcuDesignInfo& Vt_math_concat__cuda::info() {
     typedef Vt_math_concat__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -1959,7 +1960,7 @@ const VlcuDesignInfo& Vt_math_concat__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xac53cb927fecff3bULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xac53cb927fecff3bULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_math_cond_clean___024root final {
 
 struct Vt_math_cond_clean__cuda final {
     typedef Vt_math_cond_clean___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -460,7 +461,7 @@ struct Vt_math_cond_clean__cuda final {
 
 const VlcuDesignInfo& Vt_math_cond_clean__cuda::info() {
     typedef Vt_math_cond_clean__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__next", "t.next", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__next},
@@ -489,7 +490,7 @@ const VlcuDesignInfo& Vt_math_cond_clean__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x7453f98be1924a2aULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x7453f98be1924a2aULL, nullptr, 12, 12, 0};
     return s;
 }
 

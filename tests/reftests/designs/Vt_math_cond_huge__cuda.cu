@@ -34,6 +34,7 @@ struct Vt_math_cond_huge___024root final {
 
 struct Vt_math_cond_huge__cuda final {
     typedef Vt_math_cond_huge___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 80,
@@ -2496,7 +2497,7 @@ struct Vt_math_cond_huge__cuda final {
 
 const VlcuDesignInfo& Vt_math_cond_huge__cuda::info() {
     typedef Vt_math_cond_huge__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_1", "__VdfgRegularize_h6e95ff9d_0_1", VLCU_MEMBER_STATE, 1, 0, 1, 6, 5, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_1},
@@ -2526,7 +2527,7 @@ const VlcuDesignInfo& Vt_math_cond_huge__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0xd0a17948079424eULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0xd0a17948079424eULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -34,6 +34,7 @@ struct Vt_math_div0___024root final {
 
 struct Vt_math_div0__cuda final {
     typedef Vt_math_div0___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_y = 44,
@@ -261,7 +262,7 @@ struct Vt_math_div0__cuda final {
 
 const VlcuDesignInfo& Vt_math_div0__cuda::info() {
     typedef Vt_math_div0__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"y", "y", VLCU_MEMBER_OUT, 1, 0, 1, 4, 3, 0, T::OFF_y},
         {"d2", "d2", VLCU_MEMBER_OUT, 4, 0, 1, 32, 31, 0, T::OFF_d2},
@@ -286,7 +287,7 @@ const VlcuDesignInfo& Vt_math_div0__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x97f7bbf8a8d23cd8ULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x97f7bbf8a8d23cd8ULL, nullptr, 12, 12, 0};
     return s;
 }
 

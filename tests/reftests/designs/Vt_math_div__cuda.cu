@@ -52,6 +52,7 @@ struct Vt_math_div___024root final {
 
 struct Vt_math_div__cuda final {
     typedef Vt_math_div___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 120,
@@ -667,7 +668,7 @@ struct Vt_math_div__cuda final {
 
 const VlcuDesignInfo& Vt_math_div__cuda::info() {
     typedef Vt_math_div__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -701,7 +702,7 @@ const VlcuDesignInfo& Vt_math_div__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x841edae0554c77afULL, nullptr, 12, 12};
+        saveOrder, 19, 0, 0x841edae0554c77afULL, nullptr, 12, 12, 0};
     return s;
 }
 

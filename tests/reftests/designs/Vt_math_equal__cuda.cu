@@ -34,6 +34,7 @@ struct Vt_math_equal___024root final {
 
 struct Vt_math_equal__cuda final {
     typedef Vt_math_equal___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -397,7 +398,7 @@ struct Vt_math_equal__cuda final {
 
 const VlcuDesignInfo& Vt_math_equal__cuda::info() {
     typedef Vt_math_equal__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT___guard1", "t._guard1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT___guard1},
@@ -427,7 +428,7 @@ const VlcuDesignInfo& Vt_math_equal__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x310eafb1c1d8873aULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0x310eafb1c1d8873aULL, nullptr, 12, 12, 0};
     return s;
 }
 

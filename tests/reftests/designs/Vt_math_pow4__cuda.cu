@@ -37,6 +37,7 @@ struct Vt_math_pow4___024root final {
 
 struct Vt_math_pow4__cuda final {
     typedef Vt_math_pow4___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 36,
@@ -405,7 +406,7 @@ struct Vt_math_pow4__cuda final {
 
 const VlcuDesignInfo& Vt_math_pow4__cuda::info() {
     typedef Vt_math_pow4__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__a", "t.a", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__a},
@@ -433,7 +434,7 @@ const VlcuDesignInfo& Vt_math_pow4__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xe71ef57e3bf894a0ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xe71ef57e3bf894a0ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -34,6 +34,7 @@ struct Vt_math_pow5___024root final {
 
 struct Vt_math_pow5__cuda final {
     typedef Vt_math_pow5___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 80,
@@ -483,7 +484,7 @@ struct Vt_math_pow5__cuda final {
 
 const VlcuDesignInfo& Vt_math_pow5__cuda::info() {
     typedef Vt_math_pow5__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -513,7 +514,7 @@ const VlcuDesignInfo& Vt_math_pow5__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x9ea009a89d58176aULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0x9ea009a89d58176aULL, nullptr, 12, 12, 0};
     return s;
 }
 

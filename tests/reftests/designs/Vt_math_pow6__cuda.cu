@@ -40,6 +40,7 @@ struct Vt_math_pow6___024root final {
 
 struct Vt_math_pow6__cuda final {
     typedef Vt_math_pow6___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_a = 146,
@@ -376,7 +377,7 @@ struct Vt_math_pow6__cuda final {
 
 const VlcuDesignInfo& Vt_math_pow6__cuda::info() {
     typedef Vt_math_pow6__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"a", "a", VLCU_MEMBER_IN, 1, 0, 1, 4, 3, 0, T::OFF_a},
         {"a40", "a40", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_a40},
@@ -412,7 +413,7 @@ const VlcuDesignInfo& Vt_math_pow6__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x9c4ac0d2340936bULL, nullptr, 12, 12};
+        saveOrder, 21, 0, 0x9c4ac0d2340936bULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -93,6 +93,7 @@ struct Vt_math_precedence___024root final {
 
 struct Vt_math_precedence__cuda final {
     typedef Vt_math_precedence___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -934,7 +935,7 @@ struct Vt_math_precedence__cuda final {
 
 const VlcuDesignInfo& Vt_math_precedence__cuda::info() {
     typedef Vt_math_precedence__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_0", "__VdfgRegularize_h6e95ff9d_0_0", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_0},
@@ -967,7 +968,7 @@ const VlcuDesignInfo& Vt_math_precedence__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x1ae6ddec8e4e10b3ULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0x1ae6ddec8e4e10b3ULL, nullptr, 12, 12, 0};
     return s;
 }
 

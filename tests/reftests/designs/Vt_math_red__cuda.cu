@@ -35,6 +35,7 @@ struct Vt_math_red___024root final {
 
 struct Vt_math_red__cuda final {
     typedef Vt_math_red___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 44,
@@ -522,7 +523,7 @@ struct Vt_math_red__cuda final {
 
 const VlcuDesignInfo& Vt_math_red__cuda::info() {
     typedef Vt_math_red__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__and_reduce", "t.and_reduce", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__and_reduce},
@@ -553,7 +554,7 @@ const VlcuDesignInfo& Vt_math_red__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 16, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xee3bb61fd46d65f8ULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0xee3bb61fd46d65f8ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_math_shift_sel___024root final {
 
 struct Vt_math_shift_sel__cuda final {
     typedef Vt_math_shift_sel___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -428,7 +429,7 @@ struct Vt_math_shift_sel__cuda final {
 
 const VlcuDesignInfo& Vt_math_shift_sel__cuda::info() {
     typedef Vt_math_shift_sel__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__out1", "t.out1", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__out1},
@@ -457,7 +458,7 @@ const VlcuDesignInfo& Vt_math_shift_sel__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xa8d0c3fd06007d19ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0xa8d0c3fd06007d19ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -96,6 +96,7 @@ struct Vt_math_signed___024root final {
 
 struct Vt_math_signed__cuda final {
     typedef Vt_math_signed___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 490,
@@ -1753,7 +1754,7 @@ struct Vt_math_signed__cuda final {
 
 const VlcuDesignInfo& Vt_math_signed__cuda::info() {
     typedef Vt_math_signed__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__b", "t.b", VLCU_MEMBER_STATE, 1, 0, 1, 5, 4, 0, T::OFF_t__DOT__b},
@@ -1845,7 +1846,7 @@ const VlcuDesignInfo& Vt_math_signed__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 77, 0, 0x99599e39f227d7e3ULL, nullptr, 12, 12};
+        saveOrder, 77, 0, 0x99599e39f227d7e3ULL, nullptr, 12, 12, 0};
     return s;
 }
 

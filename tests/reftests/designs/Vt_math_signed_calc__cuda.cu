@@ -33,6 +33,7 @@ struct Vt_math_signed_calc___024root final {
 
 struct Vt_math_signed_calc__cuda final {
     typedef Vt_math_signed_calc___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -296,7 +297,7 @@ struct Vt_math_signed_calc__cuda final {
 
 const VlcuDesignInfo& Vt_math_signed_calc__cuda::info() {
     typedef Vt_math_signed_calc__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__in0", "t.in0", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__in0},
@@ -320,7 +321,7 @@ const VlcuDesignInfo& Vt_math_signed_calc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x599aa2a14f556933ULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x599aa2a14f556933ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -52,6 +52,7 @@ struct Vt_math_vgen___024root final {
 
 struct Vt_math_vgen__cuda final {
     typedef Vt_math_vgen___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 224,
@@ -688,7 +689,7 @@ struct Vt_math_vgen__cuda final {
 
 const VlcuDesignInfo& Vt_math_vgen__cuda::info() {
     typedef Vt_math_vgen__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__check", "t.check", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__check},
@@ -736,7 +737,7 @@ const VlcuDesignInfo& Vt_math_vgen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 33, 0, 0xf0c2b11053185e24ULL, nullptr, 12, 12};
+        saveOrder, 33, 0, 0xf0c2b11053185e24ULL, nullptr, 12, 12, 0};
     return s;
 }
 

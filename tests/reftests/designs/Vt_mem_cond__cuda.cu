@@ -34,6 +34,7 @@ struct Vt_mem_cond___024root final {
 
 struct Vt_mem_cond__cuda final {
     typedef Vt_mem_cond___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -297,7 +298,7 @@ struct Vt_mem_cond__cuda final {
 
 const VlcuDesignInfo& Vt_mem_cond__cuda::info() {
     typedef Vt_mem_cond__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"en", "en", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_en},
@@ -322,7 +323,7 @@ const VlcuDesignInfo& Vt_mem_cond__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x91a10df033baf09cULL, nullptr, 12, 12};
+        saveOrder, 10, 0, 0x91a10df033baf09cULL, nullptr, 12, 12, 0};
     return s;
 }
 

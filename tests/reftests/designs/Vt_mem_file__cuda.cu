@@ -44,6 +44,7 @@ struct Vt_mem_file___024root final {
 
 struct Vt_mem_file__cuda final {
     typedef Vt_mem_file___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 96,
@@ -640,7 +641,7 @@ struct Vt_mem_file__cuda final {
 
 const VlcuDesignInfo& Vt_mem_file__cuda::info() {
     typedef Vt_mem_file__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__file__DOT__m_w1_onehotwe", "t.file.m_w1_onehotwe", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__file__DOT__m_w1_onehotwe},
@@ -680,7 +681,7 @@ const VlcuDesignInfo& Vt_mem_file__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 25, 0, 0xf339c4d3e4fdfc3dULL, nullptr, 12, 12};
+        saveOrder, 25, 0, 0xf339c4d3e4fdfc3dULL, nullptr, 12, 12, 0};
     return s;
 }
 

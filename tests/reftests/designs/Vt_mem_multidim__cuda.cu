@@ -37,6 +37,7 @@ struct Vt_mem_multidim___024root final {
 
 struct Vt_mem_multidim__cuda final {
     typedef Vt_mem_multidim___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 488,
@@ -824,7 +825,7 @@ struct Vt_mem_multidim__cuda final {
 
 const VlcuDesignInfo& Vt_mem_multidim__cuda::info() {
     typedef Vt_mem_multidim__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__narrow", "t.narrow", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__narrow},
@@ -857,7 +858,7 @@ const VlcuDesignInfo& Vt_mem_multidim__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x87da0bcdd9ba2f6dULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0x87da0bcdd9ba2f6dULL, nullptr, 12, 12, 0};
     return s;
 }
 

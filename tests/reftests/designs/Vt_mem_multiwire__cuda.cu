@@ -36,6 +36,7 @@ struct Vt_mem_multiwire___024root final {
 
 struct Vt_mem_multiwire__cuda final {
     typedef Vt_mem_multiwire___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -488,7 +489,7 @@ struct Vt_mem_multiwire__cuda final {
 
 const VlcuDesignInfo& Vt_mem_multiwire__cuda::info() {
     typedef Vt_mem_multiwire__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -515,7 +516,7 @@ const VlcuDesignInfo& Vt_mem_multiwire__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x6978f02d6371a044ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0x6978f02d6371a044ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -69,6 +69,7 @@ struct Vt_opt_const_red___024root final {
 
 struct Vt_opt_const_red__cuda final {
     typedef Vt_opt_const_red___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 60,
@@ -861,7 +862,7 @@ struct Vt_opt_const_red__cuda final {
 
 const VlcuDesignInfo& Vt_opt_const_red__cuda::info() {
     typedef Vt_opt_const_red__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__a1", "t.a1", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__a1},
@@ -926,7 +927,7 @@ const VlcuDesignInfo& Vt_opt_const_red__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 50, 0, 0xdbd1eb0e99358474ULL, nullptr, 12, 12};
+        saveOrder, 50, 0, 0xdbd1eb0e99358474ULL, nullptr, 12, 12, 0};
     return s;
 }
 

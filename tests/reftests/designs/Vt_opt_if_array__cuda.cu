@@ -32,6 +32,7 @@ struct Vt_opt_if_array___024root final {
 
 struct Vt_opt_if_array__cuda final {
     typedef Vt_opt_if_array___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -375,7 +376,7 @@ struct Vt_opt_if_array__cuda final {
 
 const VlcuDesignInfo& Vt_opt_if_array__cuda::info() {
     typedef Vt_opt_if_array__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"rstn", "rstn", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_rstn},
@@ -403,7 +404,7 @@ const VlcuDesignInfo& Vt_opt_if_array__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x6d500e206a2acbeULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0x6d500e206a2acbeULL, nullptr, 12, 12, 0};
     return s;
 }
 

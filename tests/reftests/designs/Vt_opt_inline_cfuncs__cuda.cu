@@ -48,6 +48,7 @@ struct Vt_opt_inline_cfuncs___024root final {
 
 struct Vt_opt_inline_cfuncs__cuda final {
     typedef Vt_opt_inline_cfuncs___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 104,
@@ -512,7 +513,7 @@ struct Vt_opt_inline_cfuncs__cuda final {
 
 const VlcuDesignInfo& Vt_opt_inline_cfuncs__cuda::info() {
     typedef Vt_opt_inline_cfuncs__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__gen_sub__BRA__7__KET____DOT__sub_inst__DOT__local_b", "t.gen_sub[7].sub_inst.local_b", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__gen_sub__BRA__7__KET____DOT__sub_inst__DOT__local_b},
@@ -556,7 +557,7 @@ const VlcuDesignInfo& Vt_opt_inline_cfuncs__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x184a4089aa3972fbULL, nullptr, 12, 12};
+        saveOrder, 29, 0, 0x184a4089aa3972fbULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -53,6 +53,7 @@ struct Vt_opt_table_display___024root final {
 
 struct Vt_opt_table_display__cuda final {
     typedef Vt_opt_table_display___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -318,7 +319,7 @@ struct Vt_opt_table_display__cuda final {
 
 const VlcuDesignInfo& Vt_opt_table_display__cuda::info() {
     typedef Vt_opt_table_display__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"test", "test", VLCU_MEMBER_OUT, 1, 0, 1, 6, 5, 0, T::OFF_test},
@@ -342,7 +343,7 @@ const VlcuDesignInfo& Vt_opt_table_display__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x9693bc1fb797c01fULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x9693bc1fb797c01fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -116,6 +116,7 @@ struct Vt_opt_table_fsm___024root final {
 
 struct Vt_opt_table_fsm__cuda final {
     typedef Vt_opt_table_fsm___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -559,7 +560,7 @@ struct Vt_opt_table_fsm__cuda final {
 
 const VlcuDesignInfo& Vt_opt_table_fsm__cuda::info() {
     typedef Vt_opt_table_fsm__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__reset", "t.reset", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__reset},
@@ -597,7 +598,7 @@ const VlcuDesignInfo& Vt_opt_table_fsm__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0xd876d94756cb84f5ULL, nullptr, 12, 12};
+        saveOrder, 23, 0, 0xd876d94756cb84f5ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -45,6 +45,7 @@ struct Vt_opt_table_sparse___024root final {
 
 struct Vt_opt_table_sparse__cuda final {
     typedef Vt_opt_table_sparse___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -398,7 +399,7 @@ struct Vt_opt_table_sparse__cuda final {
 
 const VlcuDesignInfo& Vt_opt_table_sparse__cuda::info() {
     typedef Vt_opt_table_sparse__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_t__DOT__cyc},
@@ -425,7 +426,7 @@ const VlcuDesignInfo& Vt_opt_table_sparse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xa4c5fb627309d674ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xa4c5fb627309d674ULL, nullptr, 12, 12, 0};
     return s;
 }
 

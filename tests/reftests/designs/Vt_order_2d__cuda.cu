@@ -36,6 +36,7 @@ struct Vt_order_2d___024root final {
 
 struct Vt_order_2d__cuda final {
     typedef Vt_order_2d___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -497,7 +498,7 @@ struct Vt_order_2d__cuda final {
 
 const VlcuDesignInfo& Vt_order_2d__cuda::info() {
     typedef Vt_order_2d__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlDidInit", "__VstlDidInit", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlDidInit},
@@ -529,7 +530,7 @@ const VlcuDesignInfo& Vt_order_2d__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x37f049685b97fd10ULL, nullptr, 12, 12};
+        saveOrder, 17, 0, 0x37f049685b97fd10ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -47,6 +47,7 @@ struct Vt_order_clkinst___024root final {
 
 struct Vt_order_clkinst__cuda final {
     typedef Vt_order_clkinst___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 104,
@@ -659,7 +660,7 @@ struct Vt_order_clkinst__cuda final {
 
 const VlcuDesignInfo& Vt_order_clkinst__cuda::info() {
     typedef Vt_order_clkinst__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__c1_start", "t.c1_start", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__c1_start},
@@ -702,7 +703,7 @@ const VlcuDesignInfo& Vt_order_clkinst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 28, 0, 0x92fa048cdc30a64aULL, nullptr, 12, 12};
+        saveOrder, 28, 0, 0x92fa048cdc30a64aULL, nullptr, 12, 12, 0};
     return s;
 }
 

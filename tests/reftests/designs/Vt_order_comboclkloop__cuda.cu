@@ -41,6 +41,7 @@ struct Vt_order_comboclkloop___024root final {
 
 struct Vt_order_comboclkloop__cuda final {
     typedef Vt_order_comboclkloop___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 60,
@@ -538,7 +539,7 @@ struct Vt_order_comboclkloop__cuda final {
 
 const VlcuDesignInfo& Vt_order_comboclkloop__cuda::info() {
     typedef Vt_order_comboclkloop__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__run0", "t.run0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__run0},
@@ -575,7 +576,7 @@ const VlcuDesignInfo& Vt_order_comboclkloop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0x174f728ffc59c391ULL, nullptr, 12, 12};
+        saveOrder, 22, 0, 0x174f728ffc59c391ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_order_loop_bad___024root final {
 
 struct Vt_order_loop_bad__cuda final {
     typedef Vt_order_loop_bad___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -317,7 +318,7 @@ struct Vt_order_loop_bad__cuda final {
 
 const VlcuDesignInfo& Vt_order_loop_bad__cuda::info() {
     typedef Vt_order_loop_bad__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__ready", "t.ready", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__ready},
@@ -341,7 +342,7 @@ const VlcuDesignInfo& Vt_order_loop_bad__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x4c7d4bd8fc9a2b2bULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x4c7d4bd8fc9a2b2bULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -37,6 +37,7 @@ struct Vt_order_multialways___024root final {
 
 struct Vt_order_multialways__cuda final {
     typedef Vt_order_multialways___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -405,7 +406,7 @@ struct Vt_order_multialways__cuda final {
 
 const VlcuDesignInfo& Vt_order_multialways__cuda::info() {
     typedef Vt_order_multialways__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -433,7 +434,7 @@ const VlcuDesignInfo& Vt_order_multialways__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x97012b21b72c4103ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0x97012b21b72c4103ULL, nullptr, 12, 12, 0};
     return s;
 }
 

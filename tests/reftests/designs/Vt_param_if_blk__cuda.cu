@@ -41,6 +41,7 @@ struct Vt_param_if_blk___024root final {
 
 struct Vt_param_if_blk__cuda final {
     typedef Vt_param_if_blk___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -533,7 +534,7 @@ struct Vt_param_if_blk__cuda final {
 
 const VlcuDesignInfo& Vt_param_if_blk__cuda::info() {
     typedef Vt_param_if_blk__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__test__DOT__datat__BRA__7__KET__", "t.test.datat[7]", VLCU_MEMBER_STATE, 1, 0, 1, 1, 7, 7, T::OFF_t__DOT__test__DOT__datat__BRA__7__KET__},
@@ -570,7 +571,7 @@ const VlcuDesignInfo& Vt_param_if_blk__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0x7b289fbf142305f1ULL, nullptr, 12, 12};
+        saveOrder, 22, 0, 0x7b289fbf142305f1ULL, nullptr, 12, 12, 0};
     return s;
 }
 

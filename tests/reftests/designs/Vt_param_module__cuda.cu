@@ -25,6 +25,7 @@ struct Vt_param_module___024root final {
 
 struct Vt_param_module__cuda final {
     typedef Vt_param_module___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 0,
@@ -131,7 +132,7 @@ struct Vt_param_module__cuda final {
 
 const VlcuDesignInfo& Vt_param_module__cuda::info() {
     typedef Vt_param_module__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
     };
@@ -147,7 +148,7 @@ const VlcuDesignInfo& Vt_param_module__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0xeafd0b7a228757b3ULL, nullptr, 12, 12};
+        saveOrder, 1, 0, 0xeafd0b7a228757b3ULL, nullptr, 12, 12, 0};
     return s;
 }
 

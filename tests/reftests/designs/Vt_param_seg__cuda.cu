@@ -33,6 +33,7 @@ struct Vt_param_seg___024root final {
 
 struct Vt_param_seg__cuda final {
     typedef Vt_param_seg___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -290,7 +291,7 @@ struct Vt_param_seg__cuda final {
 
 const VlcuDesignInfo& Vt_param_seg__cuda::info() {
     typedef Vt_param_seg__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"syndromes", "syndromes", VLCU_MEMBER_IN, 1, 0, 1, 8, 7, 0, T::OFF_syndromes},
@@ -314,7 +315,7 @@ const VlcuDesignInfo& Vt_param_seg__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x35667d5a421817e4ULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0x35667d5a421817e4ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -24,6 +24,7 @@ struct Vt_param_width_loc_bad___024root final {
 
 struct Vt_param_width_loc_bad__cuda final {
     typedef Vt_param_width_loc_bad___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         kStateBytes = 0,  // S_persist
@@ -115,7 +116,7 @@ struct Vt_param_width_loc_bad__cuda final {
 
 const VlcuDesignInfo& Vt_param_width_loc_bad__cuda::info() {
     typedef Vt_param_width_loc_bad__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
     };
     static const char* const messages[] = {"*-* All Finished *-*\n", nullptr};
@@ -130,7 +131,7 @@ const VlcuDesignInfo& Vt_param_width_loc_bad__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 0, 0, 0xe3b0c44298fc1c14ULL, nullptr, 12, 12};
+        saveOrder, 0, 0, 0xe3b0c44298fc1c14ULL, nullptr, 12, 12, 0};
     return s;
 }
 

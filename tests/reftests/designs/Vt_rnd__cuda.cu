@@ -32,6 +32,7 @@ struct Vt_rnd___024root final {
 
 struct Vt_rnd__cuda final {
     typedef Vt_rnd___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -284,7 +285,7 @@ struct Vt_rnd__cuda final {
 
 const VlcuDesignInfo& Vt_rnd__cuda::info() {
     typedef Vt_rnd__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT___ranit", "t._ranit", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT___ranit},
@@ -307,7 +308,7 @@ const VlcuDesignInfo& Vt_rnd__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xdb94602ad3562a17ULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xdb94602ad3562a17ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -37,6 +37,7 @@ struct Vt_scheduling_1___024root final {
 
 struct Vt_scheduling_1__cuda final {
     typedef Vt_scheduling_1___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 36,
@@ -350,7 +351,7 @@ struct Vt_scheduling_1__cuda final {
 
 const VlcuDesignInfo& Vt_scheduling_1__cuda::info() {
     typedef Vt_scheduling_1__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"top__DOT__clk_half", "top.clk_half", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_top__DOT__clk_half},
@@ -378,7 +379,7 @@ const VlcuDesignInfo& Vt_scheduling_1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x7c41545dfaa25d4cULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0x7c41545dfaa25d4cULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -38,6 +38,7 @@ struct Vt_scheduling_5___024root final {
 
 struct Vt_scheduling_5__cuda final {
     typedef Vt_scheduling_5___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -373,7 +374,7 @@ struct Vt_scheduling_5__cuda final {
 
 const VlcuDesignInfo& Vt_scheduling_5__cuda::info() {
     typedef Vt_scheduling_5__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__start", "t.start", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__start},
@@ -402,7 +403,7 @@ const VlcuDesignInfo& Vt_scheduling_5__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xc58b200cdefccbe9ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0xc58b200cdefccbe9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -39,6 +39,7 @@ struct Vt_select_ascending___024root final {
 
 struct Vt_select_ascending__cuda final {
     typedef Vt_select_ascending___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 60,
@@ -622,7 +623,7 @@ struct Vt_select_ascending__cuda final {
 
 const VlcuDesignInfo& Vt_select_ascending__cuda::info() {
     typedef Vt_select_ascending__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_0", "__VdfgRegularize_h6e95ff9d_0_0", VLCU_MEMBER_STATE, 1, 0, 1, 6, 5, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_0},
@@ -657,7 +658,7 @@ const VlcuDesignInfo& Vt_select_ascending__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x13a78d95ecf6d082ULL, nullptr, 12, 12};
+        saveOrder, 20, 0, 0x13a78d95ecf6d082ULL, nullptr, 12, 12, 0};
     return s;
 }
 

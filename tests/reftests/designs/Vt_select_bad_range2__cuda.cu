@@ -32,6 +32,7 @@ struct Vt_select_bad_range2___024root final {
 
 struct Vt_select_bad_range2__cuda final {
     typedef Vt_select_bad_range2___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -285,7 +286,7 @@ struct Vt_select_bad_range2__cuda final {
 
 const VlcuDesignInfo& Vt_select_bad_range2__cuda::info() {
     typedef Vt_select_bad_range2__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__in", "t.in", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF_t__DOT__in},
@@ -308,7 +309,7 @@ const VlcuDesignInfo& Vt_select_bad_range2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xe4ce32b23f077e8fULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xe4ce32b23f077e8fULL, nullptr, 12, 12, 0};
     return s;
 }
 

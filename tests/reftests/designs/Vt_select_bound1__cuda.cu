@@ -36,6 +36,7 @@ struct Vt_select_bound1___024root final {
 
 struct Vt_select_bound1__cuda final {
     typedef Vt_select_bound1___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -394,7 +395,7 @@ struct Vt_select_bound1__cuda final {
 
 const VlcuDesignInfo& Vt_select_bound1__cuda::info() {
     typedef Vt_select_bound1__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__mask", "t.mask", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF_t__DOT__mask},
@@ -421,7 +422,7 @@ const VlcuDesignInfo& Vt_select_bound1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x6531fddcd83132adULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0x6531fddcd83132adULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_select_index___024root final {
 
 struct Vt_select_index__cuda final {
     typedef Vt_select_index___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -349,7 +350,7 @@ struct Vt_select_index__cuda final {
 
 const VlcuDesignInfo& Vt_select_index__cuda::info() {
     typedef Vt_select_index__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT___ranit", "t._ranit", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT___ranit},
@@ -375,7 +376,7 @@ const VlcuDesignInfo& Vt_select_index__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x10ae18172797f99fULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0x10ae18172797f99fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -28,7 +28,7 @@ struct Vt_select_lhs_oob2___024root final {
     VlcuLocalArray<QData/*63:0*/, 48> t__DOT__test__DOT__m_w0;  // thread-local memory
     VlcuSharedArray<QData/*63:0*/, 24> t__DOT__test__DOT__m_w2;  // run-time indexed: shared memory [index][lane]
     VlcuSharedArray<QData/*63:0*/, 24> t__DOT__test__DOT__m_w4;  // run-time indexed: shared memory [index][lane]
-    VlcuSharedArray<QData/*63:0*/, 24> t__DOT__test__DOT__m_w5;  // run-time indexed: shared memory [index][lane]
+    VlcuLocalArray<QData/*63:0*/, 24> t__DOT__test__DOT__m_w5;  // thread-local memory
     VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
@@ -37,6 +37,7 @@ struct Vt_select_lhs_oob2___024root final {
 
 struct Vt_select_lhs_oob2__cuda final {
     typedef Vt_select_lhs_oob2___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 1008,
@@ -63,11 +64,11 @@ struct Vt_select_lhs_oob2__cuda final {
     };
     struct Locals final {
         QData/*63:0*/ t__DOT__test__DOT__m_w0[48];
+        QData/*63:0*/ t__DOT__test__DOT__m_w5[24];
     };
     struct Shared final {
         QData/*63:0*/ t__DOT__test__DOT__m_w2[24][VLCU_BLOCK];
         QData/*63:0*/ t__DOT__test__DOT__m_w4[24][VLCU_BLOCK];
-        QData/*63:0*/ t__DOT__test__DOT__m_w5[24][VLCU_BLOCK];
     };
     VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
         (void)l; (void)sh; (void)st; (void)i;
@@ -75,7 +76,7 @@ struct Vt_select_lhs_oob2__cuda final {
         s.t__DOT__test__DOT__m_w0.bind(l.t__DOT__test__DOT__m_w0);
         s.t__DOT__test__DOT__m_w2.bind(sh.t__DOT__test__DOT__m_w2, threadIdx.x);
         s.t__DOT__test__DOT__m_w4.bind(sh.t__DOT__test__DOT__m_w4, threadIdx.x);
-        s.t__DOT__test__DOT__m_w5.bind(sh.t__DOT__test__DOT__m_w5, threadIdx.x);
+        s.t__DOT__test__DOT__m_w5.bind(l.t__DOT__test__DOT__m_w5);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
@@ -721,7 +722,7 @@ struct Vt_select_lhs_oob2__cuda final {
 
 const VlcuDesignInfo& Vt_select_lhs_oob2__cuda::info() {
     typedef Vt_select_lhs_oob2__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_0", "__VdfgRegularize_h6e95ff9d_0_0", VLCU_MEMBER_STATE, 1, 0, 1, 5, 4, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_0},
@@ -754,7 +755,7 @@ const VlcuDesignInfo& Vt_select_lhs_oob2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x103a4b7b474dd492ULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0x103a4b7b474dd492ULL, nullptr, 12, 12, 0};
     return s;
 }
 

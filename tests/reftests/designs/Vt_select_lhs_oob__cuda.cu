@@ -37,6 +37,7 @@ struct Vt_select_lhs_oob___024root final {
 
 struct Vt_select_lhs_oob__cuda final {
     typedef Vt_select_lhs_oob___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -2734,7 +2735,7 @@ struct Vt_select_lhs_oob__cuda final {
 
 const VlcuDesignInfo& Vt_select_lhs_oob__cuda::info() {
     typedef Vt_select_lhs_oob__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__mem1d", "t.mem1d", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF_t__DOT__mem1d},
@@ -2762,7 +2763,7 @@ const VlcuDesignInfo& Vt_select_lhs_oob__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xf9c805d031881fc2ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xf9c805d031881fc2ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -25,6 +25,7 @@ struct Vt_select_little_pack___024root final {
 
 struct Vt_select_little_pack__cuda final {
     typedef Vt_select_little_pack___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_t__DOT__pack = 0,
@@ -148,7 +149,7 @@ struct Vt_select_little_pack__cuda final {
 
 const VlcuDesignInfo& Vt_select_little_pack__cuda::info() {
     typedef Vt_select_little_pack__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"t__DOT__pack", "t.pack", VLCU_MEMBER_STATE, 1, 0, 4, 8, 7, 0, T::OFF_t__DOT__pack},
     };
@@ -164,7 +165,7 @@ const VlcuDesignInfo& Vt_select_little_pack__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0x50ab0aeba021a3b2ULL, nullptr, 12, 12};
+        saveOrder, 1, 0, 0x50ab0aeba021a3b2ULL, nullptr, 12, 12, 0};
     return s;
 }
 

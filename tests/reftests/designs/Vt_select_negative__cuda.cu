@@ -35,6 +35,7 @@ struct Vt_select_negative___024root final {
 
 struct Vt_select_negative__cuda final {
     typedef Vt_select_negative___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 60,
@@ -545,7 +546,7 @@ struct Vt_select_negative__cuda final {
 
 const VlcuDesignInfo& Vt_select_negative__cuda::info() {
     typedef Vt_select_negative__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_1", "__VdfgRegularize_h6e95ff9d_0_1", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_1},
@@ -576,7 +577,7 @@ const VlcuDesignInfo& Vt_select_negative__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xf01419856b7f8631ULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0xf01419856b7f8631ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_select_plus___024root final {
 
 struct Vt_select_plus__cuda final {
     typedef Vt_select_plus___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 52,
@@ -825,7 +826,7 @@ struct Vt_select_plus__cuda final {
 
 const VlcuDesignInfo& Vt_select_plus__cuda::info() {
     typedef Vt_select_plus__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__bitn", "t.bitn", VLCU_MEMBER_STATE, 1, 0, 1, 7, 6, 0, T::OFF_t__DOT__bitn},
@@ -856,7 +857,7 @@ const VlcuDesignInfo& Vt_select_plus__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xa20cfb4587de79c2ULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0xa20cfb4587de79c2ULL, nullptr, 12, 12, 0};
     return s;
 }
 

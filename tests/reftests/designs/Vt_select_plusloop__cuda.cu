@@ -32,6 +32,7 @@ struct Vt_select_plusloop___024root final {
 
 struct Vt_select_plusloop__cuda final {
     typedef Vt_select_plusloop___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 52,
@@ -471,7 +472,7 @@ struct Vt_select_plusloop__cuda final {
 
 const VlcuDesignInfo& Vt_select_plusloop__cuda::info() {
     typedef Vt_select_plusloop__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__crc", "t.crc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__crc},
@@ -499,7 +500,7 @@ const VlcuDesignInfo& Vt_select_plusloop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xcd8b4f7314e80764ULL, nullptr, 12, 12};
+        saveOrder, 13, 0, 0xcd8b4f7314e80764ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt_select_runtime_range___024root final {
 
 struct Vt_select_runtime_range__cuda final {
     typedef Vt_select_runtime_range___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 36,
@@ -377,7 +378,7 @@ struct Vt_select_runtime_range__cuda final {
 
 const VlcuDesignInfo& Vt_select_runtime_range__cuda::info() {
     typedef Vt_select_runtime_range__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__index", "t.index", VLCU_MEMBER_STATE, 1, 0, 1, 6, 5, 0, T::OFF_t__DOT__index},
@@ -404,7 +405,7 @@ const VlcuDesignInfo& Vt_select_runtime_range__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xab5ae6ef0e973b13ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xab5ae6ef0e973b13ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -32,6 +32,7 @@ struct Vt_threads_counter___024root final {
 
 struct Vt_threads_counter__cuda final {
     typedef Vt_threads_counter___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -288,7 +289,7 @@ struct Vt_threads_counter__cuda final {
 
 const VlcuDesignInfo& Vt_threads_counter__cuda::info() {
     typedef Vt_threads_counter__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__Vtrigprevexpr___TOP__clk__0", "__Vtrigprevexpr___TOP__clk__0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___Vtrigprevexpr___TOP__clk__0},
@@ -311,7 +312,7 @@ const VlcuDesignInfo& Vt_threads_counter__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x1d22598f10ca98a4ULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0x1d22598f10ca98a4ULL, nullptr, 12, 12, 0};
     return s;
 }
 

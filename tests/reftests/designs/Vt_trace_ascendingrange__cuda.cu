@@ -100,6 +100,7 @@ struct Vt_trace_ascendingrange___024root final {
 
 struct Vt_trace_ascendingrange__cuda final {
     typedef Vt_trace_ascendingrange___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 358,
@@ -794,7 +795,7 @@ struct Vt_trace_ascendingrange__cuda final {
 
 const VlcuDesignInfo& Vt_trace_ascendingrange__cuda::info() {
     typedef Vt_trace_ascendingrange__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__v_b", "t.v_b", VLCU_MEMBER_STATE, 1, 0, 1, 2, 1, 0, T::OFF_t__DOT__v_b},
@@ -838,7 +839,7 @@ const VlcuDesignInfo& Vt_trace_ascendingrange__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x8d500fcbce8c210bULL, nullptr, 12, 12};
+        saveOrder, 29, 0, 0x8d500fcbce8c210bULL, nullptr, 12, 12, 0};
     return s;
 }
 

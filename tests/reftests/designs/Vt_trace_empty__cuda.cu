@@ -32,6 +32,7 @@ struct Vt_trace_empty___024root final {
 
 struct Vt_trace_empty__cuda final {
     typedef Vt_trace_empty___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -289,7 +290,7 @@ struct Vt_trace_empty__cuda final {
 
 const VlcuDesignInfo& Vt_trace_empty__cuda::info() {
     typedef Vt_trace_empty__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__cyc", "t.cyc", VLCU_MEMBER_STATE, 1, 0, 1, 8, 7, 0, T::OFF_t__DOT__cyc},
@@ -312,7 +313,7 @@ const VlcuDesignInfo& Vt_trace_empty__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xe9c57d881c75e2e9ULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0xe9c57d881c75e2e9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_tri_assigndly_nba___024root final {
 
 struct Vt_tri_assigndly_nba__cuda final {
     typedef Vt_tri_assigndly_nba___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 32,
@@ -463,7 +464,7 @@ struct Vt_tri_assigndly_nba__cuda final {
 
 const VlcuDesignInfo& Vt_tri_assigndly_nba__cuda::info() {
     typedef Vt_tri_assigndly_nba__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__tribus", "t.tribus", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__tribus},
@@ -492,7 +493,7 @@ const VlcuDesignInfo& Vt_tri_assigndly_nba__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x3983b5fae076a984ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x3983b5fae076a984ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -33,6 +33,7 @@ struct Vt_tri_eqcase_input___024root final {
 
 struct Vt_tri_eqcase_input__cuda final {
     typedef Vt_tri_eqcase_input___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 24,
@@ -311,7 +312,7 @@ struct Vt_tri_eqcase_input__cuda final {
 
 const VlcuDesignInfo& Vt_tri_eqcase_input__cuda::info() {
     typedef Vt_tri_eqcase_input__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"clk__en0", "clk__en0", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_clk__en0},
@@ -335,7 +336,7 @@ const VlcuDesignInfo& Vt_tri_eqcase_input__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xf542768e5835db55ULL, nullptr, 12, 12};
+        saveOrder, 9, 0, 0xf542768e5835db55ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -35,6 +35,7 @@ struct Vt_unopt_combo___024root final {
 
 struct Vt_unopt_combo__cuda final {
     typedef Vt_unopt_combo___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -551,7 +552,7 @@ struct Vt_unopt_combo__cuda final {
 
 const VlcuDesignInfo& Vt_unopt_combo__cuda::info() {
     typedef Vt_unopt_combo__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VdfgRegularize_h6e95ff9d_0_0", "__VdfgRegularize_h6e95ff9d_0_0", VLCU_MEMBER_STATE, 1, 0, 1, 4, 3, 0, T::OFF___VdfgRegularize_h6e95ff9d_0_0},
@@ -582,7 +583,7 @@ const VlcuDesignInfo& Vt_unopt_combo__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0x3eac535f553cf573ULL, nullptr, 12, 12};
+        saveOrder, 16, 0, 0x3eac535f553cf573ULL, nullptr, 12, 12, 0};
     return s;
 }
 

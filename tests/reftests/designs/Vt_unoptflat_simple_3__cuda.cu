@@ -38,6 +38,7 @@ struct Vt_unoptflat_simple_3___024root final {
 
 struct Vt_unoptflat_simple_3__cuda final {
     typedef Vt_unoptflat_simple_3___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 52,
@@ -548,7 +549,7 @@ struct Vt_unoptflat_simple_3__cuda final {
 
 const VlcuDesignInfo& Vt_unoptflat_simple_3__cuda::info() {
     typedef Vt_unoptflat_simple_3__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__x", "t.x", VLCU_MEMBER_STATE, 1, 0, 1, 3, 2, 0, T::OFF_t__DOT__x},
@@ -582,7 +583,7 @@ const VlcuDesignInfo& Vt_unoptflat_simple_3__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x6ba00a7932f917aeULL, nullptr, 12, 12};
+        saveOrder, 19, 0, 0x6ba00a7932f917aeULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -40,6 +40,7 @@ struct Vt_var_assign_landr___024root final {
 
 struct Vt_var_assign_landr__cuda final {
     typedef Vt_var_assign_landr___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 104,
@@ -638,7 +639,7 @@ struct Vt_var_assign_landr__cuda final {
 
 const VlcuDesignInfo& Vt_var_assign_landr__cuda::info() {
     typedef Vt_var_assign_landr__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"__VstlFirstIteration", "__VstlFirstIteration", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF___VstlFirstIteration},
@@ -668,7 +669,7 @@ const VlcuDesignInfo& Vt_var_assign_landr__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x34d6550d47b2ff85ULL, nullptr, 12, 12};
+        saveOrder, 15, 0, 0x34d6550d47b2ff85ULL, nullptr, 12, 12, 0};
     return s;
 }
 

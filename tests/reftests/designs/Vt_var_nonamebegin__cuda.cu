@@ -26,6 +26,7 @@ struct Vt_var_nonamebegin___024root final {
 
 struct Vt_var_nonamebegin__cuda final {
     typedef Vt_var_nonamebegin___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 0,
@@ -144,7 +145,7 @@ struct Vt_var_nonamebegin__cuda final {
 
 const VlcuDesignInfo& Vt_var_nonamebegin__cuda::info() {
     typedef Vt_var_nonamebegin__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"reset_l", "reset_l", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_reset_l},
@@ -161,7 +162,7 @@ const VlcuDesignInfo& Vt_var_nonamebegin__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 8, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 2, 0, 0x13e4b2e8c15b0b77ULL, nullptr, 12, 12};
+        saveOrder, 2, 0, 0x13e4b2e8c15b0b77ULL, nullptr, 12, 12, 0};
     return s;
 }
 

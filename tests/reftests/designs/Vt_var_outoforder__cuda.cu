@@ -31,6 +31,7 @@ struct Vt_var_outoforder___024root final {
 
 struct Vt_var_outoforder__cuda final {
     typedef Vt_var_outoforder___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 56,
@@ -389,7 +390,7 @@ struct Vt_var_outoforder__cuda final {
 
 const VlcuDesignInfo& Vt_var_outoforder__cuda::info() {
     typedef Vt_var_outoforder__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"t__DOT__q", "t.q", VLCU_MEMBER_STATE, 1, 0, 1, 1, 0, 0, T::OFF_t__DOT__q},
@@ -416,7 +417,7 @@ const VlcuDesignInfo& Vt_var_outoforder__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x722253776c226571ULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0x722253776c226571ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -42,6 +42,7 @@ struct Vt_var_overzero___024root final {
 
 struct Vt_var_overzero__cuda final {
     typedef Vt_var_overzero___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 44,
@@ -553,7 +554,7 @@ struct Vt_var_overzero__cuda final {
 
 const VlcuDesignInfo& Vt_var_overzero__cuda::info() {
     typedef Vt_var_overzero__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"rstn", "rstn", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_rstn},
@@ -591,7 +592,7 @@ const VlcuDesignInfo& Vt_var_overzero__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0xc3119a88b7726f52ULL, nullptr, 12, 12};
+        saveOrder, 23, 0, 0xc3119a88b7726f52ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -32,6 +32,7 @@ struct Vt_var_set_link___024root final {
 
 struct Vt_var_set_link__cuda final {
     typedef Vt_var_set_link___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -286,7 +287,7 @@ struct Vt_var_set_link__cuda final {
 
 const VlcuDesignInfo& Vt_var_set_link__cuda::info() {
     typedef Vt_var_set_link__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"state", "state", VLCU_MEMBER_OUT, 1, 0, 1, 2, 1, 0, T::OFF_state},
@@ -309,7 +310,7 @@ const VlcuDesignInfo& Vt_var_set_link__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x4d0056a6c82523aULL, nullptr, 12, 12};
+        saveOrder, 8, 0, 0x4d0056a6c82523aULL, nullptr, 12, 12, 0};
     return s;
 }
 

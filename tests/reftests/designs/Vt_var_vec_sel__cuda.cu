@@ -38,6 +38,7 @@ struct Vt_var_vec_sel___024root final {
 
 struct Vt_var_vec_sel__cuda final {
     typedef Vt_var_vec_sel___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 20,
@@ -339,7 +340,7 @@ struct Vt_var_vec_sel__cuda final {
 
 const VlcuDesignInfo& Vt_var_vec_sel__cuda::info() {
     typedef Vt_var_vec_sel__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"in3", "in3", VLCU_MEMBER_IN, 1, 0, 1, 4, 3, 0, T::OFF_in3},
@@ -368,7 +369,7 @@ const VlcuDesignInfo& Vt_var_vec_sel__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x8fcc6a5925fd4841ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x8fcc6a5925fd4841ULL, nullptr, 12, 12, 0};
     return s;
 }
 

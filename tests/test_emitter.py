@@ -22,7 +22,10 @@ CASES = [  # (committed model, top-level source, extra flags)
      ["--trace-vcd", "--savable", "--prefix", "Vrv32_soc"]),
     ("wide_bus/Vwide_bus__cuda.cu", "../verilator_b200/csrc/designs/wide_bus/wide_bus.v",
      ["--trace-vcd", "--prefix", "Vwide_bus"]),
+    ("veer_class/Vveer_class__cuda.cu", "../verilator_b200/csrc/designs/veer_class/veer_class.v",
+     ["-Wno-WIDTH", "-Wno-UNOPTFLAT", "-Wno-lint", "-Wno-fatal", "--prefix", "Vveer_class"]),
 ]
+TILED = {"veer_class/Vveer_class__cuda.cu"}
 
 needs_vlite = pytest.mark.skipif(not (os.path.exists(VLITE) and os.path.isdir(REF)),
                                  reason="oracle/_ref/verilator_lite or /root/reference not present")
@@ -44,7 +47,7 @@ def test_committed_model_is_what_the_emitter_prints(tmp_path, model, source, fla
     assert os.path.exists(os.path.join(mdir, f"{prefix}___024root__0.cpp"))
 
 
-@pytest.mark.parametrize("model", [c[0] for c in CASES])
+@pytest.mark.parametrize("model", [c[0] for c in CASES if c[0] not in TILED])
 def test_emitted_model_shape(model):
     text = open(os.path.join(DESIGNS, model)).read()
     for needle in ("#include \"verilated_cuda_launch.h\"", "kStateBytes", "kTouchedReadBytes", "kTraceWords",
@@ -63,9 +66,10 @@ def test_emitted_model_shape(model):
 
 
 @needs_vlite
-def test_two_module_design_is_inlined_and_emitted(tmp_path):
-    """Hierarchy: a child module instantiated with named pins goes through V3LinkCells /
-    V3Inline of the reference and arrives at the emitter flattened into $root."""
+def test_two_module_design_keeps_its_hierarchy(tmp_path):
+    """Hierarchy: a child module marked no_inline_module stays a class of its own
+    (V3Inline), its scope is addressed through vlSymsp / the cell (V3Descope.cpp:95-125), and the
+    emitter prints the tiled form: one struct per module class, Syms as the tile image."""
     src = tmp_path / "two.v"
     src.write_text("""
 module leaf (input clk, input [7:0] d, output reg [7:0] q);
@@ -79,9 +83,18 @@ endmodule
     res = subprocess.run([VLITE, "--cc", "--cuda", "--no-std", "--no-std-waiver", "--Mdir", str(tmp_path / "o"),
                           "--top-module", "two", str(src)],
                          capture_output=True, text=True, env=dict(os.environ, VERILATOR_ROOT=REF))
-    # (the lite front end treats the no_inline pragma as a comment, so `leaf` is inlined)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert os.path.exists(tmp_path / "o" / "Vtwo__cuda.cu")
+    text = (tmp_path / "o" / "Vtwo__cuda.cu").read_text()
+    assert os.path.exists(tmp_path / "o" / "Vtwo_leaf.h")  # the C++ model keeps the class too
+    assert "struct alignas(256) Vtwo_leaf final {" in text and "struct alignas(256) Vtwo__Syms final {" in text
+    assert "Vtwo_leaf TOP__two__DOT__u;" in text and "static constexpr bool kTiled = true;" in text
+    assert re.search(r"Vtwo_leaf\* vlSelf, Vtwo__Syms\* vlSymsp, VlcuContext& vlCtx", text)
+    assert ".v[vlLane]" in text
+    # --no-cuda-stream asks for the register form, which cannot hold a second class
+    res = subprocess.run([VLITE, "--cc", "--cuda", "--no-cuda-stream", "--no-std", "--no-std-waiver", "--Mdir",
+                          str(tmp_path / "o2"), "--top-module", "two", str(src)],
+                         capture_output=True, text=True, env=dict(os.environ, VERILATOR_ROOT=REF))
+    assert res.returncode != 0 and "was not inlined" in res.stdout + res.stderr
 
 
 @needs_vlite

@@ -55,6 +55,7 @@ RUNF_BULK_1D = 0x40
 RUNF_TRACE_CHANGES = 0x80
 RUNF_TB_BEGIN, RUNF_STOP_ON_FINISH, RUNF_STIM_DEVICE, RUNF_OBS_DEVICE, RUNF_STIM_BROADCAST = (
     1, 2, 4, 8, 16)
+FUZZ_RESET_LOW, FUZZ_RESET_HIGH, FUZZ_UNIFORM = 1, 2, 4  # tb_flags of the "fuzz" testbench
 ST_DIDINIT, ST_FINISH, ST_ERROR, ST_STOPPED, ST_FATAL, ST_MSGDROP = 1, 2, 4, 8, 16, 32
 TRACE_HDR = 16
 
@@ -100,6 +101,7 @@ SIGNATURES = {
     "vlcu_commit_staged": (c_i32, [_H]),
     "vlcu_member_device_ptr": (c_i32, [_H, c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64)]),
     "vlcu_member_offset": (c_u32, [_H, c_i32]),
+    "vlcu_tile": (c_u32, [_H]),
     "vlcu_time_inc": (c_i32, [_H, c_u64]),
     "vlcu_eval": (c_i32, [_H]),
     "vlcu_run": (c_i32, [_H, ctypes.POINTER(RunDesc)]),
@@ -268,6 +270,18 @@ class Model:
         keep = []
         if stim is not None:
             stim = np.ascontiguousarray(stim, dtype=np.uint32)
+            # the runtime reads in_words * npad words per eval (in_words with STIM_BROADCAST): a
+            # buffer of any other shape would skew every row, so it is rejected -- except rows of
+            # exactly n columns, which are padded here
+            if flags & RUNF_STIM_BROADCAST:
+                assert stim.shape == (n_evals, self.in_words), (stim.shape, n_evals, self.in_words)
+            else:
+                assert stim.shape[:2] == (n_evals, self.in_words) and stim.shape[2] in (self.n, self.npad), \
+                    (stim.shape, n_evals, self.in_words, self.n, self.npad)
+                if stim.shape[2] != self.npad:
+                    padded = np.zeros((n_evals, self.in_words, self.npad), dtype=np.uint32)
+                    padded[:, :, :self.n] = stim
+                    stim = padded
             keep.append(stim)
             d.stim = stim.ctypes.data
         obs = None

@@ -59,6 +59,7 @@ struct Vtop___024root final {
 
 struct Vtop__cuda final {
     typedef Vtop___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 2348,
@@ -1010,7 +1011,7 @@ struct Vtop__cuda final {
 
 const VlcuDesignInfo& Vtop__cuda::info() {
     typedef Vtop__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"reset_l", "reset_l", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_reset_l},
@@ -1132,7 +1133,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         t.points.data(), static_cast<uint32_t>(t.points.size()), 543, T::OFF___Vcoverage,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9,
-        saveOrder, 39, VLCU_SAVE_ACTIVITY, 0x63e469006938c01ULL, nullptr, 12, 12};
+        saveOrder, 39, VLCU_SAVE_ACTIVITY, 0x63e469006938c01ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -45,6 +45,7 @@ struct Vtop_nocov___024root final {
 
 struct Vtop_nocov__cuda final {
     typedef Vtop_nocov___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 108,
@@ -673,7 +674,7 @@ struct Vtop_nocov__cuda final {
 
 const VlcuDesignInfo& Vtop_nocov__cuda::info() {
     typedef Vtop_nocov__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"reset_l", "reset_l", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_reset_l},
@@ -739,7 +740,7 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9,
-        saveOrder, 26, VLCU_SAVE_ACTIVITY, 0xa090add8b4f5237eULL, nullptr, 12, 12};
+        saveOrder, 26, VLCU_SAVE_ACTIVITY, 0xa090add8b4f5237eULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -133,6 +133,7 @@ struct Vrv32_cov___024root final {
 
 struct Vrv32_cov__cuda final {
     typedef Vrv32_cov___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 11116,
@@ -3746,7 +3747,7 @@ struct Vrv32_cov__cuda final {
 
 const VlcuDesignInfo& Vrv32_cov__cuda::info() {
     typedef Vrv32_cov__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"resetn", "resetn", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_resetn},
@@ -4129,7 +4130,7 @@ const VlcuDesignInfo& Vrv32_cov__cuda::info() {
         t.points.data(), static_cast<uint32_t>(t.points.size()), 1664, T::OFF___Vcoverage,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12};
+        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -70,6 +70,7 @@ struct Vrv32_soc___024root final {
 
 struct Vrv32_soc__cuda final {
     typedef Vrv32_soc___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 4332,
@@ -2075,7 +2076,7 @@ struct Vrv32_soc__cuda final {
 
 const VlcuDesignInfo& Vrv32_soc__cuda::info() {
     typedef Vrv32_soc__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"resetn", "resetn", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_resetn},
@@ -2246,7 +2247,7 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         traceDecls, 105, T::kTraceWords, traceOrder, 88,
-        saveOrder, 51, VLCU_SAVE_ACTIVITY, 0xe66f28a6807d2675ULL, nullptr, 12, 12};
+        saveOrder, 51, VLCU_SAVE_ACTIVITY, 0xe66f28a6807d2675ULL, nullptr, 12, 12, 0};
     return s;
 }
 

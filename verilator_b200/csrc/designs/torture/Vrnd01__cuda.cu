@@ -68,6 +68,7 @@ struct Vrnd01___024root final {
 
 struct Vrnd01__cuda final {
     typedef Vrnd01___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 254,
@@ -1808,7 +1809,7 @@ struct Vrnd01__cuda final {
 
 const VlcuDesignInfo& Vrnd01__cuda::info() {
     typedef Vrnd01__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"i0", "i0", VLCU_MEMBER_IN, 4, 0, 3, 96, 95, 0, T::OFF_i0},
@@ -1866,7 +1867,7 @@ const VlcuDesignInfo& Vrnd01__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 43, 0, 0x72d6802b2c7e727aULL, nullptr, 12, 12};
+        saveOrder, 43, 0, 0x72d6802b2c7e727aULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -61,6 +61,7 @@ struct Vrnd02___024root final {
 
 struct Vrnd02__cuda final {
     typedef Vrnd02___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 206,
@@ -1258,7 +1259,7 @@ struct Vrnd02__cuda final {
 
 const VlcuDesignInfo& Vrnd02__cuda::info() {
     typedef Vrnd02__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"i0", "i0", VLCU_MEMBER_IN, 1, 0, 1, 7, 6, 0, T::OFF_i0},
@@ -1315,7 +1316,7 @@ const VlcuDesignInfo& Vrnd02__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 42, 0, 0x11dcf6eb895aecc9ULL, nullptr, 12, 12};
+        saveOrder, 42, 0, 0x11dcf6eb895aecc9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -65,6 +65,7 @@ struct Vrnd03___024root final {
 
 struct Vrnd03__cuda final {
     typedef Vrnd03___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 324,
@@ -1585,7 +1586,7 @@ struct Vrnd03__cuda final {
 
 const VlcuDesignInfo& Vrnd03__cuda::info() {
     typedef Vrnd03__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"i0", "i0", VLCU_MEMBER_IN, 8, 0, 1, 40, 39, 0, T::OFF_i0},
@@ -1646,7 +1647,7 @@ const VlcuDesignInfo& Vrnd03__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 46, 0, 0x16d69c6230dce010ULL, nullptr, 12, 12};
+        saveOrder, 46, 0, 0x16d69c6230dce010ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -63,6 +63,7 @@ struct Vrnd04___024root final {
 
 struct Vrnd04__cuda final {
     typedef Vrnd04___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 320,
@@ -1447,7 +1448,7 @@ struct Vrnd04__cuda final {
 
 const VlcuDesignInfo& Vrnd04__cuda::info() {
     typedef Vrnd04__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"i0", "i0", VLCU_MEMBER_IN, 4, 0, 5, 150, 149, 0, T::OFF_i0},
@@ -1506,7 +1507,7 @@ const VlcuDesignInfo& Vrnd04__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 44, 0, 0xd189c098c351952cULL, nullptr, 12, 12};
+        saveOrder, 44, 0, 0xd189c098c351952cULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -54,6 +54,7 @@ struct Vt01_alu___024root final {
 
 struct Vt01_alu__cuda final {
     typedef Vt01_alu___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 122,
@@ -1047,7 +1048,7 @@ struct Vt01_alu__cuda final {
 
 const VlcuDesignInfo& Vt01_alu__cuda::info() {
     typedef Vt01_alu__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"op", "op", VLCU_MEMBER_IN, 1, 0, 1, 4, 3, 0, T::OFF_op},
@@ -1097,7 +1098,7 @@ const VlcuDesignInfo& Vt01_alu__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 35, 0, 0x7c8d40b046c830b9ULL, nullptr, 12, 12};
+        saveOrder, 35, 0, 0x7c8d40b046c830b9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

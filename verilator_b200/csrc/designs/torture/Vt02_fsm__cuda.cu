@@ -119,6 +119,7 @@ struct Vt02_fsm___024root final {
 
 struct Vt02_fsm__cuda final {
     typedef Vt02_fsm___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 46,
@@ -677,7 +678,7 @@ struct Vt02_fsm__cuda final {
 
 const VlcuDesignInfo& Vt02_fsm__cuda::info() {
     typedef Vt02_fsm__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"rst", "rst", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_rst},
@@ -718,7 +719,7 @@ const VlcuDesignInfo& Vt02_fsm__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 26, 0, 0x3b73d8ee909aca3fULL, nullptr, 12, 12};
+        saveOrder, 26, 0, 0x3b73d8ee909aca3fULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -38,7 +38,7 @@ struct Vt03_mem___024root final {
     IData/*31:0*/ __Vtrigprevexpr___TOP__wdata__0;
     IData/*31:0*/ __VactIterCount;
     VlcuSharedArray<IData/*31:0*/, 64> t03_mem__DOT__ram;  // run-time indexed: shared memory [index][lane]
-    VlcuSharedArray<CData/*7:0*/, 16> t03_mem__DOT__tag;  // run-time indexed: shared memory [index][lane]
+    VlcuLocalArray<CData/*7:0*/, 16> t03_mem__DOT__tag;  // thread-local memory
     VlUnpacked<QData/*63:0*/, 1> __VstlTriggered;
     VlUnpacked<QData/*63:0*/, 2> __VicoTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
@@ -48,6 +48,7 @@ struct Vt03_mem___024root final {
 
 struct Vt03_mem__cuda final {
     typedef Vt03_mem___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 314,
@@ -84,16 +85,16 @@ struct Vt03_mem__cuda final {
         kTouchedWriteBytes = 78,  // S_state_wr
     };
     struct Locals final {
+        CData/*7:0*/ t03_mem__DOT__tag[16];
     };
     struct Shared final {
         IData/*31:0*/ t03_mem__DOT__ram[64][VLCU_BLOCK];
-        CData/*7:0*/ t03_mem__DOT__tag[16][VLCU_BLOCK];
     };
     VLCU_D static void bind(Root& s, Locals& l, Shared& sh, const VlcuState& st, uint64_t i) {
         (void)l; (void)sh; (void)st; (void)i;
         s.vlNamep = "TOP";
         s.t03_mem__DOT__ram.bind(sh.t03_mem__DOT__ram, threadIdx.x);
-        s.t03_mem__DOT__tag.bind(sh.t03_mem__DOT__tag, threadIdx.x);
+        s.t03_mem__DOT__tag.bind(l.t03_mem__DOT__tag);
     }
     VLCU_D static void load(Root& s, const VlcuState& st, uint64_t i) {
         s.clk = st.ld<VlcuMem8>(OFF_clk, i);
@@ -727,7 +728,7 @@ struct Vt03_mem__cuda final {
 
 const VlcuDesignInfo& Vt03_mem__cuda::info() {
     typedef Vt03_mem__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"we", "we", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_we},
@@ -771,7 +772,7 @@ const VlcuDesignInfo& Vt03_mem__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0xdd8f4b7deb221c6fULL, nullptr, 12, 12};
+        saveOrder, 29, 0, 0xdd8f4b7deb221c6fULL, nullptr, 12, 12, 0};
     return s;
 }
 

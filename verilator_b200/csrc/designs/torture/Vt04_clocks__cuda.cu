@@ -40,6 +40,7 @@ struct Vt04_clocks___024root final {
 
 struct Vt04_clocks__cuda final {
     typedef Vt04_clocks___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 40,
@@ -484,7 +485,7 @@ struct Vt04_clocks__cuda final {
 
 const VlcuDesignInfo& Vt04_clocks__cuda::info() {
     typedef Vt04_clocks__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"clk2", "clk2", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk2},
@@ -520,7 +521,7 @@ const VlcuDesignInfo& Vt04_clocks__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x9da0e1ec1111a29ULL, nullptr, 12, 12};
+        saveOrder, 21, 0, 0x9da0e1ec1111a29ULL, nullptr, 12, 12, 0};
     return s;
 }
 

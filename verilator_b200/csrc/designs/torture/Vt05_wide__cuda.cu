@@ -45,6 +45,7 @@ struct Vt05_wide___024root final {
 
 struct Vt05_wide__cuda final {
     typedef Vt05_wide___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 180,
@@ -710,7 +711,7 @@ struct Vt05_wide__cuda final {
 
 const VlcuDesignInfo& Vt05_wide__cuda::info() {
     typedef Vt05_wide__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"a", "a", VLCU_MEMBER_IN, 4, 0, 3, 96, 95, 0, T::OFF_a},
@@ -751,7 +752,7 @@ const VlcuDesignInfo& Vt05_wide__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 26, 0, 0x553002b1b73e24f0ULL, nullptr, 12, 12};
+        saveOrder, 26, 0, 0x553002b1b73e24f0ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt06_loops___024root final {
 
 struct Vt06_loops__cuda final {
     typedef Vt06_loops___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 76,
@@ -678,7 +679,7 @@ struct Vt06_loops__cuda final {
 
 const VlcuDesignInfo& Vt06_loops__cuda::info() {
     typedef Vt06_loops__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"en", "en", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_en},
@@ -710,7 +711,7 @@ const VlcuDesignInfo& Vt06_loops__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x63e44c3fb0276468ULL, nullptr, 12, 12};
+        saveOrder, 17, 0, 0x63e44c3fb0276468ULL, nullptr, 12, 12, 0};
     return s;
 }
 

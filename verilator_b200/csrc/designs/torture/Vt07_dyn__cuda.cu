@@ -38,6 +38,7 @@ struct Vt07_dyn___024root final {
 
 struct Vt07_dyn__cuda final {
     typedef Vt07_dyn___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 48,
@@ -440,7 +441,7 @@ struct Vt07_dyn__cuda final {
 
 const VlcuDesignInfo& Vt07_dyn__cuda::info() {
     typedef Vt07_dyn__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"a", "a", VLCU_MEMBER_IN, 4, 0, 1, 32, 31, 0, T::OFF_a},
@@ -474,7 +475,7 @@ const VlcuDesignInfo& Vt07_dyn__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0xd80e36e69bbb5d54ULL, nullptr, 12, 12};
+        saveOrder, 19, 0, 0xd80e36e69bbb5d54ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -41,6 +41,7 @@ struct Vt08_widemem___024root final {
 
 struct Vt08_widemem__cuda final {
     typedef Vt08_widemem___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 462,
@@ -630,7 +631,7 @@ struct Vt08_widemem__cuda final {
 
 const VlcuDesignInfo& Vt08_widemem__cuda::info() {
     typedef Vt08_widemem__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"we0", "we0", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_we0},
@@ -667,7 +668,7 @@ const VlcuDesignInfo& Vt08_widemem__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0xc8b7f9412b1760ddULL, nullptr, 12, 12};
+        saveOrder, 22, 0, 0xc8b7f9412b1760ddULL, nullptr, 12, 12, 0};
     return s;
 }
 

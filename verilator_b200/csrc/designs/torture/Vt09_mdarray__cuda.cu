@@ -56,6 +56,7 @@ struct Vt09_mdarray___024root final {
 
 struct Vt09_mdarray__cuda final {
     typedef Vt09_mdarray___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 4388,
@@ -876,7 +877,7 @@ struct Vt09_mdarray__cuda final {
 
 const VlcuDesignInfo& Vt09_mdarray__cuda::info() {
     typedef Vt09_mdarray__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"we", "we", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_we},
@@ -928,7 +929,7 @@ const VlcuDesignInfo& Vt09_mdarray__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 37, 0, 0xeae58fda201bc3b0ULL, nullptr, 12, 12};
+        saveOrder, 37, 0, 0xeae58fda201bc3b0ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -36,6 +36,7 @@ struct Vt10_bigstate___024root final {
 
 struct Vt10_bigstate__cuda final {
     typedef Vt10_bigstate___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 4130,
@@ -328,7 +329,7 @@ struct Vt10_bigstate__cuda final {
 
 const VlcuDesignInfo& Vt10_bigstate__cuda::info() {
     typedef Vt10_bigstate__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"din", "din", VLCU_MEMBER_IN, 4, 0, 1, 32, 31, 0, T::OFF_din},
@@ -355,7 +356,7 @@ const VlcuDesignInfo& Vt10_bigstate__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xd2ccd3d2441ea87bULL, nullptr, 12, 12};
+        saveOrder, 12, 0, 0xd2ccd3d2441ea87bULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -40,6 +40,7 @@ struct Vt11_nbaq___024root final {
 
 struct Vt11_nbaq__cuda final {
     typedef Vt11_nbaq___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 164,
@@ -399,7 +400,7 @@ struct Vt11_nbaq__cuda final {
 
 const VlcuDesignInfo& Vt11_nbaq__cuda::info() {
     typedef Vt11_nbaq__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"n", "n", VLCU_MEMBER_IN, 1, 0, 1, 4, 3, 0, T::OFF_n},
@@ -428,7 +429,7 @@ const VlcuDesignInfo& Vt11_nbaq__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x32e76cb27619a710ULL, nullptr, 12, 12};
+        saveOrder, 14, 0, 0x32e76cb27619a710ULL, nullptr, 12, 12, 0};
     return s;
 }
 

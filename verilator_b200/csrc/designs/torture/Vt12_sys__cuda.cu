@@ -43,6 +43,7 @@ struct Vt12_sys___024root final {
 
 struct Vt12_sys__cuda final {
     typedef Vt12_sys___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 122,
@@ -577,7 +578,7 @@ struct Vt12_sys__cuda final {
 
 const VlcuDesignInfo& Vt12_sys__cuda::info() {
     typedef Vt12_sys__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"a", "a", VLCU_MEMBER_IN, 1, 0, 1, 8, 7, 0, T::OFF_a},
@@ -616,7 +617,7 @@ const VlcuDesignInfo& Vt12_sys__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 24, 0, 0xf1ec08fd9ee39637ULL, nullptr, 12, 12};
+        saveOrder, 24, 0, 0xf1ec08fd9ee39637ULL, nullptr, 12, 12, 0};
     return s;
 }
 

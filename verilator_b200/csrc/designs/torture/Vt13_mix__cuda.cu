@@ -62,6 +62,7 @@ struct Vt13_mix___024root final {
 
 struct Vt13_mix__cuda final {
     typedef Vt13_mix___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 202,
@@ -910,7 +911,7 @@ struct Vt13_mix__cuda final {
 
 const VlcuDesignInfo& Vt13_mix__cuda::info() {
     typedef Vt13_mix__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"arst", "arst", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_arst},
@@ -968,7 +969,7 @@ const VlcuDesignInfo& Vt13_mix__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 43, 0, 0xd18a6f46a954cc30ULL, nullptr, 12, 12};
+        saveOrder, 43, 0, 0xd18a6f46a954cc30ULL, nullptr, 12, 12, 0};
     return s;
 }
 

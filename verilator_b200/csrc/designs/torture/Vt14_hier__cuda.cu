@@ -37,6 +37,7 @@ struct Vt14_hier___024root final {
 
 struct Vt14_hier__cuda final {
     typedef Vt14_hier___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 42,
@@ -479,7 +480,7 @@ struct Vt14_hier__cuda final {
 
 const VlcuDesignInfo& Vt14_hier__cuda::info() {
     typedef Vt14_hier__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"rst", "rst", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_rst},
@@ -512,7 +513,7 @@ const VlcuDesignInfo& Vt14_hier__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0xbd05e079dc4e69b9ULL, nullptr, 12, 12};
+        saveOrder, 18, 0, 0xbd05e079dc4e69b9ULL, nullptr, 12, 12, 0};
     return s;
 }
 

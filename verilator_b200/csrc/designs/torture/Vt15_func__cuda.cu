@@ -35,6 +35,7 @@ struct Vt15_func___024root final {
 
 struct Vt15_func__cuda final {
     typedef Vt15_func___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 22,
@@ -349,7 +350,7 @@ struct Vt15_func__cuda final {
 
 const VlcuDesignInfo& Vt15_func__cuda::info() {
     typedef Vt15_func__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"a", "a", VLCU_MEMBER_IN, 1, 0, 1, 8, 7, 0, T::OFF_a},
@@ -375,7 +376,7 @@ const VlcuDesignInfo& Vt15_func__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x8d6472eb47ac7118ULL, nullptr, 12, 12};
+        saveOrder, 11, 0, 0x8d6472eb47ac7118ULL, nullptr, 12, 12, 0};
     return s;
 }
 

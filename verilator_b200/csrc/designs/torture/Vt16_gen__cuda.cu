@@ -36,6 +36,7 @@ struct Vt16_gen___024root final {
 
 struct Vt16_gen__cuda final {
     typedef Vt16_gen___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 36,
@@ -418,7 +419,7 @@ struct Vt16_gen__cuda final {
 
 const VlcuDesignInfo& Vt16_gen__cuda::info() {
     typedef Vt16_gen__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"d", "d", VLCU_MEMBER_IN, 4, 0, 1, 32, 31, 0, T::OFF_d},
@@ -450,7 +451,7 @@ const VlcuDesignInfo& Vt16_gen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x4455e9470139a5e6ULL, nullptr, 12, 12};
+        saveOrder, 17, 0, 0x4455e9470139a5e6ULL, nullptr, 12, 12, 0};
     return s;
 }
 

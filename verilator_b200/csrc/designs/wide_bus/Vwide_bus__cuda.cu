@@ -61,6 +61,7 @@ struct Vwide_bus___024root final {
 
 struct Vwide_bus__cuda final {
     typedef Vwide_bus___024root Root;
+    static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
         OFF_clk = 282,
@@ -1034,7 +1035,7 @@ struct Vwide_bus__cuda final {
 
 const VlcuDesignInfo& Vwide_bus__cuda::info() {
     typedef Vwide_bus__cuda T;
-    // name, hierName, kind, elemBytes, traceCode, elems, width, msb, lsb, soaOffset
+    // name, hierName, kind, elemBytes, flags, elems, width, msb, lsb, soaOffset
     static const VlcuMemberDesc members[] = {
         {"clk", "clk", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_clk},
         {"rst_n", "rst_n", VLCU_MEMBER_IN, 1, 0, 1, 1, 0, 0, T::OFF_rst_n},
@@ -1126,7 +1127,7 @@ const VlcuDesignInfo& Vwide_bus__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         traceDecls, 45, T::kTraceWords, traceOrder, 24,
-        saveOrder, 32, VLCU_SAVE_ACTIVITY, 0x2819d23c62a96db6ULL, nullptr, 12, 12};
+        saveOrder, 32, VLCU_SAVE_ACTIVITY, 0x2819d23c62a96db6ULL, nullptr, 12, 12, 0};
     return s;
 }
 

@@ -40,6 +40,8 @@ static_assert(sizeof(VlcuCtxRec) == sizeof(vlcu_status_t), "status record layout
 static_assert(sizeof(VlcuMsg) == sizeof(vlcu_msg_t), "message record layouts must agree");
 static_assert(VLCU_RUN_TB_BEGIN == VLCU_RUNF_TB_BEGIN, "flag values must agree");
 static_assert(VLCU_RUN_STOP_ON_FINISH == VLCU_RUNF_STOP_ON_FINISH, "flag values must agree");
+static_assert(VLCU_TBF_FUZZ_RESET_LOW == 1 && VLCU_TBF_FUZZ_RESET_HIGH == 2 && VLCU_TBF_FUZZ_UNIFORM == 4,
+              "fuzz testbench flags (verilated_cuda_launch.h VLCU_FUZZ_*) must agree");
 static_assert(sizeof(ncclUniqueId) == VLCU_NCCL_ID_BYTES, "NCCL unique id size");
 
 //=========================================================================
@@ -196,60 +198,89 @@ int ensureStage(vlcu_model* h, size_t bytes) {
 //-------------------------------------------------------------------------
 // Port / member transposes between the host's per-instance layout and SoA
 
-// src: packed records [inst][elems * elemBytes]; dst: SoA rows [elem][inst]
+// Where the runtime finds a member.  SoA designs: base = state + soaOffset * npad, one tile of
+// npad instances.  Tiled designs (VlcuDesignInfo::tile): base = state + soaOffset, `tile`
+// instances per tile of tileBytes bytes.  Element e of instance i is then, in units of the
+// element type, at  tile(i) + (laneMajor ? lane(i) * elems + e : e * tile + lane(i)).
+struct MemberLoc final {
+    uint8_t* base;
+    uint64_t tile;
+    uint64_t tileBytes;
+    uint32_t elems;
+    uint32_t laneMajor;
+};
 template <typename T>
-__global__ void k_scatter(T* __restrict__ dst, const T* __restrict__ src, uint64_t n, uint64_t npad,
-                          uint32_t elems, uint32_t broadcast, T topMask) {
-    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (idx >= n * elems) return;
-    const uint64_t inst = idx % n;  // instance fastest: coalesced writes
-    const uint32_t e = static_cast<uint32_t>(idx / n);
-    T v = src[(broadcast ? 0 : inst * elems) + e];
-    if (e == elems - 1) v &= topMask;  // inputs are masked to the declared width on ingest
-    dst[static_cast<uint64_t>(e) * npad + inst] = v;
-}
-template <typename T>
-__global__ void k_gather(T* __restrict__ dst, const T* __restrict__ src, uint64_t n, uint64_t npad,
-                         uint32_t elems) {
-    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (idx >= n * elems) return;
-    const uint64_t inst = idx % n;
-    const uint32_t e = static_cast<uint32_t>(idx / n);
-    dst[inst * elems + e] = src[static_cast<uint64_t>(e) * npad + inst];
+__device__ __forceinline__ T* memberAt(const MemberLoc& loc, uint32_t e, uint64_t inst) {
+    const uint64_t t = inst / loc.tile, lane = inst - t * loc.tile;
+    T* const tilep = reinterpret_cast<T*>(loc.base + t * loc.tileBytes);
+    return tilep + (loc.laneMajor ? lane * loc.elems + e : static_cast<uint64_t>(e) * loc.tile + lane);
 }
 
-// One instance's state, packed at the members' SoA offsets (npad == 1 layout)
-__global__ void k_snapshot(uint8_t* __restrict__ dst, const uint8_t* __restrict__ state,
-                           uint64_t npad, uint64_t inst, const uint32_t* __restrict__ table,
-                           uint32_t nMembers) {
-    // table: per member {soaOffset, elemBytes, elems, instanceMajor}
+// src: packed records [inst][elems] (one record when broadcast); dst: the member's slots
+template <typename T>
+__global__ void k_scatter(MemberLoc dst, const T* __restrict__ src, uint64_t n, uint32_t broadcast,
+                          T topMask, uint32_t maskEvery) {
+    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    const uint32_t elems = dst.elems;
+    if (idx >= n * elems) return;
+    // instance fastest for [element][instance] members, element fastest for [instance][element]
+    const uint64_t inst = dst.laneMajor ? idx / elems : idx % n;
+    const uint32_t e = static_cast<uint32_t>(dst.laneMajor ? idx % elems : idx / n);
+    T v = src[(broadcast ? 0 : inst * elems) + e];
+    // inputs are masked to the declared width on ingest
+    if (e % maskEvery == maskEvery - 1) v &= topMask;
+    *memberAt<T>(dst, e, inst) = v;
+}
+template <typename T>
+__global__ void k_gather(T* __restrict__ dst, MemberLoc src, uint64_t n) {
+    const uint64_t idx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    const uint32_t elems = src.elems;
+    if (idx >= n * elems) return;
+    const uint64_t inst = src.laneMajor ? idx / elems : idx % n;
+    const uint32_t e = static_cast<uint32_t>(src.laneMajor ? idx % elems : idx / n);
+    dst[inst * elems + e] = *memberAt<T>(src, e, inst);
+}
+
+// One instance's state as a packed record (what the state block would be with one instance)
+struct StateGeom final {
+    uint64_t tile, tileBytes;  // as in MemberLoc
+    uint64_t offScale;  // member base = state + soaOffset * offScale
+    uint32_t recDiv;  // offset of the member in the packed record = soaOffset / recDiv
+};
+__global__ void k_snapshot(uint8_t* __restrict__ dst, uint8_t* state, StateGeom g, uint64_t inst,
+                           const uint32_t* __restrict__ table, uint32_t nMembers) {
+    // table: per member {soaOffset, elemBytes, elems, laneMajor}
     for (uint32_t m = blockIdx.x; m < nMembers; m += gridDim.x) {
         const uint32_t off = table[m * 4 + 0], eb = table[m * 4 + 1], elems = table[m * 4 + 2];
-        const bool instMajor = table[m * 4 + 3] != 0;
-        const uint8_t* const basep = state + static_cast<uint64_t>(off) * npad;
+        const MemberLoc loc{state + static_cast<uint64_t>(off) * g.offScale, g.tile, g.tileBytes, elems,
+                            table[m * 4 + 3] & 1U};
         for (uint64_t b = threadIdx.x; b < static_cast<uint64_t>(eb) * elems; b += blockDim.x) {
-            const uint64_t e = b / eb, byte = b % eb;
-            const uint64_t src = instMajor ? ((inst * elems + e) * eb + byte)
-                                           : ((e * npad + inst) * eb + byte);
-            dst[off + b] = basep[src];
+            const uint32_t e = static_cast<uint32_t>(b / eb), byte = static_cast<uint32_t>(b % eb);
+            const uint8_t* const elemp = eb == 1   ? memberAt<uint8_t>(loc, e, inst)
+                                         : eb == 2 ? reinterpret_cast<uint8_t*>(memberAt<uint16_t>(loc, e, inst))
+                                         : eb == 4 ? reinterpret_cast<uint8_t*>(memberAt<uint32_t>(loc, e, inst))
+                                                   : reinterpret_cast<uint8_t*>(memberAt<uint64_t>(loc, e, inst));
+            dst[off / g.recDiv + b] = elemp[byte];
         }
     }
 }
 
-// The inverse: one instance's packed record back into the SoA block
-__global__ void k_restore(uint8_t* __restrict__ state, const uint8_t* __restrict__ src, uint64_t npad,
-                          uint64_t inst, const uint32_t* __restrict__ table, uint32_t nMembers) {
-    // table: per member {soaOffset, elemBytes, elems, instanceMajor | skip << 1}
+// The inverse: one instance's packed record back into the state block
+__global__ void k_restore(uint8_t* state, const uint8_t* __restrict__ src, StateGeom g, uint64_t inst,
+                          const uint32_t* __restrict__ table, uint32_t nMembers) {
+    // table: per member {soaOffset, elemBytes, elems, laneMajor | skip << 1}
     for (uint32_t m = blockIdx.x; m < nMembers; m += gridDim.x) {
         const uint32_t off = table[m * 4 + 0], eb = table[m * 4 + 1], elems = table[m * 4 + 2];
-        const bool instMajor = (table[m * 4 + 3] & 1U) != 0;
         if (table[m * 4 + 3] & 2U) continue;  // member not part of the image
-        uint8_t* const basep = state + static_cast<uint64_t>(off) * npad;
+        const MemberLoc loc{state + static_cast<uint64_t>(off) * g.offScale, g.tile, g.tileBytes, elems,
+                            table[m * 4 + 3] & 1U};
         for (uint64_t b = threadIdx.x; b < static_cast<uint64_t>(eb) * elems; b += blockDim.x) {
-            const uint64_t e = b / eb, byte = b % eb;
-            const uint64_t dst = instMajor ? ((inst * elems + e) * eb + byte)
-                                           : ((e * npad + inst) * eb + byte);
-            basep[dst] = src[off + b];
+            const uint32_t e = static_cast<uint32_t>(b / eb), byte = static_cast<uint32_t>(b % eb);
+            uint8_t* const elemp = eb == 1   ? memberAt<uint8_t>(loc, e, inst)
+                                   : eb == 2 ? reinterpret_cast<uint8_t*>(memberAt<uint16_t>(loc, e, inst))
+                                   : eb == 4 ? reinterpret_cast<uint8_t*>(memberAt<uint32_t>(loc, e, inst))
+                                             : reinterpret_cast<uint8_t*>(memberAt<uint64_t>(loc, e, inst));
+            elemp[byte] = src[off / g.recDiv + b];
         }
     }
 }
@@ -296,6 +327,33 @@ const VlcuMemberDesc* memberAt(const vlcu_model* h, int member) {
     return &h->infop->members[member];
 }
 
+bool memberLaneMajor(const VlcuMemberDesc& md) {
+    return md.kind == VLCU_MEMBER_MEMORY || (md.flags & VLCU_MEMBERF_LANE_MAJOR);
+}
+MemberLoc locOf(const vlcu_model* h, const VlcuMemberDesc& md) {
+    const uint32_t tile = h->infop->tile;
+    MemberLoc loc;
+    loc.base = h->dState + (tile ? static_cast<uint64_t>(md.soaOffset) : static_cast<uint64_t>(md.soaOffset) * h->npad);
+    loc.tile = tile ? tile : h->npad;
+    loc.tileBytes = tile ? static_cast<uint64_t>(h->infop->stateBytes) * tile : 0;
+    loc.elems = md.elems;
+    loc.laneMajor = memberLaneMajor(md);
+    return loc;
+}
+StateGeom geomOf(const vlcu_model* h) {
+    const uint32_t tile = h->infop->tile;
+    StateGeom g;
+    g.tile = tile ? tile : h->npad;
+    g.tileBytes = tile ? static_cast<uint64_t>(h->infop->stateBytes) * tile : 0;
+    g.offScale = tile ? 1 : h->npad;
+    g.recDiv = tile ? tile : 1;
+    return g;
+}
+// Offset of a member in the packed one-instance record (vlcu_snapshot, save images)
+uint32_t recordOffset(const vlcu_model* h, const VlcuMemberDesc& md) {
+    return h->infop->tile ? md.soaOffset / h->infop->tile : md.soaOffset;
+}
+
 // Width mask of a member's most significant element (inputs are masked on ingest)
 uint64_t memberTopMask(const VlcuMemberDesc& md, bool maskWidth) {
     const int topBits = md.width - static_cast<int>(md.elems - 1) * md.elemBytes * 8;
@@ -306,38 +364,56 @@ uint64_t memberTopMask(const VlcuMemberDesc& md, bool maskWidth) {
                             : ~0ULL;
 }
 
-// Device records [inst][elems] (or one record when broadcast) -> the member's SoA rows
+// Device records [inst][elems] (or one record when broadcast) -> the member's slots
 int launchScatter(vlcu_model* h, const VlcuMemberDesc& md, const uint8_t* dsrc, bool broadcast,
                   uint64_t topMask) {
     const uint64_t n = h->n;
     const uint64_t work = n * md.elems;
     const unsigned threads = 256, blocks = blocksFor(work, threads);
-    void* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
+    const MemberLoc loc = locOf(h, md);
+    // the mask applies to the most significant limb of a (wide) value; array elements of a
+    // memory are stored as given
+    const uint32_t maskEvery = md.elems;
     switch (md.elemBytes) {
     case 1:
-        k_scatter<uint8_t><<<blocks, threads, 0, h->stream>>>(static_cast<uint8_t*>(soap), dsrc, n,
-                                                              h->npad, md.elems, broadcast,
-                                                              static_cast<uint8_t>(topMask));
+        k_scatter<uint8_t><<<blocks, threads, 0, h->stream>>>(loc, dsrc, n, broadcast,
+                                                              static_cast<uint8_t>(topMask), maskEvery);
         break;
     case 2:
         k_scatter<uint16_t><<<blocks, threads, 0, h->stream>>>(
-            static_cast<uint16_t*>(soap), reinterpret_cast<const uint16_t*>(dsrc), n, h->npad,
-            md.elems, broadcast, static_cast<uint16_t>(topMask));
+            loc, reinterpret_cast<const uint16_t*>(dsrc), n, broadcast, static_cast<uint16_t>(topMask), maskEvery);
         break;
     case 4:
         k_scatter<uint32_t><<<blocks, threads, 0, h->stream>>>(
-            static_cast<uint32_t*>(soap), reinterpret_cast<const uint32_t*>(dsrc), n, h->npad,
-            md.elems, broadcast, static_cast<uint32_t>(topMask));
+            loc, reinterpret_cast<const uint32_t*>(dsrc), n, broadcast, static_cast<uint32_t>(topMask), maskEvery);
         break;
     default:
         k_scatter<uint64_t><<<blocks, threads, 0, h->stream>>>(
-            static_cast<uint64_t*>(soap), reinterpret_cast<const uint64_t*>(dsrc), n, h->npad,
-            md.elems, broadcast, topMask);
+            loc, reinterpret_cast<const uint64_t*>(dsrc), n, broadcast, topMask, maskEvery);
         break;
     }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     return VLCU_OK;
+}
+// The member's slots -> device records [inst][elems]
+int launchGather(vlcu_model* h, const VlcuMemberDesc& md, uint8_t* ddst) {
+    const uint64_t n = h->n;
+    const unsigned threads = 256, blocks = blocksFor(n * md.elems, threads);
+    const MemberLoc loc = locOf(h, md);
+    switch (md.elemBytes) {
+    case 1: k_gather<uint8_t><<<blocks, threads, 0, h->stream>>>(ddst, loc, n); break;
+    case 2: k_gather<uint16_t><<<blocks, threads, 0, h->stream>>>(reinterpret_cast<uint16_t*>(ddst), loc, n); break;
+    case 4: k_gather<uint32_t><<<blocks, threads, 0, h->stream>>>(reinterpret_cast<uint32_t*>(ddst), loc, n); break;
+    default: k_gather<uint64_t><<<blocks, threads, 0, h->stream>>>(reinterpret_cast<uint64_t*>(ddst), loc, n); break;
+    }
+    ++h->launches;
+    CUDA_TRY(cudaGetLastError());
+    return VLCU_OK;
+}
+// A memory of an SoA design is [instance][element] over the whole shard: plain copies reach it
+bool memberIsFlat(const vlcu_model* h, const VlcuMemberDesc& md) {
+    return md.kind == VLCU_MEMBER_MEMORY && !h->infop->tile;
 }
 
 int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, void* dst,
@@ -347,18 +423,11 @@ int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, voi
     if (!broadcast && stride < recBytes) return fail(VLCU_E_ARG, "stride smaller than one element");
     const uint64_t n = h->n;
     DeviceGuard guard{h->device};
-    if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major in HBM: a strided copy is enough
+    if (memberIsFlat(h, md) && !broadcast) {  // a strided copy is enough
         uint8_t* const devp = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
         if (toDevice) {
-            if (broadcast) {
-                for (uint64_t i = 0; i < n; ++i) {
-                    CUDA_TRY(cudaMemcpyAsync(devp + i * recBytes, src, recBytes,
-                                             cudaMemcpyHostToDevice, h->stream));
-                }
-            } else {
-                CUDA_TRY(cudaMemcpy2DAsync(devp, recBytes, src, stride, recBytes, n,
-                                           cudaMemcpyHostToDevice, h->stream));
-            }
+            CUDA_TRY(cudaMemcpy2DAsync(devp, recBytes, src, stride, recBytes, n, cudaMemcpyHostToDevice,
+                                       h->stream));
         } else {
             CUDA_TRY(cudaMemcpy2DAsync(dst, stride, devp, recBytes, recBytes, n,
                                        cudaMemcpyDeviceToHost, h->stream));
@@ -368,12 +437,11 @@ int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, voi
     }
     const size_t stageBytes = recBytes * (broadcast ? 1 : n);
     if (const int rc = ensureStage(h, stageBytes)) return rc;
-    const uint64_t work = n * md.elems;
-    const unsigned threads = 256, blocks = blocksFor(work, threads);
-    void* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
-    const uint64_t topMask = memberTopMask(md, maskWidth);
+    // (the elements of a memory are stored as given: only a value's top limb is masked)
+    const uint64_t topMask = memberTopMask(md, maskWidth && md.kind != VLCU_MEMBER_MEMORY);
     if (toDevice) {
         if (broadcast) {
+            // one record up, replicated into every instance on the device
             CUDA_TRY(cudaMemcpyAsync(h->dStage, src, recBytes, cudaMemcpyHostToDevice, h->stream));
         } else {
             CUDA_TRY(cudaMemcpy2DAsync(h->dStage, recBytes, src, stride, recBytes, n,
@@ -382,29 +450,7 @@ int transferMember(vlcu_model* h, const VlcuMemberDesc& md, const void* src, voi
         if (const int rc = launchScatter(h, md, h->dStage, broadcast, topMask)) return rc;
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     } else {
-        switch (md.elemBytes) {
-        case 1:
-            k_gather<uint8_t><<<blocks, threads, 0, h->stream>>>(
-                h->dStage, static_cast<const uint8_t*>(soap), n, h->npad, md.elems);
-            break;
-        case 2:
-            k_gather<uint16_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint16_t*>(h->dStage), static_cast<const uint16_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        case 4:
-            k_gather<uint32_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint32_t*>(h->dStage), static_cast<const uint32_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        default:
-            k_gather<uint64_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint64_t*>(h->dStage), static_cast<const uint64_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        }
-        ++h->launches;
-        CUDA_TRY(cudaGetLastError());
+        if (const int rc = launchGather(h, md, h->dStage)) return rc;
         CUDA_TRY(cudaMemcpy2DAsync(dst, stride, h->dStage, recBytes, recBytes, n,
                                    cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -695,6 +741,11 @@ vlcu_model_t* vlcu_create(const char* design, uint64_t n_instances, int device, 
             return bail(e, "cudaMalloc(covSums)");
     }
     // $test$plusargs are resolved here, once, into a bit per string the design asks about
+    if (h->infop->nPlusargs > 32) {
+        fail(VLCU_E_ARG, "vlcu_create: the design tests more than 32 $test$plusargs strings");
+        vlcu_destroy(h);
+        return nullptr;
+    }
     uint32_t plusBits = 0;
     if (plusargs) {
         std::istringstream is{plusargs};
@@ -897,7 +948,7 @@ int vlcu_commit_staged(vlcu_model_t* h) {
         if (!st.pending) continue;
         const VlcuMemberDesc& md = h->infop->members[it.first];
         const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
-        if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major in HBM already
+        if (memberIsFlat(h, md)) {  // instance-major in HBM already
             uint8_t* const devp = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
             CUDA_TRY(cudaMemcpyAsync(devp, st.dBuf, recBytes * h->n, cudaMemcpyDeviceToDevice,
                                      h->stream));
@@ -914,14 +965,18 @@ int vlcu_commit_staged(vlcu_model_t* h) {
 int vlcu_member_device_ptr(vlcu_model_t* h, int member, void** ptr, uint64_t* npad) {
     const VlcuMemberDesc* const mdp = memberAt(h, member);
     if (!mdp || !ptr) return fail(VLCU_E_ARG, "bad member");
-    *ptr = h->dState + static_cast<uint64_t>(mdp->soaOffset) * h->npad;
-    if (npad) *npad = h->npad;
+    // (a tiled design: lane 0 of tile 0; consecutive tiles are stateBytes * tile bytes apart and
+    // *npad is the tile size)
+    const MemberLoc loc = locOf(h, *mdp);
+    *ptr = loc.base;
+    if (npad) *npad = loc.tile;
     return VLCU_OK;
 }
 uint32_t vlcu_member_offset(const vlcu_model_t* h, int member) {
     const VlcuMemberDesc* const mdp = memberAt(h, member);
-    return mdp ? mdp->soaOffset : 0;
+    return mdp ? recordOffset(h, *mdp) : 0;
 }
+uint32_t vlcu_tile(const vlcu_model_t* h) { return h ? h->infop->tile : 0; }
 
 int vlcu_time_inc(vlcu_model_t* h, uint64_t add) {
     if (!h) return fail(VLCU_E_ARG, "null model");
@@ -1169,35 +1224,13 @@ int vlcu_results_begin(vlcu_model_t* h, uint64_t* sigs_out, vlcu_status_t* statu
     for (int k = 0; k < n_members; ++k) {
         const VlcuMemberDesc& md = h->infop->members[members[k]];
         const size_t recBytes = static_cast<size_t>(md.elemBytes) * md.elems;
-        const uint8_t* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
-        if (md.kind == VLCU_MEMBER_MEMORY) {  // instance-major already
+        if (memberIsFlat(h, md)) {  // instance-major already
+            const uint8_t* const soap = h->dState + static_cast<uint64_t>(md.soaOffset) * h->npad;
             CUDA_TRY(cudaMemcpyAsync(h->dRes + memOff[k], soap, recBytes * n, cudaMemcpyDeviceToDevice,
                                      h->stream));
             continue;
         }
-        const unsigned threads = 256, blocks = blocksFor(n * md.elems, threads);
-        switch (md.elemBytes) {
-        case 1:
-            k_gather<uint8_t><<<blocks, threads, 0, h->stream>>>(h->dRes + memOff[k], soap, n, h->npad, md.elems);
-            break;
-        case 2:
-            k_gather<uint16_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint16_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint16_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        case 4:
-            k_gather<uint32_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint32_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint32_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        default:
-            k_gather<uint64_t><<<blocks, threads, 0, h->stream>>>(
-                reinterpret_cast<uint64_t*>(h->dRes + memOff[k]), reinterpret_cast<const uint64_t*>(soap), n,
-                h->npad, md.elems);
-            break;
-        }
-        ++h->launches;
-        CUDA_TRY(cudaGetLastError());
+        if (const int rc = launchGather(h, md, h->dRes + memOff[k])) return rc;
     }
     CUDA_TRY(cudaEventRecord(h->evCaptured, h->stream));
     CUDA_TRY(cudaStreamWaitEvent(h->resStream, h->evCaptured, 0));
@@ -1269,7 +1302,7 @@ int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_byte
         table[m * 4 + 0] = info.members[m].soaOffset;
         table[m * 4 + 1] = info.members[m].elemBytes;
         table[m * 4 + 2] = info.members[m].elems;
-        table[m * 4 + 3] = info.members[m].kind == VLCU_MEMBER_MEMORY;
+        table[m * 4 + 3] = memberLaneMajor(info.members[m]);
     }
     const size_t tableBytes = table.size() * sizeof(uint32_t);
     const size_t tableOff = (static_cast<size_t>(info.stateBytes) + 15) & ~size_t{15};
@@ -1278,7 +1311,7 @@ int vlcu_snapshot(vlcu_model_t* h, uint64_t instance, void* out, size_t out_byte
     CUDA_TRY(cudaMemcpyAsync(h->dStage + tableOff, table.data(), tableBytes, cudaMemcpyHostToDevice,
                              h->stream));
     k_snapshot<<<info.nMembers < 64 ? info.nMembers : 64, 128, 0, h->stream>>>(
-        h->dStage, h->dState, h->npad, instance,
+        h->dStage, h->dState, geomOf(h), instance,
         reinterpret_cast<const uint32_t*>(h->dStage + tableOff), info.nMembers);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
@@ -1410,7 +1443,7 @@ int vlcu_save_instance(vlcu_model_t* h, uint64_t instance, const char* filename)
     put(&emptyLen, 4);  // dumpfile ""
     for (uint32_t k = 0; k < info.nSaveOrder; ++k) {
         const VlcuMemberDesc& md = info.members[info.saveOrder[k]];
-        put(rec.data() + md.soaOffset, static_cast<size_t>(md.elemBytes) * md.elems);
+        put(rec.data() + recordOffset(h, md), static_cast<size_t>(md.elemBytes) * md.elems);
     }
     put(kSaveTrailer, sizeof(kSaveTrailer) - 1);
     std::ofstream os{filename, std::ios::binary};
@@ -1469,7 +1502,7 @@ int vlcu_restore_instance(vlcu_model_t* h, uint64_t instance, const char* filena
     for (uint32_t k = 0; k < info.nSaveOrder && !short_; ++k) {
         const uint32_t m = info.saveOrder[k];
         const VlcuMemberDesc& md = info.members[m];
-        get(rec.data() + md.soaOffset, static_cast<size_t>(md.elemBytes) * md.elems);
+        get(rec.data() + recordOffset(h, md), static_cast<size_t>(md.elemBytes) * md.elems);
         table[m * 4 + 3] &= ~2U;
     }
     char trl[sizeof(kSaveTrailer) - 1];
@@ -1494,7 +1527,7 @@ int vlcu_restore_instance(vlcu_model_t* h, uint64_t instance, const char* filena
     CUDA_TRY(cudaMemcpyAsync(h->dStage + tableOff, table.data(), tableBytes, cudaMemcpyHostToDevice,
                              h->stream));
     k_restore<<<info.nMembers < 64 ? info.nMembers : 64, 128, 0, h->stream>>>(
-        h->dState, h->dStage, h->npad, instance, reinterpret_cast<const uint32_t*>(h->dStage + tableOff),
+        h->dState, h->dStage, geomOf(h), instance, reinterpret_cast<const uint32_t*>(h->dStage + tableOff),
         info.nMembers);
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
