@@ -126,6 +126,20 @@ WORKLOADS = {
         cpu_cycles=1024,
         note="t10_bigstate.v emitted with --no-cuda-array-layout: the array instance-major in HBM "
              "(VlcuGlobalArray), the layout chosen for data-indexed memories"),
+    # BASELINE.json configs[2] class at real scale: a VeeR-EH1-class design (the RTLMeter source is
+    # not vendored: veer_class.v is this repo's 4-hart SoC of the same shape, ~37,000 bits of
+    # scalar flops + 4.5 KB of arrays in 33 scopes of 9 module classes, hierarchy kept).  Its state
+    # does not fit a thread: the model image is tiled in HBM and streams every cycle.
+    "veer_class": dict(
+        design="veer_class", tb="fuzz", instances=16384, cycles=256, tb_flags=1,
+        tb_arg=(4, 0b11100000, 0, 0), rand_reset=2, inputs=(), fuzz=True,
+        note="veer_class.v (own RTL, VeeR-EH1 class): 4 in-order harts with BTB/CSR/LSU/muldiv, PIC, timers, "
+             "bus bridges; non-inlined module hierarchy, tiled model image in HBM; random instruction, bus "
+             "and interrupt stimulus made in the kernel per instance, --x-initial unique"),
+    "veer_class_64k": dict(
+        design="veer_class", tb="fuzz", instances=65536, cycles=128, tb_flags=1,
+        tb_arg=(4, 0b11100000, 0, 0), rand_reset=2, inputs=(), fuzz=True,
+        note="veer_class.v at 65,536 instances (state 4x the L2)"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -235,7 +249,11 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
         O.generic_run(design, stim, seed=1, rand_reset=wl["rand_reset"], threads=threads)
         dt = time.perf_counter() - t0  # (construction included: 1,024 reset values per instance)
         return sample_instances * cycles / dt, dt
-    if wl["design"] in ("rv32i", "rv32i_cov"):
+    if wl.get("fuzz"):
+        O.generic_fuzz(wl["design"], sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+                       tb_flags=wl["tb_flags"], reset_periods=wl["tb_arg"][0], sparse_mask=wl["tb_arg"][1],
+                       threads=threads)
+    elif wl["design"] in ("rv32i", "rv32i_cov"):
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads, cov=wl["design"] == "rv32i_cov",
                    rounds=1 if wl.get("fresh_program_per_step") else 0, reset_time=wl["tb_arg"][0],

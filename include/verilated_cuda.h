@@ -824,6 +824,22 @@ VLCU_HD uint32_t vlcu_lane() {
 #endif
 }
 
+// Ask for the line holding *p ahead of its use (the next leaf's gather, issued by the caller one
+// call ahead).  VLCU_PREFETCH_LEVEL: 1 = into L1 (default), 2 = into L2 only, 0 = off.
+#ifndef VLCU_PREFETCH_LEVEL
+#define VLCU_PREFETCH_LEVEL 1
+#endif
+template <typename T>
+VLCU_HD void vlcu_prefetch(const T* p) {
+#if defined(__CUDA_ARCH__) && VLCU_PREFETCH_LEVEL == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif defined(__CUDA_ARCH__) && VLCU_PREFETCH_LEVEL == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // One value per instance of the tile.  Emitted code names the slot explicitly (`sig.v[vlLane]`);
 // the conversions are for the few places where EmitCFunc prints a variable without going through
 // the AstVarRef visitor (V3EmitCFunc.h:320-345: wide constants assigned in place;
@@ -892,6 +908,11 @@ struct VlcuCell final {
     }
     VLCU_HD operator T_Child*() { return operator->(); }
 };
+
+// Shared code naming another scope: the struct of class T_Class that lies T_Info::kDelta bytes from
+// this function's own scope struct in every tile (V3EmitCuda "sharing between instances")
+#define VLCU_REL(T_Class, T_Info) \
+    (*reinterpret_cast<T_Class*>(reinterpret_cast<char*>(vlSelf) + T_Info::kDelta))
 
 // vlSymsp->_vm_contextp__->... in literal C text of a tiled model (cf. VlcuSymsCtxShim): the
 // queries have run-time-default answers and need no context

@@ -204,6 +204,11 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
         // (tryRun sends runs of 2^32 evals or more to the kObserve form, whose trip count is 64 bits)
         const uint32_t nEvals = static_cast<uint32_t>(r.nEvals);
         for (uint32_t e = 0; e < nEvals; ++e) {
+#ifdef VLCU_EVAL_SYNC
+            // (experiment) keep the CTA's warps at the same place in the code: a tiled design's
+            // eval is tens of thousands of straight-line instructions, fetched once per warp
+            if (T_Design::kTiled) __syncthreads();
+#endif
             T_Tb::template drive<T_Design>(root, ctx, r, inst, r.evalBase + e);
             vlcu_eval_step<T_Design>(&root, ctx);
             sig = T_Design::outputs_sig(root, sig);

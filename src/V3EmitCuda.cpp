@@ -172,6 +172,13 @@ public:
     }
 };
 
+// AstNode::sameNode (the per-node half of AstNode::sameTree, V3Ast.h:530) is protected; the code
+// sharing pass needs it node by node, because it compares scope references its own way
+struct CudaAstNodePeek final : public AstNode {
+    using AstNode::sameNode;
+};
+static bool cudaSameNode(const AstNode* ap, const AstNode* bp) { return (ap->*(&CudaAstNodePeek::sameNode))(bp); }
+
 // Tiled form: a non-root module class and one of its instances (AstScope)
 struct CudaClass final {
     const AstNodeModule* modp = nullptr;
@@ -333,6 +340,7 @@ class EmitCudaModel final : public EmitCFunc {
                 m_laneArrayVars.insert(varp);
             } else {
                 m_laneVars.insert(varp);
+                if (!m.isArray && !m.isWide) m_laneScalarType[varp] = m.memType;
             }
             out.push_back(m);
             return;
@@ -463,6 +471,7 @@ class EmitCudaModel final : public EmitCFunc {
         analyzeModule(m_topModp, m_members);
         if (m_stream) {
             for (CudaClass& cls : m_subClasses) analyzeModule(cls.modp, cls.members);
+            findSharedCode();
         }
         // Coverage bins of this module: the counters are one more (local memory) array
         const_cast<AstNodeModule*>(m_topModp)->foreach([&](AstNodeCoverDecl* declp) {
@@ -552,6 +561,34 @@ class EmitCudaModel final : public EmitCFunc {
         }
     }
     CudaMember m_pendingCoverage;
+    // Tiled form, inside a leaf function: scalar members held in locals (gather at the top, scatter
+    // at the end), keyed by the text of the access
+    struct CudaCached final {
+        AstVarRef* refp = nullptr;  // a representative reference (prints the member's lvalue)
+        string local;  // __Vm<n>
+        string ctype;  // CData SData IData QData
+        string memType;  // VlcuMem8 ...
+        bool load = false;  // the old value may be needed (read, or written on some paths only)
+        bool store = false;
+    };
+    std::map<string, CudaCached> m_cached;
+    bool m_caching = false;
+    std::set<const AstCFunc*> m_prefetchable;  // leaves with a __prefetch companion
+    // Tiled form: code shared between the instances of a module class.  V3Order prints one copy of
+    // a scope's functions PER INSTANCE whenever they name another scope absolutely
+    // (`vlSymsp->TOP__top__DOT__cpu1__DOT__pic.irq`, V3Descope.cpp:95-125), which they nearly always do;
+    // in the tile image such a scope lies at a fixed distance from the function's own scope, the
+    // same distance for every instance of a replicated block, so the copies are congruent: one
+    // is printed, with the reference relative to vlSelf, and called for all instances.
+    std::map<const AstCFunc*, const AstCFunc*> m_sharedAs;  // copy -> the one that is printed
+    std::set<const AstCFunc*> m_sharedRep;  // printed with scope references relative to vlSelf
+    std::map<const AstScope*, size_t> m_scopeIndex;  // position in m_scopeInsts
+    std::map<string, size_t> m_symIndex;  // "(&vlSymsp->TOP__x)" -> position in m_scopeInsts
+    std::map<std::pair<size_t, long>, std::set<size_t>> m_relUsed;  // (class, distance in Syms order) of
+                                                                    // relative references -> scopes relying on it
+    const AstScope* m_relSelfp = nullptr;  // scope of the shared function being printed
+    std::map<const AstVarRef*, bool> m_refAbsolute;  // ... its references that every copy spells the same
+    std::map<const AstVar*, string> m_laneScalarType;  // members a leaf may cache -> memory type
     uint32_t m_sharedBytes = 0;  // shared memory per CTA the SHARED arrays chosen so far take
     uint32_t m_touchedRead = 0, m_touchedWrite = 0;
     uint32_t m_nSaveOrder = 0;
@@ -675,6 +712,25 @@ class EmitCudaModel final : public EmitCFunc {
                 if (inst.classIdx == c) insts.emplace_back(inst.scopep, inst.sym);
             }
             cellInfos(m_subClasses[c].modp, m_subClasses[c].name, insts);
+        }
+        // Distances shared code relies on: taken from one scope, checked for the others that run it
+        for (const auto& rel : m_relUsed) {
+            const size_t classIdx = rel.first.first;
+            const long distance = rel.first.second;
+            const string name = relInfoName(m_subClasses[classIdx].name, distance);
+            bool first = true;
+            for (const size_t i : rel.second) {
+                const size_t t = i + distance;
+                const string delta = "(static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", " + m_scopeInsts[t].sym
+                                     + ")) - static_cast<ptrdiff_t>(__builtin_offsetof(" + m_symsName + ", "
+                                     + m_scopeInsts[i].sym + ")))";
+                if (first) {
+                    puts("struct " + name + " final {\nstatic constexpr ptrdiff_t kDelta = " + delta + ";\n};\n");
+                    first = false;
+                } else {
+                    puts("static_assert(" + delta + " == " + name + "::kDelta, \"scope distance differs between instances\");\n");
+                }
+            }
         }
     }
     // How the glue (port rows, signature) names a member of the root class
@@ -841,6 +897,183 @@ class EmitCudaModel final : public EmitCFunc {
         }
     }
 
+    // May this function hold members in locals from entry to exit?  Only if nothing else can
+    // see or change them meanwhile and every path runs to the end of the body.
+    bool leafCanCache(const AstCFunc* funcp) const {
+        if (!funcp->isLoose() || funcp->isStatic() || funcp->slow()) return false;
+        if (funcp->rtnTypeVoid() != "void") return false;
+        bool ok = true;
+        funcp->foreach([&](const AstNode* nodep) {
+            if (VN_IS(nodep, NodeCCall) || VN_IS(nodep, CReturn) || VN_IS(nodep, JumpGo)) ok = false;
+            if (VN_IS(nodep, CReset)) {  // `local = 0` is fine; a member's reset prints its name as text
+                const AstNodeAssign* const assignp = VN_CAST(nodep->backp(), NodeAssign);
+                const AstVarRef* const refp = assignp ? VN_CAST(assignp->lhsp(), VarRef) : nullptr;
+                if (!refp || !refp->varp()->isFuncLocal()) ok = false;
+            }
+            // (literal C text may name members or leave the function: VL_FATAL_MT)
+            if (VN_IS(nodep, CStmt) || VN_IS(nodep, CExpr) || VN_IS(nodep, CStmtUser) || VN_IS(nodep, CExprUser)) ok = false;
+            if (const AstStop* const stopp = VN_CAST(nodep, Stop)) {
+                if (stopp->isFatal()) ok = false;
+            }
+        });
+        return ok;
+    }
+    void collectCached(AstCFunc* funcp) {
+        std::set<const AstNode*> topStmts;
+        for (const AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) topStmts.insert(stmtp);
+        uint32_t next = 0;
+        funcp->foreach([&](AstVarRef* refp) {
+            const auto typeIt = m_laneScalarType.find(refp->varp());
+            if (typeIt == m_laneScalarType.end()) return;
+            CudaCached& c = m_cached[cacheKey(refp)];
+            if (!c.refp) {
+                c.refp = refp;
+                c.local = "__Vm" + cvtToStr(next++);
+                c.memType = typeIt->second;
+                c.ctype = c.memType == "VlcuMem8" ? "CData" : c.memType == "VlcuMem16" ? "SData" : c.memType;
+            }
+            if (refp->access().isReadOrRW()) c.load = true;
+            if (refp->access().isWriteOrRW()) {
+                c.store = true;
+                // written on every path and whole only as the target of a top-level assignment
+                const AstNodeAssign* const assignp = VN_CAST(refp->backp(), NodeAssign);
+                if (!(assignp && assignp->lhsp() == refp && topStmts.count(assignp))) c.load = true;
+            }
+        });
+    }
+
+    // ---- sharing between instances ------------------------------------------------------------
+    // Position, relative to `selfp`, of the scope an absolute self pointer names; 0 with ok=false
+    // if it is TOP / this / a cell (those print the same for every instance anyway)
+    long relDistance(const VSelfPointerText& self, const AstScope* selfp, bool& isAbs) const {
+        isAbs = false;
+        if (!self.isVlSym()) return 0;
+        const auto it = m_symIndex.find(self.asString());
+        if (it == m_symIndex.end()) return 0;  // (&vlSymsp->TOP)
+        isAbs = true;
+        return static_cast<long>(it->second) - static_cast<long>(m_scopeIndex.at(selfp));
+    }
+    // (refAp: the reference in the function that would be printed; how it is to be printed --
+    // absolute when every copy names the very same scope, else relative -- must come out the same
+    // against every copy)
+    bool congruentSelf(const AstVarRef* refAp, const VSelfPointerText& a, const AstScope* scopeAp,
+                       const VSelfPointerText& b, const AstScope* scopeBp, std::set<long>& rels,
+                       std::map<const AstVarRef*, bool>& modes) const {
+        bool absA, absB;
+        const long da = relDistance(a, scopeAp, absA), db = relDistance(b, scopeBp, absB);
+        if (absA != absB) return false;
+        if (!absA) return a == b;
+        const bool sameScope = a == b;
+        const auto known = m_refAbsolute.find(refAp);
+        if (known != m_refAbsolute.end() && known->second != sameScope) return false;
+        modes[refAp] = sameScope;
+        if (sameScope) return true;
+        if (da != db) return false;
+        const size_t ia = m_scopeIndex.at(scopeAp) + da, ib = m_scopeIndex.at(scopeBp) + db;
+        if (m_scopeInsts[ia].classIdx != m_scopeInsts[ib].classIdx) return false;
+        rels.insert(da);
+        return true;
+    }
+    // Are two functions of the same class the same code up to the scope they run in?
+    bool congruent(const AstNode* ap, const AstNode* bp, const AstScope* scopeAp, const AstScope* scopeBp,
+                   std::map<const AstVar*, const AstVar*>& locals, std::set<long>& rels,
+                   std::map<const AstVarRef*, bool>& modes, bool next) const {
+        for (; ap || bp; ap = ap->nextp(), bp = bp->nextp()) {
+#define return_false(why) do { if (getenv("VLCU_DEBUG_SHARE")) std::cerr << "  mismatch " << why << " at " << (ap ? ap->typeName() : "null") << " " << (ap ? ap->fileline()->ascii() : string{}) << "\n"; return false; } while (0)
+            if (!ap || !bp || ap->type() != bp->type()) return_false("type");
+            if (const AstVarRef* const ra = VN_CAST(ap, VarRef)) {
+                const AstVarRef* const rb = VN_AS(bp, VarRef);
+                if (ra->access() != rb->access()) return_false("access");
+                if (ra->varp()->isFuncLocal() != rb->varp()->isFuncLocal()) return_false("local-vs-member");
+                if (ra->varp()->isFuncLocal()) {
+                    const auto it = locals.find(ra->varp());
+                    if (it == locals.end() || it->second != rb->varp()) return_false("local var " + ra->varp()->name());
+                } else {
+                    if (ra->varp() != rb->varp()) return_false("member " + ra->varp()->name() + " vs " + rb->varp()->name());
+                    if (!congruentSelf(ra, ra->selfPointer(), scopeAp, rb->selfPointer(), scopeBp, rels, modes)) return_false("scope " + ra->selfPointer().asString() + " vs " + rb->selfPointer().asString());
+                }
+            } else if (const AstVar* const va = VN_CAST(ap, Var)) {
+                const AstVar* const vb = VN_AS(bp, Var);
+                if (va->name() != vb->name() || !va->dtypep()->skipRefp()->similarDType(vb->dtypep()->skipRefp())) return_false("var decl");
+                locals[va] = vb;
+            } else if (const AstNodeCCall* const ca = VN_CAST(ap, NodeCCall)) {
+                // (a leaf calls nothing but shared static helpers)
+                if (ca->funcp() != VN_AS(bp, NodeCCall)->funcp() || !ca->funcp()->isStatic()) return_false("call");
+            } else {
+                if (!cudaSameNode(ap, bp)) return_false("sameNode");
+                if ((ap->dtypep() == nullptr) != (bp->dtypep() == nullptr)) return_false("dtype null");
+                if (ap->dtypep() && ap->dtypep() != bp->dtypep()
+                    && !ap->dtypep()->skipRefp()->similarDType(bp->dtypep()->skipRefp())) return_false("dtype");
+            }
+            if (!congruent(ap->op1p(), bp->op1p(), scopeAp, scopeBp, locals, rels, modes, true)) return false;
+            if (!congruent(ap->op2p(), bp->op2p(), scopeAp, scopeBp, locals, rels, modes, true)) return false;
+            if (!congruent(ap->op3p(), bp->op3p(), scopeAp, scopeBp, locals, rels, modes, true)) return false;
+            if (!congruent(ap->op4p(), bp->op4p(), scopeAp, scopeBp, locals, rels, modes, true)) return false;
+            if (!next) break;
+        }
+        return true;
+    }
+    void findSharedCode() {
+        for (size_t i = 0; i < m_scopeInsts.size(); ++i) {
+            m_scopeIndex[m_scopeInsts[i].scopep] = i;
+            m_symIndex["(&vlSymsp->" + m_scopeInsts[i].sym + ")"] = i;
+        }
+        if (!V3EmitCuda::shareCode()) return;
+        for (size_t c = 0; c < m_subClasses.size(); ++c) {
+            std::vector<const CudaScopeInst*> insts;
+            for (const CudaScopeInst& inst : m_scopeInsts) {
+                if (inst.classIdx == c) insts.push_back(&inst);
+            }
+            if (insts.size() < 2) continue;
+            // A function of a later instance is a copy if it is congruent to a function (already
+            // kept) of an earlier one; V3Order numbers and splits the functions of each instance on
+            // its own, so every kept function of the same kind is tried
+            std::vector<std::pair<AstCFunc*, size_t>> kept;  // function, index of its scope in m_scopeInsts
+            const auto kindOf = [](const AstCFunc* funcp) {
+                const string::size_type pos = funcp->name().find("__TOP__");
+                return pos == string::npos ? funcp->name() : funcp->name().substr(0, pos);
+            };
+            for (const CudaScopeInst* const instp : insts) {
+                for (AstNode* nodep = m_subClasses[c].modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                    AstCFunc* const funcp = VN_CAST(nodep, CFunc);
+                    if (!funcp || !isDeviceFunc(funcp) || funcp->scopep() != instp->scopep || !funcp->isLoose()
+                        || funcp->isStatic() || funcp->name() == "_ctor_var_reset") {
+                        continue;
+                    }
+                    bool shared = false;
+                    for (const auto& cand : kept) {
+                        AstCFunc* const repp = cand.first;
+                        if (repp->scopep() == funcp->scopep() || kindOf(repp) != kindOf(funcp)) continue;
+                        if (repp->rtnTypeVoid() != funcp->rtnTypeVoid() || repp->slow() != funcp->slow()) continue;
+                        std::map<const AstVar*, const AstVar*> locals;
+                        std::set<long> rels;
+                        std::map<const AstVarRef*, bool> modes;
+                        if (getenv("VLCU_DEBUG_SHARE")) std::cerr << "try " << funcp->name() << " ~ " << repp->name() << "\n";
+                        if (!congruent(repp, funcp, repp->scopep(), funcp->scopep(), locals, rels, modes, false)) continue;
+                        for (const auto& mode : modes) m_refAbsolute[mode.first] = mode.second;
+                        m_sharedAs[funcp] = repp;
+                        m_sharedRep.insert(repp);
+                        for (const long d : rels) {
+                            std::set<size_t>& users = m_relUsed[std::make_pair(c, d)];
+                            users.insert(cand.second);
+                            users.insert(m_scopeIndex.at(funcp->scopep()));
+                        }
+                        shared = true;
+                        break;
+                    }
+                    if (!shared) kept.emplace_back(funcp, m_scopeIndex.at(instp->scopep));
+                }
+            }
+        }
+    }
+    const AstCFunc* sharedFunc(const AstCFunc* funcp) const {
+        const auto it = m_sharedAs.find(funcp);
+        return it == m_sharedAs.end() ? funcp : it->second;
+    }
+    static string relInfoName(const string& className, long distance) {
+        return className + "__rel_" + (distance < 0 ? "m" + cvtToStr(-distance) : "p" + cvtToStr(distance));
+    }
+
     // VISITORS
     using EmitCFunc::visit;
     void visit(AstConst* nodep) override {
@@ -852,15 +1085,23 @@ class EmitCudaModel final : public EmitCFunc {
     }
     void visit(AstCFunc* nodep) override {
         // EmitCFunc::visit(AstCFunc*) (V3EmitCFunc.h:398-500) for a device function
+        if (m_sharedAs.count(nodep)) return;  // another instance's copy of shared code
         VL_RESTORER(m_useSelfForThis);
         VL_RESTORER(m_cfuncp);
+        VL_RESTORER(m_relSelfp);
+        m_relSelfp = m_sharedRep.count(nodep) ? nodep->scopep() : nullptr;
         m_cfuncp = nodep;
         puts("\n");
         // Tiled form: the big functions (the leaves V3Order builds, V3OrderCFuncEmitter.h:137-157,
         // split by --output-split-cfuncs) are real calls, so that nvcc compiles each on its own
         // and the instances of a module share one copy; the small ones are inlined
+        // Tiled form: the big functions (the leaves V3Order builds, V3OrderCFuncEmitter.h:137-157)
+        // are real calls, so that ptxas compiles each on its own; the small ones are inlined.
+        // With --cuda-chunk-nodes N the per-eval leaves are inlined into chunk functions of about
+        // N AST nodes instead (visit(AstStmtExpr)); measured slower on the VeeR-class design
+        // (more spills, worse instruction-cache behaviour), so off by default.
         bool noinline = false;
-        if (m_stream) {
+        if (m_stream && (nodep->slow() || !V3EmitCuda::chunkNodes())) {
             size_t nodes = 0;
             nodep->foreach([&](const AstNode*) { ++nodes; });
             noinline = nodes > 400;
@@ -891,10 +1132,39 @@ class EmitCudaModel final : public EmitCFunc {
         // _ctor_var_reset needs its own, so declare it here and let the body's own (if it comes)
         // shadow it in an inner block
         bool scopeHash = false;
-        if (m_stream && nodep->isLoose() && !nodep->isStatic()) {
+        if (m_stream && nodep->isLoose() && !nodep->isStatic() && nodep->slow()) {
             nodep->foreach([&](const AstCReset*) { scopeHash = true; });
         }
         if (scopeHash) puts("const uint64_t __VscopeHash VL_ATTR_UNUSED = VL_MURMUR64_HASH(vlSelf->vlNamep);\n{\n");
+        // Tiled form, leaves (straight-line code of one scope, no calls): gather every scalar
+        // member the function touches into a local first, scatter the written ones at the end.
+        // The loads are then independent of every store and of each other, so they are all in
+        // flight at once -- with one warp or less per scheduler nothing else hides HBM latency.
+        VL_RESTORER(m_caching);
+        m_cached.clear();
+        m_caching = false;
+        if (m_stream && V3EmitCuda::leafCaching() && !scopeHash && leafCanCache(nodep)) {
+            collectCached(nodep);
+            m_caching = !m_cached.empty();
+        }
+        if (m_caching) {
+            std::vector<const CudaCached*> order;
+            for (const auto& it : m_cached) order.push_back(&it.second);
+            std::sort(order.begin(), order.end(), [](const CudaCached* ap, const CudaCached* bp) {
+                return std::stoul(ap->local.substr(4)) < std::stoul(bp->local.substr(4));
+            });
+            putsDecoration(nodep, "// Gather\n");
+            m_caching = false;
+            for (const CudaCached* const cp : order) {
+                puts(cp->ctype + " " + cp->local);
+                if (cp->load) {
+                    puts(" = ");
+                    iterateConst(cp->refp);
+                }
+                puts(";\n");
+            }
+            m_caching = true;
+        }
         if (nodep->varsp()) {
             putsDecoration(nodep, "// Locals\n");
             iterateAndNextConstNull(nodep->varsp());
@@ -903,15 +1173,66 @@ class EmitCudaModel final : public EmitCFunc {
             putsDecoration(nodep, "// Body\n");
             iterateAndNextConstNull(nodep->stmtsp());
         }
+        std::vector<const CudaCached*> prefetches;
+        if (m_caching) {
+            for (const auto& it : m_cached) {
+                if (it.second.load) prefetches.push_back(&it.second);
+            }
+        }
+        if (m_caching) {
+            putsDecoration(nodep, "// Scatter\n");
+            m_caching = false;
+            std::vector<const CudaCached*> order;
+            for (const auto& it : m_cached) {
+                if (it.second.store) order.push_back(&it.second);
+            }
+            std::sort(order.begin(), order.end(), [](const CudaCached* ap, const CudaCached* bp) {
+                return std::stoul(ap->local.substr(4)) < std::stoul(bp->local.substr(4));
+            });
+            for (const CudaCached* const cp : order) {
+                iterateConst(cp->refp);
+                puts(" = static_cast<" + cp->memType + ">(" + cp->local + ");\n");
+            }
+        }
         if (scopeHash) puts("}\n");
-        m_usevlSelfRef = false;
         puts("}\n");
+        // ... and its companion: the same gather as prefetches, which the CALLER issues one call
+        // ahead (visit(AstCCall)), so that the lines arrive while the previous leaf computes
+        if (m_prefetchable.count(nodep)) {
+            puts("VLCU_D static void " + funcNameProtect(nodep) + "__prefetch("
+                 + EmitCUtil::prefixNameProtect(EmitCParentModule::get(nodep)) + "* vlSelf, " + m_symsName + "* vlSymsp) {\n");
+            puts("auto& vlSelfRef = *vlSelf;\n");
+            puts("const uint32_t vlLane = vlcu_lane();\n(void)vlSymsp; (void)vlSelfRef;\n");
+            std::sort(prefetches.begin(), prefetches.end(), [](const CudaCached* ap, const CudaCached* bp) {
+                return std::stoul(ap->local.substr(4)) < std::stoul(bp->local.substr(4));
+            });
+            for (const CudaCached* const cp : prefetches) {
+                puts("vlcu_prefetch(&");
+                iterateConst(cp->refp);
+                puts(");\n");
+            }
+            puts("}\n");
+        }
+        m_cached.clear();
+        m_usevlSelfRef = false;
     }
     void visit(AstCCall* nodep) override {
         // EmitCFunc::visit(AstCCall*) + emitCCallArgs (V3EmitCFunc.h:753-779, V3EmitCFunc.cpp:368-395)
-        const AstCFunc* const funcp = nodep->funcp();
+        const AstCFunc* const funcp = sharedFunc(nodep->funcp());
         UASSERT_OBJ(funcp->isLoose() || funcp->isStatic(), nodep, "--cuda: call to a proper method");
         putnbs(nodep, "");
+        // Tiled form: issue the NEXT leaf's gather as prefetches before this call
+        const AstCCall* nextCallp = nullptr;
+        if (m_stream && VN_IS(nodep->backp(), StmtExpr) && nodep->backp()->nextp()) {
+            if (const AstStmtExpr* const nextp = VN_CAST(nodep->backp()->nextp(), StmtExpr)) {
+                nextCallp = VN_CAST(nextp->exprp(), CCall);
+                if (nextCallp && !m_prefetchable.count(sharedFunc(nextCallp->funcp()))) nextCallp = nullptr;
+            }
+        }
+        if (nextCallp) {
+            puts("(" + funcNameProtect(sharedFunc(nextCallp->funcp())) + "__prefetch("
+                 + nextCallp->selfPointerProtect(m_useSelfForThis) + ", vlSymsp), ");
+        }
         putns(nodep, funcNameProtect(funcp));
         puts("(");
         bool comma = false;
@@ -926,9 +1247,87 @@ class EmitCudaModel final : public EmitCFunc {
         }
         putCommaIterateNext(nodep->argsp(), comma);
         puts(")");
+        if (nextCallp) puts(")");
     }
-    void visit(AstVarRef* nodep) override {
+    // A run of consecutive leaf calls (the body of an `if (triggered)` in _eval_nba / _eval_ico /
+    // _eval_act, V3OrderCFuncEmitter.h:86-113) is cut into chunks, each a real function with its
+    // leaves inlined -- V3Order's --output-split-cfuncs for nvcc: ptxas sees functions of bounded
+    // size, the ABI's register saves happen once per chunk instead of once per leaf, and inside a
+    // chunk the next leaf's gather overlaps the previous leaf's arithmetic.
+    static const AstCCall* callOfStmt(const AstNode* stmtp) {
+        const AstStmtExpr* const sep = VN_CAST(stmtp, StmtExpr);
+        const AstCCall* const callp = sep ? VN_CAST(sep->exprp(), CCall) : nullptr;
+        if (!callp || !callp->funcp()->isLoose() || callp->funcp()->isStatic() || callp->argsp()) return nullptr;
+        return callp;
+    }
+    static size_t funcNodes(const AstCFunc* funcp) {
+        size_t nodes = 0;
+        funcp->foreach([&](const AstNode*) { ++nodes; });
+        return nodes;
+    }
+    std::set<const AstNode*> m_chunked;  // statements already printed inside a chunk
+    uint32_t m_chunkCount = 0;
+    void visit(AstStmtExpr* nodep) override {
+        if (m_chunked.count(nodep)) return;
+        const bool candidate = m_stream && V3EmitCuda::chunkNodes() && m_cfuncp && !m_cfuncp->slow() && !m_inChunk
+                               && callOfStmt(nodep);
+        if (candidate) {
+            // the run of call statements starting here
+            std::vector<AstNode*> run;
+            size_t total = 0;
+            for (AstNode* stmtp = nodep; stmtp && callOfStmt(stmtp); stmtp = stmtp->nextp()) {
+                run.push_back(stmtp);
+                total += funcNodes(callOfStmt(stmtp)->funcp());
+            }
+            if (run.size() >= 2 && total > V3EmitCuda::chunkNodes()) {
+                size_t i = 0;
+                while (i < run.size()) {
+                    size_t nodes = 0, j = i;
+                    while (j < run.size() && (j == i || nodes + funcNodes(callOfStmt(run[j])->funcp()) <= V3EmitCuda::chunkNodes())) {
+                        nodes += funcNodes(callOfStmt(run[j])->funcp());
+                        ++j;
+                    }
+                    const string name = "VlChunk" + cvtToStr(m_chunkCount++);
+                    puts("struct " + name + " final {\nVLCU_DN static void run(" + cudaFuncArgs(m_cfuncp) + ") {\n");
+                    puts("auto& vlSelfRef VL_ATTR_UNUSED = *vlSelf;\n");
+                    {
+                        VL_RESTORER(m_inChunk);
+                        m_inChunk = true;
+                        for (size_t k = i; k < j; ++k) {
+                            EmitCFunc::visit(VN_AS(run[k], StmtExpr));
+                            m_chunked.insert(run[k]);
+                        }
+                    }
+                    puts("}\n};\n" + name + "::run(vlSelf, vlSymsp, vlCtx);\n");
+                    i = j;
+                }
+                return;
+            }
+        }
         EmitCFunc::visit(nodep);
+    }
+    bool m_inChunk = false;
+    static string cacheKey(const AstVarRef* refp) { return refp->selfPointer().asString() + "." + refp->varp()->name(); }
+    void visit(AstVarRef* nodep) override {
+        if (m_caching) {
+            const auto it = m_cached.find(cacheKey(nodep));
+            if (it != m_cached.end()) {
+                putns(nodep, it->second.local);
+                return;
+            }
+        }
+        bool isAbs = false;
+        const long distance = m_relSelfp ? relDistance(nodep->selfPointer(), m_relSelfp, isAbs) : 0;
+        const auto absIt = m_refAbsolute.find(nodep);
+        if (isAbs && !nodep->varp()->isFuncLocal() && !(absIt != m_refAbsolute.end() && absIt->second)) {
+            // shared code: the other scope, at its fixed distance from this function's own
+            const CudaScopeInst& target = m_scopeInsts[m_scopeIndex.at(m_relSelfp) + distance];
+            const string selfClass = m_subClasses[m_scopeInsts[m_scopeIndex.at(m_relSelfp)].classIdx].name;
+            putns(nodep, "VLCU_REL(" + m_subClasses[target.classIdx].name + ", " + relInfoName(selfClass, distance)
+                             + ")." + nodep->varp()->nameProtect());
+        } else {
+            EmitCFunc::visit(nodep);
+        }
         // Tiled form: a member is one slot per instance of the tile
         if (m_laneVars.count(nodep->varp())) {
             puts(".v[vlLane]");
@@ -1225,9 +1624,11 @@ class EmitCudaModel final : public EmitCFunc {
         puts("//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -I$VERILATOR_ROOT/include\n");
         if (m_stream) {
             puts("\n// Tiled form: the model image stays in HBM (" + cvtToStr(m_scopeInsts.size() + 1)
-                 + " scopes of " + cvtToStr(m_subClasses.size() + 1) + " module classes); its kernels keep almost\n");
-            puts("// nothing in registers and are bound by memory latency: compile for full occupancy\n");
-            puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 16\n#endif\n");
+                 + " scopes of " + cvtToStr(m_subClasses.size() + 1) + " module classes); its kernels hold\n");
+            puts("// members in registers only inside a leaf (gather ... scatter) and are bound by memory latency.\n");
+            puts("// 4 CTAs of 64 threads per SM = 255 registers per thread: the leaves' gathers then keep\n");
+            puts("// 100+ loads in flight per warp without spilling (measured: profiles/README.md)\n");
+            puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 4\n#endif\n");
         } else {
             // Occupancy target of the kernels (verilated_cuda_launch.h: __launch_bounds__(64,
             // VLCU_MIN_BLOCKS), default 7 = 146 registers per thread).  A design that keeps almost
@@ -1319,6 +1720,23 @@ class EmitCudaModel final : public EmitCFunc {
         puts("enum : uint32_t { " + m_sizes + ", kTraceWords = " + cvtToStr(m_traceWords) + " };\n");
 
         // Device functions
+        if (m_stream && V3EmitCuda::leafCaching() && V3EmitCuda::leafPrefetch()) {
+            // which leaves gather (and so have a prefetch companion): known before any call is printed
+            const auto scan = [this](const AstNodeModule* modp) {
+                for (AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                    AstCFunc* const funcp = VN_CAST(nodep, CFunc);
+                    if (!funcp || !isDeviceFunc(funcp) || !leafCanCache(funcp)) continue;
+                    m_cached.clear();
+                    collectCached(funcp);
+                    bool loads = false;
+                    for (const auto& it : m_cached) loads |= it.second.load;
+                    if (loads) m_prefetchable.insert(funcp);
+                    m_cached.clear();
+                }
+            };
+            for (const CudaClass& cls : m_subClasses) scan(cls.modp);
+            scan(m_topModp);
+        }
         for (const CudaClass& cls : m_subClasses) {
             if (m_stream) emitDeviceFuncs(cls.modp);
         }
@@ -1348,7 +1766,7 @@ class EmitCudaModel final : public EmitCFunc {
                 for (const AstNode* nodep = m_subClasses[inst.classIdx].modp->stmtsp(); nodep; nodep = nodep->nextp()) {
                     const AstCFunc* const funcp = VN_CAST(nodep, CFunc);
                     if (funcp && funcp->name() == "_ctor_var_reset") {
-                        puts(funcNameProtect(funcp) + "(&vlSymsp->" + inst.sym + ", vlSymsp, vlCtx);\n");
+                        puts(funcNameProtect(sharedFunc(funcp)) + "(&vlSymsp->" + inst.sym + ", vlSymsp, vlCtx);\n");
                     }
                 }
             }
@@ -1569,6 +1987,10 @@ public:
 bool V3EmitCuda::s_enabled = false;
 bool V3EmitCuda::s_layoutSelection = true;
 int V3EmitCuda::s_streamMode = -1;
+bool V3EmitCuda::s_leafCaching = true;
+bool V3EmitCuda::s_leafPrefetch = false;
+int V3EmitCuda::s_chunkNodes = 0;
+bool V3EmitCuda::s_shareCode = true;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -33,11 +33,31 @@ public:
     // emitter chooses by hierarchy and size
     static void streamMode(bool flag) { s_streamMode = flag ? 1 : 0; }
     static int streamMode() { return s_streamMode; }
+    // --cuda-leaf-gather / --no-cuda-leaf-gather (tiled form): leaf functions gather the scalar
+    // members they touch into locals at entry and scatter the written ones at exit
+    static void leafCaching(bool flag) { s_leafCaching = flag; }
+    static bool leafCaching() { return s_leafCaching; }
+    // --cuda-leaf-prefetch / --no-cuda-leaf-prefetch: ... and the caller issues the next leaf's
+    // gather as prefetches one call ahead
+    static void leafPrefetch(bool flag) { s_leafPrefetch = flag; }
+    static bool leafPrefetch() { return s_leafPrefetch; }
+    // --cuda-chunk-nodes <n> (tiled form): AST nodes of leaf code inlined into one chunk function;
+    // 0 (default): every big leaf is a function of its own
+    static void chunkNodes(int nodes) { s_chunkNodes = nodes; }
+    static size_t chunkNodes() { return static_cast<size_t>(s_chunkNodes); }
+    // --cuda-share-code / --no-cuda-share-code (tiled form): print one copy of the functions of a
+    // module class for all its instances where they differ only in the scopes they name
+    static void shareCode(bool flag) { s_shareCode = flag; }
+    static bool shareCode() { return s_shareCode; }
 
 private:
     static bool s_enabled;
     static bool s_layoutSelection;
     static int s_streamMode;  // -1 automatic, 0 register form, 1 tiled form
+    static bool s_leafCaching;
+    static bool s_leafPrefetch;
+    static int s_chunkNodes;
+    static bool s_shareCode;
 };
 
 #endif  // Guard

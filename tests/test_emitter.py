@@ -23,7 +23,7 @@ CASES = [  # (committed model, top-level source, extra flags)
     ("wide_bus/Vwide_bus__cuda.cu", "../verilator_b200/csrc/designs/wide_bus/wide_bus.v",
      ["--trace-vcd", "--prefix", "Vwide_bus"]),
     ("veer_class/Vveer_class__cuda.cu", "../verilator_b200/csrc/designs/veer_class/veer_class.v",
-     ["-Wno-WIDTH", "-Wno-UNOPTFLAT", "-Wno-lint", "-Wno-fatal", "--prefix", "Vveer_class"]),
+     ["-Wno-WIDTH", "-Wno-UNOPTFLAT", "-Wno-lint", "-Wno-fatal", "-fno-dfg-scoped", "--prefix", "Vveer_class"]),
 ]
 TILED = {"veer_class/Vveer_class__cuda.cu"}
 
