@@ -270,6 +270,41 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
     return sample_instances * cycles / dt, dt
 
 
+def parity_gate(wl, sigs, n, inst_base, total_evals, campaign_rounds, first_round_seed):
+    """the throughput number is only reported if the benchmarked run itself is
+    right.  The running output signatures (every output port after every eval since the model was
+    constructed) of two blocks of instances -- the first and the last 24 of this rank's shard --
+    are recomputed by the oracle (the genuine Verilated C++ model) for the exact seeds and the
+    exact chain of steps this process ran (warm-up included).  Returns (instances checked,
+    mismatches)."""
+    import oracle_util as O
+    k = min(24, n)
+    checked = bad = 0
+    for base in sorted({0, n - k}):
+        gbase = inst_base + base
+        if wl.get("fuzz"):
+            _, want = O.generic_fuzz(wl["design"], k, total_evals, inst_base=gbase, seed=1,
+                                     rand_reset=wl["rand_reset"], tb_seed=3, tb_flags=wl["tb_flags"],
+                                     reset_periods=wl["tb_arg"][0], sparse_mask=wl["tb_arg"][1], threads=8)
+        elif wl["design"] in ("rv32i", "rv32i_cov"):
+            if wl.get("fresh_program_per_step"):
+                want = O.rv32_run(k, total_evals // campaign_rounds, inst_base=gbase, seed=1,
+                                  rand_reset=wl["rand_reset"], tb_seed=first_round_seed, reset_time=wl["tb_arg"][0],
+                                  rounds=campaign_rounds, cov=wl["design"] == "rv32i_cov", threads=8).sigs
+            else:
+                want = O.rv32_run(k, total_evals, inst_base=gbase, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+                                  same_program=bool(wl.get("same_program")), threads=8).sigs
+        elif wl["design"] == "wide_bus":
+            want = O.wide_run(k, total_evals, inst_base=gbase, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+                              threads=8).sigs
+        else:
+            want = O.mtc_run(k, total_evals, inst_base=gbase, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
+                             per_instance=bool(wl["tb_flags"] & 1), reset_period=wl["tb_arg"][0], threads=8).sigs
+        checked += k
+        bad += int((np.asarray(want) != sigs[base:base + k]).sum())
+    return checked, bad
+
+
 def cpu_sample_size(wl, cycles, threads, budget_s):
     """Instances for a CPU sample whose WHOLE call (construction included) takes ~budget_s."""
     cpu_reference_run(wl, threads, cycles, threads)  # load the library, warm the allocator
@@ -308,6 +343,80 @@ def run_reference(args, wl):
                          "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def coverage_leg(abi, dist, rank, world, local):
+    """N > 1 only, outside `value`: a short --coverage campaign whose per-shard counter sums are
+    merged by the system's ONE collective, ncclAllReduce(u64, sum) over NVLink inside
+    vlcu_coverage_reduce, timed, and checked on rank 0 against the sum over ALL instances of the
+    genuine C++ model's counters (include/verilated_cov.cpp:368-438 semantics)."""
+    from verilator_b200 import shard
+    import oracle_util as O
+    n, evals, rounds = 2048, 512, 2
+    with abi.Model("rv32i_cov", n, device=local, inst_base=rank * n, seed=1, rand_reset=2, msg_cap=2) as mc:
+        shard.attach_coverage_comm(mc, dist, local)
+        for k in range(rounds):
+            mc.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=40 + k, tb_flags=1, tb_arg=(6, 0, 0, 0))
+        mc.coverage_reduce()  # warm-up: NCCL connects on first use
+        mc.sync()
+        barrier(dist)
+        t0 = time.perf_counter()
+        sums = mc.coverage_reduce()
+        ms = allmax(dist, 1e3 * (time.perf_counter() - t0), local)
+    if rank != 0:
+        return None
+    want = O.rv32_run(n * world, evals, seed=1, rand_reset=2, tb_seed=40, reset_time=6, rounds=rounds, cov=True,
+                      threads=os.cpu_count() or 1)
+    return {"design": "rv32i_cov", "instances_per_gpu": n, "bins": int(len(sums)), "payload_bytes": 8 * int(len(sums)),
+            "reduce_plus_allreduce_plus_d2h_ms": ms, "total_count": int(sums.sum()),
+            "equals_sum_over_all_instances_of_reference_model": bool((sums == want.cov).all()),
+            "collective": "k_cov_reduce (u32 per instance -> u64 per bin) + ncclAllReduce(ncclUint64, ncclSum)"}
+
+
+def roofline(workload, m, n, cycles, mean_ms, clocks, hbm_peak, peak_src):
+    """The roofline of the dominant kernel (vlcu_k_run) from the figures kept in
+    profiles/traffic.json -- per launch, from the ncu captures named there -- and the launch
+    duration measured live in this run.
+
+    * designs whose state stays on chip for the K fused cycles (register form) are bound by
+      INSTRUCTION ISSUE: achieved = warp instructions per launch / duration, peak = 4 schedulers x
+      148 SMs x SM clock (one warp instruction per scheduler per cycle);
+    * designs whose state streams from HBM (tiled form) are bound by HBM: achieved = measured DRAM
+      bytes per launch / duration against the measured copy bandwidth.
+    The B_alg-equivalent bandwidth of SURVEY 8d is kept beside either as `hbm_equivalent`."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["kernels"][workload]
+    except Exception:
+        return None
+    b_alg = 2 * (m.touched_read_bytes + m.touched_write_bytes) + 2 * (m.in_bytes + m.out_bytes)
+    secs = mean_ms / 1e3
+    scale = n * cycles / float(prof["instances"] * prof["cycles"])  # profile taken at another size
+    dram = prof["dram_bytes"] * scale
+    warp_inst = prof["warp_instructions"] * scale
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 4 * 148 * sm_mhz * 1e6
+    common = {
+        "kernel": "vlcu_k_run", "traffic": dram, "dram_gbs": dram / secs / 1e9, "dram_frac": dram / secs / 1e9 / hbm_peak,
+        "warp_instructions_per_launch": warp_inst, "issue_frac": warp_inst / secs / issue_peak,
+        "lanes_active": prof.get("lanes_active"), "profile": prof.get("source"),
+        "algorithmic_bytes_per_instance_cycle": b_alg,
+        "hbm_equivalent": {"achieved": n * cycles * b_alg / secs / 1e9, "unit": "GB/s",
+                           "note": "B_alg x instance-cycles/s (SURVEY 8d): what an eval-per-launch implementation "
+                                   "would have to stream; not a fraction of anything for a fused kernel"},
+        "peak_source": peak_src,
+    }
+    if prof.get("bound") == "hbm":
+        return dict(common, bound="hbm", achieved=dram / secs / 1e9, peak=hbm_peak, unit="GB/s",
+                    frac=dram / secs / 1e9 / hbm_peak,
+                    note="state streams from HBM every eval (tiled model image): achieved = DRAM bytes per launch "
+                         "(ncu dram__bytes_read+write of the capture in `profile`, scaled by instance-cycles) / the "
+                         "launch duration measured in this run")
+    return dict(common, bound="issue", achieved=warp_inst / secs / 1e9, peak=issue_peak / 1e9, unit="Gwarp-inst/s",
+                frac=warp_inst / secs / issue_peak,
+                note="state stays on chip across the fused cycles, DRAM traffic is a few percent of peak: the binding "
+                     "resource is instruction issue.  achieved = warp instructions per launch (ncu "
+                     "smsp__inst_executed.sum of the capture in `profile`, scaled by instance-cycles) / the launch "
+                     "duration measured in this run; peak = 592 schedulers x the SM clock sampled during the run")
 
 
 def run_ours(args, wl):
@@ -360,6 +469,24 @@ def run_ours(args, wl):
     wall_s = allmax(dist, wall, local)
     total_units = world * n * cycles * args.steps
     value = total_units / dev_s
+
+    # ---- parity gate: the run that was just timed, against the oracle ---------------------
+    rounds_done = max(args.warmup, 3) + args.steps
+    gate = None
+    if not args.no_parity_gate:
+        checked, bad = parity_gate(wl, m.signatures(), n, rank * n, rounds_done * evals, rounds_done, 4)
+        bad_total = allmax(dist, float(bad), local)
+        gate = {"instances_checked_per_rank": checked, "mismatches": int(bad_total),
+                "evals_checked": rounds_done * evals,
+                "against": "genuine Verilated C++ model (oracle/_ref), same seeds and step chain, warm-up included"}
+        if bad_total:
+            if rank == 0:
+                emit_json({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world,
+                           "error": "parity gate failed: output signatures differ from the reference model; "
+                                    "no throughput is reported", "parity_gate": gate,
+                           "config": {"workload": args.workload}})
+            m.close()
+            raise SystemExit(3)
 
     # ---- end to end through the C ABI with host buffers -------------------------------
     ins = {}
@@ -460,6 +587,7 @@ def run_ours(args, wl):
     e2e_value = world * n * cycles * e2e_steps / e2e_s
 
     clocks = sampler.finish() if rank == 0 else None
+    cov_leg = coverage_leg(abi, dist, rank, world, local) if (world > 1 and not coverage) else None
     if rank != 0:
         m.close()
         return
@@ -512,8 +640,11 @@ def run_ours(args, wl):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps},
         "gpu_launches": int(launches),
+        "parity_gate": gate,
+        "coverage_allreduce": cov_leg,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": roofline(args.workload, m, n, cycles, mean_ms, clocks, peak, peak_src) or
+                    {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": "vlcu_k_run", "algorithmic_bytes_per_instance_cycle": b_alg,
                      "dram_gbs_from_traffic": (traffic / (mean_ms / 1e3) / 1e9) if traffic else None,
@@ -689,6 +820,7 @@ def main():
     ap.add_argument("--instances", type=int, default=0, help="instances per GPU")
     ap.add_argument("--cycles", type=int, default=0, help="clock cycles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-gate", action="store_true", help="(profiling runs only)")
     ap.add_argument("--stream-mode", default="tensor", choices=["tensor", "bulk1d", "direct"],
                     help="ports_stream A/B: rows staged by 2-D tensor TMA tiles (default), by per-word 1-D "
                          "bulk copies, or read/written with plain global accesses")

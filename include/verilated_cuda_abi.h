@@ -155,7 +155,10 @@ void* vlcu_device_alloc(vlcu_model_t* h, size_t bytes);
 void vlcu_device_free(vlcu_model_t* h, void* ptr);
 int vlcu_device_copy(vlcu_model_t* h, void* dst, const void* src, size_t bytes, int to_device);
 /* vlcu_run with host-resident "trace" stimulus larger than two chunks streams it through the
-   device in eval-chunks of about `bytes` (default 64 MB; 0 = always stage the whole run) */
+   device in eval-chunks of about `bytes` (default 64 MB; 0 = always stage the whole run).  The
+   copy-in of chunk c+1, the kernel of chunk c and the copy-out of chunk c-1 overlap ONLY when
+   desc->stim and desc->obs are page-locked (vlcu_host_alloc): with pageable memory every
+   cudaMemcpyAsync is synchronous and the pipeline degrades to copy, run, copy. */
 int vlcu_set_pipeline_chunk(vlcu_model_t* h, size_t bytes);
 
 /* ---- model life cycle -------------------------------------------------- */
@@ -207,7 +210,8 @@ int vlcu_get_member(vlcu_model_t* h, int member, void* dst, size_t stride_bytes)
 int vlcu_stage_member(vlcu_model_t* h, int member, const void* src, size_t stride_bytes,
                       int mask_width);
 int vlcu_commit_staged(vlcu_model_t* h);
-/* Raw device pointer + padded instance stride of a member's SoA array */
+/* Raw device pointer + padded instance stride of a member's SoA array (a tiled design, see
+   vlcu_tile(): lane 0 of tile 0, *npad = the tile size) */
 int vlcu_member_device_ptr(vlcu_model_t* h, int member, void** ptr, uint64_t* npad);
 
 /* ---- evaluation ------------------------------------------------------------- */

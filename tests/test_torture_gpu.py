@@ -1,14 +1,16 @@
-"""Breadth of the emitter + operator library: sixteen hand-written designs and four random ones, each a different corner of
+"""Breadth of the emitter + operator library: seventeen hand-written designs and four random ones, each a different corner of
 what V3Sched/V3Order/V3Expand/V3Table/V3Delayed/V3Unroll produce (scalar signed/unsigned
 mul/div/mod and shifts, case FSM + constant-pool table + casez, byte-enable memories with
 run-time indices, two clocks + negedge + asynchronous reset, 96/130-bit multiply/divide/shift,
 unrolled loops, data-dependent while/for loops + $countones/$onehot/power, arrays of wide and
 64-bit elements with two write ports, multidimensional arrays in every storage class, a 4 KB
 state array streamed by a loop, NBA commit queues, $urandom / $error / $fatal / inout / initial
-ROM / final, derived and gated clocks + latch + signed wide arithmetic, a parameterised module hierarchy, functions and tasks, generate regions; tests/gen_random_design.py's expression
+ROM / final, derived and gated clocks + latch + signed wide arithmetic, a parameterised module hierarchy, functions and tasks, generate regions, a byte table too big for shared memory; tests/gen_random_design.py's expression
 soups), taken through the reference's own compiler and V3EmitCuda with no hand-written
 code per design, and compared bit for bit with the genuine Verilated C++ model under random
 stimulus on every port at every eval."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -16,7 +18,7 @@ import oracle_util as O
 
 pytestmark = pytest.mark.gpu
 
-DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate", "t11_nbaq", "t12_sys", "t13_mix", "t14_hier", "t15_func", "t16_gen",
+DESIGNS = ["t01_alu", "t02_fsm", "t03_mem", "t04_clocks", "t05_wide", "t06_loops", "t07_dyn", "t08_widemem", "t09_mdarray", "t10_bigstate", "t11_nbaq", "t12_sys", "t13_mix", "t14_hier", "t15_func", "t16_gen", "t17_lut",
            "rnd01", "rnd02", "rnd03", "rnd04"]
 
 
@@ -82,7 +84,7 @@ VARIANTS = {"t10_bigstate_im": "t10_bigstate"}  # --no-cuda-array-layout: instan
 def test_every_port_every_eval_matches_the_genuine_model(abi, design, rand_reset):
     n, evals = 96, 600
     ref_design = VARIANTS.get(design, design)
-    rng = np.random.default_rng(hash(ref_design) % (1 << 32))
+    rng = np.random.default_rng(zlib.crc32(ref_design.encode()))  # (str hashes are salted per process)
     with abi.Model(design, n, seed=1000, rand_reset=rand_reset) as m:
         stim = random_stimulus(m, abi, n, evals, rng)
         want_obs, want_sigs = O.generic_run(ref_design, stim[:, :, :n], seed=1000, rand_reset=rand_reset,

@@ -1,0 +1,5 @@
+# usage: tools/ncu_veer.sh <tag> <workload> [VLCU_LIB]   -> gpurun_out/<tag>.csv (raw page of one vlcu_k_run launch)
+tag=$1; wl=$2; [ -n "$3" ] && export VLCU_LIB=$3
+ncu --set full --clock-control none -k regex:vlcu_k_run -c 1 -s 4 -o /tmp/$tag python bench.py --workload $wl --steps 2 --no-cpu-baseline --no-parity-gate > /dev/null 2>/tmp/$tag.err
+tail -1 /tmp/$tag.err
+ncu -i /tmp/$tag.ncu-rep --page raw --csv > /tmp/$tag.raw.csv; python3 tools/ncu_compact.py /tmp/$tag.raw.csv gpurun_out/$tag.csv

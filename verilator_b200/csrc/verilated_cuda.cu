@@ -170,6 +170,13 @@ struct vlcu_model final {
     bool fetchPending = false;
     uint8_t* dRes = nullptr;  // device-side copy of the results being read back
     size_t resBytes = 0;
+    // Device scratch of vlcu_run (host-side stimulus / observation / trace), kept between calls
+    // and grown on demand: a testbench that calls vlcu_run per step pays no cudaMalloc/cudaFree
+    enum { RB_STIM, RB_OBS, RB_TRACE, RB_SAMPLES, RB_SCRATCH, RB_COUNT };
+    struct RunBuf final {
+        void* p = nullptr;
+        size_t cap = 0;
+    } runBuf[RB_COUNT];
 };
 
 namespace {
@@ -184,6 +191,22 @@ struct DeviceGuard final {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+cudaError_t runBuffer(vlcu_model* h, int which, size_t bytes, void** out) {
+    vlcu_model::RunBuf& b = h->runBuf[which];
+    if (bytes > b.cap) {
+        // (the stream may still be using the old buffer)
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return e;
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        if ((e = cudaMalloc(&b.p, bytes)) != cudaSuccess) return e;
+        b.cap = bytes;
+    }
+    *out = b.p;
+    return cudaSuccess;
+}
 
 int ensureStage(vlcu_model* h, size_t bytes) {
     if (bytes <= h->stageBytes) return VLCU_OK;
@@ -802,6 +825,7 @@ void vlcu_destroy(vlcu_model_t* h) {
     cudaFree(h->dCovSums);
     cudaFree(h->dStage);
     cudaFree(h->dFlush);
+    for (vlcu_model::RunBuf& b : h->runBuf) cudaFree(b.p);
     if (h->evStart) cudaEventDestroy(h->evStart);
     if (h->evStop) cudaEventDestroy(h->evStop);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1007,19 +1031,13 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     r.tbSeed = d->tb_seed;
     r.tbFlags = d->tb_flags;
     for (int k = 0; k < 4; ++k) r.tbArg[k] = d->tb_arg[k];
-    // Scratch device buffers for host-side stimulus / observation / trace
+    // Scratch device buffers for host-side stimulus / observation / trace (pooled in the handle)
     uint32_t* dStim = nullptr;
     uint32_t* dObs = nullptr;
     uint8_t* dTrace = nullptr;
     uint64_t* dSamples = nullptr;
     uint32_t* dScratch = nullptr;
-    const auto cleanup = [&]() {
-        cudaFree(dStim);
-        cudaFree(dObs);
-        cudaFree(dTrace);
-        cudaFree(dSamples);
-        cudaFree(dScratch);
-    };
+    const auto cleanup = [&]() {};
 #define RUN_TRY(expr) \
     do { \
         const cudaError_t e_ = (expr); \
@@ -1028,6 +1046,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
             return failCuda(e_, #expr); \
         } \
     } while (0)
+#define RUN_BUF(ptr, which, bytes) RUN_TRY(runBuffer(h, vlcu_model::which, (bytes), reinterpret_cast<void**>(&(ptr))))
     if (!strcmp(d->tb, "trace")) {
         if (!d->stim) return fail(VLCU_E_ARG, "vlcu_run: the trace testbench needs stim");
         const size_t rowWords = static_cast<size_t>(info.inWords) * (r.stimBroadcast ? 1 : h->npad);
@@ -1046,7 +1065,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
             r.stim = d->stim;
         } else {
             const size_t bytes = rowWords * d->n_evals * sizeof(uint32_t);
-            RUN_TRY(cudaMalloc(&dStim, bytes));
+            RUN_BUF(dStim, RB_STIM, bytes);
             RUN_TRY(cudaMemcpyAsync(dStim, d->stim, bytes, cudaMemcpyHostToDevice, h->stream));
             r.stim = dStim;
         }
@@ -1058,7 +1077,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
         if (d->flags & VLCU_RUNF_OBS_DEVICE) {
             r.obs = d->obs;
         } else {
-            RUN_TRY(cudaMalloc(&dObs, obsBytes));
+            RUN_BUF(dObs, RB_OBS, obsBytes);
             RUN_TRY(cudaMemsetAsync(dObs, 0, obsBytes, h->stream));
             r.obs = dObs;
         }
@@ -1086,7 +1105,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
             traceBytes = sizeof(uint32_t) * r.traceCapWords * r.nSamples;
             const size_t scratchBytes
                 = sizeof(uint32_t) * 2U * VLCU_TRACE_WORDS_PADDED(info.traceWords) * r.nSamples;
-            RUN_TRY(cudaMalloc(&dScratch, scratchBytes));
+            RUN_BUF(dScratch, RB_SCRATCH, scratchBytes);
             RUN_TRY(cudaMemsetAsync(dScratch, 0, scratchBytes, h->stream));
             r.traceScratch = dScratch;
         } else {
@@ -1094,9 +1113,9 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
                                              + 4U * VLCU_TRACE_WORDS_PADDED(info.traceWords))
                          * r.nSamples * r.traceEvals;
         }
-        RUN_TRY(cudaMalloc(&dTrace, traceBytes));
+        RUN_BUF(dTrace, RB_TRACE, traceBytes);
         RUN_TRY(cudaMemsetAsync(dTrace, 0, traceBytes, h->stream));
-        RUN_TRY(cudaMalloc(&dSamples, sizeof(uint64_t) * r.nSamples));
+        RUN_BUF(dSamples, RB_SAMPLES, sizeof(uint64_t) * r.nSamples);
         RUN_TRY(cudaMemcpyAsync(dSamples, d->sample_instances, sizeof(uint64_t) * r.nSamples,
                                 cudaMemcpyHostToDevice, h->stream));
         r.trace = dTrace;
@@ -1116,6 +1135,7 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
     }
     if (dStim || dObs || dTrace) RUN_TRY(cudaStreamSynchronize(h->stream));
     cleanup();
+#undef RUN_BUF
 #undef RUN_TRY
     return VLCU_OK;
 }
