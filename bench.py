@@ -438,12 +438,14 @@ def run_ours(args, wl):
 
     step_no = [0]
 
+    cov_flags = 0
+
     def step():
         if wl.get("fresh_program_per_step"):
             step_no[0] += 1
-            m.run(wl["tb"], evals, flags=abi.RUNF_TB_BEGIN, **dict(run_kw, tb_seed=3 + step_no[0]))
+            m.run(wl["tb"], evals, flags=abi.RUNF_TB_BEGIN | cov_flags, **dict(run_kw, tb_seed=3 + step_no[0]))
         else:
-            m.run(wl["tb"], evals, **run_kw)
+            m.run(wl["tb"], evals, flags=cov_flags, **run_kw)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -491,7 +493,13 @@ def run_ours(args, wl):
     # ---- end to end through the C ABI with host buffers -------------------------------
     ins = {}
     images = None
-    if wl["design"] in ("rv32i", "rv32i_cov") and not wl.get("fresh_program_per_step"):
+    seeds_sets = None
+    if wl["design"] == "rv32i" and not wl.get("fresh_program_per_step") and args.e2e_mode == "seeds":
+        # what a fuzz round really needs from the host: one 64-bit program seed per instance; the
+        # image is generated on the device.  8 bytes per instance per step over PCIe.
+        seeds_sets = [pinned_array(abi, (n,), np.uint64)[0] for _ in range(2)]
+        regs_host, _ = pinned_array(abi, (n, 32), np.uint32)
+    elif wl["design"] in ("rv32i", "rv32i_cov") and not wl.get("fresh_program_per_step"):
         # the per-step input of a fuzz step is a fresh program image per instance
         images, _ptr = pinned_array(abi, (n, 1024), np.uint32)
         images[:] = m.get_member("rv32_soc__DOT__mem")
@@ -505,8 +513,9 @@ def run_ours(args, wl):
     os.makedirs(os.path.dirname(cov_path), exist_ok=True)
     sig_host, _ = pinned_array(abi, (n,), np.uint64)
     st_host, _ = pinned_array(abi, (n,), abi.STATUS_DTYPE)
-    h2d = sum(a.nbytes for a in ins.values()) + (images.nbytes if images is not None else 0)
-    d2h = sig_host.nbytes + st_host.nbytes + (regs_host.nbytes if images is not None else 0)
+    h2d = sum(a.nbytes for a in ins.values()) + (images.nbytes if images is not None else 0) \
+        + (seeds_sets[0].nbytes if seeds_sets is not None else 0)
+    d2h = sig_host.nbytes + st_host.nbytes + (regs_host.nbytes if (images is not None or seeds_sets is not None) else 0)
     if coverage:
         d2h += 8 * m.coverage_bins()
     e2e_tb = "rv32_host" if images is not None else wl["tb"]
@@ -539,15 +548,20 @@ def run_ours(args, wl):
         for _ in range(2):
             sg, _ = pinned_array(abi, (n,), np.uint64)
             st, _ = pinned_array(abi, (n,), abi.STATUS_DTYPE)
-            rg = pinned_array(abi, (n, 32), np.uint32)[0] if images is not None else None
+            rg = pinned_array(abi, (n, 32), np.uint32)[0] if (images is not None or seeds_sets is not None) else None
             res_sets.append((sg, st, rg))
 
     def e2e_launch(i):
         m.commit_staged()  # staged inputs -> state, ordered on the device behind the copies
-        if wl.get("fresh_program_per_step"):
+        if seeds_sets is not None:
+            seeds = seeds_sets[i & 1]  # this round's seeds, written by the host just now
+            seeds[:] = (np.arange(n, dtype=np.uint64) + np.uint64(rank * n)) * np.uint64(0x9e3779b97f4a7c15) \
+                + np.uint64(1000003 * (i + 1))
+            m.run("rv32_seeds", evals, flags=abi.RUNF_TB_BEGIN, tb_flags=1, tb_arg=wl["tb_arg"], tb_data=seeds)
+        elif wl.get("fresh_program_per_step"):
             step()
         else:
-            m.run(e2e_tb, evals, flags=e2e_flags, **e2e_kw)
+            m.run(e2e_tb, evals, flags=e2e_flags | cov_flags, **e2e_kw)
 
     def e2e_step(i, last):
         e2e_launch(i)
@@ -638,7 +652,11 @@ def run_ours(args, wl):
                    "timing": "sum of per-step CUDA-event durations on the launching stream, max over ranks",
                    "wall_ms_per_step_incl_flush": 1e3 * wall_s / args.steps},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "inputs": ("one 64-bit program seed per instance per round from pinned host memory (program images "
+                           "made on the device)" if seeds_sets is not None else
+                           "a 4 KB program image per instance per round from pinned host memory" if images is not None
+                           else "the testbench's per-instance inputs")},
         "gpu_launches": int(launches),
         "parity_gate": gate,
         "coverage_allreduce": cov_leg,
@@ -821,6 +839,9 @@ def main():
     ap.add_argument("--cycles", type=int, default=0, help="clock cycles per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-gate", action="store_true", help="(profiling runs only)")
+    ap.add_argument("--e2e-mode", default="seeds", choices=["seeds", "images"],
+                    help="rv32i end-to-end leg: the host sends a program seed per instance per round (default; "
+                         "images are made on the device) or a whole 4 KB program image per instance")
     ap.add_argument("--stream-mode", default="tensor", choices=["tensor", "bulk1d", "direct"],
                     help="ports_stream A/B: rows staged by 2-D tensor TMA tiles (default), by per-word 1-D "
                          "bulk copies, or read/written with plain global accesses")

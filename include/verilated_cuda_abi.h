@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define VLCU_ABI_VERSION 2
+#define VLCU_ABI_VERSION 3
 
 enum {
     VLCU_OK = 0,
@@ -132,7 +132,15 @@ typedef struct {
     uint32_t tb_flags;
     uint32_t tb_arg[4];
     uint32_t pad3_;
+    /* optional per-run data of a design-specific testbench (ABI 3): tb_data_bytes bytes copied
+       host -> device before the launch (asynchronously when page-locked) and handed to the
+       testbench as its first pointer argument -- e.g. one 64-bit program seed per instance for
+       the RV32I fuzz campaign ("rv32_seeds"), 8 bytes per instance instead of a 4 KB image.
+       With VLCU_RUNF_TBDATA_DEVICE tb_data already is device memory. */
+    const void* tb_data;
+    uint64_t tb_data_bytes;
 } vlcu_run_desc_t;
+#define VLCU_RUNF_TBDATA_DEVICE 0x100u
 #define VLCU_TBF_FUZZ_RESET_LOW 0x1u  /* input row word 1 is an active-low reset */
 #define VLCU_TBF_FUZZ_RESET_HIGH 0x2u /* ... an active-high reset */
 #define VLCU_TBF_FUZZ_UNIFORM 0x4u    /* all instances see the same stimulus */

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(abi.lib, n), f"libverilated_cuda.so lacks {n}"
     assert sorted(abi.SIGNATURES) == names, "abi.py and the header disagree"
-    assert abi.lib.vlcu_abi_version() == 2
+    assert abi.lib.vlcu_abi_version() == 3
 
 
 def test_designs_are_registered():

@@ -281,3 +281,27 @@ def test_full_batch_signatures_sample_against_oracle(abi):
         want = O.rv32_run(48, evals, inst_base=base, seed=1, rand_reset=2, tb_seed=9, threads=4)
         assert (sig[base:base + 48] == want.sigs).all()
         assert (retired[base:base + 48] == want.scalars[:, 6]).all()
+
+
+def test_campaign_with_host_supplied_seeds(abi):
+    """bench.py's end-to-end leg: the host hands one 64-bit program seed per instance to every
+    round (vlcu_run_desc_t.tb_data); the images are made on the device.  Same as loading the
+    images rv32_gen_program makes from those seeds on the host."""
+    n, evals = 130, 500
+    rng = np.random.default_rng(77)
+    with abi.Model("rv32i", n, seed=5, rand_reset=2) as m:
+        sigs = []
+        for k in range(2):
+            seeds = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+            images = np.stack([O.rv32_gen_program(int(s)) for s in seeds])
+            want = O.rv32_run(n, evals, seed=5, rand_reset=2, reset_time=6, rounds=1, mem_images=images,
+                              obs_evals=evals)
+            if k:  # (a second round on the same models: compare what a fresh oracle can)
+                m.reset()
+            obs, _ = m.run("rv32_seeds", evals, flags=abi.RUNF_TB_BEGIN, obs_evals=evals, tb_flags=1,
+                           tb_arg=(6, 0, 0, 0), tb_data=seeds)
+            assert (obs == want.obs).all() and (m.signatures() == want.sigs).all(), k
+            assert (m.get_member("rv32_soc__DOT__mem")[:, :512] == images[:, :512]).sum() > n * 500
+            sigs.append(m.signatures())
+        assert (sigs[0] != sigs[1]).any()
+

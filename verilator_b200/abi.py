@@ -38,7 +38,8 @@ class RunDesc(ctypes.Structure):
                 ("stim", c_vp), ("obs", c_vp), ("obs_evals", c_u64),
                 ("sample_instances", c_vp), ("n_samples", c_u32), ("trace_stream_words", c_u32),
                 ("trace_out", c_vp), ("trace_evals", c_u64),
-                ("tb_seed", c_u64), ("tb_flags", c_u32), ("tb_arg", c_u32 * 4), ("pad3_", c_u32)]
+                ("tb_seed", c_u64), ("tb_flags", c_u32), ("tb_arg", c_u32 * 4), ("pad3_", c_u32),
+                ("tb_data", c_vp), ("tb_data_bytes", c_u64)]
 
 
 STATUS_DTYPE = np.dtype([
@@ -53,6 +54,7 @@ DIR_IN, DIR_OUT, DIR_INOUT = 0, 1, 2
 RUNF_NO_STREAM = 0x20
 RUNF_BULK_1D = 0x40
 RUNF_TRACE_CHANGES = 0x80
+RUNF_TBDATA_DEVICE = 0x100
 RUNF_TB_BEGIN, RUNF_STOP_ON_FINISH, RUNF_STIM_DEVICE, RUNF_OBS_DEVICE, RUNF_STIM_BROADCAST = (
     1, 2, 4, 8, 16)
 FUZZ_RESET_LOW, FUZZ_RESET_HIGH, FUZZ_UNIFORM = 1, 2, 4  # tb_flags of the "fuzz" testbench
@@ -259,7 +261,7 @@ class Model:
         _check(lib.vlcu_eval(self.h))
 
     def run(self, tb, n_evals, flags=0, stim=None, obs_evals=0, samples=None, trace_evals=0,
-            tb_seed=0, tb_flags=0, tb_arg=(0, 0, 0, 0), trace_stream_words=0):
+            tb_seed=0, tb_flags=0, tb_arg=(0, 0, 0, 0), trace_stream_words=0, tb_data=None):
         """Returns (obs, trace): obs is uint32 [obs_evals][out_words][n] or None; trace is a
         uint8 array [trace_evals][n_samples][record_bytes] or None -- or, with
         trace_stream_words, the uint32 change streams [n_samples][trace_stream_words]."""
@@ -304,6 +306,11 @@ class Model:
             d.n_samples = len(samples)
             d.trace_out = trace.ctypes.data
             d.trace_evals = trace_evals
+        if tb_data is not None:  # per-run data of the design's testbench (e.g. a seed per instance)
+            tb_data = np.ascontiguousarray(tb_data)
+            keep.append(tb_data)
+            d.tb_data = tb_data.ctypes.data
+            d.tb_data_bytes = tb_data.nbytes
         d.tb_seed = tb_seed
         d.tb_flags = tb_flags
         for k in range(4):

@@ -47,7 +47,26 @@ struct TbRv32Host final {
         TbRv32Rand::drive<T_Design>(top, ctx, r, inst, e);
     }
 };
+// A fuzz campaign as the host drives it: ONE 64-bit program seed per instance per round, supplied
+// by the host (vlcu_run_desc_t.tb_data: uint64 [instances of this shard]); the program image is
+// made on the device ("stimulus generated on device"), so a round moves 8 bytes per
+// instance over PCIe instead of a 4 KB image.  Clocking as rv32_rand.
+struct TbRv32Seeds final {
+    static constexpr const char* name() { return "rv32_seeds"; }
+    template <class T_Design>
+    VLCU_D static void begin(typename T_Design::Root& top, VlcuContext&, const VlcuRunDev& r,
+                             uint64_t inst, uint64_t) {
+        top.clk = 0;
+        top.resetn = 0;
+        rv32_gen_program(top.rv32_soc__DOT__mem, static_cast<const uint64_t*>(r.tbPtr[0])[inst]);
+    }
+    template <class T_Design>
+    VLCU_D static void drive(typename T_Design::Root& top, VlcuContext& ctx, const VlcuRunDev& r,
+                             uint64_t inst, uint64_t e) {
+        TbRv32Rand::drive<T_Design>(top, ctx, r, inst, e);
+    }
+};
 // Registered with the design (VLCU_REGISTER_DESIGN at the end of the emitted model)
-#define VLCU_TESTBENCHES , TbRv32Rand, TbRv32Host
+#define VLCU_TESTBENCHES , TbRv32Rand, TbRv32Host, TbRv32Seeds
 
 #endif  // guard

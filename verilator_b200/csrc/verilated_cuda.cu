@@ -172,7 +172,7 @@ struct vlcu_model final {
     size_t resBytes = 0;
     // Device scratch of vlcu_run (host-side stimulus / observation / trace), kept between calls
     // and grown on demand: a testbench that calls vlcu_run per step pays no cudaMalloc/cudaFree
-    enum { RB_STIM, RB_OBS, RB_TRACE, RB_SAMPLES, RB_SCRATCH, RB_COUNT };
+    enum { RB_STIM, RB_OBS, RB_TRACE, RB_SAMPLES, RB_SCRATCH, RB_TBDATA, RB_COUNT };
     struct RunBuf final {
         void* p = nullptr;
         size_t cap = 0;
@@ -1068,6 +1068,16 @@ int vlcu_run(vlcu_model_t* h, const vlcu_run_desc_t* d) {
             RUN_BUF(dStim, RB_STIM, bytes);
             RUN_TRY(cudaMemcpyAsync(dStim, d->stim, bytes, cudaMemcpyHostToDevice, h->stream));
             r.stim = dStim;
+        }
+    }
+    if (d->tb_data && d->tb_data_bytes) {
+        if (d->flags & VLCU_RUNF_TBDATA_DEVICE) {
+            r.tbPtr[0] = const_cast<void*>(d->tb_data);
+        } else {
+            uint8_t* dTbData = nullptr;
+            RUN_BUF(dTbData, RB_TBDATA, d->tb_data_bytes);
+            RUN_TRY(cudaMemcpyAsync(dTbData, d->tb_data, d->tb_data_bytes, cudaMemcpyHostToDevice, h->stream));
+            r.tbPtr[0] = dTbData;
         }
     }
     size_t obsBytes = 0;
