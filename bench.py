@@ -109,6 +109,13 @@ WORKLOADS = {
         note="rv32_soc.v, one program image for all instances; instances differ only in the "
              "x-initial unique reset values of registers and register file (VL_SCOPED_RAND_RESET_* "
              "from randSeed = 1 ^ instance)"),
+    # x_initial with the index-uniformity hint: the same core emitted with
+    # --cuda-array-interleave, its memory [word][instance]: the instances run ONE program, their
+    # fetches are in lock-step, so a warp's fetch is one 128-byte line instead of 32 sectors
+    "x_initial_il": dict(
+        design="rv32i_il", ref_design="rv32i", tb="rv32_rand", instances=16384, cycles=4096, tb_flags=2,
+        tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(), same_program=True,
+        note="x_initial with the program/data memory kept [word][instance] (--cuda-array-interleave)"),
     # State streaming: 4 KB of state per instance, all of it read and rewritten
     # every clock cycle by a 1,023-iteration loop; 303,104 instances (= 2 waves of 148 SMs x 16
     # resident 64-thread CTAs) = 1.2 GB of state, so every cycle streams it from and to HBM.  V3EmitCuda keeps the array [element][instance] because
@@ -253,7 +260,7 @@ def cpu_reference_run(wl, sample_instances, cycles, threads):
         O.generic_fuzz(wl["design"], sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                        tb_flags=wl["tb_flags"], reset_periods=wl["tb_arg"][0], sparse_mask=wl["tb_arg"][1],
                        threads=threads)
-    elif wl["design"] in ("rv32i", "rv32i_cov"):
+    elif wl["design"] in ("rv32i", "rv32i_cov", "rv32i_il"):
         O.rv32_run(sample_instances, 2 * cycles, seed=1, rand_reset=wl["rand_reset"], tb_seed=3,
                    threads=threads, cov=wl["design"] == "rv32i_cov",
                    rounds=1 if wl.get("fresh_program_per_step") else 0, reset_time=wl["tb_arg"][0],
@@ -286,7 +293,7 @@ def parity_gate(wl, sigs, n, inst_base, total_evals, campaign_rounds, first_roun
             _, want = O.generic_fuzz(wl["design"], k, total_evals, inst_base=gbase, seed=1,
                                      rand_reset=wl["rand_reset"], tb_seed=3, tb_flags=wl["tb_flags"],
                                      reset_periods=wl["tb_arg"][0], sparse_mask=wl["tb_arg"][1], threads=8)
-        elif wl["design"] in ("rv32i", "rv32i_cov"):
+        elif wl["design"] in ("rv32i", "rv32i_cov", "rv32i_il"):
             if wl.get("fresh_program_per_step"):
                 want = O.rv32_run(k, total_evals // campaign_rounds, inst_base=gbase, seed=1,
                                   rand_reset=wl["rand_reset"], tb_seed=first_round_seed, reset_time=wl["tb_arg"][0],
@@ -499,7 +506,7 @@ def run_ours(args, wl):
         # image is generated on the device.  8 bytes per instance per step over PCIe.
         seeds_sets = [pinned_array(abi, (n,), np.uint64)[0] for _ in range(2)]
         regs_host, _ = pinned_array(abi, (n, 32), np.uint32)
-    elif wl["design"] in ("rv32i", "rv32i_cov") and not wl.get("fresh_program_per_step"):
+    elif wl["design"] in ("rv32i", "rv32i_cov", "rv32i_il") and not wl.get("fresh_program_per_step"):
         # the per-step input of a fuzz step is a fresh program image per instance
         images, _ptr = pinned_array(abi, (n, 1024), np.uint32)
         images[:] = m.get_member("rv32_soc__DOT__mem")

@@ -368,7 +368,8 @@ class EmitCudaModel final : public EmitCFunc {
                 m.storage = CudaStorage::SHARED;
             } else if (bytes <= 2048) {
                 m.storage = CudaStorage::LOCAL;
-            } else if (!m.isWide && !m_dataIndexed.count(varp) && V3EmitCuda::layoutSelection()) {
+            } else if (!m.isWide && m.dims.size() == 1 && V3EmitCuda::layoutSelection()
+                       && (!m_dataIndexed.count(varp) || V3EmitCuda::interleaveAll())) {
                 // large, and every run-time index is the same in all instances (loop counters):
                 // leave it in the SoA block, [element][instance], so that a warp's access coalesces
                 m.storage = CudaStorage::INTERLEAVED;
@@ -1991,6 +1992,7 @@ bool V3EmitCuda::s_leafCaching = true;
 bool V3EmitCuda::s_leafPrefetch = false;
 int V3EmitCuda::s_chunkNodes = 0;
 bool V3EmitCuda::s_shareCode = true;
+bool V3EmitCuda::s_interleaveAll = false;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -28,6 +28,12 @@ public:
     // and instance-major placement of large arrays (off: always instance-major)
     static void layoutSelection(bool flag) { s_layoutSelection = flag; }
     static bool layoutSelection() { return s_layoutSelection; }
+    // --cuda-array-interleave: the index-uniformity hint.  Large arrays indexed by design signals
+    // are kept [element][instance] too -- right when the instances index in lock-step (one
+    // program for all, BASELINE config 3: a warp's fetch is then one 128-byte line instead of 32
+    // sectors), wrong when every instance goes its own way
+    static void interleaveAll(bool flag) { s_interleaveAll = flag; }
+    static bool interleaveAll() { return s_interleaveAll; }
     // --cuda-stream / --no-cuda-stream: force the tiled (model image stays in HBM, module
     // hierarchy kept) or the register form (single $root class held by the thread); default: the
     // emitter chooses by hierarchy and size
@@ -53,6 +59,7 @@ public:
 private:
     static bool s_enabled;
     static bool s_layoutSelection;
+    static bool s_interleaveAll;
     static int s_streamMode;  // -1 automatic, 0 register form, 1 tiled form
     static bool s_leafCaching;
     static bool s_leafPrefetch;

@@ -305,3 +305,18 @@ def test_campaign_with_host_supplied_seeds(abi):
             sigs.append(m.signatures())
         assert (sigs[0] != sigs[1]).any()
 
+
+
+@pytest.mark.parametrize("same_program", [False, True])
+def test_interleaved_memory_layout_variant(abi, same_program):
+    """the same core emitted with --cuda-array-interleave (memory kept
+    [word][instance] although it is indexed by design signals) is the same machine."""
+    n, evals = 200, 700
+    want = O.rv32_run(n, evals, seed=3, rand_reset=2, tb_seed=21, obs_evals=evals, want_mem=True,
+                      same_program=same_program)
+    with abi.Model("rv32i_il", n, seed=3, rand_reset=2) as m:
+        obs, _ = m.run("rv32_rand", evals, flags=abi.RUNF_TB_BEGIN, tb_seed=21, tb_flags=2 if same_program else 0,
+                       obs_evals=evals)
+        assert (obs == want.obs).all() and (m.signatures() == want.sigs).all()
+        assert (m.get_member("rv32_soc__DOT__mem") == want.mem).all()
+        assert (m.get_member("rv32_soc__DOT__regs") == want.regs).all()
