@@ -147,6 +147,16 @@ WORKLOADS = {
         design="veer_class", tb="fuzz", instances=65536, cycles=128, tb_flags=1,
         tb_arg=(4, 0b11100000, 0, 0), rand_reset=2, inputs=(), fuzz=True,
         note="veer_class.v at 65,536 instances (state 4x the L2)"),
+    # BASELINE.json configs[4] class: the --coverage build of the VeeR-class design (line + toggle
+    # points of every scope, ~100,000 counters per instance kept per scope in the tile image),
+    # counters reduced on the device, ncclAllReduce across GPUs, ONE merged coverage.dat
+    "cov_campaign_veer": dict(
+        design="veer_class_cov", tb="fuzz", instances=16384, cycles=64, tb_flags=1,
+        tb_arg=(4, 0b11100000, 0, 0), rand_reset=2, inputs=(), fuzz=True, coverage=True,
+        library="tests/veercov/libvlcu_veercov.so",
+        note="veer_class.v built --coverage (16-entry BTBs): fuzz campaign (random instruction, bus and interrupt stimulus made in "
+             "the kernel), per-instance per-scope counters in the tile image, reduced on the device; e2e adds the "
+             "reduction + ncclAllReduce + the merged coverage.dat per step"),
     "rv32i": dict(
         design="rv32i", tb="rv32_rand", instances=65536, cycles=2048, tb_flags=0,
         tb_arg=(0, 0, 0, 0), rand_reset=2, inputs=(),
@@ -434,6 +444,8 @@ def run_ours(args, wl):
     n = args.instances or wl["instances"]
     cycles = args.cycles or wl["cycles"]
     evals = 2 * cycles
+    if wl.get("library"):  # a design that lives in a library of its own
+        abi.load_design_library(os.path.join(ROOT, wl["library"]))
     m = abi.Model(wl["design"], n, device=local, inst_base=rank * n, seed=1,
                   rand_reset=wl["rand_reset"], msg_cap=2)
     run_kw = dict(tb_seed=3, tb_flags=wl["tb_flags"], tb_arg=wl["tb_arg"])

@@ -169,7 +169,14 @@ VLCU_HD int vlcu_ctz64(uint64_t x) {
 // the largest number of changed bits in any lane, so splitting rising and falling bits into two
 // loops costs more than it saves -- with a minimal body: find the highest set bit, its new value,
 // one multiply-add for the address, the RED.
-VLCU_HD void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t chg, uint32_t newData) {
+// (A tiled design built --coverage has tens of thousands of toggle points: the loop is a real
+// function there, VLCU_COV_NOINLINE defined by the emitted model, or nvcc needs half an hour.)
+#if defined(VLCU_COV_NOINLINE) && defined(__CUDACC__)
+#define VLCU_COV_FN __device__ __noinline__ static
+#else
+#define VLCU_COV_FN VLCU_HD
+#endif
+VLCU_COV_FN void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
     // bytes between consecutive counters: fits 32 bits for any shard below 2^30 instances; the
     // product with the counter number is formed in 64 bits
@@ -881,6 +888,113 @@ struct VlcuLanes<VlWide<N_Words>> final {
     VLCU_HD operator const EData*() const { return v[vlcu_lane()].data(); }
     VLCU_HD EData& operator[](size_t index) { return v[vlcu_lane()][index]; }
 };
+
+// uint32_t __Vcoverage[N] of a module class in a TILE: one uint64 counter per bin for the tile's
+// 32 instances together.  A design of this class has ~10^5 cover points; one counter per instance
+// would be 400 KB per instance -- gigabytes of counters bumped at random, every RED a DRAM
+// read-modify-write (measured: 0.15 M instance-cycles/s, below one CPU thread) -- while what leaves a
+// campaign is the SUM over instances (verilated_cov.cpp:368-438 merges by key).  So the warp
+// aggregates: a cover point adds, once, the number of lanes that reached it; a toggle point
+// counts, per bit position that changed in any lane, the lanes where it rose and where it fell
+// (two ballots).  The counters are the exact sums of the per-instance counters the C++ model keeps.
+struct VlcuTileCovRef final {
+    unsigned long long* m_p;
+    VLCU_HD void operator++() const {
+#ifdef __CUDA_ARCH__
+        // the lanes reaching this point together, grouped by the counter they bump (the wide
+        // toggle macro walks different bits in different lanes): one add per group
+        const unsigned lanes = __activemask();
+        const unsigned same = __match_any_sync(lanes, reinterpret_cast<unsigned long long>(m_p));
+        if ((threadIdx.x & 31U) == static_cast<unsigned>(__ffs(same) - 1)) {
+            atomicAdd(m_p, static_cast<unsigned long long>(__popc(same)));
+        }
+#else
+        ++*m_p;
+#endif
+    }
+};
+struct VlcuTileCovPtr final {
+    unsigned long long* m_p;
+    VLCU_HD VlcuTileCovRef operator[](size_t bin) const { return VlcuTileCovRef{m_p + bin}; }
+    VLCU_HD VlcuTileCovPtr operator+(size_t bin) const { return VlcuTileCovPtr{m_p + bin}; }
+};
+template <size_t N_Bins>
+struct VlcuTileCov final {
+    unsigned long long c[N_Bins];
+    VLCU_HD VlcuTileCovRef operator[](size_t bin) { return VlcuTileCovRef{&c[bin]}; }
+    VLCU_HD VlcuTileCovPtr operator+(size_t bin) { return VlcuTileCovPtr{&c[bin]}; }
+    VLCU_HD void zero(uint32_t lane) {
+        for (size_t b = lane; b < N_Bins; b += VLCU_TILE) c[b] = 0ULL;
+    }
+};
+// The wide form (verilated_cov.h:94-105 with its quirk, see VL_COV_TOGGLE_CHG_ST_W above: changed
+// bit b of word w bumps the counters of bits w*32+b, w*32+b+32, ... below `width`), warp-cooperative:
+// every loop runs the same trips in all lanes, so a 2,048-bit vector does not serialise the warp
+// (left per lane, the lanes walk different bits and the warp runs 1.4 lanes wide).
+VLCU_COV_FN void vlcu_cov_bump_wide(VlcuTileCovPtr covp, int width, WDataInP newData, WDataInP oldData) {
+#ifdef __CUDA_ARCH__
+    const unsigned lanes = __activemask();
+    const bool leader = (threadIdx.x & 31U) == static_cast<unsigned>(__ffs(lanes) - 1);
+    for (int w = 0; w < VL_WORDS_I(width); ++w) {
+        const EData chg = newData[w] ^ oldData[w];
+        const EData rise = chg & newData[w];
+        const int limit = width - w * 32;  // j < limit
+        uint32_t any = __reduce_or_sync(lanes, chg);
+        while (any) {
+            const int b = __ffs(static_cast<int>(any)) - 1;
+            any &= any - 1U;
+            const unsigned changed = __ballot_sync(lanes, (chg >> b) & 1U);
+            const unsigned rose = __ballot_sync(lanes, (rise >> b) & 1U);
+            if (leader) {
+                const unsigned long long up = __popc(rose), down = __popc(changed) - __popc(rose);
+                for (int j = b; j < limit; j += 32) {
+                    if (up) atomicAdd(covp.m_p + (w * 32 + j) * 2 + 1, up);
+                    if (down) atomicAdd(covp.m_p + (w * 32 + j) * 2, down);
+                }
+            }
+        }
+    }
+#else
+    for (int w = 0; w < VL_WORDS_I(width); ++w) {
+        EData chg = newData[w] ^ oldData[w];
+        const int limit = width - w * 32;
+        for (; chg; chg &= chg - 1U) {
+            const int b = vlcu_ctz32(chg);
+            const uint32_t bit = (newData[w] >> b) & 1U;
+            for (int j = b; j < limit; j += 32) ++covp[(w * 32 + j) * 2 + bit];
+        }
+    }
+#endif
+}
+VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, VlcuTileCovPtr covp, WDataInP newData, WDataInP oldData) {
+    vlcu_cov_bump_wide(covp, width, newData, oldData);
+}
+// Counter 2*i + (bit i of newData) for every bit i of `chg`, summed over the lanes of the warp
+VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t newData) {
+#ifdef __CUDA_ARCH__
+    const unsigned lanes = __activemask();
+    const bool leader = (threadIdx.x & 31U) == static_cast<unsigned>(__ffs(lanes) - 1);
+    uint32_t any = __reduce_or_sync(lanes, chg);
+    const uint32_t rise = chg & newData;
+    while (any) {
+        uint32_t i;
+        asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(any));
+        any ^= 1U << i;
+        const unsigned changed = __ballot_sync(lanes, (chg >> i) & 1U);
+        const unsigned rose = __ballot_sync(lanes, (rise >> i) & 1U);
+        if (leader) {
+            const unsigned up = __popc(rose), down = __popc(changed) - up;
+            if (up) atomicAdd(covp.m_p + 2U * i + 1U, static_cast<unsigned long long>(up));
+            if (down) atomicAdd(covp.m_p + 2U * i, static_cast<unsigned long long>(down));
+        }
+    }
+#else
+    for (; chg; chg &= chg - 1U) {
+        const int i = vlcu_ctz32(chg);
+        ++covp[2 * i + ((newData >> i) & 1U)];
+    }
+#endif
+}
 
 // A large array kept [element][lane]: an index that is the same in all lanes of a warp (a loop
 // counter) touches one contiguous run.  `arr.lane(vlLane)[i]` is element i of this instance.

@@ -174,6 +174,11 @@ struct VlcuCoverTable final {
 };
 #endif
 
+struct VlcuCoverScope final {
+    uint32_t tileOffset;  // of counter 0 inside a tile
+    uint32_t bins;
+};
+
 struct VlcuDesignInfo final {
     const char* name;  // design name used with vlcu_create()
     const char* topName;  // Verilog top module
@@ -212,6 +217,11 @@ struct VlcuDesignInfo final {
     //    soaOffset*npad + (e*npad + i)*elemBytes).  Else the model image is tiled: `tile` instances
     //    per tile of stateBytes*tile bytes (verilated_cuda.h "Tiled model image")
     uint32_t tile;
+    // tiled designs built --coverage: every scope keeps its own counters in the tile, ONE uint64
+    // per bin for the tile's instances together (VlcuTileCov); the shard's counter b is counter
+    // (b - first) of the scope whose range holds b
+    const struct VlcuCoverScope* coverScopes;
+    uint32_t nCoverScopes;
 };
 enum : uint32_t {
     VLCU_SAVE_ACTIVITY = 1u << 0,  // Syms::__Vserialize writes __Vm_activity first (--trace builds)

@@ -175,6 +175,68 @@ extern "C" int HARNESS_FUZZ_FN(uint64_t n, uint64_t instBase, uint64_t seedBase,
     return runAll(p, threads);
 }
 #endif
+#ifdef HARNESS_COV_FN
+// --coverage builds: a fuzz campaign of n instances whose coverage is MERGED by the reference's own
+// writer -- all models live in ONE VerilatedContext (each constructed with its own randSeed, so the
+// --x-initial values are the per-instance ones), their points register in that context's coverage
+// database, and VerilatedCovContext::write sums the counters of points with the same key
+// (include/verilated_cov.cpp:368-438).  The file is what BASELINE config 5 asks the GPU campaign
+// to reproduce: "one merged coverage.dat equal to the sum of per-instance CPU runs".
+#include "verilated_cov.h"
+extern "C" int HARNESS_COV_FN(uint64_t n, uint64_t instBase, uint64_t seedBase, int randReset,
+                              uint64_t nEvals, uint64_t tbSeed, uint32_t tbFlags, uint32_t resetPeriods,
+                              uint32_t sparseMask, uint64_t* sigs, const char* covPath) {
+    Params p{n, instBase, seedBase, randReset, nEvals, nullptr, nullptr, sigs};
+    p.tbSeed = tbSeed;
+    p.tbFlags = tbFlags;
+    p.resetPeriods = resetPeriods;
+    p.sparseMask = sparseMask;
+    const std::unique_ptr<VerilatedContext> contextp{new VerilatedContext};
+    Verilated::threadContextp(contextp.get());
+    contextp->randReset(randReset);
+    const char* argv[] = {"oracle"};
+    contextp->commandArgs(1, argv);
+    std::vector<std::unique_ptr<VTOP>> tops;
+    for (uint64_t i = 0; i < n; ++i) {
+        contextp->randSeed(static_cast<int>(seedBase ^ (instBase + i)));
+        tops.emplace_back(new VTOP{contextp.get(), "TOP"});
+        VTOP* const top = tops.back().get();
+        uint64_t sig = 0xcbf29ce484222325ULL;
+        for (uint64_t e = 0; e < nEvals; ++e) {
+            contextp->timeInc(1);
+            uint32_t fuzz[kInWords > 0 ? kInWords : 1];
+            fuzzRow(p, seedBase ^ (instBase + i), e, fuzz);
+            const uint32_t* rowp = fuzz;
+            const uint64_t stride = 1;
+            int k = 0;
+#define VLCU_PORT_IN(name, width, words) \
+    setPort(top->name, width, rowp + static_cast<uint64_t>(k) * stride, stride); \
+    k += words;
+#define VLCU_PORT_OUT(name, width, words)
+#include PORTS_INC
+#undef VLCU_PORT_IN
+#undef VLCU_PORT_OUT
+            top->eval();
+            uint32_t w[kOutWords > 0 ? kOutWords : 1];
+            k = 0;
+#define VLCU_PORT_IN(name, width, words)
+#define VLCU_PORT_OUT(name, width, words) \
+    getPort(top->name, w + k); \
+    k += words;
+#include PORTS_INC
+#undef VLCU_PORT_IN
+#undef VLCU_PORT_OUT
+            uint32_t acc = 0x811c9dc5U;
+            for (int j = 0; j < kOutWords; ++j) acc = sigWord(acc, w[j]);
+            sig = sigMix(sig, acc);
+        }
+        if (sigs) sigs[i] = sig;
+    }
+    if (covPath) contextp->coveragep()->write(covPath);
+    for (auto& top : tops) top->final();
+    return 0;
+}
+#endif
 namespace {
 int runAll(const Params& p, int threads) {
     const uint64_t n = p.n;

@@ -217,7 +217,10 @@ class EmitCudaModel final : public EmitCFunc {
     std::vector<std::pair<string, string>> m_nbaQueues;  // VlNBACommitQueue members: name, device type
     std::vector<string> m_messages;
     std::vector<string> m_plusargs;
-    int m_coverBins = 0;
+    int m_coverBins = 0;  // register form: counters of the root class; tiled form: of all scopes together
+    std::map<const AstNodeModule*, int> m_classCoverBins;  // tiled form: uint32_t __Vcoverage[n] per class
+    int m_coverBinBase = 0;  // cover table: first counter of the scope whose points are being listed
+    string m_coverHierPrefix;  // ... and what its vlNamep adds in front of a point's hierarchy
     uint32_t m_stateBytes = 0;
     bool m_coverTableMode = false;  // visiting _configure_coverage: print table rows
     std::vector<string> m_traceRows;
@@ -475,9 +478,24 @@ class EmitCudaModel final : public EmitCFunc {
             findSharedCode();
         }
         // Coverage bins of this module: the counters are one more (local memory) array
-        const_cast<AstNodeModule*>(m_topModp)->foreach([&](AstNodeCoverDecl* declp) {
-            m_coverBins = std::max(m_coverBins, declp->dataDeclThisp()->localBinNum() + declp->size());
-        });
+        const auto binsOf = [](const AstNodeModule* modp) {
+            int bins = 0;
+            const_cast<AstNodeModule*>(modp)->foreach([&](AstNodeCoverDecl* declp) {
+                if (EmitCParentModule::get(declp->dataDeclThisp()) != modp) return;
+                bins = std::max(bins, declp->dataDeclThisp()->localBinNum() + declp->size());
+            });
+            return bins;
+        };
+        if (m_stream) {
+            // every class keeps its own uint32_t __Vcoverage[n] (V3EmitCHeaders.cpp:153-158), every
+            // scope its own copy: the shard's counters are those of all scopes, root first
+            m_classCoverBins[m_topModp] = binsOf(m_topModp);
+            m_coverBins = m_classCoverBins[m_topModp];
+            for (const CudaClass& cls : m_subClasses) m_classCoverBins[cls.modp] = binsOf(cls.modp);
+            for (const CudaScopeInst& inst : m_scopeInsts) m_coverBins += m_classCoverBins[m_subClasses[inst.classIdx].modp];
+        } else {
+            m_coverBins = binsOf(m_topModp);
+        }
         // Offsets: largest elements first so that every array start is aligned for its type
         // (an offset is multiplied by the padded instance count, a multiple of 128)
         uint32_t offset = 0;
@@ -487,7 +505,7 @@ class EmitCudaModel final : public EmitCFunc {
                 m.offset = offset;
                 offset += m.bytes();
             }
-            if (bytes == 4 && m_coverBins) {
+            if (bytes == 4 && m_coverBins && !m_stream) {
                 CudaMember cov;
                 cov.name = "__Vcoverage";
                 cov.kind = 4;
@@ -504,7 +522,7 @@ class EmitCudaModel final : public EmitCFunc {
                 m_pendingCoverage = cov;
             }
         }
-        if (m_coverBins) m_members.push_back(m_pendingCoverage);
+        if (m_coverBins && !m_stream) m_members.push_back(m_pendingCoverage);
         m_stateBytes = (offset + 7U) & ~7U;
         // Touched bytes per eval (static)
         const auto touched = [this](const AstNodeModule* modp, const std::vector<CudaMember>& members,
@@ -652,6 +670,9 @@ class EmitCudaModel final : public EmitCFunc {
             }
         }
         puts("const char* vlNamep;  // (one per tile, set by the reset kernel)\n");
+        if (const int bins = m_classCoverBins[modp]) {
+            puts("VlcuTileCov<" + cvtToStr(bins) + "> __Vcoverage;  // one uint64 counter per bin for the tile's instances\n");
+        }
         for (const int bytes : {8, 4, 2, 1}) {
             for (const CudaMember& m : members) {
                 if (m.elemBytes != bytes) continue;
@@ -941,6 +962,23 @@ class EmitCudaModel final : public EmitCFunc {
                 if (!(assignp && assignp->lhsp() == refp && topStmts.count(assignp))) c.load = true;
             }
         });
+        // A member that is only ever assigned, whole and on every path, gains nothing from a local:
+        // it would hold a register from the assignment to the scatter.  It is stored where it is
+        // assigned (nothing reads it back in this function, and nobody else runs meanwhile).
+        for (auto it = m_cached.begin(); it != m_cached.end();) {
+            it = it->second.load ? std::next(it) : m_cached.erase(it);
+        }
+        // ... and a thread has 255 registers: the members a big leaf meets first (up to
+        // --cuda-gather-words 32-bit words of them) are gathered, the rest are read and written in
+        // place, or the gather would only move the traffic to the stack
+        size_t words = 0;
+        std::vector<std::pair<unsigned long, string>> order;
+        for (const auto& it : m_cached) order.emplace_back(std::stoul(it.second.local.substr(4)), it.first);
+        std::sort(order.begin(), order.end());
+        for (const auto& entry : order) {
+            words += m_cached[entry.second].ctype == "QData" ? 2 : 1;
+            if (words > V3EmitCuda::gatherWords()) m_cached.erase(entry.second);
+        }
     }
 
     // ---- sharing between instances ------------------------------------------------------------
@@ -1389,11 +1427,11 @@ class EmitCudaModel final : public EmitCFunc {
     // _configure_coverage: each registration becomes a row of the host coverage table
     void visit(AstCoverOtherDecl* nodep) override {
         if (!m_coverTableMode) return;
-        puts("t.other(" + cvtToStr(coverageBinNum(nodep)) + ", ");
+        puts("t.other(" + cvtToStr(m_coverBinBase + coverageBinNum(nodep)) + ", ");
         putsQuoted(protect(nodep->fileline()->filename()));
         puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", "
              + cvtToStr(nodep->offset() + nodep->fileline()->firstColumn()) + ", ");
-        putsQuoted((!nodep->hier().empty() ? "." : "") + nodep->hier());
+        putsQuoted(m_coverHierPrefix + (!nodep->hier().empty() ? "." : "") + nodep->hier());
         puts(", ");
         putsQuoted(nodep->page());
         puts(", ");
@@ -1404,12 +1442,12 @@ class EmitCudaModel final : public EmitCFunc {
     }
     void visit(AstCoverToggleDecl* nodep) override {
         if (!m_coverTableMode) return;
-        puts("t.toggle(" + cvtToStr(coverageBinNum(nodep)) + ", " + cvtToStr(nodep->range().right()) + ", "
+        puts("t.toggle(" + cvtToStr(m_coverBinBase + coverageBinNum(nodep)) + ", " + cvtToStr(nodep->range().right()) + ", "
              + cvtToStr(nodep->range().left()) + ", " + cvtToStr(nodep->range().ranged()) + ", ");
         putsQuoted(protect(nodep->fileline()->filename()));
         puts(", " + cvtToStr(nodep->fileline()->lineno()) + ", " + cvtToStr(nodep->fileline()->firstColumn())
              + ", ");
-        putsQuoted((!nodep->hier().empty() ? "." : "") + nodep->hier());
+        putsQuoted(m_coverHierPrefix + (!nodep->hier().empty() ? "." : "") + nodep->hier());
         puts(", ");
         putsQuoted(nodep->page());
         puts(", ");
@@ -1630,6 +1668,7 @@ class EmitCudaModel final : public EmitCFunc {
             puts("// 4 CTAs of 64 threads per SM = 255 registers per thread: the leaves' gathers then keep\n");
             puts("// 100+ loads in flight per warp without spilling (measured: profiles/README.md)\n");
             puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 4\n#endif\n");
+            if (m_coverBins) puts("#define VLCU_COV_NOINLINE 1  // " + cvtToStr(m_coverBins) + " counters: the toggle loop is a real function\n");
         } else {
             // Occupancy target of the kernels (verilated_cuda_launch.h: __launch_bounds__(64,
             // VLCU_MIN_BLOCKS), default 7 = 146 registers per thread).  A design that keeps almost
@@ -1759,6 +1798,12 @@ class EmitCudaModel final : public EmitCFunc {
             // -- the reset values hash the name, V3EmitCFunc.cpp:668-678 -- and constructed
             puts("Syms* const vlSymsp = vlSelf->symsp;\n");
             puts("vlSymsp->TOP.vlNamep = \"TOP\";\n");
+            if (m_classCoverBins[m_topModp]) puts("vlSymsp->TOP.__Vcoverage.zero(vlSelf->lane);\n");
+            for (const CudaScopeInst& inst : m_scopeInsts) {
+                if (m_classCoverBins[m_subClasses[inst.classIdx].modp]) {
+                    puts("vlSymsp->" + inst.sym + ".__Vcoverage.zero(vlSelf->lane);\n");
+                }
+            }
             if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
                 puts(funcNameProtect(funcp) + "(&vlSymsp->TOP, vlSymsp, vlCtx);\n");
             }
@@ -1884,17 +1929,50 @@ class EmitCudaModel final : public EmitCFunc {
         if (m_coverBins) {
             puts("static VlcuCoverTable t;\n");
             puts("if (t.points.empty()) {\n");
-            if (const AstCFunc* const funcp = findFunc("_configure_coverage")) {
-                VL_RESTORER(m_coverTableMode);
-                VL_RESTORER(m_cfuncp);
-                m_coverTableMode = true;
-                m_cfuncp = funcp;  // coverageBinNum() picks the object-local bin inside a member function
-                for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
-                    if (VN_IS(stmtp, NodeCoverDecl)) iterateConst(stmtp);
+            // what __Vconfigure registers (V3EmitCImp.cpp:163-262), scope by scope
+            const auto listPoints = [this](const AstNodeModule* modp, int binBase, const string& hierPrefix) {
+                for (AstNode* nodep = modp->stmtsp(); nodep; nodep = nodep->nextp()) {
+                    AstCFunc* const funcp = VN_CAST(nodep, CFunc);
+                    if (!funcp || funcp->name() != "_configure_coverage") continue;
+                    VL_RESTORER(m_coverTableMode);
+                    VL_RESTORER(m_cfuncp);
+                    VL_RESTORER(m_modp);
+                    VL_RESTORER(m_coverBinBase);
+                    VL_RESTORER_COPY(m_coverHierPrefix);
+                    m_coverTableMode = true;
+                    m_cfuncp = funcp;  // coverageBinNum() picks the object-local bin inside a member function
+                    m_modp = modp;
+                    m_coverBinBase = binBase;
+                    m_coverHierPrefix = hierPrefix;
+                    for (AstNode* stmtp = funcp->stmtsp(); stmtp; stmtp = stmtp->nextp()) {
+                        if (VN_IS(stmtp, NodeCoverDecl)) iterateConst(stmtp);
+                    }
+                }
+            };
+            listPoints(m_topModp, 0, "");
+            if (m_stream) {
+                int base = m_classCoverBins[m_topModp];
+                for (const CudaScopeInst& inst : m_scopeInsts) {
+                    const AstNodeModule* const modp = m_subClasses[inst.classIdx].modp;
+                    listPoints(modp, base, "." + inst.pretty);  // vlNamep = "TOP.<scope>"
+                    base += m_classCoverBins[modp];
                 }
             }
             puts("t.finish();\n");
             puts("}\n");
+            if (m_stream) {
+                puts("// where each scope's counters are in a tile: byte offset of counter 0 (uint64 each), counters\n");
+                puts("static const VlcuCoverScope coverScopes[] = {\n");
+                if (const int bins = m_classCoverBins[m_topModp]) {
+                    puts("{VLCU_TILE_OFF(" + m_symsName + ", TOP, __Vcoverage), " + cvtToStr(bins) + "},\n");
+                }
+                for (const CudaScopeInst& inst : m_scopeInsts) {
+                    if (const int bins = m_classCoverBins[m_subClasses[inst.classIdx].modp]) {
+                        puts("{VLCU_TILE_OFF(" + m_symsName + ", " + inst.sym + ", __Vcoverage), " + cvtToStr(bins) + "},\n");
+                    }
+                }
+                puts("};\n");
+            }
         }
         // Messages and plusargs
         puts("static const char* const messages[] = {");
@@ -1944,7 +2022,9 @@ class EmitCudaModel final : public EmitCFunc {
         puts("VLCU_DESIGN_NAME, " + quoted(topName) + ", members, sizeof(members) / sizeof(members[0]),\n");
         puts("T::kStateBytes, T::kInWords, T::kOutWords, T::kInBytes, T::kOutBytes, T::kTouchedReadBytes, "
              "T::kTouchedWriteBytes,\n");
-        if (m_coverBins) {
+        if (m_coverBins && m_stream) {
+            puts("t.points.data(), static_cast<uint32_t>(t.points.size()), " + cvtToStr(m_coverBins) + ", 0,\n");
+        } else if (m_coverBins) {
             puts("t.points.data(), static_cast<uint32_t>(t.points.size()), " + cvtToStr(m_coverBins)
                  + ", T::OFF___Vcoverage,\n");
         } else {
@@ -1964,7 +2044,9 @@ class EmitCudaModel final : public EmitCFunc {
                << (v3Global.rootp()->timeprecision().isNone()
                        ? -1
                        : std::abs(v3Global.rootp()->timeprecision().powerOfTen()))
-               << ", " << (m_stream ? "VLCU_TILE" : "0") << "};\n";
+               << ", " << (m_stream ? "VLCU_TILE" : "0")
+               << (m_stream && m_coverBins ? ", coverScopes, sizeof(coverScopes) / sizeof(coverScopes[0])" : ", nullptr, 0")
+               << "};\n";
             puts(os.str());
         }
         puts("return s;\n}\n");
@@ -1993,6 +2075,7 @@ bool V3EmitCuda::s_leafPrefetch = false;
 int V3EmitCuda::s_chunkNodes = 0;
 bool V3EmitCuda::s_shareCode = true;
 bool V3EmitCuda::s_interleaveAll = false;
+int V3EmitCuda::s_gatherWords = 160;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -43,6 +43,9 @@ public:
     // members they touch into locals at entry and scatter the written ones at exit
     static void leafCaching(bool flag) { s_leafCaching = flag; }
     static bool leafCaching() { return s_leafCaching; }
+    // --cuda-gather-words <n>: 32-bit words of members one leaf may hold in locals
+    static void gatherWords(int words) { s_gatherWords = words; }
+    static size_t gatherWords() { return static_cast<size_t>(s_gatherWords); }
     // --cuda-leaf-prefetch / --no-cuda-leaf-prefetch: ... and the caller issues the next leaf's
     // gather as prefetches one call ahead
     static void leafPrefetch(bool flag) { s_leafPrefetch = flag; }
@@ -62,6 +65,7 @@ private:
     static bool s_interleaveAll;
     static int s_streamMode;  // -1 automatic, 0 register form, 1 tiled form
     static bool s_leafCaching;
+    static int s_gatherWords;
     static bool s_leafPrefetch;
     static int s_chunkNodes;
     static bool s_shareCode;

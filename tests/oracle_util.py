@@ -290,3 +290,18 @@ def last_loop_seconds():
     fn = ref().vlref_last_loop_seconds
     fn.restype = ctypes.c_double
     return fn()
+
+
+def generic_cov(design, n, n_evals, cov_path, inst_base=0, seed=1, rand_reset=2, tb_seed=0, tb_flags=0,
+                reset_periods=0, sparse_mask=0):
+    """--coverage build of a generic-harness design: a fuzz campaign of n instances whose coverage
+    the reference's own VerilatedCovContext::write merges into `cov_path` (all models in one
+    context; verilated_cov.cpp:368-438 sums the counters of points with equal keys).  Returns sigs."""
+    fn = getattr(ref(), f"vlref_{design}_cov")
+    fn.restype = i32
+    fn.argtypes = [u64, u64, u64, i32, u64, u64, u32, u32, u32, vp, cp]
+    sigs = np.zeros(n, dtype=np.uint64)
+    rc = fn(n, inst_base, seed, rand_reset, n_evals, tb_seed, tb_flags, reset_periods, sparse_mask,
+            sigs.ctypes.data, cov_path.encode())
+    assert rc == 0
+    return sigs

@@ -370,7 +370,7 @@ const VlcuDesignInfo& Vt_EXAMPLE__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x3c353f08d7831df8ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x3c353f08d7831df8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

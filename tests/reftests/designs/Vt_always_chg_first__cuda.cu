@@ -342,7 +342,7 @@ const VlcuDesignInfo& Vt_always_chg_first__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x10ce5447a7957624ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x10ce5447a7957624ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

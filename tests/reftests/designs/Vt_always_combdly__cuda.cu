@@ -364,7 +364,7 @@ const VlcuDesignInfo& Vt_always_combdly__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xf0ab091109f88985ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0xf0ab091109f88985ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -380,7 +380,7 @@ const VlcuDesignInfo& Vt_always_dly__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xdcbbc995b8129b2eULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0xdcbbc995b8129b2eULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

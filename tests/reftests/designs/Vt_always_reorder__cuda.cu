@@ -355,7 +355,7 @@ const VlcuDesignInfo& Vt_always_reorder__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xbbc1c41a4ecf7158ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xbbc1c41a4ecf7158ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

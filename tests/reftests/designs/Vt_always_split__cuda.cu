@@ -444,7 +444,7 @@ const VlcuDesignInfo& Vt_always_split__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xa46acd2e3d63e8cbULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xa46acd2e3d63e8cbULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

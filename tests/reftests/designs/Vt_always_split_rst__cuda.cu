@@ -605,7 +605,7 @@ const VlcuDesignInfo& Vt_always_split_rst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x72ea31a112838193ULL, nullptr, 12, 12, 0};
+        saveOrder, 29, 0, 0x72ea31a112838193ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

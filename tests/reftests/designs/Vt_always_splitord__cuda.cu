@@ -549,7 +549,7 @@ const VlcuDesignInfo& Vt_always_splitord__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x839bb1ba8a306f3fULL, nullptr, 12, 12, 0};
+        saveOrder, 20, 0, 0x839bb1ba8a306f3fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

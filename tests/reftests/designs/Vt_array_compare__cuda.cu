@@ -222,7 +222,7 @@ const VlcuDesignInfo& Vt_array_compare__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 3, 0, 0x7d9a61755df4f783ULL, nullptr, 12, 12, 0};
+        saveOrder, 3, 0, 0x7d9a61755df4f783ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -440,7 +440,7 @@ const VlcuDesignInfo& Vt_array_mda__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x396f93b4708e9aabULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x396f93b4708e9aabULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -153,7 +153,7 @@ const VlcuDesignInfo& Vt_array_sel_short__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0x9a3b087dbf0c2514ULL, nullptr, 12, 12, 0};
+        saveOrder, 1, 0, 0x9a3b087dbf0c2514ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

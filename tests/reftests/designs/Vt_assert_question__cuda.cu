@@ -345,7 +345,7 @@ const VlcuDesignInfo& Vt_assert_question__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x9e158bf2a1918456ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x9e158bf2a1918456ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

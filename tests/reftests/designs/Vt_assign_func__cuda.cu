@@ -560,7 +560,7 @@ const VlcuDesignInfo& Vt_assign_func__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x2208510c11c41db4ULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x2208510c11c41db4ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -332,7 +332,7 @@ const VlcuDesignInfo& Vt_assign_inline__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x37543a136dcb5baULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x37543a136dcb5baULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -445,7 +445,7 @@ const VlcuDesignInfo& Vt_blocking__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0xdb5148da9ffd80a2ULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0xdb5148da9ffd80a2ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

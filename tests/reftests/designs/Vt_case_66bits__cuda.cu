@@ -322,7 +322,7 @@ const VlcuDesignInfo& Vt_case_66bits__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xca1ed157e3ed1d2aULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xca1ed157e3ed1d2aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

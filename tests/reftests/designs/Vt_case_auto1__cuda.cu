@@ -681,7 +681,7 @@ const VlcuDesignInfo& Vt_case_auto1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xff608caab268cefULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xff608caab268cefULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -3356,7 +3356,7 @@ const VlcuDesignInfo& Vt_case_deep__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 54, 0, 0x77787360b8d7627fULL, nullptr, 12, 12, 0};
+        saveOrder, 54, 0, 0x77787360b8d7627fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -556,7 +556,7 @@ const VlcuDesignInfo& Vt_case_itemwidth__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x1953e327e2fc9fc4ULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x1953e327e2fc9fc4ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -558,7 +558,7 @@ const VlcuDesignInfo& Vt_case_nest__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x2255b7bb41ea054eULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x2255b7bb41ea054eULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

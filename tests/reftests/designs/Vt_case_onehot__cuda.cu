@@ -387,7 +387,7 @@ const VlcuDesignInfo& Vt_case_onehot__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x3c353f08d7831df8ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x3c353f08d7831df8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

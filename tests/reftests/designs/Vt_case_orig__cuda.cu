@@ -395,7 +395,7 @@ const VlcuDesignInfo& Vt_case_orig__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x52a27f05fd0e148aULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x52a27f05fd0e148aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

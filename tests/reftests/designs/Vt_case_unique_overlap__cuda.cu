@@ -330,7 +330,7 @@ const VlcuDesignInfo& Vt_case_unique_overlap__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xe4ce32b23f077e8fULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xe4ce32b23f077e8fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

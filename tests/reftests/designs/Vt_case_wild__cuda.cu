@@ -789,7 +789,7 @@ const VlcuDesignInfo& Vt_case_wild__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0xdae8648f543dd3aULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0xdae8648f543dd3aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

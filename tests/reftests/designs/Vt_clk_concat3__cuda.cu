@@ -341,7 +341,7 @@ const VlcuDesignInfo& Vt_clk_concat3__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xa67a4c71354645e9ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xa67a4c71354645e9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -361,7 +361,7 @@ const VlcuDesignInfo& Vt_clk_concat4__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x48b550baa35630c3ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x48b550baa35630c3ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

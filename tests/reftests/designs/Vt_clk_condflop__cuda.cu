@@ -504,7 +504,7 @@ const VlcuDesignInfo& Vt_clk_condflop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x86c87489facfdcc7ULL, nullptr, 12, 12, 0};
+        saveOrder, 19, 0, 0x86c87489facfdcc7ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

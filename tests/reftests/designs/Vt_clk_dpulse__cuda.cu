@@ -495,7 +495,7 @@ const VlcuDesignInfo& Vt_clk_dpulse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xba734300405edaeaULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xba734300405edaeaULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

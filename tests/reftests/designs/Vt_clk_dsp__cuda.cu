@@ -610,7 +610,7 @@ const VlcuDesignInfo& Vt_clk_dsp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0x911b6693bd329ef9ULL, nullptr, 12, 12, 0};
+        saveOrder, 23, 0, 0x911b6693bd329ef9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

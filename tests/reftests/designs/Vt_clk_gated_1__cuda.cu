@@ -360,7 +360,7 @@ const VlcuDesignInfo& Vt_clk_gated_1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xd399fac5cfc0a55cULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xd399fac5cfc0a55cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

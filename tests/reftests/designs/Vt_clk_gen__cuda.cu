@@ -521,7 +521,7 @@ const VlcuDesignInfo& Vt_clk_gen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x62ad85a9ec1d2fe7ULL, nullptr, 12, 12, 0};
+        saveOrder, 20, 0, 0x62ad85a9ec1d2fe7ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -606,7 +606,7 @@ const VlcuDesignInfo& Vt_clk_powerdn__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x28ea696f4f5177a9ULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x28ea696f4f5177a9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -131,7 +131,7 @@ const VlcuDesignInfo& Vt_concat_large__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 0, 0, 0xe3b0c44298fc1c14ULL, nullptr, 12, 12, 0};
+        saveOrder, 0, 0, 0xe3b0c44298fc1c14ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -560,7 +560,7 @@ const VlcuDesignInfo& Vt_concat_opt__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x7fe1b21b0ff0c8ffULL, nullptr, 12, 12, 0};
+        saveOrder, 21, 0, 0x7fe1b21b0ff0c8ffULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -335,7 +335,7 @@ const VlcuDesignInfo& Vt_concat_unpack__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xdaf1a4df79236b6ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0xdaf1a4df79236b6ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

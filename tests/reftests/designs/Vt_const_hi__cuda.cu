@@ -753,7 +753,7 @@ const VlcuDesignInfo& Vt_const_hi__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x6ddc4b72c7b00336ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x6ddc4b72c7b00336ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -414,7 +414,7 @@ const VlcuDesignInfo& Vt_const_op_red_scope__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x635ba2f5afd8da2bULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x635ba2f5afd8da2bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -431,7 +431,7 @@ const VlcuDesignInfo& Vt_dfg_3679__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x9e5c33396fd0ffd8ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x9e5c33396fd0ffd8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -339,7 +339,7 @@ const VlcuDesignInfo& Vt_dfg_oob_array_access__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x36f4203f4cef8dedULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x36f4203f4cef8dedULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

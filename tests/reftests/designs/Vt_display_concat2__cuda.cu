@@ -326,7 +326,7 @@ const VlcuDesignInfo& Vt_display_concat2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x90ff504e9c4d67c0ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x90ff504e9c4d67c0ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

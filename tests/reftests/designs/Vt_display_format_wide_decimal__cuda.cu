@@ -371,7 +371,7 @@ const VlcuDesignInfo& Vt_display_format_wide_decimal__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x46d49a369c4c1539ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x46d49a369c4c1539ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -452,7 +452,7 @@ const VlcuDesignInfo& Vt_display_recurse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 9, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xc9e185e9a3b65421ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xc9e185e9a3b65421ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

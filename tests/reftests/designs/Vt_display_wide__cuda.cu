@@ -1357,7 +1357,7 @@ const VlcuDesignInfo& Vt_display_wide__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x2b2182f623f93839ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x2b2182f623f93839ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

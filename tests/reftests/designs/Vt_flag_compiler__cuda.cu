@@ -352,7 +352,7 @@ const VlcuDesignInfo& Vt_flag_compiler__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0xbb694391405f399ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0xbb694391405f399ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

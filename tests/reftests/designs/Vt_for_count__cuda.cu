@@ -541,7 +541,7 @@ const VlcuDesignInfo& Vt_for_count__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x884886c1d74fdcbcULL, nullptr, 12, 12, 0};
+        saveOrder, 17, 0, 0x884886c1d74fdcbcULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

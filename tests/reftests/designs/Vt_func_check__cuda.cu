@@ -348,7 +348,7 @@ const VlcuDesignInfo& Vt_func_check__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x88913851fc348066ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x88913851fc348066ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

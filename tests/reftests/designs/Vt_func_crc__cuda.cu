@@ -1913,7 +1913,7 @@ const VlcuDesignInfo& Vt_func_crc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x3a3eb0dd5c930618ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x3a3eb0dd5c930618ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -703,7 +703,7 @@ const VlcuDesignInfo& Vt_func_endian__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0xa10ff6cf8a285155ULL, nullptr, 12, 12, 0};
+        saveOrder, 17, 0, 0xa10ff6cf8a285155ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -337,7 +337,7 @@ const VlcuDesignInfo& Vt_func_first__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x9e8d507ec2512faeULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x9e8d507ec2512faeULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -313,7 +313,7 @@ const VlcuDesignInfo& Vt_func_gen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x6c36f184ee1c41a1ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0x6c36f184ee1c41a1ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

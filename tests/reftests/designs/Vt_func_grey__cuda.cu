@@ -386,7 +386,7 @@ const VlcuDesignInfo& Vt_func_grey__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x97360986d40817c1ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x97360986d40817c1ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -613,7 +613,7 @@ const VlcuDesignInfo& Vt_func_mlog2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x4e23803a339bea9dULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x4e23803a339bea9dULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -920,7 +920,7 @@ const VlcuDesignInfo& Vt_func_noinl__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x5bbfd3b03f86b54ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0x5bbfd3b03f86b54ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -395,7 +395,7 @@ const VlcuDesignInfo& Vt_func_outfirst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x2e5641b0fbf4e3aaULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x2e5641b0fbf4e3aaULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -383,7 +383,7 @@ const VlcuDesignInfo& Vt_func_outp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xfc207a93de05d8fULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0xfc207a93de05d8fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

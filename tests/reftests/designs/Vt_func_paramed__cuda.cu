@@ -524,7 +524,7 @@ const VlcuDesignInfo& Vt_func_paramed__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xfc304cab71eea602ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xfc304cab71eea602ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -447,7 +447,7 @@ const VlcuDesignInfo& Vt_func_plog__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xc51f971ebd0fa08fULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xc51f971ebd0fa08fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -383,7 +383,7 @@ const VlcuDesignInfo& Vt_func_regfirst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x38fe9bb29eb63b7cULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x38fe9bb29eb63b7cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -438,7 +438,7 @@ const VlcuDesignInfo& Vt_func_sel__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xd9788a6d28e3530bULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0xd9788a6d28e3530bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -785,7 +785,7 @@ const VlcuDesignInfo& Vt_func_twocall__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x1a019dfe181fbb9aULL, nullptr, 12, 12, 0};
+        saveOrder, 21, 0, 0x1a019dfe181fbb9aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

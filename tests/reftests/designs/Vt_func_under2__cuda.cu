@@ -303,7 +303,7 @@ const VlcuDesignInfo& Vt_func_under2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xb284b72e9df3828cULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xb284b72e9df3828cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

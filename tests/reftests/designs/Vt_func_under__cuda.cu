@@ -327,7 +327,7 @@ const VlcuDesignInfo& Vt_func_under__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xf3cb9702e6105dfdULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xf3cb9702e6105dfdULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

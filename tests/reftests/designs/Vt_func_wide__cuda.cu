@@ -336,7 +336,7 @@ const VlcuDesignInfo& Vt_func_wide__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xf10bc46824d9a541ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0xf10bc46824d9a541ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

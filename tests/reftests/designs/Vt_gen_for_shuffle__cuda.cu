@@ -443,7 +443,7 @@ const VlcuDesignInfo& Vt_gen_for_shuffle__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x6759cf82bf5477e7ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x6759cf82bf5477e7ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

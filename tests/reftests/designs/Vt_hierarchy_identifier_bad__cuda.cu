@@ -307,7 +307,7 @@ const VlcuDesignInfo& Vt_hierarchy_identifier_bad__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x6235ffca6951a8adULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0x6235ffca6951a8adULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

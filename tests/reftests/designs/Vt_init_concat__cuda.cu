@@ -367,7 +367,7 @@ const VlcuDesignInfo& Vt_init_concat__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0xa178e7f10bed624bULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0xa178e7f10bed624bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

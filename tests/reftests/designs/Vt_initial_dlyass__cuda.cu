@@ -373,7 +373,7 @@ const VlcuDesignInfo& Vt_initial_dlyass__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x81b5e694b99147f5ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x81b5e694b99147f5ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

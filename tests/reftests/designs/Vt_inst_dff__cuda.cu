@@ -429,7 +429,7 @@ const VlcuDesignInfo& Vt_inst_dff__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xf5803a63c3c8f249ULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xf5803a63c3c8f249ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

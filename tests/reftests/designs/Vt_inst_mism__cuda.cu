@@ -304,7 +304,7 @@ const VlcuDesignInfo& Vt_inst_mism__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 7, 0, 0x326ac06d76909959ULL, nullptr, 12, 12, 0};
+        saveOrder, 7, 0, 0x326ac06d76909959ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

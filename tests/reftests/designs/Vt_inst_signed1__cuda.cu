@@ -338,7 +338,7 @@ const VlcuDesignInfo& Vt_inst_signed1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xba8bc5c7edd22e83ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0xba8bc5c7edd22e83ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -482,7 +482,7 @@ const VlcuDesignInfo& Vt_inst_tree__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x69e049e1d04eee46ULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x69e049e1d04eee46ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

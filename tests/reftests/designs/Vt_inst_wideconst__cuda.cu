@@ -451,7 +451,7 @@ const VlcuDesignInfo& Vt_inst_wideconst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xb2cf962fb28103abULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xb2cf962fb28103abULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

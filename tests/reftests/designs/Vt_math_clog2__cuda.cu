@@ -527,7 +527,7 @@ const VlcuDesignInfo& Vt_math_clog2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x9fa0f9eead67c8fbULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x9fa0f9eead67c8fbULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1872,7 +1872,7 @@ const VlcuDesignInfo& Vt_math_cmp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 8, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 55, 0, 0x4abfb8a786cb87a9ULL, nullptr, 12, 12, 0};
+        saveOrder, 55, 0, 0x4abfb8a786cb87a9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -389,7 +389,7 @@ const VlcuDesignInfo& Vt_math_concat0__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xfa2edd3b354599ffULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xfa2edd3b354599ffULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

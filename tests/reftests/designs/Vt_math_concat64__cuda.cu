@@ -1346,7 +1346,7 @@ const VlcuDesignInfo& Vt_math_concat64__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x9246ce20bf52d8bdULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x9246ce20bf52d8bdULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1960,7 +1960,7 @@ const VlcuDesignInfo& Vt_math_concat__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xac53cb927fecff3bULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xac53cb927fecff3bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -490,7 +490,7 @@ const VlcuDesignInfo& Vt_math_cond_clean__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x7453f98be1924a2aULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x7453f98be1924a2aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -2527,7 +2527,7 @@ const VlcuDesignInfo& Vt_math_cond_huge__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0xd0a17948079424eULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0xd0a17948079424eULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -287,7 +287,7 @@ const VlcuDesignInfo& Vt_math_div0__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x97f7bbf8a8d23cd8ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x97f7bbf8a8d23cd8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -702,7 +702,7 @@ const VlcuDesignInfo& Vt_math_div__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x841edae0554c77afULL, nullptr, 12, 12, 0};
+        saveOrder, 19, 0, 0x841edae0554c77afULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -488,7 +488,7 @@ const VlcuDesignInfo& Vt_math_eq__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x974431ac9b83ca2dULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x974431ac9b83ca2dULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

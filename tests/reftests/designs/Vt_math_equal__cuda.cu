@@ -428,7 +428,7 @@ const VlcuDesignInfo& Vt_math_equal__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x310eafb1c1d8873aULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x310eafb1c1d8873aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

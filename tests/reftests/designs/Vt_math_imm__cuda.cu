@@ -967,7 +967,7 @@ const VlcuDesignInfo& Vt_math_imm__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xae60ec923deb3032ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xae60ec923deb3032ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

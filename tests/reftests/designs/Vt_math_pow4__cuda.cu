@@ -434,7 +434,7 @@ const VlcuDesignInfo& Vt_math_pow4__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xe71ef57e3bf894a0ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xe71ef57e3bf894a0ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

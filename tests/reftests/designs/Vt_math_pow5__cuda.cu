@@ -514,7 +514,7 @@ const VlcuDesignInfo& Vt_math_pow5__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x9ea009a89d58176aULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x9ea009a89d58176aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -413,7 +413,7 @@ const VlcuDesignInfo& Vt_math_pow6__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x9c4ac0d2340936bULL, nullptr, 12, 12, 0};
+        saveOrder, 21, 0, 0x9c4ac0d2340936bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

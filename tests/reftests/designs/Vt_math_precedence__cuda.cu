@@ -968,7 +968,7 @@ const VlcuDesignInfo& Vt_math_precedence__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x1ae6ddec8e4e10b3ULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x1ae6ddec8e4e10b3ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

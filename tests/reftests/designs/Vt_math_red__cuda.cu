@@ -554,7 +554,7 @@ const VlcuDesignInfo& Vt_math_red__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 16, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xee3bb61fd46d65f8ULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xee3bb61fd46d65f8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

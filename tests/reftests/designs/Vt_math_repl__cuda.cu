@@ -1054,7 +1054,7 @@ const VlcuDesignInfo& Vt_math_repl__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0xc6a204c5b5e66a70ULL, nullptr, 12, 12, 0};
+        saveOrder, 22, 0, 0xc6a204c5b5e66a70ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -547,7 +547,7 @@ const VlcuDesignInfo& Vt_math_reverse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xa21144432cc87dceULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xa21144432cc87dceULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -458,7 +458,7 @@ const VlcuDesignInfo& Vt_math_shift_sel__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xa8d0c3fd06007d19ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xa8d0c3fd06007d19ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -442,7 +442,7 @@ const VlcuDesignInfo& Vt_math_shiftrs__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xbcfee41cf30f4549ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xbcfee41cf30f4549ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -596,7 +596,7 @@ const VlcuDesignInfo& Vt_math_signed2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xbccfa4fb21748de3ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0xbccfa4fb21748de3ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -294,7 +294,7 @@ const VlcuDesignInfo& Vt_math_signed7__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 7, 0, 0x326ac06d76909959ULL, nullptr, 12, 12, 0};
+        saveOrder, 7, 0, 0x326ac06d76909959ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1846,7 +1846,7 @@ const VlcuDesignInfo& Vt_math_signed__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 77, 0, 0x99599e39f227d7e3ULL, nullptr, 12, 12, 0};
+        saveOrder, 77, 0, 0x99599e39f227d7e3ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -321,7 +321,7 @@ const VlcuDesignInfo& Vt_math_signed_calc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x599aa2a14f556933ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x599aa2a14f556933ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

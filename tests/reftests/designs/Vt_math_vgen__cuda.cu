@@ -737,7 +737,7 @@ const VlcuDesignInfo& Vt_math_vgen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 33, 0, 0xf0c2b11053185e24ULL, nullptr, 12, 12, 0};
+        saveOrder, 33, 0, 0xf0c2b11053185e24ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -323,7 +323,7 @@ const VlcuDesignInfo& Vt_mem_cond__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0x91a10df033baf09cULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0x91a10df033baf09cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

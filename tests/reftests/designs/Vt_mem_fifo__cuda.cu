@@ -428,7 +428,7 @@ const VlcuDesignInfo& Vt_mem_fifo__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x364703794843c5b9ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x364703794843c5b9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

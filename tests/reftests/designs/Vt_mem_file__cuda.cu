@@ -681,7 +681,7 @@ const VlcuDesignInfo& Vt_mem_file__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 25, 0, 0xf339c4d3e4fdfc3dULL, nullptr, 12, 12, 0};
+        saveOrder, 25, 0, 0xf339c4d3e4fdfc3dULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

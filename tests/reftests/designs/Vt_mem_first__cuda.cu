@@ -919,7 +919,7 @@ const VlcuDesignInfo& Vt_mem_first__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x7425f85357fa3c58ULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x7425f85357fa3c58ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -493,7 +493,7 @@ const VlcuDesignInfo& Vt_mem_iforder__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x8b836bed0f837145ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x8b836bed0f837145ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -858,7 +858,7 @@ const VlcuDesignInfo& Vt_mem_multidim__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x87da0bcdd9ba2f6dULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x87da0bcdd9ba2f6dULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

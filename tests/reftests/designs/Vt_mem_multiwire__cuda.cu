@@ -516,7 +516,7 @@ const VlcuDesignInfo& Vt_mem_multiwire__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x6978f02d6371a044ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0x6978f02d6371a044ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -411,7 +411,7 @@ const VlcuDesignInfo& Vt_mem_shift__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0xe0282792d4b78d14ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0xe0282792d4b78d14ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -927,7 +927,7 @@ const VlcuDesignInfo& Vt_opt_const_red__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 50, 0, 0xdbd1eb0e99358474ULL, nullptr, 12, 12, 0};
+        saveOrder, 50, 0, 0xdbd1eb0e99358474ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -404,7 +404,7 @@ const VlcuDesignInfo& Vt_opt_if_array__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x6d500e206a2acbeULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x6d500e206a2acbeULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

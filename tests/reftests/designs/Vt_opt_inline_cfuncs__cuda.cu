@@ -557,7 +557,7 @@ const VlcuDesignInfo& Vt_opt_inline_cfuncs__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x184a4089aa3972fbULL, nullptr, 12, 12, 0};
+        saveOrder, 29, 0, 0x184a4089aa3972fbULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

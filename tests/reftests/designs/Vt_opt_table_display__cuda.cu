@@ -343,7 +343,7 @@ const VlcuDesignInfo& Vt_opt_table_display__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x9693bc1fb797c01fULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x9693bc1fb797c01fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

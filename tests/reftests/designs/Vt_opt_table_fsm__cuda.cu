@@ -598,7 +598,7 @@ const VlcuDesignInfo& Vt_opt_table_fsm__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0xd876d94756cb84f5ULL, nullptr, 12, 12, 0};
+        saveOrder, 23, 0, 0xd876d94756cb84f5ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

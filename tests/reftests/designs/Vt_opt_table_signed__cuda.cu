@@ -320,7 +320,7 @@ const VlcuDesignInfo& Vt_opt_table_signed__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x21e5bc65edeafb78ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0x21e5bc65edeafb78ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -426,7 +426,7 @@ const VlcuDesignInfo& Vt_opt_table_sparse__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xa4c5fb627309d674ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xa4c5fb627309d674ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -530,7 +530,7 @@ const VlcuDesignInfo& Vt_order_2d__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x37f049685b97fd10ULL, nullptr, 12, 12, 0};
+        saveOrder, 17, 0, 0x37f049685b97fd10ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

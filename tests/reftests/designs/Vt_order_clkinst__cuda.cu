@@ -703,7 +703,7 @@ const VlcuDesignInfo& Vt_order_clkinst__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 28, 0, 0x92fa048cdc30a64aULL, nullptr, 12, 12, 0};
+        saveOrder, 28, 0, 0x92fa048cdc30a64aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -576,7 +576,7 @@ const VlcuDesignInfo& Vt_order_comboclkloop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0x174f728ffc59c391ULL, nullptr, 12, 12, 0};
+        saveOrder, 22, 0, 0x174f728ffc59c391ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -554,7 +554,7 @@ const VlcuDesignInfo& Vt_order_comboloop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x79a0258f514bcf8cULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x79a0258f514bcf8cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -342,7 +342,7 @@ const VlcuDesignInfo& Vt_order_loop_bad__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x4c7d4bd8fc9a2b2bULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x4c7d4bd8fc9a2b2bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -434,7 +434,7 @@ const VlcuDesignInfo& Vt_order_multialways__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x97012b21b72c4103ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x97012b21b72c4103ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

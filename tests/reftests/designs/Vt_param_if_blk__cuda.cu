@@ -571,7 +571,7 @@ const VlcuDesignInfo& Vt_param_if_blk__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0x7b289fbf142305f1ULL, nullptr, 12, 12, 0};
+        saveOrder, 22, 0, 0x7b289fbf142305f1ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

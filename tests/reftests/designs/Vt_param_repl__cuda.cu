@@ -353,7 +353,7 @@ const VlcuDesignInfo& Vt_param_repl__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0xf6fb1e729971fd5ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0xf6fb1e729971fd5ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -315,7 +315,7 @@ const VlcuDesignInfo& Vt_param_seg__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0x35667d5a421817e4ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0x35667d5a421817e4ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -148,7 +148,7 @@ const VlcuDesignInfo& Vt_param_shift__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0xeafd0b7a228757b3ULL, nullptr, 12, 12, 0};
+        saveOrder, 1, 0, 0xeafd0b7a228757b3ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -308,7 +308,7 @@ const VlcuDesignInfo& Vt_rnd__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xdb94602ad3562a17ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xdb94602ad3562a17ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

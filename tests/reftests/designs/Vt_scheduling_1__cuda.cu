@@ -379,7 +379,7 @@ const VlcuDesignInfo& Vt_scheduling_1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x7c41545dfaa25d4cULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x7c41545dfaa25d4cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

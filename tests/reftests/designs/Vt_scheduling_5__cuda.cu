@@ -403,7 +403,7 @@ const VlcuDesignInfo& Vt_scheduling_5__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xc58b200cdefccbe9ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xc58b200cdefccbe9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

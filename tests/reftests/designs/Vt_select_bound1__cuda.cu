@@ -422,7 +422,7 @@ const VlcuDesignInfo& Vt_select_bound1__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x6531fddcd83132adULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0x6531fddcd83132adULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

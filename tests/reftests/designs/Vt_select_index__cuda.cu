@@ -376,7 +376,7 @@ const VlcuDesignInfo& Vt_select_index__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x10ae18172797f99fULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x10ae18172797f99fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -755,7 +755,7 @@ const VlcuDesignInfo& Vt_select_lhs_oob2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0x103a4b7b474dd492ULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0x103a4b7b474dd492ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

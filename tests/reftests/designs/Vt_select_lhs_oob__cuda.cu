@@ -2763,7 +2763,7 @@ const VlcuDesignInfo& Vt_select_lhs_oob__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xf9c805d031881fc2ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xf9c805d031881fc2ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

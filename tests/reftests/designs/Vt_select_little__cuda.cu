@@ -658,7 +658,7 @@ const VlcuDesignInfo& Vt_select_little__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 20, 0, 0x13a78d95ecf6d082ULL, nullptr, 12, 12, 0};
+        saveOrder, 20, 0, 0x13a78d95ecf6d082ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

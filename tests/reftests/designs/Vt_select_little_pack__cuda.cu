@@ -165,7 +165,7 @@ const VlcuDesignInfo& Vt_select_little_pack__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 1, 0, 0x50ab0aeba021a3b2ULL, nullptr, 12, 12, 0};
+        saveOrder, 1, 0, 0x50ab0aeba021a3b2ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -921,7 +921,7 @@ const VlcuDesignInfo& Vt_select_loop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0xafe40ccf7198d8e7ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0xafe40ccf7198d8e7ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

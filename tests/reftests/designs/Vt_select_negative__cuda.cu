@@ -577,7 +577,7 @@ const VlcuDesignInfo& Vt_select_negative__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xf01419856b7f8631ULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xf01419856b7f8631ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -857,7 +857,7 @@ const VlcuDesignInfo& Vt_select_plus__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0xa20cfb4587de79c2ULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0xa20cfb4587de79c2ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -502,7 +502,7 @@ const VlcuDesignInfo& Vt_select_plus_mul_pow2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0x57556bac1949ead8ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0x57556bac1949ead8ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

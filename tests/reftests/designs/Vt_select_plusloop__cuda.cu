@@ -500,7 +500,7 @@ const VlcuDesignInfo& Vt_select_plusloop__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 13, 0, 0xcd8b4f7314e80764ULL, nullptr, 12, 12, 0};
+        saveOrder, 13, 0, 0xcd8b4f7314e80764ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -405,7 +405,7 @@ const VlcuDesignInfo& Vt_select_runtime_range__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xab5ae6ef0e973b13ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xab5ae6ef0e973b13ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -403,7 +403,7 @@ const VlcuDesignInfo& Vt_select_set__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 10, 0, 0xe562a401f5f807ULL, nullptr, 12, 12, 0};
+        saveOrder, 10, 0, 0xe562a401f5f807ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -839,7 +839,7 @@ const VlcuDesignInfo& Vt_trace_ascendingrange__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0x8d500fcbce8c210bULL, nullptr, 12, 12, 0};
+        saveOrder, 29, 0, 0x8d500fcbce8c210bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -313,7 +313,7 @@ const VlcuDesignInfo& Vt_trace_empty__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xe9c57d881c75e2e9ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xe9c57d881c75e2e9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -312,7 +312,7 @@ const VlcuDesignInfo& Vt_trace_scope_no_inline__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x1d22598f10ca98a4ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0x1d22598f10ca98a4ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

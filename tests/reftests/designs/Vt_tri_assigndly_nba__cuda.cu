@@ -493,7 +493,7 @@ const VlcuDesignInfo& Vt_tri_assigndly_nba__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x3983b5fae076a984ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x3983b5fae076a984ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -336,7 +336,7 @@ const VlcuDesignInfo& Vt_tri_eqcase_input__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 9, 0, 0xf542768e5835db55ULL, nullptr, 12, 12, 0};
+        saveOrder, 9, 0, 0xf542768e5835db55ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

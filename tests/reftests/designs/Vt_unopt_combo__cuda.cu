@@ -583,7 +583,7 @@ const VlcuDesignInfo& Vt_unopt_combo__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 16, 0, 0x3eac535f553cf573ULL, nullptr, 12, 12, 0};
+        saveOrder, 16, 0, 0x3eac535f553cf573ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -574,7 +574,7 @@ const VlcuDesignInfo& Vt_unoptflat_simple_2__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0x6ba00a7932f917aeULL, nullptr, 12, 12, 0};
+        saveOrder, 19, 0, 0x6ba00a7932f917aeULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -669,7 +669,7 @@ const VlcuDesignInfo& Vt_var_assign_landr__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 2, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 15, 0, 0x34d6550d47b2ff85ULL, nullptr, 12, 12, 0};
+        saveOrder, 15, 0, 0x34d6550d47b2ff85ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

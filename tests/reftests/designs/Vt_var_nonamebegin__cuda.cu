@@ -162,7 +162,7 @@ const VlcuDesignInfo& Vt_var_nonamebegin__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 8, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 2, 0, 0x13e4b2e8c15b0b77ULL, nullptr, 12, 12, 0};
+        saveOrder, 2, 0, 0x13e4b2e8c15b0b77ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

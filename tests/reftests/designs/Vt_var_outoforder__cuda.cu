@@ -417,7 +417,7 @@ const VlcuDesignInfo& Vt_var_outoforder__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0x722253776c226571ULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0x722253776c226571ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

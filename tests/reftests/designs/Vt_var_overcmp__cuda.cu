@@ -600,7 +600,7 @@ const VlcuDesignInfo& Vt_var_overcmp__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 25, 0, 0x8f41e26529ca65c9ULL, nullptr, 12, 12, 0};
+        saveOrder, 25, 0, 0x8f41e26529ca65c9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

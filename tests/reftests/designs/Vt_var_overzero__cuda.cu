@@ -592,7 +592,7 @@ const VlcuDesignInfo& Vt_var_overzero__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 23, 0, 0xc3119a88b7726f52ULL, nullptr, 12, 12, 0};
+        saveOrder, 23, 0, 0xc3119a88b7726f52ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -310,7 +310,7 @@ const VlcuDesignInfo& Vt_var_set_link__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0x4d0056a6c82523aULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0x4d0056a6c82523aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

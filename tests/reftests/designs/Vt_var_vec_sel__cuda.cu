@@ -369,7 +369,7 @@ const VlcuDesignInfo& Vt_var_vec_sel__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x8fcc6a5925fd4841ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x8fcc6a5925fd4841ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

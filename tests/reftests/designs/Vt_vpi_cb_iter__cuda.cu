@@ -315,7 +315,7 @@ const VlcuDesignInfo& Vt_vpi_cb_iter__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 1, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 8, 0, 0xfe11c2f8b7741ae1ULL, nullptr, 12, 12, 0};
+        saveOrder, 8, 0, 0xfe11c2f8b7741ae1ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -412,3 +412,29 @@ def test_config1_one_million_cycles_vcd_bit_exact(abi, tmp_path):
     ours, ref = _sha_file(our_path), _sha_file(ref_path)
     assert ref[1] > 50_000_000  # a real waveform: tens of MB of value changes
     assert ours == ref
+
+
+def test_unmodified_sim_main_cpp_on_the_vtop_shim(abi, tmp_path):
+    """examples/make_tracing_c/sim_main.cpp, UNMODIFIED, compiled against a three-line
+    Vtop.h over include/verilated_cuda_vtop.h -- the generated model class with its public port
+    members (V3EmitCModel.cpp:108-117), one instance on the GPU.  The program pokes top->clk,
+    top->in_quad ..., calls top->eval(), polls contextp->gotFinish(), prints the design's
+    $display text and the example's own trace lines: the console must be the genuine model's."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cxx", "sim_main_vtop")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/sim_main_vtop is built where /root/reference is")
+    res = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    want = O.mtc_run(1, 1000, rand_reset=2, stop_on_finish=True)
+    assert "*-* All Finished *-*" in res.stdout
+    for line in want.console.splitlines():  # the design's $display / $write text
+        assert line in res.stdout, line
+    # the testbench's own per-eval report of the ports (sim_main.cpp:109-112) stops where the
+    # genuine run does ($finish at time 17) and shows the genuine model's outputs
+    evals = [ln for ln in res.stdout.splitlines() if ln.startswith("[") and "clk=" in ln]
+    assert len(evals) == 17 and evals[-1].startswith("[17] ")
+    obs = O.mtc_run(1, 17, rand_reset=2, obs_evals=17).obs[:, :, 0]
+    for e, line in enumerate(evals):
+        quad = int(obs[e, 1]) | (int(obs[e, 2]) << 32)
+        assert line.endswith(f"-> oquad={quad:x} owide={int(obs[e, 5]):x}_{int(obs[e, 4]):08x}_{int(obs[e, 3]):08x}"), (e, line)

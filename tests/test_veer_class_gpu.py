@@ -1,6 +1,8 @@
 """The VeeR-class design (BASELINE configs 3-5 class: ~37,000 bits of scalar flops in 34 scopes of
 9 module classes, non-inlined hierarchy, tiled model image in HBM) against the genuine Verilated
 C++ model of the same source: every output port after every eval."""
+import os
+
 import numpy as np
 import pytest
 
@@ -126,3 +128,30 @@ def test_config3_size_sampled_against_the_oracle():
     for i in list(range(0, n, 512)) + list(range(n - 16, n)):
         _, want = O.generic_fuzz(DESIGN, 1, evals, inst_base=i, seed=1, rand_reset=2, tb_seed=3, **VC_O)
         assert sigs[i] == want[0], i
+
+
+VEERCOV_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "veercov", "libvlcu_veercov.so")
+
+
+def test_coverage_campaign_merged_file_equals_the_reference_writer(tmp_path):
+    """BASELINE config 5 on one GPU: the --coverage build of the VeeR-class design (line + toggle
+    points of every scope, ~80,000 counters; 16-entry branch target buffers, see oracle/Makefile),
+    a fuzz campaign, the counters -- one per point per TILE, the warp adds up its lanes -- reduced
+    on the device, and ONE merged coverage.dat: byte for byte the file the reference's
+    VerilatedCov writes for the same instances."""
+    if not os.path.exists(VEERCOV_LIB):
+        pytest.skip("tests/veercov/libvlcu_veercov.so not built")
+    abi.load_design_library(VEERCOV_LIB)
+    n, evals = 40, 260
+    ref_path, gpu_path = str(tmp_path / "ref.dat"), str(tmp_path / "gpu.dat")
+    want_sigs = O.generic_cov("veer_class_cov", n, evals, ref_path, inst_base=9, seed=3, rand_reset=2, tb_seed=12, **VC_O)
+    with abi.Model("veer_class_cov", n, inst_base=9, seed=3, rand_reset=2) as m:
+        assert abi.lib.vlcu_tile(m.h) == 32 and m.coverage_bins() > 50000
+        m.run("fuzz", evals, tb_seed=12, **VC)
+        assert (m.signatures() == want_sigs).all()
+        sums = m.coverage_reduce()
+        m.coverage_write(sums, gpu_path)
+        assert (sums > 0).sum() > 10000
+    ours, ref = open(gpu_path).read(), open(ref_path).read()
+    assert ref.count("\n") > 5000 and "v_toggle" in ref and "v_line" in ref
+    assert ours == ref

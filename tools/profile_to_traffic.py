@@ -16,6 +16,8 @@ PROFILES = {
     "cov_campaign": ("r02_ncu_full_cov_campaign_vlcu_k_run.csv", 16384, 1024, "issue"),
     "veer_class": ("r02_ncu_full_veer_class_vlcu_k_run.csv", 16384, 256, "hbm"),
     "veer_class_64k": ("r02_ncu_full_veer_class_64k_vlcu_k_run.csv", 65536, 128, "hbm"),
+    "cov_campaign_veer": ("r02_ncu_full_cov_campaign_veer_vlcu_k_run.csv", 16384, 64, "hbm"),
+    "x_initial_il": ("r02_ncu_full_x_initial_il_vlcu_k_run.csv", 16384, 4096, "issue"),
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 

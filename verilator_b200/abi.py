@@ -143,6 +143,12 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.argtypes = _args
 
 
+def load_design_library(path):
+    """Load a library of further emitted designs (it registers them with the runtime at load
+    time): tests/reftests/libvlcu_reftests.so, tests/veercov/libvlcu_veercov.so ..."""
+    return ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+
+
 class VlcuError(RuntimeError):
     pass
 

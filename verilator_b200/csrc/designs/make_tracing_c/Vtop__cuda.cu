@@ -1133,7 +1133,7 @@ const VlcuDesignInfo& Vtop__cuda::info() {
         t.points.data(), static_cast<uint32_t>(t.points.size()), 543, T::OFF___Vcoverage,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9,
-        saveOrder, 39, VLCU_SAVE_ACTIVITY, 0x63e469006938c01ULL, nullptr, 12, 12, 0};
+        saveOrder, 39, VLCU_SAVE_ACTIVITY, 0x63e469006938c01ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -740,7 +740,7 @@ const VlcuDesignInfo& Vtop_nocov__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 4, plusargs, 1,
         traceDecls, 25, T::kTraceWords, traceOrder, 9,
-        saveOrder, 26, VLCU_SAVE_ACTIVITY, 0xa090add8b4f5237eULL, nullptr, 12, 12, 0};
+        saveOrder, 26, VLCU_SAVE_ACTIVITY, 0xa090add8b4f5237eULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -4130,7 +4130,7 @@ const VlcuDesignInfo& Vrv32_cov__cuda::info() {
         t.points.data(), static_cast<uint32_t>(t.points.size()), 1664, T::OFF___Vcoverage,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12, 0};
+        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1431,7 +1431,7 @@ const VlcuDesignInfo& Vrv32_il__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 41, 0, 0x2f9cd36244ca914aULL, nullptr, 12, 12, 0};
+        saveOrder, 41, 0, 0x2f9cd36244ca914aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -2247,7 +2247,7 @@ const VlcuDesignInfo& Vrv32_soc__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         traceDecls, 105, T::kTraceWords, traceOrder, 88,
-        saveOrder, 51, VLCU_SAVE_ACTIVITY, 0xe66f28a6807d2675ULL, nullptr, 12, 12, 0};
+        saveOrder, 51, VLCU_SAVE_ACTIVITY, 0xe66f28a6807d2675ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

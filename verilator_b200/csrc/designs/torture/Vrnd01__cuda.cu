@@ -1867,7 +1867,7 @@ const VlcuDesignInfo& Vrnd01__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 43, 0, 0x72d6802b2c7e727aULL, nullptr, 12, 12, 0};
+        saveOrder, 43, 0, 0x72d6802b2c7e727aULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

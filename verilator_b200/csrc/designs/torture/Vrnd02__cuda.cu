@@ -1316,7 +1316,7 @@ const VlcuDesignInfo& Vrnd02__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 42, 0, 0x11dcf6eb895aecc9ULL, nullptr, 12, 12, 0};
+        saveOrder, 42, 0, 0x11dcf6eb895aecc9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1647,7 +1647,7 @@ const VlcuDesignInfo& Vrnd03__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 46, 0, 0x16d69c6230dce010ULL, nullptr, 12, 12, 0};
+        saveOrder, 46, 0, 0x16d69c6230dce010ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1507,7 +1507,7 @@ const VlcuDesignInfo& Vrnd04__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 44, 0, 0xd189c098c351952cULL, nullptr, 12, 12, 0};
+        saveOrder, 44, 0, 0xd189c098c351952cULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

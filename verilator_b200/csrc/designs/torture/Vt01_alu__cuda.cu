@@ -1098,7 +1098,7 @@ const VlcuDesignInfo& Vt01_alu__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 35, 0, 0x7c8d40b046c830b9ULL, nullptr, 12, 12, 0};
+        saveOrder, 35, 0, 0x7c8d40b046c830b9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -719,7 +719,7 @@ const VlcuDesignInfo& Vt02_fsm__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 26, 0, 0x3b73d8ee909aca3fULL, nullptr, 12, 12, 0};
+        saveOrder, 26, 0, 0x3b73d8ee909aca3fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -772,7 +772,7 @@ const VlcuDesignInfo& Vt03_mem__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 29, 0, 0xdd8f4b7deb221c6fULL, nullptr, 12, 12, 0};
+        saveOrder, 29, 0, 0xdd8f4b7deb221c6fULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

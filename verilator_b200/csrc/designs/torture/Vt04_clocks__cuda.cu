@@ -521,7 +521,7 @@ const VlcuDesignInfo& Vt04_clocks__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 21, 0, 0x9da0e1ec1111a29ULL, nullptr, 12, 12, 0};
+        saveOrder, 21, 0, 0x9da0e1ec1111a29ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -752,7 +752,7 @@ const VlcuDesignInfo& Vt05_wide__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 26, 0, 0x553002b1b73e24f0ULL, nullptr, 12, 12, 0};
+        saveOrder, 26, 0, 0x553002b1b73e24f0ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -711,7 +711,7 @@ const VlcuDesignInfo& Vt06_loops__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x63e44c3fb0276468ULL, nullptr, 12, 12, 0};
+        saveOrder, 17, 0, 0x63e44c3fb0276468ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -475,7 +475,7 @@ const VlcuDesignInfo& Vt07_dyn__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 19, 0, 0xd80e36e69bbb5d54ULL, nullptr, 12, 12, 0};
+        saveOrder, 19, 0, 0xd80e36e69bbb5d54ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -668,7 +668,7 @@ const VlcuDesignInfo& Vt08_widemem__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 22, 0, 0xc8b7f9412b1760ddULL, nullptr, 12, 12, 0};
+        saveOrder, 22, 0, 0xc8b7f9412b1760ddULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

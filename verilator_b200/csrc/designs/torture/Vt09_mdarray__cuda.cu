@@ -929,7 +929,7 @@ const VlcuDesignInfo& Vt09_mdarray__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 37, 0, 0xeae58fda201bc3b0ULL, nullptr, 12, 12, 0};
+        saveOrder, 37, 0, 0xeae58fda201bc3b0ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -356,7 +356,7 @@ const VlcuDesignInfo& Vt10_bigstate_im__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 12, 0, 0xd2ccd3d2441ea87bULL, nullptr, 12, 12, 0};
+        saveOrder, 12, 0, 0xd2ccd3d2441ea87bULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

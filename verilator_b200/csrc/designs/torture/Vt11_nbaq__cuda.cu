@@ -429,7 +429,7 @@ const VlcuDesignInfo& Vt11_nbaq__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 14, 0, 0x32e76cb27619a710ULL, nullptr, 12, 12, 0};
+        saveOrder, 14, 0, 0x32e76cb27619a710ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -617,7 +617,7 @@ const VlcuDesignInfo& Vt12_sys__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 3, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 24, 0, 0xf1ec08fd9ee39637ULL, nullptr, 12, 12, 0};
+        saveOrder, 24, 0, 0xf1ec08fd9ee39637ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -969,7 +969,7 @@ const VlcuDesignInfo& Vt13_mix__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 43, 0, 0xd18a6f46a954cc30ULL, nullptr, 12, 12, 0};
+        saveOrder, 43, 0, 0xd18a6f46a954cc30ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

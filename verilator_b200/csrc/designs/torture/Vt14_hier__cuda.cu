@@ -513,7 +513,7 @@ const VlcuDesignInfo& Vt14_hier__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 18, 0, 0xbd05e079dc4e69b9ULL, nullptr, 12, 12, 0};
+        saveOrder, 18, 0, 0xbd05e079dc4e69b9ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -376,7 +376,7 @@ const VlcuDesignInfo& Vt15_func__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 11, 0, 0x8d6472eb47ac7118ULL, nullptr, 12, 12, 0};
+        saveOrder, 11, 0, 0x8d6472eb47ac7118ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

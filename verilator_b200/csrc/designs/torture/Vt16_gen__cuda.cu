@@ -451,7 +451,7 @@ const VlcuDesignInfo& Vt16_gen__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 17, 0, 0x4455e9470139a5e6ULL, nullptr, 12, 12, 0};
+        saveOrder, 17, 0, 0x4455e9470139a5e6ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

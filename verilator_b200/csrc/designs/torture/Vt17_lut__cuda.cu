@@ -644,7 +644,7 @@ const VlcuDesignInfo& Vt17_lut__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 25, 0, 0x494ebbadaed0dae4ULL, nullptr, 12, 12, 0};
+        saveOrder, 25, 0, 0x494ebbadaed0dae4ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -1127,7 +1127,7 @@ const VlcuDesignInfo& Vwide_bus__cuda::info() {
         nullptr, 0, 0, 0,
         messages, 0, plusargs, 0,
         traceDecls, 45, T::kTraceWords, traceOrder, 24,
-        saveOrder, 32, VLCU_SAVE_ACTIVITY, 0x2819d23c62a96db6ULL, nullptr, 12, 12, 0};
+        saveOrder, 32, VLCU_SAVE_ACTIVITY, 0x2819d23c62a96db6ULL, nullptr, 12, 12, 0, nullptr, 0};
     return s;
 }
 

@@ -139,6 +139,7 @@ struct vlcu_model final {
     uint64_t* dSigs = nullptr;
     uint64_t* dEvalsDone = nullptr;
     uint64_t* dCovSums = nullptr;
+    uint32_t* dCovBinOffset = nullptr;  // tiled designs: byte offset in a tile of every counter's lane 0
     VlcuModelDev dev{};
     uint64_t launches = 0;
     uint64_t evalIndex = 0;  // evals issued so far (VlcuRunDev::evalBase)
@@ -339,6 +340,20 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const uint32_t* __restrict__
         }
         __syncthreads();
     }
+}
+
+// The same for a tiled design: every tile keeps one uint64 counter per bin for its instances
+// together (VlcuTileCov), at state + tile * tileBytes + binOffset[bin]: sum them over the tiles.
+__global__ void __launch_bounds__(256) k_cov_reduce_tiled(const uint8_t* __restrict__ state, uint64_t tiles,
+                                                          uint64_t tileBytes,
+                                                          const uint32_t* __restrict__ binOffset, uint32_t bins,
+                                                          uint64_t* __restrict__ out) {
+    const uint64_t bin = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (bin >= bins) return;
+    const uint8_t* const basep = state + binOffset[bin];
+    uint64_t acc = 0;
+    for (uint64_t t = 0; t < tiles; ++t) acc += *reinterpret_cast<const unsigned long long*>(basep + t * tileBytes);
+    out[bin] = acc;
 }
 
 unsigned blocksFor(uint64_t work, unsigned threads) {
@@ -823,6 +838,7 @@ void vlcu_destroy(vlcu_model_t* h) {
     cudaFree(h->dSigs);
     cudaFree(h->dEvalsDone);
     cudaFree(h->dCovSums);
+    cudaFree(h->dCovBinOffset);
     cudaFree(h->dStage);
     cudaFree(h->dFlush);
     for (vlcu_model::RunBuf& b : h->runBuf) cudaFree(b.p);
@@ -1602,10 +1618,26 @@ int vlcu_coverage_reduce(vlcu_model_t* h, uint64_t* out) {
     const uint32_t bins = h->infop->coverBins;
     if (!bins) return fail(VLCU_E_STATE, "design was not built with coverage");
     DeviceGuard guard{h->device};
-    const uint32_t* const covp = reinterpret_cast<const uint32_t*>(
-        h->dState + static_cast<uint64_t>(h->infop->coverageSoaOffset) * h->npad);
-    k_cov_reduce<<<bins < 148 * 8 ? bins : 148 * 8, 256, 0, h->stream>>>(covp, h->n, h->npad, bins,
-                                                                       h->dCovSums);
+    if (h->infop->tile) {
+        if (!h->dCovBinOffset) {
+            std::vector<uint32_t> offsets;
+            for (uint32_t s = 0; s < h->infop->nCoverScopes; ++s) {
+                const VlcuCoverScope& cs = h->infop->coverScopes[s];
+                for (uint32_t b = 0; b < cs.bins; ++b) offsets.push_back(cs.tileOffset + b * 8U);
+            }
+            if (offsets.size() != bins) return fail(VLCU_E_STATE, "coverage scope table does not add up to coverBins");
+            CUDA_TRY(cudaMalloc(&h->dCovBinOffset, sizeof(uint32_t) * bins));
+            CUDA_TRY(cudaMemcpy(h->dCovBinOffset, offsets.data(), sizeof(uint32_t) * bins, cudaMemcpyHostToDevice));
+        }
+        k_cov_reduce_tiled<<<blocksFor(bins, 256), 256, 0, h->stream>>>(
+            h->dState, h->npad / h->infop->tile, static_cast<uint64_t>(h->infop->stateBytes) * h->infop->tile,
+            h->dCovBinOffset, bins, h->dCovSums);
+    } else {
+        const uint32_t* const covp = reinterpret_cast<const uint32_t*>(
+            h->dState + static_cast<uint64_t>(h->infop->coverageSoaOffset) * h->npad);
+        k_cov_reduce<<<bins < 148 * 8 ? bins : 148 * 8, 256, 0, h->stream>>>(covp, h->n, h->npad, bins,
+                                                                           h->dCovSums);
+    }
     ++h->launches;
     CUDA_TRY(cudaGetLastError());
     if (h->comm) {  // sum the per-shard totals over NVLink
