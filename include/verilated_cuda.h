@@ -173,8 +173,10 @@ VLCU_HD int vlcu_ctz64(uint64_t x) {
 // function there, VLCU_COV_NOINLINE defined by the emitted model, or nvcc needs half an hour.)
 #if defined(VLCU_COV_NOINLINE) && defined(__CUDACC__)
 #define VLCU_COV_FN __device__ __noinline__ static
+#define VLCU_COV_CALLER __device__ inline
 #else
 #define VLCU_COV_FN VLCU_HD
+#define VLCU_COV_CALLER VLCU_HD
 #endif
 VLCU_COV_FN void vlcu_cov_bump_bits(VlcuCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
@@ -897,17 +899,24 @@ struct VlcuLanes<VlWide<N_Words>> final {
 // aggregates: a cover point adds, once, the number of lanes that reached it; a toggle point
 // counts, per bit position that changed in any lane, the lanes where it rose and where it fell
 // (two ballots).  The counters are the exact sums of the per-instance counters the C++ model keeps.
+// One lane of `lanes` (the lanes executing this together; the lowest) adds `value` to a counter;
+// a zero is not sent.  (elect.sync with a run-time mask costs a WARPSYNC/ENDCOLLECTIVE region of
+// its own; two integer operations find the lowest lane as well.)
+#ifdef __CUDA_ARCH__
+VLCU_D void vlcu_red_elected(unsigned lanes, unsigned long long* p, uint32_t value) {
+    const uint32_t mine = (lanes & (0U - lanes)) == (1U << (threadIdx.x & 31U)) ? value : 0U;
+    if (mine) atomicAdd(p, static_cast<unsigned long long>(mine));
+}
+#endif
 struct VlcuTileCovRef final {
     unsigned long long* m_p;
     VLCU_HD void operator++() const {
 #ifdef __CUDA_ARCH__
-        // the lanes reaching this point together, grouped by the counter they bump (the wide
-        // toggle macro walks different bits in different lanes): one add per group
+        // the lanes reaching this point together bump the same counter (a line or branch point of
+        // the code they all run, for the scope they all are in): one add of their number.  (Any
+        // split of the lanes into groups gives the same sum.)
         const unsigned lanes = __activemask();
-        const unsigned same = __match_any_sync(lanes, reinterpret_cast<unsigned long long>(m_p));
-        if ((threadIdx.x & 31U) == static_cast<unsigned>(__ffs(same) - 1)) {
-            atomicAdd(m_p, static_cast<unsigned long long>(__popc(same)));
-        }
+        vlcu_red_elected(lanes, m_p, __popc(lanes));
 #else
         ++*m_p;
 #endif
@@ -966,16 +975,63 @@ VLCU_COV_FN void vlcu_cov_bump_wide(VlcuTileCovPtr covp, int width, WDataInP new
     }
 #endif
 }
-VLCU_HD void VL_COV_TOGGLE_CHG_ST_W(int width, VlcuTileCovPtr covp, WDataInP newData, WDataInP oldData) {
+VLCU_COV_CALLER void VL_COV_TOGGLE_CHG_ST_W(int width, VlcuTileCovPtr covp, WDataInP newData, WDataInP oldData) {
     vlcu_cov_bump_wide(covp, width, newData, oldData);
 }
-// Counter 2*i + (bit i of newData) for every bit i of `chg`, summed over the lanes of the warp
+// 32 x 32 bit-matrix transpose across the lanes of a FULL warp: lane l gives row l and receives
+// column l (bit k of the result = bit l of lane k's word).  Five butterfly stages of one shuffle,
+// one rotate and one LOP3 each.
+#ifdef __CUDA_ARCH__
+VLCU_D uint32_t vlcu_warp_transpose32(uint32_t x) {
+    const uint32_t lane = threadIdx.x & 31U;
+#pragma unroll
+    for (uint32_t j = 16; j >= 1; j >>= 1) {
+        const uint32_t m = j == 16 ? 0xffff0000U : j == 8 ? 0xff00ff00U : j == 4 ? 0xf0f0f0f0U : j == 2 ? 0xccccccccU : 0xaaaaaaaaU;
+        const uint32_t y = __shfl_xor_sync(0xffffffffU, x, j);
+        const bool upper = lane & j;
+        const uint32_t t = __funnelshift_l(y, y, upper ? 32U - j : j);
+        const uint32_t keep = upper ? m : ~m;
+        x = (x & keep) | (t & ~keep);
+    }
+    return x;
+}
+#endif
+// The condition of a toggle point, IF(orig ^ change) { INC; change = orig; } (V3Clock.cpp:69-97),
+// as the emitter prints it for per-tile counters: the lanes of the warp enter the point together
+// when any of them saw a change (an unchanged lane bumps nothing and rewrites its shadow copy with
+// the same value), so the bump below can work across the whole warp.
+VLCU_HD bool vlcu_cov_any(bool changed) {
+#ifdef __CUDA_ARCH__
+    return __any_sync(__activemask(), changed);
+#else
+    return changed;
+#endif
+}
+// Counter 2*i + (bit i of newData) for every bit i of `chg`, summed over the lanes of the warp.
+// Full warp (the normal case, see vlcu_cov_any): the changed and the risen masks are transposed
+// across the lanes, lane b then holds who changed bit b -- two popcounts give its two counters --
+// and the 64 counters go out as two contiguous runs of 32.  The cost does not depend on how many
+// bits changed; the per-bit ballot loop is kept for a divergent warp.
 VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
     const unsigned lanes = __activemask();
+    const uint32_t rise = chg & newData;
+    if (lanes == 0xffffffffU) {
+        const uint32_t lane = threadIdx.x & 31U;
+        const uint32_t chgT = vlcu_warp_transpose32(chg), riseT = vlcu_warp_transpose32(rise);
+        const uint32_t up = __popc(riseT), down = __popc(chgT) - up;
+        // counter k (bit k/2, direction k&1) and counter 32+k to lane k
+        const uint32_t both = (up << 8) | down;
+        const uint32_t lo = __shfl_sync(0xffffffffU, both, lane >> 1);
+        const uint32_t hi = __shfl_sync(0xffffffffU, both, 16U + (lane >> 1));
+        const uint32_t addLo = (lane & 1U) ? (lo >> 8) : (lo & 0xffU);
+        const uint32_t addHi = (lane & 1U) ? (hi >> 8) : (hi & 0xffU);
+        if (addLo) atomicAdd(covp.m_p + lane, static_cast<unsigned long long>(addLo));
+        if (addHi) atomicAdd(covp.m_p + 32U + lane, static_cast<unsigned long long>(addHi));
+        return;
+    }
     const bool leader = (threadIdx.x & 31U) == static_cast<unsigned>(__ffs(lanes) - 1);
     uint32_t any = __reduce_or_sync(lanes, chg);
-    const uint32_t rise = chg & newData;
     while (any) {
         uint32_t i;
         asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(any));
@@ -995,6 +1051,82 @@ VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t 
     }
 #endif
 }
+// Line, branch and expression points of one run of a function: the emitted code sets bit
+// (bin % 32) of a local mask per window of 32 bins when a point is passed and hands the mask over
+// here when the function ends: transposed across the warp, lane b holds who passed bin b.
+VLCU_COV_FN void vlcu_cov_flush_hits(VlcuTileCovPtr covp, uint32_t hits) {
+#ifdef __CUDA_ARCH__
+    const unsigned lanes = __activemask();
+    if (lanes == 0xffffffffU) {
+        if (!__any_sync(0xffffffffU, hits != 0U)) return;
+        const uint32_t passed = __popc(vlcu_warp_transpose32(hits));
+        if (passed) atomicAdd(covp.m_p + (threadIdx.x & 31U), static_cast<unsigned long long>(passed));
+        return;
+    }
+    uint32_t any = __reduce_or_sync(lanes, hits);
+    while (any) {
+        uint32_t i;
+        asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(any));
+        any ^= 1U << i;
+        vlcu_red_elected(lanes, covp.m_p + i, __popc(__ballot_sync(lanes, (hits >> i) & 1U)));
+    }
+#else
+    for (; hits; hits &= hits - 1U) ++covp[vlcu_ctz32(hits)];
+#endif
+}
+// One-bit signals (most toggle points of a design): two ballots, no loop
+VLCU_COV_FN void vlcu_cov_bump_bit(VlcuTileCovPtr covp, uint32_t chg, uint32_t newData) {
+#ifdef __CUDA_ARCH__
+    const unsigned lanes = __activemask();
+    const unsigned changed = __ballot_sync(lanes, chg & 1U);
+    const unsigned rose = __ballot_sync(lanes, chg & newData & 1U);
+    const unsigned up = __popc(rose);
+    vlcu_red_elected(lanes, covp.m_p + 1, up);
+    vlcu_red_elected(lanes, covp.m_p, __popc(changed) - up);
+#else
+    if (chg & 1U) ++covp[newData & 1U];
+#endif
+}
+VLCU_COV_CALLER void VL_COV_TOGGLE_CHG_ST_I(int width, VlcuTileCovPtr covp, IData newData, IData oldData) {
+    IData chg = newData ^ oldData;
+    if (width < 32) chg &= (1U << width) - 1U;
+    if (width == 1) {
+        vlcu_cov_bump_bit(covp, chg, newData);
+    } else {
+        vlcu_cov_bump_bits(covp, chg, newData);
+    }
+}
+
+VLCU_COV_CALLER void VL_COV_TOGGLE_CHG_ST_Q(int width, VlcuTileCovPtr covp, QData newData, QData oldData) {
+    QData chg = newData ^ oldData;
+    if (width < 64) chg &= (1ULL << width) - 1ULL;
+    vlcu_cov_bump_bits(covp, static_cast<uint32_t>(chg), static_cast<uint32_t>(newData));
+    vlcu_cov_bump_bits(covp + 64, static_cast<uint32_t>(chg >> 32), static_cast<uint32_t>(newData >> 32));
+}
+
+// The counters of a register-form design kept per WARP of 32 instances ([warp][bin] uint64 in the
+// block of __Vcoverage; -cuda-cover-per-instance keeps VlcuCovArray instead): `__Vcoverage + n` and
+// `++__Vcoverage[n]` of the emitted code land on the per-tile forms above.
+template <size_t N_Bins>
+struct VlcuWarpCovArray final {
+    unsigned long long* m_p;  // counter 0 of this instance's warp
+    VLCU_HD void bind(const VlcuState& st, uint32_t soaOffset, uint64_t inst) {
+        m_p = reinterpret_cast<unsigned long long*>(st.ptr<uint32_t>(soaOffset)) + (inst / VLCU_TILE) * N_Bins;
+    }
+    VLCU_HD VlcuTileCovRef operator[](size_t bin) const { return VlcuTileCovRef{m_p + bin}; }
+    VLCU_HD VlcuTileCovPtr operator+(size_t bin) const { return VlcuTileCovPtr{m_p + bin}; }
+    // (reset: the lanes that are there share the work; `bins` <= N_Bins is the real count)
+    VLCU_HD void zero(uint32_t bins) const {
+#ifdef __CUDA_ARCH__
+        const unsigned lanes = __activemask();
+        const uint32_t rank = __popc(lanes & ((1U << (threadIdx.x & 31U)) - 1U)), step = __popc(lanes);
+        for (uint32_t b = rank; b < bins; b += step) m_p[b] = 0ULL;
+#else
+        for (uint32_t b = 0; b < bins; ++b) m_p[b] = 0ULL;
+#endif
+    }
+    VLCU_HD constexpr size_t size() const { return N_Bins; }
+};
 
 // A large array kept [element][lane]: an index that is the same in all lanes of a warp (a loop
 // counter) touches one contiguous run.  `arr.lane(vlLane)[i]` is element i of this instance.

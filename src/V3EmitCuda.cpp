@@ -510,7 +510,9 @@ class EmitCudaModel final : public EmitCFunc {
                 cov.name = "__Vcoverage";
                 cov.kind = 4;
                 cov.elemBytes = 4;
-                cov.depth = m_coverBins;
+                // per instance: one uint32 per bin; per warp: one uint64 per bin for 32 instances, kept
+                // in the same block ([tile][bin], bins / 4 bytes of the block per instance)
+                cov.depth = V3EmitCuda::coverPerInstance() ? m_coverBins : (m_coverBins + 15) / 16;
                 cov.isArray = true;
                 cov.width = 32;
                 cov.msb = 31;
@@ -623,7 +625,9 @@ class EmitCudaModel final : public EmitCFunc {
         case CudaStorage::LOCAL: flat = "VlcuLocalArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::GLOBAL: flat = "VlcuGlobalArray<" + m.elemDecl + ", " + depth + ">"; break;
         case CudaStorage::INTERLEAVED: flat = "VlcuStateArray<" + m.elemDecl + ", " + depth + ">"; break;
-        case CudaStorage::COVER: return "VlcuCovArray<" + depth + "> " + m.name;
+        case CudaStorage::COVER:
+            return V3EmitCuda::coverPerInstance() ? "VlcuCovArray<" + depth + "> " + m.name
+                                                  : "VlcuWarpCovArray<" + depth + " * 16> " + m.name;
         default: return "";
         }
         if (m.dims.size() <= 1) return flat + " " + m.name;
@@ -641,7 +645,9 @@ class EmitCudaModel final : public EmitCFunc {
                 puts(handleDecl(m) + ";");
                 puts(m.storage == CudaStorage::SHARED  ? "  // run-time indexed: shared memory [index][lane]\n"
                      : m.storage == CudaStorage::LOCAL ? "  // thread-local memory\n"
-                     : m.storage == CudaStorage::COVER ? "  // stays in HBM as cov[bin][instance], RED.ADD\n"
+                     : m.storage == CudaStorage::COVER
+                         ? (V3EmitCuda::coverPerInstance() ? "  // stays in HBM as cov[bin][instance], RED.ADD\n"
+                                                           : "  // stays in HBM as cov[warp][bin], uint64 per warp of instances\n")
                      : m.storage == CudaStorage::INTERLEAVED
                          ? "  // stays in HBM, [element][instance]: instance-uniform indices coalesce\n"
                                                        : "  // stays in HBM, instance-major\n");
@@ -1208,9 +1214,21 @@ class EmitCudaModel final : public EmitCFunc {
             putsDecoration(nodep, "// Locals\n");
             iterateAndNextConstNull(nodep->varsp());
         }
+        VL_RESTORER_CLEAR(m_covHitWindows);
+        if (m_coverBins && (m_stream || !V3EmitCuda::coverPerInstance()) && nodep->isLoose() && !nodep->isStatic()
+            && !nodep->slow() && nodep->rtnTypeVoid() == "void") {
+            nodep->foreach([&](AstCoverInc* incp) {
+                if (covHitEligible(incp)) m_covHitWindows.insert(coverageBinNum(incp->declp()) / 32);
+            });
+            for (const int window : m_covHitWindows) puts("uint32_t vlCovHit" + cvtToStr(window) + " = 0U;\n");
+        }
         if (nodep->stmtsp()) {
             putsDecoration(nodep, "// Body\n");
             iterateAndNextConstNull(nodep->stmtsp());
+        }
+        for (const int window : m_covHitWindows) {
+            puts("vlcu_cov_flush_hits(vlSelf->__Vcoverage + " + cvtToStr(window * 32) + ", vlCovHit" + cvtToStr(window)
+                 + ");\n");
         }
         std::vector<const CudaCached*> prefetches;
         if (m_caching) {
@@ -1342,6 +1360,45 @@ class EmitCudaModel final : public EmitCFunc {
                 }
                 return;
             }
+        }
+        EmitCFunc::visit(nodep);
+    }
+    // Line, branch and expression points with per-warp counters: a point passed sets bit (bin % 32)
+    // of a function-local mask for its window of 32 bins (one LOP3, nothing goes to memory), and
+    // the masks are handed to the counters when the function ends (vlcu_cov_flush_hits: counted
+    // over the warp, one add per bin).  Not inside loops (a point could be passed twice) and not
+    // in functions that return a value.
+    std::set<int> m_covHitWindows;  // of the function being printed; empty: points bump directly
+    int m_loopDepth = 0;
+    bool covHitEligible(AstCoverInc* nodep) {
+        return VN_IS(nodep->declp(), CoverOtherDecl) && coverageUsesLocalCounter(nodep->declp());
+    }
+    void visit(AstCoverInc* nodep) override {
+        if (!m_covHitWindows.empty() && !m_loopDepth && covHitEligible(nodep)) {
+            const int bin = coverageBinNum(nodep->declp());
+            putns(nodep, "vlCovHit" + cvtToStr(bin / 32) + " |= " + cvtToStr(1U << (bin % 32)) + "U;\n");
+            return;
+        }
+        EmitCFunc::visit(nodep);
+    }
+    void visit(AstLoop* nodep) override {
+        ++m_loopDepth;
+        EmitCFunc::visit(nodep);
+        --m_loopDepth;
+    }
+    void visit(AstNodeIf* nodep) override {
+        // A toggle point, IF(orig ^ change) { INC; change = orig; } (V3Clock.cpp:69-97), with per-tile
+        // counters: the lanes of the warp take it together (vlcu_cov_any) so that the bump can work
+        // across the warp; a lane that saw no change bumps nothing and rewrites the same shadow value.
+        const AstCoverInc* const incp = VN_CAST(nodep->thensp(), CoverInc);
+        if ((m_stream || !V3EmitCuda::coverPerInstance()) && incp && incp->toggleExprp() && !nodep->elsesp() && VN_IS(incp->nextp(), Assign)
+            && !incp->nextp()->nextp()) {
+            putns(nodep, "if (vlcu_cov_any(");
+            iterateAndNextConstNull(nodep->condp());
+            puts(")) {\n");
+            iterateAndNextConstNull(nodep->thensp());
+            puts("}\n");
+            return;
         }
         EmitCFunc::visit(nodep);
     }
@@ -1818,7 +1875,11 @@ class EmitCudaModel final : public EmitCFunc {
             }
         } else {
             if (m_coverBins) {
-                puts("for (uint32_t b = 0; b < " + cvtToStr(m_coverBins) + "U; ++b) vlSelf->__Vcoverage[b] = 0U;\n");
+                if (V3EmitCuda::coverPerInstance()) {
+                    puts("for (uint32_t b = 0; b < " + cvtToStr(m_coverBins) + "U; ++b) vlSelf->__Vcoverage[b] = 0U;\n");
+                } else {
+                    puts("vlSelf->__Vcoverage.zero(" + cvtToStr(m_coverBins) + "U);\n");
+                }
             }
             if (const AstCFunc* const funcp = findFunc("_ctor_var_reset")) {
                 puts(funcNameProtect(funcp) + "(vlSelf, vlCtx);\n");
@@ -1960,6 +2021,10 @@ class EmitCudaModel final : public EmitCFunc {
             }
             puts("t.finish();\n");
             puts("}\n");
+            if (!m_stream && !V3EmitCuda::coverPerInstance()) {
+                puts("// one uint64 counter per bin for every warp of 32 instances, [warp][bin] in the block of __Vcoverage\n");
+                puts("static const VlcuCoverScope coverScopes[] = {{0, " + cvtToStr(m_coverBins) + "}};\n");
+            }
             if (m_stream) {
                 puts("// where each scope's counters are in a tile: byte offset of counter 0 (uint64 each), counters\n");
                 puts("static const VlcuCoverScope coverScopes[] = {\n");
@@ -2045,7 +2110,9 @@ class EmitCudaModel final : public EmitCFunc {
                        ? -1
                        : std::abs(v3Global.rootp()->timeprecision().powerOfTen()))
                << ", " << (m_stream ? "VLCU_TILE" : "0")
-               << (m_stream && m_coverBins ? ", coverScopes, sizeof(coverScopes) / sizeof(coverScopes[0])" : ", nullptr, 0")
+               << (m_coverBins && (m_stream || !V3EmitCuda::coverPerInstance())
+                       ? ", coverScopes, sizeof(coverScopes) / sizeof(coverScopes[0])"
+                       : ", nullptr, 0")
                << "};\n";
             puts(os.str());
         }
@@ -2072,6 +2139,7 @@ bool V3EmitCuda::s_layoutSelection = true;
 int V3EmitCuda::s_streamMode = -1;
 bool V3EmitCuda::s_leafCaching = true;
 bool V3EmitCuda::s_leafPrefetch = false;
+bool V3EmitCuda::s_coverPerInstance = false;
 int V3EmitCuda::s_chunkNodes = 0;
 bool V3EmitCuda::s_shareCode = true;
 bool V3EmitCuda::s_interleaveAll = false;

@@ -48,6 +48,11 @@ public:
     static size_t gatherWords() { return static_cast<size_t>(s_gatherWords); }
     // --cuda-leaf-prefetch / --no-cuda-leaf-prefetch: ... and the caller issues the next leaf's
     // gather as prefetches one call ahead
+    // --coverage counters of a register-form design: one set per instance, cov[bin][instance]
+    // (on), or one uint64 set per warp of 32 instances bumped warp-wide (off, the default: the
+    // product of a campaign is the sum over instances)
+    static void coverPerInstance(bool flag) { s_coverPerInstance = flag; }
+    static bool coverPerInstance() { return s_coverPerInstance; }
     static void leafPrefetch(bool flag) { s_leafPrefetch = flag; }
     static bool leafPrefetch() { return s_leafPrefetch; }
     // --cuda-chunk-nodes <n> (tiled form): AST nodes of leaf code inlined into one chunk function;
@@ -67,6 +72,7 @@ private:
     static bool s_leafCaching;
     static int s_gatherWords;
     static bool s_leafPrefetch;
+    static bool s_coverPerInstance;
     static int s_chunkNodes;
     static bool s_shareCode;
 };

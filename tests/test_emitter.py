@@ -15,7 +15,10 @@ REF = "/root/reference"
 
 CASES = [  # (committed model, top-level source, extra flags)
     ("make_tracing_c/Vtop__cuda.cu", f"{REF}/examples/make_tracing_c/top.v",
-     ["--trace-vcd", "--assert", "--coverage", "--prefix", "Vtop", "-y", f"{REF}/examples/make_tracing_c"]),
+     ["--trace-vcd", "--assert", "--coverage", "-cuda-cover-per-instance", "--prefix", "Vtop", "-y",
+      f"{REF}/examples/make_tracing_c"]),
+    ("rv32i/Vrv32_cov__cuda.cu", "../verilator_b200/csrc/designs/rv32i/rv32_soc.v",  # counters per warp
+     ["--coverage", "--prefix", "Vrv32_cov"]),
     ("make_tracing_c/Vtop_nocov__cuda.cu", f"{REF}/examples/make_tracing_c/top.v",
      ["--trace-vcd", "--assert", "--prefix", "Vtop_nocov", "-y", f"{REF}/examples/make_tracing_c"]),
     ("rv32i/Vrv32_soc__cuda.cu", "../verilator_b200/csrc/designs/rv32i/rv32_soc.v",

@@ -127,7 +127,7 @@ struct Vrv32_cov___024root final {
     VlUnpacked<QData/*63:0*/, 2> __VicoTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VactTriggered;
     VlUnpacked<QData/*63:0*/, 1> __VnbaTriggered;
-    VlcuCovArray<1664> __Vcoverage;  // stays in HBM as cov[bin][instance], RED.ADD
+    VlcuWarpCovArray<104 * 16> __Vcoverage;  // stays in HBM as cov[warp][bin], uint64 per warp of instances
     const char* vlNamep;
 };
 
@@ -136,68 +136,68 @@ struct Vrv32_cov__cuda final {
     static constexpr bool kTiled = false;
     // Structure-of-arrays slot table: byte offset per instance of every persistent member
     enum : uint32_t {
-        OFF_clk = 11116,
-        OFF_resetn = 11117,
-        OFF_trap = 11118,
-        OFF_mem_valid = 11119,
-        OFF_mem_instr = 11120,
+        OFF_clk = 4876,
+        OFF_resetn = 4877,
+        OFF_trap = 4878,
+        OFF_mem_valid = 4879,
+        OFF_mem_instr = 4880,
         OFF_mem_addr = 40,
         OFF_mem_wdata = 44,
-        OFF_mem_wstrb = 11121,
+        OFF_mem_wstrb = 4881,
         OFF_mem_rdata = 48,
         OFF_retired = 52,
-        OFF_rv32_soc__DOT____VlemCond_10 = 11122,
-        OFF_rv32_soc__DOT____VlemCond_6 = 11123,
-        OFF_rv32_soc__DOT__state = 11124,
-        OFF_rv32_soc__DOT__is_jalr = 11125,
-        OFF_rv32_soc__DOT__is_branch = 11126,
-        OFF_rv32_soc__DOT__is_load = 11127,
-        OFF_rv32_soc__DOT__is_store = 11128,
-        OFF_rv32_soc__DOT__is_alui = 11129,
-        OFF_rv32_soc__DOT__is_alur = 11130,
-        OFF_rv32_soc__DOT__take_branch = 11131,
-        OFF_rv32_soc__DOT__ls_misaligned = 11132,
-        OFF_rv32_soc__DOT__st_strb = 11133,
-        OFF_rv32_soc__DOT__pc_bad = 11134,
-        OFF_rv32_soc__DOT____Vtogcov__clk = 11135,
-        OFF_rv32_soc__DOT____Vtogcov__resetn = 11136,
-        OFF_rv32_soc__DOT____Vtogcov__trap = 11137,
-        OFF_rv32_soc__DOT____Vtogcov__mem_valid = 11138,
-        OFF_rv32_soc__DOT____Vtogcov__mem_instr = 11139,
-        OFF_rv32_soc__DOT____Vtogcov__mem_wstrb = 11140,
-        OFF_rv32_soc__DOT____Vtogcov__state = 11141,
-        OFF_rv32_soc__DOT____Vtogcov__opcode = 11142,
-        OFF_rv32_soc__DOT____Vtogcov__rd = 11143,
-        OFF_rv32_soc__DOT____Vtogcov__funct3 = 11144,
-        OFF_rv32_soc__DOT____Vtogcov__rs1 = 11145,
-        OFF_rv32_soc__DOT____Vtogcov__rs2 = 11146,
-        OFF_rv32_soc__DOT____Vtogcov__f7b5 = 11147,
-        OFF_rv32_soc__DOT____Vtogcov__is_lui = 11148,
-        OFF_rv32_soc__DOT____Vtogcov__is_auipc = 11149,
-        OFF_rv32_soc__DOT____Vtogcov__is_jal = 11150,
-        OFF_rv32_soc__DOT____Vtogcov__is_jalr = 11151,
-        OFF_rv32_soc__DOT____Vtogcov__is_branch = 11152,
-        OFF_rv32_soc__DOT____Vtogcov__is_load = 11153,
-        OFF_rv32_soc__DOT____Vtogcov__is_store = 11154,
-        OFF_rv32_soc__DOT____Vtogcov__is_alui = 11155,
-        OFF_rv32_soc__DOT____Vtogcov__is_alur = 11156,
-        OFF_rv32_soc__DOT____Vtogcov__shamt = 11157,
-        OFF_rv32_soc__DOT____Vtogcov__alu_sub = 11158,
-        OFF_rv32_soc__DOT____Vtogcov__take_branch = 11159,
-        OFF_rv32_soc__DOT____Vtogcov__ls_misaligned = 11160,
-        OFF_rv32_soc__DOT____Vtogcov__ls_oob = 11161,
-        OFF_rv32_soc__DOT____Vtogcov__st_strb = 11162,
-        OFF_rv32_soc__DOT____Vtogcov__pc_bad = 11163,
-        OFF_rv32_soc__DOT____Vtogcov__exec_ls = 11164,
-        OFF___VstlFirstIteration = 11165,
-        OFF___VstlPhaseResult = 11166,
-        OFF___Vtrigprevexpr___TOP__clk__0 = 11167,
-        OFF___Vtrigprevexpr___TOP__resetn__0 = 11168,
-        OFF___VicoDidInit = 11169,
-        OFF___VicoPhaseResult = 11170,
-        OFF___Vtrigprevexpr___TOP__clk__1 = 11171,
-        OFF___VactPhaseResult = 11172,
-        OFF___VnbaPhaseResult = 11173,
+        OFF_rv32_soc__DOT____VlemCond_10 = 4882,
+        OFF_rv32_soc__DOT____VlemCond_6 = 4883,
+        OFF_rv32_soc__DOT__state = 4884,
+        OFF_rv32_soc__DOT__is_jalr = 4885,
+        OFF_rv32_soc__DOT__is_branch = 4886,
+        OFF_rv32_soc__DOT__is_load = 4887,
+        OFF_rv32_soc__DOT__is_store = 4888,
+        OFF_rv32_soc__DOT__is_alui = 4889,
+        OFF_rv32_soc__DOT__is_alur = 4890,
+        OFF_rv32_soc__DOT__take_branch = 4891,
+        OFF_rv32_soc__DOT__ls_misaligned = 4892,
+        OFF_rv32_soc__DOT__st_strb = 4893,
+        OFF_rv32_soc__DOT__pc_bad = 4894,
+        OFF_rv32_soc__DOT____Vtogcov__clk = 4895,
+        OFF_rv32_soc__DOT____Vtogcov__resetn = 4896,
+        OFF_rv32_soc__DOT____Vtogcov__trap = 4897,
+        OFF_rv32_soc__DOT____Vtogcov__mem_valid = 4898,
+        OFF_rv32_soc__DOT____Vtogcov__mem_instr = 4899,
+        OFF_rv32_soc__DOT____Vtogcov__mem_wstrb = 4900,
+        OFF_rv32_soc__DOT____Vtogcov__state = 4901,
+        OFF_rv32_soc__DOT____Vtogcov__opcode = 4902,
+        OFF_rv32_soc__DOT____Vtogcov__rd = 4903,
+        OFF_rv32_soc__DOT____Vtogcov__funct3 = 4904,
+        OFF_rv32_soc__DOT____Vtogcov__rs1 = 4905,
+        OFF_rv32_soc__DOT____Vtogcov__rs2 = 4906,
+        OFF_rv32_soc__DOT____Vtogcov__f7b5 = 4907,
+        OFF_rv32_soc__DOT____Vtogcov__is_lui = 4908,
+        OFF_rv32_soc__DOT____Vtogcov__is_auipc = 4909,
+        OFF_rv32_soc__DOT____Vtogcov__is_jal = 4910,
+        OFF_rv32_soc__DOT____Vtogcov__is_jalr = 4911,
+        OFF_rv32_soc__DOT____Vtogcov__is_branch = 4912,
+        OFF_rv32_soc__DOT____Vtogcov__is_load = 4913,
+        OFF_rv32_soc__DOT____Vtogcov__is_store = 4914,
+        OFF_rv32_soc__DOT____Vtogcov__is_alui = 4915,
+        OFF_rv32_soc__DOT____Vtogcov__is_alur = 4916,
+        OFF_rv32_soc__DOT____Vtogcov__shamt = 4917,
+        OFF_rv32_soc__DOT____Vtogcov__alu_sub = 4918,
+        OFF_rv32_soc__DOT____Vtogcov__take_branch = 4919,
+        OFF_rv32_soc__DOT____Vtogcov__ls_misaligned = 4920,
+        OFF_rv32_soc__DOT____Vtogcov__ls_oob = 4921,
+        OFF_rv32_soc__DOT____Vtogcov__st_strb = 4922,
+        OFF_rv32_soc__DOT____Vtogcov__pc_bad = 4923,
+        OFF_rv32_soc__DOT____Vtogcov__exec_ls = 4924,
+        OFF___VstlFirstIteration = 4925,
+        OFF___VstlPhaseResult = 4926,
+        OFF___Vtrigprevexpr___TOP__clk__0 = 4927,
+        OFF___Vtrigprevexpr___TOP__resetn__0 = 4928,
+        OFF___VicoDidInit = 4929,
+        OFF___VicoPhaseResult = 4930,
+        OFF___Vtrigprevexpr___TOP__clk__1 = 4931,
+        OFF___VactPhaseResult = 4932,
+        OFF___VnbaPhaseResult = 4933,
         OFF_rv32_soc__DOT____VlemCond_11 = 56,
         OFF_rv32_soc__DOT____VlemCond_9 = 60,
         OFF_rv32_soc__DOT____VlemCond_8 = 64,
@@ -250,7 +250,7 @@ struct Vrv32_cov__cuda final {
         OFF___VactTriggered = 24,
         OFF___VnbaTriggered = 32,
         OFF___Vcoverage = 4460,
-        kStateBytes = 11176,  // S_persist
+        kStateBytes = 4936,  // S_persist
         kTouchedReadBytes = 336,  // S_state_rd: persistent bytes one eval can read
         kTouchedWriteBytes = 322,  // S_state_wr
     };
@@ -765,52 +765,56 @@ struct Vrv32_cov__cuda final {
                                >> 2U)))) {
             ++(vlSelf->__Vcoverage[1569]);
         }
-        if (((IData)(vlSelfRef.clk) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__clk))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.clk) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__clk)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 0, vlSelfRef.clk, vlSelfRef.rv32_soc__DOT____Vtogcov__clk);
             vlSelfRef.rv32_soc__DOT____Vtogcov__clk 
                 = vlSelfRef.clk;
         }
-        if (((IData)(vlSelfRef.resetn) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__resetn))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.resetn) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__resetn)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 2, vlSelfRef.resetn, vlSelfRef.rv32_soc__DOT____Vtogcov__resetn);
             vlSelfRef.rv32_soc__DOT____Vtogcov__resetn 
                 = vlSelfRef.resetn;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__instret 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__retired))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__instret 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__retired)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 210, vlSelfRef.rv32_soc__DOT__instret, vlSelfRef.rv32_soc__DOT____Vtogcov__retired);
             vlSelfRef.rv32_soc__DOT____Vtogcov__retired 
                 = vlSelfRef.rv32_soc__DOT__instret;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__pc ^ vlSelfRef.rv32_soc__DOT____Vtogcov__pc))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__pc 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__pc)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 274, vlSelfRef.rv32_soc__DOT__pc, vlSelfRef.rv32_soc__DOT____Vtogcov__pc);
             vlSelfRef.rv32_soc__DOT____Vtogcov__pc 
                 = vlSelfRef.rv32_soc__DOT__pc;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__insn ^ vlSelfRef.rv32_soc__DOT____Vtogcov__insn))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__insn 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__insn)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 338, vlSelfRef.rv32_soc__DOT__insn, vlSelfRef.rv32_soc__DOT____Vtogcov__insn);
             vlSelfRef.rv32_soc__DOT____Vtogcov__insn 
                 = vlSelfRef.rv32_soc__DOT__insn;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ld_addr 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 402, vlSelfRef.rv32_soc__DOT__ld_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr 
                 = vlSelfRef.rv32_soc__DOT__ld_addr;
         }
-        if ((0U != ((IData)(vlSelfRef.rv32_soc__DOT__state) 
-                    ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__state)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.rv32_soc__DOT__state) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__state))))) {
             VL_COV_TOGGLE_CHG_ST_I(2, vlSelf->__Vcoverage + 466, vlSelfRef.rv32_soc__DOT__state, vlSelfRef.rv32_soc__DOT____Vtogcov__state);
             vlSelfRef.rv32_soc__DOT____Vtogcov__state 
                 = vlSelfRef.rv32_soc__DOT__state;
         }
-        if ((0U != (0x0000007fU & (vlSelfRef.rv32_soc__DOT__insn 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__opcode))))) {
+        if (vlcu_cov_any((0U != (0x0000007fU & (vlSelfRef.rv32_soc__DOT__insn 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__opcode)))))) {
             VL_COV_TOGGLE_CHG_ST_I(7, vlSelf->__Vcoverage + 470, vlSelfRef.rv32_soc__DOT__insn, vlSelfRef.rv32_soc__DOT____Vtogcov__opcode);
             vlSelfRef.rv32_soc__DOT____Vtogcov__opcode 
                 = (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn);
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 7U) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rd))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 7U) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rd)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 484, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 7U), vlSelfRef.rv32_soc__DOT____Vtogcov__rd);
@@ -818,8 +822,9 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 7U));
         }
-        if ((0U != (7U & ((vlSelfRef.rv32_soc__DOT__insn 
-                           >> 0x0000000cU) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__funct3))))) {
+        if (vlcu_cov_any((0U != (7U & ((vlSelfRef.rv32_soc__DOT__insn 
+                                        >> 0x0000000cU) 
+                                       ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__funct3)))))) {
             VL_COV_TOGGLE_CHG_ST_I(3, vlSelf->__Vcoverage + 494, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000000cU), vlSelfRef.rv32_soc__DOT____Vtogcov__funct3);
@@ -827,9 +832,9 @@ struct Vrv32_cov__cuda final {
                 = (7U & (vlSelfRef.rv32_soc__DOT__insn 
                          >> 0x0000000cU));
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 0x0000000fU) 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs1))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 0x0000000fU) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs1)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 500, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000000fU), vlSelfRef.rv32_soc__DOT____Vtogcov__rs1);
@@ -837,9 +842,9 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 0x0000000fU));
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 0x00000014U) 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs2))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 0x00000014U) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs2)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 510, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x00000014U), vlSelfRef.rv32_soc__DOT____Vtogcov__rs2);
@@ -847,8 +852,8 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 0x00000014U));
         }
-        if ((1U & ((vlSelfRef.rv32_soc__DOT__insn >> 0x0000001eU) 
-                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5)))) {
+        if (vlcu_cov_any((1U & ((vlSelfRef.rv32_soc__DOT__insn 
+                                 >> 0x0000001eU) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5))))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 520, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000001eU), vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5);
@@ -856,15 +861,16 @@ struct Vrv32_cov__cuda final {
                 = (1U & (vlSelfRef.rv32_soc__DOT__insn 
                          >> 0x0000001eU));
         }
-        if ((0U != ((((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
-                                  >> 0x0000001fU))) 
-                      << 0x0000000cU) | ((0x00000fe0U 
-                                          & (vlSelfRef.rv32_soc__DOT__insn 
-                                             >> 0x00000014U)) 
-                                         | (0x0000001fU 
-                                            & (vlSelfRef.rv32_soc__DOT__insn 
-                                               >> 7U)))) 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_s))) {
+        if (vlcu_cov_any((0U != ((((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
+                                               >> 0x0000001fU))) 
+                                   << 0x0000000cU) 
+                                  | ((0x00000fe0U & 
+                                      (vlSelfRef.rv32_soc__DOT__insn 
+                                       >> 0x00000014U)) 
+                                     | (0x0000001fU 
+                                        & (vlSelfRef.rv32_soc__DOT__insn 
+                                           >> 7U)))) 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_s)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 586, 
                                    (((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
                                                  >> 0x0000001fU))) 
@@ -883,31 +889,31 @@ struct Vrv32_cov__cuda final {
                       | (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                         >> 7U))));
         }
-        if ((0U != ((0xfffff000U & vlSelfRef.rv32_soc__DOT__insn) 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u))) {
+        if (vlcu_cov_any((0U != ((0xfffff000U & vlSelfRef.rv32_soc__DOT__insn) 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 714, 
                                    (0xfffff000U & vlSelfRef.rv32_soc__DOT__insn), vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u 
                 = (0xfffff000U & vlSelfRef.rv32_soc__DOT__insn);
         }
-        if (((0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui))) {
+        if (vlcu_cov_any(((0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 842, 
                                    (0x37U == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui 
                 = (0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn));
         }
-        if (((0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc))) {
+        if (vlcu_cov_any(((0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 844, 
                                    (0x17U == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc 
                 = (0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn));
         }
-        if (((0x6fU == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal))) {
+        if (vlcu_cov_any(((0x6fU == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 846, 
                                    (0x6fU == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal);
@@ -917,10 +923,10 @@ struct Vrv32_cov__cuda final {
         vlSelfRef.rv32_soc__DOT__imm_u = (0xfffff000U 
                                           & vlSelfRef.rv32_soc__DOT__insn);
         vlSelfRef.retired = vlSelfRef.rv32_soc__DOT__instret;
-        if ((0U != (vlSelfRef.rv32_soc__DOT__mem[(0x000003ffU 
-                                                  & (vlSelfRef.rv32_soc__DOT__ld_addr 
-                                                     >> 2U))] 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_word))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__mem
+                                 [(0x000003ffU & (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                                  >> 2U))] 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_word)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1363, vlSelfRef.rv32_soc__DOT__mem
                                    [(0x000003ffU & 
                                      (vlSelfRef.rv32_soc__DOT__ld_addr 
@@ -1093,42 +1099,43 @@ struct Vrv32_cov__cuda final {
                                                 (7U 
                                                  & (vlSelfRef.rv32_soc__DOT__insn 
                                                     >> 0x0000000cU)))));
-        if (((IData)(vlSelfRef.trap) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__trap))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.trap) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__trap)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 4, vlSelfRef.trap, vlSelfRef.rv32_soc__DOT____Vtogcov__trap);
             vlSelfRef.rv32_soc__DOT____Vtogcov__trap 
                 = vlSelfRef.trap;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_b 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_b 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 650, vlSelfRef.rv32_soc__DOT__imm_b, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b 
                 = vlSelfRef.rv32_soc__DOT__imm_b;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_j 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_j 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 778, vlSelfRef.rv32_soc__DOT__imm_j, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j 
                 = vlSelfRef.rv32_soc__DOT__imm_j;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_jalr) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_jalr) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 848, vlSelfRef.rv32_soc__DOT__is_jalr, vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr 
                 = vlSelfRef.rv32_soc__DOT__is_jalr;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_branch) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_branch) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 853, vlSelfRef.rv32_soc__DOT__is_branch, vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch 
                 = vlSelfRef.rv32_soc__DOT__is_branch;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_alui) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_alui) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 875, vlSelfRef.rv32_soc__DOT__is_alui, vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui 
                 = vlSelfRef.rv32_soc__DOT__is_alui;
         }
-        if ((0U != (rv32_soc__DOT__ld_shift ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__ld_shift 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1427, rv32_soc__DOT__ld_shift, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift 
                 = rv32_soc__DOT__ld_shift;
@@ -1183,8 +1190,8 @@ struct Vrv32_cov__cuda final {
                           >> 0x0000000cU)))) {
             ++(vlSelf->__Vcoverage[1556]);
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_i 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_i 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 522, vlSelfRef.rv32_soc__DOT__imm_i, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i 
                 = vlSelfRef.rv32_soc__DOT__imm_i;
@@ -1199,8 +1206,8 @@ struct Vrv32_cov__cuda final {
         if ((0U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
             ++(vlSelf->__Vcoverage[1584]);
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__pc_bad) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__pc_bad) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1565, vlSelfRef.rv32_soc__DOT__pc_bad, vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad);
             vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad 
                 = vlSelfRef.rv32_soc__DOT__pc_bad;
@@ -1218,8 +1225,8 @@ struct Vrv32_cov__cuda final {
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_alur)))) {
             ++(vlSelf->__Vcoverage[1112]);
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_alur) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_alur) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 886, vlSelfRef.rv32_soc__DOT__is_alur, vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur 
                 = vlSelfRef.rv32_soc__DOT__is_alur;
@@ -1227,7 +1234,8 @@ struct Vrv32_cov__cuda final {
         rv32_soc__DOT__alu_sub = ((vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x0000001eU) 
                                   & (IData)(vlSelfRef.rv32_soc__DOT__is_alur));
-        if ((0U != (rv32_soc__DOT__rs2_val ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__rs2_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 962, rv32_soc__DOT__rs2_val, vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val 
                 = rv32_soc__DOT__rs2_val;
@@ -1279,8 +1287,8 @@ struct Vrv32_cov__cuda final {
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_alur)))) {
             ++(vlSelf->__Vcoverage[1095]);
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__rs1_val 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 894, vlSelfRef.rv32_soc__DOT__rs1_val, vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val 
                 = vlSelfRef.rv32_soc__DOT__rs1_val;
@@ -1339,35 +1347,38 @@ struct Vrv32_cov__cuda final {
                                               == (0x0000007fU 
                                                   & vlSelfRef.rv32_soc__DOT__insn)) 
                                              & (IData)(__VdfgRegularize_h6e95ff9d_0_0));
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ld_val 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ld_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1491, vlSelfRef.rv32_soc__DOT__ld_val, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val 
                 = vlSelfRef.rv32_soc__DOT__ld_val;
         }
-        if (((IData)(vlSelfRef.mem_instr) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.mem_instr) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 8, vlSelfRef.mem_instr, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr 
                 = vlSelfRef.mem_instr;
         }
-        if (((IData)(rv32_soc__DOT__alu_sub) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub))) {
+        if (vlcu_cov_any(((IData)(rv32_soc__DOT__alu_sub) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1108, rv32_soc__DOT__alu_sub, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub 
                 = rv32_soc__DOT__alu_sub;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__st_data 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__st_data))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__st_data 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__st_data)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1279, vlSelfRef.rv32_soc__DOT__st_data, vlSelfRef.rv32_soc__DOT____Vtogcov__st_data);
             vlSelfRef.rv32_soc__DOT____Vtogcov__st_data 
                 = vlSelfRef.rv32_soc__DOT__st_data;
         }
-        if ((0U != (rv32_soc__DOT__alu_b ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__alu_b 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1030, rv32_soc__DOT__alu_b, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b 
                 = rv32_soc__DOT__alu_b;
         }
-        if ((0U != (0x0000001fU & (rv32_soc__DOT__alu_b 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__shamt))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & (rv32_soc__DOT__alu_b 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__shamt)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 1098, rv32_soc__DOT__alu_b, vlSelfRef.rv32_soc__DOT____Vtogcov__shamt);
             vlSelfRef.rv32_soc__DOT____Vtogcov__shamt 
                 = (0x0000001fU & rv32_soc__DOT__alu_b);
@@ -1452,14 +1463,14 @@ struct Vrv32_cov__cuda final {
             ++(vlSelf->__Vcoverage[1187]);
         }
         ++(vlSelf->__Vcoverage[1193]);
-        if (((IData)(vlSelfRef.rv32_soc__DOT__take_branch) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__take_branch) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1194, vlSelfRef.rv32_soc__DOT__take_branch, vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch);
             vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch 
                 = vlSelfRef.rv32_soc__DOT__take_branch;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_load) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_load))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_load) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_load)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 859, vlSelfRef.rv32_soc__DOT__is_load, vlSelfRef.rv32_soc__DOT____Vtogcov__is_load);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_load 
                 = vlSelfRef.rv32_soc__DOT__is_load;
@@ -1470,8 +1481,8 @@ struct Vrv32_cov__cuda final {
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_store)))) {
             ++(vlSelf->__Vcoverage[1268]);
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_store) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_store))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_store) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_store)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 868, vlSelfRef.rv32_soc__DOT__is_store, vlSelfRef.rv32_soc__DOT____Vtogcov__is_store);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_store 
                 = vlSelfRef.rv32_soc__DOT__is_store;
@@ -1492,8 +1503,8 @@ struct Vrv32_cov__cuda final {
                                                          : 
                                                         (vlSelfRef.rv32_soc__DOT__insn 
                                                          >> 0x00000014U))))));
-        if ((0U != (vlSelfRef.rv32_soc__DOT__alu_out 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__alu_out 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1113, vlSelfRef.rv32_soc__DOT__alu_out, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out 
                 = vlSelfRef.rv32_soc__DOT__alu_out;
@@ -1529,14 +1540,15 @@ struct Vrv32_cov__cuda final {
                                                     >> 0x0000000cU))))) {
             ++(vlSelf->__Vcoverage[1276]);
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ls_addr 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ls_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1203, vlSelfRef.rv32_soc__DOT__ls_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr 
                 = vlSelfRef.rv32_soc__DOT__ls_addr;
         }
-        if (((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
-                              >> 2U)) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_oob))) {
+        if (vlcu_cov_any(((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
+                                           >> 2U)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_oob)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1277, 
                                    (0x00000400U <= 
                                     (vlSelfRef.rv32_soc__DOT__ls_addr 
@@ -1588,14 +1600,14 @@ struct Vrv32_cov__cuda final {
                                                                 != 
                                                                 (3U 
                                                                  & vlSelfRef.rv32_soc__DOT__ls_addr)))));
-        if ((0U != ((IData)(vlSelfRef.rv32_soc__DOT__st_strb) 
-                    ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.rv32_soc__DOT__st_strb) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb))))) {
             VL_COV_TOGGLE_CHG_ST_I(4, vlSelf->__Vcoverage + 1349, vlSelfRef.rv32_soc__DOT__st_strb, vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb);
             vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb 
                 = vlSelfRef.rv32_soc__DOT__st_strb;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1269, vlSelfRef.rv32_soc__DOT__ls_misaligned, vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned 
                 = vlSelfRef.rv32_soc__DOT__ls_misaligned;
@@ -1650,7 +1662,8 @@ struct Vrv32_cov__cuda final {
              & (~ (IData)(rv32_soc__DOT__exec_ls)))) {
             ++(vlSelf->__Vcoverage[1581]);
         }
-        if (((IData)(rv32_soc__DOT__exec_ls) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls))) {
+        if (vlcu_cov_any(((IData)(rv32_soc__DOT__exec_ls) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1570, rv32_soc__DOT__exec_ls, vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls);
             vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls 
                 = rv32_soc__DOT__exec_ls;
@@ -1749,27 +1762,32 @@ struct Vrv32_cov__cuda final {
         if ((0U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
             ++(vlSelf->__Vcoverage[1604]);
         }
-        if (((IData)(vlSelfRef.mem_valid) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.mem_valid) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 6, vlSelfRef.mem_valid, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid 
                 = vlSelfRef.mem_valid;
         }
-        if ((0U != (vlSelfRef.mem_wdata ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_wdata 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 74, vlSelfRef.mem_wdata, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata 
                 = vlSelfRef.mem_wdata;
         }
-        if ((0U != ((IData)(vlSelfRef.mem_wstrb) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.mem_wstrb) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb))))) {
             VL_COV_TOGGLE_CHG_ST_I(4, vlSelf->__Vcoverage + 138, vlSelfRef.mem_wstrb, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb 
                 = vlSelfRef.mem_wstrb;
         }
-        if ((0U != (vlSelfRef.mem_addr ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 10, vlSelfRef.mem_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr 
                 = vlSelfRef.mem_addr;
         }
-        if ((0U != (vlSelfRef.mem_rdata ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_rdata 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 146, vlSelfRef.mem_rdata, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata 
                 = vlSelfRef.mem_rdata;
@@ -1862,8 +1880,8 @@ struct Vrv32_cov__cuda final {
                 if ((1ULL & vlSelfRef.__VicoTriggered[0U])) {
                     {
                         // Inlined CFunc: _ico_sequent__TOP__0
-                        if (((IData)(vlSelfRef.clk) 
-                             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__clk))) {
+                        if (vlcu_cov_any(((IData)(vlSelfRef.clk) 
+                                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__clk)))) {
                             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 0, vlSelfRef.clk, vlSelfRef.rv32_soc__DOT____Vtogcov__clk);
                             vlSelfRef.rv32_soc__DOT____Vtogcov__clk 
                                 = vlSelfRef.clk;
@@ -1873,8 +1891,8 @@ struct Vrv32_cov__cuda final {
                 if ((2ULL & vlSelfRef.__VicoTriggered[0U])) {
                     {
                         // Inlined CFunc: _ico_sequent__TOP__1
-                        if (((IData)(vlSelfRef.resetn) 
-                             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__resetn))) {
+                        if (vlcu_cov_any(((IData)(vlSelfRef.resetn) 
+                                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__resetn)))) {
                             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 2, vlSelfRef.resetn, vlSelfRef.rv32_soc__DOT____Vtogcov__resetn);
                             vlSelfRef.rv32_soc__DOT____Vtogcov__resetn 
                                 = vlSelfRef.resetn;
@@ -1987,6 +2005,21 @@ struct Vrv32_cov__cuda final {
         __VdlyDim0__rv32_soc__DOT__regs__v5 = 0;
         CData/*0:0*/ __VdlySet__rv32_soc__DOT__regs__v5;
         __VdlySet__rv32_soc__DOT__regs__v5 = 0;
+        uint32_t vlCovHit26 = 0U;
+        uint32_t vlCovHit27 = 0U;
+        uint32_t vlCovHit29 = 0U;
+        uint32_t vlCovHit30 = 0U;
+        uint32_t vlCovHit32 = 0U;
+        uint32_t vlCovHit34 = 0U;
+        uint32_t vlCovHit36 = 0U;
+        uint32_t vlCovHit37 = 0U;
+        uint32_t vlCovHit39 = 0U;
+        uint32_t vlCovHit41 = 0U;
+        uint32_t vlCovHit42 = 0U;
+        uint32_t vlCovHit48 = 0U;
+        uint32_t vlCovHit49 = 0U;
+        uint32_t vlCovHit50 = 0U;
+        uint32_t vlCovHit51 = 0U;
         // Body
         __Vdly__rv32_soc__DOT__instret = vlSelfRef.rv32_soc__DOT__instret;
         __VdlySet__rv32_soc__DOT__mem__v0 = 0U;
@@ -2005,16 +2038,16 @@ struct Vrv32_cov__cuda final {
         if (vlSelfRef.resetn) {
             if ((0U == (IData)(vlSelfRef.rv32_soc__DOT__state))) {
                 if (vlSelfRef.rv32_soc__DOT__pc_bad) {
-                    ++(vlSelf->__Vcoverage[1609]);
+                    vlCovHit50 |= 512U;
                     __Vdly__rv32_soc__DOT__state = 3U;
                 } else {
-                    ++(vlSelf->__Vcoverage[1610]);
+                    vlCovHit50 |= 1024U;
                     __Vdly__rv32_soc__DOT__insn = vlSelfRef.rv32_soc__DOT__mem
                         [(0x000003ffU & (vlSelfRef.rv32_soc__DOT__pc 
                                          >> 2U))];
                     __Vdly__rv32_soc__DOT__state = 1U;
                 }
-                ++(vlSelf->__Vcoverage[1611]);
+                vlCovHit50 |= 2048U;
             } else if ((1U == (IData)(vlSelfRef.rv32_soc__DOT__state))) {
                 __Vdly__rv32_soc__DOT__state = 0U;
                 __Vdly__rv32_soc__DOT__pc = ((IData)(4U) 
@@ -2024,7 +2057,7 @@ struct Vrv32_cov__cuda final {
                 if ((0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
                     if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                                >> 7U)))) {
-                        ++(vlSelf->__Vcoverage[1612]);
+                        vlCovHit50 |= 4096U;
                         __VdlyVal__rv32_soc__DOT__regs__v0 
                             = vlSelfRef.rv32_soc__DOT__imm_u;
                         __VdlyDim0__rv32_soc__DOT__regs__v0 
@@ -2032,13 +2065,13 @@ struct Vrv32_cov__cuda final {
                                               >> 7U));
                         __VdlySet__rv32_soc__DOT__regs__v0 = 1U;
                     } else {
-                        ++(vlSelf->__Vcoverage[1613]);
+                        vlCovHit50 |= 8192U;
                     }
-                    ++(vlSelf->__Vcoverage[1653]);
+                    vlCovHit51 |= 2097152U;
                 } else if ((0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
                     if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                                >> 7U)))) {
-                        ++(vlSelf->__Vcoverage[1614]);
+                        vlCovHit50 |= 16384U;
                         __VdlyVal__rv32_soc__DOT__regs__v1 
                             = (vlSelfRef.rv32_soc__DOT__pc 
                                + vlSelfRef.rv32_soc__DOT__imm_u);
@@ -2047,13 +2080,13 @@ struct Vrv32_cov__cuda final {
                                               >> 7U));
                         __VdlySet__rv32_soc__DOT__regs__v1 = 1U;
                     } else {
-                        ++(vlSelf->__Vcoverage[1615]);
+                        vlCovHit50 |= 32768U;
                     }
-                    ++(vlSelf->__Vcoverage[1652]);
+                    vlCovHit51 |= 1048576U;
                 } else if ((0x6fU == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
                     if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                                >> 7U)))) {
-                        ++(vlSelf->__Vcoverage[1616]);
+                        vlCovHit50 |= 65536U;
                         __VdlyVal__rv32_soc__DOT__regs__v2 
                             = ((IData)(4U) + vlSelfRef.rv32_soc__DOT__pc);
                         __VdlyDim0__rv32_soc__DOT__regs__v2 
@@ -2061,15 +2094,15 @@ struct Vrv32_cov__cuda final {
                                               >> 7U));
                         __VdlySet__rv32_soc__DOT__regs__v2 = 1U;
                     } else {
-                        ++(vlSelf->__Vcoverage[1617]);
+                        vlCovHit50 |= 131072U;
                     }
                     __Vdly__rv32_soc__DOT__pc = (vlSelfRef.rv32_soc__DOT__pc 
                                                  + vlSelfRef.rv32_soc__DOT__imm_j);
-                    ++(vlSelf->__Vcoverage[1651]);
+                    vlCovHit51 |= 524288U;
                 } else if (vlSelfRef.rv32_soc__DOT__is_jalr) {
                     if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                                >> 7U)))) {
-                        ++(vlSelf->__Vcoverage[1618]);
+                        vlCovHit50 |= 262144U;
                         __VdlyVal__rv32_soc__DOT__regs__v3 
                             = ((IData)(4U) + vlSelfRef.rv32_soc__DOT__pc);
                         __VdlyDim0__rv32_soc__DOT__regs__v3 
@@ -2077,9 +2110,9 @@ struct Vrv32_cov__cuda final {
                                               >> 7U));
                         __VdlySet__rv32_soc__DOT__regs__v3 = 1U;
                     } else {
-                        ++(vlSelf->__Vcoverage[1619]);
+                        vlCovHit50 |= 524288U;
                     }
-                    ++(vlSelf->__Vcoverage[1650]);
+                    vlCovHit51 |= 262144U;
                     __Vdly__rv32_soc__DOT__pc = (0xfffffffeU 
                                                  & (vlSelfRef.rv32_soc__DOT__rs1_val 
                                                     + vlSelfRef.rv32_soc__DOT__imm_i));
@@ -2088,17 +2121,17 @@ struct Vrv32_cov__cuda final {
                         __Vdly__rv32_soc__DOT__pc = 
                             (vlSelfRef.rv32_soc__DOT__pc 
                              + vlSelfRef.rv32_soc__DOT__imm_b);
-                        ++(vlSelf->__Vcoverage[1620]);
+                        vlCovHit50 |= 1048576U;
                     } else {
-                        ++(vlSelf->__Vcoverage[1621]);
+                        vlCovHit50 |= 2097152U;
                     }
-                    ++(vlSelf->__Vcoverage[1649]);
+                    vlCovHit51 |= 131072U;
                 } else {
                     if (((IData)(vlSelfRef.rv32_soc__DOT__is_alui) 
                          | (IData)(vlSelfRef.rv32_soc__DOT__is_alur))) {
                         if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                                    >> 7U)))) {
-                            ++(vlSelf->__Vcoverage[1622]);
+                            vlCovHit50 |= 4194304U;
                             __VdlyVal__rv32_soc__DOT__regs__v4 
                                 = vlSelfRef.rv32_soc__DOT__alu_out;
                             __VdlyDim0__rv32_soc__DOT__regs__v4 
@@ -2106,9 +2139,9 @@ struct Vrv32_cov__cuda final {
                                                   >> 7U));
                             __VdlySet__rv32_soc__DOT__regs__v4 = 1U;
                         } else {
-                            ++(vlSelf->__Vcoverage[1623]);
+                            vlCovHit50 |= 8388608U;
                         }
-                        ++(vlSelf->__Vcoverage[1645]);
+                        vlCovHit51 |= 8192U;
                     } else if (vlSelfRef.rv32_soc__DOT__is_load) {
                         if (((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
                              | (0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
@@ -2117,31 +2150,31 @@ struct Vrv32_cov__cuda final {
                                 = vlSelfRef.rv32_soc__DOT__pc;
                             __Vdly__rv32_soc__DOT__instret 
                                 = vlSelfRef.rv32_soc__DOT__instret;
-                            ++(vlSelf->__Vcoverage[1624]);
+                            vlCovHit50 |= 16777216U;
                             __Vdly__rv32_soc__DOT__state = 3U;
                         } else {
                             __Vdly__rv32_soc__DOT__pc 
                                 = vlSelfRef.rv32_soc__DOT__pc;
                             __Vdly__rv32_soc__DOT__instret 
                                 = vlSelfRef.rv32_soc__DOT__instret;
-                            ++(vlSelf->__Vcoverage[1625]);
+                            vlCovHit50 |= 33554432U;
                             vlSelfRef.rv32_soc__DOT__ld_addr 
                                 = vlSelfRef.rv32_soc__DOT__ls_addr;
                             __Vdly__rv32_soc__DOT__state = 2U;
                         }
                         if ((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
                                              >> 2U))) {
-                            ++(vlSelf->__Vcoverage[1626]);
+                            vlCovHit50 |= 67108864U;
                         }
                         if (vlSelfRef.rv32_soc__DOT__ls_misaligned) {
-                            ++(vlSelf->__Vcoverage[1627]);
+                            vlCovHit50 |= 134217728U;
                         }
                         if (((~ (IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned)) 
                              & (0x00000400U > (vlSelfRef.rv32_soc__DOT__ls_addr 
                                                >> 2U)))) {
-                            ++(vlSelf->__Vcoverage[1628]);
+                            vlCovHit50 |= 268435456U;
                         }
-                        ++(vlSelf->__Vcoverage[1644]);
+                        vlCovHit51 |= 4096U;
                     } else if (vlSelfRef.rv32_soc__DOT__is_store) {
                         if (((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
                              | (0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
@@ -2150,11 +2183,11 @@ struct Vrv32_cov__cuda final {
                                 = vlSelfRef.rv32_soc__DOT__pc;
                             __Vdly__rv32_soc__DOT__instret 
                                 = vlSelfRef.rv32_soc__DOT__instret;
-                            ++(vlSelf->__Vcoverage[1637]);
+                            vlCovHit51 |= 32U;
                             __Vdly__rv32_soc__DOT__state = 3U;
                         } else {
                             if ((1U & (IData)(vlSelfRef.rv32_soc__DOT__st_strb))) {
-                                ++(vlSelf->__Vcoverage[1629]);
+                                vlCovHit50 |= 536870912U;
                                 __VdlyVal__rv32_soc__DOT__mem__v0 
                                     = (0x000000ffU 
                                        & vlSelfRef.rv32_soc__DOT__st_data);
@@ -2164,10 +2197,10 @@ struct Vrv32_cov__cuda final {
                                           >> 2U));
                                 __VdlySet__rv32_soc__DOT__mem__v0 = 1U;
                             } else {
-                                ++(vlSelf->__Vcoverage[1630]);
+                                vlCovHit50 |= 1073741824U;
                             }
                             if ((2U & (IData)(vlSelfRef.rv32_soc__DOT__st_strb))) {
-                                ++(vlSelf->__Vcoverage[1631]);
+                                vlCovHit50 |= 2147483648U;
                                 __VdlyVal__rv32_soc__DOT__mem__v1 
                                     = (0x000000ffU 
                                        & (vlSelfRef.rv32_soc__DOT__st_data 
@@ -2178,10 +2211,10 @@ struct Vrv32_cov__cuda final {
                                           >> 2U));
                                 __VdlySet__rv32_soc__DOT__mem__v1 = 1U;
                             } else {
-                                ++(vlSelf->__Vcoverage[1632]);
+                                vlCovHit51 |= 1U;
                             }
                             if ((4U & (IData)(vlSelfRef.rv32_soc__DOT__st_strb))) {
-                                ++(vlSelf->__Vcoverage[1633]);
+                                vlCovHit51 |= 2U;
                                 __VdlyVal__rv32_soc__DOT__mem__v2 
                                     = (0x000000ffU 
                                        & (vlSelfRef.rv32_soc__DOT__st_data 
@@ -2192,10 +2225,10 @@ struct Vrv32_cov__cuda final {
                                           >> 2U));
                                 __VdlySet__rv32_soc__DOT__mem__v2 = 1U;
                             } else {
-                                ++(vlSelf->__Vcoverage[1634]);
+                                vlCovHit51 |= 4U;
                             }
                             if ((8U & (IData)(vlSelfRef.rv32_soc__DOT__st_strb))) {
-                                ++(vlSelf->__Vcoverage[1635]);
+                                vlCovHit51 |= 8U;
                                 __VdlyVal__rv32_soc__DOT__mem__v3 
                                     = (vlSelfRef.rv32_soc__DOT__st_data 
                                        >> 0x18U);
@@ -2205,42 +2238,42 @@ struct Vrv32_cov__cuda final {
                                           >> 2U));
                                 __VdlySet__rv32_soc__DOT__mem__v3 = 1U;
                             } else {
-                                ++(vlSelf->__Vcoverage[1636]);
+                                vlCovHit51 |= 16U;
                             }
-                            ++(vlSelf->__Vcoverage[1638]);
+                            vlCovHit51 |= 64U;
                         }
                         if ((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
                                              >> 2U))) {
-                            ++(vlSelf->__Vcoverage[1639]);
+                            vlCovHit51 |= 128U;
                         }
                         if (vlSelfRef.rv32_soc__DOT__ls_misaligned) {
-                            ++(vlSelf->__Vcoverage[1640]);
+                            vlCovHit51 |= 256U;
                         }
                         if (((~ (IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned)) 
                              & (0x00000400U > (vlSelfRef.rv32_soc__DOT__ls_addr 
                                                >> 2U)))) {
-                            ++(vlSelf->__Vcoverage[1641]);
+                            vlCovHit51 |= 512U;
                         }
-                        ++(vlSelf->__Vcoverage[1642]);
+                        vlCovHit51 |= 1024U;
                     } else {
                         __Vdly__rv32_soc__DOT__pc = vlSelfRef.rv32_soc__DOT__pc;
                         __Vdly__rv32_soc__DOT__instret 
                             = vlSelfRef.rv32_soc__DOT__instret;
-                        ++(vlSelf->__Vcoverage[1643]);
+                        vlCovHit51 |= 2048U;
                         __Vdly__rv32_soc__DOT__state = 3U;
                     }
                     if (vlSelfRef.rv32_soc__DOT__is_alur) {
-                        ++(vlSelf->__Vcoverage[1646]);
+                        vlCovHit51 |= 16384U;
                     }
                     if (vlSelfRef.rv32_soc__DOT__is_alui) {
-                        ++(vlSelf->__Vcoverage[1647]);
+                        vlCovHit51 |= 32768U;
                     }
                     if ((1U & ((~ (IData)(vlSelfRef.rv32_soc__DOT__is_alui)) 
                                & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_alur))))) {
-                        ++(vlSelf->__Vcoverage[1648]);
+                        vlCovHit51 |= 65536U;
                     }
                 }
-                ++(vlSelf->__Vcoverage[1654]);
+                vlCovHit51 |= 4194304U;
             } else if ((2U == (IData)(vlSelfRef.rv32_soc__DOT__state))) {
                 __Vdly__rv32_soc__DOT__pc = ((IData)(4U) 
                                              + vlSelfRef.rv32_soc__DOT__pc);
@@ -2248,7 +2281,7 @@ struct Vrv32_cov__cuda final {
                                                   + vlSelfRef.rv32_soc__DOT__instret);
                 if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                            >> 7U)))) {
-                    ++(vlSelf->__Vcoverage[1655]);
+                    vlCovHit51 |= 8388608U;
                     __VdlyVal__rv32_soc__DOT__regs__v5 
                         = vlSelfRef.rv32_soc__DOT__ld_val;
                     __VdlyDim0__rv32_soc__DOT__regs__v5 
@@ -2256,28 +2289,28 @@ struct Vrv32_cov__cuda final {
                                           >> 7U));
                     __VdlySet__rv32_soc__DOT__regs__v5 = 1U;
                 } else {
-                    ++(vlSelf->__Vcoverage[1656]);
+                    vlCovHit51 |= 16777216U;
                 }
                 __Vdly__rv32_soc__DOT__state = 0U;
-                ++(vlSelf->__Vcoverage[1657]);
+                vlCovHit51 |= 33554432U;
             } else {
-                ++(vlSelf->__Vcoverage[1658]);
+                vlCovHit51 |= 67108864U;
                 __Vdly__rv32_soc__DOT__state = 3U;
             }
-            ++(vlSelf->__Vcoverage[1660]);
+            vlCovHit51 |= 268435456U;
         } else {
-            ++(vlSelf->__Vcoverage[1659]);
+            vlCovHit51 |= 134217728U;
             __Vdly__rv32_soc__DOT__pc = 0U;
             __Vdly__rv32_soc__DOT__state = 0U;
             __Vdly__rv32_soc__DOT__instret = 0U;
         }
         if ((1U & (~ (IData)(vlSelfRef.resetn)))) {
-            ++(vlSelf->__Vcoverage[1661]);
+            vlCovHit51 |= 536870912U;
         }
         if (vlSelfRef.resetn) {
-            ++(vlSelf->__Vcoverage[1662]);
+            vlCovHit51 |= 1073741824U;
         }
-        ++(vlSelf->__Vcoverage[1663]);
+        vlCovHit51 |= 2147483648U;
         vlSelfRef.rv32_soc__DOT__instret = __Vdly__rv32_soc__DOT__instret;
         if (__VdlySet__rv32_soc__DOT__mem__v0) {
             vlSelfRef.rv32_soc__DOT__mem[__VdlyDim0__rv32_soc__DOT__mem__v0] 
@@ -2333,23 +2366,23 @@ struct Vrv32_cov__cuda final {
                 = __VdlyVal__rv32_soc__DOT__regs__v5;
         }
         vlSelfRef.rv32_soc__DOT__insn = __Vdly__rv32_soc__DOT__insn;
-        if ((0U != (vlSelfRef.rv32_soc__DOT__instret 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__retired))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__instret 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__retired)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 210, vlSelfRef.rv32_soc__DOT__instret, vlSelfRef.rv32_soc__DOT____Vtogcov__retired);
             vlSelfRef.rv32_soc__DOT____Vtogcov__retired 
                 = vlSelfRef.rv32_soc__DOT__instret;
         }
         vlSelfRef.retired = vlSelfRef.rv32_soc__DOT__instret;
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ld_addr 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 402, vlSelfRef.rv32_soc__DOT__ld_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_addr 
                 = vlSelfRef.rv32_soc__DOT__ld_addr;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__mem[(0x000003ffU 
-                                                  & (vlSelfRef.rv32_soc__DOT__ld_addr 
-                                                     >> 2U))] 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_word))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__mem
+                                 [(0x000003ffU & (vlSelfRef.rv32_soc__DOT__ld_addr 
+                                                  >> 2U))] 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_word)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1363, vlSelfRef.rv32_soc__DOT__mem
                                    [(0x000003ffU & 
                                      (vlSelfRef.rv32_soc__DOT__ld_addr 
@@ -2367,17 +2400,18 @@ struct Vrv32_cov__cuda final {
                                                       << 3U)));
         if ((0x00000400U <= (vlSelfRef.rv32_soc__DOT__pc 
                              >> 2U))) {
-            ++(vlSelf->__Vcoverage[1567]);
+            vlCovHit48 |= 2147483648U;
         }
         if ((0U != (3U & vlSelfRef.rv32_soc__DOT__pc))) {
-            ++(vlSelf->__Vcoverage[1568]);
+            vlCovHit49 |= 1U;
         }
         if (((0U == (3U & vlSelfRef.rv32_soc__DOT__pc)) 
              & (0x00000400U > (vlSelfRef.rv32_soc__DOT__pc 
                                >> 2U)))) {
-            ++(vlSelf->__Vcoverage[1569]);
+            vlCovHit49 |= 2U;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__pc ^ vlSelfRef.rv32_soc__DOT____Vtogcov__pc))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__pc 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__pc)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 274, vlSelfRef.rv32_soc__DOT__pc, vlSelfRef.rv32_soc__DOT____Vtogcov__pc);
             vlSelfRef.rv32_soc__DOT____Vtogcov__pc 
                 = vlSelfRef.rv32_soc__DOT__pc;
@@ -2387,55 +2421,55 @@ struct Vrv32_cov__cuda final {
                                            | (0x00000400U 
                                               <= (vlSelfRef.rv32_soc__DOT__pc 
                                                   >> 2U)));
-        if ((0U != ((IData)(vlSelfRef.rv32_soc__DOT__state) 
-                    ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__state)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.rv32_soc__DOT__state) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__state))))) {
             VL_COV_TOGGLE_CHG_ST_I(2, vlSelf->__Vcoverage + 466, vlSelfRef.rv32_soc__DOT__state, vlSelfRef.rv32_soc__DOT____Vtogcov__state);
             vlSelfRef.rv32_soc__DOT____Vtogcov__state 
                 = vlSelfRef.rv32_soc__DOT__state;
         }
         vlSelfRef.trap = (3U == (IData)(vlSelfRef.rv32_soc__DOT__state));
         if ((IData)((0x00000067U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[850]);
+            vlCovHit26 |= 262144U;
         }
         if ((0U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[851]);
+            vlCovHit26 |= 524288U;
         }
         if ((0x67U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[852]);
+            vlCovHit26 |= 1048576U;
         }
         if ((((0x63U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
               & (2U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU)))) & 
              (3U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                            >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[855]);
+            vlCovHit26 |= 8388608U;
         }
         if ((3U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[856]);
+            vlCovHit26 |= 16777216U;
         }
         if ((2U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[857]);
+            vlCovHit26 |= 33554432U;
         }
         if ((0x63U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[858]);
+            vlCovHit26 |= 67108864U;
         }
         if ((IData)((0x00005003U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[861]);
+            vlCovHit26 |= 536870912U;
         }
         if ((IData)((0x00004003U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[862]);
+            vlCovHit26 |= 1073741824U;
         }
         if ((IData)((0x00002003U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[863]);
+            vlCovHit26 |= 2147483648U;
         }
         if ((IData)((0x00001003U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[864]);
+            vlCovHit27 |= 1U;
         }
         if ((IData)((3U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[865]);
+            vlCovHit27 |= 2U;
         }
         if ((((((0U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU))) & (1U 
@@ -2451,19 +2485,19 @@ struct Vrv32_cov__cuda final {
                                                   (7U 
                                                    & (vlSelfRef.rv32_soc__DOT__insn 
                                                       >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[866]);
+            vlCovHit27 |= 4U;
         }
         if ((3U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[867]);
+            vlCovHit27 |= 8U;
         }
         if ((IData)((0x00002023U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[870]);
+            vlCovHit27 |= 64U;
         }
         if ((IData)((0x00001023U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[871]);
+            vlCovHit27 |= 128U;
         }
         if ((IData)((0x00000023U == (0x0000707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[872]);
+            vlCovHit27 |= 256U;
         }
         if ((((0U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                             >> 0x0000000cU))) & (1U 
@@ -2473,88 +2507,90 @@ struct Vrv32_cov__cuda final {
                                                      >> 0x0000000cU)))) 
              & (2U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                              >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[873]);
+            vlCovHit27 |= 512U;
         }
         if ((0x23U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[874]);
+            vlCovHit27 |= 1024U;
         }
         if ((IData)((0x00000013U == (0xfe00007fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[878]);
+            vlCovHit27 |= 16384U;
         }
         if ((IData)(((0x00000013U == (0xfe00007fU & vlSelfRef.rv32_soc__DOT__insn)) 
                      & (5U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                      >> 0x0000000cU)))))) {
-            ++(vlSelf->__Vcoverage[879]);
+            vlCovHit27 |= 32768U;
         }
         if ((IData)(((0x40000013U == (0xfe00007fU & vlSelfRef.rv32_soc__DOT__insn)) 
                      & (1U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                      >> 0x0000000cU)))))) {
-            ++(vlSelf->__Vcoverage[880]);
+            vlCovHit27 |= 65536U;
         }
         if ((IData)(((0x00000013U == (0xfe00007fU & vlSelfRef.rv32_soc__DOT__insn)) 
                      & (1U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                      >> 0x0000000cU)))))) {
-            ++(vlSelf->__Vcoverage[881]);
+            vlCovHit27 |= 131072U;
         }
         if ((((0x13U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
               & (1U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU)))) & 
              (5U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                            >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[882]);
+            vlCovHit27 |= 262144U;
         }
         if ((IData)(((0x00005000U == (0x00007000U & vlSelfRef.rv32_soc__DOT__insn)) 
                      & ((0U != (vlSelfRef.rv32_soc__DOT__insn 
                                 >> 0x19U)) & (0x20U 
                                               != (vlSelfRef.rv32_soc__DOT__insn 
                                                   >> 0x19U)))))) {
-            ++(vlSelf->__Vcoverage[883]);
+            vlCovHit27 |= 524288U;
         }
         if ((IData)(((0x00001000U == (0x00007000U & vlSelfRef.rv32_soc__DOT__insn)) 
                      & (0U != (vlSelfRef.rv32_soc__DOT__insn 
                                >> 0x19U))))) {
-            ++(vlSelf->__Vcoverage[884]);
+            vlCovHit27 |= 1048576U;
         }
         if ((0x13U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[885]);
+            vlCovHit27 |= 2097152U;
         }
         if ((IData)((0x40005033U == (0xfe00707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[888]);
+            vlCovHit27 |= 16777216U;
         }
         if ((IData)((0x40000033U == (0xfe00707fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[889]);
+            vlCovHit27 |= 33554432U;
         }
         if ((IData)((0x00000033U == (0xfe00007fU & vlSelfRef.rv32_soc__DOT__insn)))) {
-            ++(vlSelf->__Vcoverage[890]);
+            vlCovHit27 |= 67108864U;
         }
         if ((((0U != (vlSelfRef.rv32_soc__DOT__insn 
                       >> 0x19U)) & (0U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                                  >> 0x0000000cU)))) 
              & (5U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                              >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[891]);
+            vlCovHit27 |= 134217728U;
         }
         if (((0U != (vlSelfRef.rv32_soc__DOT__insn 
                      >> 0x19U)) & (0x20U != (vlSelfRef.rv32_soc__DOT__insn 
                                              >> 0x19U)))) {
-            ++(vlSelf->__Vcoverage[892]);
+            vlCovHit27 |= 268435456U;
         }
         if ((0x33U != (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn))) {
-            ++(vlSelf->__Vcoverage[893]);
+            vlCovHit27 |= 536870912U;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__insn ^ vlSelfRef.rv32_soc__DOT____Vtogcov__insn))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__insn 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__insn)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 338, vlSelfRef.rv32_soc__DOT__insn, vlSelfRef.rv32_soc__DOT____Vtogcov__insn);
             vlSelfRef.rv32_soc__DOT____Vtogcov__insn 
                 = vlSelfRef.rv32_soc__DOT__insn;
         }
-        if ((0U != (0x0000007fU & (vlSelfRef.rv32_soc__DOT__insn 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__opcode))))) {
+        if (vlcu_cov_any((0U != (0x0000007fU & (vlSelfRef.rv32_soc__DOT__insn 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__opcode)))))) {
             VL_COV_TOGGLE_CHG_ST_I(7, vlSelf->__Vcoverage + 470, vlSelfRef.rv32_soc__DOT__insn, vlSelfRef.rv32_soc__DOT____Vtogcov__opcode);
             vlSelfRef.rv32_soc__DOT____Vtogcov__opcode 
                 = (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn);
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 7U) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rd))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 7U) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rd)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 484, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 7U), vlSelfRef.rv32_soc__DOT____Vtogcov__rd);
@@ -2562,8 +2598,9 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 7U));
         }
-        if ((0U != (7U & ((vlSelfRef.rv32_soc__DOT__insn 
-                           >> 0x0000000cU) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__funct3))))) {
+        if (vlcu_cov_any((0U != (7U & ((vlSelfRef.rv32_soc__DOT__insn 
+                                        >> 0x0000000cU) 
+                                       ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__funct3)))))) {
             VL_COV_TOGGLE_CHG_ST_I(3, vlSelf->__Vcoverage + 494, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000000cU), vlSelfRef.rv32_soc__DOT____Vtogcov__funct3);
@@ -2571,9 +2608,9 @@ struct Vrv32_cov__cuda final {
                 = (7U & (vlSelfRef.rv32_soc__DOT__insn 
                          >> 0x0000000cU));
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 0x0000000fU) 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs1))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 0x0000000fU) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs1)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 500, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000000fU), vlSelfRef.rv32_soc__DOT____Vtogcov__rs1);
@@ -2581,9 +2618,9 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 0x0000000fU));
         }
-        if ((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
-                                    >> 0x00000014U) 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs2))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & ((vlSelfRef.rv32_soc__DOT__insn 
+                                                 >> 0x00000014U) 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__rs2)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 510, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x00000014U), vlSelfRef.rv32_soc__DOT____Vtogcov__rs2);
@@ -2591,8 +2628,8 @@ struct Vrv32_cov__cuda final {
                 = (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 0x00000014U));
         }
-        if ((1U & ((vlSelfRef.rv32_soc__DOT__insn >> 0x0000001eU) 
-                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5)))) {
+        if (vlcu_cov_any((1U & ((vlSelfRef.rv32_soc__DOT__insn 
+                                 >> 0x0000001eU) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5))))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 520, 
                                    (vlSelfRef.rv32_soc__DOT__insn 
                                     >> 0x0000001eU), vlSelfRef.rv32_soc__DOT____Vtogcov__f7b5);
@@ -2600,15 +2637,16 @@ struct Vrv32_cov__cuda final {
                 = (1U & (vlSelfRef.rv32_soc__DOT__insn 
                          >> 0x0000001eU));
         }
-        if ((0U != ((((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
-                                  >> 0x0000001fU))) 
-                      << 0x0000000cU) | ((0x00000fe0U 
-                                          & (vlSelfRef.rv32_soc__DOT__insn 
-                                             >> 0x00000014U)) 
-                                         | (0x0000001fU 
-                                            & (vlSelfRef.rv32_soc__DOT__insn 
-                                               >> 7U)))) 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_s))) {
+        if (vlcu_cov_any((0U != ((((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
+                                               >> 0x0000001fU))) 
+                                   << 0x0000000cU) 
+                                  | ((0x00000fe0U & 
+                                      (vlSelfRef.rv32_soc__DOT__insn 
+                                       >> 0x00000014U)) 
+                                     | (0x0000001fU 
+                                        & (vlSelfRef.rv32_soc__DOT__insn 
+                                           >> 7U)))) 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_s)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 586, 
                                    (((- (IData)((vlSelfRef.rv32_soc__DOT__insn 
                                                  >> 0x0000001fU))) 
@@ -2627,31 +2665,31 @@ struct Vrv32_cov__cuda final {
                       | (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                         >> 7U))));
         }
-        if ((0U != ((0xfffff000U & vlSelfRef.rv32_soc__DOT__insn) 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u))) {
+        if (vlcu_cov_any((0U != ((0xfffff000U & vlSelfRef.rv32_soc__DOT__insn) 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 714, 
                                    (0xfffff000U & vlSelfRef.rv32_soc__DOT__insn), vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_u 
                 = (0xfffff000U & vlSelfRef.rv32_soc__DOT__insn);
         }
-        if (((0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui))) {
+        if (vlcu_cov_any(((0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 842, 
                                    (0x37U == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_lui 
                 = (0x37U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn));
         }
-        if (((0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc))) {
+        if (vlcu_cov_any(((0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 844, 
                                    (0x17U == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_auipc 
                 = (0x17U == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn));
         }
-        if (((0x6fU == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal))) {
+        if (vlcu_cov_any(((0x6fU == (0x0000007fU & vlSelfRef.rv32_soc__DOT__insn)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 846, 
                                    (0x6fU == (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)), vlSelfRef.rv32_soc__DOT____Vtogcov__is_jal);
@@ -2763,10 +2801,10 @@ struct Vrv32_cov__cuda final {
                                                             >> 0x0000000cU)))))));
         if ((0U == (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x00000014U)))) {
-            ++(vlSelf->__Vcoverage[1028]);
+            vlCovHit32 |= 16U;
             vlSelfRef.rv32_soc__DOT____VlemCond_1 = 0U;
         } else {
-            ++(vlSelf->__Vcoverage[1029]);
+            vlCovHit32 |= 32U;
             vlSelfRef.rv32_soc__DOT____VlemCond_1 = vlSelfRef.rv32_soc__DOT__regs
                 [(0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                  >> 0x00000014U))];
@@ -2774,18 +2812,18 @@ struct Vrv32_cov__cuda final {
         rv32_soc__DOT__rs2_val = vlSelfRef.rv32_soc__DOT____VlemCond_1;
         if ((0U == (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x00000014U)))) {
-            ++(vlSelf->__Vcoverage[1026]);
+            vlCovHit32 |= 4U;
         }
         if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x00000014U)))) {
-            ++(vlSelf->__Vcoverage[1027]);
+            vlCovHit32 |= 8U;
         }
         if ((0U == (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x0000000fU)))) {
-            ++(vlSelf->__Vcoverage[960]);
+            vlCovHit30 |= 1U;
             vlSelfRef.rv32_soc__DOT____VlemCond_0 = 0U;
         } else {
-            ++(vlSelf->__Vcoverage[961]);
+            vlCovHit30 |= 2U;
             vlSelfRef.rv32_soc__DOT____VlemCond_0 = vlSelfRef.rv32_soc__DOT__regs
                 [(0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                  >> 0x0000000fU))];
@@ -2793,11 +2831,11 @@ struct Vrv32_cov__cuda final {
         vlSelfRef.rv32_soc__DOT__rs1_val = vlSelfRef.rv32_soc__DOT____VlemCond_0;
         if ((0U == (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x0000000fU)))) {
-            ++(vlSelf->__Vcoverage[958]);
+            vlCovHit29 |= 1073741824U;
         }
         if ((0U != (0x0000001fU & (vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x0000000fU)))) {
-            ++(vlSelf->__Vcoverage[959]);
+            vlCovHit29 |= 2147483648U;
         }
         __VdfgRegularize_h6e95ff9d_0_0 = ((0U == (7U 
                                                   & (vlSelfRef.rv32_soc__DOT__insn 
@@ -2811,44 +2849,45 @@ struct Vrv32_cov__cuda final {
                                                 (7U 
                                                  & (vlSelfRef.rv32_soc__DOT__insn 
                                                     >> 0x0000000cU)))));
-        if ((0U != (rv32_soc__DOT__ld_shift ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__ld_shift 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1427, rv32_soc__DOT__ld_shift, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_shift 
                 = rv32_soc__DOT__ld_shift;
         }
         if ((0U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1557]);
+            vlCovHit48 |= 2097152U;
             vlSelfRef.rv32_soc__DOT____VlemCond_7 = 
                 (((- (IData)((1U & (rv32_soc__DOT__ld_shift 
                                     >> 7U)))) << 8U) 
                  | (0x000000ffU & rv32_soc__DOT__ld_shift));
         } else {
-            ++(vlSelf->__Vcoverage[1564]);
+            vlCovHit48 |= 268435456U;
             if ((1U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU)))) {
-                ++(vlSelf->__Vcoverage[1558]);
+                vlCovHit48 |= 4194304U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_7 
                     = (((- (IData)((1U & (rv32_soc__DOT__ld_shift 
                                           >> 0x0fU)))) 
                         << 0x00000010U) | (0x0000ffffU 
                                            & rv32_soc__DOT__ld_shift));
             } else {
-                ++(vlSelf->__Vcoverage[1563]);
+                vlCovHit48 |= 134217728U;
                 if ((4U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                   >> 0x0000000cU)))) {
-                    ++(vlSelf->__Vcoverage[1559]);
+                    vlCovHit48 |= 8388608U;
                     vlSelfRef.rv32_soc__DOT____VlemCond_7 
                         = (0x000000ffU & rv32_soc__DOT__ld_shift);
                 } else {
-                    ++(vlSelf->__Vcoverage[1562]);
+                    vlCovHit48 |= 67108864U;
                     if ((5U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                                       >> 0x0000000cU)))) {
-                        ++(vlSelf->__Vcoverage[1560]);
+                        vlCovHit48 |= 16777216U;
                         vlSelfRef.rv32_soc__DOT____VlemCond_7 
                             = (0x0000ffffU & rv32_soc__DOT__ld_shift);
                     } else {
-                        ++(vlSelf->__Vcoverage[1561]);
+                        vlCovHit48 |= 33554432U;
                         vlSelfRef.rv32_soc__DOT____VlemCond_7 
                             = vlSelfRef.rv32_soc__DOT__mem
                             [(0x000003ffU & (vlSelfRef.rv32_soc__DOT__ld_addr 
@@ -2860,84 +2899,84 @@ struct Vrv32_cov__cuda final {
         vlSelfRef.rv32_soc__DOT__ld_val = vlSelfRef.rv32_soc__DOT____VlemCond_7;
         if ((0U == (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1555]);
+            vlCovHit48 |= 524288U;
         }
         if ((0U != (7U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1556]);
+            vlCovHit48 |= 1048576U;
         }
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1582]);
+            vlCovHit49 |= 16384U;
         }
         if (vlSelfRef.rv32_soc__DOT__pc_bad) {
-            ++(vlSelf->__Vcoverage[1583]);
+            vlCovHit49 |= 32768U;
         }
         if ((0U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
-            ++(vlSelf->__Vcoverage[1584]);
+            vlCovHit49 |= 65536U;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__pc_bad) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__pc_bad) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1565, vlSelfRef.rv32_soc__DOT__pc_bad, vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad);
             vlSelfRef.rv32_soc__DOT____Vtogcov__pc_bad 
                 = vlSelfRef.rv32_soc__DOT__pc_bad;
         }
         vlSelfRef.mem_instr = ((~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)) 
                                & (0U == (IData)(vlSelfRef.rv32_soc__DOT__state)));
-        if (((IData)(vlSelfRef.trap) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__trap))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.trap) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__trap)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 4, vlSelfRef.trap, vlSelfRef.rv32_soc__DOT____Vtogcov__trap);
             vlSelfRef.rv32_soc__DOT____Vtogcov__trap 
                 = vlSelfRef.trap;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_b 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_b 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 650, vlSelfRef.rv32_soc__DOT__imm_b, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_b 
                 = vlSelfRef.rv32_soc__DOT__imm_b;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_j 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_j 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 778, vlSelfRef.rv32_soc__DOT__imm_j, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_j 
                 = vlSelfRef.rv32_soc__DOT__imm_j;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_jalr) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_jalr) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 848, vlSelfRef.rv32_soc__DOT__is_jalr, vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_jalr 
                 = vlSelfRef.rv32_soc__DOT__is_jalr;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_branch) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_branch) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 853, vlSelfRef.rv32_soc__DOT__is_branch, vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_branch 
                 = vlSelfRef.rv32_soc__DOT__is_branch;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_alui) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_alui) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 875, vlSelfRef.rv32_soc__DOT__is_alui, vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_alui 
                 = vlSelfRef.rv32_soc__DOT__is_alui;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__imm_i 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__imm_i 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 522, vlSelfRef.rv32_soc__DOT__imm_i, vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i);
             vlSelfRef.rv32_soc__DOT____Vtogcov__imm_i 
                 = vlSelfRef.rv32_soc__DOT__imm_i;
         }
         if (((IData)(vlSelfRef.rv32_soc__DOT__is_alur) 
              & (vlSelfRef.rv32_soc__DOT__insn >> 0x0000001eU))) {
-            ++(vlSelf->__Vcoverage[1110]);
+            vlCovHit34 |= 4194304U;
         }
         if ((1U & (~ (vlSelfRef.rv32_soc__DOT__insn 
                       >> 0x0000001eU)))) {
-            ++(vlSelf->__Vcoverage[1111]);
+            vlCovHit34 |= 8388608U;
         }
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_alur)))) {
-            ++(vlSelf->__Vcoverage[1112]);
+            vlCovHit34 |= 16777216U;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_alur) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_alur) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 886, vlSelfRef.rv32_soc__DOT__is_alur, vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_alur 
                 = vlSelfRef.rv32_soc__DOT__is_alur;
@@ -2945,14 +2984,15 @@ struct Vrv32_cov__cuda final {
         rv32_soc__DOT__alu_sub = ((vlSelfRef.rv32_soc__DOT__insn 
                                    >> 0x0000001eU) 
                                   & (IData)(vlSelfRef.rv32_soc__DOT__is_alur));
-        if ((0U != (rv32_soc__DOT__rs2_val ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__rs2_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 962, rv32_soc__DOT__rs2_val, vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__rs2_val 
                 = rv32_soc__DOT__rs2_val;
         }
         if ((0U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1345]);
+            vlCovHit42 |= 2U;
             vlSelfRef.rv32_soc__DOT____VlemCond_5 = 
                 ((rv32_soc__DOT__rs2_val << 0x00000018U) 
                  | ((0x00ff0000U & (rv32_soc__DOT__rs2_val 
@@ -2961,15 +3001,15 @@ struct Vrv32_cov__cuda final {
                                        << 8U)) | (0x000000ffU 
                                                   & rv32_soc__DOT__rs2_val))));
         } else {
-            ++(vlSelf->__Vcoverage[1348]);
+            vlCovHit42 |= 16U;
             if ((1U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU)))) {
-                ++(vlSelf->__Vcoverage[1346]);
+                vlCovHit42 |= 4U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_5 
                     = ((rv32_soc__DOT__rs2_val << 0x00000010U) 
                        | (0x0000ffffU & rv32_soc__DOT__rs2_val));
             } else {
-                ++(vlSelf->__Vcoverage[1347]);
+                vlCovHit42 |= 8U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_5 
                     = rv32_soc__DOT__rs2_val;
             }
@@ -2977,28 +3017,28 @@ struct Vrv32_cov__cuda final {
         vlSelfRef.rv32_soc__DOT__st_data = vlSelfRef.rv32_soc__DOT____VlemCond_5;
         if ((0U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1343]);
+            vlCovHit41 |= 2147483648U;
         }
         if ((0U != (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1344]);
+            vlCovHit42 |= 1U;
         }
         if (vlSelfRef.rv32_soc__DOT__is_alur) {
-            ++(vlSelf->__Vcoverage[1096]);
+            vlCovHit34 |= 256U;
             vlSelfRef.rv32_soc__DOT____VlemCond_2 = rv32_soc__DOT__rs2_val;
         } else {
-            ++(vlSelf->__Vcoverage[1097]);
+            vlCovHit34 |= 512U;
             vlSelfRef.rv32_soc__DOT____VlemCond_2 = vlSelfRef.rv32_soc__DOT__imm_i;
         }
         rv32_soc__DOT__alu_b = vlSelfRef.rv32_soc__DOT____VlemCond_2;
         if (vlSelfRef.rv32_soc__DOT__is_alur) {
-            ++(vlSelf->__Vcoverage[1094]);
+            vlCovHit34 |= 64U;
         }
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_alur)))) {
-            ++(vlSelf->__Vcoverage[1095]);
+            vlCovHit34 |= 128U;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__rs1_val 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__rs1_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 894, vlSelfRef.rv32_soc__DOT__rs1_val, vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__rs1_val 
                 = vlSelfRef.rv32_soc__DOT__rs1_val;
@@ -3009,36 +3049,36 @@ struct Vrv32_cov__cuda final {
                     vlSelfRef.rv32_soc__DOT__take_branch 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            >= rv32_soc__DOT__rs2_val);
-                    ++(vlSelf->__Vcoverage[1201]);
+                    vlCovHit37 |= 131072U;
                 } else {
                     vlSelfRef.rv32_soc__DOT__take_branch 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            < rv32_soc__DOT__rs2_val);
-                    ++(vlSelf->__Vcoverage[1200]);
+                    vlCovHit37 |= 65536U;
                 }
             } else if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
                 vlSelfRef.rv32_soc__DOT__take_branch 
                     = VL_GTES_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, rv32_soc__DOT__rs2_val);
-                ++(vlSelf->__Vcoverage[1199]);
+                vlCovHit37 |= 32768U;
             } else {
                 vlSelfRef.rv32_soc__DOT__take_branch 
                     = VL_LTS_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, rv32_soc__DOT__rs2_val);
-                ++(vlSelf->__Vcoverage[1198]);
+                vlCovHit37 |= 16384U;
             }
         } else if ((0x00002000U & vlSelfRef.rv32_soc__DOT__insn)) {
             vlSelfRef.rv32_soc__DOT__take_branch = 
                 (vlSelfRef.rv32_soc__DOT__rs1_val >= rv32_soc__DOT__rs2_val);
-            ++(vlSelf->__Vcoverage[1201]);
+            vlCovHit37 |= 131072U;
         } else if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
             vlSelfRef.rv32_soc__DOT__take_branch = 
                 (vlSelfRef.rv32_soc__DOT__rs1_val != rv32_soc__DOT__rs2_val);
-            ++(vlSelf->__Vcoverage[1197]);
+            vlCovHit37 |= 8192U;
         } else {
             vlSelfRef.rv32_soc__DOT__take_branch = 
                 (vlSelfRef.rv32_soc__DOT__rs1_val == rv32_soc__DOT__rs2_val);
-            ++(vlSelf->__Vcoverage[1196]);
+            vlCovHit37 |= 4096U;
         }
-        ++(vlSelf->__Vcoverage[1202]);
+        vlCovHit37 |= 262144U;
         vlSelfRef.rv32_soc__DOT__is_load = ((3U == 
                                              (0x0000007fU 
                                               & vlSelfRef.rv32_soc__DOT__insn)) 
@@ -3057,35 +3097,38 @@ struct Vrv32_cov__cuda final {
                                               == (0x0000007fU 
                                                   & vlSelfRef.rv32_soc__DOT__insn)) 
                                              & (IData)(__VdfgRegularize_h6e95ff9d_0_0));
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ld_val 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ld_val 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1491, vlSelfRef.rv32_soc__DOT__ld_val, vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ld_val 
                 = vlSelfRef.rv32_soc__DOT__ld_val;
         }
-        if (((IData)(vlSelfRef.mem_instr) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.mem_instr) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 8, vlSelfRef.mem_instr, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_instr 
                 = vlSelfRef.mem_instr;
         }
-        if (((IData)(rv32_soc__DOT__alu_sub) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub))) {
+        if (vlcu_cov_any(((IData)(rv32_soc__DOT__alu_sub) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1108, rv32_soc__DOT__alu_sub, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_sub 
                 = rv32_soc__DOT__alu_sub;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__st_data 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__st_data))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__st_data 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__st_data)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1279, vlSelfRef.rv32_soc__DOT__st_data, vlSelfRef.rv32_soc__DOT____Vtogcov__st_data);
             vlSelfRef.rv32_soc__DOT____Vtogcov__st_data 
                 = vlSelfRef.rv32_soc__DOT__st_data;
         }
-        if ((0U != (rv32_soc__DOT__alu_b ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b))) {
+        if (vlcu_cov_any((0U != (rv32_soc__DOT__alu_b 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1030, rv32_soc__DOT__alu_b, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_b 
                 = rv32_soc__DOT__alu_b;
         }
-        if ((0U != (0x0000001fU & (rv32_soc__DOT__alu_b 
-                                   ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__shamt))))) {
+        if (vlcu_cov_any((0U != (0x0000001fU & (rv32_soc__DOT__alu_b 
+                                                ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__shamt)))))) {
             VL_COV_TOGGLE_CHG_ST_I(5, vlSelf->__Vcoverage + 1098, rv32_soc__DOT__alu_b, vlSelfRef.rv32_soc__DOT____Vtogcov__shamt);
             vlSelfRef.rv32_soc__DOT____Vtogcov__shamt 
                 = (0x0000001fU & rv32_soc__DOT__alu_b);
@@ -3096,100 +3139,100 @@ struct Vrv32_cov__cuda final {
                     vlSelfRef.rv32_soc__DOT__alu_out 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            & rv32_soc__DOT__alu_b);
-                    ++(vlSelf->__Vcoverage[1192]);
+                    vlCovHit37 |= 256U;
                 } else {
                     vlSelfRef.rv32_soc__DOT__alu_out 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            | rv32_soc__DOT__alu_b);
-                    ++(vlSelf->__Vcoverage[1191]);
+                    vlCovHit37 |= 128U;
                 }
             } else if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
                 if ((0x40000000U & vlSelfRef.rv32_soc__DOT__insn)) {
-                    ++(vlSelf->__Vcoverage[1188]);
+                    vlCovHit37 |= 16U;
                     vlSelfRef.rv32_soc__DOT____VlemCond_4 
                         = VL_SHIFTRS_III(32,32,5, vlSelfRef.rv32_soc__DOT__rs1_val, 
                                          (0x0000001fU 
                                           & rv32_soc__DOT__alu_b));
                 } else {
-                    ++(vlSelf->__Vcoverage[1189]);
+                    vlCovHit37 |= 32U;
                     vlSelfRef.rv32_soc__DOT____VlemCond_4 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            >> (0x0000001fU & rv32_soc__DOT__alu_b));
                 }
                 vlSelfRef.rv32_soc__DOT__alu_out = vlSelfRef.rv32_soc__DOT____VlemCond_4;
-                ++(vlSelf->__Vcoverage[1190]);
+                vlCovHit37 |= 64U;
             } else {
                 vlSelfRef.rv32_soc__DOT__alu_out = 
                     (vlSelfRef.rv32_soc__DOT__rs1_val 
                      ^ rv32_soc__DOT__alu_b);
-                ++(vlSelf->__Vcoverage[1185]);
+                vlCovHit37 |= 2U;
             }
         } else if ((0x00002000U & vlSelfRef.rv32_soc__DOT__insn)) {
             if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
                 vlSelfRef.rv32_soc__DOT__alu_out = 
                     (vlSelfRef.rv32_soc__DOT__rs1_val 
                      < rv32_soc__DOT__alu_b);
-                ++(vlSelf->__Vcoverage[1184]);
+                vlCovHit37 |= 1U;
             } else {
                 vlSelfRef.rv32_soc__DOT__alu_out = 
                     VL_LTS_III(32, vlSelfRef.rv32_soc__DOT__rs1_val, rv32_soc__DOT__alu_b);
-                ++(vlSelf->__Vcoverage[1183]);
+                vlCovHit36 |= 2147483648U;
             }
         } else if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
             vlSelfRef.rv32_soc__DOT__alu_out = (vlSelfRef.rv32_soc__DOT__rs1_val 
                                                 << 
                                                 (0x0000001fU 
                                                  & rv32_soc__DOT__alu_b));
-            ++(vlSelf->__Vcoverage[1182]);
+            vlCovHit36 |= 1073741824U;
         } else {
             if (rv32_soc__DOT__alu_sub) {
-                ++(vlSelf->__Vcoverage[1179]);
+                vlCovHit36 |= 134217728U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_3 
                     = (vlSelfRef.rv32_soc__DOT__rs1_val 
                        - rv32_soc__DOT__alu_b);
             } else {
-                ++(vlSelf->__Vcoverage[1180]);
+                vlCovHit36 |= 268435456U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_3 
                     = (vlSelfRef.rv32_soc__DOT__rs1_val 
                        + rv32_soc__DOT__alu_b);
             }
             vlSelfRef.rv32_soc__DOT__alu_out = vlSelfRef.rv32_soc__DOT____VlemCond_3;
-            ++(vlSelf->__Vcoverage[1181]);
+            vlCovHit36 |= 536870912U;
         }
         if (rv32_soc__DOT__alu_sub) {
-            ++(vlSelf->__Vcoverage[1177]);
+            vlCovHit36 |= 33554432U;
         }
         if ((1U & (~ (IData)(rv32_soc__DOT__alu_sub)))) {
-            ++(vlSelf->__Vcoverage[1178]);
+            vlCovHit36 |= 67108864U;
         }
         if ((0x40000000U & vlSelfRef.rv32_soc__DOT__insn)) {
-            ++(vlSelf->__Vcoverage[1186]);
+            vlCovHit37 |= 4U;
         }
         if ((1U & (~ (vlSelfRef.rv32_soc__DOT__insn 
                       >> 0x0000001eU)))) {
-            ++(vlSelf->__Vcoverage[1187]);
+            vlCovHit37 |= 8U;
         }
-        ++(vlSelf->__Vcoverage[1193]);
-        if (((IData)(vlSelfRef.rv32_soc__DOT__take_branch) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch))) {
+        vlCovHit37 |= 512U;
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__take_branch) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1194, vlSelfRef.rv32_soc__DOT__take_branch, vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch);
             vlSelfRef.rv32_soc__DOT____Vtogcov__take_branch 
                 = vlSelfRef.rv32_soc__DOT__take_branch;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_load) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_load))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_load) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_load)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 859, vlSelfRef.rv32_soc__DOT__is_load, vlSelfRef.rv32_soc__DOT____Vtogcov__is_load);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_load 
                 = vlSelfRef.rv32_soc__DOT__is_load;
         }
         if (vlSelfRef.rv32_soc__DOT__is_store) {
-            ++(vlSelf->__Vcoverage[1267]);
+            vlCovHit39 |= 524288U;
         }
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_store)))) {
-            ++(vlSelf->__Vcoverage[1268]);
+            vlCovHit39 |= 1048576U;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__is_store) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_store))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__is_store) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__is_store)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 868, vlSelfRef.rv32_soc__DOT__is_store, vlSelfRef.rv32_soc__DOT____Vtogcov__is_store);
             vlSelfRef.rv32_soc__DOT____Vtogcov__is_store 
                 = vlSelfRef.rv32_soc__DOT__is_store;
@@ -3210,34 +3253,34 @@ struct Vrv32_cov__cuda final {
                                                          : 
                                                         (vlSelfRef.rv32_soc__DOT__insn 
                                                          >> 0x00000014U))))));
-        if ((0U != (vlSelfRef.rv32_soc__DOT__alu_out 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__alu_out 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1113, vlSelfRef.rv32_soc__DOT__alu_out, vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out);
             vlSelfRef.rv32_soc__DOT____Vtogcov__alu_out 
                 = vlSelfRef.rv32_soc__DOT__alu_out;
         }
         if ((IData)(((0x00002000U == (0x00003000U & vlSelfRef.rv32_soc__DOT__insn)) 
                      & (0U != (3U & vlSelfRef.rv32_soc__DOT__ls_addr))))) {
-            ++(vlSelf->__Vcoverage[1271]);
+            vlCovHit39 |= 8388608U;
         }
         if ((IData)(((0x00001000U == (0x00003000U & vlSelfRef.rv32_soc__DOT__insn)) 
                      & vlSelfRef.rv32_soc__DOT__ls_addr))) {
-            ++(vlSelf->__Vcoverage[1272]);
+            vlCovHit39 |= 16777216U;
         }
         if ((IData)((0U == (3U & vlSelfRef.rv32_soc__DOT__ls_addr)))) {
-            ++(vlSelf->__Vcoverage[1273]);
+            vlCovHit39 |= 33554432U;
         }
         if (((~ vlSelfRef.rv32_soc__DOT__ls_addr) & 
              (2U != (3U & (vlSelfRef.rv32_soc__DOT__insn 
                            >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[1274]);
+            vlCovHit39 |= 67108864U;
         }
         if (((1U != (3U & (vlSelfRef.rv32_soc__DOT__insn 
                            >> 0x0000000cU))) & (0U 
                                                 == 
                                                 (3U 
                                                  & vlSelfRef.rv32_soc__DOT__ls_addr)))) {
-            ++(vlSelf->__Vcoverage[1275]);
+            vlCovHit39 |= 134217728U;
         }
         if (((1U != (3U & (vlSelfRef.rv32_soc__DOT__insn 
                            >> 0x0000000cU))) & (2U 
@@ -3245,16 +3288,17 @@ struct Vrv32_cov__cuda final {
                                                 (3U 
                                                  & (vlSelfRef.rv32_soc__DOT__insn 
                                                     >> 0x0000000cU))))) {
-            ++(vlSelf->__Vcoverage[1276]);
+            vlCovHit39 |= 268435456U;
         }
-        if ((0U != (vlSelfRef.rv32_soc__DOT__ls_addr 
-                    ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.rv32_soc__DOT__ls_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 1203, vlSelfRef.rv32_soc__DOT__ls_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ls_addr 
                 = vlSelfRef.rv32_soc__DOT__ls_addr;
         }
-        if (((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
-                              >> 2U)) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_oob))) {
+        if (vlcu_cov_any(((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
+                                           >> 2U)) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_oob)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1277, 
                                    (0x00000400U <= 
                                     (vlSelfRef.rv32_soc__DOT__ls_addr 
@@ -3265,31 +3309,31 @@ struct Vrv32_cov__cuda final {
         }
         if ((0U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1359]);
+            vlCovHit42 |= 32768U;
             vlSelfRef.rv32_soc__DOT____VlemCond_6 = 
                 (0x0000000fU & ((IData)(1U) << (3U 
                                                 & vlSelfRef.rv32_soc__DOT__ls_addr)));
         } else {
-            ++(vlSelf->__Vcoverage[1362]);
+            vlCovHit42 |= 262144U;
             if ((1U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                               >> 0x0000000cU)))) {
-                ++(vlSelf->__Vcoverage[1360]);
+                vlCovHit42 |= 65536U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_6 
                     = (0x0000000fU & ((IData)(3U) << 
                                       (3U & vlSelfRef.rv32_soc__DOT__ls_addr)));
             } else {
-                ++(vlSelf->__Vcoverage[1361]);
+                vlCovHit42 |= 131072U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_6 = 0x0fU;
             }
         }
         vlSelfRef.rv32_soc__DOT__st_strb = vlSelfRef.rv32_soc__DOT____VlemCond_6;
         if ((0U == (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1357]);
+            vlCovHit42 |= 8192U;
         }
         if ((0U != (3U & (vlSelfRef.rv32_soc__DOT__insn 
                           >> 0x0000000cU)))) {
-            ++(vlSelf->__Vcoverage[1358]);
+            vlCovHit42 |= 16384U;
         }
         vlSelfRef.rv32_soc__DOT__ls_misaligned = ((IData)(
                                                           ((0x00001000U 
@@ -3306,14 +3350,14 @@ struct Vrv32_cov__cuda final {
                                                                 != 
                                                                 (3U 
                                                                  & vlSelfRef.rv32_soc__DOT__ls_addr)))));
-        if ((0U != ((IData)(vlSelfRef.rv32_soc__DOT__st_strb) 
-                    ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.rv32_soc__DOT__st_strb) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb))))) {
             VL_COV_TOGGLE_CHG_ST_I(4, vlSelf->__Vcoverage + 1349, vlSelfRef.rv32_soc__DOT__st_strb, vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb);
             vlSelfRef.rv32_soc__DOT____Vtogcov__st_strb 
                 = vlSelfRef.rv32_soc__DOT__st_strb;
         }
-        if (((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
-             ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1269, vlSelfRef.rv32_soc__DOT__ls_misaligned, vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned);
             vlSelfRef.rv32_soc__DOT____Vtogcov__ls_misaligned 
                 = vlSelfRef.rv32_soc__DOT__ls_misaligned;
@@ -3323,28 +3367,28 @@ struct Vrv32_cov__cuda final {
               & (~ (IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned))) 
              & (0x00000400U > (vlSelfRef.rv32_soc__DOT__ls_addr 
                                >> 2U)))) {
-            ++(vlSelf->__Vcoverage[1572]);
+            vlCovHit49 |= 16U;
         }
         if (((((1U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
                & (IData)(vlSelfRef.rv32_soc__DOT__is_load)) 
               & (~ (IData)(vlSelfRef.rv32_soc__DOT__ls_misaligned))) 
              & (0x00000400U > (vlSelfRef.rv32_soc__DOT__ls_addr 
                                >> 2U)))) {
-            ++(vlSelf->__Vcoverage[1573]);
+            vlCovHit49 |= 32U;
         }
         if ((0x00000400U <= (vlSelfRef.rv32_soc__DOT__ls_addr 
                              >> 2U))) {
-            ++(vlSelf->__Vcoverage[1574]);
+            vlCovHit49 |= 64U;
         }
         if (vlSelfRef.rv32_soc__DOT__ls_misaligned) {
-            ++(vlSelf->__Vcoverage[1575]);
+            vlCovHit49 |= 128U;
         }
         if ((1U & ((~ (IData)(vlSelfRef.rv32_soc__DOT__is_load)) 
                    & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_store))))) {
-            ++(vlSelf->__Vcoverage[1576]);
+            vlCovHit49 |= 256U;
         }
         if ((1U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
-            ++(vlSelf->__Vcoverage[1577]);
+            vlCovHit49 |= 512U;
         }
         rv32_soc__DOT__exec_ls = ((1U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
                                   & ((~ ((0x00000400U 
@@ -3354,21 +3398,22 @@ struct Vrv32_cov__cuda final {
                                      & ((IData)(vlSelfRef.rv32_soc__DOT__is_load) 
                                         | (IData)(vlSelfRef.rv32_soc__DOT__is_store))));
         if (rv32_soc__DOT__exec_ls) {
-            ++(vlSelf->__Vcoverage[1578]);
+            vlCovHit49 |= 1024U;
         }
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1579]);
+            vlCovHit49 |= 2048U;
         }
         if (((IData)(vlSelfRef.rv32_soc__DOT__pc_bad) 
              & (~ (IData)(rv32_soc__DOT__exec_ls)))) {
-            ++(vlSelf->__Vcoverage[1580]);
+            vlCovHit49 |= 4096U;
         }
         if (((0U != (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(rv32_soc__DOT__exec_ls)))) {
-            ++(vlSelf->__Vcoverage[1581]);
+            vlCovHit49 |= 8192U;
         }
-        if (((IData)(rv32_soc__DOT__exec_ls) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls))) {
+        if (vlcu_cov_any(((IData)(rv32_soc__DOT__exec_ls) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 1570, rv32_soc__DOT__exec_ls, vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls);
             vlSelfRef.rv32_soc__DOT____Vtogcov__exec_ls 
                 = rv32_soc__DOT__exec_ls;
@@ -3376,122 +3421,142 @@ struct Vrv32_cov__cuda final {
         vlSelfRef.mem_valid = ((IData)(vlSelfRef.mem_instr) 
                                | (IData)(rv32_soc__DOT__exec_ls));
         if (((IData)(rv32_soc__DOT__exec_ls) & (IData)(vlSelfRef.rv32_soc__DOT__is_store))) {
-            ++(vlSelf->__Vcoverage[1595]);
+            vlCovHit49 |= 134217728U;
             vlSelfRef.rv32_soc__DOT____VlemCond_9 = vlSelfRef.rv32_soc__DOT__st_data;
         } else {
-            ++(vlSelf->__Vcoverage[1596]);
+            vlCovHit49 |= 268435456U;
             vlSelfRef.rv32_soc__DOT____VlemCond_9 = 0U;
         }
         vlSelfRef.mem_wdata = vlSelfRef.rv32_soc__DOT____VlemCond_9;
         if (((IData)(rv32_soc__DOT__exec_ls) & (IData)(vlSelfRef.rv32_soc__DOT__is_store))) {
-            ++(vlSelf->__Vcoverage[1592]);
+            vlCovHit49 |= 16777216U;
         }
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_store)))) {
-            ++(vlSelf->__Vcoverage[1593]);
+            vlCovHit49 |= 33554432U;
         }
         if ((1U & (~ (IData)(rv32_soc__DOT__exec_ls)))) {
-            ++(vlSelf->__Vcoverage[1594]);
+            vlCovHit49 |= 67108864U;
         }
         if (((IData)(rv32_soc__DOT__exec_ls) & (IData)(vlSelfRef.rv32_soc__DOT__is_store))) {
-            ++(vlSelf->__Vcoverage[1600]);
+            vlCovHit50 |= 1U;
             vlSelfRef.rv32_soc__DOT____VlemCond_10 
                 = vlSelfRef.rv32_soc__DOT__st_strb;
         } else {
-            ++(vlSelf->__Vcoverage[1601]);
+            vlCovHit50 |= 2U;
             vlSelfRef.rv32_soc__DOT____VlemCond_10 = 0U;
         }
         vlSelfRef.mem_wstrb = vlSelfRef.rv32_soc__DOT____VlemCond_10;
         if (((IData)(rv32_soc__DOT__exec_ls) & (IData)(vlSelfRef.rv32_soc__DOT__is_store))) {
-            ++(vlSelf->__Vcoverage[1597]);
+            vlCovHit49 |= 536870912U;
         }
         if ((1U & (~ (IData)(vlSelfRef.rv32_soc__DOT__is_store)))) {
-            ++(vlSelf->__Vcoverage[1598]);
+            vlCovHit49 |= 1073741824U;
         }
         if ((1U & (~ (IData)(rv32_soc__DOT__exec_ls)))) {
-            ++(vlSelf->__Vcoverage[1599]);
+            vlCovHit49 |= 2147483648U;
         }
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1588]);
+            vlCovHit49 |= 1048576U;
             vlSelfRef.rv32_soc__DOT____VlemCond_8 = vlSelfRef.rv32_soc__DOT__pc;
         } else {
-            ++(vlSelf->__Vcoverage[1591]);
+            vlCovHit49 |= 8388608U;
             if (rv32_soc__DOT__exec_ls) {
-                ++(vlSelf->__Vcoverage[1589]);
+                vlCovHit49 |= 2097152U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_8 
                     = (0xfffffffcU & vlSelfRef.rv32_soc__DOT__ls_addr);
             } else {
-                ++(vlSelf->__Vcoverage[1590]);
+                vlCovHit49 |= 4194304U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_8 = 0U;
             }
         }
         vlSelfRef.mem_addr = vlSelfRef.rv32_soc__DOT____VlemCond_8;
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1585]);
+            vlCovHit49 |= 131072U;
         }
         if (vlSelfRef.rv32_soc__DOT__pc_bad) {
-            ++(vlSelf->__Vcoverage[1586]);
+            vlCovHit49 |= 262144U;
         }
         if ((0U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
-            ++(vlSelf->__Vcoverage[1587]);
+            vlCovHit49 |= 524288U;
         }
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1605]);
+            vlCovHit50 |= 32U;
             vlSelfRef.rv32_soc__DOT____VlemCond_11 
                 = vlSelfRef.rv32_soc__DOT__mem[(0x000003ffU 
                                                 & (vlSelfRef.rv32_soc__DOT__pc 
                                                    >> 2U))];
         } else {
-            ++(vlSelf->__Vcoverage[1608]);
+            vlCovHit50 |= 256U;
             if (((IData)(rv32_soc__DOT__exec_ls) & (IData)(vlSelfRef.rv32_soc__DOT__is_load))) {
-                ++(vlSelf->__Vcoverage[1606]);
+                vlCovHit50 |= 64U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_11 
                     = vlSelfRef.rv32_soc__DOT__mem[
                     (0x000003ffU & (vlSelfRef.rv32_soc__DOT__ls_addr 
                                     >> 2U))];
             } else {
-                ++(vlSelf->__Vcoverage[1607]);
+                vlCovHit50 |= 128U;
                 vlSelfRef.rv32_soc__DOT____VlemCond_11 = 0U;
             }
         }
         vlSelfRef.mem_rdata = vlSelfRef.rv32_soc__DOT____VlemCond_11;
         if (((0U == (IData)(vlSelfRef.rv32_soc__DOT__state)) 
              & (~ (IData)(vlSelfRef.rv32_soc__DOT__pc_bad)))) {
-            ++(vlSelf->__Vcoverage[1602]);
+            vlCovHit50 |= 4U;
         }
         if (vlSelfRef.rv32_soc__DOT__pc_bad) {
-            ++(vlSelf->__Vcoverage[1603]);
+            vlCovHit50 |= 8U;
         }
         if ((0U != (IData)(vlSelfRef.rv32_soc__DOT__state))) {
-            ++(vlSelf->__Vcoverage[1604]);
+            vlCovHit50 |= 16U;
         }
-        if (((IData)(vlSelfRef.mem_valid) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid))) {
+        if (vlcu_cov_any(((IData)(vlSelfRef.mem_valid) 
+                          ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid)))) {
             VL_COV_TOGGLE_CHG_ST_I(1, vlSelf->__Vcoverage + 6, vlSelfRef.mem_valid, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_valid 
                 = vlSelfRef.mem_valid;
         }
-        if ((0U != (vlSelfRef.mem_wdata ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_wdata 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 74, vlSelfRef.mem_wdata, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wdata 
                 = vlSelfRef.mem_wdata;
         }
-        if ((0U != ((IData)(vlSelfRef.mem_wstrb) ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb)))) {
+        if (vlcu_cov_any((0U != ((IData)(vlSelfRef.mem_wstrb) 
+                                 ^ (IData)(vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb))))) {
             VL_COV_TOGGLE_CHG_ST_I(4, vlSelf->__Vcoverage + 138, vlSelfRef.mem_wstrb, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_wstrb 
                 = vlSelfRef.mem_wstrb;
         }
-        if ((0U != (vlSelfRef.mem_addr ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_addr 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 10, vlSelfRef.mem_addr, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_addr 
                 = vlSelfRef.mem_addr;
         }
-        if ((0U != (vlSelfRef.mem_rdata ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata))) {
+        if (vlcu_cov_any((0U != (vlSelfRef.mem_rdata 
+                                 ^ vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata)))) {
             VL_COV_TOGGLE_CHG_ST_I(32, vlSelf->__Vcoverage + 146, vlSelfRef.mem_rdata, vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata);
             vlSelfRef.rv32_soc__DOT____Vtogcov__mem_rdata 
                 = vlSelfRef.mem_rdata;
         }
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 832, vlCovHit26);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 864, vlCovHit27);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 928, vlCovHit29);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 960, vlCovHit30);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1024, vlCovHit32);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1088, vlCovHit34);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1152, vlCovHit36);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1184, vlCovHit37);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1248, vlCovHit39);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1312, vlCovHit41);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1344, vlCovHit42);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1536, vlCovHit48);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1568, vlCovHit49);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1600, vlCovHit50);
+        vlcu_cov_flush_hits(vlSelf->__Vcoverage + 1632, vlCovHit51);
     }
 
     VLCU_D static void Vrv32_cov___024root___trigger_orInto__act_vec_vec(VlUnpacked<QData/*63:0*/, 1> &out, const VlUnpacked<QData/*63:0*/, 1> &in) {
@@ -3730,7 +3795,7 @@ struct Vrv32_cov__cuda final {
     }
 
     VLCU_D static void ctor_var_reset(Root* vlSelf, VlcuContext& vlCtx) {
-        for (uint32_t b = 0; b < 1664U; ++b) vlSelf->__Vcoverage[b] = 0U;
+        vlSelf->__Vcoverage.zero(1664U);
         Vrv32_cov___024root___ctor_var_reset(vlSelf, vlCtx);
     }
     VLCU_D static void eval_static(Root* vlSelf, VlcuContext& vlCtx) { Vrv32_cov___024root___eval_static(vlSelf, vlCtx); }
@@ -3862,7 +3927,7 @@ const VlcuDesignInfo& Vrv32_cov__cuda::info() {
         {"__VicoTriggered", "__VicoTriggered", VLCU_MEMBER_STATE, 8, 0, 2, 64, 63, 0, T::OFF___VicoTriggered},
         {"__VactTriggered", "__VactTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VactTriggered},
         {"__VnbaTriggered", "__VnbaTriggered", VLCU_MEMBER_STATE, 8, 0, 1, 64, 63, 0, T::OFF___VnbaTriggered},
-        {"__Vcoverage", nullptr, VLCU_MEMBER_COVERAGE, 4, 0, 1664, 32, 31, 0, T::OFF___Vcoverage},
+        {"__Vcoverage", nullptr, VLCU_MEMBER_COVERAGE, 4, 0, 104, 32, 31, 0, T::OFF___Vcoverage},
     };
     static VlcuCoverTable t;
     if (t.points.empty()) {
@@ -4118,6 +4183,8 @@ const VlcuDesignInfo& Vrv32_cov__cuda::info() {
         t.other(1663, "../verilator_b200/csrc/designs/rv32i/rv32_soc.v", 132, 3, ".rv32_soc", "v_line/rv32_soc", "block", "132");
         t.finish();
     }
+    // one uint64 counter per bin for every warp of 32 instances, [warp][bin] in the block of __Vcoverage
+    static const VlcuCoverScope coverScopes[] = {{0, 1664}};
     static const char* const messages[] = {nullptr};
     static const char* const plusargs[] = {nullptr};
     static const VlcuTraceDecl traceDecls[] = {
@@ -4130,7 +4197,7 @@ const VlcuDesignInfo& Vrv32_cov__cuda::info() {
         t.points.data(), static_cast<uint32_t>(t.points.size()), 1664, T::OFF___Vcoverage,
         messages, 0, plusargs, 0,
         nullptr, 0, 0, nullptr, 0,
-        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12, 0, nullptr, 0};
+        saveOrder, 113, 0, 0xef0e7ce4001d23d2ULL, nullptr, 12, 12, 0, coverScopes, sizeof(coverScopes) / sizeof(coverScopes[0])};
     return s;
 }
 

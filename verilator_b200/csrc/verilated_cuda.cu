@@ -348,12 +348,25 @@ __global__ void __launch_bounds__(256) k_cov_reduce_tiled(const uint8_t* __restr
                                                           uint64_t tileBytes,
                                                           const uint32_t* __restrict__ binOffset, uint32_t bins,
                                                           uint64_t* __restrict__ out) {
-    const uint64_t bin = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (bin >= bins) return;
-    const uint8_t* const basep = state + binOffset[bin];
+    // 32 adjacent bins per CTA (one 256-byte run of a scope's counters per tile), the tiles dealt
+    // to the CTA's 8 warps
+    __shared__ uint64_t s_part[8][32];
+    const uint32_t lane = threadIdx.x & 31U, slice = threadIdx.x >> 5;
+    const uint64_t bin = blockIdx.x * 32ULL + lane;
     uint64_t acc = 0;
-    for (uint64_t t = 0; t < tiles; ++t) acc += *reinterpret_cast<const unsigned long long*>(basep + t * tileBytes);
-    out[bin] = acc;
+    if (bin < bins) {
+        const uint8_t* const basep = state + binOffset[bin];
+#pragma unroll 4
+        for (uint64_t t = slice; t < tiles; t += 8) {
+            acc += *reinterpret_cast<const unsigned long long*>(basep + t * tileBytes);
+        }
+    }
+    s_part[slice][lane] = acc;
+    __syncthreads();
+    if (slice == 0 && bin < bins) {
+        for (uint32_t k = 1; k < 8; ++k) acc += s_part[k][lane];
+        out[bin] = acc;
+    }
 }
 
 unsigned blocksFor(uint64_t work, unsigned threads) {
@@ -1629,9 +1642,22 @@ int vlcu_coverage_reduce(vlcu_model_t* h, uint64_t* out) {
             CUDA_TRY(cudaMalloc(&h->dCovBinOffset, sizeof(uint32_t) * bins));
             CUDA_TRY(cudaMemcpy(h->dCovBinOffset, offsets.data(), sizeof(uint32_t) * bins, cudaMemcpyHostToDevice));
         }
-        k_cov_reduce_tiled<<<blocksFor(bins, 256), 256, 0, h->stream>>>(
+        k_cov_reduce_tiled<<<blocksFor(bins, 32), 256, 0, h->stream>>>(
             h->dState, h->npad / h->infop->tile, static_cast<uint64_t>(h->infop->stateBytes) * h->infop->tile,
             h->dCovBinOffset, bins, h->dCovSums);
+    } else if (h->infop->nCoverScopes) {
+        // register form, counters per warp of 32 instances: [warp][bin] uint64 in the block of __Vcoverage
+        if (!h->dCovBinOffset) {
+            std::vector<uint32_t> offsets(bins);
+            for (uint32_t b = 0; b < bins; ++b) offsets[b] = b * 8U;
+            CUDA_TRY(cudaMalloc(&h->dCovBinOffset, sizeof(uint32_t) * bins));
+            CUDA_TRY(cudaMemcpy(h->dCovBinOffset, offsets.data(), sizeof(uint32_t) * bins, cudaMemcpyHostToDevice));
+        }
+        // (N_Bins of VlcuWarpCovArray: the block's words per instance x 16)
+        const uint64_t warpBins = static_cast<uint64_t>((bins + 15U) / 16U) * 16U;
+        k_cov_reduce_tiled<<<blocksFor(bins, 32), 256, 0, h->stream>>>(
+            h->dState + static_cast<uint64_t>(h->infop->coverageSoaOffset) * h->npad, (h->n + 31U) / 32U,
+            warpBins * 8U, h->dCovBinOffset, bins, h->dCovSums);
     } else {
         const uint32_t* const covp = reinterpret_cast<const uint32_t*>(
             h->dState + static_cast<uint64_t>(h->infop->coverageSoaOffset) * h->npad);
