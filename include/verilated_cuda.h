@@ -899,6 +899,22 @@ struct VlcuLanes<VlWide<N_Words>> final {
 // aggregates: a cover point adds, once, the number of lanes that reached it; a toggle point
 // counts, per bit position that changed in any lane, the lanes where it rose and where it fell
 // (two ballots).  The counters are the exact sums of the per-instance counters the C++ model keeps.
+// The lanes that work on one cover point together.  Where the bump functions are inlined, every
+// point has its own code and the lanes executing it together are at that point.  As real functions
+// (VLCU_COV_NOINLINE) they have ONE copy of code: lanes that come from different points -- the two
+// sides of an if, say -- may be scheduled through it together, and __activemask() alone would mix
+// their counters (a narrow signal's lanes would add past its counters).  There the lanes are
+// grouped by the counter they were given: one MATCH.ANY.
+#ifdef __CUDA_ARCH__
+VLCU_D unsigned vlcu_cov_lanes(const unsigned long long* p) {
+#if (defined(VLCU_COV_NOINLINE) || defined(VLCU_COV_GROUP_LANES)) && !defined(VLCU_COV_NO_MATCH)  // (NO_MATCH: tests/optest shows the hazard)
+    return __match_any_sync(__activemask(), reinterpret_cast<unsigned long long>(p));
+#else
+    (void)p;
+    return __activemask();
+#endif
+}
+#endif
 // One lane of `lanes` (the lanes executing this together; the lowest) adds `value` to a counter;
 // a zero is not sent.  (elect.sync with a run-time mask costs a WARPSYNC/ENDCOLLECTIVE region of
 // its own; two integer operations find the lowest lane as well.)
@@ -915,7 +931,7 @@ struct VlcuTileCovRef final {
         // the lanes reaching this point together bump the same counter (a line or branch point of
         // the code they all run, for the scope they all are in): one add of their number.  (Any
         // split of the lanes into groups gives the same sum.)
-        const unsigned lanes = __activemask();
+        const unsigned lanes = vlcu_cov_lanes(m_p);
         vlcu_red_elected(lanes, m_p, __popc(lanes));
 #else
         ++*m_p;
@@ -932,8 +948,15 @@ struct VlcuTileCov final {
     unsigned long long c[N_Bins];
     VLCU_HD VlcuTileCovRef operator[](size_t bin) { return VlcuTileCovRef{&c[bin]}; }
     VLCU_HD VlcuTileCovPtr operator+(size_t bin) { return VlcuTileCovPtr{&c[bin]}; }
+    // (reset: the lanes that are there -- the last tile of a shard may be partial -- share the work)
     VLCU_HD void zero(uint32_t lane) {
+#ifdef __CUDA_ARCH__
+        const unsigned lanes = __activemask();
+        const uint32_t rank = __popc(lanes & ((1U << lane) - 1U)), step = __popc(lanes);
+        for (size_t b = rank; b < N_Bins; b += step) c[b] = 0ULL;
+#else
         for (size_t b = lane; b < N_Bins; b += VLCU_TILE) c[b] = 0ULL;
+#endif
     }
 };
 // The wide form (verilated_cov.h:94-105 with its quirk, see VL_COV_TOGGLE_CHG_ST_W above: changed
@@ -942,7 +965,7 @@ struct VlcuTileCov final {
 // (left per lane, the lanes walk different bits and the warp runs 1.4 lanes wide).
 VLCU_COV_FN void vlcu_cov_bump_wide(VlcuTileCovPtr covp, int width, WDataInP newData, WDataInP oldData) {
 #ifdef __CUDA_ARCH__
-    const unsigned lanes = __activemask();
+    const unsigned lanes = vlcu_cov_lanes(covp.m_p);
     const bool leader = (threadIdx.x & 31U) == static_cast<unsigned>(__ffs(lanes) - 1);
     for (int w = 0; w < VL_WORDS_I(width); ++w) {
         const EData chg = newData[w] ^ oldData[w];
@@ -1014,7 +1037,7 @@ VLCU_HD bool vlcu_cov_any(bool changed) {
 // bits changed; the per-bit ballot loop is kept for a divergent warp.
 VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
-    const unsigned lanes = __activemask();
+    const unsigned lanes = vlcu_cov_lanes(covp.m_p);
     const uint32_t rise = chg & newData;
     if (lanes == 0xffffffffU) {
         const uint32_t lane = threadIdx.x & 31U;
@@ -1056,7 +1079,7 @@ VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t 
 // here when the function ends: transposed across the warp, lane b holds who passed bin b.
 VLCU_COV_FN void vlcu_cov_flush_hits(VlcuTileCovPtr covp, uint32_t hits) {
 #ifdef __CUDA_ARCH__
-    const unsigned lanes = __activemask();
+    const unsigned lanes = vlcu_cov_lanes(covp.m_p);
     if (lanes == 0xffffffffU) {
         if (!__any_sync(0xffffffffU, hits != 0U)) return;
         const uint32_t passed = __popc(vlcu_warp_transpose32(hits));
@@ -1077,7 +1100,7 @@ VLCU_COV_FN void vlcu_cov_flush_hits(VlcuTileCovPtr covp, uint32_t hits) {
 // One-bit signals (most toggle points of a design): two ballots, no loop
 VLCU_COV_FN void vlcu_cov_bump_bit(VlcuTileCovPtr covp, uint32_t chg, uint32_t newData) {
 #ifdef __CUDA_ARCH__
-    const unsigned lanes = __activemask();
+    const unsigned lanes = vlcu_cov_lanes(covp.m_p);
     const unsigned changed = __ballot_sync(lanes, chg & 1U);
     const unsigned rose = __ballot_sync(lanes, chg & newData & 1U);
     const unsigned up = __popc(rose);

@@ -968,15 +968,13 @@ class EmitCudaModel final : public EmitCFunc {
                 if (!(assignp && assignp->lhsp() == refp && topStmts.count(assignp))) c.load = true;
             }
         });
-        // A member that is only ever assigned, whole and on every path, gains nothing from a local:
-        // it would hold a register from the assignment to the scatter.  It is stored where it is
-        // assigned (nothing reads it back in this function, and nobody else runs meanwhile).
-        for (auto it = m_cached.begin(); it != m_cached.end();) {
-            it = it->second.load ? std::next(it) : m_cached.erase(it);
-        }
-        // ... and a thread has 255 registers: the members a big leaf meets first (up to
-        // --cuda-gather-words 32-bit words of them) are gathered, the rest are read and written in
-        // place, or the gather would only move the traffic to the stack
+        // (A member that is only ever assigned keeps its local too: stored where it is assigned, the
+        // store would sit between the loads of everything gathered later -- nvcc cannot know they
+        // do not alias -- and the leaf would wait for its loads one group at a time: 73 -> 49 M
+        // instance-cycles/s on the VeeR-class design.)
+        // --cuda-gather-words N (0 = no limit, the default) gathers only the members a big leaf
+        // meets first, up to N 32-bit words; the rest are read and written in place
+        if (!V3EmitCuda::gatherWords()) return;
         size_t words = 0;
         std::vector<std::pair<unsigned long, string>> order;
         for (const auto& it : m_cached) order.emplace_back(std::stoul(it.second.local.substr(4)), it.first);
@@ -1215,11 +1213,22 @@ class EmitCudaModel final : public EmitCFunc {
             iterateAndNextConstNull(nodep->varsp());
         }
         VL_RESTORER_CLEAR(m_covHitWindows);
+        VL_RESTORER_CLEAR(m_covHitRepeated);
         if (m_coverBins && (m_stream || !V3EmitCuda::coverPerInstance()) && nodep->isLoose() && !nodep->isStatic()
-            && !nodep->slow() && nodep->rtnTypeVoid() == "void") {
+            && !nodep->slow() && nodep->rtnTypeVoid() == "void" && !getenv("VLCU_DEBUG_NO_HITS")) {
+            // (a bin with several points in one function -- V3Unroll's copies of a loop body -- can
+            // be passed several times in one run: those keep the direct bump)
+            std::map<int, int> points;
             nodep->foreach([&](AstCoverInc* incp) {
-                if (covHitEligible(incp)) m_covHitWindows.insert(coverageBinNum(incp->declp()) / 32);
+                if (covHitEligible(incp)) ++points[coverageBinNum(incp->declp())];
             });
+            for (const auto& it : points) {
+                if (it.second > 1) {
+                    m_covHitRepeated.insert(it.first);
+                } else {
+                    m_covHitWindows.insert(it.first / 32);
+                }
+            }
             for (const int window : m_covHitWindows) puts("uint32_t vlCovHit" + cvtToStr(window) + " = 0U;\n");
         }
         if (nodep->stmtsp()) {
@@ -1369,12 +1378,14 @@ class EmitCudaModel final : public EmitCFunc {
     // over the warp, one add per bin).  Not inside loops (a point could be passed twice) and not
     // in functions that return a value.
     std::set<int> m_covHitWindows;  // of the function being printed; empty: points bump directly
+    std::set<int> m_covHitRepeated;  // bins with several points in the function (an unrolled loop)
     int m_loopDepth = 0;
     bool covHitEligible(AstCoverInc* nodep) {
         return VN_IS(nodep->declp(), CoverOtherDecl) && coverageUsesLocalCounter(nodep->declp());
     }
     void visit(AstCoverInc* nodep) override {
-        if (!m_covHitWindows.empty() && !m_loopDepth && covHitEligible(nodep)) {
+        if (!m_covHitWindows.empty() && !m_loopDepth && covHitEligible(nodep)
+            && !m_covHitRepeated.count(coverageBinNum(nodep->declp()))) {
             const int bin = coverageBinNum(nodep->declp());
             putns(nodep, "vlCovHit" + cvtToStr(bin / 32) + " |= " + cvtToStr(1U << (bin % 32)) + "U;\n");
             return;
@@ -1391,7 +1402,7 @@ class EmitCudaModel final : public EmitCFunc {
         // counters: the lanes of the warp take it together (vlcu_cov_any) so that the bump can work
         // across the warp; a lane that saw no change bumps nothing and rewrites the same shadow value.
         const AstCoverInc* const incp = VN_CAST(nodep->thensp(), CoverInc);
-        if ((m_stream || !V3EmitCuda::coverPerInstance()) && incp && incp->toggleExprp() && !nodep->elsesp() && VN_IS(incp->nextp(), Assign)
+        if ((m_stream || !V3EmitCuda::coverPerInstance()) && !getenv("VLCU_DEBUG_NO_HOIST") && incp && incp->toggleExprp() && !nodep->elsesp() && VN_IS(incp->nextp(), Assign)
             && !incp->nextp()->nextp()) {
             putns(nodep, "if (vlcu_cov_any(");
             iterateAndNextConstNull(nodep->condp());
@@ -1725,7 +1736,11 @@ class EmitCudaModel final : public EmitCFunc {
             puts("// 4 CTAs of 64 threads per SM = 255 registers per thread: the leaves' gathers then keep\n");
             puts("// 100+ loads in flight per warp without spilling (measured: profiles/README.md)\n");
             puts("#ifndef VLCU_MIN_BLOCKS\n#define VLCU_MIN_BLOCKS 4\n#endif\n");
-            if (m_coverBins) puts("#define VLCU_COV_NOINLINE 1  // " + cvtToStr(m_coverBins) + " counters: the toggle loop is a real function\n");
+            if (m_coverBins) {
+                puts("// " + cvtToStr(m_coverBins) + " counters: the bump functions are real functions (-DVLCU_COV_INLINE: inlined,\n");
+                puts("// a much longer compilation), and lanes that meet in them are grouped by the counter they hold\n");
+                puts("#ifndef VLCU_COV_INLINE\n#define VLCU_COV_NOINLINE 1\n#endif\n#define VLCU_COV_GROUP_LANES 1\n");
+            }
         } else {
             // Occupancy target of the kernels (verilated_cuda_launch.h: __launch_bounds__(64,
             // VLCU_MIN_BLOCKS), default 7 = 146 registers per thread).  A design that keeps almost
@@ -2143,7 +2158,7 @@ bool V3EmitCuda::s_coverPerInstance = false;
 int V3EmitCuda::s_chunkNodes = 0;
 bool V3EmitCuda::s_shareCode = true;
 bool V3EmitCuda::s_interleaveAll = false;
-int V3EmitCuda::s_gatherWords = 160;
+int V3EmitCuda::s_gatherWords = 0;
 
 void V3EmitCuda::emitCuda() {
     UINFO(2, __FUNCTION__ << ":");

@@ -15,6 +15,8 @@ run make_tracing_c --workload make_tracing_c --steps 10
 run wide_bus --workload wide_bus --steps 10
 run wide_bus_65536 --workload wide_bus --instances 65536 --steps 10 --no-cpu-baseline
 run cov_campaign --workload cov_campaign --steps 5
+run cov_campaign_65536 --workload cov_campaign --instances 65536 --steps 5 --no-cpu-baseline
+run rv32i_16384 --workload rv32i --instances 16384 --steps 10 --no-cpu-baseline
 run cov_campaign_mtc --workload cov_campaign_mtc --steps 5
 run cov_campaign_veer --workload cov_campaign_veer --steps 5
 run veer_class --workload veer_class --steps 10

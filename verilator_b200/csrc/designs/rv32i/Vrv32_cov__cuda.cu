@@ -3049,7 +3049,7 @@ struct Vrv32_cov__cuda final {
                     vlSelfRef.rv32_soc__DOT__take_branch 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
                            >= rv32_soc__DOT__rs2_val);
-                    vlCovHit37 |= 131072U;
+                    ++(vlSelf->__Vcoverage[1201]);
                 } else {
                     vlSelfRef.rv32_soc__DOT__take_branch 
                         = (vlSelfRef.rv32_soc__DOT__rs1_val 
@@ -3068,7 +3068,7 @@ struct Vrv32_cov__cuda final {
         } else if ((0x00002000U & vlSelfRef.rv32_soc__DOT__insn)) {
             vlSelfRef.rv32_soc__DOT__take_branch = 
                 (vlSelfRef.rv32_soc__DOT__rs1_val >= rv32_soc__DOT__rs2_val);
-            vlCovHit37 |= 131072U;
+            ++(vlSelf->__Vcoverage[1201]);
         } else if ((0x00001000U & vlSelfRef.rv32_soc__DOT__insn)) {
             vlSelfRef.rv32_soc__DOT__take_branch = 
                 (vlSelfRef.rv32_soc__DOT__rs1_val != rv32_soc__DOT__rs2_val);
