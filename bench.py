@@ -82,7 +82,8 @@ WORKLOADS = {
     "cov_campaign": dict(
         design="rv32i_cov", tb="rv32_rand", instances=16384, cycles=1024, tb_flags=1,
         tb_arg=(16, 0, 0, 0), rand_reset=2, inputs=(), coverage=True, fresh_program_per_step=True,
-        note="rv32_soc.v built --coverage (1,664 line/toggle/branch/expression counters per instance), "
+        note="rv32_soc.v built --coverage (1,664 line/toggle/branch/expression counters, one uint64 set "
+             "per warp of 32 instances), "
              "fuzz campaign: fresh random program + reset every step; e2e adds the on-device coverage "
              "reduction + ncclAllReduce + coverage.dat write per step"),
     # BASELINE.json configs[3] class: wide-bus, VlWide-heavy path, 4,096 instances (OpenTitan is
@@ -387,7 +388,7 @@ def coverage_leg(abi, dist, rank, world, local):
     return {"design": "rv32i_cov", "instances_per_gpu": n, "bins": int(len(sums)), "payload_bytes": 8 * int(len(sums)),
             "reduce_plus_allreduce_plus_d2h_ms": ms, "total_count": int(sums.sum()),
             "equals_sum_over_all_instances_of_reference_model": bool((sums == want.cov).all()),
-            "collective": "k_cov_reduce (u32 per instance -> u64 per bin) + ncclAllReduce(ncclUint64, ncclSum)"}
+            "collective": "k_cov_reduce_tiled (u64 per warp of 32 instances -> u64 per bin) + ncclAllReduce(ncclUint64, ncclSum)"}
 
 
 def roofline(workload, m, n, cycles, mean_ms, clocks, hbm_peak, peak_src):
@@ -425,9 +426,12 @@ def roofline(workload, m, n, cycles, mean_ms, clocks, hbm_peak, peak_src):
     if prof.get("bound") == "hbm":
         return dict(common, bound="hbm", achieved=dram / secs / 1e9, peak=hbm_peak, unit="GB/s",
                     frac=dram / secs / 1e9 / hbm_peak,
+                    algorithmic_frac=n * cycles * b_alg / secs / 1e9 / hbm_peak,
                     note="state streams from HBM every eval (tiled model image): achieved = DRAM bytes per launch "
                          "(ncu dram__bytes_read+write of the capture in `profile`, scaled by instance-cycles) / the "
-                         "launch duration measured in this run")
+                         "launch duration measured in this run -- the conservative figure: the L2 serves part of "
+                         "the algorithmic bytes (SURVEY 8d's B_alg x throughput = hbm_equivalent, as a fraction of "
+                         "the peak = algorithmic_frac)")
     return dict(common, bound="issue", achieved=warp_inst / secs / 1e9, peak=issue_peak / 1e9, unit="Gwarp-inst/s",
                 frac=warp_inst / secs / issue_peak,
                 note="state stays on chip across the fused cycles, DRAM traffic is a few percent of peak: the binding "

@@ -203,7 +203,13 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
     if (!kObserve) {
         // (tryRun sends runs of 2^32 evals or more to the kObserve form, whose trip count is 64 bits)
         const uint32_t nEvals = static_cast<uint32_t>(r.nEvals);
+        // A tiled design calls real functions; lanes that leave one of them apart (a cover point
+        // only some of them passed) stay apart in the caller -- nothing there waits for them --
+        // and would run the rest of the LAUNCH a few lanes at a time.  All lanes of the warp that
+        // are there run the same number of evals: they meet again at the top of each.
+        const unsigned live = __activemask();
         for (uint32_t e = 0; e < nEvals; ++e) {
+            if (T_Design::kTiled) __syncwarp(live);
 #ifdef VLCU_EVAL_SYNC
             // (experiment) keep the CTA's warps at the same place in the code: a tiled design's
             // eval is tens of thousands of straight-line instructions, fetched once per warp
