@@ -915,6 +915,17 @@ VLCU_D unsigned vlcu_cov_lanes(const unsigned long long* p) {
 #endif
 }
 #endif
+// The lanes that entered a bump function leave it together -- where it is a real function; inlined,
+// the code that follows reconverges them anyway, and the barrier would only cost
+#ifdef __CUDA_ARCH__
+VLCU_D void vlcu_cov_leave(unsigned lanes) {
+#ifdef VLCU_COV_NOINLINE
+    __syncwarp(lanes);
+#else
+    (void)lanes;
+#endif
+}
+#endif
 // One lane of `lanes` (the lanes executing this together; the lowest) adds `value` to a counter;
 // a zero is not sent.  (As the LAST statement of a real function this is a divergent return: the
 // other lanes leave while the elected one still adds, and nothing in the caller waits for it --
@@ -989,7 +1000,7 @@ VLCU_COV_FN void vlcu_cov_bump_wide(VlcuTileCovPtr covp, int width, WDataInP new
             }
         }
     }
-    __syncwarp(lanes);  // leave together, see vlcu_red_elected
+    vlcu_cov_leave(lanes);  // leave together, see vlcu_red_elected
 #else
     for (int w = 0; w < VL_WORDS_I(width); ++w) {
         EData chg = newData[w] ^ oldData[w];
@@ -1055,7 +1066,7 @@ VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t 
         const uint32_t addHi = (lane & 1U) ? (hi >> 8) : (hi & 0xffU);
         if (addLo) atomicAdd(covp.m_p + lane, static_cast<unsigned long long>(addLo));
         if (addHi) atomicAdd(covp.m_p + 32U + lane, static_cast<unsigned long long>(addHi));
-        __syncwarp();
+        vlcu_cov_leave(0xffffffffU);
         return;
     }
     const bool leader = (threadIdx.x & 31U) == static_cast<unsigned>(__ffs(lanes) - 1);
@@ -1072,7 +1083,7 @@ VLCU_COV_FN void vlcu_cov_bump_bits(VlcuTileCovPtr covp, uint32_t chg, uint32_t 
             if (down) atomicAdd(covp.m_p + 2U * i, static_cast<unsigned long long>(down));
         }
     }
-    __syncwarp(lanes);
+    vlcu_cov_leave(lanes);
 #else
     for (; chg; chg &= chg - 1U) {
         const int i = vlcu_ctz32(chg);
@@ -1090,7 +1101,7 @@ VLCU_COV_FN void vlcu_cov_flush_hits(VlcuTileCovPtr covp, uint32_t hits) {
         if (!__any_sync(0xffffffffU, hits != 0U)) return;
         const uint32_t passed = __popc(vlcu_warp_transpose32(hits));
         if (passed) atomicAdd(covp.m_p + (threadIdx.x & 31U), static_cast<unsigned long long>(passed));
-        __syncwarp();
+        vlcu_cov_leave(0xffffffffU);
         return;
     }
     uint32_t any = __reduce_or_sync(lanes, hits);
@@ -1100,7 +1111,7 @@ VLCU_COV_FN void vlcu_cov_flush_hits(VlcuTileCovPtr covp, uint32_t hits) {
         any ^= 1U << i;
         vlcu_red_elected(lanes, covp.m_p + i, __popc(__ballot_sync(lanes, (hits >> i) & 1U)));
     }
-    __syncwarp(lanes);
+    vlcu_cov_leave(lanes);
 #else
     for (; hits; hits &= hits - 1U) ++covp[vlcu_ctz32(hits)];
 #endif
@@ -1114,7 +1125,7 @@ VLCU_COV_FN void vlcu_cov_bump_bit(VlcuTileCovPtr covp, uint32_t chg, uint32_t n
     const unsigned up = __popc(rose);
     vlcu_red_elected(lanes, covp.m_p + 1, up);
     vlcu_red_elected(lanes, covp.m_p, __popc(changed) - up);
-    __syncwarp(lanes);
+    vlcu_cov_leave(lanes);
 #else
     if (chg & 1U) ++covp[newData & 1U];
 #endif

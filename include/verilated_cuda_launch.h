@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(VLCU_BLOCK, VLCU_MIN_BLOCKS) vlcu_k_run(VlcuMo
         // only some of them passed) stay apart in the caller -- nothing there waits for them --
         // and would run the rest of the LAUNCH a few lanes at a time.  All lanes of the warp that
         // are there run the same number of evals: they meet again at the top of each.
-        const unsigned live = __activemask();
+        const unsigned live = T_Design::kTiled ? __activemask() : 0U;  // (nothing at all for a register-form design)
         for (uint32_t e = 0; e < nEvals; ++e) {
             if (T_Design::kTiled) __syncwarp(live);
 #ifdef VLCU_EVAL_SYNC
