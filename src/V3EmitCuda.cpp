@@ -1215,7 +1215,7 @@ class EmitCudaModel final : public EmitCFunc {
         VL_RESTORER_CLEAR(m_covHitWindows);
         VL_RESTORER_CLEAR(m_covHitRepeated);
         if (m_coverBins && (m_stream || !V3EmitCuda::coverPerInstance()) && nodep->isLoose() && !nodep->isStatic()
-            && !nodep->slow() && nodep->rtnTypeVoid() == "void" && !getenv("VLCU_DEBUG_NO_HITS")) {
+            && !nodep->slow() && nodep->rtnTypeVoid() == "void") {
             // (a bin with several points in one function -- V3Unroll's copies of a loop body -- can
             // be passed several times in one run: those keep the direct bump)
             std::map<int, int> points;
@@ -1402,7 +1402,7 @@ class EmitCudaModel final : public EmitCFunc {
         // counters: the lanes of the warp take it together (vlcu_cov_any) so that the bump can work
         // across the warp; a lane that saw no change bumps nothing and rewrites the same shadow value.
         const AstCoverInc* const incp = VN_CAST(nodep->thensp(), CoverInc);
-        if ((m_stream || !V3EmitCuda::coverPerInstance()) && !getenv("VLCU_DEBUG_NO_HOIST") && incp && incp->toggleExprp() && !nodep->elsesp() && VN_IS(incp->nextp(), Assign)
+        if ((m_stream || !V3EmitCuda::coverPerInstance()) && incp && incp->toggleExprp() && !nodep->elsesp() && VN_IS(incp->nextp(), Assign)
             && !incp->nextp()->nextp()) {
             putns(nodep, "if (vlcu_cov_any(");
             iterateAndNextConstNull(nodep->condp());
